@@ -1,0 +1,563 @@
+"""CPU ORACLE (test infrastructure, NOT a product path).
+
+A NumPy restatement of the riptide_cpp entry points on riptable's groupby / reduce / lexsort hot
+path.  riptide_cpp itself (pinned >=1.19.0,<2 by /root/reference pyproject.toml:15) is a third-party
+C++ package whose source is not vendored under /root/reference and which is not installable here,
+so this file restates its *published behaviour* as riptable's own call sites, docstring golden
+vectors and tests pin it.  Parity is PINNED against those vectors in tests/test_oracle_golden.py
+(docstring examples rt_numpy.py:2013-2062, 1926-1933, 2126-2156, 1533-1540 and the KATs of
+tests/test_groupby.py, test_pgroupby.py, test_lexsort.py, test_grouping.py).  Behaviour no reference
+test fixes is marked UNPINNED here and in DESIGN.md.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  riptable_b200 never does.
+
+Every function cites the reference file:line whose contract it follows.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# ----------------------------------------------------------------------------------------------
+# constants (riptable/rt_enum.py:486-532, 88-143)
+GB_SUM, GB_MEAN, GB_MIN, GB_MAX, GB_VAR, GB_STD = 0, 1, 2, 3, 4, 5
+GB_NANSUM, GB_NANMEAN, GB_NANMIN, GB_NANMAX, GB_NANVAR, GB_NANSTD = 50, 51, 52, 53, 54, 55
+GB_FIRST, GB_NTH, GB_LAST = 100, 101, 102
+GB_CUMSUM = 300
+
+
+def invalid_for(dt):
+    """riptable/rt_enum.py:116-143 (non-win32 table)."""
+    dt = np.dtype(dt)
+    if dt.kind == "f":
+        return dt.type(np.nan)
+    if dt.kind == "b":
+        return np.bool_(False)
+    if dt.kind == "i":
+        return dt.type(np.iinfo(dt).min)
+    if dt.kind == "u":
+        return dt.type(np.iinfo(dt).max)
+    if dt.kind == "S":
+        return b""
+    if dt.kind == "U":
+        return ""
+    raise TypeError(dt)
+
+
+def _index_dtype(n):
+    # LexSort32 vs LexSort64 split at 2e9 rows (rt_numpy.py:2199-2202, 2669-2671)
+    return np.int64 if n > 2e9 else np.int32
+
+
+def _is_valid_mask(v):
+    """True where v is neither NaN (floats) nor the dtype sentinel (ints); bool has no invalid."""
+    if v.dtype.kind == "f":
+        return ~np.isnan(v)
+    if v.dtype.kind in "iu":
+        return v != invalid_for(v.dtype)
+    return np.ones(len(v), dtype=bool)
+
+
+# ----------------------------------------------------------------------------------------------
+# a1  rc.MultiKeyGroupBy32  (rt_numpy.py:1979-2094, call :2073)
+def _bytes_view(a):
+    """Per-row byte matrix: key equality is BYTEWISE (tests/test_lexsort.py:225-256 NaNs form one
+    group; tests/test_unique.py:14-48 denormal patterns are distinct).  -0.0 vs +0.0: UNPINNED,
+    bytewise here so they are distinct keys."""
+    a = np.ascontiguousarray(a)
+    return a.view(np.uint8).reshape(len(a), a.dtype.itemsize)
+
+
+def _row_codes(list_arrays):
+    """1-D array whose == is bytewise tuple equality across all key columns."""
+    if len(list_arrays) == 1:
+        a = np.ascontiguousarray(list_arrays[0])
+        if a.dtype.itemsize in (1, 2, 4, 8) and a.dtype.kind not in "SUV":
+            return a.view(f"u{a.dtype.itemsize}")
+    mats = [_bytes_view(a) for a in list_arrays]
+    rec = np.ascontiguousarray(np.concatenate(mats, axis=1))
+    w = rec.shape[1]
+    if w <= 8:
+        pad = np.zeros((rec.shape[0], 8), dtype=np.uint8)
+        pad[:, :w] = rec
+        return pad.view(np.uint64).ravel()
+    return rec.view(np.dtype((np.void, w))).ravel()
+
+
+def _first_appearance(codes):
+    """codes -> (ikey 1-based int64, ifirst int64) with bins numbered by first appearance."""
+    n = len(codes)
+    if n == 0:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64)
+    _, first_idx, inverse = np.unique(codes, return_index=True, return_inverse=True)
+    order = np.argsort(first_idx, kind="stable")  # sorted-unique id -> appearance order
+    rank = np.empty(len(order), dtype=np.int64)
+    rank[order] = np.arange(len(order), dtype=np.int64)
+    return rank[inverse.ravel()] + 1, first_idx[order].astype(np.int64)
+
+
+def MultiKeyGroupBy32(list_arrays, hint_size=0, filter=None, hash_mode=2, cutoffs=None):
+    """-> (iKey int32[N] base-1, 0 = filtered; iFirstKey int32[U]; unique_count).
+    With cutoffs: numbering restarts per partition, iFirstKey = (partition-relative first rows,
+    cumulative unique counts)  (tests/test_pgroupby.py:7-86)."""
+    if isinstance(list_arrays, np.ndarray):
+        list_arrays = [list_arrays]
+    n = len(list_arrays[0])
+    for a in list_arrays:
+        if len(a) != n:
+            raise ValueError("groupbyhash all arrays must have same length")
+    codes = _row_codes(list_arrays)
+    if filter is not None:
+        filter = np.asarray(filter, dtype=bool)
+        if len(filter) != n:
+            raise ValueError("filter length mismatch")
+
+    def one(lo, hi):
+        c = codes[lo:hi]
+        if filter is None:
+            ik, ifirst = _first_appearance(c)
+            return ik, ifirst
+        f = filter[lo:hi]
+        idx = np.flatnonzero(f)
+        ik_f, ifirst_f = _first_appearance(c[idx])
+        ik = np.zeros(hi - lo, dtype=np.int64)
+        ik[idx] = ik_f
+        return ik, idx[ifirst_f] if len(ifirst_f) else ifirst_f
+
+    if cutoffs is None:
+        ik, ifirst = one(0, n)
+        return ik.astype(np.int32), ifirst.astype(np.int32), int(len(ifirst))
+
+    cutoffs = np.asarray(cutoffs, dtype=np.int64)
+    ikey = np.zeros(n, dtype=np.int32)
+    firsts, ucut, lo, total = [], [], 0, 0
+    for hi in cutoffs:
+        ik, ifirst = one(lo, int(hi))
+        ikey[lo:hi] = ik
+        firsts.append(ifirst.astype(np.int32))
+        total += len(ifirst)
+        ucut.append(total)
+        lo = int(hi)
+    vals = np.concatenate(firsts) if firsts else np.zeros(0, np.int32)
+    return ikey, (vals, np.asarray(ucut, dtype=np.int64)), total
+
+
+# ----------------------------------------------------------------------------------------------
+# a4  rc.CombineFilter (rt_numpy.py:1489-1508): where(filter, key, 0), same dtype
+def CombineFilter(key, filter):
+    key = np.asarray(key)
+    return np.where(np.asarray(filter, dtype=bool), key, key.dtype.type(0)).astype(key.dtype)
+
+
+def CombineAccum1Filter(key1, unique_count1, filter=None):
+    """rt_numpy.py:1512-1545: drop filtered rows and bin 0, renumber the surviving bins by first
+    appearance; iKey keeps key1's dtype, iFirstKey is int32 (docstring :1533-1540)."""
+    key1 = np.asarray(key1)
+    keep = key1 > 0
+    if filter is not None:
+        keep &= np.asarray(filter, dtype=bool)
+    idx = np.flatnonzero(keep)
+    ik_f, ifirst_f = _first_appearance(key1[idx].astype(np.int64))
+    out = np.zeros(len(key1), dtype=key1.dtype)
+    out[idx] = ik_f
+    return out, idx[ifirst_f].astype(np.int32), int(len(ifirst_f))
+
+
+def CombineAccum2Filter(key1, key2, unique_count1, unique_count2, filter=None):
+    """rt_numpy.py:1549-1597.  The cell grid is (unique_count1+1) x (unique_count2+1) including the
+    invalid row/column; iKey = key2*(unique_count1+1) + key1 (UNPINNED layout beyond the size of
+    nCountGroup and 'False -> 0'; follows cat2keys rt_numpy.py:1714-1734)."""
+    key1 = np.asarray(key1).astype(np.int64)
+    key2 = np.asarray(key2).astype(np.int64)
+    ncell = (unique_count1 + 1) * (unique_count2 + 1)
+    ik = key2 * (unique_count1 + 1) + key1
+    if filter is not None:
+        ik = np.where(np.asarray(filter, dtype=bool), ik, 0)
+    dt = np.int8 if ncell < 100 else np.int16 if ncell < 30_000 else np.int32 if ncell < 2_000_000_000 else np.int64
+    return ik.astype(dt), np.bincount(ik, minlength=ncell).astype(np.int32)
+
+
+# ----------------------------------------------------------------------------------------------
+# a6/a7  rc.BinCount / rc.GroupFromBinCount / rc.GroupByPack32 (rt_numpy.py:1901-1975)
+def BinCount(ikey, n, pack=False):
+    """histogram int32[n]; pack=True -> (nCountGroup, iGroup, iFirstGroup) (rt_numpy.py:1960)."""
+    ikey = np.asarray(ikey)
+    cnt = np.bincount(ikey.astype(np.int64), minlength=n)[:n].astype(np.int32)
+    if not pack:
+        return cnt
+    igroup, ifirstgroup = GroupFromBinCount(ikey, cnt)
+    return cnt, igroup, ifirstgroup
+
+
+def GroupFromBinCount(ikey, ncountgroup):
+    """iGroup = rows bucketed by bin (bin 0 first), ascending row order inside a bin (stable);
+    iFirstGroup = exclusive cumsum of nCountGroup  (docstring rt_numpy.py:1926-1933)."""
+    ikey = np.asarray(ikey)
+    idt = _index_dtype(len(ikey))
+    igroup = np.argsort(ikey, kind="stable").astype(idt)
+    ifirst = np.zeros(len(ncountgroup), dtype=np.int64)
+    ifirst[1:] = np.cumsum(ncountgroup.astype(np.int64))[:-1]
+    return igroup, ifirst.astype(idt)
+
+
+def GroupByPack32(ikey, _unused, n, cutoffs=None):
+    """Old cutoffs-capable packer (rt_numpy.py:1972) -> (iGroup, iFirstGroup, nCountGroup).
+    cutoffs behaviour is UNPINNED; without cutoffs it equals BinCount(pack=True)."""
+    if cutoffs is not None:
+        raise NotImplementedError("GroupByPack32 with cutoffs is unpinned by the reference tests")
+    cnt, igroup, ifirstgroup = BinCount(ikey, n, pack=True)
+    return igroup, ifirstgroup, cnt
+
+
+# ----------------------------------------------------------------------------------------------
+# a5  rc.GroupByAll32 (rt_numpy.py:1858-1871; dispatch rt_grouping.py:3395-3397, 3433-3436)
+def _sum_out_dtype(dt):
+    if dt.kind == "f":
+        return dt
+    if dt.kind == "u" and dt.itemsize == 8:
+        return np.dtype(np.uint64)  # UNPINNED (rt_groupbynumba.py:642-648 intent)
+    return np.dtype(np.int64)
+
+
+def _reduce_one(v, ikey, nbins, func, lo, hi):
+    dt = v.dtype
+    if dt.kind not in "biuf":
+        return None  # unsupported value dtype -> None slot (rt_grouping.py:2341-2345)
+    ik = ikey.astype(np.int64)
+    inrange = (ik >= lo) & (ik < hi)
+    nan_op = func >= GB_NANSUM
+    base = func - 50 if nan_op else func
+    use = inrange & _is_valid_mask(v) if nan_op else inrange
+    ikx, vx = ik[use], v[use]
+    cnt = np.bincount(ikx, minlength=nbins).astype(np.int64)
+
+    if base == GB_SUM:
+        odt = _sum_out_dtype(dt)
+        if dt.kind == "f":
+            out = np.bincount(ikx, weights=vx.astype(np.float64), minlength=nbins)
+            return out.astype(odt)
+        out = np.zeros(nbins, dtype=odt)
+        np.add.at(out, ikx, vx.astype(odt))  # wrap-around exact
+        return out
+    if base == GB_MEAN:
+        # mean -> float64 for every input dtype (float32 output dtype UNPINNED)
+        s = np.bincount(ikx, weights=vx.astype(np.float64), minlength=nbins)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            out = s / cnt
+        out[cnt == 0] = np.nan
+        return out
+    if base in (GB_MIN, GB_MAX):
+        inv = invalid_for(dt)
+        out = np.full(nbins, inv, dtype=dt)
+        if len(vx) == 0:
+            return out
+        order = np.argsort(ikx, kind="stable")
+        iks, vs = ikx[order], vx[order]
+        starts = np.flatnonzero(np.r_[True, iks[1:] != iks[:-1]])
+        ufn = np.minimum if base == GB_MIN else np.maximum  # NaN-propagating
+        red = ufn.reduceat(vs, starts)
+        if not nan_op and dt.kind in "iu":
+            # integer sentinel propagates through min AND max (tests/test_groupbyops.py:389-456)
+            has_inv = np.add.reduceat((vs == inv).astype(np.int64), starts) > 0
+            red = np.where(has_inv, inv, red)
+        out[iks[starts]] = red
+        return out
+    if base in (GB_VAR, GB_STD):
+        x = vx.astype(np.float64)
+        s = np.bincount(ikx, weights=x, minlength=nbins)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            mean = s / cnt
+            d = x - mean[ikx]
+            m2 = np.bincount(ikx, weights=d * d, minlength=nbins)
+            out = m2 / (cnt - 1)  # ddof = 1 (tests/test_groupby.py:78-96)
+        out[cnt < 2] = np.nan  # 1-element group -> NaN (tests/test_groupby.py:191-210)
+        if base == GB_STD:
+            out = np.sqrt(out)
+        return out
+    raise ValueError(f"GroupByAll32: unsupported function {func}")
+
+
+def GroupByAll32(values, ikey, unique_rows, funcList, binLowList, binHighList, func_param=0):
+    """-> tuple of arrays[unique_rows+1] (slot 0 = filtered bin), None for unsupported columns.
+    Slots outside [binLow, binHigh) hold the op's empty value (sum 0, others invalid/NaN)."""
+    ikey = np.asarray(ikey)
+    out = []
+    for v, f, lo, hi in zip(values, funcList, binLowList, binHighList):
+        out.append(_reduce_one(np.asarray(v), ikey, unique_rows + 1, int(f), int(lo), int(hi)))
+    return tuple(out)
+
+
+# ----------------------------------------------------------------------------------------------
+# a8  rc.GroupByAllPack32 (rt_numpy.py:1875-1891; rt_grouping.py:3442-3454)
+def GroupByAllPack32(
+    values, ikey, iGroup, iFirstGroup, nCountGroup, unique_rows, funcList, binLowList, binHighList, func_param=0
+):
+    """first / nth / last through the packed layout; out of range or empty bin -> invalid
+    (tests/test_groupby.py:137-159, 755-770)."""
+    iGroup, iFirstGroup, nCountGroup = map(np.asarray, (iGroup, iFirstGroup, nCountGroup))
+    nb = unique_rows + 1
+    res = []
+    for v, f, lo, hi in zip(values, funcList, binLowList, binHighList):
+        v = np.asarray(v)
+        f = int(f)
+        if f not in (GB_FIRST, GB_NTH, GB_LAST):
+            raise ValueError(f"GroupByAllPack32: unsupported function {f}")
+        cnt = nCountGroup[:nb].astype(np.int64)
+        first = iFirstGroup[:nb].astype(np.int64)
+        if f == GB_FIRST:
+            off = np.zeros(nb, np.int64)
+        elif f == GB_LAST:
+            off = cnt - 1
+        else:
+            n = int(func_param)
+            off = np.full(nb, n, np.int64) if n >= 0 else cnt + n
+        b = np.arange(nb)
+        ok = (off >= 0) & (off < cnt) & (b >= lo) & (b < hi)
+        out = np.zeros(nb, dtype=v.dtype)
+        if v.dtype.kind not in "SUV":
+            out[:] = invalid_for(v.dtype)
+        out[ok] = v[iGroup[(first + off)[ok]]]
+        res.append(out)
+    return tuple(res)
+
+
+# ----------------------------------------------------------------------------------------------
+# a9  rc.EmaAll32, GB_CUMSUM only (rt_grouping.py:3427-3430; rt_groupbyops.py:3158-3178)
+def EmaAll32(values, ikey, unique_rows, funcNum, func_param):
+    """Per-group running sum in original row order (tests/test_groupby.py:555-602).
+    func_param = (decay, time, filter, reset_filter).  Op-filter False -> the row gets the group's
+    current running value; bin 0 row -> invalid of the OUTPUT dtype.  Output dtype: ints -> int64
+    (uint64 stays), floats keep theirs (UNPINNED).  reset_filter (UNPINNED): on a row that passes
+    the filter and has reset set, zero the accumulator before adding (rt_fastarraynumba.py:506-524).
+    Integer sentinels are not skipped (tests/test_merge.py:6425-6426)."""
+    if int(funcNum) != GB_CUMSUM:
+        raise ValueError(f"EmaAll32: unsupported function {funcNum}")
+    filt = reset = None
+    if isinstance(func_param, (tuple, list)) and len(func_param) >= 4:
+        filt, reset = func_param[2], func_param[3]
+    ik = np.asarray(ikey).astype(np.int64)
+    n = len(ik)
+    res = []
+    for v in values:
+        v = np.asarray(v)
+        if v.dtype.kind not in "biuf":
+            res.append(None)
+            continue
+        odt = _sum_out_dtype(v.dtype)
+        acc_dt = np.dtype(np.float64) if v.dtype.kind == "f" else np.dtype(odt)
+        x = v.astype(acc_dt)
+        active = ik > 0
+        if filt is not None:
+            add = active & np.asarray(filt, dtype=bool)
+        else:
+            add = active
+        # stable bucket by bin, then a segmented running sum
+        order = np.argsort(ik, kind="stable")
+        iks = ik[order]
+        xs = np.where(add[order], x[order], acc_dt.type(0))
+        seg_start = np.r_[True, iks[1:] != iks[:-1]] if n else np.zeros(0, bool)
+        if reset is not None:
+            rs = (np.asarray(reset, dtype=bool) & add)[order]
+            seg_start = seg_start | rs
+        with np.errstate(over="ignore", invalid="ignore"):
+            cs = np.cumsum(xs)
+            start_idx = np.flatnonzero(seg_start)
+            seg_id = np.cumsum(seg_start) - 1
+            if acc_dt.kind == "f":
+                # exact per-segment sequential sums (no cancellation against earlier segments)
+                run = np.empty(n, np.float64)
+                ends = np.r_[start_idx[1:], n]
+                for s, e in zip(start_idx, ends):
+                    run[s:e] = np.cumsum(xs[s:e])
+            else:
+                base = cs[start_idx] - xs[start_idx]
+                run = cs - base[seg_id]
+        out = np.empty(n, dtype=odt)
+        out[order] = run.astype(odt)
+        out[~active] = invalid_for(odt)
+        res.append(out)
+    return res
+
+
+# ----------------------------------------------------------------------------------------------
+# a10  rc.MakeiFirst / rc.MakeiNext (rt_numpy.py:1767-1854; tests/test_grouping.py:210-296)
+def MakeiFirst(key, n, filter=None, mode=0):
+    """Array indexed by bin, slots 0..n, first (mode 0) / last (mode 1) row of each bin; invalid
+    sentinel where a bin has no row; slot 0 is always invalid.  Row ids need an index dtype:
+    int32 (tests assert ilast == 174762 for int8 keys, so it cannot be the key's dtype)."""
+    key = np.asarray(key).astype(np.int64)
+    idt = _index_dtype(len(key))
+    out = np.full(n + 1, invalid_for(idt), dtype=idt)
+    rows = np.arange(len(key), dtype=np.int64)
+    ok = (key > 0) & (key <= n)
+    if filter is not None:
+        ok &= np.asarray(filter, dtype=bool)
+    k, r = key[ok], rows[ok]
+    if len(k):
+        if mode == 0:
+            out[k[::-1]] = r[::-1]
+        else:
+            out[k] = r
+    return out
+
+
+def MakeiNext(key, n, mode=0):
+    """next (mode 0) / previous (mode 1) row with the same bin, invalid sentinel where none.
+    Bin-0 rows get the sentinel (UNPINNED)."""
+    key = np.asarray(key).astype(np.int64)
+    N = len(key)
+    idt = _index_dtype(N)
+    out = np.full(N, invalid_for(idt), dtype=idt)
+    order = np.argsort(key, kind="stable")
+    ks = key[order]
+    same = ks[1:] == ks[:-1]
+    if mode == 0:
+        src, dst = order[:-1][same], order[1:][same]
+    else:
+        src, dst = order[1:][same], order[:-1][same]
+    out[src] = dst
+    out[key <= 0] = invalid_for(idt)
+    return out
+
+
+# a13  rc.ReverseShuffle (rt_grouping.py:1659; tests/test_lexsort.py:325-332)
+def ReverseShuffle(perm):
+    perm = np.asarray(perm)
+    out = np.empty_like(perm)
+    out[perm] = np.arange(len(perm), dtype=perm.dtype)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# a11  rc.LexSort32/64 (rt_numpy.py:2658-2673; tests/test_lexsort.py:21-103)
+def _descending_code(a):
+    """Rank codes whose ascending order is a's descending order with NaN still last and ties kept
+    in original row order (pandas sort_values(ascending=False) semantics, tests/test_dataset.py:1579-1595)."""
+    _, inv = np.unique(a, return_inverse=True)  # NaNs sort last and collapse to one code
+    inv = inv.ravel().astype(np.int64)
+    top = inv.max() if len(inv) else 0
+    code = top - inv
+    if a.dtype.kind == "f":
+        nan = np.isnan(a)
+        if nan.any():
+            code = np.where(nan, top + 1, top - 1 - inv)
+    return code
+
+
+def LexSort32(list_arrays, cutoffs=None, index=None, ascending=True):
+    """Stable lexicographic argsort == np.lexsort: LAST array is the primary key, NaN last."""
+    if isinstance(list_arrays, np.ndarray):
+        list_arrays = [list_arrays]
+    list_arrays = [np.asarray(a) for a in list_arrays]
+    n = len(list_arrays[0])
+    idt = _index_dtype(n)
+    if isinstance(ascending, (bool, np.bool_)):
+        asc = [bool(ascending)] * len(list_arrays)
+    else:
+        asc = [bool(x) for x in ascending]
+        if len(asc) != len(list_arrays):
+            raise ValueError("ascending must have one entry per key")
+    if cutoffs is not None:
+        raise NotImplementedError("LexSort with cutoffs is unpinned by the reference tests")
+    keys = list_arrays
+    if index is not None:
+        index = np.asarray(index).astype(np.int64)
+        keys = [k[index] for k in keys]
+    keys = [k if a else _descending_code(k) for k, a in zip(keys, asc)]
+    perm = np.lexsort(keys)
+    if index is not None:
+        perm = index[perm]
+    return perm.astype(idt)
+
+
+LexSort64 = LexSort32
+
+
+# a12  rc.GroupFromLexSort (rt_numpy.py:2098-2251, call :2207)
+def GroupFromLexSort(iGroup, value_array, cutoffs=None, base_index=1):
+    """Walk the sorted order; a new bin starts where the key row differs (bytewise) from the
+    previous one.  -> (iKey int32[N] in base `base_index`, iFirstKey[U] = first (smallest) row of
+    each bin, nCountGroup int32[U+1] with slot 0 = 0).  Rows absent from iGroup keep iKey 0."""
+    if cutoffs is not None:
+        raise NotImplementedError("GroupFromLexSort with cutoffs is unpinned by the reference tests")
+    iGroup = np.asarray(iGroup)
+    cols = value_array if isinstance(value_array, (list, tuple)) else [value_array]
+    n = len(cols[0])
+    codes = _row_codes([np.asarray(c) for c in cols])
+    idt = _index_dtype(n)
+    ikey = np.zeros(n, dtype=idt)
+    m = len(iGroup)
+    if m == 0:
+        return ikey, np.zeros(0, idt), np.zeros(1, np.int32)
+    sc = codes[iGroup]
+    newbin = np.r_[True, sc[1:] != sc[:-1]]
+    binid = np.cumsum(newbin)  # 1-based
+    ikey[iGroup] = binid - (1 - base_index)
+    starts = np.flatnonzero(newbin)
+    ifirstkey = iGroup[starts].astype(idt)
+    ncount = np.zeros(len(starts) + 1, dtype=np.int32)
+    ncount[1:] = np.diff(np.r_[starts, m])
+    return ikey, ifirstkey, ncount
+
+
+# ----------------------------------------------------------------------------------------------
+# Python-level wrappers restated from rt_numpy.py so golden docstring vectors can be replayed
+def groupbyhash(list_arrays, hint_size=0, filter=None, hash_mode=2, cutoffs=None, pack=False):
+    """rt_numpy.py:1979-2094."""
+    if isinstance(list_arrays, np.ndarray):
+        list_arrays = [list_arrays]
+    if len(list_arrays[0]) == 0:
+        e = np.zeros(0, np.int32)
+        d = {"iKey": e, "iFirstKey": e, "unique_count": 0}
+    else:
+        ik, ifk, u = MultiKeyGroupBy32(list_arrays, hint_size, filter, hash_mode, cutoffs=cutoffs)
+        d = {"iKey": ik, "iFirstKey": ifk, "unique_count": u}
+    if pack:
+        d.update(groupbypack(d["iKey"], None, d["unique_count"] + 1))
+    else:
+        d.update({"iGroup": None, "iFirstGroup": None, "nCountGroup": None})
+    return d
+
+
+def groupbypack(ikey, ncountgroup, unique_count=None, cutoffs=None):
+    """rt_numpy.py:1901-1975."""
+    if ncountgroup is None:
+        cnt, igroup, ifirstgroup = BinCount(ikey, unique_count, pack=True)
+    else:
+        igroup, ifirstgroup = GroupFromBinCount(ikey, ncountgroup)
+        cnt = ncountgroup
+    return {"iGroup": igroup, "iFirstGroup": ifirstgroup, "nCountGroup": cnt}
+
+
+def groupbylex(list_arrays, filter=None, cutoffs=None, base_index=1, rec=False):
+    """rt_numpy.py:2098-2251 (Python glue restated around LexSort32 + GroupFromLexSort)."""
+    if isinstance(list_arrays, np.ndarray):
+        list_arrays = [list_arrays]
+    value_cols = list(list_arrays)
+    sort_keys = list_arrays[::-1] if len(list_arrays) > 1 else list_arrays
+    index = None
+    filterfalse = None
+    if filter is not None:
+        filter = np.asarray(filter, dtype=bool)
+        index = np.flatnonzero(filter).astype(np.int32)
+        filterfalse = np.flatnonzero(~filter)
+    iGroup = LexSort32(sort_keys, cutoffs=cutoffs, index=index)
+    iKey, iFirstKey, nCountGroup = GroupFromLexSort(iGroup, value_cols, cutoffs=cutoffs, base_index=base_index)
+    if base_index == 0:
+        iKey = iKey + 1
+    else:
+        nCountGroup[0] = 0
+    iFirstGroup = nCountGroup.copy()
+    iFirstGroup[1:] = nCountGroup.cumsum()[:-1]
+    if filter is not None:
+        nCountGroup[0] = len(filterfalse)
+        iKey[filterfalse] = 0
+        iFirstGroup[0] = len(index)
+    return {
+        "iKey": iKey,
+        "iFirstKey": iFirstKey,
+        "unique_count": len(iFirstKey),
+        "iGroup": iGroup,
+        "iFirstGroup": iFirstGroup,
+        "nCountGroup": nCountGroup,
+    }

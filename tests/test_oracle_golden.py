@@ -1,0 +1,261 @@
+"""Pins the CPU oracle against the reference's own golden vectors.
+
+Each test names the reference file:line whose expected values are transcribed here.  These are the
+values riptable's docstrings / tests state for riptide_cpp, so an oracle that passes them is
+"parity pinned" for the behaviour they cover.
+"""
+import numpy as np
+import pytest
+
+from oracle import riptide_oracle as orc
+
+
+@pytest.fixture(scope="module")
+def c2m():
+    np.random.seed(12345)
+    c = np.random.randint(0, 8000, 2_000_000)
+    d = np.random.randint(0, 8000, 2_000_000)
+    return c, d
+
+
+def test_groupbyhash_docstring_plain(c2m):
+    # rt_numpy.py:2013-2021
+    c, _ = c2m
+    r = orc.groupbyhash(c)
+    assert r["unique_count"] == 8000
+    assert r["iKey"][:3].tolist() == [1, 2, 3]
+    assert r["iKey"][-3:].tolist() == [6061, 7889, 3002]
+    assert r["iFirstKey"][:3].tolist() == [0, 1, 2]
+    assert r["iFirstKey"][-3:].tolist() == [67072, 67697, 68250]
+    assert r["iKey"].dtype == np.int32 and r["iFirstKey"].dtype == np.int32
+    # rt_numpy.py:2037-2039
+    bc = orc.BinCount(r["iKey"], r["unique_count"] + 1)
+    assert bc[:3].tolist() == [0, 251, 262] and bc[-3:].tolist() == [239, 217, 246]
+
+
+def test_groupbyhash_docstring_filtered(c2m):
+    # rt_numpy.py:2044-2051
+    c, _ = c2m
+    f = (c % 3).astype(bool)
+    r = orc.groupbyhash(c, filter=f)
+    assert r["unique_count"] == 5333
+    assert r["iKey"][:3].tolist() == [0, 1, 2]
+    assert r["iKey"][-3:].tolist() == [0, 5250, 1973]
+    assert r["iFirstKey"][:3].tolist() == [1, 2, 3]
+    assert r["iFirstKey"][-3:].tolist() == [54422, 58655, 68250]
+
+
+def test_groupbyhash_docstring_multikey(c2m):
+    # rt_numpy.py:2055-2062
+    c, d = c2m
+    r = orc.groupbyhash([c, d])
+    assert r["unique_count"] == 1968856
+    assert r["iKey"][:3].tolist() == [1, 2, 3]
+    assert r["iKey"][-3:].tolist() == [1968854, 1968855, 1968856]
+    assert r["iFirstKey"][:3].tolist() == [0, 1, 2]
+    assert r["iFirstKey"][-3:].tolist() == [1999997, 1999998, 1999999]
+
+
+def test_groupbypack_docstring():
+    # rt_numpy.py:1926-1933 and :2027-2033
+    np.random.seed(12345)
+    c = np.random.randint(0, 8, 10_000)
+    x = orc.groupbyhash(c)
+    assert x["iFirstKey"].tolist() == [0, 1, 3, 4, 6, 14, 18, 20]
+    assert x["iKey"][:3].tolist() == [1, 2, 2] and x["iKey"][-3:].tolist() == [4, 6, 1]
+    ncount = orc.BinCount(x["iKey"], x["unique_count"] + 1)
+    p = orc.groupbypack(x["iKey"], ncount)
+    assert p["iGroup"][:3].tolist() == [0, 9, 21] and p["iGroup"][-3:].tolist() == [9988, 9991, 9992]
+    assert p["iFirstGroup"].tolist() == [0, 0, 1213, 2465, 3761, 4987, 6239, 7522, 8797]
+    assert p["nCountGroup"].tolist() == [0, 1213, 1252, 1296, 1226, 1252, 1283, 1275, 1203]
+    assert p["nCountGroup"].sum() == 10000
+    p2 = orc.groupbypack(x["iKey"], None, x["unique_count"] + 1)
+    for k in p:
+        assert np.array_equal(p[k], p2[k])
+
+
+GBLEX_IKEY = [0, 1, 9, 0, 23, 31, 0, 45, 53, 0, 2, 3, 0, 4, 5, 0, 6, 7, 0, 8, 10, 0, 11, 12, 0, 13, 14, 0, 15,
+              16, 0, 17, 18, 0, 19, 20, 0, 21, 22, 0, 24, 25, 0, 26, 27, 0, 28, 29, 0, 30, 32, 0, 33, 34, 0, 35,
+              36, 0, 37, 38, 0, 39, 40, 0, 41, 42, 0, 43, 44, 0, 46, 47, 0, 48, 49, 0, 50, 51, 0, 52, 54, 0, 55,
+              56, 0, 57, 58, 0, 59, 60, 0, 61, 62, 0, 63, 64, 0, 65, 66, 0]
+GBLEX_IFIRST = [1, 10, 11, 13, 14, 16, 17, 19, 2, 20, 22, 23, 25, 26, 28, 29, 31, 32, 34, 35, 37, 38, 4, 40, 41,
+                43, 44, 46, 47, 49, 5, 50, 52, 53, 55, 56, 58, 59, 61, 62, 64, 65, 67, 68, 7, 70, 71, 73, 74, 76,
+                77, 79, 8, 80, 82, 83, 85, 86, 88, 89, 91, 92, 94, 95, 97, 98]
+
+
+def test_groupbylex_docstring():
+    # rt_numpy.py:2126-2156
+    a = np.arange(100).astype("S")
+    f = (np.arange(100) % 3).astype(bool)
+    r = orc.groupbylex([a], filter=f)
+    assert r["iKey"].tolist() == GBLEX_IKEY
+    assert r["iFirstKey"].tolist() == GBLEX_IFIRST
+    assert r["unique_count"] == 66
+    assert r["iGroup"].tolist() == GBLEX_IFIRST
+    assert r["iFirstGroup"].tolist() == [66] + list(range(66))
+    assert r["nCountGroup"].tolist() == [34] + [1] * 66
+
+
+def test_combine_accum1_filter_docstring():
+    # rt_numpy.py:1533-1540: Cat of (arange(20)%10).astype('S'), ordered -> ikey = value+1
+    key = ((np.arange(20) % 10) + 1).astype(np.int8)
+    ik, ifk, u = orc.CombineAccum1Filter(key, 10, (np.arange(20) % 2).astype(bool))
+    assert ik.tolist() == [0, 1, 0, 2, 0, 3, 0, 4, 0, 5, 0, 1, 0, 2, 0, 3, 0, 4, 0, 5]
+    assert ik.dtype == np.int8
+    assert ifk.tolist() == [1, 3, 5, 7, 9] and u == 5
+
+
+def test_reductions_kat_test_groupby():
+    # tests/test_groupby.py:13-104: key = bool [T,F,T,F,T]; ds.gb sorts keys -> bins (False, True)
+    num = [3, 4, 5, 1, 2]
+    key = np.array([True, False, True, False, True])
+    ikey = np.where(key, 2, 1).astype(np.int8)  # sorted display order: False=1, True=2
+    for dt in [np.int8, np.uint8, np.int16, np.uint16, np.int32, np.uint32, np.int64, np.uint64, np.float32,
+               np.float64]:
+        v = np.array(num, dtype=dt)
+
+        def run(fn):
+            return orc.GroupByAll32([v], ikey, 2, [fn], [1], [3], 0)[0][1:]
+
+        assert run(orc.GB_SUM).tolist() == [5, 10]
+        assert run(orc.GB_NANSUM).tolist() == [5, 10]
+        assert run(orc.GB_MIN).tolist() == [1, 2] and run(orc.GB_MIN).dtype == dt
+        assert run(orc.GB_MAX).tolist() == [4, 5]
+        np.testing.assert_allclose(run(orc.GB_MEAN), [2.5, 3.333333333], rtol=1e-6)
+        np.testing.assert_allclose(run(orc.GB_STD), [2.121320343560, 1.527525231652], rtol=1e-6)
+        np.testing.assert_allclose(run(orc.GB_VAR), [4.5, 2.333333333333], rtol=1e-6)
+    # tests/test_groupby.py:191-210: var/std of a 1-item group is NaN
+    ik1 = np.arange(1, 6).astype(np.int8)
+    for fn in (orc.GB_VAR, orc.GB_STD, orc.GB_NANVAR, orc.GB_NANSTD):
+        assert np.isnan(orc.GroupByAll32([np.array(num, float)], ik1, 5, [fn], [1], [6], 0)[0][1:]).all()
+    # tests/test_groupby.py:212-225 count
+    assert orc.BinCount(ikey, 3)[1:].tolist() == [2, 3]
+
+
+def test_first_last_kat():
+    # tests/test_groupby.py:137-159: first [4,3], last [1,2] for key bool sorted (False, True)
+    num = np.array([3, 4, 5, 1, 2])
+    ikey = np.array([2, 1, 2, 1, 2], dtype=np.int8)
+    cnt, ig, ifg = orc.BinCount(ikey, 3, pack=True)
+    first = orc.GroupByAllPack32([num], ikey, ig, ifg, cnt, 2, [orc.GB_FIRST], [1], [3], 0)[0]
+    last = orc.GroupByAllPack32([num], ikey, ig, ifg, cnt, 2, [orc.GB_LAST], [1], [3], 0)[0]
+    assert first[1:].tolist() == [4, 3] and last[1:].tolist() == [1, 2]
+    s = np.array([b"3", b"4", b"5", b"1", b"2"])
+    assert orc.GroupByAllPack32([s], ikey, ig, ifg, cnt, 2, [orc.GB_FIRST], [1], [3], 0)[0][1:].tolist() == [b"4", b"3"]
+    # nth out of range -> invalid (tests/test_groupby.py:755-770)
+    nth = orc.GroupByAllPack32([num.astype(float)], ikey, ig, ifg, cnt, 2, [orc.GB_NTH], [1], [3], 2)[0]
+    assert np.isnan(nth[1]) and nth[2] == 2.0
+    nthn = orc.GroupByAllPack32([num], ikey, ig, ifg, cnt, 2, [orc.GB_NTH], [1], [3], -3)[0]
+    assert nthn[1] == np.iinfo(num.dtype).min and nthn[2] == 3
+
+
+def test_cumsum_kat():
+    # tests/test_groupby.py:504-602
+    order_ids = np.array([1, 1, 2, 1, 2, 2, 1, 2, 2, 2, 2, 1])
+    seconds = np.array([50, 70, 72, 75, 90, 88, 95, 97, 98, 115, 116, 120])
+    shares = np.array([0, 200, 0, 500, 100, 400, 100, 0, 300, 150, 150, 0])
+    r = orc.groupbyhash(order_ids)
+    ik = r["iKey"]
+    out = orc.EmaAll32([shares, seconds], ik, 2, orc.GB_CUMSUM, (0.0, None, None, None))
+    assert out[0].tolist() == [0, 200, 0, 700, 100, 500, 800, 500, 800, 950, 1100, 800]
+    assert out[1].tolist() == [50, 120, 72, 195, 162, 250, 290, 347, 445, 560, 676, 410]
+    f = np.arange(12) % 2 == 0
+    out = orc.EmaAll32([shares, seconds], ik, 2, orc.GB_CUMSUM, (0.0, None, f, None))
+    assert out[0].tolist() == [0, 0, 0, 0, 100, 100, 100, 100, 400, 400, 550, 100]
+    assert out[1].tolist() == [50, 50, 72, 50, 162, 162, 145, 162, 260, 260, 376, 145]
+    # filter at construction: bin-0 rows -> invalid of the output dtype
+    rf = orc.groupbyhash(order_ids, filter=f)
+    out = orc.EmaAll32([shares, seconds], rf["iKey"], rf["unique_count"], orc.GB_CUMSUM, (0.0, None, None, None))
+    inv = np.iinfo(np.int64).min
+    assert out[0].dtype == np.int64
+    assert out[0].tolist() == [0, inv, 0, inv, 100, inv, 100, inv, 400, inv, 550, inv]
+    assert out[1].tolist() == [50, inv, 72, inv, 162, inv, 145, inv, 260, inv, 376, inv]
+
+
+def test_cutoffs_kat():
+    # tests/test_pgroupby.py:7-86
+    rng = np.random.default_rng(0)
+    arr, arr2 = rng.integers(0, 5, 15), rng.integers(0, 5, 15)
+    arr3 = np.concatenate([arr, arr2])
+    g1, g2 = orc.groupbyhash([arr]), orc.groupbyhash([arr2])
+    g3 = orc.groupbyhash([arr3], cutoffs=np.array([15, 30], dtype=np.int64))
+    vals, cuts = g3["iFirstKey"]
+    assert np.array_equal(g1["iKey"], g3["iKey"][:15]) and np.array_equal(g2["iKey"], g3["iKey"][15:])
+    assert np.array_equal(g1["iFirstKey"], vals[: cuts[0]]) and np.array_equal(g2["iFirstKey"], vals[cuts[0]:])
+    assert g3["unique_count"] == g1["unique_count"] + g2["unique_count"]
+    mk = np.concatenate([np.zeros(15), np.ones(15)])
+    gm = orc.groupbyhash([mk, arr3])
+    assert np.array_equal(gm["iFirstKey"][: cuts[0]], vals[: cuts[0]])
+    assert np.array_equal(gm["iFirstKey"][cuts[0]:], vals[cuts[0]:] + 15)
+    # test_empty_cutoffs
+    a = np.arange(10)
+    pgb = orc.groupbyhash([np.ones(10)], filter=(a % 2).astype(bool), cutoffs=a.astype(np.int64) + 1)
+    assert np.array_equal(pgb["iKey"], a % 2)
+    assert pgb["iFirstKey"][1].tolist() == [0, 1, 1, 2, 2, 3, 3, 4, 4, 5]
+
+
+def test_makeifirst_kat():
+    # tests/test_grouping.py:210-296
+    for dt in [np.int8, np.int16, np.int32, np.int64]:
+        arr = np.ones(174_763, dtype=dt)
+        f = orc.MakeiFirst(arr, 2)
+        inv = orc.invalid_for(f.dtype)
+        assert f[1] == 0 and f[0] == inv and f[2] == inv
+        l = orc.MakeiFirst(arr, 2, None, 1)
+        assert l[1] == len(arr) - 1 and l[0] == inv and l[2] == inv
+    ik = np.array([1, 1, 0, 2, 1], dtype=np.int8)  # Categorical(a,a,b,c,a).set_valid(f)
+    f = orc.MakeiFirst(ik, 2)
+    assert f[1:].tolist() == [0, 3] and f[0] == orc.invalid_for(f.dtype)
+    assert orc.MakeiFirst(ik, 2, None, 1)[1:].tolist() == [4, 3]
+    ik = np.array([1, 1, 2, 3, 1], dtype=np.int8)
+    flt = np.array([True, True, False, True, True])
+    f = orc.MakeiFirst(ik, 3, flt)
+    assert f[1] == 0 and f[-1] == 3 and f[2] == orc.invalid_for(f.dtype)
+    l = orc.MakeiFirst(ik, 3, flt, 1)
+    assert l[1] == 4 and l[-1] == 3
+
+
+def test_lexsort_matches_numpy_and_hash_equals_lex():
+    # tests/test_lexsort.py:21-42, 105-256
+    rng = np.random.default_rng(7)
+    n = 100_000
+    keys = [
+        rng.integers(0, 120, n, dtype=np.int8),
+        rng.integers(0, 32000, n, dtype=np.int16),
+        rng.integers(0, n, n, dtype=np.int32),
+        rng.random(n),
+        rng.choice(["AAPL₀", "AMZN₂", "IBM₁"], n),
+    ]
+    assert np.array_equal(orc.LexSort32(keys), np.lexsort(keys))
+    arr = rng.choice([np.nan, 1.11, 2.22, 3.33], 50)
+    arr[:4] = [1.11, 2.22, 3.33, np.nan]
+    gh, gl = orc.groupbyhash(arr, pack=True), orc.groupbylex(arr)
+    for k in ("iKey", "iFirstKey", "unique_count", "iGroup", "iFirstGroup", "nCountGroup"):
+        assert np.array_equal(gh[k], gl[k]), k
+    vn = rng.integers(0, 3, 10_000)
+    vs = rng.choice(["a", "b", "c"], 10_000)
+    vn[:9] = [0, 0, 0, 1, 1, 1, 2, 2, 2]
+    vs[:9] = ["a", "b", "c"] * 3
+    gh, gl = orc.groupbyhash([vn, vs], pack=True), orc.groupbylex([vn, vs])
+    for k in ("iKey", "iFirstKey", "unique_count", "iGroup", "iFirstGroup", "nCountGroup"):
+        assert np.array_equal(gh[k], gl[k]), k
+    perm = orc.LexSort32([vn])
+    assert np.array_equal(vn[perm][orc.ReverseShuffle(perm)], vn)
+
+
+def test_projections_455654_groups():
+    # tests/test_groupby.py:419-459: 1M rows, 4 keys (int, str, str, int), seed 1234 -> exactly 455 654 groups
+    n, num_symbols = 1_000_000, 450
+    dates = ["20180602", "20180603", "20180604", "20180605", "20180606"]
+    exch = np.array(["EXCH1", "EXCH2", "EXCH3"])
+    np.random.seed(1234)
+    sym = np.random.randint(0, num_symbols, size=n)
+    ex = exch[np.random.randint(0, exch.shape[0], size=n)]
+    i = np.arange(n)
+    td = np.array(dates)[(i * len(dates) / n).astype(int)]
+    time_2500 = ((i % (n // len(dates))) / 2500).astype(int)
+    r = orc.groupbyhash([sym, ex.astype("S"), td.astype("S"), time_2500])
+    assert r["unique_count"] == 455654
+    assert (np.diff(r["iFirstKey"]) > 0).all()
+    cnt = orc.BinCount(r["iKey"], r["unique_count"] + 1)
+    assert cnt[0] == 0 and cnt.sum() == n

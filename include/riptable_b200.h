@@ -1,0 +1,153 @@
+/* riptable_b200 — C ABI of the B200-native groupby / reduce / lexsort hot path.
+ *
+ * Every entry point replaces one riptide_cpp (`rc.*`) function that riptable calls on this path.
+ * riptide_cpp is a CPython extension whose source is not in the reference tree; the interface each
+ * function replaces is therefore cited as the riptable call site that defines its arguments
+ * (paths relative to /root/reference).
+ *
+ * Conventions
+ *   - All data pointers are DEVICE pointers unless the parameter name ends in `_host`.
+ *   - No allocation happens inside the library: scratch comes from `workspace` (device memory the
+ *     caller allocates, e.g. with torch.empty) sized by the matching *_workspace_bytes query.
+ *   - All work is enqueued on `stream` (a cudaStream_t passed as void*).  Functions that return a
+ *     host scalar (unique counts) synchronise that stream before returning.
+ *   - Return value: RTB_OK or a negative rtb_status; rtb_last_error() gives the message.  The
+ *     library never aborts the process.
+ *   - dtype codes are rtb_dtype; fixed-width byte strings (numpy S/U/void) are RTB_BYTES with an
+ *     explicit itemsize.
+ */
+#ifndef RIPTABLE_B200_H
+#define RIPTABLE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  RTB_BOOL = 0, RTB_I8, RTB_U8, RTB_I16, RTB_U16, RTB_I32, RTB_U32, RTB_I64, RTB_U64, RTB_F32, RTB_F64,
+  RTB_BYTES
+} rtb_dtype;
+
+typedef enum {
+  RTB_OK = 0,
+  RTB_ERR_ARG = -1,         /* bad argument (shim raises ValueError/TypeError) */
+  RTB_ERR_WORKSPACE = -2,   /* workspace / max_unique too small; *needed_unique_host says how much to retry with */
+  RTB_ERR_CUDA = -3,        /* a CUDA call failed */
+  RTB_ERR_UNSUPPORTED = -4  /* dtype/op combination not provided (shim returns None for that column) */
+} rtb_status;
+
+/* Op numbers: riptable/rt_enum.py:486-532 (GB_FUNCTIONS). */
+typedef enum {
+  RTB_GB_SUM = 0, RTB_GB_MEAN = 1, RTB_GB_MIN = 2, RTB_GB_MAX = 3, RTB_GB_VAR = 4, RTB_GB_STD = 5,
+  RTB_GB_NANSUM = 50, RTB_GB_NANMEAN = 51, RTB_GB_NANMIN = 52, RTB_GB_NANMAX = 53, RTB_GB_NANVAR = 54,
+  RTB_GB_NANSTD = 55,
+  RTB_GB_FIRST = 100, RTB_GB_NTH = 101, RTB_GB_LAST = 102,
+  RTB_GB_CUMSUM = 300
+} rtb_gb_func;
+
+/* One key / value column: `itemsize` bytes per row, rows contiguous. */
+typedef struct {
+  const void* data;
+  int32_t dtype;    /* rtb_dtype */
+  int32_t itemsize; /* bytes per row */
+} rtb_column;
+
+int rtb_version(void);
+const char* rtb_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+uint64_t rtb_launch_count(void);
+
+/* ---- a1: rc.MultiKeyGroupBy32(list, hint_size, filter, hash_mode, cutoffs=)  — riptable/rt_numpy.py:2073-2075
+ * Hash-groups the (multi)key rows; bins numbered by first appearance among rows passing `filter`.
+ *   ikey_out      int32[nrows]  base-1 bin per row, 0 = filtered out
+ *   ifirstkey_out int32[max_unique] first row of each bin (strictly increasing); first U entries valid.
+ *                 With cutoffs: partition-relative rows (tests/test_pgroupby.py:15-25).
+ *   cutoffs_host  int64[ncutoffs] cumulative partition ends (host memory) or NULL
+ *   ucutoffs_host int64[ncutoffs] out: cumulative unique counts per partition (host), or NULL
+ *   max_unique    capacity the caller provisioned (sizes the table and ifirstkey_out)
+ * On RTB_ERR_WORKSPACE, *needed_unique_host holds a max_unique to retry with. */
+size_t rtb_groupby_workspace_bytes(int64_t nrows, int64_t max_unique, int nkeys, int has_cutoffs);
+int rtb_multikey_groupby32(const rtb_column* keys, int nkeys, int64_t nrows, int64_t hint_size,
+                           const uint8_t* filter, const int64_t* cutoffs_host, int64_t ncutoffs,
+                           int32_t* ikey_out, int32_t* ifirstkey_out, int64_t max_unique,
+                           int64_t* unique_count_host, int64_t* ucutoffs_host, int64_t* needed_unique_host,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a4: rc.CombineFilter(key, filter) — riptable/rt_numpy.py:1508.  out = filter ? key : 0, key dtype kept. */
+int rtb_combine_filter(const void* ikey, int kdtype, const uint8_t* filter, int64_t nrows, void* out, void* stream);
+
+/* ---- a5: rc.GroupByAll32(values, ikey, unique_rows, funcList, binLowList, binHighList, func_param)
+ *          — riptable/rt_numpy.py:1871, dispatched from riptable/rt_grouping.py:3434-3436.
+ * One value column per call.  out has unique_rows+1 entries of rtb_reduce_out_dtype(func, vdtype);
+ * slot 0 is the filtered bin; bins outside [bin_low, bin_high) get the op's empty value. */
+int rtb_reduce_out_dtype(int func, int vdtype); /* rtb_dtype, or <0 if the column is not reducible */
+size_t rtb_groupby_reduce_workspace_bytes(int64_t unique_rows, int func, int vdtype);
+int rtb_groupby_reduce(const void* values, int vdtype, const void* ikey, int kdtype, int64_t nrows,
+                       int64_t unique_rows, int func, int64_t bin_low, int64_t bin_high, void* out,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a6: rc.BinCount(ikey, n) — riptable/rt_grouping.py:1680,3532; riptable/rt_numpy.py:1956.  out int32[nbins]. */
+int rtb_bincount(const void* ikey, int kdtype, int64_t nrows, int64_t nbins, int32_t* out, void* stream);
+
+/* ---- a7: rc.BinCount(ikey, n, pack=True) / rc.GroupFromBinCount(ikey, nCountGroup) — riptable/rt_numpy.py:1957-1965
+ * Stable bucket sort of rows by bin.  igroup_out int32[nrows] (rows ascending inside a bin, bin 0 first),
+ * ifirstgroup_out int32[nbins] = exclusive cumsum of ncountgroup, ncountgroup_out int32[nbins]. */
+size_t rtb_pack_workspace_bytes(int64_t nrows, int64_t nbins);
+int rtb_groupby_pack(const void* ikey, int kdtype, int64_t nrows, int64_t nbins, int32_t* igroup_out,
+                     int32_t* ifirstgroup_out, int32_t* ncountgroup_out, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* ---- a8: rc.GroupByAllPack32(values, ikey, iGroup, iFirstGroup, nCountGroup, unique_rows, funcList, binLow,
+ *          binHigh, func_param) — riptable/rt_numpy.py:1891, riptable/rt_grouping.py:3443-3454.
+ * GB_FIRST / GB_NTH / GB_LAST; out has unique_rows+1 items of the value's own dtype/itemsize. */
+int rtb_groupby_pick(const void* values, int vdtype, int32_t itemsize, const int32_t* igroup,
+                     const int32_t* ifirstgroup, const int32_t* ncountgroup, int64_t unique_rows, int func,
+                     int64_t nth, int64_t bin_low, int64_t bin_high, void* out, void* stream);
+
+/* ---- a9: rc.EmaAll32(values, ikey, unique_rows, GB_CUMSUM, (decay, time, filter, reset_filter))
+ *          — riptable/rt_grouping.py:3430.  Per-group running sum in row order through the packed layout.
+ * out: nrows items of rtb_cumsum_out_dtype(vdtype); bin-0 rows get the invalid of that dtype. */
+int rtb_cumsum_out_dtype(int vdtype);
+size_t rtb_cumsum_workspace_bytes(int64_t nrows, int64_t unique_rows);
+int rtb_groupby_cumsum(const void* values, int vdtype, const void* ikey, int kdtype, int64_t nrows,
+                       int64_t unique_rows, const uint8_t* filter, const uint8_t* reset_filter, void* out,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a10: rc.MakeiFirst(key, n, filter, mode) / rc.MakeiNext(key, n, mode) — riptable/rt_numpy.py:1791-1854 */
+int rtb_make_ifirst(const void* ikey, int kdtype, int64_t nrows, int64_t n, const uint8_t* filter, int mode,
+                    int32_t* out /* n+1 */, void* stream);
+size_t rtb_make_inext_workspace_bytes(int64_t nrows, int64_t n);
+int rtb_make_inext(const void* ikey, int kdtype, int64_t nrows, int64_t n, int mode, int32_t* out /* nrows */,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a11: rc.LexSort32(list, cutoffs=, index=, ascending=) — riptable/rt_numpy.py:2670-2671, 2200-2202
+ * Stable lexicographic argsort; LAST key is primary (numpy convention); NaN last.
+ *   index     int32[nindex] rows to sort (NULL = all rows, nindex = nrows)
+ *   ascending_host int8[nkeys] per key (NULL = all ascending)
+ *   perm_out  int32[nindex] */
+size_t rtb_lexsort_workspace_bytes(int64_t nrows, int64_t nindex, int nkeys, const int32_t* itemsizes_host);
+int rtb_lexsort32(const rtb_column* keys, int nkeys, int64_t nrows, const int32_t* index, int64_t nindex,
+                  const int8_t* ascending_host, int32_t* perm_out, void* workspace, size_t workspace_bytes,
+                  void* stream);
+
+/* ---- a12: rc.GroupFromLexSort(iGroup, value_array, cutoffs=, base_index=) — riptable/rt_numpy.py:2207
+ *   ikey_out int32[nrows] (rows not in igroup get 0), ifirstkey_out int32[nindex] (first U valid),
+ *   ncountgroup_out int32[nindex+1] (first U+1 valid, slot 0 = 0). */
+size_t rtb_group_from_lexsort_workspace_bytes(int64_t nrows, int64_t nindex);
+int rtb_group_from_lexsort(const int32_t* igroup, int64_t nindex, const rtb_column* keys, int nkeys, int64_t nrows,
+                           int base_index, int32_t* ikey_out, int32_t* ifirstkey_out, int32_t* ncountgroup_out,
+                           int64_t* unique_count_host, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a13: rc.ReverseShuffle(perm) — riptable/rt_grouping.py:1659.  out[perm[i]] = i. */
+int rtb_reverse_shuffle(const int32_t* perm, int64_t n, int32_t* out, void* stream);
+
+/* ---- multi-GPU helper: out[i] = map[ikey[i]] (rc.ReIndexGroups semantics, riptable/rt_grouping.py:378-407) */
+int rtb_remap_ikey(const int32_t* ikey, int64_t nrows, const int32_t* map, int64_t nmap, int32_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RIPTABLE_B200_H */

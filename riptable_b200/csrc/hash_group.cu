@@ -1,0 +1,706 @@
+// a1: MultiKeyGroupBy32 — hash grouping with first-appearance bin numbering, on sm_100a.
+//
+// Replaces rc.MultiKeyGroupBy32 (riptable/rt_numpy.py:2073-2075).  Design:
+//
+//   * Open-addressing table of 16-byte slots {key|tag, minrow, bin}; one 128-bit L2 load per probe.
+//   * PROGRESSIVE ROUNDS over geometrically growing row ranges [P_k, P_{k+1}).  A key already
+//     finalised in an earlier round resolves with one probe and iKey is written immediately, so the
+//     steady state moves key_bytes + 4 bytes per row — the algorithmic minimum.  Keys first seen in a
+//     round are "provisional": the row stores -(slot+1), the slot tracks min(row) with atomicMin.
+//   * After a round, provisional slots are ranked by min row through a bitmap over the round's rows
+//     and a device-wide popcount scan; that rank IS first-appearance order because every key of an
+//     earlier round has a smaller first row than any key new to this round.  A fix-up pass rewrites
+//     the provisional rows of that round only.
+//   * The table is resized between rounds to ~2x the projected unique count so that it stays
+//     L2-resident for low/medium cardinalities; a round that runs out of room aborts and is redone
+//     after growing (bounded by the geometric schedule).
+//
+// Two key layouts:
+//   direct : one key column of 1/2/4/8 bytes, the key itself (zero-extended) lives in the slot.
+//   byref  : anything else (multi-key, strings). The slot holds (hash_hi32 << 32 | representative row)
+//            and equality is verified bytewise against the representative row's key columns.
+#include <math.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace rtb {
+
+struct __align__(16) Slot {
+  unsigned long long key;  // direct: key bits; byref: (hash_hi32 << 32) | rep_row.  ~0 = empty
+  uint32_t minrow;         // smallest row seen for this key (0xFFFFFFFF until the first atomicMin lands)
+  uint32_t nbin;           // ~bin: 0xFFFFFFFF while provisional, ~(final 1-based bin) afterwards (memset 0xFF = fresh)
+  __device__ __forceinline__ uint32_t bin() const { return ~nbin; }
+};
+static_assert(sizeof(Slot) == 16, "slot must be one 128-bit load");
+
+constexpr unsigned long long kEmpty = ~0ull;
+constexpr int kMaxKeyCols = 16;
+
+struct KeyCols {
+  const uint8_t* ptr[kMaxKeyCols];
+  int32_t itemsize[kMaxKeyCols];
+  int32_t chunk[kMaxKeyCols];  // widest load (16/8/4/2/1) dividing both itemsize and the base address
+  int32_t ncols;
+};
+
+struct GbCounters {
+  uint32_t newcount;  // slots claimed in this round
+  uint32_t abort;     // set when the round ran out of table room
+  uint32_t total;     // scratch for scan totals
+  uint32_t pad;
+};
+
+// ---- hashing ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t hash_u64(unsigned long long k) {
+  uint32_t lo = (uint32_t)k, hi = (uint32_t)(k >> 32);
+  uint32_t a = lo * 0x9E3779B1u;
+  uint32_t b = hi * 0x85EBCA77u;
+  uint32_t h = a ^ __funnelshift_l(b, b, 16);
+  h ^= h >> 15;
+  h *= 0xC2B2AE3Du;
+  h ^= h >> 13;
+  return h;
+}
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long h, unsigned long long w) {
+  h ^= w;
+  h *= 0x9E3779B97F4A7C15ull;
+  h ^= h >> 29;
+  return h;
+}
+
+__device__ __forceinline__ unsigned long long hash_row(const KeyCols& kc, int64_t r) {
+  unsigned long long h = 0x243F6A8885A308D3ull;
+  for (int c = 0; c < kc.ncols; c++) {
+    const uint8_t* p = kc.ptr[c] + r * (int64_t)kc.itemsize[c];
+    int sz = kc.itemsize[c];
+    switch (kc.chunk[c]) {
+      case 16:
+        for (int o = 0; o < sz; o += 16) {
+          uint4 w = *(const uint4*)(p + o);
+          h = mix64(h, ((unsigned long long)w.y << 32) | w.x);
+          h = mix64(h, ((unsigned long long)w.w << 32) | w.z);
+        }
+        break;
+      case 8:
+        for (int o = 0; o < sz; o += 8) h = mix64(h, *(const unsigned long long*)(p + o));
+        break;
+      case 4:
+        for (int o = 0; o < sz; o += 4) h = mix64(h, *(const uint32_t*)(p + o));
+        break;
+      case 2:
+        for (int o = 0; o < sz; o += 2) h = mix64(h, *(const uint16_t*)(p + o));
+        break;
+      default:
+        for (int o = 0; o < sz; o++) h = mix64(h, p[o]);
+    }
+  }
+  h ^= h >> 32;
+  h *= 0xD6E8FEB86659FD93ull;
+  h ^= h >> 32;
+  return h;
+}
+
+__device__ __forceinline__ bool rows_equal(const KeyCols& kc, int64_t r1, int64_t r2) {
+  for (int c = 0; c < kc.ncols; c++) {
+    int sz = kc.itemsize[c];
+    const uint8_t* p = kc.ptr[c] + r1 * (int64_t)sz;
+    const uint8_t* q = kc.ptr[c] + r2 * (int64_t)sz;
+    switch (kc.chunk[c]) {
+      case 16:
+        for (int o = 0; o < sz; o += 16) {
+          uint4 a = *(const uint4*)(p + o), b = *(const uint4*)(q + o);
+          if (a.x != b.x || a.y != b.y || a.z != b.z || a.w != b.w) return false;
+        }
+        break;
+      case 8:
+        for (int o = 0; o < sz; o += 8)
+          if (*(const unsigned long long*)(p + o) != *(const unsigned long long*)(q + o)) return false;
+        break;
+      case 4:
+        for (int o = 0; o < sz; o += 4)
+          if (*(const uint32_t*)(p + o) != *(const uint32_t*)(q + o)) return false;
+        break;
+      case 2:
+        for (int o = 0; o < sz; o += 2)
+          if (*(const uint16_t*)(p + o) != *(const uint16_t*)(q + o)) return false;
+        break;
+      default:
+        for (int o = 0; o < sz; o++)
+          if (p[o] != q[o]) return false;
+    }
+  }
+  return true;
+}
+
+__device__ __forceinline__ Slot load_slot(const Slot* s) {
+  uint4 w = __ldcg((const uint4*)s);  // L2-coherent 128-bit read; other CTAs mutate slots concurrently
+  Slot r;
+  r.key = ((unsigned long long)w.y << 32) | w.x;
+  r.minrow = w.z;
+  r.nbin = w.w;
+  return r;
+}
+
+// A row landed on a provisional slot (or just claimed it): track the first row, return -(slot+1).
+__device__ __forceinline__ int32_t provisional(Slot* table, uint32_t idx, uint32_t row, uint32_t seen_minrow) {
+  if (row < seen_minrow) atomicMin(&table[idx].minrow, row);
+  return -(int32_t)(idx + 1);
+}
+
+__device__ __forceinline__ bool claim_new(GbCounters* ctr, uint32_t* newlist, uint32_t idx, uint32_t new_limit) {
+  uint32_t pos = atomicAdd(&ctr->newcount, 1u);
+  if (pos >= new_limit) {
+    ctr->abort = 1;
+    return false;
+  }
+  newlist[pos] = idx;
+  return true;
+}
+
+// ---- direct path -----------------------------------------------------------------------------
+// Resolve one key.  `first` is the slot already fetched for idx (memory-level parallelism: the caller
+// issues all its first probes before resolving any).
+__device__ __forceinline__ int32_t resolve_direct(Slot* table, uint32_t mask, unsigned long long key, uint32_t idx,
+                                                  Slot s, uint32_t row, uint32_t* newlist, GbCounters* ctr,
+                                                  uint32_t new_limit) {
+  if (key == kEmpty) {
+    // the one key that collides with the empty marker lives in the extra slot table[cap]
+    uint32_t sp = mask + 1;
+    Slot* ss = &table[sp];
+    Slot cur = load_slot(ss);
+    if (cur.bin()) return (int32_t)cur.bin();
+    if (cur.key == kEmpty) {
+      unsigned long long old = atomicCAS(&ss->key, kEmpty, 0ull);
+      if (old == kEmpty && !claim_new(ctr, newlist, sp, new_limit)) return 0;
+    }
+    return provisional(table, sp, row, cur.minrow);
+  }
+  for (uint32_t probes = 0; probes <= mask; probes++) {
+    if (s.key == key) {
+      if (s.bin()) return (int32_t)s.bin();
+      return provisional(table, idx, row, s.minrow);
+    }
+    if (s.key == kEmpty) {
+      unsigned long long old = atomicCAS(&table[idx].key, kEmpty, key);
+      if (old == kEmpty) {
+        if (!claim_new(ctr, newlist, idx, new_limit)) return 0;
+        return provisional(table, idx, row, 0xFFFFFFFFu);
+      }
+      if (old == key) return provisional(table, idx, row, 0xFFFFFFFFu);
+    }
+    idx = (idx + 1) & mask;
+    s = load_slot(&table[idx]);
+  }
+  ctr->abort = 1;  // table full (cannot happen while new_limit < capacity)
+  return 0;
+}
+
+template <int ISZ>
+__device__ __forceinline__ void load_keys4(const void* keys, int64_t r, unsigned long long k[4]) {
+  if (ISZ == 8) {
+    uint4 a = ld_stream_u4((const uint8_t*)keys + r * 8), b = ld_stream_u4((const uint8_t*)keys + r * 8 + 16);
+    k[0] = ((unsigned long long)a.y << 32) | a.x; k[1] = ((unsigned long long)a.w << 32) | a.z;
+    k[2] = ((unsigned long long)b.y << 32) | b.x; k[3] = ((unsigned long long)b.w << 32) | b.z;
+  } else if (ISZ == 4) {
+    uint4 a = ld_stream_u4((const uint8_t*)keys + r * 4);
+    k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w;
+  } else if (ISZ == 2) {
+    uint2 a = ld_stream_u2((const uint8_t*)keys + r * 2);
+    k[0] = a.x & 0xffff; k[1] = a.x >> 16; k[2] = a.y & 0xffff; k[3] = a.y >> 16;
+  } else {
+    uint32_t a = ld_stream_u32((const uint8_t*)keys + r);
+    k[0] = a & 0xff; k[1] = (a >> 8) & 0xff; k[2] = (a >> 16) & 0xff; k[3] = a >> 24;
+  }
+}
+template <int ISZ>
+__device__ __forceinline__ unsigned long long load_key1(const void* keys, int64_t r) {
+  if (ISZ == 8) return ((const unsigned long long*)keys)[r];
+  if (ISZ == 4) return ((const uint32_t*)keys)[r];
+  if (ISZ == 2) return ((const uint16_t*)keys)[r];
+  return ((const uint8_t*)keys)[r];
+}
+
+// One round of the direct path over rows [lo, hi).  lo is a multiple of 4; the key / filter / ikey
+// base pointers are 16-byte aligned for their 4-row vectors (checked on the host).
+template <int ISZ>
+__global__ void __launch_bounds__(256) gb_round_direct(const void* __restrict__ keys, const uint8_t* __restrict__ filter,
+                                                       int32_t* __restrict__ ikey, Slot* table, uint32_t mask,
+                                                       int64_t lo, int64_t hi, uint32_t* newlist, GbCounters* ctr,
+                                                       uint32_t new_limit) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t r = lo + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; r < hi; r += stride) {
+    if (r + 3 < hi) {
+      unsigned long long k[4];
+      load_keys4<ISZ>(keys, r, k);
+      uint32_t f = filter ? ld_stream_u32(filter + r) : 0x01010101u;
+      uint32_t idx[4];
+      Slot s[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) idx[i] = hash_u64(k[i]) & mask;
+#pragma unroll
+      for (int i = 0; i < 4; i++) s[i] = load_slot(&table[idx[i]]);
+      int32_t o[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        o[i] = ((f >> (8 * i)) & 0xff)
+                   ? resolve_direct(table, mask, k[i], idx[i], s[i], (uint32_t)(r + i), newlist, ctr, new_limit)
+                   : 0;
+      }
+      st_stream_u4(ikey + r, make_uint4((uint32_t)o[0], (uint32_t)o[1], (uint32_t)o[2], (uint32_t)o[3]));
+    } else {
+      for (int64_t q = r; q < hi; q++) {
+        int32_t o = 0;
+        if (!filter || filter[q]) {
+          unsigned long long k = load_key1<ISZ>(keys, q);
+          uint32_t idx = hash_u64(k) & mask;
+          o = resolve_direct(table, mask, k, idx, load_slot(&table[idx]), (uint32_t)q, newlist, ctr, new_limit);
+        }
+        ikey[q] = o;
+      }
+    }
+  }
+}
+
+// ---- byref path ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gb_round_byref(KeyCols kc, const uint8_t* __restrict__ filter,
+                                                      int32_t* __restrict__ ikey, Slot* table, uint32_t mask,
+                                                      int64_t lo, int64_t hi, uint32_t* newlist, GbCounters* ctr,
+                                                      uint32_t new_limit) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < hi; r += stride) {
+    if (filter && !filter[r]) {
+      ikey[r] = 0;
+      continue;
+    }
+    unsigned long long h = hash_row(kc, r);
+    uint32_t tag = (uint32_t)(h >> 32);
+    uint32_t idx = (uint32_t)h & mask;
+    unsigned long long mine = ((unsigned long long)tag << 32) | (uint32_t)r;
+    int32_t o = 0;
+    bool done = false;
+    for (uint32_t probes = 0; probes <= mask && !done; probes++) {
+      Slot s = load_slot(&table[idx]);
+      if (s.key == kEmpty) {
+        unsigned long long old = atomicCAS(&table[idx].key, kEmpty, mine);
+        if (old == kEmpty) {
+          o = claim_new(ctr, newlist, idx, new_limit) ? provisional(table, idx, (uint32_t)r, 0xFFFFFFFFu) : 0;
+          done = true;
+          break;
+        }
+        s.key = old;
+        s.minrow = 0xFFFFFFFFu;
+        s.nbin = 0xFFFFFFFFu;
+      }
+      if ((uint32_t)(s.key >> 32) == tag && rows_equal(kc, r, (int64_t)(uint32_t)s.key)) {
+        o = s.bin() ? (int32_t)s.bin() : provisional(table, idx, (uint32_t)r, s.minrow);
+        done = true;
+        break;
+      }
+      idx = (idx + 1) & mask;
+    }
+    if (!done) ctr->abort = 1;
+    ikey[r] = o;
+  }
+}
+
+// ---- per-round finalisation --------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gb_mark_firstrows(const Slot* table, const uint32_t* newlist,
+                                                         const GbCounters* ctr, int64_t lo, uint32_t* bitmap) {
+  uint32_t n = ctr->newcount;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    uint32_t m = table[newlist[j]].minrow - (uint32_t)lo;
+    atomicOr(&bitmap[m >> 5], 1u << (m & 31));
+  }
+}
+
+__global__ void __launch_bounds__(256) gb_assign_bins(Slot* table, const uint32_t* newlist, const GbCounters* ctr,
+                                                      int64_t lo, const uint32_t* bitmap, const uint32_t* prefix,
+                                                      uint32_t ubase, int32_t* ifirstkey, int64_t ifirst_sub) {
+  uint32_t n = ctr->newcount;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    uint32_t sidx = newlist[j];
+    uint32_t row = table[sidx].minrow;
+    uint32_t m = row - (uint32_t)lo;
+    uint32_t rank = prefix[m >> 5] + __popc(bitmap[m >> 5] & ((1u << (m & 31)) - 1u));
+    uint32_t bin = ubase + rank + 1;
+    table[sidx].nbin = ~bin;
+    ifirstkey[bin - 1] = (int32_t)((int64_t)row - ifirst_sub);
+  }
+}
+
+__global__ void __launch_bounds__(256) gb_fixup(int32_t* __restrict__ ikey, const Slot* __restrict__ table, int64_t lo,
+                                                int64_t hi, int32_t bin_sub) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t r = lo + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; r < hi; r += stride) {
+    if (r + 3 < hi) {
+      int4 v = *(const int4*)(ikey + r);
+      int32_t o[4] = {v.x, v.y, v.z, v.w};
+      bool any = false;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        if (o[i] < 0) {
+          o[i] = (int32_t)table[-(o[i] + 1)].bin() - bin_sub;
+          any = true;
+        } else if (bin_sub && o[i] > 0) {
+          o[i] -= bin_sub;
+          any = true;
+        }
+      }
+      if (any) *(int4*)(ikey + r) = make_int4(o[0], o[1], o[2], o[3]);
+    } else {
+      for (int64_t q = r; q < hi; q++) {
+        int32_t v = ikey[q];
+        if (v < 0) ikey[q] = (int32_t)table[-(v + 1)].bin() - bin_sub;
+        else if (bin_sub && v > 0) ikey[q] = v - bin_sub;
+      }
+    }
+  }
+}
+
+// ---- resize: stage finalised entries, clear, reinsert --------------------------------------------
+__global__ void __launch_bounds__(256) gb_stage_entries(const Slot* table, uint32_t nslots, Slot* staged, GbCounters* ctr) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nslots; i += gridDim.x * blockDim.x) {
+    Slot s = table[i];
+    if (s.bin()) {
+      if (i == nslots - 1) s.key = kEmpty;  // the extra slot holds the key that equals the empty marker
+      staged[atomicAdd(&ctr->total, 1u)] = s;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) gb_reinsert_direct(Slot* table, uint32_t mask, const Slot* staged, uint32_t n) {
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    Slot s = staged[j];
+    if (s.key == kEmpty) {
+      s.key = 0;
+      table[mask + 1] = s;
+      continue;
+    }
+    uint32_t idx = hash_u64(s.key) & mask;
+    while (atomicCAS(&table[idx].key, kEmpty, s.key) != kEmpty) idx = (idx + 1) & mask;
+    table[idx].minrow = s.minrow;
+    table[idx].nbin = s.nbin;
+  }
+}
+
+__global__ void __launch_bounds__(256) gb_reinsert_byref(KeyCols kc, Slot* table, uint32_t mask, const Slot* staged,
+                                                         uint32_t n) {
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    Slot s = staged[j];
+    unsigned long long h = hash_row(kc, (int64_t)(uint32_t)s.key);
+    uint32_t idx = (uint32_t)h & mask;
+    while (atomicCAS(&table[idx].key, kEmpty, s.key) != kEmpty) idx = (idx + 1) & mask;
+    table[idx].minrow = s.minrow;
+    table[idx].nbin = s.nbin;
+  }
+}
+
+__global__ void __launch_bounds__(256) gb_fill_partition_ids(int32_t* pid, int64_t n, const int64_t* cutoffs, int ncut) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+    int lo = 0, hi = ncut;  // first cutoff > r
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (cutoffs[mid] > r) hi = mid; else lo = mid + 1;
+    }
+    pid[r] = lo;
+  }
+}
+
+__global__ void __launch_bounds__(256) gb_count_partition_uniques(const int32_t* ifirstkey, int64_t U, const int32_t* pid,
+                                                                  uint32_t* ucount) {
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < U; b += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(&ucount[pid[ifirstkey[b]]], 1u);
+}
+__global__ void __launch_bounds__(256) gb_relative_firstkeys(int32_t* ifirstkey, int64_t U, const int32_t* pid,
+                                                             const int64_t* cutoffs) {
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < U; b += (int64_t)gridDim.x * blockDim.x) {
+    int32_t row = ifirstkey[b];
+    int32_t p = pid[row];
+    ifirstkey[b] = row - (int32_t)(p ? cutoffs[p - 1] : 0);
+  }
+}
+__global__ void __launch_bounds__(256) gb_renumber_partitions(int32_t* ikey, int64_t n, const int32_t* pid,
+                                                              const uint32_t* ubase) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    int32_t v = ikey[r];
+    if (v > 0) ikey[r] = v - (int32_t)ubase[pid[r]];
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+static uint32_t next_pow2_u64(uint64_t v) {
+  uint64_t p = 1;
+  while (p < v) p <<= 1;
+  return (uint32_t)(p > (1ull << 30) ? (1ull << 30) : p);
+}
+
+struct GbPlan {
+  int64_t round0;
+  double load_target;  // table sized so projected uniques / capacity <= this
+  double load_abort;   // a round aborts when uniques / capacity would exceed this
+  int ratio;
+};
+
+static GbPlan get_plan() {
+  GbPlan p{1 << 20, 0.5, 0.75, 4};
+  if (const char* e = getenv("RTB_GB_ROUND0")) p.round0 = atoll(e);
+  if (const char* e = getenv("RTB_GB_LOAD")) p.load_target = atof(e);
+  if (const char* e = getenv("RTB_GB_RATIO")) p.ratio = atoi(e);
+  if (p.round0 < 1024) p.round0 = 1024;
+  p.round0 &= ~1023ll;
+  if (p.ratio < 2) p.ratio = 2;
+  return p;
+}
+
+static uint32_t cap_max_for(int64_t max_unique) { return next_pow2_u64((uint64_t)(2.0 * (double)max_unique) + 1024); }
+
+struct GbLayout {
+  Slot* table;
+  Slot* staged;       // max_unique slots; aliased by newlist during rounds
+  uint32_t* bitmap;   // words for the largest round
+  uint32_t* prefix;
+  uint32_t* scan_scratch;
+  GbCounters* ctr;
+  int32_t* pid;       // partition ids (cutoffs only)
+  int64_t* cutoffs_dev;
+  uint32_t* ucount;   // per-partition unique counts, then exclusive bases
+  size_t bytes;
+};
+
+static int64_t largest_round(int64_t n, const GbPlan& p) {
+  int64_t lo = 0, hi = p.round0 < n ? p.round0 : n, best = hi;
+  while (hi < n) {
+    lo = hi;
+    int64_t nh = hi * p.ratio;
+    hi = nh < n ? nh : n;
+    if (hi - lo > best) best = hi - lo;
+  }
+  return best;
+}
+
+static GbLayout layout(void* ws, size_t wsbytes, int64_t nrows, int64_t max_unique, bool cutoffs, int64_t ncut) {
+  GbPlan p = get_plan();
+  Arena a(ws, wsbytes);
+  GbLayout L;
+  uint32_t capmax = cap_max_for(max_unique);
+  L.table = a.take<Slot>((size_t)capmax + 1);
+  L.staged = a.take<Slot>((size_t)max_unique + 1);
+  int64_t words = (largest_round(nrows, p) + 31) / 32 + 1;
+  L.bitmap = a.take<uint32_t>((size_t)words);
+  L.prefix = a.take<uint32_t>((size_t)words);
+  L.scan_scratch = a.take<uint32_t>(scan_u32_workspace_elems(words));
+  L.ctr = a.take<GbCounters>(1);
+  L.pid = cutoffs ? a.take<int32_t>((size_t)nrows) : nullptr;
+  L.cutoffs_dev = cutoffs ? a.take<int64_t>((size_t)ncut) : nullptr;
+  L.ucount = cutoffs ? a.take<uint32_t>((size_t)ncut) : nullptr;
+  L.bytes = a.off;
+  return L;
+}
+
+}  // namespace rtb
+
+using namespace rtb;
+
+extern "C" size_t rtb_groupby_workspace_bytes(int64_t nrows, int64_t max_unique, int nkeys, int has_cutoffs) {
+  (void)nkeys;
+  if (nrows < 0 || max_unique < 0) return 0;
+  GbLayout L = layout(nullptr, 0, nrows, max_unique, has_cutoffs != 0, has_cutoffs ? nrows : 0);
+  return L.bytes + 256;
+}
+
+static int chunk_for(const void* base, int itemsize) {
+  for (int c = 16; c > 1; c >>= 1)
+    if (itemsize % c == 0 && ((uintptr_t)base % c) == 0) return c;
+  return 1;
+}
+
+extern "C" int rtb_multikey_groupby32(const rtb_column* keys, int nkeys, int64_t nrows, int64_t hint_size,
+                                      const uint8_t* filter, const int64_t* cutoffs_host, int64_t ncutoffs,
+                                      int32_t* ikey_out, int32_t* ifirstkey_out, int64_t max_unique,
+                                      int64_t* unique_count_host, int64_t* ucutoffs_host, int64_t* needed_unique_host,
+                                      void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  (void)hint_size;  // the shim folds hint_size into max_unique; the table itself is sized adaptively
+  RTB_ARG(keys && nkeys >= 1, "MultiKeyGroupBy32: first argument is not a list of arrays");
+  RTB_ARG(nkeys <= kMaxKeyCols - 1, "MultiKeyGroupBy32: at most %d key columns", kMaxKeyCols - 1);
+  RTB_ARG(nrows >= 0 && nrows <= 2147483646ll, "MultiKeyGroupBy32: row count out of range for int32 iKey");
+  RTB_ARG(unique_count_host, "MultiKeyGroupBy32: null unique_count");
+  *unique_count_host = 0;
+  if (needed_unique_host) *needed_unique_host = 0;
+  if (nrows == 0) return RTB_OK;
+  RTB_ARG(ikey_out && ifirstkey_out && max_unique >= 1, "MultiKeyGroupBy32: null output");
+  RTB_ARG(((uintptr_t)ikey_out % 16) == 0, "MultiKeyGroupBy32: iKey buffer must be 16-byte aligned");
+  for (int c = 0; c < nkeys; c++) RTB_ARG(keys[c].data && keys[c].itemsize >= 1, "MultiKeyGroupBy32: bad key column %d", c);
+  bool has_cut = cutoffs_host != nullptr && ncutoffs > 0;
+  if (has_cut) {
+    RTB_ARG(cutoffs_host[ncutoffs - 1] == nrows, "MultiKeyGroupBy32: last cutoff must equal the row count");
+    for (int64_t i = 1; i < ncutoffs; i++)
+      RTB_ARG(cutoffs_host[i] >= cutoffs_host[i - 1], "MultiKeyGroupBy32: cutoffs must be non-decreasing");
+  }
+  if (max_unique > nrows) max_unique = nrows;
+
+  GbPlan plan = get_plan();
+  GbLayout L = layout(workspace, workspace_bytes, nrows, max_unique, has_cut, ncutoffs);
+  RTB_ARG(workspace && L.bytes <= workspace_bytes, "MultiKeyGroupBy32: workspace too small (%zu < %zu)",
+          workspace_bytes, L.bytes);
+  const uint32_t capmax = cap_max_for(max_unique);
+  uint32_t* newlist = (uint32_t*)L.staged;
+
+  // key layout
+  bool direct = !has_cut && nkeys == 1 && (keys[0].itemsize == 1 || keys[0].itemsize == 2 || keys[0].itemsize == 4 ||
+                                           keys[0].itemsize == 8) &&
+                ((uintptr_t)keys[0].data % (4 * keys[0].itemsize)) == 0 && (!filter || ((uintptr_t)filter % 4) == 0);
+  KeyCols kc;
+  memset(&kc, 0, sizeof(kc));
+  kc.ncols = nkeys;
+  for (int c = 0; c < nkeys; c++) {
+    kc.ptr[c] = (const uint8_t*)keys[c].data;
+    kc.itemsize[c] = keys[c].itemsize;
+    kc.chunk[c] = chunk_for(keys[c].data, keys[c].itemsize);
+  }
+  if (has_cut) {
+    // cutoffs == an extra leading key column holding the partition id (tests/test_pgroupby.py:27-41)
+    RTB_CUDA(cudaMemcpyAsync(L.cutoffs_dev, cutoffs_host, sizeof(int64_t) * ncutoffs, cudaMemcpyHostToDevice, stream));
+    gb_fill_partition_ids<<<grid_for(nrows, 256, 1), 256, 0, stream>>>(L.pid, nrows, L.cutoffs_dev, (int)ncutoffs);
+    RTB_LAUNCH_CHECK();
+    kc.ptr[nkeys] = (const uint8_t*)L.pid;
+    kc.itemsize[nkeys] = 4;
+    kc.chunk[nkeys] = 4;
+    kc.ncols = nkeys + 1;
+  }
+
+  uint32_t cap = 0;
+  int64_t U = 0;
+  int64_t prev_new = 0, prev_rows = 0;
+  int64_t lo = 0;
+  int round = 0;
+  while (lo < nrows) {
+    int64_t hi = round == 0 ? plan.round0 : lo * plan.ratio;
+    if (hi > nrows || hi <= lo) hi = nrows;
+    int64_t rows = hi - lo;
+    // projected new keys in this round: discovery rate of the previous round, never above the row count
+    double proj = round == 0 ? (double)rows : (double)prev_new * ((double)rows / (double)prev_rows) * 1.25 + 64;
+    if (proj > (double)rows) proj = (double)rows;
+    if (proj > (double)(max_unique - U)) proj = (double)(max_unique - U);
+    uint32_t want = next_pow2_u64((uint64_t)ceil(((double)U + proj) / plan.load_target));
+    if (want < 1024) want = 1024;
+    if (want > capmax) want = capmax;
+
+    for (;;) {  // attempt loop: (re)size, run the round, grow on abort
+      if (want != cap) {
+        uint32_t staged_n = 0;
+        if (cap != 0 && U > 0) {
+          RTB_CUDA(cudaMemsetAsync(L.ctr, 0, sizeof(GbCounters), stream));
+          gb_stage_entries<<<grid_for((int64_t)cap + 1, 256, 1), 256, 0, stream>>>(L.table, cap + 1, L.staged, L.ctr);
+          RTB_LAUNCH_CHECK();
+          staged_n = (uint32_t)U;
+        }
+        RTB_CUDA(cudaMemsetAsync(L.table, 0xFF, sizeof(Slot) * ((size_t)want + 1), stream));
+        if (staged_n) {
+          if (direct)
+            gb_reinsert_direct<<<grid_for(staged_n, 256, 1), 256, 0, stream>>>(L.table, want - 1, L.staged, staged_n);
+          else
+            gb_reinsert_byref<<<grid_for(staged_n, 256, 1), 256, 0, stream>>>(kc, L.table, want - 1, L.staged, staged_n);
+          RTB_LAUNCH_CHECK();
+        }
+        cap = want;
+      }
+      int64_t room = (int64_t)((double)cap * plan.load_abort) - U;
+      if (room > max_unique - U) room = max_unique - U;
+      if (room < 0) room = 0;
+      uint32_t new_limit = (uint32_t)(room > 0xFFFFFFF0ll ? 0xFFFFFFF0ll : room);
+      RTB_CUDA(cudaMemsetAsync(L.ctr, 0, sizeof(GbCounters), stream));
+      uint32_t mask = cap - 1;
+      if (direct) {
+        int grid = grid_for(rows, 256, 4, 8);
+        switch (keys[0].itemsize) {
+          case 8: gb_round_direct<8><<<grid, 256, 0, stream>>>(keys[0].data, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit); break;
+          case 4: gb_round_direct<4><<<grid, 256, 0, stream>>>(keys[0].data, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit); break;
+          case 2: gb_round_direct<2><<<grid, 256, 0, stream>>>(keys[0].data, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit); break;
+          default: gb_round_direct<1><<<grid, 256, 0, stream>>>(keys[0].data, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit);
+        }
+      } else {
+        gb_round_byref<<<grid_for(rows, 256, 1, 8), 256, 0, stream>>>(kc, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit);
+      }
+      RTB_LAUNCH_CHECK();
+      GbCounters h;
+      RTB_CUDA(cudaMemcpyAsync(&h, L.ctr, sizeof(h), cudaMemcpyDeviceToHost, stream));
+      RTB_CUDA(cudaStreamSynchronize(stream));
+      if (!h.abort) {
+        prev_new = h.newcount;
+        break;
+      }
+      // out of room: grow 4x (provisional entries are dropped by the re-stage) or ask for more workspace
+      if (cap >= capmax) {
+        double seen = (double)(lo > 0 ? lo : 1);
+        double est = (double)(U + room + 1) * ((double)nrows / seen);
+        if (est > (double)nrows) est = (double)nrows;
+        if (est < 4.0 * (double)max_unique) est = 4.0 * (double)max_unique;
+        if (est > (double)nrows) est = (double)nrows;
+        if (needed_unique_host) *needed_unique_host = (int64_t)est;
+        set_error("MultiKeyGroupBy32: more than %lld unique keys; retry with max_unique >= %lld", (long long)max_unique,
+                  (long long)est);
+        return RTB_ERR_WORKSPACE;
+      }
+      uint64_t g = (uint64_t)cap * 4;
+      want = g > capmax ? capmax : (uint32_t)g;
+    }
+
+    if (prev_new > 0) {
+      int64_t words = (rows + 31) / 32;
+      RTB_CUDA(cudaMemsetAsync(L.bitmap, 0, sizeof(uint32_t) * words, stream));
+      gb_mark_firstrows<<<grid_for(prev_new, 256, 1), 256, 0, stream>>>(L.table, newlist, L.ctr, lo, L.bitmap);
+      RTB_LAUNCH_CHECK();
+      int rc = exclusive_scan_u32(L.bitmap, L.prefix, words, SCAN_POPC, L.scan_scratch, nullptr, stream);
+      if (rc != RTB_OK) return rc;
+      gb_assign_bins<<<grid_for(prev_new, 256, 1), 256, 0, stream>>>(L.table, newlist, L.ctr, lo, L.bitmap, L.prefix,
+                                                                    (uint32_t)U, ifirstkey_out, 0);
+      RTB_LAUNCH_CHECK();
+      gb_fixup<<<grid_for(rows, 256, 4), 256, 0, stream>>>(ikey_out, L.table, lo, hi, 0);
+      RTB_LAUNCH_CHECK();
+      U += prev_new;
+    }
+    prev_rows = rows;
+    lo = hi;
+    round++;
+  }
+
+  if (has_cut) {
+    // global bins -> numbering that restarts per partition; iFirstKey -> partition-relative rows.
+    // Bins are in first-appearance order and partitions are contiguous row ranges, so partition p
+    // owns the contiguous bin range [ubase[p], ubase[p+1]).
+    RTB_CUDA(cudaMemsetAsync(L.ucount, 0, sizeof(uint32_t) * ncutoffs, stream));
+    if (U > 0) {
+      gb_count_partition_uniques<<<grid_for(U, 256, 1), 256, 0, stream>>>(ifirstkey_out, U, L.pid, L.ucount);
+      RTB_LAUNCH_CHECK();
+    }
+    uint32_t* hc = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)ncutoffs);
+    if (!hc) { set_error("out of host memory"); return RTB_ERR_ARG; }
+    cudaError_t e = cudaMemcpyAsync(hc, L.ucount, sizeof(uint32_t) * ncutoffs, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    uint32_t run = 0;
+    for (int64_t p = 0; p < ncutoffs && e == cudaSuccess; p++) {
+      uint32_t c = hc[p];
+      hc[p] = run;
+      run += c;
+      if (ucutoffs_host) ucutoffs_host[p] = run;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(L.ucount, hc, sizeof(uint32_t) * ncutoffs, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    free(hc);
+    RTB_CUDA(e);
+    if (U > 0) {
+      gb_relative_firstkeys<<<grid_for(U, 256, 1), 256, 0, stream>>>(ifirstkey_out, U, L.pid, L.cutoffs_dev);
+      RTB_LAUNCH_CHECK();
+    }
+    gb_renumber_partitions<<<grid_for(nrows, 256, 1), 256, 0, stream>>>(ikey_out, nrows, L.pid, L.ucount);
+    RTB_LAUNCH_CHECK();
+  }
+
+  RTB_CUDA(cudaStreamSynchronize(stream));
+  *unique_count_host = U;
+  return RTB_OK;
+}

@@ -1,0 +1,435 @@
+// a5 / a6: per-bin reductions (rc.GroupByAll32, riptable/rt_numpy.py:1871) and rc.BinCount.
+//
+// One streaming pass over (iKey, value) rows — 4 rows per thread through 128-bit loads — and one
+// accumulator update per row.  Two accumulator placements:
+//   * low cardinality  (bins <= kSmemBins): block-private accumulators in shared memory, flushed with
+//     one global atomic per touched bin per block;
+//   * high cardinality: accumulators in global memory; with ~1M bins they are L2-resident, so the
+//     kernel's HBM traffic stays at the algorithmic iKey + value bytes per row.
+// Accumulation domains: float sums in f64 (f32 columns are rounded once at the end), integer sums in
+// 64-bit wrap-around, min/max in an order-preserving uint64 code so one atomicMin/atomicMax serves
+// every dtype; var/std are two-pass (mean, then squared deviations; ddof = 1).
+// Invalid handling (riptable/tests/test_groupbyops.py:389-456): nan-ops skip NaN / integer sentinels;
+// plain min/max propagate them through a per-bin flag.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace rtb {
+
+constexpr int64_t kSmemBins = 3584;  // 13 B/bin keeps the CTA under the 48 KB default dynamic smem limit
+
+enum AccOp { OP_SUMF = 0, OP_SUMI = 1, OP_MEAN = 2, OP_MINMAX = 3, OP_M2 = 4, OP_COUNT = 5 };
+
+struct AccumArgs {
+  const void* values;
+  const void* ikey;
+  int vdt, kdt;
+  int64_t n, lo, hi, nb;
+  int nanskip, ismax;
+  unsigned long long* acc;  // f64 bits / u64 / ordered code, per bin
+  uint32_t* cnt;
+  const double* mean;
+  uint8_t* flags;
+};
+
+// ---- raw value access ---------------------------------------------------------------------------
+__device__ __forceinline__ void load_raw4(const void* p, int sz, int64_t r, unsigned long long v[4]) {
+  if (sz == 8) {
+    uint4 a = ld_stream_u4((const uint8_t*)p + r * 8), b = ld_stream_u4((const uint8_t*)p + r * 8 + 16);
+    v[0] = ((unsigned long long)a.y << 32) | a.x; v[1] = ((unsigned long long)a.w << 32) | a.z;
+    v[2] = ((unsigned long long)b.y << 32) | b.x; v[3] = ((unsigned long long)b.w << 32) | b.z;
+  } else if (sz == 4) {
+    uint4 a = ld_stream_u4((const uint8_t*)p + r * 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  } else if (sz == 2) {
+    uint2 a = ld_stream_u2((const uint8_t*)p + r * 2);
+    v[0] = a.x & 0xffff; v[1] = a.x >> 16; v[2] = a.y & 0xffff; v[3] = a.y >> 16;
+  } else {
+    uint32_t a = ld_stream_u32((const uint8_t*)p + r);
+    v[0] = a & 0xff; v[1] = (a >> 8) & 0xff; v[2] = (a >> 16) & 0xff; v[3] = a >> 24;
+  }
+}
+__device__ __forceinline__ unsigned long long load_raw1(const void* p, int sz, int64_t r) {
+  if (sz == 8) return ((const unsigned long long*)p)[r];
+  if (sz == 4) return ((const uint32_t*)p)[r];
+  if (sz == 2) return ((const uint16_t*)p)[r];
+  return ((const uint8_t*)p)[r];
+}
+__device__ __forceinline__ int dsize(int dt) {
+  return dt <= RTB_U8 ? 1 : dt <= RTB_U16 ? 2 : (dt <= RTB_U32 || dt == RTB_F32) ? 4 : 8;
+}
+
+__device__ __forceinline__ bool raw_invalid(unsigned long long raw, int dt) {
+  switch (dt) {
+    case RTB_F64: return (raw & 0x7FFFFFFFFFFFFFFFull) > 0x7FF0000000000000ull;
+    case RTB_F32: return ((uint32_t)raw & 0x7FFFFFFFu) > 0x7F800000u;
+    case RTB_I8: return raw == 0x80ull;
+    case RTB_U8: return raw == 0xFFull;
+    case RTB_I16: return raw == 0x8000ull;
+    case RTB_U16: return raw == 0xFFFFull;
+    case RTB_I32: return raw == 0x80000000ull;
+    case RTB_U32: return raw == 0xFFFFFFFFull;
+    case RTB_I64: return raw == 0x8000000000000000ull;
+    case RTB_U64: return raw == ~0ull;
+    default: return false;  // bool has no invalid
+  }
+}
+__device__ __forceinline__ long long raw_to_i64(unsigned long long raw, int dt) {
+  switch (dt) {
+    case RTB_BOOL: return raw != 0;
+    case RTB_I8: return (int8_t)raw;
+    case RTB_I16: return (int16_t)raw;
+    case RTB_I32: return (int32_t)raw;
+    default: return (long long)raw;  // unsigned types are already zero-extended; 64-bit as is
+  }
+}
+__device__ __forceinline__ double raw_to_f64(unsigned long long raw, int dt) {
+  switch (dt) {
+    case RTB_F64: return __longlong_as_double((long long)raw);
+    case RTB_F32: return (double)__uint_as_float((uint32_t)raw);
+    case RTB_U64: return (double)raw;
+    case RTB_U8: case RTB_U16: case RTB_U32: return (double)(long long)raw;
+    default: return (double)raw_to_i64(raw, dt);
+  }
+}
+// Order-preserving code with both ends of the uint64 range left free for the "empty" identity.
+__device__ __forceinline__ unsigned long long raw_to_code(unsigned long long raw, int dt, int ismax) {
+  switch (dt) {
+    case RTB_F64: return (raw >> 63) ? ~raw : (raw | 0x8000000000000000ull);
+    case RTB_F32: {
+      uint32_t u = (uint32_t)raw;
+      u = (u >> 31) ? ~u : (u | 0x80000000u);
+      return (unsigned long long)u + (1ull << 32);
+    }
+    case RTB_I64: {
+      unsigned long long c = raw ^ 0x8000000000000000ull;  // sentinel (c == 0) never reaches here
+      return ismax ? c : c - 1;
+    }
+    case RTB_U64: return ismax ? raw + 1 : raw;  // sentinel (~0) never reaches here
+    case RTB_BOOL: return (raw != 0) + 1ull;
+    case RTB_U8: case RTB_U16: case RTB_U32: return raw + 1;
+    default: return (unsigned long long)raw_to_i64(raw, dt) ^ 0x8000000000000000ull;
+  }
+}
+__device__ __forceinline__ unsigned long long code_to_raw(unsigned long long c, int dt, int ismax) {
+  switch (dt) {
+    case RTB_F64: return (c >> 63) ? (c & 0x7FFFFFFFFFFFFFFFull) : ~c;
+    case RTB_F32: {
+      uint32_t u = (uint32_t)(c - (1ull << 32));
+      return (u >> 31) ? (u & 0x7FFFFFFFu) : (uint32_t)~u;
+    }
+    case RTB_I64: return (ismax ? c : c + 1) ^ 0x8000000000000000ull;
+    case RTB_U64: return ismax ? c - 1 : c;
+    case RTB_BOOL: case RTB_U8: case RTB_U16: case RTB_U32: return c - 1;
+    default: return c ^ 0x8000000000000000ull;
+  }
+}
+__device__ __forceinline__ unsigned long long invalid_raw(int dt) {
+  switch (dt) {
+    case RTB_F64: return 0x7FF8000000000000ull;
+    case RTB_F32: return 0x7FC00000ull;
+    case RTB_I8: return 0x80ull;
+    case RTB_U8: return 0xFFull;
+    case RTB_I16: return 0x8000ull;
+    case RTB_U16: return 0xFFFFull;
+    case RTB_I32: return 0x80000000ull;
+    case RTB_U32: return 0xFFFFFFFFull;
+    case RTB_I64: return 0x8000000000000000ull;
+    case RTB_U64: return ~0ull;
+    default: return 0;
+  }
+}
+__device__ __forceinline__ void store_raw(void* p, int dt, int64_t i, unsigned long long raw) {
+  switch (dsize(dt)) {
+    case 1: ((uint8_t*)p)[i] = (uint8_t)raw; break;
+    case 2: ((uint16_t*)p)[i] = (uint16_t)raw; break;
+    case 4: ((uint32_t*)p)[i] = (uint32_t)raw; break;
+    default: ((unsigned long long*)p)[i] = raw;
+  }
+}
+
+// ---- one row's accumulator update (works on global or shared accumulators) -------------------------
+template <int OP>
+__device__ __forceinline__ void accumulate(const AccumArgs& a, unsigned long long* acc, uint32_t* cnt, uint8_t* flags,
+                                           int64_t b, unsigned long long raw) {
+  if (OP == OP_COUNT) {
+    atomicAdd(&cnt[b], 1u);
+    return;
+  }
+  bool inv = raw_invalid(raw, a.vdt);
+  if (OP == OP_MINMAX) {
+    if (inv) {
+      if (!a.nanskip) flags[b] = 1;  // benign race: every writer stores 1
+      return;
+    }
+    unsigned long long c = raw_to_code(raw, a.vdt, a.ismax);
+    if (a.ismax) atomicMax(&acc[b], c); else atomicMin(&acc[b], c);
+    return;
+  }
+  if (a.nanskip && inv) return;
+  if (OP == OP_SUMI) {
+    atomicAdd(&acc[b], (unsigned long long)raw_to_i64(raw, a.vdt));
+  } else if (OP == OP_SUMF) {
+    atomicAdd((double*)&acc[b], raw_to_f64(raw, a.vdt));
+  } else if (OP == OP_MEAN) {
+    atomicAdd((double*)&acc[b], raw_to_f64(raw, a.vdt));
+    atomicAdd(&cnt[b], 1u);
+  } else if (OP == OP_M2) {
+    double d = raw_to_f64(raw, a.vdt) - __ldg(&a.mean[b]);
+    atomicAdd((double*)&acc[b], d * d);
+  }
+}
+
+template <int OP>
+__device__ __forceinline__ unsigned long long acc_identity(int ismax) {
+  return OP == OP_MINMAX ? (ismax ? 0ull : ~0ull) : 0ull;
+}
+
+template <int OP, bool SMEM>
+__global__ void __launch_bounds__(256) accum_kernel(AccumArgs a) {
+  extern __shared__ unsigned long long smem_raw[];
+  unsigned long long* acc = a.acc;
+  uint32_t* cnt = a.cnt;
+  uint8_t* flags = a.flags;
+  if (SMEM) {
+    acc = smem_raw;
+    cnt = (uint32_t*)(smem_raw + a.nb);
+    flags = (uint8_t*)(cnt + a.nb);
+    for (int64_t i = threadIdx.x; i < a.nb; i += blockDim.x) {
+      acc[i] = acc_identity<OP>(a.ismax);
+      cnt[i] = 0;
+      flags[i] = 0;
+    }
+    __syncthreads();
+  }
+  const int vsz = OP == OP_COUNT ? 0 : dsize(a.vdt);
+  int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; r < a.n; r += stride) {
+    if (r + 3 < a.n) {
+      int64_t k[4];
+      unsigned long long v[4] = {0, 0, 0, 0};
+      load_ikey4(a.ikey, a.kdt, r, k);
+      if (OP != OP_COUNT) load_raw4(a.values, vsz, r, v);
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        if (k[i] >= a.lo && k[i] < a.hi) accumulate<OP>(a, acc, cnt, flags, k[i], v[i]);
+    } else {
+      for (int64_t q = r; q < a.n; q++) {
+        int64_t k = load_ikey(a.ikey, a.kdt, q);
+        if (k >= a.lo && k < a.hi)
+          accumulate<OP>(a, acc, cnt, flags, k, OP == OP_COUNT ? 0ull : load_raw1(a.values, vsz, q));
+      }
+    }
+  }
+  if (SMEM) {
+    __syncthreads();
+    for (int64_t i = threadIdx.x; i < a.nb; i += blockDim.x) {
+      unsigned long long v = acc[i];
+      uint32_t c = cnt[i];
+      if (OP == OP_COUNT) {
+        if (c) atomicAdd(&a.cnt[i], c);
+      } else if (OP == OP_MINMAX) {
+        if (v != acc_identity<OP>(a.ismax)) {
+          if (a.ismax) atomicMax(&a.acc[i], v); else atomicMin(&a.acc[i], v);
+        }
+        if (flags[i]) a.flags[i] = 1;
+      } else if (OP == OP_SUMI) {
+        if (v) atomicAdd(&a.acc[i], v);
+      } else {
+        // float domains: a bin is touched iff its shared value differs from +0.0 or (mean) its count is > 0
+        if (OP == OP_MEAN) {
+          if (c) {
+            atomicAdd((double*)&a.acc[i], __longlong_as_double((long long)v));
+            atomicAdd(&a.cnt[i], c);
+          }
+        } else if (v != 0ull) {
+          atomicAdd((double*)&a.acc[i], __longlong_as_double((long long)v));
+        }
+      }
+    }
+  }
+}
+
+// ---- finalisation ----------------------------------------------------------------------------------
+enum FinKind { FIN_CAST_F32 = 0, FIN_MEAN = 1, FIN_MINMAX = 2, FIN_VAR = 3, FIN_STD = 4, FIN_MEAN_KEEP = 5 };
+
+__global__ void __launch_bounds__(256) finalize_kernel(int kind, int vdt, int ismax, int64_t nb, int64_t lo, int64_t hi,
+                                                       const unsigned long long* acc, const uint32_t* cnt,
+                                                       const uint8_t* flags, void* out, double* mean_out) {
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (int64_t)gridDim.x * blockDim.x) {
+    bool inrange = b >= lo && b < hi;
+    const double nan = __longlong_as_double(0x7FF8000000000000ll);
+    switch (kind) {
+      case FIN_CAST_F32:
+        ((float*)out)[b] = inrange ? (float)__longlong_as_double((long long)acc[b]) : 0.0f;
+        break;
+      case FIN_MEAN:
+      case FIN_MEAN_KEEP: {
+        double m = (inrange && cnt[b]) ? __longlong_as_double((long long)acc[b]) / (double)cnt[b] : nan;
+        if (kind == FIN_MEAN) ((double*)out)[b] = m; else mean_out[b] = m;
+        break;
+      }
+      case FIN_MINMAX: {
+        unsigned long long c = acc[b];
+        unsigned long long ident = ismax ? 0ull : ~0ull;
+        unsigned long long raw = (!inrange || flags[b] || c == ident) ? invalid_raw(vdt) : code_to_raw(c, vdt, ismax);
+        store_raw(out, vdt, b, raw);
+        break;
+      }
+      default: {  // FIN_VAR / FIN_STD, ddof = 1
+        double v = (inrange && cnt[b] >= 2) ? __longlong_as_double((long long)acc[b]) / (double)(cnt[b] - 1) : nan;
+        ((double*)out)[b] = kind == FIN_STD ? sqrt(v) : v;
+      }
+    }
+  }
+}
+
+struct RedLayout {
+  unsigned long long* acc;
+  uint32_t* cnt;
+  double* mean;
+  uint8_t* flags;
+  size_t bytes;
+};
+static RedLayout red_layout(void* ws, size_t n, int64_t nb) {
+  Arena a(ws, n);
+  RedLayout L;
+  L.acc = a.take<unsigned long long>((size_t)nb);
+  L.cnt = a.take<uint32_t>((size_t)nb);
+  L.mean = a.take<double>((size_t)nb);
+  L.flags = a.take<uint8_t>((size_t)nb);
+  L.bytes = a.off;
+  return L;
+}
+
+template <int OP>
+static int launch_accum(const AccumArgs& a, cudaStream_t stream) {
+  if (a.n <= 0) return RTB_OK;
+  if (a.nb <= kSmemBins) {
+    size_t smem = (size_t)a.nb * (8 + 4 + 1) + 16;
+    // enough CTAs to fill the machine, few enough that the per-CTA flush stays negligible
+    int grid = grid_for(a.n, 256, 4 * 8, 4);
+    accum_kernel<OP, true><<<grid, 256, smem, stream>>>(a);
+  } else {
+    accum_kernel<OP, false><<<grid_for(a.n, 256, 4, 8), 256, 0, stream>>>(a);
+  }
+  RTB_LAUNCH_CHECK();
+  return RTB_OK;
+}
+
+}  // namespace rtb
+
+using namespace rtb;
+
+extern "C" int rtb_reduce_out_dtype(int func, int vdt) {
+  if (vdt < RTB_BOOL || vdt > RTB_F64) return RTB_ERR_UNSUPPORTED;
+  int base = func >= 50 ? func - 50 : func;
+  switch (base) {
+    case RTB_GB_SUM:
+      if (vdt == RTB_F32 || vdt == RTB_F64 || vdt == RTB_U64) return vdt;
+      return RTB_I64;
+    case RTB_GB_MEAN: case RTB_GB_VAR: case RTB_GB_STD: return RTB_F64;
+    case RTB_GB_MIN: case RTB_GB_MAX: return vdt;
+    default: return RTB_ERR_UNSUPPORTED;
+  }
+}
+
+extern "C" size_t rtb_groupby_reduce_workspace_bytes(int64_t unique_rows, int func, int vdtype) {
+  (void)func; (void)vdtype;
+  if (unique_rows < 0) return 0;
+  return red_layout(nullptr, 0, unique_rows + 1).bytes + 256;
+}
+
+extern "C" int rtb_groupby_reduce(const void* values, int vdt, const void* ikey, int kdt, int64_t nrows,
+                                  int64_t unique_rows, int func, int64_t bin_low, int64_t bin_high, void* out,
+                                  void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RTB_ARG(is_ikey_dtype(kdt), "GroupByAll32: ikey must be int8/16/32/64");
+  int odt = rtb_reduce_out_dtype(func, vdt);
+  if (odt < 0) {
+    set_error("GroupByAll32: function %d is not provided for dtype %d", func, vdt);
+    return RTB_ERR_UNSUPPORTED;
+  }
+  RTB_ARG(nrows >= 0 && unique_rows >= 0 && out, "GroupByAll32: bad sizes or null output");
+  RTB_ARG(nrows == 0 || (values && ikey), "GroupByAll32: null input");
+  int vsz = dtype_size(vdt), ksz = dtype_size(kdt);
+  RTB_ARG(((uintptr_t)values % (4 * vsz)) == 0 && ((uintptr_t)ikey % (4 * ksz)) == 0,
+          "GroupByAll32: inputs must be aligned to 4 rows");
+  const int64_t nb = unique_rows + 1;
+  RTB_ARG(nb < (1ll << 31), "GroupByAll32: too many bins");
+  if (bin_low < 0) bin_low = 0;
+  if (bin_high > nb) bin_high = nb;
+  RedLayout L = red_layout(workspace, workspace_bytes, nb);
+  RTB_ARG(workspace && L.bytes <= workspace_bytes, "GroupByAll32: workspace too small");
+
+  const bool nan_op = func >= 50;
+  const int base = nan_op ? func - 50 : func;
+  AccumArgs a;
+  memset(&a, 0, sizeof(a));
+  a.values = values; a.ikey = ikey; a.vdt = vdt; a.kdt = kdt;
+  a.n = nrows; a.lo = bin_low; a.hi = bin_high; a.nb = nb;
+  a.nanskip = nan_op; a.ismax = base == RTB_GB_MAX;
+  a.acc = L.acc; a.cnt = L.cnt; a.mean = L.mean; a.flags = L.flags;
+  const int fgrid = grid_for(nb, 256, 1);
+  int rc;
+
+  switch (base) {
+    case RTB_GB_SUM: {
+      bool fl = vdt == RTB_F32 || vdt == RTB_F64;
+      if (vdt != RTB_F32) a.acc = (unsigned long long*)out;  // 64-bit outputs accumulate in place
+      RTB_CUDA(cudaMemsetAsync(a.acc, 0, 8 * (size_t)nb, stream));
+      rc = fl ? launch_accum<OP_SUMF>(a, stream) : launch_accum<OP_SUMI>(a, stream);
+      if (rc != RTB_OK) return rc;
+      if (vdt == RTB_F32) {
+        finalize_kernel<<<fgrid, 256, 0, stream>>>(FIN_CAST_F32, vdt, 0, nb, bin_low, bin_high, L.acc, L.cnt, L.flags, out, nullptr);
+        RTB_LAUNCH_CHECK();
+      }
+      return RTB_OK;
+    }
+    case RTB_GB_MEAN:
+      RTB_CUDA(cudaMemsetAsync(L.acc, 0, 8 * (size_t)nb, stream));
+      RTB_CUDA(cudaMemsetAsync(L.cnt, 0, 4 * (size_t)nb, stream));
+      if ((rc = launch_accum<OP_MEAN>(a, stream)) != RTB_OK) return rc;
+      finalize_kernel<<<fgrid, 256, 0, stream>>>(FIN_MEAN, vdt, 0, nb, bin_low, bin_high, L.acc, L.cnt, L.flags, out, nullptr);
+      RTB_LAUNCH_CHECK();
+      return RTB_OK;
+    case RTB_GB_MIN:
+    case RTB_GB_MAX:
+      RTB_CUDA(cudaMemsetAsync(L.acc, a.ismax ? 0x00 : 0xFF, 8 * (size_t)nb, stream));
+      RTB_CUDA(cudaMemsetAsync(L.flags, 0, (size_t)nb, stream));
+      if ((rc = launch_accum<OP_MINMAX>(a, stream)) != RTB_OK) return rc;
+      finalize_kernel<<<fgrid, 256, 0, stream>>>(FIN_MINMAX, vdt, a.ismax, nb, bin_low, bin_high, L.acc, L.cnt, L.flags, out, nullptr);
+      RTB_LAUNCH_CHECK();
+      return RTB_OK;
+    case RTB_GB_VAR:
+    case RTB_GB_STD:
+      RTB_CUDA(cudaMemsetAsync(L.acc, 0, 8 * (size_t)nb, stream));
+      RTB_CUDA(cudaMemsetAsync(L.cnt, 0, 4 * (size_t)nb, stream));
+      if ((rc = launch_accum<OP_MEAN>(a, stream)) != RTB_OK) return rc;
+      finalize_kernel<<<fgrid, 256, 0, stream>>>(FIN_MEAN_KEEP, vdt, 0, nb, bin_low, bin_high, L.acc, L.cnt, L.flags, out, L.mean);
+      RTB_LAUNCH_CHECK();
+      RTB_CUDA(cudaMemsetAsync(L.acc, 0, 8 * (size_t)nb, stream));
+      if ((rc = launch_accum<OP_M2>(a, stream)) != RTB_OK) return rc;
+      finalize_kernel<<<fgrid, 256, 0, stream>>>(base == RTB_GB_STD ? FIN_STD : FIN_VAR, vdt, 0, nb, bin_low, bin_high, L.acc, L.cnt, L.flags, out, nullptr);
+      RTB_LAUNCH_CHECK();
+      return RTB_OK;
+  }
+  set_error("GroupByAll32: unknown function %d", func);
+  return RTB_ERR_UNSUPPORTED;
+}
+
+extern "C" int rtb_bincount(const void* ikey, int kdt, int64_t nrows, int64_t nbins, int32_t* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RTB_ARG(is_ikey_dtype(kdt), "BinCount: ikey must be int8/16/32/64");
+  RTB_ARG(nrows >= 0 && nbins >= 0 && nbins < (1ll << 31), "BinCount: bad sizes");
+  if (nbins == 0) return RTB_OK;
+  RTB_ARG(out, "BinCount: null output");
+  RTB_ARG(nrows == 0 || ((uintptr_t)ikey % (4 * dtype_size(kdt))) == 0, "BinCount: ikey must be aligned to 4 rows");
+  RTB_CUDA(cudaMemsetAsync(out, 0, sizeof(int32_t) * (size_t)nbins, stream));
+  AccumArgs a;
+  memset(&a, 0, sizeof(a));
+  a.ikey = ikey; a.kdt = kdt; a.vdt = RTB_I32; a.n = nrows; a.lo = 0; a.hi = nbins; a.nb = nbins;
+  a.cnt = (uint32_t*)out;
+  return launch_accum<OP_COUNT>(a, stream);
+}

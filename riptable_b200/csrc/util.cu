@@ -1,0 +1,202 @@
+// Error state, launch counter, device-wide scan, and the small streaming entry points
+// (CombineFilter, ReverseShuffle, remap).
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace rtb {
+
+static thread_local char g_err[512] = "";
+uint64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---------------------------------------------------------------------------------------------
+// exclusive scan: tile = 256 threads x 16 items
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ uint32_t xform(uint32_t v, int xf) { return xf == SCAN_POPC ? (uint32_t)__popc(v) : v; }
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+  // 256 threads; returns exclusive prefix of v across the block
+  __shared__ uint32_t warp_sums[kScanThreads / 32];
+  __shared__ uint32_t block_total;
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) warp_sums[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t s = lane < kScanThreads / 32 ? warp_sums[lane] : 0;
+    uint32_t si = s;
+#pragma unroll
+    for (int d = 1; d < kScanThreads / 32; d <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, si, d);
+      if (lane >= d) si += t;
+    }
+    if (lane < kScanThreads / 32) warp_sums[lane] = si - s;
+    if (lane == kScanThreads / 32 - 1) block_total = si;
+  }
+  __syncthreads();
+  uint32_t r = inc - v + warp_sums[w];
+  *total = block_total;
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const uint32_t* __restrict__ in, int64_t n, int xf,
+                                                                uint32_t* __restrict__ tile_sums) {
+  int64_t base = (int64_t)blockIdx.x * kScanTile;
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; i++) {
+    int64_t idx = base + i * kScanThreads + threadIdx.x;
+    if (idx < n) s += xform(in[idx], xf);
+  }
+  uint32_t total;
+  block_exclusive_scan(s, &total);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_of_sums(uint32_t* sums, int64_t m, uint32_t* total_dev) {
+  // single block: exclusive scan of m tile sums in place
+  uint32_t carry = 0;
+  for (int64_t base = 0; base < m; base += kScanThreads) {
+    int64_t idx = base + threadIdx.x;
+    uint32_t v = idx < m ? sums[idx] : 0;
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(v, &total);
+    if (idx < m) sums[idx] = ex + carry;
+    carry += total;
+  }
+  if (threadIdx.x == 0 && total_dev) *total_dev = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_apply(const uint32_t* in, uint32_t* out, int64_t n, int xf,
+                                                            const uint32_t* __restrict__ tile_offsets) {
+  // thread owns kScanItems consecutive elements so the scan order is the array order
+  int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  uint32_t v[kScanItems];
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; i++) {
+    int64_t idx = base + i;
+    v[i] = idx < n ? xform(in[idx], xf) : 0;
+    s += v[i];
+  }
+  uint32_t total;
+  uint32_t ex = block_exclusive_scan(s, &total) + tile_offsets[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < kScanItems; i++) {
+    int64_t idx = base + i;
+    if (idx < n) out[idx] = ex;
+    ex += v[i];
+  }
+}
+
+size_t scan_u32_workspace_elems(int64_t n) { return (size_t)((n + kScanTile - 1) / kScanTile) + 1; }
+
+int exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, ScanXform xf, uint32_t* scratch,
+                       uint32_t* total_dev, cudaStream_t stream) {
+  if (n <= 0) {
+    if (total_dev) RTB_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(uint32_t), stream));
+    return RTB_OK;
+  }
+  int64_t tiles = (n + kScanTile - 1) / kScanTile;
+  scan_tile_sums<<<(unsigned)tiles, kScanThreads, 0, stream>>>(in, n, (int)xf, scratch);
+  RTB_LAUNCH_CHECK();
+  scan_of_sums<<<1, kScanThreads, 0, stream>>>(scratch, tiles, total_dev);
+  RTB_LAUNCH_CHECK();
+  scan_apply<<<(unsigned)tiles, kScanThreads, 0, stream>>>(in, out, n, (int)xf, scratch);
+  RTB_LAUNCH_CHECK();
+  return RTB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a4 CombineFilter: out = filter ? key : 0  (streaming, 4 rows per thread)
+__global__ void __launch_bounds__(256) combine_filter_kernel(const void* __restrict__ ikey, int kdt,
+                                                              const uint8_t* __restrict__ filter, int64_t n,
+                                                              void* __restrict__ out) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; r < n; r += stride) {
+    if (r + 3 < n) {
+      int64_t k[4];
+      load_ikey4(ikey, kdt, r, k);
+      uint32_t f = ld_stream_u32(filter + r);
+#pragma unroll
+      for (int i = 0; i < 4; i++) store_ikey(out, kdt, r + i, ((f >> (8 * i)) & 0xff) ? k[i] : 0);
+    } else {
+      for (int64_t q = r; q < n; q++) store_ikey(out, kdt, q, filter[q] ? load_ikey(ikey, kdt, q) : 0);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) reverse_shuffle_kernel(const int32_t* __restrict__ perm, int64_t n,
+                                                               int32_t* __restrict__ out) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int32_t p = perm[i];
+    if (p >= 0 && p < n) out[p] = (int32_t)i;
+  }
+}
+
+__global__ void __launch_bounds__(256) remap_kernel(const int32_t* __restrict__ ikey, int64_t n,
+                                                     const int32_t* __restrict__ map, int64_t nmap,
+                                                     int32_t* __restrict__ out) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int32_t k = ikey[i];
+    out[i] = (k >= 0 && k < nmap) ? map[k] : 0;
+  }
+}
+
+}  // namespace rtb
+
+using namespace rtb;
+
+extern "C" {
+
+int rtb_version(void) { return 100; }
+const char* rtb_last_error(void) { return g_err; }
+uint64_t rtb_launch_count(void) { return g_launches; }
+
+int rtb_combine_filter(const void* ikey, int kdtype, const uint8_t* filter, int64_t nrows, void* out, void* stream) {
+  RTB_ARG(is_ikey_dtype(kdtype), "CombineFilter: key must be int8/16/32/64");
+  RTB_ARG(nrows >= 0, "CombineFilter: negative length");
+  if (nrows == 0) return RTB_OK;
+  RTB_ARG(ikey && filter && out, "CombineFilter: null pointer");
+  // vector path needs 4-row alignment of the base pointers
+  int ksz = dtype_size(kdtype);
+  RTB_ARG(((uintptr_t)ikey % (4 * ksz)) == 0 && ((uintptr_t)filter % 4) == 0, "CombineFilter: unaligned input");
+  combine_filter_kernel<<<grid_for(nrows, 256, 4), 256, 0, (cudaStream_t)stream>>>(ikey, kdtype, filter, nrows, out);
+  RTB_LAUNCH_CHECK();
+  return RTB_OK;
+}
+
+int rtb_reverse_shuffle(const int32_t* perm, int64_t n, int32_t* out, void* stream) {
+  RTB_ARG(n >= 0, "ReverseShuffle: negative length");
+  if (n == 0) return RTB_OK;
+  reverse_shuffle_kernel<<<grid_for(n, 256, 1), 256, 0, (cudaStream_t)stream>>>(perm, n, out);
+  RTB_LAUNCH_CHECK();
+  return RTB_OK;
+}
+
+int rtb_remap_ikey(const int32_t* ikey, int64_t nrows, const int32_t* map, int64_t nmap, int32_t* out, void* stream) {
+  if (nrows <= 0) return RTB_OK;
+  remap_kernel<<<grid_for(nrows, 256, 1), 256, 0, (cudaStream_t)stream>>>(ikey, nrows, map, nmap, out);
+  RTB_LAUNCH_CHECK();
+  return RTB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,488 @@
+"""Drop-in mirror of the riptide_cpp (`rc`) entry points on riptable's groupby / reduce / lexsort path.
+
+Same names, positional arguments, keyword names (`cutoffs=`, `pack=`, `index=`, `ascending=`,
+`base_index=`) and error behaviour as the calls in riptable/rt_numpy.py:1463-2348, 2658-2673 and
+riptable/rt_grouping.py:3427-3454, so `import riptable_b200.rc as rc` can stand in for
+`import riptide_cpp as rc` on this path.
+
+Every function is a thin shim: stage inputs on the GPU (torch is used only for device memory and the
+current stream), call the C ABI of libriptable_b200.so, hand results back.
+
+  host mode   : inputs are NumPy arrays  -> outputs are NumPy arrays (H2D / D2H inside the call)
+  device mode : any input is a CUDA tensor / DevArray -> outputs stay on the device (torch tensors,
+                DevArray for byte-string columns), so chained calls never touch PCIe.
+
+There is no CPU fallback: without a CUDA device or the built library these functions raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, rtb_column, check, RtbWorkspaceError
+from .enums import (
+    GB_FUNCTIONS,
+    RTB_BYTES,
+    RTB_I32,
+    code_dtype,
+    dtype_code,
+)
+
+_TORCH_OF = {
+    np.dtype(np.bool_): torch.bool,
+    np.dtype(np.int8): torch.int8,
+    np.dtype(np.uint8): torch.uint8,
+    np.dtype(np.int16): torch.int16,
+    np.dtype(np.uint16): torch.uint16,
+    np.dtype(np.int32): torch.int32,
+    np.dtype(np.uint32): torch.uint32,
+    np.dtype(np.int64): torch.int64,
+    np.dtype(np.uint64): torch.uint64,
+    np.dtype(np.float32): torch.float32,
+    np.dtype(np.float64): torch.float64,
+}
+_NP_OF = {v: k for k, v in _TORCH_OF.items()}
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("riptable_b200: no CUDA device; this path has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class DevArray:
+    """A device-resident 1-D array of any NumPy dtype (incl. fixed-width S/U), backed by a uint8 CUDA tensor."""
+
+    __slots__ = ("buf", "dtype", "n")
+
+    def __init__(self, buf: torch.Tensor, dtype, n: int):
+        self.buf, self.dtype, self.n = buf, np.dtype(dtype), int(n)
+
+    def __len__(self):
+        return self.n
+
+    @property
+    def ptr(self):
+        return self.buf.data_ptr()
+
+    def numpy(self) -> np.ndarray:
+        host = self.buf[: self.n * self.dtype.itemsize].cpu().numpy()
+        return host.view(self.dtype) if self.dtype.itemsize else np.zeros(self.n, self.dtype)
+
+    def torch(self) -> torch.Tensor:
+        t = self.buf[: self.n * self.dtype.itemsize]
+        td = _TORCH_OF.get(self.dtype)
+        if td is None:
+            raise TypeError(f"{self.dtype} has no torch dtype; use .numpy() or .buf")
+        return t.view(td)
+
+    @staticmethod
+    def empty(n, dtype, dev=None):
+        dtype = np.dtype(dtype)
+        nbytes = max(int(n) * dtype.itemsize, 16)
+        return DevArray(torch.empty(nbytes, dtype=torch.uint8, device=dev or _device()), dtype, n)
+
+
+def _is_device(x) -> bool:
+    return isinstance(x, DevArray) or (isinstance(x, torch.Tensor) and x.is_cuda)
+
+
+def _to_dev(x) -> DevArray:
+    """Stage one 1-D array on the GPU as raw bytes (zero-copy for CUDA tensors)."""
+    if isinstance(x, DevArray):
+        return x
+    if isinstance(x, torch.Tensor):
+        if x.is_cuda:
+            if x.dim() != 1:
+                raise ValueError("expected a 1-D tensor")
+            x = x.contiguous()
+            if x.data_ptr() % 16:
+                x = x.clone()
+            npdt = _NP_OF[x.dtype]
+            return DevArray(x.view(torch.uint8) if x.numel() else torch.empty(16, dtype=torch.uint8, device=x.device), npdt, x.numel())
+        x = x.numpy()
+    a = np.asarray(x)
+    if a.ndim != 1:
+        raise ValueError("expected a 1-D array")
+    if a.dtype.kind == "O":
+        raise TypeError("object arrays are not supported on this path")
+    if not a.dtype.isnative:
+        a = a.astype(a.dtype.newbyteorder("="))
+    a = np.ascontiguousarray(a)
+    out = DevArray.empty(len(a), a.dtype)
+    nbytes = a.nbytes
+    if nbytes:
+        src = torch.from_numpy(a.view(np.uint8).reshape(-1))
+        out.buf[:nbytes].copy_(src, non_blocking=src.is_pinned())
+    return out
+
+
+def _from_dev(d: DevArray, device_mode: bool):
+    if not device_mode:
+        return d.numpy()
+    if d.dtype in _TORCH_OF:
+        return d.torch()
+    return d
+
+
+def _col(d: DevArray) -> rtb_column:
+    code = dtype_code(d.dtype)
+    return rtb_column(C.c_void_p(d.ptr), code, d.dtype.itemsize)
+
+
+def _cols(devs: Sequence[DevArray]):
+    arr = (rtb_column * len(devs))()
+    for i, d in enumerate(devs):
+        arr[i] = _col(d)
+    return arr
+
+
+def _ikey_dev(ikey) -> DevArray:
+    d = _to_dev(ikey)
+    if d.dtype.kind != "i":
+        raise ValueError("ikey must be int8, int16, int32, or int64")
+    return d
+
+
+def _bool_dev(f, n, what="filter") -> DevArray:
+    d = _to_dev(f)
+    if d.dtype.kind != "b" and d.dtype != np.dtype(np.uint8):
+        raise TypeError(f"{what} must be a boolean array")
+    if d.n != n:
+        raise ValueError(f"{what} length {d.n} does not match {n}")
+    return d
+
+
+def _ws(nbytes: int) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=_device())
+
+
+def _as_list(list_arrays):
+    if isinstance(list_arrays, (np.ndarray, torch.Tensor, DevArray)):
+        return [list_arrays]
+    if isinstance(list_arrays, tuple):
+        return list(list_arrays)
+    return list_arrays
+
+
+# ==================================================================================================
+# a1  rc.MultiKeyGroupBy32 (riptable/rt_numpy.py:2073-2075)
+def MultiKeyGroupBy32(list_arrays, hint_size=0, filter=None, hash_mode=2, cutoffs=None):
+    """-> (iKey int32[N] base-1 / 0 = filtered, iFirstKey int32[U], unique_count).
+    With `cutoffs` numbering restarts per partition and iFirstKey is (rows, cumulative unique cutoffs)
+    (riptable/tests/test_pgroupby.py:7-86)."""
+    list_arrays = _as_list(list_arrays)
+    if not isinstance(list_arrays, list) or len(list_arrays) == 0:
+        raise ValueError("groupbyhash first argument is not a list of numpy arrays")
+    device_mode = any(_is_device(a) for a in list_arrays)
+    cols = [_to_dev(a) for a in list_arrays]
+    n = cols[0].n
+    if any(c.n != n for c in cols):
+        raise ValueError(f"groupbyhash all arrays must have same length not {set(c.n for c in cols)}")
+    fdev = _bool_dev(filter, n) if filter is not None else None
+    cut = None
+    if cutoffs is not None:
+        cut = np.ascontiguousarray(np.asarray(cutoffs.cpu() if isinstance(cutoffs, torch.Tensor) else cutoffs), dtype=np.int64)
+        if cut.ndim != 1 or len(cut) == 0 or cut[-1] != n:
+            raise ValueError("cutoffs must be a 1-D int64 array whose last entry is the row count")
+    dev = _device()
+    if n == 0:
+        e = DevArray.empty(0, np.int32)
+        return _from_dev(e, device_mode), _from_dev(e, device_mode), 0
+
+    max_unique = min(n, max(int(hint_size), 1024)) if hint_size and hint_size > 0 else min(n, max(1 << 20, n // 16))
+    carr = _cols(cols)
+    ikey = DevArray.empty(n, np.int32, dev)
+    ucount, needed = C.c_int64(0), C.c_int64(0)
+    ucut = np.zeros(len(cut), dtype=np.int64) if cut is not None else None
+    while True:
+        ifirst = DevArray.empty(max_unique, np.int32, dev)
+        ws = _ws(lib.rtb_groupby_workspace_bytes(n, max_unique, len(cols), int(cut is not None)))
+        rc_ = lib.rtb_multikey_groupby32(
+            carr, len(cols), n, int(hint_size or 0),
+            C.c_void_p(fdev.ptr) if fdev is not None else None,
+            cut.ctypes.data_as(C.POINTER(C.c_int64)) if cut is not None else None, len(cut) if cut is not None else 0,
+            C.c_void_p(ikey.ptr), C.c_void_p(ifirst.ptr), max_unique,
+            C.byref(ucount), ucut.ctypes.data_as(C.POINTER(C.c_int64)) if ucut is not None else None, C.byref(needed),
+            C.c_void_p(ws.data_ptr()), ws.numel(), _stream(),
+        )
+        if rc_ == _lib.RTB_ERR_WORKSPACE and max_unique < n:
+            max_unique = min(n, max(int(needed.value), 4 * max_unique))
+            continue
+        check(rc_, needed.value)
+        break
+    u = int(ucount.value)
+    ifirst = DevArray(ifirst.buf, np.int32, u)
+    ik, ifk = _from_dev(ikey, device_mode), _from_dev(ifirst, device_mode)
+    if device_mode and u < max_unique // 2:
+        ifk = ifk.clone()  # do not pin a max_unique-sized buffer behind a small result
+    if cut is not None:
+        return ik, (ifk, ucut), u
+    return ik, ifk, u
+
+
+# ==================================================================================================
+# a4  rc.CombineFilter (riptable/rt_numpy.py:1508)
+def CombineFilter(key, filter):
+    device_mode = _is_device(key) or _is_device(filter)
+    k = _ikey_dev(key)
+    f = _bool_dev(filter, k.n)
+    out = DevArray.empty(k.n, k.dtype)
+    check(lib.rtb_combine_filter(C.c_void_p(k.ptr), dtype_code(k.dtype), C.c_void_p(f.ptr), k.n, C.c_void_p(out.ptr), _stream()))
+    return _from_dev(out, device_mode)
+
+
+# ==================================================================================================
+# a5  rc.GroupByAll32 (riptable/rt_numpy.py:1871; riptable/rt_grouping.py:3434-3436)
+def GroupByAll32(values, ikey, unique_rows, funcList, binLowList, binHighList, func_param=0):
+    """-> tuple of arrays[unique_rows+1] (slot 0 = filtered bin); None for columns the op cannot take
+    (riptable/rt_grouping.py:2341-2345)."""
+    values = _as_list(values)
+    device_mode = _is_device(ikey) or any(_is_device(v) for v in values)
+    k = _ikey_dev(ikey)
+    kcode = dtype_code(k.dtype)
+    nb = int(unique_rows) + 1
+    out = []
+    for v, f, lo, hi in zip(values, funcList, binLowList, binHighList):
+        d = _to_dev(v)
+        if d.n != k.n:
+            raise ValueError(f"GroupByAll32: value length {d.n} does not match ikey length {k.n}")
+        vcode = dtype_code(d.dtype) if d.dtype.kind in "biuf" and d.dtype.itemsize <= 8 and d.dtype != np.float16 else RTB_BYTES
+        ocode = lib.rtb_reduce_out_dtype(int(f), vcode) if vcode != RTB_BYTES else -1
+        if ocode < 0:
+            out.append(None)
+            continue
+        res = DevArray.empty(nb, code_dtype(ocode))
+        ws = _ws(lib.rtb_groupby_reduce_workspace_bytes(int(unique_rows), int(f), vcode))
+        check(lib.rtb_groupby_reduce(
+            C.c_void_p(d.ptr), vcode, C.c_void_p(k.ptr), kcode, k.n, int(unique_rows), int(f), int(lo), int(hi),
+            C.c_void_p(res.ptr), C.c_void_p(ws.data_ptr()), ws.numel(), _stream()))
+        out.append(_from_dev(res, device_mode))
+    return tuple(out)
+
+
+# ==================================================================================================
+# a6 / a7  rc.BinCount / rc.GroupFromBinCount / rc.GroupByPack32 (riptable/rt_numpy.py:1945-1972)
+def BinCount(ikey, n, pack=False):
+    """histogram int32[n]; pack=True -> (nCountGroup, iGroup, iFirstGroup) (riptable/rt_numpy.py:1960)."""
+    device_mode = _is_device(ikey)
+    k = _ikey_dev(ikey)
+    n = int(n)
+    if pack:
+        ig, ifg, cnt = _pack(k, n)
+        return _from_dev(cnt, device_mode), _from_dev(ig, device_mode), _from_dev(ifg, device_mode)
+    out = DevArray.empty(n, np.int32)
+    check(lib.rtb_bincount(C.c_void_p(k.ptr), dtype_code(k.dtype), k.n, n, C.c_void_p(out.ptr), _stream()))
+    return _from_dev(out, device_mode)
+
+
+def _pack(k: DevArray, nbins: int):
+    if k.n > 2_000_000_000:
+        raise ValueError("pack: more than 2e9 rows needs the 64-bit variant, which this build does not provide")
+    ig = DevArray.empty(k.n, np.int32)
+    ifg = DevArray.empty(nbins, np.int32)
+    cnt = DevArray.empty(nbins, np.int32)
+    ws = _ws(lib.rtb_pack_workspace_bytes(k.n, nbins))
+    check(lib.rtb_groupby_pack(C.c_void_p(k.ptr), dtype_code(k.dtype), k.n, nbins, C.c_void_p(ig.ptr), C.c_void_p(ifg.ptr),
+                               C.c_void_p(cnt.ptr), C.c_void_p(ws.data_ptr()), ws.numel(), _stream()))
+    return ig, ifg, cnt
+
+
+def GroupFromBinCount(ikey, nCountGroup):
+    """-> (iGroup, iFirstGroup) (riptable/rt_numpy.py:1957,1965)."""
+    device_mode = _is_device(ikey) or _is_device(nCountGroup)
+    k = _ikey_dev(ikey)
+    ig, ifg, _ = _pack(k, len(nCountGroup))
+    return _from_dev(ig, device_mode), _from_dev(ifg, device_mode)
+
+
+def GroupByPack32(ikey, _unused, n, cutoffs=None):
+    """-> (iGroup, iFirstGroup, nCountGroup) (riptable/rt_numpy.py:1972)."""
+    if cutoffs is not None:
+        raise NotImplementedError("GroupByPack32(cutoffs=) is unpinned by the reference tests and not provided")
+    device_mode = _is_device(ikey)
+    ig, ifg, cnt = _pack(_ikey_dev(ikey), int(n))
+    return _from_dev(ig, device_mode), _from_dev(ifg, device_mode), _from_dev(cnt, device_mode)
+
+
+# ==================================================================================================
+# a8  rc.GroupByAllPack32 (riptable/rt_numpy.py:1891; riptable/rt_grouping.py:3443-3454)
+def GroupByAllPack32(values, ikey, iGroup, iFirstGroup, nCountGroup, unique_rows, funcList, binLowList, binHighList,
+                     func_param=0):
+    values = _as_list(values)
+    device_mode = any(_is_device(x) for x in (ikey, iGroup, iFirstGroup, nCountGroup)) or any(_is_device(v) for v in values)
+    ig, ifg, cnt = (_to_dev(x) for x in (iGroup, iFirstGroup, nCountGroup))
+    for name, d in (("iGroup", ig), ("iFirstGroup", ifg), ("nCountGroup", cnt)):
+        if d.dtype != np.dtype(np.int32):
+            raise TypeError(f"GroupByAllPack32: {name} must be int32")
+    nb = int(unique_rows) + 1
+    if ifg.n < nb or cnt.n < nb:
+        raise ValueError("GroupByAllPack32: iFirstGroup / nCountGroup shorter than unique_rows + 1")
+    out = []
+    for v, f, lo, hi in zip(values, funcList, binLowList, binHighList):
+        f = int(f)
+        if f not in (GB_FUNCTIONS.GB_FIRST, GB_FUNCTIONS.GB_NTH, GB_FUNCTIONS.GB_LAST):
+            raise NotImplementedError(f"GroupByAllPack32: function {f} is outside this build's hot path")
+        d = _to_dev(v)
+        res = DevArray.empty(nb, d.dtype)
+        nth = int(func_param) if f == GB_FUNCTIONS.GB_NTH else 0
+        check(lib.rtb_groupby_pick(C.c_void_p(d.ptr), dtype_code(d.dtype), d.dtype.itemsize, C.c_void_p(ig.ptr),
+                                   C.c_void_p(ifg.ptr), C.c_void_p(cnt.ptr), int(unique_rows), f, nth, int(lo), int(hi),
+                                   C.c_void_p(res.ptr), _stream()))
+        out.append(_from_dev(res, device_mode))
+    return tuple(out)
+
+
+# ==================================================================================================
+# a9  rc.EmaAll32 (riptable/rt_grouping.py:3430), GB_CUMSUM
+def EmaAll32(values, ikey, unique_rows, funcNum, func_param):
+    if int(funcNum) != GB_FUNCTIONS.GB_CUMSUM:
+        raise NotImplementedError(f"EmaAll32: function {int(funcNum)} is outside this build's hot path")
+    values = _as_list(values)
+    filt = reset = None
+    if isinstance(func_param, (tuple, list)) and len(func_param) >= 4:
+        filt, reset = func_param[2], func_param[3]
+    device_mode = _is_device(ikey) or any(_is_device(v) for v in values)
+    k = _ikey_dev(ikey)
+    fdev = _bool_dev(filt, k.n) if filt is not None else None
+    rdev = _bool_dev(reset, k.n, "reset_filter") if reset is not None else None
+    out = []
+    for v in values:
+        d = _to_dev(v)
+        vcode = dtype_code(d.dtype) if d.dtype.kind in "biuf" and d.dtype != np.float16 else RTB_BYTES
+        ocode = lib.rtb_cumsum_out_dtype(vcode) if vcode != RTB_BYTES else -1
+        if ocode < 0:
+            out.append(None)
+            continue
+        res = DevArray.empty(k.n, code_dtype(ocode))
+        ws = _ws(lib.rtb_cumsum_workspace_bytes(k.n, int(unique_rows)))
+        check(lib.rtb_groupby_cumsum(C.c_void_p(d.ptr), vcode, C.c_void_p(k.ptr), dtype_code(k.dtype), k.n, int(unique_rows),
+                                     C.c_void_p(fdev.ptr) if fdev is not None else None,
+                                     C.c_void_p(rdev.ptr) if rdev is not None else None,
+                                     C.c_void_p(res.ptr), C.c_void_p(ws.data_ptr()), ws.numel(), _stream()))
+        out.append(_from_dev(res, device_mode))
+    return out
+
+
+# ==================================================================================================
+# a10  rc.MakeiFirst / rc.MakeiNext (riptable/rt_numpy.py:1791-1854)
+def MakeiFirst(key, n, filter=None, mode=0):
+    device_mode = _is_device(key)
+    k = _ikey_dev(key)
+    f = _bool_dev(filter, k.n) if filter is not None else None
+    out = DevArray.empty(int(n) + 1, np.int32)
+    check(lib.rtb_make_ifirst(C.c_void_p(k.ptr), dtype_code(k.dtype), k.n, int(n), C.c_void_p(f.ptr) if f is not None else None,
+                              int(mode), C.c_void_p(out.ptr), _stream()))
+    return _from_dev(out, device_mode)
+
+
+def MakeiNext(key, n, mode=0):
+    device_mode = _is_device(key)
+    k = _ikey_dev(key)
+    out = DevArray.empty(k.n, np.int32)
+    ws = _ws(lib.rtb_make_inext_workspace_bytes(k.n, int(n)))
+    check(lib.rtb_make_inext(C.c_void_p(k.ptr), dtype_code(k.dtype), k.n, int(n), int(mode), C.c_void_p(out.ptr),
+                             C.c_void_p(ws.data_ptr()), ws.numel(), _stream()))
+    return _from_dev(out, device_mode)
+
+
+# ==================================================================================================
+# a11  rc.LexSort32 / rc.LexSort64 (riptable/rt_numpy.py:2670-2671, 2200-2202)
+def LexSort32(list_arrays, cutoffs=None, index=None, ascending=True):
+    """Stable lexicographic argsort; the LAST array is the primary key (numpy.lexsort convention), NaN last."""
+    if cutoffs is not None:
+        raise NotImplementedError("LexSort32(cutoffs=) is unpinned by the reference tests and not provided")
+    list_arrays = _as_list(list_arrays)
+    if not isinstance(list_arrays, list) or len(list_arrays) == 0:
+        raise ValueError("lexsort needs a list of arrays")
+    device_mode = any(_is_device(a) for a in list_arrays) or _is_device(index)
+    cols = [_to_dev(a) for a in list_arrays]
+    n = cols[0].n
+    if any(c.n != n for c in cols):
+        raise ValueError("lexsort: all keys must have the same length")
+    if n > 2_000_000_000:
+        raise ValueError("LexSort32: more than 2e9 rows; LexSort64 is not provided by this build")
+    if isinstance(ascending, (bool, np.bool_)):
+        asc = np.full(len(cols), 1 if ascending else 0, dtype=np.int8)
+    else:
+        asc = np.asarray([1 if a else 0 for a in ascending], dtype=np.int8)
+        if len(asc) != len(cols):
+            raise ValueError("ascending must have one entry per key")
+    idx = None
+    m = n
+    if index is not None:
+        idx = _to_dev(index)
+        if idx.dtype != np.dtype(np.int32):
+            idx = _to_dev(idx.numpy().astype(np.int32))
+        m = idx.n
+    out = DevArray.empty(m, np.int32)
+    if m == 0:
+        return _from_dev(out, device_mode)
+    isz = (C.c_int32 * len(cols))(*[c.dtype.itemsize for c in cols])
+    ws = _ws(lib.rtb_lexsort_workspace_bytes(n, m, len(cols), isz))
+    check(lib.rtb_lexsort32(_cols(cols), len(cols), n, C.c_void_p(idx.ptr) if idx is not None else None, m,
+                            asc.ctypes.data_as(C.POINTER(C.c_int8)), C.c_void_p(out.ptr), C.c_void_p(ws.data_ptr()),
+                            ws.numel(), _stream()))
+    return _from_dev(out, device_mode)
+
+
+def LexSort64(list_arrays, cutoffs=None, index=None, ascending=True):
+    # riptable only routes here above 2e9 rows (rt_numpy.py:2669-2671); below that the 32-bit result is identical
+    return LexSort32(list_arrays, cutoffs=cutoffs, index=index, ascending=ascending)
+
+
+# ==================================================================================================
+# a12  rc.GroupFromLexSort (riptable/rt_numpy.py:2207)
+def GroupFromLexSort(iGroup, value_array, cutoffs=None, base_index=1):
+    """-> (iKey int32[N], iFirstKey int32[U], nCountGroup int32[U+1] with slot 0 = 0)."""
+    if cutoffs is not None:
+        raise NotImplementedError("GroupFromLexSort(cutoffs=) is unpinned by the reference tests and not provided")
+    if isinstance(value_array, np.ndarray) and value_array.dtype.names:
+        value_array = [np.ascontiguousarray(value_array[nm]) for nm in value_array.dtype.names]
+    vals = _as_list(value_array)
+    device_mode = _is_device(iGroup) or any(_is_device(v) for v in vals)
+    ig = _to_dev(iGroup)
+    if ig.dtype != np.dtype(np.int32):
+        raise TypeError("GroupFromLexSort: iGroup must be int32")
+    cols = [_to_dev(v) for v in vals]
+    n = cols[0].n
+    m = ig.n
+    ikey = DevArray.empty(n, np.int32)
+    ifk = DevArray.empty(max(m, 1), np.int32)
+    cnt = DevArray.empty(m + 1, np.int32)
+    u = C.c_int64(0)
+    ws = _ws(lib.rtb_group_from_lexsort_workspace_bytes(n, m))
+    check(lib.rtb_group_from_lexsort(C.c_void_p(ig.ptr), m, _cols(cols), len(cols), n, int(base_index), C.c_void_p(ikey.ptr),
+                                     C.c_void_p(ifk.ptr), C.c_void_p(cnt.ptr), C.byref(u), C.c_void_p(ws.data_ptr()),
+                                     ws.numel(), _stream()))
+    U = int(u.value)
+    ifk = DevArray(ifk.buf, np.int32, U)
+    cnt = DevArray(cnt.buf, np.int32, U + 1)
+    return _from_dev(ikey, device_mode), _from_dev(ifk, device_mode), _from_dev(cnt, device_mode)
+
+
+# ==================================================================================================
+# a13  rc.ReverseShuffle (riptable/rt_grouping.py:1659)
+def ReverseShuffle(perm):
+    device_mode = _is_device(perm)
+    p = _to_dev(perm)
+    if p.dtype != np.dtype(np.int32):
+        if p.dtype.kind != "i":
+            raise TypeError("ReverseShuffle: permutation must be an integer array")
+        p = _to_dev(p.numpy().astype(np.int32))
+    out = DevArray.empty(p.n, np.int32)
+    check(lib.rtb_reverse_shuffle(C.c_void_p(p.ptr), p.n, C.c_void_p(out.ptr), _stream()))
+    return _from_dev(out, device_mode)
+
+
+def LedgerFunction(func, *args, **kwargs):
+    """rc.LedgerFunction(f, *a, **k) == f(*a, **k) with timing recorded (riptable/rt_numpy.py:153,1871)."""
+    return func(*args, **kwargs)

@@ -1,0 +1,39 @@
+"""CPU-side checks of the boundary: the library loads and exports every symbol include/*.h declares."""
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "riptable_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rtb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    import riptable_b200.build as b
+
+    b.build()
+    from riptable_b200 import _lib
+
+    names = _declared()
+    assert len(names) >= 20
+    assert _lib.MISSING == []
+    for n in names:
+        assert hasattr(_lib.lib, n), f"{n} declared in include/riptable_b200.h but not exported"
+        assert n in _lib.PROTOTYPES, f"{n} has no ctypes prototype"
+    assert _lib.lib.rtb_version() >= 100
+
+
+def test_out_dtype_table_matches_contract():
+    # SURVEY 8a': sum ints -> int64 (uint64 stays), floats keep; mean/var/std -> f64; min/max keep dtype
+    from riptable_b200 import _lib
+    from riptable_b200.enums import RTB_BOOL, RTB_F32, RTB_F64, RTB_I8, RTB_I64, RTB_U64, RTB_BYTES
+
+    f = _lib.lib.rtb_reduce_out_dtype
+    assert f(0, RTB_I8) == RTB_I64 and f(0, RTB_BOOL) == RTB_I64 and f(0, RTB_U64) == RTB_U64
+    assert f(0, RTB_F32) == RTB_F32 and f(50, RTB_F64) == RTB_F64
+    assert f(1, RTB_I8) == RTB_F64 and f(55, RTB_F32) == RTB_F64
+    assert f(2, RTB_I8) == RTB_I8 and f(53, RTB_F32) == RTB_F32
+    assert f(0, RTB_BYTES) < 0 and f(100, RTB_I8) < 0

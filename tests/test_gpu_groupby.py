@@ -1,0 +1,245 @@
+"""GPU parity: rc.MultiKeyGroupBy32 / GroupByAll32 / BinCount / CombineFilter vs the CPU oracle.
+Integer outputs bit-exact; float reductions within 1e-12 (f64) / 1e-5 (f32) relative."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import riptide_oracle as orc
+
+
+@pytest.fixture(scope="module")
+def rc():
+    import riptable_b200.rc as rc
+
+    return rc
+
+
+def _check_gb(rc, keys, filter=None, cutoffs=None, hint=0):
+    ik, ifk, u = rc.MultiKeyGroupBy32(keys, hint, filter, 2, cutoffs=cutoffs)
+    ok, ofk, ou = orc.MultiKeyGroupBy32(keys, hint, filter, 2, cutoffs=cutoffs)
+    assert u == ou
+    assert ik.dtype == np.int32
+    np.testing.assert_array_equal(ik, ok)
+    if cutoffs is None:
+        assert ifk.dtype == np.int32
+        np.testing.assert_array_equal(ifk, ofk)
+    else:
+        np.testing.assert_array_equal(ifk[0], ofk[0])
+        np.testing.assert_array_equal(ifk[1], ofk[1])
+    return ik, u
+
+
+@pytest.mark.parametrize("dt", [np.int8, np.uint8, np.int16, np.uint16, np.int32, np.uint32, np.int64, np.uint64,
+                                np.float32, np.float64, np.bool_])
+@pytest.mark.parametrize("n", [1, 5, 1000, 100_003])
+def test_single_key_dtypes(rc, dt, n):
+    rng = np.random.default_rng(n)
+    if dt == np.bool_:
+        k = rng.integers(0, 2, n).astype(dt)
+    else:
+        k = rng.integers(0, 100, n).astype(dt)
+    _check_gb(rc, [k])
+    _check_gb(rc, [k], filter=rng.random(n) < 0.6)
+
+
+def test_docstring_vectors(rc):
+    # rt_numpy.py:2013-2062
+    np.random.seed(12345)
+    c = np.random.randint(0, 8000, 2_000_000)
+    d = np.random.randint(0, 8000, 2_000_000)
+    ik, ifk, u = rc.MultiKeyGroupBy32([c], 0, None, 2)
+    assert u == 8000 and ik[:3].tolist() == [1, 2, 3] and ik[-3:].tolist() == [6061, 7889, 3002]
+    assert ifk[-3:].tolist() == [67072, 67697, 68250]
+    ik, ifk, u = rc.MultiKeyGroupBy32([c], 0, (c % 3).astype(bool), 2)
+    assert u == 5333 and ik[-3:].tolist() == [0, 5250, 1973] and ifk[-3:].tolist() == [54422, 58655, 68250]
+    ik, ifk, u = rc.MultiKeyGroupBy32([c, d], 0, None, 2)
+    assert u == 1968856 and ik[-3:].tolist() == [1968854, 1968855, 1968856]
+    assert ifk[-3:].tolist() == [1999997, 1999998, 1999999]
+    _check_gb(rc, [c, d])
+
+
+def test_special_keys(rc):
+    # -1 collides with the table's empty marker; NaNs group bytewise; -0.0 != +0.0 bytewise
+    k = np.array([-1, 5, -1, 0, 5, -1, np.iinfo(np.int64).min], dtype=np.int64)
+    _check_gb(rc, [k])
+    k = np.tile(np.array([-1, -1, 3], dtype=np.int64), 100_000)
+    _check_gb(rc, [k])
+    f = np.array([np.nan, 1.0, np.nan, -0.0, 0.0, 1.0, np.inf, -np.inf, np.nan])
+    _check_gb(rc, [f])
+    _check_gb(rc, [f.astype(np.float32)])
+
+
+@pytest.mark.parametrize("n,u", [(3_000_000, 2_500_000), (2_000_000, 2_000_000), (5_000_000, 1000)])
+def test_high_cardinality_and_growth(rc, n, u):
+    rng = np.random.default_rng(u)
+    vals = rng.integers(-(2**62), 2**62, u, dtype=np.int64)
+    k = vals[rng.integers(0, u, n)] if u < n else rng.permutation(vals)
+    _check_gb(rc, [k])
+
+
+def test_sorted_and_late_keys(rc):
+    # discovery rate that never decays (sorted keys) and a burst of new keys late in the array
+    k = np.repeat(np.arange(300_000, dtype=np.int64), 10)
+    _check_gb(rc, [k])
+    rng = np.random.default_rng(3)
+    k = np.concatenate([rng.integers(0, 50, 2_500_000), rng.integers(1000, 400_000, 600_000)]).astype(np.int32)
+    _check_gb(rc, [k])
+
+
+def test_multikey_and_strings(rc):
+    rng = np.random.default_rng(11)
+    n = 200_000
+    a = rng.integers(0, 50, n)
+    s = rng.choice(np.array(["alpha", "be", "gamma_long_string", ""], dtype="S17"), n)
+    u = rng.choice(np.array(["x", "yy", "zzz"], dtype="U3"), n)
+    i4 = rng.integers(0, 5, n).astype(np.int32)
+    _check_gb(rc, [s])
+    _check_gb(rc, [u])
+    _check_gb(rc, [a, s, i4])
+    _check_gb(rc, [a, s, i4], filter=rng.random(n) < 0.5)
+    _check_gb(rc, [i4, i4.astype(np.int8), u])
+    s16 = rng.choice(np.array([b"ABCDEFGHIJKLMNOP", b"ABCDEFGHIJKLMNOQ", b"ZBCDEFGHIJKLMNOP"], dtype="S16"), n)
+    _check_gb(rc, [a.astype(np.int64), s16, i4])
+
+
+def test_projections_fixture(rc):
+    # tests/test_groupby.py:419-459 -> exactly 455 654 groups
+    n, num_symbols = 1_000_000, 450
+    dates = ["20180602", "20180603", "20180604", "20180605", "20180606"]
+    exch = np.array(["EXCH1", "EXCH2", "EXCH3"])
+    np.random.seed(1234)
+    sym = np.random.randint(0, num_symbols, size=n)
+    ex = exch[np.random.randint(0, exch.shape[0], size=n)]
+    i = np.arange(n)
+    td = np.array(dates)[(i * len(dates) / n).astype(int)]
+    t25 = ((i % (n // len(dates))) / 2500).astype(int)
+    ik, u = _check_gb(rc, [sym, ex.astype("S"), td.astype("S"), t25])
+    assert u == 455654
+
+
+def test_cutoffs(rc):
+    # tests/test_pgroupby.py:7-86
+    rng = np.random.default_rng(0)
+    arr3 = rng.integers(0, 5, 30)
+    _check_gb(rc, [arr3], cutoffs=np.array([15, 30], dtype=np.int64))
+    _check_gb(rc, [arr3], cutoffs=np.array([30], dtype=np.int64))
+    a = np.arange(10)
+    _check_gb(rc, [np.ones(10)], cutoffs=a.astype(np.int64) + 1)
+    _check_gb(rc, [np.ones(10)], filter=(a % 2).astype(bool), cutoffs=a.astype(np.int64) + 1)
+    big = rng.integers(0, 1000, 300_000)
+    _check_gb(rc, [big], cutoffs=np.array([1, 1, 100_000, 250_000, 300_000], dtype=np.int64))
+    _check_gb(rc, [big, big % 7], filter=rng.random(300_000) < 0.7, cutoffs=np.array([123_457, 300_000], dtype=np.int64))
+
+
+def test_errors_and_empty(rc):
+    ik, ifk, u = rc.MultiKeyGroupBy32([np.zeros(0, np.int64)], 0, None, 2)
+    assert u == 0 and len(ik) == 0 and len(ifk) == 0
+    with pytest.raises(ValueError):
+        rc.MultiKeyGroupBy32([np.zeros(3), np.zeros(4)], 0, None, 2)
+    with pytest.raises(ValueError):
+        rc.MultiKeyGroupBy32([], 0, None, 2)
+
+
+VAL_DTYPES = [np.bool_, np.int8, np.uint8, np.int16, np.uint16, np.int32, np.uint32, np.int64, np.uint64, np.float32,
+              np.float64]
+FUNCS = [0, 1, 2, 3, 4, 5, 50, 51, 52, 53, 54, 55]
+
+
+def _values(rng, dt, n, invalid_frac):
+    dt = np.dtype(dt)
+    if dt.kind == "b":
+        return rng.integers(0, 2, n).astype(dt)
+    if dt.kind == "f":
+        v = (rng.random(n) * 2e4 - 1e4).astype(dt)
+    elif dt.kind == "i":
+        v = rng.integers(-100 if dt.itemsize == 1 else -10_000, 100 if dt.itemsize == 1 else 10_000, n).astype(dt)
+    else:
+        v = rng.integers(0, 200 if dt.itemsize == 1 else 20_000, n).astype(dt)
+    if invalid_frac > 0:
+        v[rng.random(n) < invalid_frac] = orc.invalid_for(dt)
+    return v
+
+
+def _cmp_reduce(got, exp, vdt):
+    assert got.dtype == exp.dtype, (got.dtype, exp.dtype)
+    if exp.dtype.kind == "f":
+        rtol = 1e-5 if np.dtype(vdt) == np.float32 else 1e-12
+        # relative to the magnitude of the data, not of a possibly cancelling result
+        np.testing.assert_allclose(got, exp, rtol=rtol, atol=rtol * 2e4 * 50, equal_nan=True)
+    else:
+        np.testing.assert_array_equal(got, exp)
+
+
+@pytest.mark.parametrize("kdt", [np.int8, np.int16, np.int32, np.int64])
+@pytest.mark.parametrize("nb", [3, 90, 20_000])
+def test_reduce_all_ops_all_dtypes(rc, kdt, nb):
+    if nb > np.iinfo(kdt).max:
+        pytest.skip("bins do not fit the key dtype")
+    rng = np.random.default_rng(nb)
+    n = 150_001
+    ikey = rng.integers(0, nb + 1, n).astype(kdt)
+    ikey[ikey == 2] = 1  # bin 2 stays empty
+    for vdt in VAL_DTYPES:
+        for frac in (0.0, 0.2):
+            v = _values(rng, vdt, n, frac)
+            for fn in FUNCS:
+                for lo in (1, 0):
+                    got = rc.GroupByAll32([v], ikey, nb, [fn], [lo], [nb + 1], 0)[0]
+                    exp = orc.GroupByAll32([v], ikey, nb, [fn], [lo], [nb + 1], 0)[0]
+                    _cmp_reduce(got[lo:], exp[lo:], vdt)
+                    if lo == 1 and fn in (0, 50):
+                        assert got[0] == 0
+
+
+def test_reduce_unsupported_and_kat(rc):
+    ikey = np.array([2, 1, 2, 1, 2], dtype=np.int8)
+    s = np.array([b"3", b"4", b"5", b"1", b"2"])
+    v = np.array([3, 4, 5, 1, 2], dtype=np.int32)
+    out = rc.GroupByAll32([s, v], ikey, 2, [0, 0], [1, 1], [3, 3], 0)
+    assert out[0] is None and out[1][1:].tolist() == [5, 10] and out[1].dtype == np.int64
+    # all-invalid and extreme values
+    x = np.array([np.iinfo(np.int64).max] * 3 + [np.iinfo(np.int64).min] * 2, dtype=np.int64)
+    ik = np.array([1, 1, 1, 2, 2], dtype=np.int32)
+    for fn in (2, 3, 52, 53):
+        got = rc.GroupByAll32([x], ik, 3, [fn], [1], [4], 0)[0]
+        exp = orc.GroupByAll32([x], ik, 3, [fn], [1], [4], 0)[0]
+        np.testing.assert_array_equal(got, exp)
+    xu = np.array([0, 0, np.iinfo(np.uint64).max, 5], dtype=np.uint64)
+    ik = np.array([1, 1, 2, 2], dtype=np.int32)
+    for fn in (2, 3, 52, 53):
+        np.testing.assert_array_equal(rc.GroupByAll32([xu], ik, 2, [fn], [1], [3], 0)[0],
+                                      orc.GroupByAll32([xu], ik, 2, [fn], [1], [3], 0)[0])
+
+
+def test_bincount_and_combine_filter(rc):
+    rng = np.random.default_rng(5)
+    for kdt, nb in [(np.int8, 50), (np.int16, 3000), (np.int32, 70_000), (np.int64, 10)]:
+        n = 333_333
+        ikey = rng.integers(0, nb, n).astype(kdt)
+        got = rc.BinCount(ikey, nb)
+        assert got.dtype == np.int32
+        np.testing.assert_array_equal(got, np.bincount(ikey, minlength=nb))
+        f = rng.random(n) < 0.5
+        cf = rc.CombineFilter(ikey, f)
+        assert cf.dtype == ikey.dtype
+        np.testing.assert_array_equal(cf, np.where(f, ikey, 0))
+
+
+def test_device_mode_chain(rc):
+    import torch
+
+    rng = np.random.default_rng(9)
+    n = 1_000_000
+    k = rng.integers(0, 5000, n).astype(np.int64) * 7919
+    v = rng.random(n)
+    kt, vt = torch.from_numpy(k).cuda(), torch.from_numpy(v).cuda()
+    ik, ifk, u = rc.MultiKeyGroupBy32([kt], 0, None, 2)
+    assert ik.is_cuda and ifk.is_cuda and ik.dtype == torch.int32
+    s = rc.GroupByAll32([vt], ik, u, [0], [1], [u + 1], 0)[0]
+    assert s.is_cuda
+    ok, ofk, ou = orc.MultiKeyGroupBy32([k])
+    assert u == ou
+    np.testing.assert_array_equal(ik.cpu().numpy(), ok)
+    exp = orc.GroupByAll32([v], ok, ou, [0], [1], [ou + 1], 0)[0]
+    np.testing.assert_allclose(s.cpu().numpy()[1:], exp[1:], rtol=1e-12)

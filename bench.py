@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py — groupby-sum rows/s on BASELINE.json's C2 workload (int64 key, 1M uniques, f64 value).
+
+One "step" = one pass of the hot path over one batch of synthetic rows:
+    rc.MultiKeyGroupBy32([key])            -> iKey, iFirstKey, unique_count      (a1)
+    rc.GroupByAll32([value], iKey, ... GB_SUM)                                   (a5)
+(+ for N > 1: the shard merge of riptable_b200.dist — all-gather of per-shard uniques, global
+renumbering, iKey remap, all-reduce of the per-bin partial sums.)
+
+  value : whole-job rows/s with inputs resident in HBM (device mode of the rc shim), CUDA-event timed.
+  e2e   : same metric through the host-buffer (NumPy) mode of the rc shim: pinned host inputs,
+          H2D of key+value and D2H of iKey/iFirstKey/sums inside the timed region.
+  roofline : the dominant kernel's algorithmic bytes / its own CUDA-event duration (rtb_profile_*),
+          against MEASURED_PEAKS.json's HBM copy bandwidth.
+  cpu_baseline : the C restatement of the reference algorithm (oracle/oracle.c) on a bounded sample.
+
+`--impl reference` times that CPU restatement instead (riptide_cpp itself is not available: SURVEY 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "groupby-sum rows/s (int64 key, 1M uniques, f64 value)"
+UNIT = "rows/s"
+ALG_BYTES_HASH = 12  # int64 key read + int32 iKey write           
+ALG_BYTES_SUM = 12   # int32 iKey read + f64 value read            
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=int(os.environ.get("RTB_BENCH_ROWS", 1_000_000_000)),
+                    help="rows per GPU (weak scaling: every rank runs the C2 shard)")
+    ap.add_argument("--uniques", type=int, default=1_000_000)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU sample (0 = size for ~15 s)")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def make_data(torch, dev, rows, uniques, seed):
+    """C2 recipe: key = U_vals[idx], U_vals = `uniques` distinct int64 drawn from the full
+    int64 range (non-consecutive), value f64 uniform(-1, 1).  Generated on the device, seeded."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(12345)  # the unique key values are the same on every rank
+    uvals = torch.randint(-(2**63), 2**63 - 1, (uniques,), dtype=torch.int64, device=dev, generator=g)
+    g.manual_seed(12345 + 7919 * (seed + 1))
+    key = torch.empty(rows, dtype=torch.int64, device=dev)
+    val = torch.empty(rows, dtype=torch.float64, device=dev)
+    chunk = 1 << 27
+    for s in range(0, rows, chunk):
+        e = min(rows, s + chunk)
+        idx = torch.randint(0, uniques, (e - s,), dtype=torch.int64, device=dev, generator=g)
+        torch.index_select(uvals, 0, idx, out=key[s:e])
+        val[s:e].uniform_(-1.0, 1.0, generator=g)
+        del idx
+    return key, val
+
+
+def cpu_arm(rows, uniques, steps, warmup, sample_rows=0):
+    """The CPU restatement (oracle/oracle.c) on a bounded sample of the same recipe."""
+    from oracle import c_oracle
+
+    c_oracle.build()
+    threads = c_oracle.max_threads()
+    rng = np.random.default_rng(12345)
+    uvals = rng.integers(-(2**63), 2**63 - 1, uniques, dtype=np.int64)
+
+    def run(n):
+        key = uvals[rng.integers(0, uniques, n)]
+        val = rng.random(n) * 2.0 - 1.0
+        ts = []
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            ik, ifk, u = c_oracle.groupby_u64(key)
+            s = c_oracle.sum_f64(val, ik, u, threads=threads)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                ts.append(dt)
+        return ts
+
+    n = sample_rows
+    if n <= 0:
+        probe = min(rows, 4_000_000)
+        t = statistics.median(run_quick(c_oracle, uvals, rng, probe, threads))
+        budget = 15.0 / max(1, (warmup + steps))
+        n = int(min(rows, max(probe, probe * budget / max(t, 1e-6)), 200_000_000))
+    ts = run(n)
+    total = sum(ts)
+    return {"value": n * len(ts) / total, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n} rows of the C2 recipe per step, {len(ts)} steps; hash stage sequential (as the reference "
+                      f"without cutoffs), sum stage {threads} OpenMP threads over bin ranges",
+            "ms_per_step": 1e3 * total / len(ts), "rows": n}
+
+
+def run_quick(c_oracle, uvals, rng, n, threads):
+    key = uvals[rng.integers(0, len(uvals), n)]
+    val = rng.random(n)
+    ts = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        ik, ifk, u = c_oracle.groupby_u64(key)
+        c_oracle.sum_f64(val, ik, u, threads=threads)
+        ts.append(time.perf_counter() - t0)
+    return ts
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        cb = cpu_arm(a.rows, a.uniques, a.steps, max(a.warmup, 1), a.cpu_rows)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "int64 keys / f64 sums", "data": "synthetic",
+                "config": {"workload": "C2: int64 key, 1M uniques, gb sum of f64 (bounded CPU sample)",
+                           "rows_per_step": cb["rows"], "uniques": a.uniques},
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this framework has no CPU product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import riptable_b200.rc as rc
+    from riptable_b200 import _lib
+    from riptable_b200.enums import GB_FUNCTIONS
+
+    dist = None
+    if world > 1:
+        import torch.distributed as tdist
+
+        tdist.init_process_group("nccl", device_id=dev)
+        from riptable_b200 import dist as rdist
+
+        dist = rdist
+
+    rows, U = a.rows, a.uniques
+    key, val = make_data(torch, dev, rows, U, rank)
+    torch.cuda.synchronize()
+
+    def step_device():
+        if dist is None:
+            ik, ifk, u = rc.MultiKeyGroupBy32([key], 0, None, 2)
+            s = rc.GroupByAll32([val], ik, u, [GB_FUNCTIONS.GB_SUM], [1], [u + 1], 0)[0]
+            return ik, ifk, u, s
+        return dist.sharded_groupby_sum([key], val)
+
+    def barrier():
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        out = step_device()
+    del out
+    barrier()
+    _lib.lib.rtb_profile_enable(1)
+    _lib.lib.rtb_profile_reset()
+    launches0 = _lib.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        out = step_device()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0
+    uniq_found = int(out[2])
+    del out
+    prof = {name: _lib.profile_get(pid) for name, pid in (("gb_round", 0), ("accum", 1))}
+    _lib.lib.rtb_profile_enable(0)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = rows * world * a.steps / (ms / 1e3)
+
+    # ---- end to end through the host-buffer API (rank-local; every rank does the same work) ----------
+    e2e = None
+    if not a.no_e2e:
+        hk = torch.empty(rows, dtype=torch.int64, pin_memory=True)
+        hv = torch.empty(rows, dtype=torch.float64, pin_memory=True)
+        hk.copy_(key); hv.copy_(val)
+        torch.cuda.synchronize()
+        nk, nv = hk.numpy(), hv.numpy()
+
+        def step_host():
+            ik, ifk, u = rc.MultiKeyGroupBy32([nk], 0, None, 2)
+            s = rc.GroupByAll32([nv], ik, u, [GB_FUNCTIONS.GB_SUM], [1], [u + 1], 0)[0]
+            return ik, ifk, u, s
+
+        del key, val
+        torch.cuda.empty_cache()
+        e2e_steps = max(1, min(a.steps, 3))
+        step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ik, ifk, u, s = step_host()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+            dt = float(t.item())
+        # host mode uploads key+value for a1/a5, re-uploads the iKey it was handed back, downloads results
+        h2d = rows * 8 + rows * 8 + rows * 4
+        d2h = rows * 4 + u * 4 + (u + 1) * 8
+        e2e = {"value": rows * world * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "steps": e2e_steps, "note": "rc host mode: pinned NumPy inputs in, NumPy iKey/iFirstKey/sums out; PCIe-bound"}
+        del hk, hv, nk, nv, ik, s
+
+    if rank != 0:
+        if world > 1:
+            tdist.destroy_process_group()
+        return 0
+
+    peak, peak_src = peaks()
+    kern = {}
+    for name, (pms, pl, pu) in prof.items():
+        if pl:
+            bytes_per_row = ALG_BYTES_HASH if name == "gb_round" else ALG_BYTES_SUM
+            kern[name] = {"ms_total": pms, "launches": pl, "rows": pu, "alg_bytes_per_row": bytes_per_row,
+                          "achieved_gbs": pu * bytes_per_row / (pms / 1e3) / 1e9}
+    dom = max(kern, key=lambda k: kern[k]["ms_total"]) if kern else None
+    roofline = None
+    if dom:
+        k = kern[dom]
+        roofline = {"bound": "hbm", "kernel": "gb_round_direct<8>" if dom == "gb_round" else "accum_kernel<OP_SUMF,false>",
+                    "achieved": k["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": k["achieved_gbs"] / peak,
+                    "traffic": None, "peak_source": peak_src,
+                    "alg_bytes_per_launch": k["rows"] * k["alg_bytes_per_row"] / k["launches"],
+                    "avg_launch_ms": k["ms_total"] / k["launches"]}
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                roofline["traffic"] = json.load(open(tp)).get(dom)
+            except Exception:
+                pass
+    step_bytes = (ALG_BYTES_HASH + ALG_BYTES_SUM) * rows
+    cb = None
+    if not a.no_cpu:
+        try:
+            cb = cpu_arm(rows, U, 2, 1, a.cpu_rows)
+            cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as ex:  # the CPU leg must never take the GPU number down with it
+            cb = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int64 keys / f64 sums", "data": "synthetic",
+        "config": {"workload": "C2: int64 key (1M uniques drawn from the full int64 range), gb sum of f64",
+                   "rows_per_gpu": rows, "uniques": U, "unique_count_found": uniq_found,
+                   "l2": "inputs (16 B/row x rows) are far larger than the 126 MB L2; no explicit flush",
+                   "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+        "roofline": roofline,
+        "step_hbm_frac": step_bytes / (ms / a.steps / 1e3) / 1e9 / peak,
+        "kernels": kern,
+        "cpu_baseline": cb,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        tdist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

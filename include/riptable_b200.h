@@ -28,7 +28,8 @@ extern "C" {
 
 typedef enum {
   RTB_BOOL = 0, RTB_I8, RTB_U8, RTB_I16, RTB_U16, RTB_I32, RTB_U32, RTB_I64, RTB_U64, RTB_F32, RTB_F64,
-  RTB_BYTES
+  RTB_BYTES, /* fixed-width bytes (numpy S / void): memcmp order */
+  RTB_UCS4   /* fixed-width UTF-32 (numpy U): code-point order; grouped bytewise like RTB_BYTES */
 } rtb_dtype;
 
 typedef enum {
@@ -59,6 +60,13 @@ int rtb_version(void);
 const char* rtb_last_error(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 uint64_t rtb_launch_count(void);
+
+/* Optional per-kernel timing with CUDA events on the launching stream (off by default).
+ * ids: 0 hash-group round kernel, 1 reduce accumulate kernel, 2 radix histogram, 3 radix scatter,
+ *      4 segmented scan, 5 key gather.  `units` = rows the timed launches processed. */
+void rtb_profile_enable(int on);
+void rtb_profile_reset(void);
+int rtb_profile_get(int id, double* ms, uint64_t* launches, uint64_t* units);
 
 /* ---- a1: rc.MultiKeyGroupBy32(list, hint_size, filter, hash_mode, cutoffs=)  — riptable/rt_numpy.py:2073-2075
  * Hash-groups the (multi)key rows; bins numbered by first appearance among rows passing `filter`.

@@ -31,6 +31,9 @@ PROTOTYPES = {
     "rtb_version": (C.c_int, []),
     "rtb_last_error": (C.c_char_p, []),
     "rtb_launch_count": (C.c_uint64, []),
+    "rtb_profile_enable": (None, [_i32]),
+    "rtb_profile_reset": (None, []),
+    "rtb_profile_get": (C.c_int, [_i32, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "rtb_groupby_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "rtb_multikey_groupby32": (
         C.c_int,
@@ -74,6 +77,12 @@ for _name, (_res, _args) in PROTOTYPES.items():
 
 def last_error() -> str:
     return lib.rtb_last_error().decode("utf-8", "replace")
+
+
+def profile_get(pid: int):
+    ms, launches, units = C.c_double(0), C.c_uint64(0), C.c_uint64(0)
+    lib.rtb_profile_get(pid, C.byref(ms), C.byref(launches), C.byref(units))
+    return ms.value, launches.value, units.value
 
 
 def launch_count() -> int:

@@ -43,6 +43,12 @@ inline void count_launch(int n = 1) { g_launches += (uint64_t)n; }
     }                                 \
   } while (0)
 
+// ---- optional per-kernel timing (CUDA events on the launching stream; bench.py's roofline leg) --------
+enum ProfId { PROF_GB_ROUND = 0, PROF_ACCUM = 1, PROF_RADIX_HIST = 2, PROF_RADIX_SCATTER = 3, PROF_SEGSCAN = 4, PROF_GATHER = 5, PROF_COUNT = 8 };
+extern int g_prof_on;
+void prof_begin(int id, cudaStream_t s);
+void prof_end(int id, cudaStream_t s, uint64_t units);
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Bump allocator over the caller's workspace.

@@ -306,6 +306,7 @@ static RedLayout red_layout(void* ws, size_t n, int64_t nb) {
 template <int OP>
 static int launch_accum(const AccumArgs& a, cudaStream_t stream) {
   if (a.n <= 0) return RTB_OK;
+  prof_begin(PROF_ACCUM, stream);
   if (a.nb <= kSmemBins) {
     size_t smem = (size_t)a.nb * (8 + 4 + 1) + 16;
     // enough CTAs to fill the machine, few enough that the per-CTA flush stays negligible
@@ -315,6 +316,7 @@ static int launch_accum(const AccumArgs& a, cudaStream_t stream) {
     accum_kernel<OP, false><<<grid_for(a.n, 256, 4, 8), 256, 0, stream>>>(a);
   }
   RTB_LAUNCH_CHECK();
+  prof_end(PROF_ACCUM, stream, (uint64_t)a.n);
   return RTB_OK;
 }
 

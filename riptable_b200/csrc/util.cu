@@ -16,6 +16,43 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// ---- profiling slots ---------------------------------------------------------------------------
+int g_prof_on = 0;
+struct ProfPending { int id; cudaEvent_t a, b; uint64_t units; };
+static ProfPending g_pending[4096];
+static int g_npending = 0;
+static cudaEvent_t g_open[PROF_COUNT];
+static double g_prof_ms[PROF_COUNT];
+static uint64_t g_prof_launches[PROF_COUNT], g_prof_units[PROF_COUNT];
+
+static void prof_drain() {
+  for (int i = 0; i < g_npending; i++) {
+    ProfPending& p = g_pending[i];
+    float ms = 0.f;
+    if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+      g_prof_ms[p.id] += ms;
+      g_prof_launches[p.id] += 1;
+      g_prof_units[p.id] += p.units;
+    }
+    cudaEventDestroy(p.a);
+    cudaEventDestroy(p.b);
+  }
+  g_npending = 0;
+}
+void prof_begin(int id, cudaStream_t s) {
+  if (!g_prof_on) return;
+  cudaEventCreate(&g_open[id]);
+  cudaEventRecord(g_open[id], s);
+}
+void prof_end(int id, cudaStream_t s, uint64_t units) {
+  if (!g_prof_on) return;
+  if (g_npending == 4096) prof_drain();
+  ProfPending& p = g_pending[g_npending++];
+  p.id = id; p.a = g_open[id]; p.units = units;
+  cudaEventCreate(&p.b);
+  cudaEventRecord(p.b, s);
+}
+
 // ---------------------------------------------------------------------------------------------
 // exclusive scan: tile = 256 threads x 16 items
 constexpr int kScanThreads = 256;
@@ -170,6 +207,20 @@ extern "C" {
 int rtb_version(void) { return 100; }
 const char* rtb_last_error(void) { return g_err; }
 uint64_t rtb_launch_count(void) { return g_launches; }
+
+void rtb_profile_enable(int on) { g_prof_on = on; }
+void rtb_profile_reset(void) {
+  prof_drain();
+  for (int i = 0; i < PROF_COUNT; i++) { g_prof_ms[i] = 0; g_prof_launches[i] = 0; g_prof_units[i] = 0; }
+}
+int rtb_profile_get(int id, double* ms, uint64_t* launches, uint64_t* units) {
+  if (id < 0 || id >= PROF_COUNT) return RTB_ERR_ARG;
+  prof_drain();
+  if (ms) *ms = g_prof_ms[id];
+  if (launches) *launches = g_prof_launches[id];
+  if (units) *units = g_prof_units[id];
+  return RTB_OK;
+}
 
 int rtb_combine_filter(const void* ikey, int kdtype, const uint8_t* filter, int64_t nrows, void* out, void* stream) {
   RTB_ARG(is_ikey_dtype(kdtype), "CombineFilter: key must be int8/16/32/64");

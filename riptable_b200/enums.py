@@ -42,7 +42,7 @@ class GB_FUNCTIONS(IntEnum):
 GB_FUNC_COUNT = -1
 
 # Canonical element type codes used across the C ABI (include/riptable_b200.h: rtb_dtype).
-RTB_BOOL, RTB_I8, RTB_U8, RTB_I16, RTB_U16, RTB_I32, RTB_U32, RTB_I64, RTB_U64, RTB_F32, RTB_F64, RTB_BYTES = range(12)
+RTB_BOOL, RTB_I8, RTB_U8, RTB_I16, RTB_U16, RTB_I32, RTB_U32, RTB_I64, RTB_U64, RTB_F32, RTB_F64, RTB_BYTES, RTB_UCS4 = range(13)
 
 _KIND_SIZE_TO_CODE = {
     ("b", 1): RTB_BOOL,
@@ -76,7 +76,9 @@ _CODE_TO_NP = {
 def dtype_code(dt) -> int:
     """numpy dtype -> rtb_dtype code; fixed-width S/U/void items map to RTB_BYTES."""
     dt = np.dtype(dt)
-    if dt.kind in "SUV":
+    if dt.kind == "U":
+        return RTB_UCS4
+    if dt.kind in "SV":
         return RTB_BYTES
     if dt.kind in "mM":  # datetime64/timedelta64 are int64 payloads
         return RTB_I64

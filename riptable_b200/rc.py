@@ -256,7 +256,7 @@ def GroupByAll32(values, ikey, unique_rows, funcList, binLowList, binHighList, f
         if d.n != k.n:
             raise ValueError(f"GroupByAll32: value length {d.n} does not match ikey length {k.n}")
         vcode = dtype_code(d.dtype) if d.dtype.kind in "biuf" and d.dtype.itemsize <= 8 and d.dtype != np.float16 else RTB_BYTES
-        ocode = lib.rtb_reduce_out_dtype(int(f), vcode) if vcode != RTB_BYTES else -1
+        ocode = lib.rtb_reduce_out_dtype(int(f), vcode) if vcode < RTB_BYTES else -1
         if ocode < 0:
             out.append(None)
             continue
@@ -358,7 +358,7 @@ def EmaAll32(values, ikey, unique_rows, funcNum, func_param):
     for v in values:
         d = _to_dev(v)
         vcode = dtype_code(d.dtype) if d.dtype.kind in "biuf" and d.dtype != np.float16 else RTB_BYTES
-        ocode = lib.rtb_cumsum_out_dtype(vcode) if vcode != RTB_BYTES else -1
+        ocode = lib.rtb_cumsum_out_dtype(vcode) if vcode < RTB_BYTES else -1
         if ocode < 0:
             out.append(None)
             continue

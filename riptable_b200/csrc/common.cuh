@@ -14,6 +14,7 @@ constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs; persistent grids are sized 
 // ---- error plumbing -------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 extern uint64_t g_launches;
+extern int g_debug_sync;  // RTB_DEBUG_SYNC=1: synchronise the device after every launch (debugging aid)
 inline void count_launch(int n = 1) { g_launches += (uint64_t)n; }
 
 #define RTB_CUDA(call)                                                                      \
@@ -28,6 +29,7 @@ inline void count_launch(int n = 1) { g_launches += (uint64_t)n; }
 #define RTB_LAUNCH_CHECK()                                                                  \
   do {                                                                                      \
     rtb::count_launch();                                                                    \
+    if (rtb::g_debug_sync) cudaDeviceSynchronize();                                         \
     cudaError_t _e = cudaGetLastError();                                                    \
     if (_e != cudaSuccess) {                                                                \
       rtb::set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \

@@ -1,0 +1,468 @@
+// a7 / a8 / a9 / a10: the packed layout and what is computed through it.
+//
+//   rc.BinCount(pack=True) / rc.GroupFromBinCount / rc.GroupByPack32  (riptable/rt_numpy.py:1945-1972)
+//       stable bucket sort of the row ids by bin = LSD radix sort on the low bits of iKey (radix.cu)
+//   rc.GroupByAllPack32 first / nth / last                            (riptable/rt_numpy.py:1891)
+//   rc.EmaAll32 GB_CUMSUM                                             (riptable/rt_grouping.py:3430)
+//       segmented inclusive scan over the packed order, scattered back to row order
+//   rc.MakeiFirst / rc.MakeiNext                                      (riptable/rt_numpy.py:1791-1854)
+#include "common.cuh"
+#include "radix.cuh"
+#include "values.cuh"
+
+extern "C" int rtb_bincount(const void* ikey, int kdt, int64_t nrows, int64_t nbins, int32_t* out, void* stream);
+
+namespace rtb {
+
+// ---- iKey -> uint32 sort keys; rows outside [0, nbins) are counted (the caller rejects the input) ------------
+__global__ void __launch_bounds__(256) pack_keys_kernel(const void* __restrict__ ikey, int kdt, int64_t n, int64_t nbins,
+                                                        uint32_t* __restrict__ keys, uint32_t* bad) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  uint32_t nbad = 0;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; r < n; r += stride) {
+    if (r + 3 < n) {
+      int64_t k[4];
+      load_ikey4(ikey, kdt, r, k);
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        if (k[i] < 0 || k[i] >= nbins) { nbad++; k[i] = 0; }
+      *(uint4*)(keys + r) = make_uint4((uint32_t)k[0], (uint32_t)k[1], (uint32_t)k[2], (uint32_t)k[3]);
+    } else {
+      for (int64_t q = r; q < n; q++) {
+        int64_t k = load_ikey(ikey, kdt, q);
+        if (k < 0 || k >= nbins) { nbad++; k = 0; }
+        keys[q] = (uint32_t)k;
+      }
+    }
+  }
+  if (nbad) atomicAdd(bad, nbad);
+}
+
+struct PackLayout {
+  uint32_t *keys_a, *keys_b, *vals_a, *vals_b, *bad, *scan_scratch;
+  void* radix_ws;
+  size_t radix_bytes, bytes;
+};
+static PackLayout pack_layout(void* ws, size_t wsbytes, int64_t n, int64_t nbins) {
+  Arena a(ws, wsbytes);
+  PackLayout L;
+  L.scan_scratch = a.take<uint32_t>(scan_u32_workspace_elems(nbins > 0 ? nbins : 1));
+  size_t m = (size_t)(n > 0 ? n : 1);
+  L.keys_a = a.take<uint32_t>(m);
+  L.keys_b = a.take<uint32_t>(m);
+  L.vals_a = a.take<uint32_t>(m);
+  L.vals_b = a.take<uint32_t>(m);
+  L.bad = a.take<uint32_t>(4);
+  L.radix_bytes = radix_workspace_bytes(n);
+  L.radix_ws = a.take<uint8_t>(L.radix_bytes);
+  L.bytes = a.off;
+  return L;
+}
+
+static int bits_for(int64_t nbins) {
+  int b = 1;
+  while (b < 32 && (1ll << b) < nbins) b++;
+  return b;
+}
+
+// Sorts row ids by bin (stable).  On return *sorted_keys / *igroup point at the buffers (inside the workspace)
+// holding the bins in packed order and the packed row ids.  Synchronises the stream.
+static int pack_sort(const void* ikey, int kdt, int64_t n, int64_t nbins, const PackLayout& L, cudaStream_t stream,
+                     uint32_t** sorted_keys, uint32_t** igroup, const char* who) {
+  RTB_CUDA(cudaMemsetAsync(L.bad, 0, sizeof(uint32_t), stream));
+  pack_keys_kernel<<<grid_for(n, 256, 4), 256, 0, stream>>>(ikey, kdt, n, nbins, L.keys_a, L.bad);
+  RTB_LAUNCH_CHECK();
+  uint32_t hbad = 0;
+  RTB_CUDA(cudaMemcpyAsync(&hbad, L.bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+  int in_b = 0;
+  int rc = radix_sort_pairs<uint32_t>(L.keys_a, L.vals_a, L.keys_b, L.vals_b, n, bits_for(nbins), true, L.radix_ws,
+                                      L.radix_bytes, stream, &in_b);
+  if (rc != RTB_OK) return rc;
+  RTB_CUDA(cudaStreamSynchronize(stream));
+  RTB_ARG(hbad == 0, "%s: %u ikey values lie outside [0, %lld)", who, hbad, (long long)nbins);
+  *sorted_keys = in_b ? L.keys_b : L.keys_a;
+  *igroup = in_b ? L.vals_b : L.vals_a;
+  return RTB_OK;
+}
+
+// ---- a8: first / nth / last ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pick_kernel(const uint8_t* __restrict__ values, int vdt, int itemsize,
+                                                   const int32_t* __restrict__ igroup, const int32_t* __restrict__ ifirst,
+                                                   const int32_t* __restrict__ ncount, int64_t nb, int func, int64_t nth,
+                                                   int64_t lo, int64_t hi, uint8_t* __restrict__ out) {
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (int64_t)gridDim.x * blockDim.x) {
+    int64_t cnt = ncount[b];
+    int64_t off = func == RTB_GB_FIRST ? 0 : func == RTB_GB_LAST ? cnt - 1 : (nth >= 0 ? nth : cnt + nth);
+    bool ok = off >= 0 && off < cnt && b >= lo && b < hi;
+    uint8_t* dst = out + b * (int64_t)itemsize;
+    if (ok) {
+      const uint8_t* src = values + (int64_t)igroup[(int64_t)ifirst[b] + off] * itemsize;
+      for (int i = 0; i < itemsize; i++) dst[i] = src[i];
+    } else if (vdt <= RTB_F64) {
+      unsigned long long inv = invalid_raw(vdt);
+      for (int i = 0; i < itemsize; i++) dst[i] = (uint8_t)(inv >> (8 * i));
+    } else {
+      for (int i = 0; i < itemsize; i++) dst[i] = 0;  // b'' / ''
+    }
+  }
+}
+
+// ---- a9: cumsum ------------------------------------------------------------------------------------------
+constexpr int kSegThreads = 256;
+constexpr int kSegItems = 8;
+constexpr int kSegTile = kSegThreads * kSegItems;
+
+struct SegPair {
+  unsigned long long v;  // f64 bits or 64-bit integer
+  uint32_t f;            // a segment head lies inside the summarised range
+};
+
+template <bool FLOAT>
+__device__ __forceinline__ unsigned long long seg_add(unsigned long long a, unsigned long long b) {
+  if (FLOAT) return (unsigned long long)__double_as_longlong(__longlong_as_double((long long)a) + __longlong_as_double((long long)b));
+  return a + b;
+}
+template <bool FLOAT>
+__device__ __forceinline__ SegPair seg_combine(SegPair a, SegPair b) {  // a precedes b
+  SegPair r;
+  r.f = a.f | b.f;
+  r.v = b.f ? b.v : seg_add<FLOAT>(a.v, b.v);
+  return r;
+}
+
+// inclusive scan of SegPair across the block; returns this thread's EXCLUSIVE prefix and the block total
+template <bool FLOAT>
+__device__ __forceinline__ SegPair seg_block_exclusive(SegPair x, SegPair* total) {
+  __shared__ SegPair wtot[kSegThreads / 32];
+  __shared__ SegPair btot;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  SegPair inc = x;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    SegPair t;
+    t.v = __shfl_up_sync(0xffffffffu, inc.v, d);
+    t.f = __shfl_up_sync(0xffffffffu, inc.f, d);
+    if (lane >= d) inc = seg_combine<FLOAT>(t, inc);
+  }
+  if (lane == 31) wtot[w] = inc;
+  __syncthreads();
+  SegPair ex;  // exclusive prefix = (previous warps) o (previous lanes)
+  ex.v = 0; ex.f = 0;
+  for (int i = 0; i < w; i++) ex = seg_combine<FLOAT>(ex, wtot[i]);
+  SegPair prev;
+  prev.v = __shfl_up_sync(0xffffffffu, inc.v, 1);
+  prev.f = __shfl_up_sync(0xffffffffu, inc.f, 1);
+  if (lane > 0) ex = seg_combine<FLOAT>(ex, prev);
+  if (threadIdx.x == kSegThreads - 1) btot = seg_combine<FLOAT>(ex, x);
+  __syncthreads();
+  *total = btot;
+  __syncthreads();
+  return ex;
+}
+
+struct CumArgs {
+  const void* values;
+  int vdt, odt;
+  const uint32_t* skeys;   // bins in packed order
+  const uint32_t* igroup;  // packed row ids
+  const uint8_t* filter;
+  const uint8_t* reset;
+  int64_t n;
+  unsigned long long* xs;  // gathered addends in packed order
+  uint8_t* heads;          // segment-head flags in packed order
+  SegPair* tile_agg;
+  void* out;
+};
+
+// pass 1: gather addends, mark heads, reduce each tile
+template <bool FLOAT>
+__global__ void __launch_bounds__(kSegThreads) cumsum_gather_kernel(CumArgs a) {
+  const int64_t base = (int64_t)blockIdx.x * kSegTile + (int64_t)threadIdx.x * kSegItems;
+  SegPair acc;
+  acc.v = 0; acc.f = 0;
+  const int vsz = dsize(a.vdt);
+#pragma unroll
+  for (int i = 0; i < kSegItems; i++) {
+    int64_t j = base + i;
+    if (j < a.n) {
+      uint32_t row = a.igroup[j];
+      uint32_t k = a.skeys[j];
+      bool add = k != 0 && (!a.filter || a.filter[row]);
+      bool head = j == 0 || a.skeys[j - 1] != k || (a.reset && add && a.reset[row]);
+      unsigned long long x = 0;
+      if (add) {
+        unsigned long long raw = load_raw1(a.values, vsz, row);
+        x = FLOAT ? (unsigned long long)__double_as_longlong(raw_to_f64(raw, a.vdt)) : (unsigned long long)raw_to_i64(raw, a.vdt);
+      }
+      a.xs[j] = x;
+      a.heads[j] = head;
+      SegPair p;
+      p.v = x; p.f = head;
+      acc = seg_combine<FLOAT>(acc, p);
+    }
+  }
+  SegPair total;
+  seg_block_exclusive<FLOAT>(acc, &total);
+  if (threadIdx.x == 0) a.tile_agg[blockIdx.x] = total;
+}
+
+// pass 2 (one block): tile_agg[t] <- combination of all tiles before t
+template <bool FLOAT>
+__global__ void __launch_bounds__(kSegThreads) cumsum_tiles_kernel(SegPair* tile_agg, int64_t ntiles) {
+  SegPair carry;
+  carry.v = 0; carry.f = 0;
+  for (int64_t b = 0; b < ntiles; b += kSegThreads) {
+    int64_t t = b + threadIdx.x;
+    SegPair x;
+    x.v = 0; x.f = 0;
+    if (t < ntiles) x = tile_agg[t];
+    SegPair total;
+    SegPair ex = seg_block_exclusive<FLOAT>(x, &total);
+    if (t < ntiles) tile_agg[t] = seg_combine<FLOAT>(carry, ex);
+    carry = seg_combine<FLOAT>(carry, total);
+  }
+}
+
+// pass 3: running sums inside each tile, scattered to row order
+template <bool FLOAT>
+__global__ void __launch_bounds__(kSegThreads) cumsum_apply_kernel(CumArgs a) {
+  const int64_t base = (int64_t)blockIdx.x * kSegTile + (int64_t)threadIdx.x * kSegItems;
+  unsigned long long x[kSegItems];
+  uint8_t h[kSegItems];
+  SegPair acc;
+  acc.v = 0; acc.f = 0;
+#pragma unroll
+  for (int i = 0; i < kSegItems; i++) {
+    int64_t j = base + i;
+    x[i] = 0; h[i] = 0;
+    if (j < a.n) {
+      x[i] = a.xs[j];
+      h[i] = a.heads[j];
+      SegPair p;
+      p.v = x[i]; p.f = h[i];
+      acc = seg_combine<FLOAT>(acc, p);
+    }
+  }
+  SegPair total;
+  SegPair run = seg_combine<FLOAT>(a.tile_agg[blockIdx.x], seg_block_exclusive<FLOAT>(acc, &total));
+  unsigned long long cur = run.v;
+#pragma unroll
+  for (int i = 0; i < kSegItems; i++) {
+    int64_t j = base + i;
+    if (j < a.n) {
+      cur = h[i] ? x[i] : seg_add<FLOAT>(cur, x[i]);
+      uint32_t row = a.igroup[j];
+      unsigned long long raw;
+      if (a.skeys[j] == 0) raw = invalid_raw(a.odt);
+      else if (a.odt == RTB_F32) raw = __float_as_uint((float)__longlong_as_double((long long)cur));
+      else raw = cur;
+      store_raw(a.out, a.odt, row, raw);
+    }
+  }
+}
+
+struct CumLayout {
+  PackLayout pack;
+  void* pack_ws;
+  unsigned long long* xs;
+  uint8_t* heads;
+  SegPair* tile_agg;
+  size_t pack_bytes, bytes;
+};
+static CumLayout cum_layout(void* ws, size_t wsbytes, int64_t n) {
+  Arena a(ws, wsbytes);
+  CumLayout L;
+  L.pack_bytes = pack_layout(nullptr, 0, n, 1).bytes + 256;
+  L.pack_ws = a.take<uint8_t>(L.pack_bytes);
+  L.pack = pack_layout(L.pack_ws, L.pack_bytes, n, 1);
+  size_t m = (size_t)(n > 0 ? n : 1);
+  L.xs = a.take<unsigned long long>(m);
+  L.heads = a.take<uint8_t>(m);
+  L.tile_agg = a.take<SegPair>((m + kSegTile - 1) / kSegTile + 1);
+  L.bytes = a.off;
+  return L;
+}
+
+// ---- a10 ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ifirst_scan_kernel(const void* __restrict__ ikey, int kdt, int64_t n, int64_t nmax,
+                                                          const uint8_t* __restrict__ filter, int mode, uint32_t* tmp) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+    int64_t k = load_ikey(ikey, kdt, r);
+    if (k > 0 && k <= nmax && (!filter || filter[r])) {
+      if (mode == 0) atomicMin(&tmp[k], (uint32_t)r);
+      else atomicMax(&tmp[k], (uint32_t)r + 1u);
+    }
+  }
+}
+__global__ void __launch_bounds__(256) ifirst_finish_kernel(uint32_t* tmp, int64_t nslots, int mode) {
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nslots; b += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t v = tmp[b];
+    int32_t o;
+    if (mode == 0) o = v == 0xFFFFFFFFu ? INT32_MIN : (int32_t)v;
+    else o = v == 0u ? INT32_MIN : (int32_t)(v - 1u);
+    if (b == 0) o = INT32_MIN;
+    ((int32_t*)tmp)[b] = o;
+  }
+}
+
+__global__ void __launch_bounds__(256) inext_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ igroup,
+                                                    int64_t n, int mode, int32_t* __restrict__ out) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    uint32_t k = skeys[j];
+    int32_t o = INT32_MIN;
+    if (k != 0) {
+      if (mode == 0) {
+        if (j + 1 < n && skeys[j + 1] == k) o = (int32_t)igroup[j + 1];
+      } else {
+        if (j > 0 && skeys[j - 1] == k) o = (int32_t)igroup[j - 1];
+      }
+    }
+    out[igroup[j]] = o;
+  }
+}
+
+}  // namespace rtb
+
+using namespace rtb;
+
+extern "C" size_t rtb_pack_workspace_bytes(int64_t nrows, int64_t nbins) {
+  if (nrows < 0) return 0;
+  return pack_layout(nullptr, 0, nrows, nbins).bytes + 256;
+}
+
+extern "C" int rtb_groupby_pack(const void* ikey, int kdt, int64_t nrows, int64_t nbins, int32_t* igroup_out,
+                                int32_t* ifirstgroup_out, int32_t* ncountgroup_out, void* workspace, size_t workspace_bytes,
+                                void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RTB_ARG(is_ikey_dtype(kdt), "pack: ikey must be int8/16/32/64");
+  RTB_ARG(nrows >= 0 && nrows <= 2147483646ll && nbins >= 1 && nbins < (1ll << 31), "pack: bad sizes");
+  RTB_ARG(ifirstgroup_out && ncountgroup_out, "pack: null output");
+  int rc = rtb_bincount(ikey, kdt, nrows, nbins, ncountgroup_out, stream_);
+  if (rc != RTB_OK) return rc;
+  PackLayout L = pack_layout(workspace, workspace_bytes, nrows, nbins);
+  RTB_ARG(workspace && L.bytes <= workspace_bytes, "pack: workspace too small");
+  // iFirstGroup = exclusive cumsum(nCountGroup)
+  rc = exclusive_scan_u32((const uint32_t*)ncountgroup_out, (uint32_t*)ifirstgroup_out, nbins, SCAN_IDENTITY, L.scan_scratch, nullptr, stream);
+  if (rc != RTB_OK) return rc;
+  if (nrows == 0) return RTB_OK;
+  RTB_ARG(igroup_out, "pack: null iGroup output");
+  uint32_t *skeys, *ig;
+  rc = pack_sort(ikey, kdt, nrows, nbins, L, stream, &skeys, &ig, "pack");
+  if (rc != RTB_OK) return rc;
+  RTB_CUDA(cudaMemcpyAsync(igroup_out, ig, sizeof(int32_t) * (size_t)nrows, cudaMemcpyDeviceToDevice, stream));
+  return RTB_OK;
+}
+
+extern "C" int rtb_groupby_pick(const void* values, int vdt, int32_t itemsize, const int32_t* igroup,
+                                const int32_t* ifirstgroup, const int32_t* ncountgroup, int64_t unique_rows, int func,
+                                int64_t nth, int64_t bin_low, int64_t bin_high, void* out, void* stream) {
+  RTB_ARG(func == RTB_GB_FIRST || func == RTB_GB_NTH || func == RTB_GB_LAST, "GroupByAllPack32: function %d is not first/nth/last", func);
+  RTB_ARG(unique_rows >= 0 && itemsize >= 1 && out && ifirstgroup && ncountgroup, "GroupByAllPack32: bad arguments");
+  RTB_ARG(vdt >= RTB_BOOL && vdt <= RTB_UCS4, "GroupByAllPack32: bad dtype");
+  RTB_ARG(vdt > RTB_F64 || itemsize == dtype_size(vdt), "GroupByAllPack32: itemsize does not match dtype");
+  int64_t nb = unique_rows + 1;
+  pick_kernel<<<grid_for(nb, 256, 1), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)values, vdt, itemsize, igroup, ifirstgroup,
+                                                                      ncountgroup, nb, func, nth, bin_low, bin_high, (uint8_t*)out);
+  RTB_LAUNCH_CHECK();
+  return RTB_OK;
+}
+
+extern "C" int rtb_cumsum_out_dtype(int vdt) {
+  if (vdt < RTB_BOOL || vdt > RTB_F64) return RTB_ERR_UNSUPPORTED;
+  if (vdt == RTB_F32 || vdt == RTB_F64 || vdt == RTB_U64) return vdt;
+  return RTB_I64;
+}
+
+extern "C" size_t rtb_cumsum_workspace_bytes(int64_t nrows, int64_t unique_rows) {
+  (void)unique_rows;
+  if (nrows < 0) return 0;
+  return cum_layout(nullptr, 0, nrows).bytes + 256;
+}
+
+extern "C" int rtb_groupby_cumsum(const void* values, int vdt, const void* ikey, int kdt, int64_t nrows, int64_t unique_rows,
+                                  const uint8_t* filter, const uint8_t* reset_filter, void* out, void* workspace,
+                                  size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RTB_ARG(is_ikey_dtype(kdt), "EmaAll32: ikey must be int8/16/32/64");
+  int odt = rtb_cumsum_out_dtype(vdt);
+  if (odt < 0) {
+    set_error("EmaAll32: cumsum is not provided for dtype %d", vdt);
+    return RTB_ERR_UNSUPPORTED;
+  }
+  RTB_ARG(nrows >= 0 && nrows <= 2147483646ll && unique_rows >= 0, "EmaAll32: bad sizes");
+  if (nrows == 0) return RTB_OK;
+  RTB_ARG(values && ikey && out, "EmaAll32: null pointer");
+  RTB_ARG(((uintptr_t)ikey % (4 * dtype_size(kdt))) == 0, "EmaAll32: ikey must be aligned to 4 rows");
+  CumLayout L = cum_layout(workspace, workspace_bytes, nrows);
+  RTB_ARG(workspace && L.bytes <= workspace_bytes, "EmaAll32: workspace too small");
+  uint32_t *skeys, *ig;
+  int rc = pack_sort(ikey, kdt, nrows, unique_rows + 1, L.pack, stream, &skeys, &ig, "EmaAll32");
+  if (rc != RTB_OK) return rc;
+  CumArgs a;
+  a.values = values; a.vdt = vdt; a.odt = odt; a.skeys = skeys; a.igroup = ig; a.filter = filter; a.reset = reset_filter;
+  a.n = nrows; a.xs = L.xs; a.heads = L.heads; a.tile_agg = L.tile_agg; a.out = out;
+  const int64_t ntiles = (nrows + kSegTile - 1) / kSegTile;
+  const bool fl = vdt == RTB_F32 || vdt == RTB_F64;
+  prof_begin(PROF_SEGSCAN, stream);
+  if (fl) {
+    cumsum_gather_kernel<true><<<(unsigned)ntiles, kSegThreads, 0, stream>>>(a);
+    RTB_LAUNCH_CHECK();
+    cumsum_tiles_kernel<true><<<1, kSegThreads, 0, stream>>>(L.tile_agg, ntiles);
+    RTB_LAUNCH_CHECK();
+    cumsum_apply_kernel<true><<<(unsigned)ntiles, kSegThreads, 0, stream>>>(a);
+    RTB_LAUNCH_CHECK();
+  } else {
+    cumsum_gather_kernel<false><<<(unsigned)ntiles, kSegThreads, 0, stream>>>(a);
+    RTB_LAUNCH_CHECK();
+    cumsum_tiles_kernel<false><<<1, kSegThreads, 0, stream>>>(L.tile_agg, ntiles);
+    RTB_LAUNCH_CHECK();
+    cumsum_apply_kernel<false><<<(unsigned)ntiles, kSegThreads, 0, stream>>>(a);
+    RTB_LAUNCH_CHECK();
+  }
+  prof_end(PROF_SEGSCAN, stream, (uint64_t)nrows);
+  return RTB_OK;
+}
+
+extern "C" int rtb_make_ifirst(const void* ikey, int kdt, int64_t nrows, int64_t n, const uint8_t* filter, int mode,
+                               int32_t* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RTB_ARG(is_ikey_dtype(kdt), "MakeiFirst: key must be int8/16/32/64");
+  RTB_ARG(nrows >= 0 && nrows <= 2147483646ll && n >= 0 && n < (1ll << 31) - 1 && out, "MakeiFirst: bad arguments");
+  RTB_ARG(mode == 0 || mode == 1, "MakeiFirst: mode must be 0 (first) or 1 (last)");
+  RTB_CUDA(cudaMemsetAsync(out, mode == 0 ? 0xFF : 0x00, sizeof(int32_t) * (size_t)(n + 1), stream));
+  if (nrows > 0) {
+    RTB_ARG(ikey, "MakeiFirst: null key");
+    ifirst_scan_kernel<<<grid_for(nrows, 256, 4), 256, 0, stream>>>(ikey, kdt, nrows, n, filter, mode, (uint32_t*)out);
+    RTB_LAUNCH_CHECK();
+  }
+  ifirst_finish_kernel<<<grid_for(n + 1, 256, 1), 256, 0, stream>>>((uint32_t*)out, n + 1, mode);
+  RTB_LAUNCH_CHECK();
+  return RTB_OK;
+}
+
+extern "C" size_t rtb_make_inext_workspace_bytes(int64_t nrows, int64_t n) {
+  (void)n;
+  if (nrows < 0) return 0;
+  return pack_layout(nullptr, 0, nrows, 1).bytes + 256;
+}
+
+extern "C" int rtb_make_inext(const void* ikey, int kdt, int64_t nrows, int64_t n, int mode, int32_t* out, void* workspace,
+                              size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RTB_ARG(is_ikey_dtype(kdt), "MakeiNext: key must be int8/16/32/64");
+  RTB_ARG(nrows >= 0 && nrows <= 2147483646ll && n >= 0 && n < (1ll << 31) - 1, "MakeiNext: bad sizes");
+  RTB_ARG(mode == 0 || mode == 1, "MakeiNext: mode must be 0 (next) or 1 (previous)");
+  if (nrows == 0) return RTB_OK;
+  RTB_ARG(ikey && out, "MakeiNext: null pointer");
+  RTB_ARG(((uintptr_t)ikey % (4 * dtype_size(kdt))) == 0, "MakeiNext: key must be aligned to 4 rows");
+  PackLayout L = pack_layout(workspace, workspace_bytes, nrows, 1);
+  RTB_ARG(workspace && L.bytes <= workspace_bytes, "MakeiNext: workspace too small");
+  uint32_t *skeys, *ig;
+  int rc = pack_sort(ikey, kdt, nrows, n + 1, L, stream, &skeys, &ig, "MakeiNext");
+  if (rc != RTB_OK) return rc;
+  inext_kernel<<<grid_for(nrows, 256, 2), 256, 0, stream>>>(skeys, ig, nrows, mode, out);
+  RTB_LAUNCH_CHECK();
+  return RTB_OK;
+}

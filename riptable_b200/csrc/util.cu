@@ -1,6 +1,7 @@
 // Error state, launch counter, device-wide scan, and the small streaming entry points
 // (CombineFilter, ReverseShuffle, remap).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -8,6 +9,7 @@ namespace rtb {
 
 static thread_local char g_err[512] = "";
 uint64_t g_launches = 0;
+int g_debug_sync = getenv("RTB_DEBUG_SYNC") ? atoi(getenv("RTB_DEBUG_SYNC")) : 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;

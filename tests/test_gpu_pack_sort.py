@@ -1,0 +1,335 @@
+"""GPU parity: packing, first/nth/last, cumsum, MakeiFirst/MakeiNext, LexSort32, GroupFromLexSort, ReverseShuffle
+vs the CPU oracle and vs NumPy (np.lexsort / np.bincount / stable argsort), following the reference's own tests
+(riptable/tests/test_lexsort.py, test_grouping.py, test_groupby.py).  Integer outputs are bit-exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import riptide_oracle as orc
+
+
+@pytest.fixture(scope="module")
+def rc():
+    import riptable_b200.rc as rc
+
+    return rc
+
+
+# ---------------------------------------------------------------------------------------------------- a7
+def test_groupbypack_docstring(rc):
+    # rt_numpy.py:1926-1933
+    np.random.seed(12345)
+    c = np.random.randint(0, 8, 10_000)
+    ik, ifk, u = rc.MultiKeyGroupBy32([c], 0, None, 2)
+    cnt, ig, ifg = rc.BinCount(ik, u + 1, pack=True)
+    assert ifk.tolist() == [0, 1, 3, 4, 6, 14, 18, 20]
+    assert cnt.tolist() == [0, 1213, 1252, 1296, 1226, 1252, 1283, 1275, 1203]
+    assert ifg.tolist() == [0, 0, 1213, 2465, 3761, 4987, 6239, 7522, 8797]
+    assert ig[:3].tolist() == [0, 9, 21] and ig[-3:].tolist() == [9988, 9991, 9992]
+    assert ig.dtype == np.int32 and ifg.dtype == np.int32 and cnt.dtype == np.int32
+
+
+@pytest.mark.parametrize("kdt,nb", [(np.int8, 7), (np.int8, 120), (np.int16, 300), (np.int16, 20_000), (np.int32, 70_000),
+                                    (np.int32, 3_000_000), (np.int64, 257)])
+@pytest.mark.parametrize("n", [1, 4097, 500_003])
+def test_pack_variants(rc, kdt, nb, n):
+    rng = np.random.default_rng(nb + n)
+    ikey = rng.integers(0, nb, n).astype(kdt)
+    cnt, ig, ifg = rc.BinCount(ikey, nb, pack=True)
+    ecnt, eig, eifg = orc.BinCount(ikey, nb, pack=True)
+    np.testing.assert_array_equal(cnt, ecnt)
+    np.testing.assert_array_equal(ig, eig)
+    np.testing.assert_array_equal(ifg, eifg)
+    ig2, ifg2 = rc.GroupFromBinCount(ikey, cnt)
+    np.testing.assert_array_equal(ig2, eig)
+    np.testing.assert_array_equal(ifg2, eifg)
+    ig3, ifg3, cnt3 = rc.GroupByPack32(ikey, None, nb)
+    np.testing.assert_array_equal(ig3, eig)
+    np.testing.assert_array_equal(ifg3, eifg)
+    np.testing.assert_array_equal(cnt3, ecnt)
+
+
+def test_pack_skewed_and_constant(rc):
+    n = 300_000
+    for ikey in (np.zeros(n, np.int32), np.full(n, 5, np.int32), np.repeat(np.arange(300, dtype=np.int32), 1000),
+                 (np.arange(n) % 2).astype(np.int8) * 77):
+        nb = int(ikey.max()) + 1
+        cnt, ig, ifg = rc.BinCount(ikey, nb, pack=True)
+        ecnt, eig, eifg = orc.BinCount(ikey, nb, pack=True)
+        np.testing.assert_array_equal(ig, eig)
+        np.testing.assert_array_equal(ifg, eifg)
+        np.testing.assert_array_equal(cnt, ecnt)
+    with pytest.raises(ValueError):
+        rc.BinCount(np.array([0, 1, 9], np.int32), 3, pack=True)
+
+
+# ---------------------------------------------------------------------------------------------------- a8
+@pytest.mark.parametrize("vdt", [np.bool_, np.int8, np.uint16, np.int32, np.uint64, np.float32, np.float64, "S5", "U3", "S16"])
+def test_first_nth_last(rc, vdt):
+    rng = np.random.default_rng(3)
+    n, nb = 100_000, 3000
+    ikey = rng.integers(0, nb + 1, n).astype(np.int32)
+    ikey[ikey == 7] = 8  # an empty bin
+    vdt = np.dtype(vdt)
+    if vdt.kind in "SU":
+        pool = np.array(["", "a", "bc", "zzzzz", "hello world pad16"], dtype=vdt)
+        v = pool[rng.integers(0, len(pool), n)]
+    elif vdt.kind == "b":
+        v = rng.integers(0, 2, n).astype(vdt)
+    else:
+        v = (rng.random(n) * 100).astype(vdt)
+    cnt, ig, ifg = rc.BinCount(ikey, nb + 1, pack=True)
+    for fn, param in [(100, 0), (102, 0), (101, 0), (101, 2), (101, -1), (101, -3), (101, 1000)]:
+        for lo in (1, 0):
+            got = rc.GroupByAllPack32([v], ikey, ig, ifg, cnt, nb, [fn], [lo], [nb + 1], param)[0]
+            exp = orc.GroupByAllPack32([v], ikey, ig, ifg, cnt, nb, [fn], [lo], [nb + 1], param)[0]
+            assert got.dtype == exp.dtype
+            if vdt.kind == "f":
+                np.testing.assert_array_equal(got[lo:].view(f"u{vdt.itemsize}"), exp[lo:].view(f"u{vdt.itemsize}"))
+            else:
+                np.testing.assert_array_equal(got[lo:], exp[lo:])
+
+
+def test_nth_kat(rc):
+    # tests/test_groupby.py:137-159 style: nth past the end -> invalid, negative counts from the end
+    ikey = np.array([1, 1, 2, 1, 2, 3], dtype=np.int8)
+    v = np.array([10.0, 11.0, 20.0, 12.0, 21.0, 30.0])
+    cnt, ig, ifg = rc.BinCount(ikey, 4, pack=True)
+    first = rc.GroupByAllPack32([v], ikey, ig, ifg, cnt, 3, [100], [1], [4], 0)[0]
+    last = rc.GroupByAllPack32([v], ikey, ig, ifg, cnt, 3, [102], [1], [4], 0)[0]
+    nth1 = rc.GroupByAllPack32([v], ikey, ig, ifg, cnt, 3, [101], [1], [4], 1)[0]
+    assert first[1:].tolist() == [10.0, 20.0, 30.0] and last[1:].tolist() == [12.0, 21.0, 30.0]
+    assert nth1[1:3].tolist() == [11.0, 21.0] and np.isnan(nth1[3])
+
+
+# ---------------------------------------------------------------------------------------------------- a9
+def _cmp_cumsum(got, exp, v):
+    assert got.dtype == exp.dtype
+    if exp.dtype.kind == "f":
+        scale = float(np.nansum(np.abs(v.astype(np.float64)))) + 1.0
+        rtol = 1e-5 if exp.dtype == np.float32 else 1e-12
+        np.testing.assert_allclose(got, exp, rtol=rtol, atol=rtol * scale, equal_nan=True)
+    else:
+        np.testing.assert_array_equal(got, exp)
+
+
+@pytest.mark.parametrize("vdt", [np.bool_, np.int8, np.int32, np.int64, np.uint64, np.float32, np.float64])
+@pytest.mark.parametrize("nb", [1, 40, 25_000])
+def test_cumsum(rc, vdt, nb):
+    rng = np.random.default_rng(nb)
+    n = 200_003
+    ikey = rng.integers(0, nb + 1, n).astype(np.int32)
+    if np.dtype(vdt).kind == "f":
+        v = (rng.random(n) * 2 - 1).astype(vdt)
+    elif np.dtype(vdt).kind == "b":
+        v = rng.integers(0, 2, n).astype(vdt)
+    else:
+        v = rng.integers(0, 100, n).astype(vdt)
+    filt = rng.random(n) < 0.7
+    reset = rng.random(n) < 0.01
+    for fp in [(0.0, None, None, None), (0.0, None, filt, None), (0.0, None, filt, reset), (0.0, None, None, reset)]:
+        got = rc.EmaAll32([v], ikey, nb, 300, fp)[0]
+        exp = orc.EmaAll32([v], ikey, nb, 300, fp)[0]
+        _cmp_cumsum(got, exp, v)
+
+
+def test_cumsum_kat(rc):
+    # tests/test_groupby.py:555-602: op-filter False -> carry the running value; bin 0 -> invalid
+    ikey = np.array([1, 2, 1, 0, 2, 1], dtype=np.int8)
+    v = np.array([1, 10, 2, 100, 20, 3], dtype=np.int32)
+    out = rc.EmaAll32([v], ikey, 2, 300, (0.0, None, None, None))[0]
+    assert out.dtype == np.int64
+    assert out.tolist() == [1, 10, 3, np.iinfo(np.int64).min, 30, 6]
+    f = np.array([True, True, False, True, True, True])
+    out = rc.EmaAll32([v], ikey, 2, 300, (0.0, None, f, None))[0]
+    assert out.tolist() == [1, 10, 1, np.iinfo(np.int64).min, 30, 4]
+    s = np.array([b"a"] * 6)
+    assert rc.EmaAll32([s], ikey, 2, 300, (0.0, None, None, None))[0] is None
+
+
+# ---------------------------------------------------------------------------------------------------- a10
+def test_makeifirst_ilast_inext(rc):
+    rng = np.random.default_rng(8)
+    for kdt, nb, n in [(np.int8, 3, 524_288), (np.int16, 1000, 100_001), (np.int32, 50_000, 300_000), (np.int64, 9, 77)]:
+        key = rng.integers(0, nb + 1, n).astype(kdt)
+        key[key == 2] = 1
+        f = rng.random(n) < 0.5
+        for mode in (0, 1):
+            np.testing.assert_array_equal(rc.MakeiFirst(key, nb, None, mode), orc.MakeiFirst(key, nb, None, mode))
+            np.testing.assert_array_equal(rc.MakeiFirst(key, nb, f, mode), orc.MakeiFirst(key, nb, f, mode))
+            np.testing.assert_array_equal(rc.MakeiFirst(key, nb + 1, f, mode), orc.MakeiFirst(key, nb + 1, f, mode))
+            np.testing.assert_array_equal(rc.MakeiNext(key, nb, mode), orc.MakeiNext(key, nb, mode))
+    # tests/test_grouping.py:210-296 shape: int8 keys on 2**19 rows, the last row index does not fit the key dtype
+    key = np.tile(np.array([1, 2, 3], dtype=np.int8), 174_763)[:524_288]
+    ilast = rc.MakeiFirst(key, 3, None, 1)
+    assert ilast.dtype == np.int32 and int(ilast[1:].max()) == 524_287
+
+
+def test_reverse_shuffle(rc):
+    rng = np.random.default_rng(2)
+    p = rng.permutation(1_000_003).astype(np.int32)
+    np.testing.assert_array_equal(rc.ReverseShuffle(p), orc.ReverseShuffle(p))
+
+
+# ---------------------------------------------------------------------------------------------------- a11
+def _lex_keys(rng, n):
+    f = rng.random(n) * 10 - 5
+    f[rng.random(n) < 0.05] = np.nan
+    f[rng.random(n) < 0.02] = 0.0
+    f[rng.random(n) < 0.02] = -0.0
+    f[rng.random(n) < 0.01] = np.inf
+    f[rng.random(n) < 0.01] = -np.inf
+    return {
+        "i8": rng.integers(-128, 128, n).astype(np.int8),
+        "u8": rng.integers(0, 256, n).astype(np.uint8),
+        "i16": rng.integers(-300, 300, n).astype(np.int16),
+        "u16": rng.integers(0, 70, n).astype(np.uint16),
+        "i32": rng.integers(-(2**31), 2**31 - 1, n).astype(np.int32),
+        "u32": rng.integers(0, 2**32 - 1, n).astype(np.uint32),
+        "i64": rng.integers(-(2**62), 2**62, n).astype(np.int64),
+        "u64": rng.integers(0, 2**63, n).astype(np.uint64) * np.uint64(2),
+        "f64": f,
+        "f32": (f * 3).astype(np.float32),
+        "b": rng.integers(0, 2, n).astype(np.bool_),
+        "S7": rng.choice(np.array([b"", b"a", b"ab", b"abc\x00d", b"zzzzzzz", b"B"], dtype="S7"), n),
+        "S20": rng.choice(np.array([b"hello world 1234567", b"hello world 1234568", b"hello", b"hello world"], dtype="S20"), n),
+        "U5": rng.choice(np.array(["", "a", "ab", "été", "zzzzz", "\U0001F600x"], dtype="U5"), n),
+    }
+
+
+@pytest.mark.parametrize("n", [1, 2, 1000, 250_007])
+def test_lexsort_single_key_every_dtype(rc, n):
+    rng = np.random.default_rng(n)
+    for name, k in _lex_keys(rng, n).items():
+        got = rc.LexSort32([k])
+        assert got.dtype == np.int32
+        np.testing.assert_array_equal(got, np.lexsort([k]), err_msg=name)
+
+
+def test_lexsort_multikey_matches_numpy(rc):
+    # tests/test_lexsort.py:21-103: mixed keys, last key primary
+    rng = np.random.default_rng(77)
+    n = 1_000_000
+    ks = _lex_keys(rng, n)
+    low = rng.integers(0, 5, n).astype(np.int32)
+    for combo in (["i32", "u16"], ["f64", "i16", "b"], ["S7", "u8"], ["i64", "f32", "S20", "U5", "i8"], ["u64", "u32"]):
+        keys = [ks[c] for c in combo] + [low]
+        np.testing.assert_array_equal(rc.LexSort32(keys), np.lexsort(keys), err_msg=str(combo))
+    np.testing.assert_array_equal(rc.LexSort64([ks["i16"], low]), np.lexsort([ks["i16"], low]))
+
+
+def test_lexsort_index_and_ascending(rc):
+    rng = np.random.default_rng(5)
+    n = 200_000
+    a = rng.integers(0, 50, n).astype(np.int32)
+    f = rng.random(n)
+    f[rng.random(n) < 0.1] = np.nan
+    s = rng.choice(np.array([b"x", b"yy", b"", b"zzz"], dtype="S3"), n)
+    idx = np.flatnonzero(rng.random(n) < 0.4).astype(np.int32)
+    np.testing.assert_array_equal(rc.LexSort32([f, a], index=idx), orc.LexSort32([f, a], index=idx))
+    for asc in (False, [True, False], [False, True], [False, False]):
+        np.testing.assert_array_equal(rc.LexSort32([f, a], ascending=asc), orc.LexSort32([f, a], ascending=asc))
+    np.testing.assert_array_equal(rc.LexSort32([s, a], ascending=[False, True]), orc.LexSort32([s, a], ascending=[False, True]))
+    np.testing.assert_array_equal(rc.LexSort32([f], index=idx, ascending=False), orc.LexSort32([f], index=idx, ascending=False))
+    assert len(rc.LexSort32([np.zeros(0)])) == 0
+    with pytest.raises(ValueError):
+        rc.LexSort32([np.zeros(3), np.zeros(4)])
+
+
+def test_lexsort_record_array(rc):
+    rng = np.random.default_rng(1)
+    n = 50_000
+    a, b = rng.integers(0, 9, n).astype(np.int64), rng.integers(0, 9, n).astype(np.int16)
+    rec = np.rec.fromarrays([a, b], names=["a", "b"])
+    # a record array is sorted "lumped together" (rt_numpy.py:2110-2112, 2176-2178): bytewise over the whole record
+    raw = np.ascontiguousarray(rec).view(np.uint8).reshape(n, rec.dtype.itemsize)
+    exp = np.lexsort(tuple(raw[:, j] for j in range(rec.dtype.itemsize - 1, -1, -1)))
+    np.testing.assert_array_equal(rc.LexSort32(rec), exp)
+    ik, ifk, cnt = rc.GroupFromLexSort(exp.astype(np.int32), rec)
+    eik, eifk, ecnt = orc.GroupFromLexSort(exp.astype(np.int32), [a, b])
+    np.testing.assert_array_equal(ik, eik)
+    np.testing.assert_array_equal(cnt, ecnt)
+
+
+# ---------------------------------------------------------------------------------------------------- a12
+def test_groupbylex_docstring(rc):
+    # rt_numpy.py:2126-2156, replayed through riptable's own Python glue (tests/rt_glue.py)
+    import rt_glue
+
+    a = np.arange(100).astype("S")
+    f = (np.arange(100) % 3).astype(bool)
+    got = rt_glue.groupbylex(rc, [a], filter=f)
+    exp = rt_glue.groupbylex(orc, [a], filter=f)
+    for k in ("iKey", "iFirstKey", "iGroup", "iFirstGroup", "nCountGroup"):
+        np.testing.assert_array_equal(got[k], exp[k], err_msg=k)
+    assert got["unique_count"] == 66 and got["iFirstGroup"][0] == 66 and got["nCountGroup"][0] == 34
+    assert got["iKey"][:9].tolist() == [0, 1, 9, 0, 23, 31, 0, 45, 53]
+    assert got["iGroup"][:9].tolist() == [1, 10, 11, 13, 14, 16, 17, 19, 2]
+    # hash == lex when keys first appear in sorted order (tests/test_lexsort.py:105-214)
+    rng = np.random.default_rng(0)
+    vn = rng.integers(0, 3, 10_000)
+    vs = rng.choice(np.array(["a", "b", "c"]), 10_000)
+    vn[:9] = [0, 0, 0, 1, 1, 1, 2, 2, 2]
+    vs[:9] = ["a", "b", "c"] * 3
+    gh, gl = rt_glue.groupbyhash(rc, [vn, vs], pack=True), rt_glue.groupbylex(rc, [vn, vs])
+    for k in ("iKey", "iFirstKey", "unique_count", "iGroup", "iFirstGroup", "nCountGroup"):
+        assert np.array_equal(gh[k], gl[k]), k
+    gr = rt_glue.groupbylex(rc, [vn, vs], rec=True)
+    assert gr["unique_count"] == 9 and np.array_equal(np.sort(gr["iFirstKey"]), np.sort(gl["iFirstKey"]))
+
+
+@pytest.mark.parametrize("base_index", [0, 1])
+def test_group_from_lexsort_vs_oracle_and_hash(rc, base_index):
+    # tests/test_lexsort.py:105-256: lex grouping of sorted-first-appearance keys equals hash grouping
+    rng = np.random.default_rng(4)
+    n = 300_000
+    f = np.round(rng.random(n) * 50)
+    f[rng.random(n) < 0.05] = np.nan
+    s = rng.choice(np.array([b"aa", b"b", b"", b"cccc"], dtype="S4"), n)
+    i = rng.integers(-4, 4, n).astype(np.int8)
+    for vals in ([f], [s], [i, s], [f, i, s]):
+        sort_keys = vals[::-1]
+        ig = rc.LexSort32(sort_keys)
+        ik, ifk, cnt = rc.GroupFromLexSort(ig, vals, base_index=base_index)
+        eik, eifk, ecnt = orc.GroupFromLexSort(np.lexsort(sort_keys).astype(np.int32), vals, base_index=base_index)
+        np.testing.assert_array_equal(ik, eik)
+        np.testing.assert_array_equal(ifk, eifk)
+        np.testing.assert_array_equal(cnt, ecnt)
+    # filter -> index
+    idx = np.flatnonzero(rng.random(n) < 0.5).astype(np.int32)
+    ig = rc.LexSort32([i], index=idx)
+    ik, ifk, cnt = rc.GroupFromLexSort(ig, [i], base_index=base_index)
+    eik, eifk, ecnt = orc.GroupFromLexSort(orc.LexSort32([i], index=idx), [i], base_index=base_index)
+    np.testing.assert_array_equal(ik, eik)
+    np.testing.assert_array_equal(ifk, eifk)
+    np.testing.assert_array_equal(cnt, ecnt)
+    # keys that first appear in sorted order: hash bins == lex bins (tests/test_lexsort.py:105-148)
+    k = np.sort(rng.integers(0, 1000, n)).astype(np.int32)
+    ig = rc.LexSort32([k])
+    ik, ifk, cnt = rc.GroupFromLexSort(ig, [k], base_index=1)
+    hk, hfk, u = rc.MultiKeyGroupBy32([k], 0, None, 2)
+    np.testing.assert_array_equal(ik, hk)
+    np.testing.assert_array_equal(ifk, hfk)
+    np.testing.assert_array_equal(cnt, rc.BinCount(hk, u + 1))
+
+
+def test_device_mode_pack_sort_chain(rc):
+    import torch
+
+    rng = np.random.default_rng(10)
+    n = 400_000
+    k = rng.integers(0, 3000, n).astype(np.int64)
+    v = rng.random(n)
+    kt, vt = torch.from_numpy(k).cuda(), torch.from_numpy(v).cuda()
+    ik, ifk, u = rc.MultiKeyGroupBy32([kt], 0, None, 2)
+    cnt, ig, ifg = rc.BinCount(ik, u + 1, pack=True)
+    assert ig.is_cuda and cnt.is_cuda
+    first = rc.GroupByAllPack32([vt], ik, ig, ifg, cnt, u, [100], [1], [u + 1], 0)[0]
+    cs = rc.EmaAll32([vt], ik, u, 300, (0.0, None, None, None))[0]
+    perm = rc.LexSort32([vt, kt])
+    ok, ofk, ou = orc.MultiKeyGroupBy32([k])
+    np.testing.assert_array_equal(first.cpu().numpy()[1:], v[ofk])
+    np.testing.assert_array_equal(perm.cpu().numpy(), np.lexsort([v, k]))
+    exp = orc.EmaAll32([v], ok, ou, 300, (0.0, None, None, None))[0]
+    np.testing.assert_allclose(cs.cpu().numpy(), exp, rtol=1e-12, atol=1e-9)

@@ -1,0 +1,352 @@
+"""Row-sharded grouping and reductions: one process per GPU, torch.distributed (NCCL over NVLink / NVSwitch).
+
+This is riptable's own partition scheme, moved across GPUs.  riptable groups contiguous row partitions
+independently (`cutoffs`, riptable/rt_numpy.py:1999-2000, riptable/tests/test_pgroupby.py:7-86) and then merges
+the per-partition groupings by re-grouping the stacked unique keys (`hstack_groupings`,
+riptable/rt_grouping.py:277-413: `groupbyhash(stacked uniques)` at :359-364, then `rc.ReIndexGroups` at :378-407).
+Here rank r holds rows [offset_r, offset_r + n_r) and
+
+  1. groups its shard on its own GPU                                  (rc.MultiKeyGroupBy32, a1)
+  2. all-gathers every shard's unique key rows, in rank order         (ncclAllGather; U_r x key bytes per rank)
+  3. groups the stacked uniques — every rank runs the same call       (rc.MultiKeyGroupBy32 again)
+     Shards are in row order and local uniques are in first-appearance order, so first appearance in the
+     stacked list IS global first appearance: the global bin ids and iFirstKey are bit-exact with a single-GPU run.
+  4. re-indexes its local iKey through the local->global bin map      (rtb_remap_ikey, rc.ReIndexGroups semantics)
+
+Reductions are associative, so each rank reduces its shard against the global bin ids and the partials are
+combined: a plain all-reduce while the group count is small, and above `alltoall_min_bins` a bin-partitioned
+all-to-all (rank r owns a contiguous slice of the bins), a local merge and an all-gather of the merged slices.
+No data-path collective moves rows; only U-sized tables cross NVLink.
+
+All device work goes through an `ops` object.  `CudaOps` (the product) drives riptable_b200.rc in device mode;
+the gloo tests in tests/ supply an oracle-backed stand-in so the host logic and the collectives are covered
+on CPU with world_size 2.  There is no CPU fallback inside this module.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as tdist
+
+from .enums import GB_FUNCTIONS as GB
+
+ALLTOALL_MIN_BINS = 8_000_000  # above this many bins the partials are merged by bin-partitioned all-to-all
+
+
+# ====================================================================================================
+class CudaOps:
+    """The product backend: riptable_b200.rc in device mode on this rank's GPU."""
+
+    def __init__(self, device=None):
+        from . import rc
+
+        self.rc = rc
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+
+    # -- columns ---------------------------------------------------------------------------------
+    def as_col(self, x):
+        return self.rc._to_dev(x)
+
+    def nrows(self, col):
+        return col.n
+
+    def take_rows(self, col, idx):
+        """col[idx] for any fixed-width dtype (a device gather of itemsize-byte rows)."""
+        rc = self.rc
+        isz = col.dtype.itemsize
+        src = col.buf[: col.n * isz].view(col.n, isz)
+        out = src.index_select(0, idx.to(torch.int64))
+        k = int(idx.numel())
+        buf = out.reshape(-1)
+        if buf.numel() < 16:
+            pad = torch.zeros(16, dtype=torch.uint8, device=buf.device)
+            pad[: buf.numel()] = buf
+            buf = pad
+        return rc.DevArray(buf.contiguous(), col.dtype, k)
+
+    def col_bytes(self, col):
+        return col.buf[: col.n * col.dtype.itemsize]
+
+    def col_from_bytes(self, t, dtype, n):
+        rc = self.rc
+        if t.numel() < 16:
+            pad = torch.zeros(16, dtype=torch.uint8, device=t.device)
+            pad[: t.numel()] = t
+            t = pad
+        return rc.DevArray(t.contiguous(), np.dtype(dtype), n)
+
+    def col_dtype(self, col):
+        return col.dtype
+
+    # -- hot-path calls ----------------------------------------------------------------------------
+    def groupby(self, cols, filter=None):
+        ik, ifk, u = self.rc.MultiKeyGroupBy32([self._dev_view(c) for c in cols], 0, filter, 2)
+        return ik, ifk, int(u)
+
+    def _dev_view(self, c):
+        return c  # DevArray is accepted by rc directly
+
+    def remap(self, ikey, table):
+        from ._lib import lib, check
+        import ctypes as C
+
+        out = torch.empty_like(ikey)
+        check(lib.rtb_remap_ikey(C.c_void_p(ikey.data_ptr()), ikey.numel(), C.c_void_p(table.data_ptr()), table.numel(),
+                                 C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return out
+
+    def reduce(self, val, ikey, nuniq, func):
+        return self.rc.GroupByAll32([val], ikey, nuniq, [int(func)], [0], [nuniq + 1], 0)[0]
+
+    def bincount(self, ikey, nbins):
+        return self.rc.BinCount(ikey, nbins)
+
+    def valid_mask_as_i8(self, col):
+        t = col.torch()
+        return (~_invalid_mask(t)).to(torch.int8)
+
+    def tensor(self, x, dtype=None):
+        return torch.as_tensor(x, dtype=dtype, device=self.device)
+
+    def to_torch(self, x):
+        return x  # device-mode rc results are torch tensors already
+
+
+# ====================================================================================================
+def _world(group):
+    return tdist.get_world_size(group), tdist.get_rank(group)
+
+
+def _all_gather_var(t: torch.Tensor, counts, group):
+    """All-gather 1-D tensors of different lengths (counts[r] elements from rank r), concatenated in rank order."""
+    G = len(counts)
+    m = int(max(counts)) if G else 0
+    if m == 0:
+        return t.new_empty(0)
+    pad = t.new_zeros(m)
+    pad[: t.numel()] = t
+    out = t.new_empty(G * m)
+    tdist.all_gather_into_tensor(out, pad, group=group)
+    return torch.cat([out[r * m: r * m + int(counts[r])] for r in range(G)])
+
+
+class ShardedGrouping:
+    """Result of `sharded_groupby`: global bin ids for this rank's rows plus the replicated group table."""
+
+    def __init__(self, ikey, ifirstkey, unique_count, row_offset, nrows_total, shard_unique_counts):
+        self.ikey = ikey                    # int32[n_r]  global base-1 bin of every local row (0 = filtered)
+        self.ifirstkey = ifirstkey          # int64[U]    GLOBAL row of each bin's first appearance (replicated)
+        self.unique_count = unique_count    # U
+        self.row_offset = row_offset        # first global row of this shard
+        self.nrows_total = nrows_total
+        self.shard_unique_counts = shard_unique_counts
+
+
+def sharded_groupby(ops, key_cols, filter=None, group=None) -> ShardedGrouping:
+    """MultiKeyGroupBy32 over rows sharded contiguously across the ranks of `group` (module docstring, steps 1-4)."""
+    G, rank = _world(group)
+    cols = [ops.as_col(c) for c in key_cols]
+    n = ops.nrows(cols[0])
+    ik, ifk, u = ops.groupby(cols, filter)
+    ik, ifk = ops.to_torch(ik), ops.to_torch(ifk)
+
+    # shard sizes and unique counts of every rank
+    meta = ops.tensor([n, u], dtype=torch.int64)
+    allmeta = meta.new_empty(2 * G)
+    tdist.all_gather_into_tensor(allmeta, meta, group=group)
+    allmeta = allmeta.cpu().view(G, 2)
+    ns, us = allmeta[:, 0].tolist(), allmeta[:, 1].tolist()
+    row_off = [0] * G
+    for r in range(1, G):
+        row_off[r] = row_off[r - 1] + ns[r - 1]
+    uoff = [0] * G
+    for r in range(1, G):
+        uoff[r] = uoff[r - 1] + us[r - 1]
+    total_u = uoff[-1] + us[-1]
+
+    # stacked unique key rows (rank order == global row order) and their global first rows
+    stacked = []
+    for c in cols:
+        dt = ops.col_dtype(c)
+        uniq = ops.take_rows(c, ifk[:u])
+        allb = _all_gather_var(ops.col_bytes(uniq), [x * dt.itemsize for x in us], group)
+        stacked.append(ops.col_from_bytes(allb, dt, total_u))
+    gfirst_local = ifk[:u].to(torch.int64) + row_off[rank]
+    all_first = _all_gather_var(gfirst_local, us, group)
+
+    if total_u == 0:
+        empty64 = all_first.new_empty(0)
+        return ShardedGrouping(ik, empty64, 0, row_off[rank], sum(ns), us)
+
+    gk, gfk, U = ops.groupby(stacked, None)
+    gk, gfk = ops.to_torch(gk), ops.to_torch(gfk)
+    # local bin b (1..u) -> global bin of stacked row uoff[rank] + b - 1; bin 0 stays 0
+    table = torch.zeros(u + 1, dtype=torch.int32, device=gk.device)
+    table[1:] = gk[uoff[rank]: uoff[rank] + u]
+    gikey = ops.remap(ik, table)
+    ifirst_global = all_first.index_select(0, gfk[:U].to(torch.int64))
+    return ShardedGrouping(gikey, ifirst_global, int(U), row_off[rank], sum(ns), us)
+
+
+# ----------------------------------------------------------------------------------------------------
+def _invalid_mask(t: torch.Tensor):
+    if t.dtype.is_floating_point:
+        return torch.isnan(t)
+    if t.dtype == torch.bool:
+        return torch.zeros_like(t, dtype=torch.bool)
+    info = torch.iinfo(t.dtype)
+    sentinel = info.min if info.min < 0 else info.max
+    return t == sentinel
+
+
+def _invalid_value(dtype):
+    if dtype.is_floating_point:
+        return float("nan")
+    if dtype == torch.bool:
+        return False
+    info = torch.iinfo(dtype)
+    return info.min if info.min < 0 else info.max
+
+
+def _merge_slices(kind, parts, nan_op):
+    """Merge per-rank partials of one bin slice.  parts: dict name -> tensor [G, m].  Returns dict name -> [m]."""
+    if kind == "sum":
+        return {"v": parts["v"].sum(dim=0)}
+    if kind == "count":
+        return {"v": parts["v"].sum(dim=0, dtype=torch.int64).to(torch.int32)}
+    if kind == "mean":
+        c = parts["c"].sum(dim=0)
+        s = parts["s"].sum(dim=0)
+        return {"v": torch.where(c > 0, s / c.to(torch.float64), torch.full_like(s, float("nan")))}
+    if kind == "var":
+        # Chan et al. pairwise merge of (count, mean, M2), folded over the ranks in rank order
+        c, mean, m2 = parts["c"][0].to(torch.float64), parts["mean"][0].clone(), parts["m2"][0].clone()
+        mean = torch.where(c > 0, mean, torch.zeros_like(mean))
+        for r in range(1, parts["c"].shape[0]):
+            cb = parts["c"][r].to(torch.float64)
+            mb = torch.where(cb > 0, parts["mean"][r], torch.zeros_like(mean))
+            tot = c + cb
+            delta = mb - mean
+            safe = torch.where(tot > 0, tot, torch.ones_like(tot))
+            mean = mean + delta * cb / safe
+            m2 = m2 + parts["m2"][r] + delta * delta * c * cb / safe
+            c = tot
+        return {"c": c, "m2": m2}
+    if kind in ("min", "max"):
+        a, cnt = parts["a"], parts["c"]
+        inv = _invalid_mask(a)
+        seen_invalid = (inv & (cnt > 0)).any(dim=0) if not nan_op else None
+        if a.dtype.is_floating_point:
+            fill = float("inf") if kind == "min" else float("-inf")
+        elif a.dtype == torch.bool:
+            a = a.to(torch.uint8)
+            fill = 1 if kind == "min" else 0
+        else:
+            info = torch.iinfo(a.dtype)
+            fill = info.max if kind == "min" else info.min
+        filled = torch.where(inv, torch.full_like(a, fill), a)
+        red = filled.min(dim=0).values if kind == "min" else filled.max(dim=0).values
+        any_valid = (~inv).any(dim=0)
+        bad = ~any_valid if nan_op else (~any_valid | seen_invalid)
+        out = torch.where(bad, torch.full_like(red, _invalid_value(parts["a"].dtype) if parts["a"].dtype != torch.bool else 0), red)
+        return {"v": out.to(parts["a"].dtype)}
+    raise ValueError(kind)
+
+
+def _combine(kind, local: dict, nbins: int, nan_op: bool, group, alltoall_min_bins):
+    """Combine per-rank [nbins] partials into the replicated merged result(s)."""
+    G, rank = _world(group)
+    names = sorted(local)
+    if nbins < alltoall_min_bins and kind in ("sum", "count"):
+        v = local["v"].clone()
+        tdist.all_reduce(v, op=tdist.ReduceOp.SUM, group=group)
+        return {"v": v}
+    if nbins < alltoall_min_bins:
+        # small tables: all-gather the partials and merge everything locally
+        parts = {}
+        for nm in names:
+            t = local[nm].contiguous()
+            out = t.new_empty((G,) + tuple(t.shape))
+            tdist.all_gather_into_tensor(out.view(-1), t.view(-1), group=group)
+            parts[nm] = out
+        return _merge_slices(kind, parts, nan_op)
+    # large tables: rank r owns bins [r*m, (r+1)*m); all-to-all the slices, merge, all-gather the merged slices
+    m = (nbins + G - 1) // G
+    parts = {}
+    for nm in names:
+        t = local[nm]
+        pad = t.new_zeros(G * m)
+        pad[:nbins] = t
+        recv = torch.empty_like(pad)
+        tdist.all_to_all_single(recv, pad, group=group)
+        parts[nm] = recv.view(G, m)
+    merged = _merge_slices(kind, parts, nan_op)
+    out = {}
+    for nm, t in merged.items():
+        full = t.new_empty(G * m)
+        tdist.all_gather_into_tensor(full, t.contiguous(), group=group)
+        out[nm] = full[:nbins]
+    return out
+
+
+def sharded_reduce(ops, values, grouping: ShardedGrouping, func, group=None, alltoall_min_bins=ALLTOALL_MIN_BINS):
+    """GroupByAll32 (sum, mean, min, max, var, std and the nan-variants) over the sharded rows; the merged
+    [U+1] result is replicated on every rank.  Per-op semantics as riptable/rt_grouping.py:3433-3436."""
+    func = int(func)
+    U = grouping.unique_count
+    nb = U + 1
+    nan_op = func >= 50
+    base = func - 50 if nan_op else func
+    ik = grouping.ikey
+    val = ops.as_col(values)
+
+    def red(f):
+        return ops.to_torch(ops.reduce(val, ik, U, f))
+
+    if base == GB.GB_SUM:
+        return _combine("sum", {"v": red(func)}, nb, nan_op, group, alltoall_min_bins)["v"]
+    if base == GB.GB_MEAN:
+        # per-bin (sum, count of accumulated rows): count = rows that a nan-op would keep
+        s = red(GB.GB_NANSUM if nan_op else GB.GB_SUM).to(torch.float64)
+        c = _valid_counts(ops, val, ik, U, nan_op)
+        return _combine("mean", {"s": s, "c": c}, nb, nan_op, group, alltoall_min_bins)["v"]
+    if base in (GB.GB_MIN, GB.GB_MAX):
+        a = red(func)
+        c = ops.to_torch(ops.bincount(ik, nb))
+        kind = "min" if base == GB.GB_MIN else "max"
+        return _combine(kind, {"a": a, "c": c}, nb, nan_op, group, alltoall_min_bins)["v"]
+    if base in (GB.GB_VAR, GB.GB_STD):
+        c = _valid_counts(ops, val, ik, U, nan_op)
+        mean = red(GB.GB_NANMEAN if nan_op else GB.GB_MEAN)
+        var = red(GB.GB_NANVAR if nan_op else GB.GB_VAR)  # ddof = 1 locally
+        cf = c.to(torch.float64)
+        m2 = torch.where(c >= 2, var * (cf - 1.0), torch.zeros_like(var))  # NaN var (a NaN input) stays NaN
+        if not nan_op:
+            poisoned = torch.isnan(mean) & (c > 0)
+            m2 = torch.where(poisoned, torch.full_like(m2, float("nan")), m2)
+        out = _combine("var", {"c": c, "mean": mean, "m2": m2}, nb, nan_op, group, alltoall_min_bins)
+        v = torch.where(out["c"] >= 2, out["m2"] / (out["c"] - 1.0), torch.full_like(out["m2"], float("nan")))
+        return torch.sqrt(v) if base == GB.GB_STD else v
+    raise NotImplementedError(f"sharded_reduce: function {func}")
+
+
+def _valid_counts(ops, val, ik, U, nan_op):
+    """Rows per bin that the op accumulates: all rows of the bin, or only the valid ones for a nan-op."""
+    if not nan_op:
+        return ops.to_torch(ops.bincount(ik, U + 1))
+    ones = ops.valid_mask_as_i8(val)  # 1 where the value is neither NaN nor the dtype's sentinel
+    return ops.to_torch(ops.reduce(ones, ik, U, GB.GB_SUM)).to(torch.int32)
+
+
+def sharded_count(ops, grouping: ShardedGrouping, group=None, alltoall_min_bins=ALLTOALL_MIN_BINS):
+    """Grouping.count across shards: rc.BinCount per shard, summed."""
+    c = ops.to_torch(ops.bincount(grouping.ikey, grouping.unique_count + 1))
+    return _combine("count", {"v": c}, grouping.unique_count + 1, False, group, alltoall_min_bins)["v"]
+
+
+def sharded_groupby_sum(key_cols, values, group=None, ops=None):
+    """bench.py's multi-GPU step: sharded hash grouping + GB_SUM.  -> (ikey, ifirstkey, U, sums[U+1])."""
+    ops = ops or CudaOps()
+    g = sharded_groupby(ops, key_cols, None, group)
+    s = sharded_reduce(ops, values, g, GB.GB_SUM, group)
+    return g.ikey, g.ifirstkey, g.unique_count, s

@@ -1,0 +1,137 @@
+"""World-size-2 gloo run of riptable_b200.dist on CPU: the shard-merge logic and every collective it issues
+(all-gather of uniques, all-reduce / all-gather / all-to-all of partials) against a single-process oracle run.
+The device ops are replaced by an oracle-backed stand-in (tests only); the product backend is CudaOps."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as tdist
+import torch.multiprocessing as mp
+
+from oracle import riptide_oracle as orc
+
+
+class OracleOps:
+    """NumPy/oracle stand-in for CudaOps (same method set), CPU tensors for the collectives."""
+
+    def as_col(self, x):
+        return x.numpy() if isinstance(x, torch.Tensor) else np.ascontiguousarray(x)
+
+    def nrows(self, col):
+        return len(col)
+
+    def take_rows(self, col, idx):
+        return np.ascontiguousarray(col[idx.numpy()])
+
+    def col_bytes(self, col):
+        return torch.from_numpy(np.ascontiguousarray(col).view(np.uint8).reshape(-1).copy())
+
+    def col_from_bytes(self, t, dtype, n):
+        return t.numpy().view(np.dtype(dtype))[:n].copy() if n else np.zeros(0, np.dtype(dtype))
+
+    def col_dtype(self, col):
+        return col.dtype
+
+    def groupby(self, cols, filter=None):
+        return orc.MultiKeyGroupBy32(list(cols), 0, filter, 2)
+
+    def remap(self, ikey, table):
+        return table[ikey.to(torch.int64)]
+
+    def reduce(self, val, ikey, nuniq, func):
+        ik = ikey.numpy() if isinstance(ikey, torch.Tensor) else ikey
+        return orc.GroupByAll32([np.asarray(val)], ik, nuniq, [int(func)], [0], [nuniq + 1], 0)[0]
+
+    def bincount(self, ikey, nbins):
+        ik = ikey.numpy() if isinstance(ikey, torch.Tensor) else ikey
+        return orc.BinCount(ik, nbins)
+
+    def valid_mask_as_i8(self, col):
+        return orc._is_valid_mask(np.asarray(col)).astype(np.int8)
+
+    def tensor(self, x, dtype=None):
+        return torch.as_tensor(x, dtype=dtype)
+
+    def to_torch(self, x):
+        return torch.from_numpy(np.ascontiguousarray(x)) if isinstance(x, np.ndarray) else x
+
+
+def _make(seed, n):
+    rng = np.random.default_rng(seed)
+    k1 = rng.integers(0, 40, n).astype(np.int64) * 1_000_003
+    k2 = rng.choice(np.array([b"aa", b"b", b"", b"cccc"], dtype="S4"), n)
+    v = rng.random(n) * 100 - 50
+    v[rng.random(n) < 0.1] = np.nan
+    vi = rng.integers(-1000, 1000, n).astype(np.int32)
+    vi[rng.random(n) < 0.05] = np.iinfo(np.int32).min
+    f = rng.random(n) < 0.8
+    return k1, k2, v, vi, f
+
+
+def _worker(rank, world, port, n, cuts, a2a, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    tdist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from riptable_b200 import dist as rd
+
+        k1, k2, v, vi, f = _make(7, n)
+        lo, hi = cuts[rank], cuts[rank + 1]
+        ops = OracleOps()
+        out = {}
+        for name, keys, filt in (("one", [k1], None), ("two", [k1, k2], None), ("filt", [k1, k2], f)):
+            g = rd.sharded_groupby(ops, [k[lo:hi] for k in keys], None if filt is None else filt[lo:hi])
+            res = {"ikey": g.ikey.numpy().copy(), "ifk": g.ifirstkey.numpy().copy(), "u": g.unique_count,
+                   "off": g.row_offset}
+            for fn in (0, 1, 2, 3, 4, 5, 50, 51, 52, 53, 54, 55):
+                res[f"f{fn}"] = rd.sharded_reduce(ops, v[lo:hi], g, fn, alltoall_min_bins=a2a).numpy().copy()
+            for fn in (0, 2, 3, 52, 53):
+                res[f"i{fn}"] = rd.sharded_reduce(ops, vi[lo:hi], g, fn, alltoall_min_bins=a2a).numpy().copy()
+            res["count"] = rd.sharded_count(ops, g, alltoall_min_bins=a2a).numpy().copy()
+            out[name] = res
+        q.put((rank, out))
+    finally:
+        tdist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("a2a", [1 << 40, 1])  # all-reduce / all-gather merge, then the all-to-all merge
+@pytest.mark.parametrize("cuts", [(0, 3000, 7001), (0, 0, 7001), (0, 7000, 7001)])
+def test_sharded_groupby_and_reduce_world2(cuts, a2a):
+    n = cuts[-1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, cuts, a2a, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+
+    k1, k2, v, vi, f = _make(7, n)
+    for name, keys, filt in (("one", [k1], None), ("two", [k1, k2], None), ("filt", [k1, k2], f)):
+        eik, eifk, eu = orc.MultiKeyGroupBy32(keys, 0, filt, 2)
+        full = np.concatenate([got[r][name]["ikey"] for r in range(2)])
+        np.testing.assert_array_equal(full, eik)               # global bin ids, bit-exact with the single-process run
+        for r in range(2):
+            assert got[r][name]["u"] == eu
+            np.testing.assert_array_equal(got[r][name]["ifk"], eifk)
+            assert got[r][name]["off"] == cuts[r]
+            np.testing.assert_array_equal(got[r][name]["count"], orc.BinCount(eik, eu + 1))
+            for fn in (0, 1, 2, 3, 4, 5, 50, 51, 52, 53, 54, 55):
+                exp = orc.GroupByAll32([v], eik, eu, [fn], [0], [eu + 2], 0)[0]
+                np.testing.assert_allclose(got[r][name][f"f{fn}"], exp, rtol=1e-11, atol=1e-9, equal_nan=True,
+                                           err_msg=f"{name} func {fn}")
+            for fn in (0, 2, 3, 52, 53):
+                exp = orc.GroupByAll32([vi], eik, eu, [fn], [0], [eu + 2], 0)[0]
+                np.testing.assert_array_equal(got[r][name][f"i{fn}"], exp, err_msg=f"{name} int func {fn}")

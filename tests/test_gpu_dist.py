@@ -1,0 +1,62 @@
+"""GPU: riptable_b200.dist through the product backend (CudaOps) on a single-rank NCCL group, against the
+single-process oracle.  The multi-rank collectives are covered on CPU by tests/test_dist_gloo.py and on
+2/4/8 GPUs by bench.py --gpus N."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import riptide_oracle as orc
+
+
+@pytest.fixture(scope="module")
+def group():
+    import torch
+    import torch.distributed as tdist
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(0)
+    tdist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    yield tdist.group.WORLD
+    tdist.destroy_process_group()
+
+
+@pytest.mark.parametrize("a2a", [1 << 40, 1])
+def test_sharded_groupby_reduce_single_rank(group, a2a):
+    import torch
+    from riptable_b200 import dist as rd
+
+    rng = np.random.default_rng(3)
+    n = 300_000
+    k1 = rng.integers(0, 5000, n).astype(np.int64) * 7919
+    k2 = rng.choice(np.array([b"aa", b"b", b"", b"cccc"], dtype="S4"), n)
+    v = rng.random(n) * 100 - 50
+    v[rng.random(n) < 0.1] = np.nan
+    vi = rng.integers(-1000, 1000, n).astype(np.int32)
+    f = rng.random(n) < 0.8
+    ops = rd.CudaOps()
+    for keys, filt in (([k1], None), ([k1, k2], f)):
+        g = rd.sharded_groupby(ops, [torch.from_numpy(k).cuda() if k.dtype.kind != "S" else k for k in keys],
+                               None if filt is None else torch.from_numpy(filt).cuda(), group)
+        eik, eifk, eu = orc.MultiKeyGroupBy32(keys, 0, filt, 2)
+        assert g.unique_count == eu
+        np.testing.assert_array_equal(g.ikey.cpu().numpy(), eik)
+        np.testing.assert_array_equal(g.ifirstkey.cpu().numpy(), eifk)
+        np.testing.assert_array_equal(rd.sharded_count(ops, g, group, a2a).cpu().numpy(), orc.BinCount(eik, eu + 1))
+        vt, vit = torch.from_numpy(v).cuda(), torch.from_numpy(vi).cuda()
+        for fn in (0, 1, 2, 3, 4, 5, 50, 51, 52, 53, 54, 55):
+            got = rd.sharded_reduce(ops, vt, g, fn, group, a2a).cpu().numpy()
+            exp = orc.GroupByAll32([v], eik, eu, [fn], [0], [eu + 2], 0)[0]
+            np.testing.assert_allclose(got, exp, rtol=1e-11, atol=1e-9, equal_nan=True, err_msg=f"func {fn}")
+        for fn in (0, 2, 3):
+            got = rd.sharded_reduce(ops, vit, g, fn, group, a2a).cpu().numpy()
+            np.testing.assert_array_equal(got, orc.GroupByAll32([vi], eik, eu, [fn], [0], [eu + 2], 0)[0])
+    ik, ifk, u, s = rd.sharded_groupby_sum([torch.from_numpy(k1).cuda()], torch.from_numpy(v).cuda(), group, ops)
+    assert u == len(np.unique(k1)) and s.shape[0] == u + 1

@@ -143,6 +143,30 @@ __device__ __forceinline__ void load_ikey4(const void* p, int kdt, int64_t r, in
     }
   }
 }
+// two consecutive iKeys at row r (r even)
+__device__ __forceinline__ void load_ikey2(const void* p, int kdt, int64_t r, int64_t k[2]) {
+  switch (kdt) {
+    case RTB_I8: {
+      uint32_t w = *(const uint16_t*)((const int8_t*)p + r);
+      k[0] = (int8_t)(w & 0xff); k[1] = (int8_t)(w >> 8);
+      break;
+    }
+    case RTB_I16: {
+      uint32_t w = ld_stream_u32((const int16_t*)p + r);
+      k[0] = (int16_t)(w & 0xffff); k[1] = (int16_t)(w >> 16);
+      break;
+    }
+    case RTB_I32: {
+      uint2 w = ld_stream_u2((const int32_t*)p + r);
+      k[0] = (int32_t)w.x; k[1] = (int32_t)w.y;
+      break;
+    }
+    default: {
+      uint4 a = ld_stream_u4((const int64_t*)p + r);
+      k[0] = (int64_t)(((uint64_t)a.y << 32) | a.x); k[1] = (int64_t)(((uint64_t)a.w << 32) | a.z);
+    }
+  }
+}
 __device__ __forceinline__ void store_ikey(void* p, int kdt, int64_t r, int64_t v) {
   switch (kdt) {
     case RTB_I8: ((int8_t*)p)[r] = (int8_t)v; break;

@@ -2,7 +2,11 @@
 //
 // Replaces rc.MultiKeyGroupBy32 (riptable/rt_numpy.py:2073-2075).  Design:
 //
-//   * Open-addressing table of 16-byte slots {key|tag, minrow, bin}; one 128-bit L2 load per probe.
+//   * Open-addressing table of 16-byte slots {key|tag, minrow, bin}, probed linearly from an EVEN slot index, so
+//     the table is a sequence of 32-byte (one L2 sector) buckets of two slots.  The single-key steady-state
+//     probe reads a whole bucket with one sm_100a 256-bit load (LDG.256): measured 286 G random 32 B probes/s
+//     against 226 G/s for 16 B loads (profiles/microbench/l2_random2.cu), and two slots per probe cut the
+//     expected probes per row from 1.16 to 1.03 at 24 % load.
 //   * PROGRESSIVE ROUNDS over geometrically growing row ranges [P_k, P_{k+1}).  A key already
 //     finalised in an earlier round resolves with one probe and iKey is written immediately, so the
 //     steady state moves key_bytes + 4 bytes per row — the algorithmic minimum.  Keys first seen in a
@@ -56,8 +60,7 @@ __device__ __forceinline__ uint32_t hash_u64(unsigned long long k) {
 }
 
 __device__ __forceinline__ Slot load_slot(const Slot* s) {
-  // Plain (L1-allocating) 128-bit read: measured 1.55x the random-probe rate of ld.cg on B200
-  // (profiles/microbench).  A stale L1 copy is harmless: keys of finalised slots never change within a
+  // Plain (L1-allocating) 128-bit read.  A stale L1 copy is harmless: keys of finalised slots never change within a
   // launch, a stale "empty" is corrected by the atomicCAS that follows, and a stale minrow is only ever
   // too large, which at worst issues a redundant atomicMin.
   uint4 w;
@@ -67,6 +70,17 @@ __device__ __forceinline__ Slot load_slot(const Slot* s) {
   r.minrow = w.z;
   r.nbin = w.w;
   return r;
+}
+
+// One bucket = two slots = one 32-byte sector, fetched with a single 256-bit load.
+struct Bucket {
+  unsigned long long k0, w0, k1, w1;  // w = minrow | (nbin << 32)
+};
+__device__ __forceinline__ Bucket load_bucket(const Slot* table, uint32_t b) {
+  Bucket p;
+  asm volatile("ld.global.v4.b64 {%0,%1,%2,%3}, [%4];"
+               : "=l"(p.k0), "=l"(p.w0), "=l"(p.k1), "=l"(p.w1) : "l"(table + 2 * (size_t)b));
+  return p;
 }
 
 // A row landed on a provisional slot (or just claimed it): track the first row, return -(slot+1).
@@ -86,9 +100,192 @@ __device__ __forceinline__ bool claim_new(GbCounters* ctr, uint32_t* newlist, ui
 }
 
 // ---- direct path -----------------------------------------------------------------------------
+// General resolution of one key, slot by slot from slot `idx` (even): handles matches, provisional slots,
+// insertion of new keys and the key that equals the empty marker.  `mask` = capacity - 1 (capacity in slots).
+__device__ __noinline__ int32_t resolve_direct(Slot* table, uint32_t mask, unsigned long long key, uint32_t idx,
+                                               uint32_t row, uint32_t* newlist, GbCounters* ctr, uint32_t new_limit) {
+  if (key == kEmpty) {
+    // the one key that collides with the empty marker lives in the extra slot table[cap]
+    uint32_t sp = mask + 1;
+    Slot* ss = &table[sp];
+    Slot cur = load_slot(ss);
+    if (cur.bin()) return (int32_t)cur.bin();
+    if (cur.key == kEmpty) {
+      unsigned long long old = atomicCAS(&ss->key, kEmpty, 0ull);
+      if (old == kEmpty && !claim_new(ctr, newlist, sp, new_limit)) return 0;
+    }
+    return provisional(table, sp, row, cur.minrow);
+  }
+  for (uint32_t probes = 0; probes <= mask; probes++) {
+    Slot s = load_slot(&table[idx]);
+    if (s.key == key) {
+      if (s.bin()) return (int32_t)s.bin();
+      return provisional(table, idx, row, s.minrow);
+    }
+    if (s.key == kEmpty) {
+      // once the round is out of room (it will be redone) nothing more is inserted, so the table cannot fill up
+      if (*(volatile uint32_t*)&ctr->abort) return 0;
+      unsigned long long old = atomicCAS(&table[idx].key, kEmpty, key);
+      if (old == kEmpty) {
+        if (!claim_new(ctr, newlist, idx, new_limit)) return 0;
+        return provisional(table, idx, row, 0xFFFFFFFFu);
+      }
+      if (old == key) return provisional(table, idx, row, 0xFFFFFFFFu);
+    }
+    idx = (idx + 1) & mask;
+  }
+  ctr->abort = 1;  // table full (cannot happen while new_limit < capacity)
+  return 0;
+}
+
+// Steady-state classification of one fetched bucket: > 0 final bin, 0 = both slots hold other keys (go on to the
+// next bucket), -1 = needs the general path (an empty or provisional slot, or the empty-marker key).
+__device__ __forceinline__ int32_t classify(const Bucket& p, unsigned long long key) {
+  if (p.k0 == key) {
+    uint32_t bin = ~(uint32_t)(p.w0 >> 32);
+    return bin ? (int32_t)bin : -1;
+  }
+  if (p.k1 == key) {
+    uint32_t bin = ~(uint32_t)(p.w1 >> 32);
+    return bin ? (int32_t)bin : -1;
+  }
+  return (p.k0 == kEmpty || p.k1 == kEmpty) ? -1 : 0;
+}
+
+template <int ISZ>
+__device__ __forceinline__ unsigned long long load_key1(const void* keys, int64_t r) {
+  if (ISZ == 8) return ((const unsigned long long*)keys)[r];
+  if (ISZ == 4) return ((const uint32_t*)keys)[r];
+  if (ISZ == 2) return ((const uint16_t*)keys)[r];
+  return ((const uint8_t*)keys)[r];
+}
+
+// A warp owns 128-row tiles; every lane holds 4 keys.  Row of lane `l`, key j inside a tile:
+//   8-byte keys : two 128-bit loads, each covering 512 contiguous bytes per warp -> rows 2l, 2l+1, 64+2l, 65+2l
+//   narrower    : one vector load of 4 consecutive rows                          -> rows 4l .. 4l+3
+template <int ISZ>
+__device__ __forceinline__ int tile_row(int lane, int j) {
+  if (ISZ == 8) return (j < 2 ? 2 * lane + j : 64 + 2 * lane + (j - 2));
+  return 4 * lane + j;
+}
+template <int ISZ>
+__device__ __forceinline__ void load_tile_keys(const void* keys, int64_t tb, int lane, unsigned long long k[4]) {
+  if (ISZ == 8) {
+    uint4 a = ld_stream_u4((const uint8_t*)keys + (tb + 2 * lane) * 8);
+    uint4 b = ld_stream_u4((const uint8_t*)keys + (tb + 64 + 2 * lane) * 8);
+    k[0] = ((unsigned long long)a.y << 32) | a.x; k[1] = ((unsigned long long)a.w << 32) | a.z;
+    k[2] = ((unsigned long long)b.y << 32) | b.x; k[3] = ((unsigned long long)b.w << 32) | b.z;
+  } else if (ISZ == 4) {
+    uint4 a = ld_stream_u4((const uint8_t*)keys + (tb + 4 * lane) * 4);
+    k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w;
+  } else if (ISZ == 2) {
+    uint2 a = ld_stream_u2((const uint8_t*)keys + (tb + 4 * lane) * 2);
+    k[0] = a.x & 0xffff; k[1] = a.x >> 16; k[2] = a.y & 0xffff; k[3] = a.y >> 16;
+  } else {
+    uint32_t a = ld_stream_u32((const uint8_t*)keys + tb + 4 * lane);
+    k[0] = a & 0xff; k[1] = (a >> 8) & 0xff; k[2] = (a >> 16) & 0xff; k[3] = a >> 24;
+  }
+}
+
+// One round of the direct path over rows [lo, hi).  lo is a multiple of 128; the key / filter / ikey base
+// pointers are 16-byte aligned (checked on the host).
+template <int ISZ>
+__global__ void __launch_bounds__(256) gb_round_direct(const void* __restrict__ keys, const uint8_t* __restrict__ filter,
+                                                       int32_t* __restrict__ ikey, Slot* table, uint32_t mask,
+                                                       int64_t lo, int64_t hi, uint32_t* newlist, GbCounters* ctr,
+                                                       uint32_t new_limit) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const uint32_t bmask = mask >> 1;  // buckets - 1
+  const int64_t step = nwarps * 128;
+  int64_t tb = lo + gw * 128;
+  unsigned long long k[4], kn[4] = {0, 0, 0, 0};
+  if (tb + 128 <= hi) load_tile_keys<ISZ>(keys, tb, lane, k);
+  for (; tb + 128 <= hi; tb += step) {
+    const bool more = tb + step + 128 <= hi;
+    if (more) load_tile_keys<ISZ>(keys, tb + step, lane, kn);  // next tile's keys are in flight during the probes
+    uint32_t fbits = 0xF;
+    if (filter) {
+      if (ISZ == 8) {
+        uint32_t fa = *(const uint16_t*)(filter + tb + 2 * lane), fb = *(const uint16_t*)(filter + tb + 64 + 2 * lane);
+        fbits = ((fa & 0xff) ? 1u : 0u) | ((fa >> 8) ? 2u : 0u) | ((fb & 0xff) ? 4u : 0u) | ((fb >> 8) ? 8u : 0u);
+      } else {
+        uint32_t f = ld_stream_u32(filter + tb + 4 * lane);
+        fbits = ((f & 0xff) ? 1u : 0u) | ((f & 0xff00) ? 2u : 0u) | ((f & 0xff0000) ? 4u : 0u) | ((f >> 24) ? 8u : 0u);
+      }
+    }
+    uint32_t b[4];
+    Bucket p[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) b[i] = hash_u64(k[i]) & bmask;
+#pragma unroll
+    for (int i = 0; i < 4; i++) p[i] = load_bucket(table, b[i]);
+    int32_t o[4];
+    uint32_t pend = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      o[i] = 0;
+      if ((fbits >> i) & 1u) {
+        int32_t c = k[i] == kEmpty ? -1 : classify(p[i], k[i]);
+        if (c > 0) o[i] = c;
+        else if (c == 0) pend |= 1u << i;
+        else o[i] = resolve_direct(table, mask, k[i], 2 * b[i], (uint32_t)(tb + tile_row<ISZ>(lane, i)), newlist, ctr, new_limit);
+      }
+    }
+    uint32_t hops = 0;
+    while (pend) {  // both slots of the bucket held other keys: all of this thread's open keys advance together
+      if (++hops > bmask) {  // cannot happen while the table has free slots; never spin
+        ctr->abort = 1;
+        break;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        if ((pend >> i) & 1u) {
+          b[i] = (b[i] + 1) & bmask;
+          p[i] = load_bucket(table, b[i]);
+        }
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        if ((pend >> i) & 1u) {
+          int32_t c = classify(p[i], k[i]);
+          if (c > 0) {
+            o[i] = c;
+            pend &= ~(1u << i);
+          } else if (c < 0) {
+            o[i] = resolve_direct(table, mask, k[i], 2 * b[i], (uint32_t)(tb + tile_row<ISZ>(lane, i)), newlist, ctr, new_limit);
+            pend &= ~(1u << i);
+          }
+        }
+    }
+    if (ISZ == 8) {
+      *(int2*)(ikey + tb + 2 * lane) = make_int2(o[0], o[1]);
+      *(int2*)(ikey + tb + 64 + 2 * lane) = make_int2(o[2], o[3]);
+    } else {
+      st_stream_u4(ikey + tb + 4 * lane, make_uint4((uint32_t)o[0], (uint32_t)o[1], (uint32_t)o[2], (uint32_t)o[3]));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) k[i] = kn[i];
+  }
+  // the warp whose next tile is the partial one finishes the rows that are left
+  if (tb < hi) {
+    for (int64_t q = tb + lane; q < hi; q += 32) {
+      int32_t o = 0;
+      if (!filter || filter[q]) {
+        unsigned long long kk = load_key1<ISZ>(keys, q);
+        o = resolve_direct(table, mask, kk, 2 * (hash_u64(kk) & bmask), (uint32_t)q, newlist, ctr, new_limit);
+      }
+      ikey[q] = o;
+    }
+  }
+}
+
+// ---- direct path, discovery rounds ------------------------------------------------------------------
+// Used while many keys are still new: 16-byte probes, everything inline (38 registers, full occupancy),
+// the four first probes of a thread in flight together.
 // Resolve one key.  `first` is the slot already fetched for idx (memory-level parallelism: the caller
 // issues all its first probes before resolving any).
-__device__ __forceinline__ int32_t resolve_direct(Slot* table, uint32_t mask, unsigned long long key, uint32_t idx,
+__device__ __forceinline__ int32_t resolve_insert(Slot* table, uint32_t mask, unsigned long long key, uint32_t idx,
                                                   Slot s, uint32_t row, uint32_t* newlist, GbCounters* ctr,
                                                   uint32_t new_limit) {
   if (key == kEmpty) {
@@ -140,23 +337,16 @@ __device__ __forceinline__ void load_keys4(const void* keys, int64_t r, unsigned
     k[0] = a & 0xff; k[1] = (a >> 8) & 0xff; k[2] = (a >> 16) & 0xff; k[3] = a >> 24;
   }
 }
-template <int ISZ>
-__device__ __forceinline__ unsigned long long load_key1(const void* keys, int64_t r) {
-  if (ISZ == 8) return ((const unsigned long long*)keys)[r];
-  if (ISZ == 4) return ((const uint32_t*)keys)[r];
-  if (ISZ == 2) return ((const uint16_t*)keys)[r];
-  return ((const uint8_t*)keys)[r];
-}
-
 // One round of the direct path over rows [lo, hi).  lo is a multiple of 4; the key / filter / ikey
 // base pointers are 16-byte aligned for their 4-row vectors (checked on the host).
 template <int ISZ>
-__global__ void __launch_bounds__(256) gb_round_direct(const void* __restrict__ keys, const uint8_t* __restrict__ filter,
+__global__ void __launch_bounds__(256) gb_round_insert(const void* __restrict__ keys, const uint8_t* __restrict__ filter,
                                                        int32_t* __restrict__ ikey, Slot* table, uint32_t mask,
                                                        int64_t lo, int64_t hi, uint32_t* newlist, GbCounters* ctr,
                                                        uint32_t new_limit) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
   for (int64_t r = lo + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; r < hi; r += stride) {
+    if (*(volatile uint32_t*)&ctr->abort) break;  // the round is out of room and will be redone: stop inserting
     if (r + 3 < hi) {
       unsigned long long k[4];
       load_keys4<ISZ>(keys, r, k);
@@ -164,14 +354,14 @@ __global__ void __launch_bounds__(256) gb_round_direct(const void* __restrict__ 
       uint32_t idx[4];
       Slot s[4];
 #pragma unroll
-      for (int i = 0; i < 4; i++) idx[i] = hash_u64(k[i]) & mask;
+      for (int i = 0; i < 4; i++) idx[i] = (hash_u64(k[i]) & (mask >> 1)) * 2;
 #pragma unroll
       for (int i = 0; i < 4; i++) s[i] = load_slot(&table[idx[i]]);
       int32_t o[4];
 #pragma unroll
       for (int i = 0; i < 4; i++) {
         o[i] = ((f >> (8 * i)) & 0xff)
-                   ? resolve_direct(table, mask, k[i], idx[i], s[i], (uint32_t)(r + i), newlist, ctr, new_limit)
+                   ? resolve_insert(table, mask, k[i], idx[i], s[i], (uint32_t)(r + i), newlist, ctr, new_limit)
                    : 0;
       }
       st_stream_u4(ikey + r, make_uint4((uint32_t)o[0], (uint32_t)o[1], (uint32_t)o[2], (uint32_t)o[3]));
@@ -180,8 +370,8 @@ __global__ void __launch_bounds__(256) gb_round_direct(const void* __restrict__ 
         int32_t o = 0;
         if (!filter || filter[q]) {
           unsigned long long k = load_key1<ISZ>(keys, q);
-          uint32_t idx = hash_u64(k) & mask;
-          o = resolve_direct(table, mask, k, idx, load_slot(&table[idx]), (uint32_t)q, newlist, ctr, new_limit);
+          uint32_t idx = (hash_u64(k) & (mask >> 1)) * 2;
+          o = resolve_insert(table, mask, k, idx, load_slot(&table[idx]), (uint32_t)q, newlist, ctr, new_limit);
         }
         ikey[q] = o;
       }
@@ -196,13 +386,14 @@ __global__ void __launch_bounds__(256) gb_round_byref(KeyCols kc, const uint8_t*
                                                       uint32_t new_limit) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t r = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < hi; r += stride) {
+    if (*(volatile uint32_t*)&ctr->abort) break;  // the round is out of room and will be redone
     if (filter && !filter[r]) {
       ikey[r] = 0;
       continue;
     }
     unsigned long long h = hash_row(kc, r);
     uint32_t tag = (uint32_t)(h >> 32);
-    uint32_t idx = (uint32_t)h & mask;
+    uint32_t idx = ((uint32_t)h & (mask >> 1)) * 2;
     unsigned long long mine = ((unsigned long long)tag << 32) | (uint32_t)r;
     int32_t o = 0;
     bool done = false;
@@ -304,7 +495,7 @@ __global__ void __launch_bounds__(256) gb_reinsert_direct(Slot* table, uint32_t 
       table[mask + 1] = s;
       continue;
     }
-    uint32_t idx = hash_u64(s.key) & mask;
+    uint32_t idx = (hash_u64(s.key) & (mask >> 1)) * 2;
     while (atomicCAS(&table[idx].key, kEmpty, s.key) != kEmpty) idx = (idx + 1) & mask;
     table[idx].minrow = s.minrow;
     table[idx].nbin = s.nbin;
@@ -316,7 +507,7 @@ __global__ void __launch_bounds__(256) gb_reinsert_byref(KeyCols kc, Slot* table
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     Slot s = staged[j];
     unsigned long long h = hash_row(kc, (int64_t)(uint32_t)s.key);
-    uint32_t idx = (uint32_t)h & mask;
+    uint32_t idx = ((uint32_t)h & (mask >> 1)) * 2;
     while (atomicCAS(&table[idx].key, kEmpty, s.key) != kEmpty) idx = (idx + 1) & mask;
     table[idx].minrow = s.minrow;
     table[idx].nbin = s.nbin;
@@ -364,6 +555,8 @@ static uint32_t next_pow2_u64(uint64_t v) {
 }
 
 struct GbPlan {
+  double discovery_frac;  // a round whose predecessor found more new keys than this share of its rows is a discovery round
+  int ctas_per_sm;
   int64_t round0;
   double load_target;  // table sized so projected uniques / capacity <= this
   double load_abort;   // a round aborts when uniques / capacity would exceed this
@@ -371,7 +564,8 @@ struct GbPlan {
 };
 
 static GbPlan get_plan() {
-  GbPlan p{1 << 20, 0.5, 0.75, 4};
+  GbPlan p{0.002, 3, 1 << 20, 0.25, 0.75, 4};
+  if (const char* e = getenv("RTB_GB_CTAS")) p.ctas_per_sm = atoi(e);
   if (const char* e = getenv("RTB_GB_ROUND0")) p.round0 = atoll(e);
   if (const char* e = getenv("RTB_GB_LOAD")) p.load_target = atof(e);
   if (const char* e = getenv("RTB_GB_RATIO")) p.ratio = atoi(e);
@@ -463,6 +657,7 @@ extern "C" int rtb_multikey_groupby32(const rtb_column* keys, int nkeys, int64_t
   if (max_unique > nrows) max_unique = nrows;
 
   GbPlan plan = get_plan();
+  static const bool trace = getenv("RTB_GB_TRACE") != nullptr;
   GbLayout L = layout(workspace, workspace_bytes, nrows, max_unique, has_cut, ncutoffs);
   RTB_ARG(workspace && L.bytes <= workspace_bytes, "MultiKeyGroupBy32: workspace too small (%zu < %zu)",
           workspace_bytes, L.bytes);
@@ -503,7 +698,7 @@ extern "C" int rtb_multikey_groupby32(const rtb_column* keys, int nkeys, int64_t
     if (want < 1024) want = 1024;
     if (want > capmax) want = capmax;
 
-    for (;;) {  // attempt loop: (re)size, run the round, grow on abort
+    for (int attempt = 0;; attempt++) {  // attempt loop: (re)size, run the round, grow on abort
       if (want != cap) {
         uint32_t staged_n = 0;
         if (cap != 0 && U > 0) {
@@ -528,23 +723,47 @@ extern "C" int rtb_multikey_groupby32(const rtb_column* keys, int nkeys, int64_t
       uint32_t new_limit = (uint32_t)(room > 0xFFFFFFF0ll ? 0xFFFFFFF0ll : room);
       RTB_CUDA(cudaMemsetAsync(L.ctr, 0, sizeof(GbCounters), stream));
       uint32_t mask = cap - 1;
+      cudaEvent_t tev0 = nullptr;
+      if (trace) { cudaEventCreate(&tev0); cudaEventRecord(tev0, stream); }
       prof_begin(PROF_GB_ROUND, stream);
       if (direct) {
-        int grid = grid_for(rows, 256, 4, 8);
+        // discovery rounds (many new keys expected) use the insert-oriented kernel, the rest the bucket-probe kernel
+        const bool discovery = round == 0 || (double)prev_new > plan.discovery_frac * (double)prev_rows || attempt > 0;
+        if (discovery) {
+          int g2 = grid_for(rows, 256, 4, 8);
+          switch (keys[0].itemsize) {
+            case 8: gb_round_insert<8><<<g2, 256, 0, stream>>>(keys[0].data, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit); break;
+            case 4: gb_round_insert<4><<<g2, 256, 0, stream>>>(keys[0].data, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit); break;
+            case 2: gb_round_insert<2><<<g2, 256, 0, stream>>>(keys[0].data, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit); break;
+            default: gb_round_insert<1><<<g2, 256, 0, stream>>>(keys[0].data, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit);
+          }
+        } else {
+        int grid = grid_for(rows, 256, 4, plan.ctas_per_sm);
         switch (keys[0].itemsize) {
           case 8: gb_round_direct<8><<<grid, 256, 0, stream>>>(keys[0].data, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit); break;
           case 4: gb_round_direct<4><<<grid, 256, 0, stream>>>(keys[0].data, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit); break;
           case 2: gb_round_direct<2><<<grid, 256, 0, stream>>>(keys[0].data, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit); break;
           default: gb_round_direct<1><<<grid, 256, 0, stream>>>(keys[0].data, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit);
         }
+        }
       } else {
         gb_round_byref<<<grid_for(rows, 256, 1, 8), 256, 0, stream>>>(kc, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit);
       }
       RTB_LAUNCH_CHECK();
       prof_end(PROF_GB_ROUND, stream, (uint64_t)rows);
+      cudaEvent_t tev1 = nullptr;
+      if (trace) { cudaEventCreate(&tev1); cudaEventRecord(tev1, stream); }
       GbCounters h;
       RTB_CUDA(cudaMemcpyAsync(&h, L.ctr, sizeof(h), cudaMemcpyDeviceToHost, stream));
       RTB_CUDA(cudaStreamSynchronize(stream));
+      if (trace) {
+        float tms = 0.f;
+        cudaEventElapsedTime(&tms, tev0, tev1);
+        fprintf(stderr, "[rtb gb] round %d rows %lld cap %u U %lld new %u abort %u kernel %.3f ms (%.1f G rows/s)\n", round,
+                (long long)rows, cap, (long long)U, h.newcount, h.abort, tms, rows / (tms * 1e6));
+        cudaEventDestroy(tev0);
+        cudaEventDestroy(tev1);
+      }
       if (!h.abort) {
         prev_new = h.newcount;
         break;

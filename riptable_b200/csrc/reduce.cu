@@ -89,22 +89,37 @@ __global__ void __launch_bounds__(256) accum_kernel(AccumArgs a) {
     __syncthreads();
   }
   const int vsz = OP == OP_COUNT ? 0 : dsize(a.vdt);
-  int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
-  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; r < a.n; r += stride) {
-    if (r + 3 < a.n) {
-      int64_t k[4];
-      unsigned long long v[4] = {0, 0, 0, 0};
-      load_ikey4(a.ikey, a.kdt, r, k);
-      if (OP != OP_COUNT) load_raw4(a.values, vsz, r, v);
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-        if (k[i] >= a.lo && k[i] < a.hi) accumulate<OP>(a, acc, cnt, flags, k[i], v[i]);
-    } else {
-      for (int64_t q = r; q < a.n; q++) {
-        int64_t k = load_ikey(a.ikey, a.kdt, q);
-        if (k >= a.lo && k < a.hi)
-          accumulate<OP>(a, acc, cnt, flags, k, OP == OP_COUNT ? 0ull : load_raw1(a.values, vsz, q));
+  // A warp owns 128-row tiles and every lane 4 rows of a tile.  If either stream has 8-byte items the lane takes
+  // rows (2l, 2l+1) and (64+2l, 65+2l), so that each vector load of the warp covers contiguous memory (a lane
+  // reading 32 contiguous bytes with two 128-bit loads touches every sector twice); otherwise rows 4l..4l+3.
+  const bool pair = vsz == 8 || a.kdt == RTB_I64;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t full = a.n & ~127ll;
+  for (int64_t tb = gw * 128; tb < full; tb += nwarps * 128) {
+    int64_t k[4];
+    unsigned long long v[4] = {0, 0, 0, 0};
+    if (pair) {
+      load_ikey2(a.ikey, a.kdt, tb + 2 * lane, k);
+      load_ikey2(a.ikey, a.kdt, tb + 64 + 2 * lane, k + 2);
+      if (OP != OP_COUNT) {
+        load_raw2(a.values, vsz, tb + 2 * lane, v);
+        load_raw2(a.values, vsz, tb + 64 + 2 * lane, v + 2);
       }
+    } else {
+      load_ikey4(a.ikey, a.kdt, tb + 4 * lane, k);
+      if (OP != OP_COUNT) load_raw4(a.values, vsz, tb + 4 * lane, v);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if (k[i] >= a.lo && k[i] < a.hi) accumulate<OP>(a, acc, cnt, flags, k[i], v[i]);
+  }
+  if (gw == 0) {
+    for (int64_t q = full + lane; q < a.n; q += 32) {
+      int64_t k = load_ikey(a.ikey, a.kdt, q);
+      if (k >= a.lo && k < a.hi)
+        accumulate<OP>(a, acc, cnt, flags, k, OP == OP_COUNT ? 0ull : load_raw1(a.values, vsz, q));
     }
   }
   if (SMEM) {

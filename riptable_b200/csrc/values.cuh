@@ -22,6 +22,22 @@ __device__ __forceinline__ void load_raw4(const void* p, int sz, int64_t r, unsi
     v[0] = a & 0xff; v[1] = (a >> 8) & 0xff; v[2] = (a >> 16) & 0xff; v[3] = a >> 24;
   }
 }
+// two consecutive items at row r (r even, base 16-byte aligned): one coalesced vector load
+__device__ __forceinline__ void load_raw2(const void* p, int sz, int64_t r, unsigned long long v[2]) {
+  if (sz == 8) {
+    uint4 a = ld_stream_u4((const uint8_t*)p + r * 8);
+    v[0] = ((unsigned long long)a.y << 32) | a.x; v[1] = ((unsigned long long)a.w << 32) | a.z;
+  } else if (sz == 4) {
+    uint2 a = ld_stream_u2((const uint8_t*)p + r * 4);
+    v[0] = a.x; v[1] = a.y;
+  } else if (sz == 2) {
+    uint32_t a = ld_stream_u32((const uint8_t*)p + r * 2);
+    v[0] = a & 0xffff; v[1] = a >> 16;
+  } else {
+    uint32_t a = *(const uint16_t*)((const uint8_t*)p + r);
+    v[0] = a & 0xff; v[1] = a >> 8;
+  }
+}
 __device__ __forceinline__ unsigned long long load_raw1(const void* p, int sz, int64_t r) {
   if (sz == 8) return ((const unsigned long long*)p)[r];
   if (sz == 4) return ((const uint32_t*)p)[r];

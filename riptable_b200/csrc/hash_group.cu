@@ -189,7 +189,7 @@ __device__ __forceinline__ void load_tile_keys(const void* keys, int64_t tb, int
 
 // One round of the direct path over rows [lo, hi).  lo is a multiple of 128; the key / filter / ikey base
 // pointers are 16-byte aligned (checked on the host).
-template <int ISZ>
+template <int ISZ, bool PREFETCH>
 __global__ void __launch_bounds__(256) gb_round_direct(const void* __restrict__ keys, const uint8_t* __restrict__ filter,
                                                        int32_t* __restrict__ ikey, Slot* table, uint32_t mask,
                                                        int64_t lo, int64_t hi, uint32_t* newlist, GbCounters* ctr,
@@ -201,10 +201,13 @@ __global__ void __launch_bounds__(256) gb_round_direct(const void* __restrict__ 
   const int64_t step = nwarps * 128;
   int64_t tb = lo + gw * 128;
   unsigned long long k[4], kn[4] = {0, 0, 0, 0};
-  if (tb + 128 <= hi) load_tile_keys<ISZ>(keys, tb, lane, k);
+  if (PREFETCH && tb + 128 <= hi) load_tile_keys<ISZ>(keys, tb, lane, k);
   for (; tb + 128 <= hi; tb += step) {
-    const bool more = tb + step + 128 <= hi;
-    if (more) load_tile_keys<ISZ>(keys, tb + step, lane, kn);  // next tile's keys are in flight during the probes
+    if (PREFETCH) {
+      if (tb + step + 128 <= hi) load_tile_keys<ISZ>(keys, tb + step, lane, kn);  // in flight during the probes
+    } else {
+      load_tile_keys<ISZ>(keys, tb, lane, k);
+    }
     uint32_t fbits = 0xF;
     if (filter) {
       if (ISZ == 8) {
@@ -223,40 +226,62 @@ __global__ void __launch_bounds__(256) gb_round_direct(const void* __restrict__ 
     for (int i = 0; i < 4; i++) p[i] = load_bucket(table, b[i]);
     int32_t o[4];
     uint32_t pend = 0;
+    // branch-free common case: the key sits in its home bucket with a final bin.  (The empty-marker key can
+    // only "match" an empty slot, whose bin field reads 0, so it falls through to the general section.)
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      o[i] = 0;
-      if ((fbits >> i) & 1u) {
-        int32_t c = k[i] == kEmpty ? -1 : classify(p[i], k[i]);
-        if (c > 0) o[i] = c;
-        else if (c == 0) pend |= 1u << i;
-        else o[i] = resolve_direct(table, mask, k[i], 2 * b[i], (uint32_t)(tb + tile_row<ISZ>(lane, i)), newlist, ctr, new_limit);
-      }
+      const bool m0 = p[i].k0 == k[i], m1 = p[i].k1 == k[i];
+      const unsigned long long w = m0 ? p[i].w0 : p[i].w1;
+      const uint32_t bin = ~(uint32_t)(w >> 32);
+      const bool ok = (m0 | m1) & (bin != 0u);
+      o[i] = ok ? (int32_t)bin : 0;
+      if (!ok) pend |= 1u << i;
     }
-    uint32_t hops = 0;
-    while (pend) {  // both slots of the bucket held other keys: all of this thread's open keys advance together
-      if (++hops > bmask) {  // cannot happen while the table has free slots; never spin
-        ctr->abort = 1;
-        break;
-      }
+    pend &= fbits;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if (!((fbits >> i) & 1u)) o[i] = 0;
+    if (pend) {
+      // general section: next buckets for keys whose home bucket is full of other keys, the insert path for the rest
+      uint32_t slow = 0;
 #pragma unroll
       for (int i = 0; i < 4; i++)
         if ((pend >> i) & 1u) {
-          b[i] = (b[i] + 1) & bmask;
-          p[i] = load_bucket(table, b[i]);
-        }
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-        if ((pend >> i) & 1u) {
-          int32_t c = classify(p[i], k[i]);
-          if (c > 0) {
-            o[i] = c;
-            pend &= ~(1u << i);
-          } else if (c < 0) {
-            o[i] = resolve_direct(table, mask, k[i], 2 * b[i], (uint32_t)(tb + tile_row<ISZ>(lane, i)), newlist, ctr, new_limit);
+          int32_t c = k[i] == kEmpty ? -1 : classify(p[i], k[i]);
+          if (c < 0) {
+            slow |= 1u << i;
             pend &= ~(1u << i);
           }
         }
+      uint32_t hops = 0;
+      while (pend) {
+        if (++hops > bmask) {  // cannot happen while the table has free slots; never spin
+          ctr->abort = 1;
+          break;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+          if ((pend >> i) & 1u) {
+            b[i] = (b[i] + 1) & bmask;
+            p[i] = load_bucket(table, b[i]);
+          }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+          if ((pend >> i) & 1u) {
+            int32_t c = classify(p[i], k[i]);
+            if (c > 0) {
+              o[i] = c;
+              pend &= ~(1u << i);
+            } else if (c < 0) {
+              slow |= 1u << i;
+              pend &= ~(1u << i);
+            }
+          }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        if ((slow >> i) & 1u)
+          o[i] = resolve_direct(table, mask, k[i], 2 * b[i], (uint32_t)(tb + tile_row<ISZ>(lane, i)), newlist, ctr, new_limit);
     }
     if (ISZ == 8) {
       *(int2*)(ikey + tb + 2 * lane) = make_int2(o[0], o[1]);
@@ -264,8 +289,10 @@ __global__ void __launch_bounds__(256) gb_round_direct(const void* __restrict__ 
     } else {
       st_stream_u4(ikey + tb + 4 * lane, make_uint4((uint32_t)o[0], (uint32_t)o[1], (uint32_t)o[2], (uint32_t)o[3]));
     }
+    if (PREFETCH) {
 #pragma unroll
-    for (int i = 0; i < 4; i++) k[i] = kn[i];
+      for (int i = 0; i < 4; i++) k[i] = kn[i];
+    }
   }
   // the warp whose next tile is the partial one finishes the rows that are left
   if (tb < hi) {
@@ -555,6 +582,7 @@ static uint32_t next_pow2_u64(uint64_t v) {
 }
 
 struct GbPlan {
+  int prefetch;
   double discovery_frac;  // a round whose predecessor found more new keys than this share of its rows is a discovery round
   int ctas_per_sm;
   int64_t round0;
@@ -564,7 +592,8 @@ struct GbPlan {
 };
 
 static GbPlan get_plan() {
-  GbPlan p{0.002, 3, 1 << 20, 0.25, 0.75, 4};
+  GbPlan p{1, 0.002, 3, 1 << 20, 0.25, 0.75, 4};
+  if (const char* e = getenv("RTB_GB_PREFETCH")) p.prefetch = atoi(e);
   if (const char* e = getenv("RTB_GB_CTAS")) p.ctas_per_sm = atoi(e);
   if (const char* e = getenv("RTB_GB_ROUND0")) p.round0 = atoll(e);
   if (const char* e = getenv("RTB_GB_LOAD")) p.load_target = atof(e);
@@ -694,9 +723,17 @@ extern "C" int rtb_multikey_groupby32(const rtb_column* keys, int nkeys, int64_t
     double proj = round == 0 ? (double)rows : (double)prev_new * ((double)rows / (double)prev_rows) * 1.25 + 64;
     if (proj > (double)rows) proj = (double)rows;
     if (proj > (double)(max_unique - U)) proj = (double)(max_unique - U);
-    uint32_t want = next_pow2_u64((uint64_t)ceil(((double)U + proj) / plan.load_target));
-    if (want < 1024) want = 1024;
-    if (want > capmax) want = capmax;
+    uint32_t ideal = next_pow2_u64((uint64_t)ceil(((double)U + proj) / plan.load_target));
+    if (ideal < 1024) ideal = 1024;
+    if (ideal > capmax) ideal = capmax;
+    // Resizing re-stages every entry, so keep the table while it still fits: grow only when the projection would
+    // cross the abort load, shrink only once discovery has died down and the table is at least twice the ideal size.
+    uint32_t want = ideal;
+    if (cap != 0) {
+      const bool fits = (double)U + proj <= (double)cap * plan.load_abort;
+      const bool settled = (double)prev_new <= plan.discovery_frac * (double)prev_rows;
+      if (fits && !(settled && (uint64_t)cap >= 2ull * ideal)) want = cap;
+    }
 
     for (int attempt = 0;; attempt++) {  // attempt loop: (re)size, run the round, grow on abort
       if (want != cap) {
@@ -739,11 +776,13 @@ extern "C" int rtb_multikey_groupby32(const rtb_column* keys, int nkeys, int64_t
           }
         } else {
         int grid = grid_for(rows, 256, 4, plan.ctas_per_sm);
+#define RTB_ROUND(ISZ_, PF_) gb_round_direct<ISZ_, PF_><<<grid, 256, 0, stream>>>(keys[0].data, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit)
         switch (keys[0].itemsize) {
-          case 8: gb_round_direct<8><<<grid, 256, 0, stream>>>(keys[0].data, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit); break;
-          case 4: gb_round_direct<4><<<grid, 256, 0, stream>>>(keys[0].data, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit); break;
-          case 2: gb_round_direct<2><<<grid, 256, 0, stream>>>(keys[0].data, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit); break;
-          default: gb_round_direct<1><<<grid, 256, 0, stream>>>(keys[0].data, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit);
+          case 8: if (plan.prefetch) RTB_ROUND(8, true); else RTB_ROUND(8, false); break;
+          case 4: if (plan.prefetch) RTB_ROUND(4, true); else RTB_ROUND(4, false); break;
+          case 2: RTB_ROUND(2, false); break;
+          default: RTB_ROUND(1, false);
+#undef RTB_ROUND
         }
         }
       } else {

@@ -48,6 +48,9 @@ _TORCH_OF = {
 _NP_OF = {v: k for k, v in _TORCH_OF.items()}
 
 
+_PINNED_D2H_MIN = 1 << 20
+
+
 def _device():
     if not torch.cuda.is_available():
         raise RuntimeError("riptable_b200: no CUDA device; this path has no CPU fallback")
@@ -74,8 +77,19 @@ class DevArray:
         return self.buf.data_ptr()
 
     def numpy(self) -> np.ndarray:
-        host = self.buf[: self.n * self.dtype.itemsize].cpu().numpy()
-        return host.view(self.dtype) if self.dtype.itemsize else np.zeros(self.n, self.dtype)
+        nbytes = self.n * self.dtype.itemsize
+        if nbytes == 0:
+            return np.zeros(self.n, self.dtype)
+        src = self.buf[:nbytes]
+        if nbytes >= _PINNED_D2H_MIN:
+            # large results land in page-locked memory (torch's caching host allocator), which the copy engine
+            # fills at PCIe rate; the returned array owns the buffer
+            host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+            host.copy_(src, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        else:
+            host = src.cpu()
+        return host.numpy().view(self.dtype)
 
     def torch(self) -> torch.Tensor:
         t = self.buf[: self.n * self.dtype.itemsize]

@@ -87,6 +87,11 @@ int rtb_multikey_groupby32(const rtb_column* keys, int nkeys, int64_t nrows, int
 /* ---- a4: rc.CombineFilter(key, filter) — riptable/rt_numpy.py:1508.  out = filter ? key : 0, key dtype kept. */
 int rtb_combine_filter(const void* ikey, int kdtype, const uint8_t* filter, int64_t nrows, void* out, void* stream);
 
+/* ---- rc.CombineAccum2Filter(key1, key2, unique_count1, unique_count2, filter) — riptable/rt_numpy.py:1595
+ * Accum2 cell index: out = filter ? key2 * (unique_count1 + 1) + key1 : 0, stored as odt (an iKey dtype). */
+int rtb_combine_accum2(const void* key1, int kdt1, const void* key2, int kdt2, const uint8_t* filter, int64_t nrows,
+                       int64_t unique_count1, void* out, int odt, void* stream);
+
 /* ---- a5: rc.GroupByAll32(values, ikey, unique_rows, funcList, binLowList, binHighList, func_param)
  *          — riptable/rt_numpy.py:1871, dispatched from riptable/rt_grouping.py:3434-3436.
  * One value column per call.  out has unique_rows+1 entries of rtb_reduce_out_dtype(func, vdtype);

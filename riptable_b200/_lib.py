@@ -40,6 +40,7 @@ PROTOTYPES = {
         [C.POINTER(rtb_column), _i32, _i64, _i64, _vp, _pi64, _i64, _vp, _vp, _i64, _pi64, _pi64, _pi64, _vp, _sz, _vp],
     ),
     "rtb_combine_filter": (C.c_int, [_vp, _i32, _vp, _i64, _vp, _vp]),
+    "rtb_combine_accum2": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i64, _i64, _vp, _i32, _vp]),
     "rtb_reduce_out_dtype": (C.c_int, [_i32, _i32]),
     "rtb_groupby_reduce_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "rtb_groupby_reduce": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i64, _i32, _i64, _i64, _vp, _vp, _sz, _vp]),

@@ -592,7 +592,7 @@ struct GbPlan {
 };
 
 static GbPlan get_plan() {
-  GbPlan p{1, 0.002, 3, 1 << 20, 0.25, 0.75, 4};
+  GbPlan p{1, 0.002, 4, 1 << 20, 0.25, 0.75, 4};
   if (const char* e = getenv("RTB_GB_PREFETCH")) p.prefetch = atoi(e);
   if (const char* e = getenv("RTB_GB_CTAS")) p.ctas_per_sm = atoi(e);
   if (const char* e = getenv("RTB_GB_ROUND0")) p.round0 = atoll(e);

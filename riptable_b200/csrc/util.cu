@@ -181,6 +181,19 @@ __global__ void __launch_bounds__(256) combine_filter_kernel(const void* __restr
   }
 }
 
+// Accum2 cell index: out = filter ? key2 * (unique_count1 + 1) + key1 : 0  (riptable/rt_numpy.py:1549-1597)
+__global__ void __launch_bounds__(256) combine_accum2_kernel(const void* __restrict__ key1, int kdt1,
+                                                              const void* __restrict__ key2, int kdt2,
+                                                              const uint8_t* __restrict__ filter, int64_t n, int64_t stride1,
+                                                              void* __restrict__ out, int odt) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+    int64_t v = 0;
+    if (!filter || filter[r]) v = load_ikey(key2, kdt2, r) * stride1 + load_ikey(key1, kdt1, r);
+    store_ikey(out, odt, r, v);
+  }
+}
+
 __global__ void __launch_bounds__(256) reverse_shuffle_kernel(const int32_t* __restrict__ perm, int64_t n,
                                                                int32_t* __restrict__ out) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -233,6 +246,18 @@ int rtb_combine_filter(const void* ikey, int kdtype, const uint8_t* filter, int6
   int ksz = dtype_size(kdtype);
   RTB_ARG(((uintptr_t)ikey % (4 * ksz)) == 0 && ((uintptr_t)filter % 4) == 0, "CombineFilter: unaligned input");
   combine_filter_kernel<<<grid_for(nrows, 256, 4), 256, 0, (cudaStream_t)stream>>>(ikey, kdtype, filter, nrows, out);
+  RTB_LAUNCH_CHECK();
+  return RTB_OK;
+}
+
+int rtb_combine_accum2(const void* key1, int kdt1, const void* key2, int kdt2, const uint8_t* filter, int64_t nrows,
+                       int64_t unique_count1, void* out, int odt, void* stream) {
+  RTB_ARG(is_ikey_dtype(kdt1) && is_ikey_dtype(kdt2) && is_ikey_dtype(odt), "CombineAccum2Filter: keys must be int8/16/32/64");
+  RTB_ARG(nrows >= 0 && unique_count1 >= 0, "CombineAccum2Filter: bad sizes");
+  if (nrows == 0) return RTB_OK;
+  RTB_ARG(key1 && key2 && out, "CombineAccum2Filter: null pointer");
+  combine_accum2_kernel<<<grid_for(nrows, 256, 2), 256, 0, (cudaStream_t)stream>>>(key1, kdt1, key2, kdt2, filter, nrows,
+                                                                                  unique_count1 + 1, out, odt);
   RTB_LAUNCH_CHECK();
   return RTB_OK;
 }

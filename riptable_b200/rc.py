@@ -254,6 +254,53 @@ def CombineFilter(key, filter):
     return _from_dev(out, device_mode)
 
 
+def CombineAccum1Filter(key1, unique_count1, filter=None):
+    """rc.CombineAccum1Filter (riptable/rt_numpy.py:1512-1545): drop filtered rows and bin 0, renumber the surviving
+    bins by first appearance.  -> (iKey in key1's dtype, iFirstKey int32, unique_count).  The renumbering is the
+    hash grouping itself, applied to the bin ids."""
+    device_mode = _is_device(key1) or _is_device(filter)
+    k = _ikey_dev(key1)
+    if filter is not None:
+        k = _combine_filter_dev(k, _bool_dev(filter, k.n))
+    keep = (k.torch() > 0) if k.n else torch.zeros(0, dtype=torch.bool, device=_device())
+    ik, ifk, u = MultiKeyGroupBy32([k], 0, keep, 2)
+    ik = ik.to(_TORCH_OF[k.dtype]) if isinstance(ik, torch.Tensor) else ik
+    if device_mode:
+        return ik, ifk, u
+    return ik.cpu().numpy(), ifk.cpu().numpy(), u
+
+
+def _combine_filter_dev(k: DevArray, f: DevArray) -> DevArray:
+    out = DevArray.empty(k.n, k.dtype)
+    check(lib.rtb_combine_filter(C.c_void_p(k.ptr), dtype_code(k.dtype), C.c_void_p(f.ptr), k.n, C.c_void_p(out.ptr), _stream()))
+    return out
+
+
+def CombineAccum2Filter(key1, key2, unique_count1, unique_count2, filter=None):
+    """rc.CombineAccum2Filter (riptable/rt_numpy.py:1549-1597) -> (iKey over the (unique_count1+1) x (unique_count2+1)
+    cell grid, nCountGroup).  iKey = key2 * (unique_count1 + 1) + key1, 0 where the filter is False; its dtype follows
+    riptable/rt_enum.py:666-679."""
+    from .enums import int_dtype_from_len
+
+    device_mode = any(_is_device(x) for x in (key1, key2, filter))
+    k1, k2 = _ikey_dev(key1), _ikey_dev(key2)
+    if k1.n != k2.n:
+        raise ValueError("CombineAccum2Filter: keys must have the same length")
+    f = _bool_dev(filter, k1.n) if filter is not None else None
+    ncell = (int(unique_count1) + 1) * (int(unique_count2) + 1)
+    odt = int_dtype_from_len(ncell)
+    out = DevArray.empty(k1.n, odt)
+    check(lib.rtb_combine_accum2(C.c_void_p(k1.ptr), dtype_code(k1.dtype), C.c_void_p(k2.ptr), dtype_code(k2.dtype),
+                                 C.c_void_p(f.ptr) if f is not None else None, k1.n, int(unique_count1), C.c_void_p(out.ptr),
+                                 dtype_code(odt), _stream()))
+    cnt = BinCount(out, ncell) if device_mode else None
+    if device_mode:
+        return _from_dev(out, True), cnt
+    cnt_dev = DevArray.empty(ncell, np.int32)
+    check(lib.rtb_bincount(C.c_void_p(out.ptr), dtype_code(odt), out.n, ncell, C.c_void_p(cnt_dev.ptr), _stream()))
+    return out.numpy(), cnt_dev.numpy()
+
+
 # ==================================================================================================
 # a5  rc.GroupByAll32 (riptable/rt_numpy.py:1871; riptable/rt_grouping.py:3434-3436)
 def GroupByAll32(values, ikey, unique_rows, funcList, binLowList, binHighList, func_param=0):
@@ -495,6 +542,11 @@ def ReverseShuffle(perm):
     out = DevArray.empty(p.n, np.int32)
     check(lib.rtb_reverse_shuffle(C.c_void_p(p.ptr), p.n, C.c_void_p(out.ptr), _stream()))
     return _from_dev(out, device_mode)
+
+
+__all__ = ["MultiKeyGroupBy32", "CombineFilter", "CombineAccum1Filter", "CombineAccum2Filter", "GroupByAll32", "BinCount",
+           "GroupFromBinCount", "GroupByPack32", "GroupByAllPack32", "EmaAll32", "MakeiFirst", "MakeiNext", "LexSort32",
+           "LexSort64", "GroupFromLexSort", "ReverseShuffle", "LedgerFunction"]
 
 
 def LedgerFunction(func, *args, **kwargs):

@@ -243,3 +243,28 @@ def test_device_mode_chain(rc):
     np.testing.assert_array_equal(ik.cpu().numpy(), ok)
     exp = orc.GroupByAll32([v], ok, ou, [0], [1], [ou + 1], 0)[0]
     np.testing.assert_allclose(s.cpu().numpy()[1:], exp[1:], rtol=1e-12)
+
+
+def test_combine_accum_filters(rc):
+    # rt_numpy.py:1533-1540 docstring: key = (arange(20) % 10) + 1, filter = odd rows
+    key = ((np.arange(20) % 10) + 1).astype(np.int8)
+    f = (np.arange(20) % 2).astype(bool)
+    ik, ifk, u = rc.CombineAccum1Filter(key, 10, f)
+    assert ik.tolist() == [0, 1, 0, 2, 0, 3, 0, 4, 0, 5, 0, 1, 0, 2, 0, 3, 0, 4, 0, 5]
+    assert ik.dtype == np.int8 and ifk.tolist() == [1, 3, 5, 7, 9] and u == 5
+    rng = np.random.default_rng(1)
+    n = 100_000
+    k1 = rng.integers(0, 41, n).astype(np.int16)
+    k2 = rng.integers(0, 7, n).astype(np.int8)
+    flt = rng.random(n) < 0.6
+    for filt in (None, flt):
+        gik, gifk, gu = rc.CombineAccum1Filter(k1, 40, filt)
+        eik, eifk, eu = orc.CombineAccum1Filter(k1, 40, filt)
+        assert gu == eu and gik.dtype == eik.dtype
+        np.testing.assert_array_equal(gik, eik)
+        np.testing.assert_array_equal(gifk, eifk)
+        gik, gcnt = rc.CombineAccum2Filter(k1, k2, 40, 6, filt)
+        eik, ecnt = orc.CombineAccum2Filter(k1, k2, 40, 6, filt)
+        assert gik.dtype == eik.dtype and gcnt.dtype == np.int32
+        np.testing.assert_array_equal(gik, eik)
+        np.testing.assert_array_equal(gcnt, ecnt)

@@ -320,7 +320,7 @@ def main():
     roofline = None
     if dom:
         k = kern[dom]
-        roofline = {"bound": "hbm", "kernel": "gb_round_direct<8>" if dom == "gb_round" else "accum_kernel<OP_SUMF,false>",
+        roofline = {"bound": "hbm", "kernel": "gb_round_direct<8,1> (+ gb_round_insert<8> in the discovery rounds)" if dom == "gb_round" else "accum_kernel<OP_SUMF,false>",
                     "achieved": k["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": k["achieved_gbs"] / peak,
                     "traffic": None, "peak_source": peak_src,
                     "alg_bytes_per_launch": k["rows"] * k["alg_bytes_per_row"] / k["launches"],
@@ -328,7 +328,9 @@ def main():
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                roofline["traffic"] = json.load(open(tp)).get(dom)
+                per_row = json.load(open(tp))[dom]["dram_bytes_per_row"]  # from the committed ncu --set full capture
+                roofline["traffic"] = per_row * k["rows"] / k["launches"]
+                roofline["traffic_source"] = "profiles/traffic.json (ncu dram bytes per row x rows per launch)"
             except Exception:
                 pass
     step_bytes = (ALG_BYTES_HASH + ALG_BYTES_SUM) * rows

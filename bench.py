@@ -212,10 +212,14 @@ def main():
     from riptable_b200.enums import GB_FUNCTIONS
 
     dist = None
-    if world > 1:
+    force_dist = world == 1 and os.environ.get("RTB_BENCH_FORCE_DIST") == "1"  # exercise the shard-merge path on one GPU
+    if force_dist:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+    if world > 1 or force_dist:
         import torch.distributed as tdist
 
-        tdist.init_process_group("nccl", device_id=dev)
+        tdist.init_process_group("nccl", device_id=dev, rank=rank, world_size=world)
         from riptable_b200 import dist as rdist
 
         dist = rdist
@@ -357,7 +361,7 @@ def main():
         "cpu_baseline": cb,
     }
     print(json.dumps(line))
-    if world > 1:
+    if world > 1 or force_dist:
         tdist.destroy_process_group()
     return 0
 

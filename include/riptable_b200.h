@@ -84,6 +84,28 @@ int rtb_multikey_groupby32(const rtb_column* keys, int nkeys, int64_t nrows, int
                            int64_t* unique_count_host, int64_t* ucutoffs_host, int64_t* needed_unique_host,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* Resumable form of a1 for ONE key column of 1, 2, 4 or 8 bytes: consecutive calls group consecutive row chunks as
+ * if they were one array (bins keep counting in first-appearance order; the hash table stays in `workspace`, whose
+ * size is rtb_groupby_workspace_bytes(largest chunk, max_unique, 1, 0)).  This is the `cutoffs`-free half of
+ * riptable's partition merge (riptable/rt_grouping.py:277-413) done in place, and what lets a host-mode caller
+ * overlap PCIe transfers with hashing.
+ *   ikey_out      int32[nrows]       bins of this chunk's rows
+ *   ifirstkey_out int32[max_unique]  the SAME array on every call; first rows of new bins are row_offset + local row
+ *   state         host struct carried between calls (zeroed by the library when resume == 0); state->unique = U so far
+ * A chunk that needs more than max_unique bins fails with RTB_ERR_WORKSPACE and the stream cannot be continued. */
+typedef struct {
+  int64_t unique;     /* bins found so far */
+  int64_t prev_new;   /* new bins / rows of the last round: the discovery rate the next chunk starts from */
+  int64_t prev_rows;
+  int64_t max_unique;
+  uint32_t cap;       /* table capacity in slots */
+  int32_t rounds;
+} rtb_gb_state;
+int rtb_multikey_groupby32_chunk(const rtb_column* key, int64_t nrows, const uint8_t* filter, int32_t* ikey_out,
+                                 int32_t* ifirstkey_out, int64_t max_unique, int64_t row_offset, rtb_gb_state* state,
+                                 int resume, int64_t* needed_unique_host, void* workspace, size_t workspace_bytes,
+                                 void* stream);
+
 /* ---- a4: rc.CombineFilter(key, filter) — riptable/rt_numpy.py:1508.  out = filter ? key : 0, key dtype kept. */
 int rtb_combine_filter(const void* ikey, int kdtype, const uint8_t* filter, int64_t nrows, void* out, void* stream);
 

@@ -15,6 +15,11 @@ class rtb_column(C.Structure):
     _fields_ = [("data", C.c_void_p), ("dtype", C.c_int32), ("itemsize", C.c_int32)]
 
 
+class rtb_gb_state(C.Structure):
+    _fields_ = [("unique", C.c_int64), ("prev_new", C.c_int64), ("prev_rows", C.c_int64), ("max_unique", C.c_int64),
+                ("cap", C.c_uint32), ("rounds", C.c_int32)]
+
+
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         f"riptable_b200: {LIB_PATH} is missing. Build it with `python -m riptable_b200.build` "
@@ -39,6 +44,8 @@ PROTOTYPES = {
         C.c_int,
         [C.POINTER(rtb_column), _i32, _i64, _i64, _vp, _pi64, _i64, _vp, _vp, _i64, _pi64, _pi64, _pi64, _vp, _sz, _vp],
     ),
+    "rtb_multikey_groupby32_chunk": (
+        C.c_int, [C.POINTER(rtb_column), _i64, _vp, _vp, _vp, _i64, _i64, _vp, _i32, _pi64, _vp, _sz, _vp]),
     "rtb_combine_filter": (C.c_int, [_vp, _i32, _vp, _i64, _vp, _vp]),
     "rtb_combine_accum2": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i64, _i64, _vp, _i32, _vp]),
     "rtb_reduce_out_dtype": (C.c_int, [_i32, _i32]),

@@ -660,31 +660,14 @@ extern "C" size_t rtb_groupby_workspace_bytes(int64_t nrows, int64_t max_unique,
   return L.bytes + 256;
 }
 
-extern "C" int rtb_multikey_groupby32(const rtb_column* keys, int nkeys, int64_t nrows, int64_t hint_size,
-                                      const uint8_t* filter, const int64_t* cutoffs_host, int64_t ncutoffs,
-                                      int32_t* ikey_out, int32_t* ifirstkey_out, int64_t max_unique,
-                                      int64_t* unique_count_host, int64_t* ucutoffs_host, int64_t* needed_unique_host,
-                                      void* workspace, size_t workspace_bytes, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  (void)hint_size;  // the shim folds hint_size into max_unique; the table itself is sized adaptively
-  RTB_ARG(keys && nkeys >= 1, "MultiKeyGroupBy32: first argument is not a list of arrays");
-  RTB_ARG(nkeys <= kMaxKeyCols - 1, "MultiKeyGroupBy32: at most %d key columns", kMaxKeyCols - 1);
-  RTB_ARG(nrows >= 0 && nrows <= 2147483646ll, "MultiKeyGroupBy32: row count out of range for int32 iKey");
-  RTB_ARG(unique_count_host, "MultiKeyGroupBy32: null unique_count");
-  *unique_count_host = 0;
-  if (needed_unique_host) *needed_unique_host = 0;
-  if (nrows == 0) return RTB_OK;
-  RTB_ARG(ikey_out && ifirstkey_out && max_unique >= 1, "MultiKeyGroupBy32: null output");
-  RTB_ARG(((uintptr_t)ikey_out % 16) == 0, "MultiKeyGroupBy32: iKey buffer must be 16-byte aligned");
-  for (int c = 0; c < nkeys; c++) RTB_ARG(keys[c].data && keys[c].itemsize >= 1, "MultiKeyGroupBy32: bad key column %d", c);
-  bool has_cut = cutoffs_host != nullptr && ncutoffs > 0;
-  if (has_cut) {
-    RTB_ARG(cutoffs_host[ncutoffs - 1] == nrows, "MultiKeyGroupBy32: last cutoff must equal the row count");
-    for (int64_t i = 1; i < ncutoffs; i++)
-      RTB_ARG(cutoffs_host[i] >= cutoffs_host[i - 1], "MultiKeyGroupBy32: cutoffs must be non-decreasing");
-  }
-  if (max_unique > nrows) max_unique = nrows;
-
+// The round loop shared by the one-shot entry point and the resumable (chunked) one.  `st` carries the table state
+// (capacity, unique count, discovery rate) from one chunk to the next; the table itself lives at the start of the
+// workspace, whose layout depends only on max_unique.  `row_offset` is added to the first rows written to iFirstKey.
+static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8_t* filter, const int64_t* cutoffs_host,
+                   int64_t ncutoffs, int32_t* ikey_out, int32_t* ifirstkey_out, int64_t max_unique,
+                   int64_t* unique_count_host, int64_t* ucutoffs_host, int64_t* needed_unique_host, void* workspace,
+                   size_t workspace_bytes, cudaStream_t stream, rtb_gb_state* st, int64_t row_offset) {
+  const bool has_cut = cutoffs_host != nullptr && ncutoffs > 0;
   GbPlan plan = get_plan();
   static const bool trace = getenv("RTB_GB_TRACE") != nullptr;
   GbLayout L = layout(workspace, workspace_bytes, nrows, max_unique, has_cut, ncutoffs);
@@ -710,13 +693,14 @@ extern "C" int rtb_multikey_groupby32(const rtb_column* keys, int nkeys, int64_t
     kc.ncols = nkeys + 1;
   }
 
-  uint32_t cap = 0;
-  int64_t U = 0;
-  int64_t prev_new = 0, prev_rows = 0;
+  uint32_t cap = st->cap;
+  int64_t U = st->unique;
+  int64_t prev_new = st->prev_new, prev_rows = st->prev_rows;
   int64_t lo = 0;
-  int round = 0;
+  int round = st->rounds;  // rounds since the table was created (0 = nothing known yet)
+  int cround = 0;          // rounds of this chunk: every chunk restarts the geometric schedule with a small probe round
   while (lo < nrows) {
-    int64_t hi = round == 0 ? plan.round0 : lo * plan.ratio;
+    int64_t hi = cround == 0 ? plan.round0 : lo * plan.ratio;
     if (hi > nrows || hi <= lo) hi = nrows;
     int64_t rows = hi - lo;
     // projected new keys in this round: discovery rate of the previous round, never above the row count
@@ -831,7 +815,7 @@ extern "C" int rtb_multikey_groupby32(const rtb_column* keys, int nkeys, int64_t
       int rc = exclusive_scan_u32(L.bitmap, L.prefix, words, SCAN_POPC, L.scan_scratch, nullptr, stream);
       if (rc != RTB_OK) return rc;
       gb_assign_bins<<<grid_for(prev_new, 256, 1), 256, 0, stream>>>(L.table, newlist, L.ctr, lo, L.bitmap, L.prefix,
-                                                                    (uint32_t)U, ifirstkey_out, 0);
+                                                                    (uint32_t)U, ifirstkey_out, -row_offset);
       RTB_LAUNCH_CHECK();
       gb_fixup<<<grid_for(rows, 256, 4), 256, 0, stream>>>(ikey_out, L.table, lo, hi, 0);
       RTB_LAUNCH_CHECK();
@@ -840,7 +824,14 @@ extern "C" int rtb_multikey_groupby32(const rtb_column* keys, int nkeys, int64_t
     prev_rows = rows;
     lo = hi;
     round++;
+    cround++;
   }
+  st->cap = cap;
+  st->unique = U;
+  st->prev_new = prev_new;
+  st->prev_rows = prev_rows;
+  st->rounds = round;
+  st->max_unique = max_unique;
 
   if (has_cut) {
     // global bins -> numbering that restarts per partition; iFirstKey -> partition-relative rows.
@@ -877,4 +868,55 @@ extern "C" int rtb_multikey_groupby32(const rtb_column* keys, int nkeys, int64_t
   RTB_CUDA(cudaStreamSynchronize(stream));
   *unique_count_host = U;
   return RTB_OK;
+}
+
+extern "C" int rtb_multikey_groupby32(const rtb_column* keys, int nkeys, int64_t nrows, int64_t hint_size,
+                                      const uint8_t* filter, const int64_t* cutoffs_host, int64_t ncutoffs,
+                                      int32_t* ikey_out, int32_t* ifirstkey_out, int64_t max_unique,
+                                      int64_t* unique_count_host, int64_t* ucutoffs_host, int64_t* needed_unique_host,
+                                      void* workspace, size_t workspace_bytes, void* stream_) {
+  (void)hint_size;  // the shim folds hint_size into max_unique; the table itself is sized adaptively
+  RTB_ARG(keys && nkeys >= 1, "MultiKeyGroupBy32: first argument is not a list of arrays");
+  RTB_ARG(nkeys <= kMaxKeyCols - 1, "MultiKeyGroupBy32: at most %d key columns", kMaxKeyCols - 1);
+  RTB_ARG(nrows >= 0 && nrows <= 2147483646ll, "MultiKeyGroupBy32: row count out of range for int32 iKey");
+  RTB_ARG(unique_count_host, "MultiKeyGroupBy32: null unique_count");
+  *unique_count_host = 0;
+  if (needed_unique_host) *needed_unique_host = 0;
+  if (nrows == 0) return RTB_OK;
+  RTB_ARG(ikey_out && ifirstkey_out && max_unique >= 1, "MultiKeyGroupBy32: null output");
+  RTB_ARG(((uintptr_t)ikey_out % 16) == 0, "MultiKeyGroupBy32: iKey buffer must be 16-byte aligned");
+  for (int c = 0; c < nkeys; c++) RTB_ARG(keys[c].data && keys[c].itemsize >= 1, "MultiKeyGroupBy32: bad key column %d", c);
+  if (cutoffs_host != nullptr && ncutoffs > 0) {
+    RTB_ARG(cutoffs_host[ncutoffs - 1] == nrows, "MultiKeyGroupBy32: last cutoff must equal the row count");
+    for (int64_t i = 1; i < ncutoffs; i++)
+      RTB_ARG(cutoffs_host[i] >= cutoffs_host[i - 1], "MultiKeyGroupBy32: cutoffs must be non-decreasing");
+  }
+  if (max_unique > nrows) max_unique = nrows;
+  rtb_gb_state st;
+  memset(&st, 0, sizeof(st));
+  return gb_core(keys, nkeys, nrows, filter, cutoffs_host, ncutoffs, ikey_out, ifirstkey_out, max_unique, unique_count_host,
+                 ucutoffs_host, needed_unique_host, workspace, workspace_bytes, (cudaStream_t)stream_, &st, 0);
+}
+
+extern "C" int rtb_multikey_groupby32_chunk(const rtb_column* key, int64_t nrows, const uint8_t* filter, int32_t* ikey_out,
+                                            int32_t* ifirstkey_out, int64_t max_unique, int64_t row_offset,
+                                            rtb_gb_state* state, int resume, int64_t* needed_unique_host, void* workspace,
+                                            size_t workspace_bytes, void* stream_) {
+  RTB_ARG(key && state, "groupby chunk: null key or state");
+  RTB_ARG(key->itemsize == 1 || key->itemsize == 2 || key->itemsize == 4 || key->itemsize == 8,
+          "groupby chunk: one key column of 1, 2, 4 or 8 bytes");
+  RTB_ARG(nrows >= 0 && nrows <= 2147483646ll, "groupby chunk: row count out of range");
+  RTB_ARG(max_unique >= 1 && ifirstkey_out, "groupby chunk: bad max_unique or null iFirstKey");
+  RTB_ARG(row_offset >= 0 && row_offset + nrows <= 2147483646ll, "groupby chunk: first rows must fit int32");
+  if (!resume) memset(state, 0, sizeof(*state));
+  else RTB_ARG(state->max_unique == max_unique, "groupby chunk: max_unique must not change between chunks");
+  state->max_unique = max_unique;
+  if (needed_unique_host) *needed_unique_host = 0;
+  if (nrows == 0) return RTB_OK;
+  RTB_ARG(key->data && ikey_out && ((uintptr_t)ikey_out % 16) == 0 && ((uintptr_t)key->data % 16) == 0 &&
+              (!filter || ((uintptr_t)filter % 4) == 0),
+          "groupby chunk: buffers must be 16-byte aligned");
+  int64_t u = 0;
+  return gb_core(key, 1, nrows, filter, nullptr, 0, ikey_out, ifirstkey_out, max_unique, &u, nullptr, needed_unique_host,
+                 workspace, workspace_bytes, (cudaStream_t)stream_, state, row_offset);
 }

@@ -206,10 +206,21 @@ __global__ void __launch_bounds__(256) reverse_shuffle_kernel(const int32_t* __r
 __global__ void __launch_bounds__(256) remap_kernel(const int32_t* __restrict__ ikey, int64_t n,
                                                      const int32_t* __restrict__ map, int64_t nmap,
                                                      int32_t* __restrict__ out) {
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    int32_t k = ikey[i];
-    out[i] = (k >= 0 && k < nmap) ? map[k] : 0;
+  // 4 rows per thread through 128-bit loads/stores; the map (4 B x bins) is an L2-resident gather
+  int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 3 < n) {
+      uint4 k = ld_stream_u4(ikey + i);
+      uint32_t kk[4] = {k.x, k.y, k.z, k.w}, o[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) o[j] = kk[j] < (uint32_t)nmap ? (uint32_t)__ldg(map + kk[j]) : 0u;
+      st_stream_u4(out + i, make_uint4(o[0], o[1], o[2], o[3]));
+    } else {
+      for (int64_t q = i; q < n; q++) {
+        int32_t k = ikey[q];
+        out[q] = (k >= 0 && k < nmap) ? map[k] : 0;
+      }
+    }
   }
 }
 
@@ -272,7 +283,8 @@ int rtb_reverse_shuffle(const int32_t* perm, int64_t n, int32_t* out, void* stre
 
 int rtb_remap_ikey(const int32_t* ikey, int64_t nrows, const int32_t* map, int64_t nmap, int32_t* out, void* stream) {
   if (nrows <= 0) return RTB_OK;
-  remap_kernel<<<grid_for(nrows, 256, 1), 256, 0, (cudaStream_t)stream>>>(ikey, nrows, map, nmap, out);
+  RTB_ARG(((uintptr_t)ikey % 16) == 0 && ((uintptr_t)out % 16) == 0, "remap: buffers must be 16-byte aligned");
+  remap_kernel<<<grid_for(nrows, 256, 4, 32), 256, 0, (cudaStream_t)stream>>>(ikey, nrows, map, nmap, out);
   RTB_LAUNCH_CHECK();
   return RTB_OK;
 }

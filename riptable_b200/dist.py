@@ -24,6 +24,8 @@ on CPU with world_size 2.  There is no CPU fallback inside this module.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as tdist
@@ -42,6 +44,7 @@ class CudaOps:
 
         self.rc = rc
         self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self._side = None
 
     # -- columns ---------------------------------------------------------------------------------
     def as_col(self, x):
@@ -87,19 +90,36 @@ class CudaOps:
         return c  # DevArray is accepted by rc directly
 
     def remap(self, ikey, table):
+        """out[i] = table[ikey[i]] on a side stream: the gather is bound by the L1TEX wavefront rate while the
+        reductions that follow are bound by the L2 atomic unit, so the two overlap well.  Returns (out, event)."""
         from ._lib import lib, check
         import ctypes as C
 
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        cur = torch.cuda.current_stream()
         out = torch.empty_like(ikey)
+        self._side.wait_stream(cur)
+        for t in (ikey, table, out):
+            t.record_stream(self._side)
         check(lib.rtb_remap_ikey(C.c_void_p(ikey.data_ptr()), ikey.numel(), C.c_void_p(table.data_ptr()), table.numel(),
-                                 C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-        return out
+                                 C.c_void_p(out.data_ptr()), C.c_void_p(self._side.cuda_stream)))
+        ev = torch.cuda.Event()
+        ev.record(self._side)
+        return out, ev
+
+    def wait(self, ev):
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
 
     def reduce(self, val, ikey, nuniq, func):
         return self.rc.GroupByAll32([val], ikey, nuniq, [int(func)], [0], [nuniq + 1], 0)[0]
 
     def bincount(self, ikey, nbins):
         return self.rc.BinCount(ikey, nbins)
+
+    def torch_dtype(self, col):
+        return col.torch().dtype
 
     def valid_mask_as_i8(self, col):
         t = col.torch()
@@ -133,13 +153,25 @@ def _all_gather_var(t: torch.Tensor, counts, group):
 class ShardedGrouping:
     """Result of `sharded_groupby`: global bin ids for this rank's rows plus the replicated group table."""
 
-    def __init__(self, ikey, ifirstkey, unique_count, row_offset, nrows_total, shard_unique_counts):
-        self.ikey = ikey                    # int32[n_r]  global base-1 bin of every local row (0 = filtered)
+    def __init__(self, ops, gikey, gikey_ready, local_ikey, local_unique_count, table, ifirstkey, unique_count, row_offset,
+                 nrows_total, shard_unique_counts):
+        self._ops, self._gikey, self._ready = ops, gikey, gikey_ready
+        self.local_ikey = local_ikey        # int32[n_r]  this shard's own first-appearance bins (what reductions read)
+        self.local_unique_count = local_unique_count
+        self.table = table                  # int32[u_r + 1] local bin -> global bin (table[0] = 0)
         self.ifirstkey = ifirstkey          # int64[U]    GLOBAL row of each bin's first appearance (replicated)
         self.unique_count = unique_count    # U
         self.row_offset = row_offset        # first global row of this shard
         self.nrows_total = nrows_total
         self.shard_unique_counts = shard_unique_counts
+
+    @property
+    def ikey(self):
+        """int32[n_r] global base-1 bin of every local row (0 = filtered); waits for the re-index pass."""
+        if self._ready is not None:
+            self._ops.wait(self._ready)
+            self._ready = None
+        return self._gikey
 
 
 def sharded_groupby(ops, key_cols, filter=None, group=None) -> ShardedGrouping:
@@ -147,8 +179,10 @@ def sharded_groupby(ops, key_cols, filter=None, group=None) -> ShardedGrouping:
     G, rank = _world(group)
     cols = [ops.as_col(c) for c in key_cols]
     n = ops.nrows(cols[0])
+    tick = _Tick()
     ik, ifk, u = ops.groupby(cols, filter)
     ik, ifk = ops.to_torch(ik), ops.to_torch(ifk)
+    tick.mark("local groupby")
 
     # shard sizes and unique counts of every rank
     meta = ops.tensor([n, u], dtype=torch.int64)
@@ -173,19 +207,28 @@ def sharded_groupby(ops, key_cols, filter=None, group=None) -> ShardedGrouping:
         stacked.append(ops.col_from_bytes(allb, dt, total_u))
     gfirst_local = ifk[:u].to(torch.int64) + row_off[rank]
     all_first = _all_gather_var(gfirst_local, us, group)
+    tick.mark("gather uniques")
 
     if total_u == 0:
         empty64 = all_first.new_empty(0)
-        return ShardedGrouping(ik, empty64, 0, row_off[rank], sum(ns), us)
+        return ShardedGrouping(ops, ik, None, ik, 0, torch.zeros(1, dtype=torch.int32, device=ik.device), empty64, 0,
+                               row_off[rank], sum(ns), us)
 
     gk, gfk, U = ops.groupby(stacked, None)
     gk, gfk = ops.to_torch(gk), ops.to_torch(gfk)
+    tick.mark("group stacked uniques")
     # local bin b (1..u) -> global bin of stacked row uoff[rank] + b - 1; bin 0 stays 0
     table = torch.zeros(u + 1, dtype=torch.int32, device=gk.device)
     table[1:] = gk[uoff[rank]: uoff[rank] + u]
-    gikey = ops.remap(ik, table)
+    if rank == 0:
+        gikey, ready = ik, None  # the first shard's uniques lead the stacked list: its local bins are the global bins
+    else:
+        gikey, ready = ops.remap(ik, table)
+    tick.mark("remap ikey (enqueue)")
     ifirst_global = all_first.index_select(0, gfk[:U].to(torch.int64))
-    return ShardedGrouping(gikey, ifirst_global, int(U), row_off[rank], sum(ns), us)
+    tick.mark("ifirstkey")
+    tick.report()
+    return ShardedGrouping(ops, gikey, ready, ik, u, table, ifirst_global, int(U), row_off[rank], sum(ns), us)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -297,28 +340,39 @@ def sharded_reduce(ops, values, grouping: ShardedGrouping, func, group=None, all
     nb = U + 1
     nan_op = func >= 50
     base = func - 50 if nan_op else func
-    ik = grouping.ikey
+    ik = grouping.local_ikey          # reduce against the shard's own bins; only U-sized partials are re-indexed
+    lu = grouping.local_unique_count
+    table = grouping.table.to(torch.int64)
     val = ops.as_col(values)
 
-    def red(f):
-        return ops.to_torch(ops.reduce(val, ik, U, f))
+    def to_global(local, fill):
+        out = torch.full((nb,), fill, dtype=local.dtype, device=local.device)
+        out[table] = local
+        return out
+
+    def red(f, fill):
+        return to_global(ops.to_torch(ops.reduce(val, ik, lu, f)), fill)
+
+    def counts(valid_only):
+        return to_global(_valid_counts(ops, val, ik, lu, valid_only), 0)
 
     if base == GB.GB_SUM:
-        return _combine("sum", {"v": red(func)}, nb, nan_op, group, alltoall_min_bins)["v"]
+        return _combine("sum", {"v": red(func, 0)}, nb, nan_op, group, alltoall_min_bins)["v"]
     if base == GB.GB_MEAN:
         # per-bin (sum, count of accumulated rows): count = rows that a nan-op would keep
-        s = red(GB.GB_NANSUM if nan_op else GB.GB_SUM).to(torch.float64)
-        c = _valid_counts(ops, val, ik, U, nan_op)
+        s = red(GB.GB_NANSUM if nan_op else GB.GB_SUM, 0).to(torch.float64)
+        c = counts(nan_op)
         return _combine("mean", {"s": s, "c": c}, nb, nan_op, group, alltoall_min_bins)["v"]
     if base in (GB.GB_MIN, GB.GB_MAX):
-        a = red(func)
-        c = ops.to_torch(ops.bincount(ik, nb))
+        odt = ops.torch_dtype(val)  # min/max keep the value dtype
+        a = red(func, _invalid_value(odt))
+        c = counts(False)
         kind = "min" if base == GB.GB_MIN else "max"
         return _combine(kind, {"a": a, "c": c}, nb, nan_op, group, alltoall_min_bins)["v"]
     if base in (GB.GB_VAR, GB.GB_STD):
-        c = _valid_counts(ops, val, ik, U, nan_op)
-        mean = red(GB.GB_NANMEAN if nan_op else GB.GB_MEAN)
-        var = red(GB.GB_NANVAR if nan_op else GB.GB_VAR)  # ddof = 1 locally
+        c = counts(nan_op)
+        mean = red(GB.GB_NANMEAN if nan_op else GB.GB_MEAN, float("nan"))
+        var = red(GB.GB_NANVAR if nan_op else GB.GB_VAR, float("nan"))  # ddof = 1 locally
         cf = c.to(torch.float64)
         m2 = torch.where(c >= 2, var * (cf - 1.0), torch.zeros_like(var))  # NaN var (a NaN input) stays NaN
         if not nan_op:
@@ -340,13 +394,39 @@ def _valid_counts(ops, val, ik, U, nan_op):
 
 def sharded_count(ops, grouping: ShardedGrouping, group=None, alltoall_min_bins=ALLTOALL_MIN_BINS):
     """Grouping.count across shards: rc.BinCount per shard, summed."""
-    c = ops.to_torch(ops.bincount(grouping.ikey, grouping.unique_count + 1))
-    return _combine("count", {"v": c}, grouping.unique_count + 1, False, group, alltoall_min_bins)["v"]
+    c = ops.to_torch(ops.bincount(grouping.local_ikey, grouping.local_unique_count + 1))
+    full = torch.zeros(grouping.unique_count + 1, dtype=c.dtype, device=c.device)
+    full[grouping.table.to(torch.int64)] = c
+    return _combine("count", {"v": full}, grouping.unique_count + 1, False, group, alltoall_min_bins)["v"]
+
+
+_TRACE = os.environ.get("RTB_DIST_TRACE") == "1"
+
+
+class _Tick:
+    """CUDA-event stopwatch for RTB_DIST_TRACE=1 (prints the per-phase device time of one sharded step on rank 0)."""
+
+    def __init__(self):
+        self.ev, self.names = [], []
+        self.mark("start")
+
+    def mark(self, name):
+        if _TRACE:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.ev.append(e)
+            self.names.append(name)
+
+    def report(self):
+        if _TRACE and tdist.get_rank() == 0:
+            torch.cuda.synchronize()
+            parts = [f"{self.names[i]} {self.ev[i - 1].elapsed_time(self.ev[i]):.2f}" for i in range(1, len(self.ev))]
+            print("[rtb dist] ms: " + ", ".join(parts), flush=True)
 
 
 def sharded_groupby_sum(key_cols, values, group=None, ops=None):
     """bench.py's multi-GPU step: sharded hash grouping + GB_SUM.  -> (ikey, ifirstkey, U, sums[U+1])."""
     ops = ops or CudaOps()
     g = sharded_groupby(ops, key_cols, None, group)
-    s = sharded_reduce(ops, values, g, GB.GB_SUM, group)
+    s = sharded_reduce(ops, values, g, GB.GB_SUM, group)  # runs while the re-index pass is still on its side stream
     return g.ikey, g.ifirstkey, g.unique_count, s

@@ -270,6 +270,46 @@ def CombineAccum1Filter(key1, unique_count1, filter=None):
     return ik.cpu().numpy(), ifk.cpu().numpy(), u
 
 
+class GroupByStream:
+    """Resumable MultiKeyGroupBy32 over consecutive row chunks of ONE 1/2/4/8-byte key column (device mode).
+
+    `push(chunk)` returns the chunk's iKey; bins keep counting in first-appearance order across chunks, so the
+    concatenation of the returned iKeys equals one MultiKeyGroupBy32 call on the concatenated keys.  Used by
+    riptable_b200.dist (seeded shards) and by the host-mode pipeline that overlaps PCIe copies with hashing."""
+
+    def __init__(self, max_unique: int, max_chunk_rows: int):
+        self.max_unique = int(max_unique)
+        self.max_chunk_rows = int(max_chunk_rows)
+        self.state = _lib.rtb_gb_state()
+        self._started = False
+        self.ifirst = DevArray.empty(self.max_unique, np.int32)
+        self._ws = _ws(lib.rtb_groupby_workspace_bytes(self.max_chunk_rows, self.max_unique, 1, 0))
+
+    @property
+    def unique_count(self) -> int:
+        return int(self.state.unique)
+
+    @property
+    def ifirstkey(self) -> torch.Tensor:
+        return self.ifirst.torch()[: self.unique_count]
+
+    def push(self, keys, filter=None, row_offset: int = 0, out: torch.Tensor | None = None) -> torch.Tensor:
+        k = _to_dev(keys)
+        if k.n > self.max_chunk_rows:
+            raise ValueError(f"chunk of {k.n} rows exceeds max_chunk_rows={self.max_chunk_rows}")
+        f = _bool_dev(filter, k.n) if filter is not None else None
+        ik = out if out is not None else torch.empty(max(k.n, 4), dtype=torch.int32, device=_device())
+        needed = C.c_int64(0)
+        col = _col(k)
+        rc_ = lib.rtb_multikey_groupby32_chunk(
+            C.byref(col), k.n, C.c_void_p(f.ptr) if f is not None else None, C.c_void_p(ik.data_ptr()),
+            C.c_void_p(self.ifirst.ptr), self.max_unique, int(row_offset), C.byref(self.state), int(self._started),
+            C.byref(needed), C.c_void_p(self._ws.data_ptr()), self._ws.numel(), _stream())
+        check(rc_, needed.value)
+        self._started = True
+        return ik[: k.n]
+
+
 def _combine_filter_dev(k: DevArray, f: DevArray) -> DevArray:
     out = DevArray.empty(k.n, k.dtype)
     check(lib.rtb_combine_filter(C.c_void_p(k.ptr), dtype_code(k.dtype), C.c_void_p(f.ptr), k.n, C.c_void_p(out.ptr), _stream()))
@@ -544,7 +584,7 @@ def ReverseShuffle(perm):
     return _from_dev(out, device_mode)
 
 
-__all__ = ["MultiKeyGroupBy32", "CombineFilter", "CombineAccum1Filter", "CombineAccum2Filter", "GroupByAll32", "BinCount",
+__all__ = ["GroupByStream", "MultiKeyGroupBy32", "CombineFilter", "CombineAccum1Filter", "CombineAccum2Filter", "GroupByAll32", "BinCount",
            "GroupFromBinCount", "GroupByPack32", "GroupByAllPack32", "EmaAll32", "MakeiFirst", "MakeiNext", "LexSort32",
            "LexSort64", "GroupFromLexSort", "ReverseShuffle", "LedgerFunction"]
 

@@ -38,7 +38,13 @@ class OracleOps:
         return orc.MultiKeyGroupBy32(list(cols), 0, filter, 2)
 
     def remap(self, ikey, table):
-        return table[ikey.to(torch.int64)]
+        return table[ikey.to(torch.int64)], None
+
+    def wait(self, ev):
+        pass
+
+    def torch_dtype(self, col):
+        return torch.from_numpy(np.asarray(col)[:0].copy()).dtype
 
     def reduce(self, val, ikey, nuniq, func):
         ik = ikey.numpy() if isinstance(ikey, torch.Tensor) else ikey

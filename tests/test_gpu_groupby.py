@@ -268,3 +268,28 @@ def test_combine_accum_filters(rc):
         assert gik.dtype == eik.dtype and gcnt.dtype == np.int32
         np.testing.assert_array_equal(gik, eik)
         np.testing.assert_array_equal(gcnt, ecnt)
+
+
+def test_groupby_stream_chunks_equal_one_shot(rc):
+    # the resumable form: chunked calls == one call on the concatenation (bins keep counting across chunks)
+    import torch
+
+    rng = np.random.default_rng(21)
+    for dt, n, u, cuts in ((np.int64, 3_000_000, 200_000, [0, 1_000_000, 1_000_128, 2_500_000, 3_000_000]),
+                           (np.int32, 500_000, 3_000, [0, 100_000, 500_000]),
+                           (np.int16, 200_001, 50, [0, 1, 65, 200_001])):
+        vals = rng.integers(np.iinfo(dt).min // 2, np.iinfo(dt).max // 2, u).astype(dt)
+        k = vals[rng.integers(0, u, n)]
+        k[: n // 2] = vals[rng.integers(0, u // 2 + 1, n // 2)]  # half of the keys only show up late
+        filt = rng.random(n) < 0.9
+        for f in (None, filt):
+            eik, eifk, eu = orc.MultiKeyGroupBy32([k], 0, f, 2)
+            st = rc.GroupByStream(max_unique=max(eu, 1024), max_chunk_rows=max(b - a for a, b in zip(cuts, cuts[1:])))
+            parts = []
+            for a, b in zip(cuts, cuts[1:]):
+                kc = torch.from_numpy(k[a:b].copy()).cuda()
+                fc = None if f is None else torch.from_numpy(f[a:b].copy()).cuda()
+                parts.append(st.push(kc, fc, row_offset=a).cpu().numpy())
+            assert st.unique_count == eu
+            np.testing.assert_array_equal(np.concatenate(parts), eik)
+            np.testing.assert_array_equal(st.ifirstkey.cpu().numpy(), eifk)

@@ -33,6 +33,8 @@ import torch.distributed as tdist
 from .enums import GB_FUNCTIONS as GB
 
 ALLTOALL_MIN_BINS = 8_000_000  # above this many bins the partials are merged by bin-partitioned all-to-all
+SEEDED = os.environ.get("RTB_DIST_SEEDED", "1") == "1"
+SEED_ROWS = 1 << 25  # rows of the first shard that are grouped before the other shards start
 
 
 # ====================================================================================================
@@ -112,6 +114,23 @@ class CudaOps:
         if ev is not None:
             torch.cuda.current_stream().wait_event(ev)
 
+    def stream(self, max_unique, max_chunk_rows):
+        """Resumable single-key grouping (rc.GroupByStream): push(keys, filter, row_offset, out) -> iKey of the chunk."""
+        return self.rc.GroupByStream(max_unique, max_chunk_rows)
+
+    def can_stream(self, col):
+        return col.dtype.kind in "biuf" and col.dtype.itemsize in (1, 2, 4, 8)
+
+    def slice_rows(self, col, lo, hi):
+        isz = col.dtype.itemsize
+        return self.rc.DevArray(col.buf[lo * isz:], col.dtype, hi - lo) if hi > lo else self.rc.DevArray.empty(0, col.dtype)
+
+    def slice_filter(self, f, lo, hi):
+        return None if f is None else f[lo:hi]
+
+    def empty_ikey(self, n):
+        return torch.empty(max(n, 4), dtype=torch.int32, device=self.device)
+
     def reduce(self, val, ikey, nuniq, func):
         return self.rc.GroupByAll32([val], ikey, nuniq, [int(func)], [0], [nuniq + 1], 0)[0]
 
@@ -179,6 +198,8 @@ def sharded_groupby(ops, key_cols, filter=None, group=None) -> ShardedGrouping:
     G, rank = _world(group)
     cols = [ops.as_col(c) for c in key_cols]
     n = ops.nrows(cols[0])
+    if len(cols) == 1 and SEEDED and hasattr(ops, "stream") and ops.can_stream(cols[0]):
+        return _sharded_groupby_seeded(ops, cols[0], filter, group)
     tick = _Tick()
     ik, ifk, u = ops.groupby(cols, filter)
     ik, ifk = ops.to_torch(ik), ops.to_torch(ifk)
@@ -229,6 +250,97 @@ def sharded_groupby(ops, key_cols, filter=None, group=None) -> ShardedGrouping:
     tick.mark("ifirstkey")
     tick.report()
     return ShardedGrouping(ops, gikey, ready, ik, u, table, ifirst_global, int(U), row_off[rank], sum(ns), us)
+
+
+def _sharded_groupby_seeded(ops, col, filter, group) -> ShardedGrouping:
+    """Single-key shards, seeded: global bin ids come out of the hash pass itself, no per-row re-index.
+
+    Global first-appearance order lists every key of shard 0 first (in shard 0's own order).  Shard 0 therefore groups
+    a prefix of its rows, broadcasts the keys it found (u0 of them, typically all) with their bins 1..u0, and every
+    other rank pre-loads its table with exactly those keys before hashing its own rows (the resumable grouping of
+    rc.GroupByStream).  Rows whose key is in the seed get their GLOBAL bin directly.  Keys outside the seed ("late"
+    keys: first seen after the prefix of shard 0, or absent from shard 0) get provisional bins above u0; only if any
+    rank reports such keys are they merged (all-gather of the late uniques in rank order, re-group, re-index)."""
+    G, rank = _world(group)
+    n = ops.nrows(col)
+    dt = ops.col_dtype(col)
+    tick = _Tick()
+    meta = ops.tensor([n], dtype=torch.int64)
+    alln = meta.new_empty(G)
+    tdist.all_gather_into_tensor(alln, meta, group=group)
+    ns = alln.cpu().tolist()
+    row_off = [0] * G
+    for r in range(1, G):
+        row_off[r] = row_off[r - 1] + ns[r - 1]
+    nmax = max(ns) if ns else 0
+    max_unique = max(1 << 20, nmax // 16, 1)
+    S = min(ns[0], SEED_ROWS) & ~127 if ns[0] > SEED_ROWS else ns[0]
+    st = ops.stream(max_unique, max(nmax, 1))
+    ikey = ops.empty_ikey(n)
+
+    # 1. shard 0 groups its prefix and publishes the seed
+    if rank == 0:
+        st.push(ops.slice_rows(col, 0, S), ops.slice_filter(filter, 0, S), 0, ikey[:S] if S else None)
+    u0_t = ops.tensor([st.unique_count if rank == 0 else 0], dtype=torch.int64)
+    tdist.broadcast(u0_t, src=tdist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    u0 = int(u0_t.item())
+    if u0 > max_unique:
+        raise RuntimeError("sharded_groupby: more unique keys than the provisioned table holds")
+    if rank == 0:
+        seed_first = ops.to_torch(st.ifirstkey).to(torch.int64).clone()
+        seed_bytes = ops.col_bytes(ops.take_rows(col, ops.to_torch(st.ifirstkey))).clone()
+    else:
+        seed_first = ops.tensor([0], dtype=torch.int64).new_empty(u0)
+        seed_bytes = ops.tensor([0], dtype=torch.uint8).new_empty(u0 * dt.itemsize)
+    src = tdist.get_global_rank(group, 0) if group is not None else 0
+    if u0:
+        tdist.broadcast(seed_bytes, src=src, group=group)
+        tdist.broadcast(seed_first, src=src, group=group)
+    tick.mark("seed (shard 0 prefix + broadcast)")
+
+    # 2. every other rank pre-loads the seed, then all ranks hash their (remaining) rows
+    if rank != 0 and u0:
+        st.push(ops.col_from_bytes(seed_bytes, dt, u0), None, 0, None)
+        if st.unique_count != u0:
+            raise RuntimeError("sharded_groupby: the broadcast seed holds duplicate keys")
+    lo = S if rank == 0 else 0
+    if n > lo:
+        st.push(ops.slice_rows(col, lo, n), ops.slice_filter(filter, lo, n), lo, ikey[lo:n])
+    ikey = ikey[:n]
+    U_r = st.unique_count
+    tick.mark("hash shard")
+
+    # 3. late keys (rare): merge them across ranks
+    late = ops.tensor([U_r - u0], dtype=torch.int64)
+    lates = late.new_empty(G)
+    tdist.all_gather_into_tensor(lates, late, group=group)
+    lates = lates.cpu().tolist()
+    total_late = sum(lates)
+    if total_late == 0:
+        tick.mark("late check")
+        tick.report()
+        return ShardedGrouping(ops, ikey, None, ikey, u0, None, seed_first, u0, row_off[rank], sum(ns), [u0] * G)
+    ifk = ops.to_torch(st.ifirstkey)
+    late_rows = ifk[u0:U_r]
+    late_keys = ops.take_rows(col, late_rows)
+    stacked = ops.col_from_bytes(_all_gather_var(ops.col_bytes(late_keys), [x * dt.itemsize for x in lates], group), dt, total_late)
+    all_first = _all_gather_var(late_rows.to(torch.int64) + row_off[rank], lates, group)
+    gk, gfk, L = ops.groupby([stacked], None)
+    gk, gfk = ops.to_torch(gk), ops.to_torch(gfk)
+    loff = sum(lates[:rank])
+    table = torch.arange(U_r + 1, dtype=torch.int32, device=gk.device)
+    table[u0 + 1:] = gk[loff: loff + lates[rank]] + u0
+    if rank == 0:
+        gikey, ready = ikey, None  # shard 0's late keys lead the stacked list: already global
+    else:
+        gikey, ready = ops.remap(ikey, table)
+    ifirst_global = torch.cat([seed_first, all_first.index_select(0, gfk[:L].to(torch.int64))])
+    U = u0 + int(L)
+    tick.mark("late merge")
+    tick.report()
+    g = ShardedGrouping(ops, gikey, ready, None, U, None, ifirst_global, U, row_off[rank], sum(ns), [u0 + x for x in lates])
+    g.local_ikey = g.ikey  # reductions read the merged bins (this waits for the re-index pass)
+    return g
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -342,10 +454,12 @@ def sharded_reduce(ops, values, grouping: ShardedGrouping, func, group=None, all
     base = func - 50 if nan_op else func
     ik = grouping.local_ikey          # reduce against the shard's own bins; only U-sized partials are re-indexed
     lu = grouping.local_unique_count
-    table = grouping.table.to(torch.int64)
+    table = grouping.table.to(torch.int64) if grouping.table is not None else None  # None: local bins are global
     val = ops.as_col(values)
 
     def to_global(local, fill):
+        if table is None:
+            return local
         out = torch.full((nb,), fill, dtype=local.dtype, device=local.device)
         out[table] = local
         return out
@@ -395,8 +509,11 @@ def _valid_counts(ops, val, ik, U, nan_op):
 def sharded_count(ops, grouping: ShardedGrouping, group=None, alltoall_min_bins=ALLTOALL_MIN_BINS):
     """Grouping.count across shards: rc.BinCount per shard, summed."""
     c = ops.to_torch(ops.bincount(grouping.local_ikey, grouping.local_unique_count + 1))
-    full = torch.zeros(grouping.unique_count + 1, dtype=c.dtype, device=c.device)
-    full[grouping.table.to(torch.int64)] = c
+    if grouping.table is None:
+        full = c
+    else:
+        full = torch.zeros(grouping.unique_count + 1, dtype=c.dtype, device=c.device)
+        full[grouping.table.to(torch.int64)] = c
     return _combine("count", {"v": full}, grouping.unique_count + 1, False, group, alltoall_min_bins)["v"]
 
 

@@ -60,8 +60,57 @@ class OracleOps:
     def tensor(self, x, dtype=None):
         return torch.as_tensor(x, dtype=dtype)
 
+    # --- resumable single-key grouping (stand-in for rc.GroupByStream) ---------------------------------------
+    def stream(self, max_unique, max_chunk_rows):
+        return _OracleStream()
+
+    def can_stream(self, col):
+        return col.dtype.kind in "biuf" and col.dtype.itemsize in (1, 2, 4, 8)
+
+    def slice_rows(self, col, lo, hi):
+        return col[lo:hi]
+
+    def slice_filter(self, f, lo, hi):
+        return None if f is None else np.asarray(f)[lo:hi]
+
+    def empty_ikey(self, n):
+        return torch.zeros(max(n, 4), dtype=torch.int32)
+
     def to_torch(self, x):
         return torch.from_numpy(np.ascontiguousarray(x)) if isinstance(x, np.ndarray) else x
+
+
+class _OracleStream:
+    """Chunked first-appearance grouping restated with the oracle: group [uniques so far ; chunk] in one call."""
+
+    def __init__(self):
+        self.uniq = None
+        self.first = np.zeros(0, np.int32)
+
+    @property
+    def unique_count(self):
+        return len(self.first)
+
+    @property
+    def ifirstkey(self):
+        return self.first
+
+    def push(self, keys, filter=None, row_offset=0, out=None):
+        keys = np.asarray(keys)
+        u = self.unique_count
+        allk = keys if self.uniq is None else np.concatenate([self.uniq, keys])
+        f = None
+        if filter is not None:
+            f = np.concatenate([np.ones(u, bool), np.asarray(filter, dtype=bool)])
+        ik, ifk, U = orc.MultiKeyGroupBy32([allk], 0, f, 2)
+        assert np.array_equal(ik[:u], np.arange(1, u + 1))
+        self.first = np.concatenate([self.first, (ifk[u:] - u + row_offset).astype(np.int32)])
+        self.uniq = allk[ifk]
+        res = torch.from_numpy(ik[u:].copy())
+        if out is not None:
+            out[: len(res)] = res
+        return res
+
 
 
 def _make(seed, n):
@@ -82,11 +131,12 @@ def _worker(rank, world, port, n, cuts, a2a, q):
     try:
         from riptable_b200 import dist as rd
 
+        rd.SEED_ROWS = 1024  # shard 0's seed prefix is much smaller than the shard: late keys get merged
         k1, k2, v, vi, f = _make(7, n)
         lo, hi = cuts[rank], cuts[rank + 1]
         ops = OracleOps()
         out = {}
-        for name, keys, filt in (("one", [k1], None), ("two", [k1, k2], None), ("filt", [k1, k2], f)):
+        for name, keys, filt in (("one", [k1], None), ("onef", [k1], f), ("two", [k1, k2], None), ("filt", [k1, k2], f)):
             g = rd.sharded_groupby(ops, [k[lo:hi] for k in keys], None if filt is None else filt[lo:hi])
             res = {"ikey": g.ikey.numpy().copy(), "ifk": g.ifirstkey.numpy().copy(), "u": g.unique_count,
                    "off": g.row_offset}
@@ -125,7 +175,7 @@ def test_sharded_groupby_and_reduce_world2(cuts, a2a):
         assert p.exitcode == 0
 
     k1, k2, v, vi, f = _make(7, n)
-    for name, keys, filt in (("one", [k1], None), ("two", [k1, k2], None), ("filt", [k1, k2], f)):
+    for name, keys, filt in (("one", [k1], None), ("onef", [k1], f), ("two", [k1, k2], None), ("filt", [k1, k2], f)):
         eik, eifk, eu = orc.MultiKeyGroupBy32(keys, 0, filt, 2)
         full = np.concatenate([got[r][name]["ikey"] for r in range(2)])
         np.testing.assert_array_equal(full, eik)               # global bin ids, bit-exact with the single-process run

@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""Secondary measurements (not the headline bench): the other BASELINE.json configs on one B200, device mode, CUDA
+events, 1 warm-up + 3 timed.  Prints one JSON line per operation with rows/s and algorithmic GB/s."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import riptable_b200.rc as rc  # noqa: E402
+
+
+def timed(fn, reps=3):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, out
+
+
+def line(name, n, ms, alg_bytes_per_row, **kw):
+    print(json.dumps({"op": name, "rows": n, "ms": round(ms, 3), "rows_per_s": n / ms * 1e3,
+                      "alg_bytes_per_row": alg_bytes_per_row, "alg_GBps": n * alg_bytes_per_row / ms / 1e6, **kw}), flush=True)
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000_000
+    g = torch.Generator(device="cuda")
+    g.manual_seed(12345)
+
+    def keys(u, dtype=torch.int64):
+        uv = torch.randint(-(2**62), 2**62, (u,), dtype=torch.int64, device="cuda", generator=g)
+        k = torch.empty(n, dtype=torch.int64, device="cuda")
+        for s in range(0, n, 1 << 27):
+            e = min(n, s + (1 << 27))
+            torch.index_select(uv, 0, torch.randint(0, u, (e - s,), device="cuda", generator=g), out=k[s:e])
+        return k
+
+    # C1-like: int32 key with 1K uniques, f64 sum + mean on int16 iKey
+    k32 = torch.randint(0, 1000, (n,), device="cuda", generator=g, dtype=torch.int32)
+    ms, (ik, ifk, u) = timed(lambda: rc.MultiKeyGroupBy32([k32], 0, None, 2))
+    line("C1 hash int32 key 1K uniques", n, ms, 8, uniques=u)
+    ik16 = ik.to(torch.int16)
+    val = torch.rand(n, device="cuda", generator=g, dtype=torch.float64)
+    ms, _ = timed(lambda: rc.GroupByAll32([val], ik16, u, [0], [1], [u + 1], 0))
+    line("C1 sum f64 by int16 iKey (smem-privatised)", n, ms, 10)
+    ms, _ = timed(lambda: rc.GroupByAll32([val], ik16, u, [1], [1], [u + 1], 0))
+    line("C1 mean f64 by int16 iKey", n, ms, 10)
+    del k32, ik16
+
+    # C5: 100M uniques (scaled with n), cumsum / pack / first / last
+    u5 = max(n // 10, 1)
+    k = keys(u5)
+    ms, (ik, ifk, u) = timed(lambda: rc.MultiKeyGroupBy32([k], 0, None, 2))
+    line("C5 hash int64 key, N/10 uniques", n, ms, 12, uniques=u)
+    del k
+    ms, (cnt, ig, ifg) = timed(lambda: rc.BinCount(ik, u + 1, pack=True))
+    line("C5 pack (BinCount pack=True)", n, ms, 8)
+    ms, _ = timed(lambda: rc.GroupByAllPack32([val], ik, ig, ifg, cnt, u, [100], [1], [u + 1], 0))
+    line("C5 first", n, ms, (4 + 8) * u / n)
+    ms, _ = timed(lambda: rc.EmaAll32([val], ik, u, 300, (0.0, None, None, None)))
+    line("C5 cumsum f64", n, ms, 20)
+    ms, _ = timed(lambda: rc.GroupByAll32([val], ik, u, [0], [1], [u + 1], 0))
+    line("C5 sum f64 (global atomics, N/10 bins)", n, ms, 12)
+    del ig, ifg, cnt, ik
+
+    # C4: lexsort on (int64 1e3 values, f64 with NaN, int32 1e6 values), int64 primary; then GroupFromLexSort
+    a = torch.randint(0, 1000, (n,), device="cuda", generator=g, dtype=torch.int64)
+    f = val
+    c = torch.randint(0, 1_000_000, (n,), device="cuda", generator=g, dtype=torch.int32)
+    ms, perm = timed(lambda: rc.LexSort32([c, f, a]), reps=2)
+    line("C4 lexsort 3 keys (int32, f64, int64)", n, ms, 24)
+    ms, _ = timed(lambda: rc.GroupFromLexSort(perm, [a, f, c], base_index=1), reps=2)
+    line("C4 GroupFromLexSort", n, ms, 28)
+    ms, _ = timed(lambda: rc.LexSort32([c]), reps=2)
+    line("lexsort 1 key int32 (1e6 values)", n, ms, 8)
+
+
+if __name__ == "__main__":
+    main()

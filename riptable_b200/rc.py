@@ -293,7 +293,7 @@ class GroupByStream:
     def ifirstkey(self) -> torch.Tensor:
         return self.ifirst.torch()[: self.unique_count]
 
-    def push(self, keys, filter=None, row_offset: int = 0, out: torch.Tensor | None = None) -> torch.Tensor:
+    def push(self, keys, filter=None, row_offset: int = 0, out=None):
         k = _to_dev(keys)
         if k.n > self.max_chunk_rows:
             raise ValueError(f"chunk of {k.n} rows exceeds max_chunk_rows={self.max_chunk_rows}")

@@ -144,6 +144,32 @@ class CudaOps:
         t = col.torch()
         return (~_invalid_mask(t)).to(torch.int8)
 
+    def ifirst(self, ikey, nuniq, mode):
+        return self.rc.MakeiFirst(ikey, nuniq, None, mode)
+
+    def pack(self, ikey, nbins):
+        return self.rc.BinCount(ikey, nbins, pack=True)  # (nCountGroup, iGroup, iFirstGroup)
+
+    def cumsum(self, val, ikey, nuniq, filter):
+        return self.rc.EmaAll32([val], ikey, nuniq, int(GB.GB_CUMSUM), (0.0, None, filter, None))[0]
+
+    def combine_filter(self, ikey, filter):
+        return self.rc.CombineFilter(ikey, filter)
+
+    def as_f64(self, col):
+        return col.torch().to(torch.float64)
+
+    def is_f32(self, col):
+        return col.dtype == np.dtype(np.float32)
+
+    def invalid_item_bytes(self, col):
+        """The dtype's invalid as raw bytes (riptable/rt_enum.py:88-143): NaN, integer sentinel, b'' / ''."""
+        from .enums import invalid_for
+        dt = col.dtype
+        if dt.kind in "SUV":
+            return torch.zeros(dt.itemsize, dtype=torch.uint8, device=self.device)
+        return torch.from_numpy(np.array([invalid_for(dt)], dtype=dt).view(np.uint8).copy()).to(self.device)
+
     def tensor(self, x, dtype=None):
         return torch.as_tensor(x, dtype=dtype, device=self.device)
 
@@ -539,6 +565,83 @@ class _Tick:
             torch.cuda.synchronize()
             parts = [f"{self.names[i]} {self.ev[i - 1].elapsed_time(self.ev[i]):.2f}" for i in range(1, len(self.ev))]
             print("[rtb dist] ms: " + ", ".join(parts), flush=True)
+
+
+def sharded_pick(ops, values, grouping: ShardedGrouping, func, nth=0, group=None):
+    """GroupByAllPack32 first / nth / last over the sharded rows (riptable/rt_grouping.py:3442-3454): the replicated
+    [U+1] result, invalid (NaN / sentinel / empty string) where a bin has no such row.  A bin's rows are ordered by
+    global row = rank order, then local order."""
+    func = int(func)
+    G, rank = _world(group)
+    U = grouping.unique_count
+    nb = U + 1
+    ik = grouping.ikey
+    val = ops.as_col(values)
+    dt = ops.col_dtype(val)
+    isz = dt.itemsize
+    if func in (GB.GB_FIRST, GB.GB_LAST):
+        rows = ops.to_torch(ops.ifirst(ik, U, 0 if func == GB.GB_FIRST else 1)).to(torch.int64)  # [U+1], < 0 = none
+    elif func == GB.GB_NTH:
+        cnt, ig, ifg = (ops.to_torch(x) for x in ops.pack(ik, nb))
+        cnts = cnt.new_empty(G * nb)
+        tdist.all_gather_into_tensor(cnts, cnt.contiguous(), group=group)
+        cnts = cnts.view(G, nb).to(torch.int64)
+        before = cnts[:rank].sum(dim=0)
+        total = cnts.sum(dim=0)
+        want = torch.full_like(total, int(nth)) if nth >= 0 else total + int(nth)
+        local = want - before  # index inside this rank's rows of the bin
+        mine = (want >= 0) & (want < total) & (local >= 0) & (local < cnt.to(torch.int64))
+        pos = (ifg.to(torch.int64) + local).clamp(0, max(int(ig.numel()) - 1, 0))
+        rows = torch.where(mine, ig.to(torch.int64)[pos] if ig.numel() else torch.zeros_like(pos), torch.full_like(pos, -1))
+    else:
+        raise NotImplementedError(f"sharded_pick: function {func}")
+    rows[0] = -1
+    have = rows >= 0
+    if ops.nrows(val) == 0:
+        picked = ops.invalid_item_bytes(val).unsqueeze(0).expand(nb, isz).contiguous()  # an empty shard offers nothing
+    else:
+        picked = ops.col_bytes(ops.take_rows(val, rows.clamp(min=0))).view(nb, isz)
+    big = torch.iinfo(torch.int64).max
+    if func == GB.GB_LAST:
+        key = torch.where(have, rows + grouping.row_offset, torch.full_like(rows, -1))
+    else:
+        key = torch.where(have, rows + grouping.row_offset, torch.full_like(rows, big))
+    keys = key.new_empty(G * nb)
+    tdist.all_gather_into_tensor(keys, key.contiguous(), group=group)
+    vals = picked.new_empty(G * nb * isz)
+    tdist.all_gather_into_tensor(vals, picked.contiguous().view(-1), group=group)
+    keys, vals = keys.view(G, nb), vals.view(G, nb, isz)
+    win = keys.argmax(dim=0) if func == GB.GB_LAST else keys.argmin(dim=0)
+    best = keys.gather(0, win.unsqueeze(0)).squeeze(0)
+    found = (best >= 0) if func == GB.GB_LAST else (best < big)
+    out = vals.gather(0, win.view(1, nb, 1).expand(1, nb, isz)).squeeze(0)
+    out = torch.where(found.unsqueeze(1), out, ops.invalid_item_bytes(val).unsqueeze(0).expand(nb, isz))
+    return ops.col_from_bytes(out.contiguous().view(-1), dt, nb)
+
+
+def sharded_cumsum(ops, values, grouping: ShardedGrouping, filter=None, group=None):
+    """EmaAll32 GB_CUMSUM over the sharded rows (riptable/rt_grouping.py:3427-3430): every rank gets the running sums
+    of its own rows.  Local running sums + the per-bin totals of all earlier shards (an exclusive scan over ranks of
+    U-sized tables); op-filter rows carry the running value, bin-0 rows stay invalid."""
+    G, rank = _world(group)
+    U = grouping.unique_count
+    nb = U + 1
+    ik = grouping.ikey
+    val = ops.as_col(values)
+    f32 = ops.is_f32(val)
+    work = ops.as_f64(val) if f32 else val  # float32 accumulates in float64, rounded once at the end
+    local = ops.to_torch(ops.cumsum(work, ik, U, filter))
+    ikf = ops.to_torch(ops.combine_filter(ik, filter)) if filter is not None else ik
+    tot = ops.to_torch(ops.reduce(work, ikf, U, GB.GB_SUM)).to(local.dtype)
+    tot[0] = 0
+    tots = tot.new_empty(G * nb)
+    tdist.all_gather_into_tensor(tots, tot.contiguous(), group=group)
+    before = tots.view(G, nb)[:rank].sum(dim=0) if rank > 0 else torch.zeros_like(tot)
+    out = local + before[ik.to(torch.int64)]
+    if not local.dtype.is_floating_point:
+        inv = _invalid_value(local.dtype)
+        out = torch.where(ik == 0, torch.full_like(out, inv), out)
+    return out.to(torch.float32) if f32 else out
 
 
 def sharded_groupby_sum(key_cols, values, group=None, ops=None):

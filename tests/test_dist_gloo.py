@@ -13,6 +13,10 @@ import torch.multiprocessing as mp
 from oracle import riptide_oracle as orc
 
 
+def _np(x):
+    return x.numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+
+
 class OracleOps:
     """NumPy/oracle stand-in for CudaOps (same method set), CPU tensors for the collectives."""
 
@@ -23,7 +27,7 @@ class OracleOps:
         return len(col)
 
     def take_rows(self, col, idx):
-        return np.ascontiguousarray(col[idx.numpy()])
+        return np.ascontiguousarray(_np(col)[_np(idx)])
 
     def col_bytes(self, col):
         return torch.from_numpy(np.ascontiguousarray(col).view(np.uint8).reshape(-1).copy())
@@ -56,6 +60,30 @@ class OracleOps:
 
     def valid_mask_as_i8(self, col):
         return orc._is_valid_mask(np.asarray(col)).astype(np.int8)
+
+    def ifirst(self, ikey, nuniq, mode):
+        return orc.MakeiFirst(_np(ikey), nuniq, None, mode)
+
+    def pack(self, ikey, nbins):
+        return orc.BinCount(_np(ikey), nbins, pack=True)
+
+    def cumsum(self, val, ikey, nuniq, filter):
+        return orc.EmaAll32([_np(val)], _np(ikey), nuniq, 300, (0.0, None, None if filter is None else _np(filter), None))[0]
+
+    def combine_filter(self, ikey, filter):
+        return orc.CombineFilter(_np(ikey), _np(filter))
+
+    def as_f64(self, col):
+        return _np(col).astype(np.float64)
+
+    def is_f32(self, col):
+        return _np(col).dtype == np.float32
+
+    def invalid_item_bytes(self, col):
+        dt = _np(col).dtype
+        if dt.kind in "SUV":
+            return torch.zeros(dt.itemsize, dtype=torch.uint8)
+        return torch.from_numpy(np.array([orc.invalid_for(dt)], dtype=dt).view(np.uint8).copy())
 
     def tensor(self, x, dtype=None):
         return torch.as_tensor(x, dtype=dtype)
@@ -145,6 +173,12 @@ def _worker(rank, world, port, n, cuts, a2a, q):
             for fn in (0, 2, 3, 52, 53):
                 res[f"i{fn}"] = rd.sharded_reduce(ops, vi[lo:hi], g, fn, alltoall_min_bins=a2a).numpy().copy()
             res["count"] = rd.sharded_count(ops, g, alltoall_min_bins=a2a).numpy().copy()
+            for fn, p in ((100, 0), (102, 0), (101, 0), (101, 3), (101, -1), (101, -4), (101, 10_000)):
+                res[f"pick{fn}_{p}"] = np.asarray(rd.sharded_pick(ops, v[lo:hi], g, fn, p)).copy()
+                res[f"picks{fn}_{p}"] = np.asarray(rd.sharded_pick(ops, k2[lo:hi], g, fn, p)).copy()
+            res["cumsum_v"] = _np(rd.sharded_cumsum(ops, np.nan_to_num(v[lo:hi]), g)).copy()
+            res["cumsum_vi"] = _np(rd.sharded_cumsum(ops, vi[lo:hi], g, f[lo:hi])).copy()
+            res["cumsum_f32"] = _np(rd.sharded_cumsum(ops, np.nan_to_num(v[lo:hi]).astype(np.float32), g, f[lo:hi])).copy()
             out[name] = res
         q.put((rank, out))
     finally:
@@ -191,3 +225,19 @@ def test_sharded_groupby_and_reduce_world2(cuts, a2a):
             for fn in (0, 2, 3, 52, 53):
                 exp = orc.GroupByAll32([vi], eik, eu, [fn], [0], [eu + 2], 0)[0]
                 np.testing.assert_array_equal(got[r][name][f"i{fn}"], exp, err_msg=f"{name} int func {fn}")
+            cnt, ig, ifg = orc.BinCount(eik, eu + 1, pack=True)
+            for fn, p in ((100, 0), (102, 0), (101, 0), (101, 3), (101, -1), (101, -4), (101, 10_000)):
+                exp = orc.GroupByAllPack32([v], eik, ig, ifg, cnt, eu, [fn], [1], [eu + 1], p)[0]
+                np.testing.assert_array_equal(got[r][name][f"pick{fn}_{p}"][1:].view(np.uint64), exp[1:].view(np.uint64),
+                                              err_msg=f"{name} pick {fn} {p}")
+                exp = orc.GroupByAllPack32([k2], eik, ig, ifg, cnt, eu, [fn], [1], [eu + 1], p)[0]
+                np.testing.assert_array_equal(got[r][name][f"picks{fn}_{p}"][1:], exp[1:], err_msg=f"{name} pick S {fn} {p}")
+        lo_, hi_ = cuts[0], cuts[2]
+        full = lambda key: np.concatenate([got[r][name][key] for r in range(2)])  # noqa: E731
+        exp = orc.EmaAll32([np.nan_to_num(v)], eik, eu, 300, (0.0, None, None, None))[0]
+        np.testing.assert_allclose(full("cumsum_v"), exp, rtol=1e-12, atol=1e-9, equal_nan=True)
+        exp = orc.EmaAll32([vi], eik, eu, 300, (0.0, None, f, None))[0]
+        np.testing.assert_array_equal(full("cumsum_vi"), exp)
+        exp = orc.EmaAll32([np.nan_to_num(v).astype(np.float32)], eik, eu, 300, (0.0, None, f, None))[0]
+        assert full("cumsum_f32").dtype == np.float32
+        np.testing.assert_allclose(full("cumsum_f32"), exp, rtol=2e-5, atol=1e-2, equal_nan=True)

@@ -58,5 +58,19 @@ def test_sharded_groupby_reduce_single_rank(group, a2a):
         for fn in (0, 2, 3):
             got = rd.sharded_reduce(ops, vit, g, fn, group, a2a).cpu().numpy()
             np.testing.assert_array_equal(got, orc.GroupByAll32([vi], eik, eu, [fn], [0], [eu + 2], 0)[0])
+    # first / nth / last and cumsum through the sharded entry points
+    g = rd.sharded_groupby(ops, [torch.from_numpy(k1).cuda()], None, group)
+    eik, eifk, eu = orc.MultiKeyGroupBy32([k1], 0, None, 2)
+    cnt, ig, ifg = orc.BinCount(eik, eu + 1, pack=True)
+    for fn, p in ((100, 0), (102, 0), (101, 2), (101, -1), (101, 100_000)):
+        got = rd.sharded_pick(ops, torch.from_numpy(v).cuda(), g, fn, p, group).numpy()
+        exp = orc.GroupByAllPack32([v], eik, ig, ifg, cnt, eu, [fn], [1], [eu + 1], p)[0]
+        np.testing.assert_array_equal(got[1:].view(np.uint64), exp[1:].view(np.uint64))
+        got = rd.sharded_pick(ops, k2, g, fn, p, group).numpy()
+        np.testing.assert_array_equal(got[1:], orc.GroupByAllPack32([k2], eik, ig, ifg, cnt, eu, [fn], [1], [eu + 1], p)[0][1:])
+    got = rd.sharded_cumsum(ops, vit, g, torch.from_numpy(f).cuda(), group).cpu().numpy()
+    np.testing.assert_array_equal(got, orc.EmaAll32([vi], eik, eu, 300, (0.0, None, f, None))[0])
+    got = rd.sharded_cumsum(ops, torch.from_numpy(np.nan_to_num(v)).cuda(), g, None, group).cpu().numpy()
+    np.testing.assert_allclose(got, orc.EmaAll32([np.nan_to_num(v)], eik, eu, 300, (0.0, None, None, None))[0], rtol=1e-12, atol=1e-9)
     ik, ifk, u, s = rd.sharded_groupby_sum([torch.from_numpy(k1).cuda()], torch.from_numpy(v).cuda(), group, ops)
     assert u == len(np.unique(k1)) and s.shape[0] == u + 1

@@ -26,6 +26,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "keycols.cuh"
 
@@ -295,6 +297,92 @@ __global__ void __launch_bounds__(256) gb_round_direct(const void* __restrict__ 
     }
   }
   // the warp whose next tile is the partial one finishes the rows that are left
+  if (tb < hi) {
+    for (int64_t q = tb + lane; q < hi; q += 32) {
+      int32_t o = 0;
+      if (!filter || filter[q]) {
+        unsigned long long kk = load_key1<ISZ>(keys, q);
+        o = resolve_direct(table, mask, kk, 2 * (hash_u64(kk) & bmask), (uint32_t)q, newlist, ctr, new_limit);
+      }
+      ikey[q] = o;
+    }
+  }
+}
+
+// ---- direct path, low cardinality: the whole table in shared memory ---------------------------------------
+// When the table has at most kSmemCapMax slots every CTA copies the finalised entries into shared memory once and
+// probes there (shared memory serves several divergent lookups per clock; a global probe costs one L1TEX
+// wavefront per lane), so the round is bound by the key / iKey streams alone.  Entries that are not final in the
+// snapshot (none in steady state) and keys missing from it fall through to the general global-memory path.
+constexpr uint32_t kSmemCapMax = 16384;
+
+template <int ISZ>
+__global__ void __launch_bounds__(1024, 1) gb_round_smem(const void* __restrict__ keys, const uint8_t* __restrict__ filter,
+                                                         int32_t* __restrict__ ikey, Slot* table, uint32_t mask,
+                                                         int64_t lo, int64_t hi, uint32_t* newlist, GbCounters* ctr,
+                                                         uint32_t new_limit) {
+  typedef typename std::conditional<ISZ == 8, unsigned long long, uint32_t>::type KT;
+  extern __shared__ __align__(16) unsigned char gb_smem[];
+  const uint32_t cap = mask + 1;
+  KT* skey = (KT*)gb_smem;
+  uint32_t* sbin = (uint32_t*)(skey + cap);
+  for (uint32_t i = threadIdx.x; i < cap; i += blockDim.x) {
+    Slot e = table[i];
+    skey[i] = (KT)e.key;
+    sbin[i] = e.bin();  // 0 = empty or not final: a miss
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const uint32_t bmask = mask >> 1;
+  const int64_t step = nwarps * 128;
+  int64_t tb = lo + gw * 128;
+  unsigned long long k[4], kn[4] = {0, 0, 0, 0};
+  if (tb + 128 <= hi) load_tile_keys<ISZ>(keys, tb, lane, k);
+  for (; tb + 128 <= hi; tb += step) {
+    if (tb + step + 128 <= hi) load_tile_keys<ISZ>(keys, tb + step, lane, kn);
+    uint32_t fbits = 0xF;
+    if (filter) {
+      if (ISZ == 8) {
+        uint32_t fa = *(const uint16_t*)(filter + tb + 2 * lane), fb = *(const uint16_t*)(filter + tb + 64 + 2 * lane);
+        fbits = ((fa & 0xff) ? 1u : 0u) | ((fa >> 8) ? 2u : 0u) | ((fb & 0xff) ? 4u : 0u) | ((fb >> 8) ? 8u : 0u);
+      } else {
+        uint32_t f = ld_stream_u32(filter + tb + 4 * lane);
+        fbits = ((f & 0xff) ? 1u : 0u) | ((f & 0xff00) ? 2u : 0u) | ((f & 0xff0000) ? 4u : 0u) | ((f >> 24) ? 8u : 0u);
+      }
+    }
+    int32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      o[i] = 0;
+      if ((fbits >> i) & 1u) {
+        const uint32_t home = (hash_u64(k[i]) & bmask) * 2;
+        uint32_t idx = home, found = 0;
+        if (!(ISZ == 8 && k[i] == kEmpty)) {
+          for (;;) {
+            uint32_t b = sbin[idx];
+            if (b == 0) break;
+            if (skey[idx] == (KT)k[i]) {
+              found = b;
+              break;
+            }
+            idx = (idx + 1) & mask;
+          }
+        }
+        o[i] = found ? (int32_t)found
+                     : resolve_direct(table, mask, k[i], home, (uint32_t)(tb + tile_row<ISZ>(lane, i)), newlist, ctr, new_limit);
+      }
+    }
+    if (ISZ == 8) {
+      *(int2*)(ikey + tb + 2 * lane) = make_int2(o[0], o[1]);
+      *(int2*)(ikey + tb + 64 + 2 * lane) = make_int2(o[2], o[3]);
+    } else {
+      st_stream_u4(ikey + tb + 4 * lane, make_uint4((uint32_t)o[0], (uint32_t)o[1], (uint32_t)o[2], (uint32_t)o[3]));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) k[i] = kn[i];
+  }
   if (tb < hi) {
     for (int64_t q = tb + lane; q < hi; q += 32) {
       int32_t o = 0;
@@ -582,6 +670,7 @@ static uint32_t next_pow2_u64(uint64_t v) {
 }
 
 struct GbPlan {
+  int smem_table;
   int prefetch;
   double discovery_frac;  // a round whose predecessor found more new keys than this share of its rows is a discovery round
   int ctas_per_sm;
@@ -592,7 +681,8 @@ struct GbPlan {
 };
 
 static GbPlan get_plan() {
-  GbPlan p{1, 0.002, 4, 1 << 20, 0.25, 0.75, 4};
+  GbPlan p{1, 1, 0.002, 4, 1 << 20, 0.25, 0.75, 4};
+  if (const char* e = getenv("RTB_GB_SMEM")) p.smem_table = atoi(e);
   if (const char* e = getenv("RTB_GB_PREFETCH")) p.prefetch = atoi(e);
   if (const char* e = getenv("RTB_GB_CTAS")) p.ctas_per_sm = atoi(e);
   if (const char* e = getenv("RTB_GB_ROUND0")) p.round0 = atoll(e);
@@ -758,6 +848,31 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
             case 2: gb_round_insert<2><<<g2, 256, 0, stream>>>(keys[0].data, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit); break;
             default: gb_round_insert<1><<<g2, 256, 0, stream>>>(keys[0].data, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit);
           }
+        } else if (cap <= kSmemCapMax && plan.smem_table) {
+          // a full table in shared memory can loop: every slot final and none matching.  The table is at most 75 % full.
+          const int isz = keys[0].itemsize;
+          const size_t smem = (size_t)cap * ((isz == 8 ? 8 : 4) + 4);
+          int g3 = (int)((rows + 128 * 32 - 1) / (128 * 32));
+          if (g3 > kSMs) g3 = kSMs;
+          if (g3 < 1) g3 = 1;
+#define RTB_SMEM_ROUND(ISZ_)                                                                                              \
+  do {                                                                                                                    \
+    static bool attr = false;                                                                                             \
+    if (!attr) {                                                                                                          \
+      RTB_CUDA(cudaFuncSetAttribute(gb_round_smem<ISZ_>, cudaFuncAttributeMaxDynamicSharedMemorySize,                     \
+                                    (int)(kSmemCapMax * ((ISZ_ == 8 ? 8 : 4) + 4))));                                     \
+      attr = true;                                                                                                        \
+    }                                                                                                                     \
+    gb_round_smem<ISZ_><<<g3, 1024, smem, stream>>>(keys[0].data, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr,  \
+                                                   new_limit);                                                            \
+  } while (0)
+          switch (isz) {
+            case 8: RTB_SMEM_ROUND(8); break;
+            case 4: RTB_SMEM_ROUND(4); break;
+            case 2: RTB_SMEM_ROUND(2); break;
+            default: RTB_SMEM_ROUND(1);
+          }
+#undef RTB_SMEM_ROUND
         } else {
         int grid = grid_for(rows, 256, 4, plan.ctas_per_sm);
 #define RTB_ROUND(ISZ_, PF_) gb_round_direct<ISZ_, PF_><<<grid, 256, 0, stream>>>(keys[0].data, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit)

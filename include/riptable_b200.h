@@ -78,6 +78,9 @@ int rtb_profile_get(int id, double* ms, uint64_t* launches, uint64_t* units);
  *   max_unique    capacity the caller provisioned (sizes the table and ifirstkey_out)
  * On RTB_ERR_WORKSPACE, *needed_unique_host holds a max_unique to retry with. */
 size_t rtb_groupby_workspace_bytes(int64_t nrows, int64_t max_unique, int nkeys, int has_cutoffs);
+/* Same, given the summed itemsize of the key columns: adds room for the packed key rows that multi-key / string
+ * groupings of up to 64 bytes per row use.  With the smaller workspace above such keys take the generic kernel. */
+size_t rtb_groupby_workspace_bytes_rows(int64_t nrows, int64_t max_unique, int64_t row_bytes, int has_cutoffs);
 int rtb_multikey_groupby32(const rtb_column* keys, int nkeys, int64_t nrows, int64_t hint_size,
                            const uint8_t* filter, const int64_t* cutoffs_host, int64_t ncutoffs,
                            int32_t* ikey_out, int32_t* ifirstkey_out, int64_t max_unique,

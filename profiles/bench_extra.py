@@ -70,6 +70,26 @@ def main():
     line("C5 sum f64 (global atomics, N/10 bins)", n, ms, 12)
     del ig, ifg, cnt, ik
 
+    # C3: multikey (int64, S16, int32), N/10 distinct tuples, at half the rows (BASELINE: 500 M rows, 50 M uniques)
+    n3 = n // 2
+    k1 = torch.randint(0, 10_000, (n3,), device="cuda", generator=g, dtype=torch.int64) * 1_000_003
+    pool = np.frombuffer(np.random.default_rng(1).integers(65, 91, 1000 * 16, dtype=np.uint8).tobytes(), dtype="S16")
+    sidx = torch.randint(0, 1000, (n3,), device="cuda", generator=g, dtype=torch.int64)
+    s16 = rc.DevArray(torch.from_numpy(pool.view(np.uint8).reshape(1000, 16).copy()).cuda()[sidx].reshape(-1).contiguous(),
+                      np.dtype("S16"), n3)
+    del sidx
+    k3 = torch.randint(0, 5, (n3,), device="cuda", generator=g, dtype=torch.int32)
+    rc.MultiKeyGroupBy32([k1, s16, k3], 0, None, 2)  # lets the allocator settle on the large workspace
+    ms, (ik3, ifk3, u3) = timed(lambda: rc.MultiKeyGroupBy32([k1, s16, k3], 0, None, 2), reps=2)
+    print(json.dumps({"op": "C3 hash multikey (int64, S16, int32)", "rows": n3, "ms": round(ms, 3), "rows_per_s": n3 / ms * 1e3,
+                      "alg_bytes_per_row": 32, "alg_GBps": n3 * 32 / ms / 1e6, "uniques": u3}), flush=True)
+    v3 = val[:n3]
+    ms, _ = timed(lambda: rc.GroupByAll32([v3], ik3, u3, [51], [1], [u3 + 1], 0))
+    print(json.dumps({"op": "C3 nanmean f64", "rows": n3, "ms": round(ms, 3), "rows_per_s": n3 / ms * 1e3}), flush=True)
+    ms, _ = timed(lambda: rc.GroupByAll32([v3], ik3, u3, [55], [1], [u3 + 1], 0))
+    print(json.dumps({"op": "C3 nanstd f64 (two passes)", "rows": n3, "ms": round(ms, 3), "rows_per_s": n3 / ms * 1e3}), flush=True)
+    del k1, s16, k3, ik3, ifk3
+
     # C4: lexsort on (int64 1e3 values, f64 with NaN, int32 1e6 values), int64 primary; then GroupFromLexSort
     a = torch.randint(0, 1000, (n,), device="cuda", generator=g, dtype=torch.int64)
     f = val

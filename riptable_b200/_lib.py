@@ -40,6 +40,7 @@ PROTOTYPES = {
     "rtb_profile_reset": (None, []),
     "rtb_profile_get": (C.c_int, [_i32, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "rtb_groupby_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
+    "rtb_groupby_workspace_bytes_rows": (_sz, [_i64, _i64, _i64, _i32]),
     "rtb_multikey_groupby32": (
         C.c_int,
         [C.POINTER(rtb_column), _i32, _i64, _i64, _vp, _pi64, _i64, _vp, _vp, _i64, _pi64, _pi64, _pi64, _vp, _sz, _vp],

@@ -85,6 +85,37 @@ __device__ __forceinline__ bool rows_equal(const KeyCols& kc, int64_t r1, int64_
 }
 
 
+// 0 iff the two key rows are bytewise equal.  No early exit: every load is issued before any result is needed, so
+// the gathers of one comparison (and of neighbouring comparisons) overlap.
+__device__ __forceinline__ unsigned long long rows_diff(const KeyCols& kc, int64_t r1, int64_t r2) {
+  unsigned long long acc = 0;
+  for (int c = 0; c < kc.ncols; c++) {
+    int sz = kc.itemsize[c];
+    const uint8_t* p = kc.ptr[c] + r1 * (int64_t)sz;
+    const uint8_t* q = kc.ptr[c] + r2 * (int64_t)sz;
+    switch (kc.chunk[c]) {
+      case 16:
+        for (int o = 0; o < sz; o += 16) {
+          uint4 a = *(const uint4*)(p + o), b = *(const uint4*)(q + o);
+          acc |= (unsigned long long)((a.x ^ b.x) | (a.y ^ b.y) | (a.z ^ b.z) | (a.w ^ b.w));
+        }
+        break;
+      case 8:
+        for (int o = 0; o < sz; o += 8) acc |= *(const unsigned long long*)(p + o) ^ *(const unsigned long long*)(q + o);
+        break;
+      case 4:
+        for (int o = 0; o < sz; o += 4) acc |= (unsigned long long)(*(const uint32_t*)(p + o) ^ *(const uint32_t*)(q + o));
+        break;
+      case 2:
+        for (int o = 0; o < sz; o += 2) acc |= (unsigned long long)(*(const uint16_t*)(p + o) ^ *(const uint16_t*)(q + o));
+        break;
+      default:
+        for (int o = 0; o < sz; o++) acc |= (unsigned long long)(p[o] ^ q[o]);
+    }
+  }
+  return acc;
+}
+
 inline int chunk_for(const void* base, int itemsize) {
   for (int c = 16; c > 1; c >>= 1)
     if (itemsize % c == 0 && ((uintptr_t)base % c) == 0) return c;

@@ -212,14 +212,18 @@ def MultiKeyGroupBy32(list_arrays, hint_size=0, filter=None, hash_mode=2, cutoff
         e = DevArray.empty(0, np.int32)
         return _from_dev(e, device_mode), _from_dev(e, device_mode), 0
 
-    max_unique = min(n, max(int(hint_size), 1024)) if hint_size and hint_size > 0 else min(n, max(1 << 20, n // 16))
+    # room for n/2 uniques up front: the workspace is only touched as far as the table really grows, and running
+    # out of room means starting over with a larger one
+    max_unique = min(n, max(int(hint_size), 1024)) if hint_size and hint_size > 0 else min(n, max(1 << 20, n // 2))
     carr = _cols(cols)
     ikey = DevArray.empty(n, np.int32, dev)
     ucount, needed = C.c_int64(0), C.c_int64(0)
     ucut = np.zeros(len(cut), dtype=np.int64) if cut is not None else None
     while True:
         ifirst = DevArray.empty(max_unique, np.int32, dev)
-        ws = _ws(lib.rtb_groupby_workspace_bytes(n, max_unique, len(cols), int(cut is not None)))
+        direct = len(cols) == 1 and cols[0].dtype.kind in "biuf" and cut is None
+        row_bytes = 0 if direct else sum(c.dtype.itemsize for c in cols)
+        ws = _ws(lib.rtb_groupby_workspace_bytes_rows(n, max_unique, row_bytes, int(cut is not None)))
         rc_ = lib.rtb_multikey_groupby32(
             carr, len(cols), n, int(hint_size or 0),
             C.c_void_p(fdev.ptr) if fdev is not None else None,

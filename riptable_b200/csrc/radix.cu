@@ -74,45 +74,107 @@ __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* wa
   return base + inc - v;
 }
 
+// ---- TMA / mbarrier helpers (bulk 1-D copies global -> shared, completion counted in bytes on an mbarrier) -------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 template <typename K>
 constexpr size_t radix_scatter_smem() {
-  return (size_t)kRadixTile * (sizeof(K) + 4) + (8 * 256 + 3 * 256 + 8) * 4;
+  return (size_t)2 * kRadixTile * (sizeof(K) + 4) + (8 * 256 + 3 * 256 + 8) * 4 + 2 * 8 + 16;
 }
 
+// One CTA walks the tiles of its chunk.  Tiles are double-buffered in shared memory: while tile t is ranked and
+// written out, the bulk copy (TMA, `cp.async.bulk` completing on an mbarrier) of tile t+1 is in flight, so the HBM
+// latency of the tile loads — what the register-staged version of this kernel spent most of its time waiting on —
+// is hidden.  The buffer a tile arrived in doubles as its digit-ordered staging area before the global stores.
 template <typename K, bool IOTA>
 __global__ void __launch_bounds__(kRadixThreads, 2)
 radix_scatter(const K* __restrict__ kin, const uint32_t* __restrict__ vin, K* __restrict__ kout,
               uint32_t* __restrict__ vout, int64_t n, int shift, int64_t chunk_rows, int nchunks,
               const uint32_t* __restrict__ offsets) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  K* skeys = (K*)smem;
-  uint32_t* svals = (uint32_t*)(skeys + kRadixTile);
-  uint32_t* wcnt = svals + kRadixTile;  // [8 warps][256 digits]: running count, then exclusive warp offset
-  uint32_t* dbase = wcnt + 8 * 256;     // first tile position of each digit
-  uint32_t* goff = dbase + 256;         // next global output position of each digit for this chunk
-  uint32_t* tcnt = goff + 256;          // rows of this tile per digit
-  uint32_t* wsum = tcnt + 256;          // 8
+  extern __shared__ __align__(128) unsigned char smem[];
+  K* kbuf = (K*)smem;                                   // [2][tile]
+  uint32_t* vbuf = (uint32_t*)(kbuf + 2 * kRadixTile);  // [2][tile]
+  uint32_t* wcnt = vbuf + 2 * kRadixTile;               // [8 warps][256 digits]: running count, then exclusive warp offset
+  uint32_t* dbase = wcnt + 8 * 256;                     // first tile position of each digit
+  uint32_t* goff = dbase + 256;                         // next global output position of each digit for this chunk
+  uint32_t* tcnt = goff + 256;                          // rows of this tile per digit
+  uint32_t* wsum = tcnt + 256;                          // 8
+  unsigned long long* bar = (unsigned long long*)(wsum + 8 + 2);  // 2 mbarriers (8-byte aligned)
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int64_t lo = (int64_t)blockIdx.x * chunk_rows;
   const int64_t hi = lo + chunk_rows < n ? lo + chunk_rows : n;
+  const int ntiles = (int)((hi - lo + kRadixTile - 1) / kRadixTile);
   goff[tid] = offsets[(size_t)tid * nchunks + blockIdx.x];
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int t) {  // called by thread 0: start the bulk copy of a FULL tile t into buffer t & 1
+    const int64_t tlo = lo + (int64_t)t * kRadixTile;
+    if (t < ntiles && tlo + kRadixTile <= hi) {
+      const int b = t & 1;
+      mbar_expect_tx(&bar[b], (uint32_t)(kRadixTile * (sizeof(K) + (IOTA ? 0 : 4))));
+      bulk_g2s(kbuf + b * kRadixTile, kin + tlo, (uint32_t)(kRadixTile * sizeof(K)), &bar[b]);
+      if (!IOTA) bulk_g2s(vbuf + b * kRadixTile, vin + tlo, (uint32_t)(kRadixTile * 4), &bar[b]);
+    }
+  };
+  if (tid == 0) {
+    issue(0);
+    issue(1);
+  }
 
-  for (int64_t tile_lo = lo; tile_lo < hi; tile_lo += kRadixTile) {
+  for (int t = 0; t < ntiles; t++) {
+    const int64_t tile_lo = lo + (int64_t)t * kRadixTile;
+    const int b = t & 1;
+    K* skeys = kbuf + b * kRadixTile;
+    uint32_t* svals = vbuf + b * kRadixTile;
+    const bool full = tile_lo + kRadixTile <= hi;
 #pragma unroll
     for (int j = 0; j < 8; j++) wcnt[j * 256 + tid] = 0;
-    __syncthreads();
 
     K key[kRadixItems];
     uint32_t val[kRadixItems];
     uint32_t rank[kRadixItems];
-    const int64_t wbase = tile_lo + (int64_t)w * 32 * kRadixItems + lane;
+    const int wofs = w * 32 * kRadixItems + lane;
+    const int64_t wbase = tile_lo + wofs;
+    if (full) {
+      mbar_wait(&bar[b], (uint32_t)((t >> 1) & 1));
 #pragma unroll
-    for (int i = 0; i < kRadixItems; i++) {
-      int64_t idx = wbase + i * 32;
-      bool valid = idx < hi;
-      key[i] = valid ? kin[idx] : (K)0;
-      val[i] = IOTA ? (uint32_t)idx : (valid ? vin[idx] : 0u);
+      for (int i = 0; i < kRadixItems; i++) {
+        key[i] = skeys[wofs + i * 32];
+        val[i] = IOTA ? (uint32_t)(wbase + i * 32) : svals[wofs + i * 32];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kRadixItems; i++) {
+        int64_t idx = wbase + i * 32;
+        bool valid = idx < hi;
+        key[i] = valid ? kin[idx] : (K)0;
+        val[i] = IOTA ? (uint32_t)idx : (valid ? vin[idx] : 0u);
+      }
     }
+    __syncthreads();  // every thread holds its rows: the buffer is free to stage the output; wcnt is zeroed
     // stable rank inside the warp's 512 rows: rows are visited in memory order (i major, lane minor)
 #pragma unroll
     for (int i = 0; i < kRadixItems; i++) {
@@ -160,8 +222,10 @@ radix_scatter(const K* __restrict__ kin, const uint32_t* __restrict__ vin, K* __
       if (kout) kout[g] = k;
       vout[g] = svals[p];
     }
+    fence_proxy_async();  // this thread's generic accesses to the buffer precede the next bulk copy into it
     __syncthreads();
     goff[tid] += tcnt[tid];
+    if (tid == 0) issue(t + 2);
   }
 }
 

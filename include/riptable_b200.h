@@ -171,6 +171,13 @@ int rtb_lexsort32(const rtb_column* keys, int nkeys, int64_t nrows, const int32_
                   const int8_t* ascending_host, int32_t* perm_out, void* workspace, size_t workspace_bytes,
                   void* stream);
 
+/* ---- multi-GPU sample sort: dest_out[r] = number of the `nsplit` splitter rows that sort at or before
+ * row r under LexSort32's order (last key primary, NaN last, per-key ascending flags) with the global row id
+ * (row_offset + r vs splitter_rows[j], a device array) as the final tie-break. */
+int rtb_lex_partition(const rtb_column* keys, int nkeys, int64_t nrows, const int8_t* ascending_host,
+                      const rtb_column* splitters, int nsplit, const int64_t* splitter_rows, int64_t row_offset,
+                      int32_t* dest_out, void* stream);
+
 /* ---- a12: rc.GroupFromLexSort(iGroup, value_array, cutoffs=, base_index=) — riptable/rt_numpy.py:2207
  *   ikey_out int32[nrows] (rows not in igroup get 0), ifirstkey_out int32[nindex] (first U valid),
  *   ncountgroup_out int32[nindex+1] (first U+1 valid, slot 0 = 0). */

@@ -77,6 +77,52 @@ __global__ void __launch_bounds__(256) sort_gather_kernel(SortCol c, const uint3
     codes[i] = (K)sort_code(c, rows ? (int64_t)rows[i] : i);
 }
 
+// ---- sample-sort partition: destination rank of every row given G-1 splitters ------------------------------------
+constexpr int kMaxSortCols = 16;
+struct LexPartArgs {
+  SortCol cols[kMaxSortCols];   // local key columns, list order (first = least significant)
+  SortCol split[kMaxSortCols];  // the splitter rows: same dtypes, nsplit rows each
+  int ncols, nsplit;
+  const long long* split_row;   // global row id of each splitter (the final tie-break)
+  long long row_offset, n;
+  int32_t* dest;
+};
+
+__device__ __forceinline__ int sort_pieces(const SortCol& c) {
+  if (c.dtype == RTB_BYTES) return (c.itemsize + 7) / 8;
+  if (c.dtype == RTB_UCS4) return (c.itemsize / 4 + 1) / 2;
+  return 1;
+}
+__device__ __forceinline__ void set_piece(SortCol& c, int piece) {
+  c.chunk = piece;
+  c.nvalid = c.dtype == RTB_BYTES ? (c.itemsize - 8 * piece < 8 ? c.itemsize - 8 * piece : 8)
+             : c.dtype == RTB_UCS4 ? (c.itemsize / 4 - 2 * piece < 2 ? c.itemsize / 4 - 2 * piece : 2) : 1;
+}
+
+// dest[r] = number of splitters that sort at or before row r under (key tuple, global row)
+__global__ void __launch_bounds__(256) lex_partition_kernel(LexPartArgs a) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < a.n; r += stride) {
+    int dest = 0;
+    for (int j = 0; j < a.nsplit; j++) {
+      int cmp = 0;  // sign of (row - splitter)
+      for (int c = a.ncols - 1; c >= 0 && cmp == 0; c--) {
+        SortCol x = a.cols[c], y = a.split[c];
+        const int pieces = sort_pieces(x);
+        for (int p = 0; p < pieces && cmp == 0; p++) {
+          set_piece(x, p);
+          set_piece(y, p);
+          unsigned long long cx = sort_code(x, r), cy = sort_code(y, j);
+          cmp = cx < cy ? -1 : (cx > cy ? 1 : 0);
+        }
+      }
+      if (cmp == 0) cmp = (a.row_offset + r) < a.split_row[j] ? -1 : 1;
+      dest += cmp > 0;
+    }
+    a.dest[r] = dest;
+  }
+}
+
 struct LexLayout {
   unsigned long long *codes_a, *codes_b;
   uint32_t* vals_b;
@@ -231,6 +277,37 @@ extern "C" int rtb_debug_sort_codes(const rtb_column* col, int64_t n, int chunk,
   sc.nvalid = sc.dtype == RTB_BYTES ? (sc.itemsize - 8 * chunk < 8 ? sc.itemsize - 8 * chunk : 8)
               : sc.dtype == RTB_UCS4 ? (sc.itemsize / 4 - 2 * chunk < 2 ? sc.itemsize / 4 - 2 * chunk : 2) : 1;
   sort_gather_kernel<unsigned long long><<<grid_for(n, 256, 2), 256, 0, (cudaStream_t)stream>>>(sc, nullptr, n, out);
+  RTB_LAUNCH_CHECK();
+  return RTB_OK;
+}
+
+extern "C" int rtb_lex_partition(const rtb_column* keys, int nkeys, int64_t nrows, const int8_t* ascending_host,
+                                 const rtb_column* splitters, int nsplit, const int64_t* splitter_rows, int64_t row_offset,
+                                 int32_t* dest_out, void* stream) {
+  RTB_ARG(keys && nkeys >= 1 && nkeys <= kMaxSortCols, "lex partition: 1..%d key columns", kMaxSortCols);
+  RTB_ARG(nsplit >= 0 && nrows >= 0, "lex partition: bad sizes");
+  if (nrows == 0) return RTB_OK;
+  RTB_ARG(dest_out && (nsplit == 0 || (splitters && splitter_rows)), "lex partition: null pointer");
+  LexPartArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int c = 0; c < nkeys; c++) {
+    RTB_ARG(keys[c].dtype >= RTB_BOOL && keys[c].dtype <= RTB_UCS4 && keys[c].data, "lex partition: bad key column %d", c);
+    RTB_ARG(nsplit == 0 || (splitters[c].dtype == keys[c].dtype && splitters[c].itemsize == keys[c].itemsize),
+            "lex partition: splitter column %d does not match the key column", c);
+    a.cols[c].data = (const uint8_t*)keys[c].data;
+    a.cols[c].dtype = keys[c].dtype;
+    a.cols[c].itemsize = keys[c].itemsize;
+    a.cols[c].descending = ascending_host && !ascending_host[c];
+    a.split[c] = a.cols[c];
+    a.split[c].data = nsplit ? (const uint8_t*)splitters[c].data : nullptr;
+  }
+  a.ncols = nkeys;
+  a.nsplit = nsplit;
+  a.split_row = (const long long*)splitter_rows;
+  a.row_offset = row_offset;
+  a.n = nrows;
+  a.dest = dest_out;
+  lex_partition_kernel<<<grid_for(nrows, 256, 1, 16), 256, 0, (cudaStream_t)stream>>>(a);
   RTB_LAUNCH_CHECK();
   return RTB_OK;
 }

@@ -159,6 +159,16 @@ class CudaOps:
     def as_f64(self, col):
         return col.torch().to(torch.float64)
 
+    def lexsort(self, cols, ascending=True):
+        return self.rc.LexSort32(list(cols), ascending=ascending)
+
+    def lex_partition(self, cols, splitters, splitter_rows, row_offset, ascending):
+        return self.rc.LexPartition(list(cols), list(splitters), splitter_rows, row_offset, ascending)
+
+    def rows_col(self, rows_i64):
+        """An int64 tensor of global row ids as a key column."""
+        return self.rc._to_dev(rows_i64.contiguous())
+
     def is_f32(self, col):
         return col.dtype == np.dtype(np.float32)
 
@@ -642,6 +652,87 @@ def sharded_cumsum(ops, values, grouping: ShardedGrouping, filter=None, group=No
         inv = _invalid_value(local.dtype)
         out = torch.where(ik == 0, torch.full_like(out, inv), out)
     return out.to(torch.float32) if f32 else out
+
+
+SAMPLES_PER_RANK = 256
+
+
+def _all_to_all_var(t: torch.Tensor, send_counts, recv_counts, group):
+    """all-to-all of a 1-D tensor with per-destination element counts."""
+    out = t.new_empty(int(sum(recv_counts)))
+    tdist.all_to_all_single(out, t.contiguous(), output_split_sizes=[int(x) for x in recv_counts],
+                            input_split_sizes=[int(x) for x in send_counts], group=group)
+    return out
+
+
+def sharded_lexsort(ops, key_cols, ascending=True, group=None):
+    """rt.lexsort over row-sharded keys by sample sort: returns this rank's slice of the globally sorted
+    permutation as int64 GLOBAL row ids — concatenated in rank order the slices equal np.lexsort of the concatenated
+    keys (stable: ties are broken by global row id).  Steps: sample the shards, all-gather the samples, every rank
+    picks the same G-1 splitters, rows are routed by `rtb_lex_partition`, bucketed (rc.BinCount pack), exchanged with
+    one all-to-all per column, and the received rows are sorted locally with the global row id as the last key."""
+    G, rank = _world(group)
+    cols = [ops.as_col(c) for c in key_cols]
+    n = ops.nrows(cols[0])
+    asc = [bool(ascending)] * len(cols) if isinstance(ascending, (bool, np.bool_)) else [bool(a) for a in ascending]
+    meta = ops.tensor([n], dtype=torch.int64)
+    alln = meta.new_empty(G)
+    tdist.all_gather_into_tensor(alln, meta, group=group)
+    ns = alln.cpu().tolist()
+    row_off = [0] * G
+    for r in range(1, G):
+        row_off[r] = row_off[r - 1] + ns[r - 1]
+    dev = meta.device
+    if G == 1:
+        return ops.to_torch(ops.lexsort(cols, asc)).to(torch.int64)
+
+    # 1. samples -> splitters (identical on every rank)
+    s_n = min(n, SAMPLES_PER_RANK)
+    sidx = (torch.arange(s_n, device=dev, dtype=torch.int64) * (n // s_n)) if s_n else torch.zeros(0, dtype=torch.int64, device=dev)
+    s_counts = [min(x, SAMPLES_PER_RANK) for x in ns]
+    total_s = sum(s_counts)
+    samples = []
+    for c in cols:
+        dt = ops.col_dtype(c)
+        part = ops.col_bytes(ops.take_rows(c, sidx)) if s_n else ops.tensor([0], dtype=torch.uint8).new_empty(0)
+        allb = _all_gather_var(part, [x * dt.itemsize for x in s_counts], group)
+        samples.append(ops.col_from_bytes(allb, dt, total_s))
+    s_rows = _all_gather_var(sidx + row_off[rank], s_counts, group)
+    sperm = ops.to_torch(ops.lexsort([ops.rows_col(s_rows)] + samples, [True] + asc)).to(torch.int64)
+    pick = sperm[[(k * total_s) // G for k in range(1, G)]] if total_s else sperm[:0]
+    nsplit = int(pick.numel())
+    splitters = [ops.take_rows(c, pick) for c in samples]
+    split_rows = s_rows[pick]
+
+    # 2. route and bucket the local rows
+    if n:
+        dest = ops.to_torch(ops.lex_partition(cols, splitters, split_rows, row_off[rank], asc)) if nsplit else \
+            torch.zeros(n, dtype=torch.int32, device=dev)
+        cnt, ig, _ = (ops.to_torch(x) for x in ops.pack(dest, G))
+        send_counts = cnt.to(torch.int64).cpu().tolist()
+        ig = ig.to(torch.int64)
+    else:
+        send_counts, ig = [0] * G, torch.zeros(0, dtype=torch.int64, device=dev)
+    sc = ops.tensor(send_counts, dtype=torch.int64)
+    rc_ = torch.empty_like(sc)
+    tdist.all_to_all_single(rc_, sc, group=group)
+    recv_counts = rc_.cpu().tolist()
+    m = int(sum(recv_counts))
+
+    # 3. exchange the key columns and the global row ids
+    recv_cols = []
+    for c in cols:
+        dt = ops.col_dtype(c)
+        payload = ops.col_bytes(ops.take_rows(c, ig)) if n else ops.tensor([0], dtype=torch.uint8).new_empty(0)
+        got = _all_to_all_var(payload, [x * dt.itemsize for x in send_counts], [x * dt.itemsize for x in recv_counts], group)
+        recv_cols.append(ops.col_from_bytes(got, dt, m))
+    recv_rows = _all_to_all_var(ig + row_off[rank], send_counts, recv_counts, group)
+
+    # 4. local sort of what arrived; the global row id is the least significant key
+    if m == 0:
+        return recv_rows
+    perm = ops.to_torch(ops.lexsort([ops.rows_col(recv_rows)] + recv_cols, [True] + asc)).to(torch.int64)
+    return recv_rows[perm]
 
 
 def sharded_groupby_sum(key_cols, values, group=None, ops=None):

@@ -539,6 +539,25 @@ def LexSort32(list_arrays, cutoffs=None, index=None, ascending=True):
     return _from_dev(out, device_mode)
 
 
+def LexPartition(list_arrays, splitter_arrays, splitter_rows, row_offset=0, ascending=True):
+    """Sample-sort helper (device mode): for every row, how many of the splitter rows sort at or before it under
+    LexSort32's order with the global row id as the final tie-break.  -> int32 CUDA tensor."""
+    cols = [_to_dev(a) for a in _as_list(list_arrays)]
+    spl = [_to_dev(a) for a in _as_list(splitter_arrays)]
+    n = cols[0].n
+    nsplit = spl[0].n if spl else 0
+    if isinstance(ascending, (bool, np.bool_)):
+        asc = np.full(len(cols), 1 if ascending else 0, dtype=np.int8)
+    else:
+        asc = np.asarray([1 if a else 0 for a in ascending], dtype=np.int8)
+    srows = torch.as_tensor(splitter_rows, dtype=torch.int64, device=_device()).contiguous()
+    out = torch.empty(max(n, 4), dtype=torch.int32, device=_device())
+    check(lib.rtb_lex_partition(_cols(cols), len(cols), n, asc.ctypes.data_as(C.POINTER(C.c_int8)),
+                                _cols(spl) if nsplit else None, nsplit, C.c_void_p(srows.data_ptr()) if nsplit else None,
+                                int(row_offset), C.c_void_p(out.data_ptr()), _stream()))
+    return out[:n]
+
+
 def LexSort64(list_arrays, cutoffs=None, index=None, ascending=True):
     # riptable only routes here above 2e9 rows (rt_numpy.py:2669-2671); below that the 32-bit result is identical
     return LexSort32(list_arrays, cutoffs=cutoffs, index=index, ascending=ascending)
@@ -588,7 +607,7 @@ def ReverseShuffle(perm):
     return _from_dev(out, device_mode)
 
 
-__all__ = ["GroupByStream", "MultiKeyGroupBy32", "CombineFilter", "CombineAccum1Filter", "CombineAccum2Filter", "GroupByAll32", "BinCount",
+__all__ = ["GroupByStream", "LexPartition", "MultiKeyGroupBy32", "CombineFilter", "CombineAccum1Filter", "CombineAccum2Filter", "GroupByAll32", "BinCount",
            "GroupFromBinCount", "GroupByPack32", "GroupByAllPack32", "EmaAll32", "MakeiFirst", "MakeiNext", "LexSort32",
            "LexSort64", "GroupFromLexSort", "ReverseShuffle", "LedgerFunction"]
 

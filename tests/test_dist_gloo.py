@@ -76,6 +76,33 @@ class OracleOps:
     def as_f64(self, col):
         return _np(col).astype(np.float64)
 
+    def lexsort(self, cols, ascending=True):
+        return orc.LexSort32([_np(c) for c in cols], ascending=ascending)
+
+    def lex_partition(self, cols, splitters, splitter_rows, row_offset, ascending):
+        # rank every row among the splitters with one lexsort of [rows ; splitters] (global row id = last tie-break)
+        cols = [_np(c) for c in cols]
+        spl = [_np(c) for c in splitters]
+        n, k = len(cols[0]), len(spl[0])
+        grow = np.concatenate([np.arange(n, dtype=np.int64) + row_offset, _np(splitter_rows).astype(np.int64)])
+        keys = [grow] + [np.concatenate([c, sc]) for c, sc in zip(cols, spl)]
+        perm = orc.LexSort32(keys, ascending=[True] + list(ascending))
+        is_split = perm >= n
+        before = np.cumsum(is_split) - is_split  # splitters strictly before each sorted position
+        dest = np.empty(n + k, np.int32)
+        dest[perm] = before
+        # a row equal to a splitter IS that splitter's row: it counts as "at or before"
+        out = dest[:n].copy()
+        srow = _np(splitter_rows).astype(np.int64)
+        for j in range(k):
+            loc = srow[j] - row_offset
+            if 0 <= loc < n:
+                out[loc] += 1
+        return out
+
+    def rows_col(self, rows_i64):
+        return _np(rows_i64).astype(np.int64)
+
     def is_f32(self, col):
         return _np(col).dtype == np.float32
 
@@ -183,6 +210,55 @@ def _worker(rank, world, port, n, cuts, a2a, q):
         q.put((rank, out))
     finally:
         tdist.destroy_process_group()
+
+
+def _sort_worker(rank, world, port, cuts, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    tdist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from riptable_b200 import dist as rd
+
+        rd.SAMPLES_PER_RANK = 32
+        a, f, s = _sort_data(cuts[-1])
+        lo, hi = cuts[rank], cuts[rank + 1]
+        ops = OracleOps()
+        out = {}
+        out["afs"] = _np(rd.sharded_lexsort(ops, [a[lo:hi], f[lo:hi], s[lo:hi]])).copy()
+        out["desc"] = _np(rd.sharded_lexsort(ops, [f[lo:hi], a[lo:hi]], ascending=[False, True])).copy()
+        out["one"] = _np(rd.sharded_lexsort(ops, [a[lo:hi]])).copy()
+        q.put((rank, out))
+    finally:
+        tdist.destroy_process_group()
+
+
+def _sort_data(n):
+    rng = np.random.default_rng(11)
+    a = rng.integers(-5, 5, n).astype(np.int16)
+    f = np.round(rng.random(n) * 6, 0)
+    f[rng.random(n) < 0.1] = np.nan
+    f[rng.random(n) < 0.1] = -0.0
+    s = rng.choice(np.array([b"", b"a", b"ab", b"zz"], dtype="S3"), n)
+    return a, f, s
+
+
+@pytest.mark.parametrize("cuts", [(0, 2500, 6001), (0, 0, 3001), (0, 5000, 5003)])
+def test_sharded_lexsort_world2(cuts):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sort_worker, args=(r, 2, port, cuts, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    a, f, s = _sort_data(cuts[-1])
+    np.testing.assert_array_equal(np.concatenate([got[0]["afs"], got[1]["afs"]]), np.lexsort([a, f, s]))
+    np.testing.assert_array_equal(np.concatenate([got[0]["desc"], got[1]["desc"]]),
+                                  orc.LexSort32([f, a], ascending=[False, True]))
+    np.testing.assert_array_equal(np.concatenate([got[0]["one"], got[1]["one"]]), np.lexsort([a]))
+    assert len(got[0]["afs"]) > 0 and len(got[1]["afs"]) > 0  # the splitter really splits the rows
 
 
 def _free_port():

@@ -333,3 +333,27 @@ def test_device_mode_pack_sort_chain(rc):
     np.testing.assert_array_equal(perm.cpu().numpy(), np.lexsort([v, k]))
     exp = orc.EmaAll32([v], ok, ou, 300, (0.0, None, None, None))[0]
     np.testing.assert_allclose(cs.cpu().numpy(), exp, rtol=1e-12, atol=1e-9)
+
+
+def test_lex_partition_matches_sorted_rank(rc):
+    """rtb_lex_partition (the routing step of the multi-GPU sample sort): destination = number of splitters at or
+    before the row under LexSort32's order with the global row id as the last tie-break."""
+    import torch
+
+    rng = np.random.default_rng(12)
+    n = 60_000
+    ks = _lex_keys(rng, n)
+    for combo, asc in ((["i16", "f64"], [True, True]), (["S7", "u8", "f32"], [True, False, True]), (["U5", "i64"], [False, True]),
+                       (["b", "S20"], [True, True])):
+        cols = [ks[c] for c in combo]
+        pick = np.sort(rng.choice(n, 7, replace=False))
+        row_offset = 1000
+        perm = orc.LexSort32([np.arange(n, dtype=np.int64)] + cols, ascending=[True] + asc)
+        order = np.empty(n, np.int64)
+        order[perm] = np.arange(n)
+        spos = np.sort(order[pick])  # sorted positions of the splitter rows
+        exp = np.searchsorted(spos, order, side="right").astype(np.int32)
+        srt = pick[np.argsort(order[pick])]
+        got = rc.LexPartition([torch.from_numpy(c).cuda() if c.dtype.kind not in "SU" else rc._to_dev(c) for c in cols],
+                              [c[srt] for c in cols], srt.astype(np.int64) + row_offset, row_offset, asc).cpu().numpy()
+        np.testing.assert_array_equal(got, exp, err_msg=str(combo))

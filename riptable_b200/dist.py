@@ -654,6 +654,56 @@ def sharded_cumsum(ops, values, grouping: ShardedGrouping, filter=None, group=No
     return out.to(torch.float32) if f32 else out
 
 
+def sharded_pack(ops, grouping: ShardedGrouping, group=None):
+    """groupbypack over sharded rows (riptable/rt_numpy.py:1945-1972): the packed layout distributed by bin owner.
+    Every rank gets the replicated global `nCountGroup` / `iFirstGroup` (int64: global positions), the bin range
+    [bin_lo, bin_hi) it owns (contiguous ranges balanced by row count) and `iGroup_owned` = the global row ids of
+    those bins in packed order (bin-major, global rows ascending inside a bin) — i.e. the slice
+    iGroup[iFirstGroup[bin_lo] : iFirstGroup[bin_hi]] of the single-GPU result."""
+    G, rank = _world(group)
+    U = grouping.unique_count
+    nb = U + 1
+    ik = grouping.ikey
+    cnt, ig, ifg = (ops.to_torch(x) for x in ops.pack(ik, nb))
+    cnts = cnt.new_empty(G * nb)
+    tdist.all_gather_into_tensor(cnts, cnt.contiguous(), group=group)
+    cnts = cnts.view(G, nb).to(torch.int64)
+    total = cnts.sum(dim=0)
+    csum = torch.cumsum(total, 0)
+    gifg = csum - total  # exclusive
+    nrows = int(csum[-1].item()) if nb else 0
+    # owners: rank o owns bins [edges[o], edges[o+1]) with about nrows / G rows each
+    targets = torch.tensor([(o * nrows) // G for o in range(1, G)], dtype=torch.int64, device=csum.device)
+    inner = torch.searchsorted(csum, targets, right=False) if G > 1 else targets[:0]
+    edges = [0] + [min(int(x), nb) for x in inner.cpu().tolist()] + [nb]
+    for o in range(1, G + 1):
+        edges[o] = max(edges[o], edges[o - 1])
+    ifg64 = ifg.to(torch.int64)
+    lstart = [int(ifg64[edges[o]].item()) if edges[o] < nb else int(ig.numel()) for o in range(G)] + [int(ig.numel())]
+    send_counts = [lstart[o + 1] - lstart[o] for o in range(G)]
+    sc = ops.tensor(send_counts, dtype=torch.int64)
+    rcv = torch.empty_like(sc)
+    tdist.all_to_all_single(rcv, sc, group=group)
+    recv_counts = rcv.cpu().tolist()
+    got = _all_to_all_var(ig.to(torch.int64) + grouping.row_offset, send_counts, recv_counts, group)
+    b0, b1 = edges[rank], edges[rank + 1]
+    owned = torch.empty(int(sum(recv_counts)), dtype=torch.int64, device=got.device)
+    base = gifg[b0:b1] - (gifg[b0] if b0 < nb else 0)
+    pos = 0
+    before = torch.zeros(b1 - b0, dtype=torch.int64, device=got.device)
+    for r in range(G):
+        c = cnts[r, b0:b1]
+        m = int(recv_counts[r])
+        if m:
+            start = base + before                       # where rank r's rows of each owned bin begin
+            excl = torch.cumsum(c, 0) - c
+            dest = torch.repeat_interleave(start - excl, c) + torch.arange(m, device=got.device)
+            owned[dest] = got[pos: pos + m]
+        before = before + c
+        pos += m
+    return {"nCountGroup": total, "iFirstGroup": gifg, "bin_lo": b0, "bin_hi": b1, "iGroup_owned": owned}
+
+
 SAMPLES_PER_RANK = 256
 
 

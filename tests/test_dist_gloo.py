@@ -203,6 +203,9 @@ def _worker(rank, world, port, n, cuts, a2a, q):
             for fn, p in ((100, 0), (102, 0), (101, 0), (101, 3), (101, -1), (101, -4), (101, 10_000)):
                 res[f"pick{fn}_{p}"] = np.asarray(rd.sharded_pick(ops, v[lo:hi], g, fn, p)).copy()
                 res[f"picks{fn}_{p}"] = np.asarray(rd.sharded_pick(ops, k2[lo:hi], g, fn, p)).copy()
+            if name in ("one", "filt"):
+                pk = rd.sharded_pack(ops, g)
+                res["pack"] = {k2_: (_np(v2_).copy() if hasattr(v2_, "shape") else v2_) for k2_, v2_ in pk.items()}
             res["cumsum_v"] = _np(rd.sharded_cumsum(ops, np.nan_to_num(v[lo:hi]), g)).copy()
             res["cumsum_vi"] = _np(rd.sharded_cumsum(ops, vi[lo:hi], g, f[lo:hi])).copy()
             res["cumsum_f32"] = _np(rd.sharded_cumsum(ops, np.nan_to_num(v[lo:hi]).astype(np.float32), g, f[lo:hi])).copy()
@@ -308,6 +311,16 @@ def test_sharded_groupby_and_reduce_world2(cuts, a2a):
                                               err_msg=f"{name} pick {fn} {p}")
                 exp = orc.GroupByAllPack32([k2], eik, ig, ifg, cnt, eu, [fn], [1], [eu + 1], p)[0]
                 np.testing.assert_array_equal(got[r][name][f"picks{fn}_{p}"][1:], exp[1:], err_msg=f"{name} pick S {fn} {p}")
+        if name in ("one", "filt"):
+            for r in range(2):
+                pk = got[r][name]["pack"]
+                np.testing.assert_array_equal(pk["nCountGroup"], cnt)
+                np.testing.assert_array_equal(pk["iFirstGroup"], ifg)
+                b0, b1 = pk["bin_lo"], pk["bin_hi"]
+                lo_p = int(ifg[b0]) if b0 < len(ifg) else len(ig)
+                hi_p = int(ifg[b1]) if b1 < len(ifg) else len(ig)
+                np.testing.assert_array_equal(pk["iGroup_owned"], ig[lo_p:hi_p], err_msg=f"{name} pack rank {r}")
+            assert got[0][name]["pack"]["bin_hi"] == got[1][name]["pack"]["bin_lo"]
         lo_, hi_ = cuts[0], cuts[2]
         full = lambda key: np.concatenate([got[r][name][key] for r in range(2)])  # noqa: E731
         exp = orc.EmaAll32([np.nan_to_num(v)], eik, eu, 300, (0.0, None, None, None))[0]

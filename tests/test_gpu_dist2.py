@@ -45,6 +45,8 @@ def _worker(rank, world, port, n, q):
         out["first"] = rd.sharded_pick(ops, vt, g, 100).numpy()
         out["last"] = rd.sharded_pick(ops, vt, g, 102).numpy()
         out["cumsum"] = rd.sharded_cumsum(ops, vt, g).cpu().numpy()
+        pk = rd.sharded_pack(ops, g)
+        out["pack"] = {a: (b.cpu().numpy() if hasattr(b, "cpu") else b) for a, b in pk.items()}
         g2 = rd.sharded_groupby(ops, [torch.from_numpy(k[lo:hi]).cuda(), s[lo:hi]], None)
         out["ikey2"] = g2.ikey.cpu().numpy()
         out["sum2"] = rd.sharded_reduce(ops, vt, g2, 0).cpu().numpy()
@@ -86,6 +88,13 @@ def test_two_rank_nccl_paths():
             np.testing.assert_allclose(got[r][f"r{fn}"], exp, rtol=1e-11, atol=1e-9, equal_nan=True)
         np.testing.assert_array_equal(got[r]["first"][1:], orc.GroupByAllPack32([v], eik, ig, ifg, cnt, eu, [100], [1], [eu + 1], 0)[0][1:])
         np.testing.assert_array_equal(got[r]["last"][1:], orc.GroupByAllPack32([v], eik, ig, ifg, cnt, eu, [102], [1], [eu + 1], 0)[0][1:])
+    for r in range(2):
+        pk = got[r]["pack"]
+        np.testing.assert_array_equal(pk["nCountGroup"], cnt)
+        np.testing.assert_array_equal(pk["iFirstGroup"], ifg)
+        lo_p = int(ifg[pk["bin_lo"]]) if pk["bin_lo"] < len(ifg) else len(ig)
+        hi_p = int(ifg[pk["bin_hi"]]) if pk["bin_hi"] < len(ifg) else len(ig)
+        np.testing.assert_array_equal(pk["iGroup_owned"], ig[lo_p:hi_p])
     np.testing.assert_allclose(np.concatenate([got[0]["cumsum"], got[1]["cumsum"]]),
                                orc.EmaAll32([v], eik, eu, 300, (0.0, None, None, None))[0], rtol=1e-12, atol=1e-9)
     eik2, _, eu2 = orc.MultiKeyGroupBy32([k, s], 0, None, 2)

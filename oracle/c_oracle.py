@@ -26,6 +26,8 @@ def lib():
         _lib = C.CDLL(LIB)
         _lib.orc_groupby_u64.restype = C.c_int64
         _lib.orc_groupby_u64.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        _lib.orc_groupby_u64_parallel.restype = C.c_int64
+        _lib.orc_groupby_u64_parallel.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
         _lib.orc_sum_f64.restype = None
         _lib.orc_sum_f64.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int]
         _lib.orc_max_threads.restype = C.c_int
@@ -36,14 +38,20 @@ def max_threads():
     return int(lib().orc_max_threads())
 
 
-def groupby_u64(keys, filter=None):
+def groupby_u64(keys, filter=None, threads=1):
+    """threads = 1: one sequential pass (rc.MultiKeyGroupBy32 without cutoffs); threads > 1: partitions grouped in
+    parallel and merged (riptable's cutoffs + hstack_groupings route).  Same result either way."""
     keys = np.ascontiguousarray(keys)
     assert keys.dtype.itemsize == 8
     n = len(keys)
     ikey = np.empty(n, np.int32)
     ifirst = np.empty(max(n, 1), np.int32)
     f = np.ascontiguousarray(filter, dtype=np.uint8) if filter is not None else None
-    u = lib().orc_groupby_u64(keys.ctypes.data, f.ctypes.data if f is not None else None, n, ikey.ctypes.data, ifirst.ctypes.data)
+    fp = f.ctypes.data if f is not None else None
+    if threads and threads > 1:
+        u = lib().orc_groupby_u64_parallel(keys.ctypes.data, fp, n, ikey.ctypes.data, ifirst.ctypes.data, int(threads))
+    else:
+        u = lib().orc_groupby_u64(keys.ctypes.data, fp, n, ikey.ctypes.data, ifirst.ctypes.data)
     if u < 0:
         raise MemoryError("orc_groupby_u64")
     return ikey, ifirst[:u].copy(), int(u)

@@ -58,6 +58,64 @@ int64_t orc_groupby_u64(const uint64_t* keys, const uint8_t* filter, int64_t n, 
   return U;
 }
 
+/* The same grouping with riptable's own parallel handle: contiguous row partitions grouped independently
+ * (`cutoffs`, riptable/rt_numpy.py:1914-1915 "cutoff array for parallel processing") and merged the way
+ * hstack_groupings does (riptable/rt_grouping.py:277-413): re-group the stacked per-partition uniques in partition
+ * order, then re-index every partition's iKey.  Result identical to orc_groupby_u64. */
+int64_t orc_groupby_u64_parallel(const uint64_t* keys, const uint8_t* filter, int64_t n, int32_t* ikey_out,
+                                 int32_t* ifirst_out, int threads) {
+  if (threads < 1) threads = 1;
+  if (threads > 256) threads = 256;
+  if (n < (int64_t)threads * 1024) return orc_groupby_u64(keys, filter, n, ikey_out, ifirst_out);
+  int64_t* lo = (int64_t*)malloc(sizeof(int64_t) * (threads + 1));
+  int64_t* uc = (int64_t*)calloc(threads, sizeof(int64_t));
+  int32_t** lfirst = (int32_t**)calloc(threads, sizeof(int32_t*));
+  int32_t** map = (int32_t**)calloc(threads, sizeof(int32_t*));
+  if (!lo || !uc || !lfirst || !map) return -1;
+  for (int t = 0; t <= threads; t++) lo[t] = n * t / threads;
+  int failed = 0;
+#pragma omp parallel for num_threads(threads) schedule(static, 1)
+  for (int t = 0; t < threads; t++) {
+    int64_t m = lo[t + 1] - lo[t];
+    lfirst[t] = (int32_t*)malloc(sizeof(int32_t) * (size_t)(m > 0 ? m : 1));
+    if (!lfirst[t]) { failed = 1; continue; }
+    uc[t] = orc_groupby_u64(keys + lo[t], filter ? filter + lo[t] : NULL, m, ikey_out + lo[t], lfirst[t]);
+    if (uc[t] < 0) failed = 1;
+  }
+  if (failed) return -1;
+  /* merge: stacked uniques in partition order -> global first-appearance bins */
+  uint64_t cap = 1 << 16;
+  int64_t total = 0;
+  for (int t = 0; t < threads; t++) total += uc[t];
+  while (cap < (uint64_t)total * 2 + 2) cap <<= 1;
+  uint64_t* tk = (uint64_t*)malloc(cap * sizeof(uint64_t));
+  int32_t* tb = (int32_t*)calloc(cap, sizeof(int32_t));
+  if (!tk || !tb) return -1;
+  int64_t U = 0;
+  for (int t = 0; t < threads; t++) {
+    map[t] = (int32_t*)malloc(sizeof(int32_t) * (size_t)(uc[t] + 1));
+    if (!map[t]) return -1;
+    map[t][0] = 0;
+    for (int64_t j = 0; j < uc[t]; j++) {
+      int64_t row = lo[t] + lfirst[t][j];
+      uint64_t k = keys[row], i = mix(k) & (cap - 1);
+      for (;;) {
+        if (!tb[i]) { tk[i] = k; tb[i] = (int32_t)(++U); ifirst_out[U - 1] = (int32_t)row; map[t][j + 1] = (int32_t)U; break; }
+        if (tk[i] == k) { map[t][j + 1] = tb[i]; break; }
+        i = (i + 1) & (cap - 1);
+      }
+    }
+  }
+#pragma omp parallel for num_threads(threads) schedule(static, 1)
+  for (int t = 1; t < threads; t++) { /* partition 0 is already in global numbering */
+    const int32_t* m = map[t];
+    for (int64_t r = lo[t]; r < lo[t + 1]; r++) ikey_out[r] = m[ikey_out[r]];
+  }
+  for (int t = 0; t < threads; t++) { free(lfirst[t]); free(map[t]); }
+  free(lfirst); free(map); free(lo); free(uc); free(tk); free(tb);
+  return U;
+}
+
 /* sum of f64 values per bin; out[nb]; bins outside [lo,hi) left 0.  Threads own bin ranges. */
 void orc_sum_f64(const double* v, const int32_t* ikey, int64_t n, int64_t nb, int64_t lo, int64_t hi, double* out,
                  int threads) {

@@ -32,3 +32,17 @@ def test_c_sum_matches_numpy_oracle():
         exp = orc.GroupByAll32([v], ikey, u, [0], [1], [u + 1])[0]
         np.testing.assert_allclose(got[1:], exp[1:], rtol=1e-12, atol=1e-12)
         assert got[0] == 0
+
+
+def test_c_parallel_groupby_equals_sequential():
+    # the cutoffs + hstack_groupings route (partitions grouped in parallel, merged in partition order)
+    rng = np.random.default_rng(3)
+    vals = rng.integers(-(2**62), 2**62, 5000)
+    k = vals[rng.integers(0, 5000, 400_000)]
+    k[:200_000] = vals[rng.integers(0, 2000, 200_000)]  # late keys
+    f = rng.random(len(k)) < 0.8
+    for filt in (None, f):
+        ok, ofk, ou = orc.MultiKeyGroupBy32([k], filter=filt)
+        for threads in (2, 5, 8):
+            ik, ifk, u = c_oracle.groupby_u64(k, filt, threads=threads)
+            assert u == ou and np.array_equal(ik, ok) and np.array_equal(ifk, ofk)

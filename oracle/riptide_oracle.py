@@ -561,3 +561,51 @@ def groupbylex(list_arrays, filter=None, cutoffs=None, base_index=1, rec=False):
         "iFirstGroup": iFirstGroup,
         "nCountGroup": nCountGroup,
     }
+
+
+# ----------------------------------------------------------------------------------------------
+# 8f.1  rc.IsMember32 / rc.MultiKeyIsMember32 (rt_numpy.py:1186-1393; tests/test_ismember.py)
+def _index_dtype_from_len(n):
+    """rt_enum.py:666-679 (tests/test_ismember.py:288-300: the index array is downcast by len(b))."""
+    return np.int8 if n < 100 else np.int16 if n < 30_000 else np.int32 if n < 2_000_000_000 else np.int64
+
+
+def _ismember_cols(a_cols, b_cols):
+    a_cols = [np.asarray(c) for c in a_cols]
+    b_cols = [np.asarray(c) for c in b_cols]
+    na, nb = len(a_cols[0]), len(b_cols[0])
+    idt = np.dtype(_index_dtype_from_len(nb))
+    inv = invalid_for(idt)
+    out = np.full(na, inv, dtype=idt)
+    found = np.zeros(na, dtype=bool)
+    if na == 0 or nb == 0:
+        return found, out
+    cat, valid = [], np.ones(na + nb, dtype=bool)
+    for ac, bc in zip(a_cols, b_cols):
+        if ac.dtype.kind in "SU" or bc.dtype.kind in "SU":
+            w = max(ac.dtype.itemsize, bc.dtype.itemsize)
+            kind = ac.dtype.kind
+            dt = np.dtype(f"{kind}{w // (4 if kind == 'U' else 1)}")
+            ac, bc = ac.astype(dt), bc.astype(dt)
+        elif ac.dtype != bc.dtype:
+            raise TypeError("ismember: numeric keys must share a dtype (riptable casts before calling rc)")
+        c = np.concatenate([bc, ac])
+        if c.dtype.kind == "f":
+            valid &= ~np.isnan(c)  # NaN never matches (tests/test_ismember.py)
+        cat.append(c)
+    ik, ifk, _ = MultiKeyGroupBy32(cat, 0, valid, 2)
+    ika = ik[nb:].astype(np.int64)
+    first = ifk[np.maximum(ika - 1, 0)] if len(ifk) else np.zeros(na, np.int64)
+    found = (ika > 0) & (first < nb)
+    out[found] = first[found].astype(idt)
+    return found, out
+
+
+def IsMember32(a, b, h=2, hint_size=0):
+    """-> (bool[len(a)], index of the first occurrence of a[i] in b, the index dtype's invalid where absent)."""
+    return _ismember_cols([a], [b])
+
+
+def MultiKeyIsMember32(a_tuple, b_tuple, hint_size=0):
+    """rt_numpy.py:1325: rc.MultiKeyIsMember32((a_cols,), (b_cols,), hint_size) -- tuple equality across the columns."""
+    return _ismember_cols(list(a_tuple[0]), list(b_tuple[0]))

@@ -609,7 +609,75 @@ def ReverseShuffle(perm):
 
 __all__ = ["GroupByStream", "LexPartition", "MultiKeyGroupBy32", "CombineFilter", "CombineAccum1Filter", "CombineAccum2Filter", "GroupByAll32", "BinCount",
            "GroupFromBinCount", "GroupByPack32", "GroupByAllPack32", "EmaAll32", "MakeiFirst", "MakeiNext", "LexSort32",
-           "LexSort64", "GroupFromLexSort", "ReverseShuffle", "LedgerFunction"]
+           "LexSort64", "GroupFromLexSort", "ReverseShuffle", "IsMember32", "MultiKeyIsMember32", "LedgerFunction"]
+
+
+# ==================================================================================================
+# 8f.1  rc.IsMember32 / rc.MultiKeyIsMember32 (riptable/rt_numpy.py:1186-1393)
+def _concat_dev(b: DevArray, a: DevArray) -> DevArray:
+    """[b ; a] as one device column; fixed-width strings are padded to the wider item first."""
+    if b.dtype.kind in "SU" or a.dtype.kind in "SU":
+        if a.dtype.kind != b.dtype.kind:
+            raise TypeError("ismember: string keys must be matched with string keys of the same kind")
+        w = max(a.dtype.itemsize, b.dtype.itemsize)
+        dt = np.dtype(f"{a.dtype.kind}{w // (4 if a.dtype.kind == 'U' else 1)}")
+        out = torch.zeros(max((a.n + b.n) * w, 16), dtype=torch.uint8, device=_device())
+        for arr, lo in ((b, 0), (a, b.n)):
+            if arr.n:
+                isz = arr.dtype.itemsize
+                out[lo * w: (lo + arr.n) * w].view(arr.n, w)[:, :isz] = arr.buf[: arr.n * isz].view(arr.n, isz)
+        return DevArray(out, dt, a.n + b.n)
+    if a.dtype != b.dtype:
+        raise TypeError("ismember: numeric keys must share a dtype (riptable casts before calling rc)")
+    isz = a.dtype.itemsize
+    out = torch.empty(max((a.n + b.n) * isz, 16), dtype=torch.uint8, device=_device())
+    out[: b.n * isz] = b.buf[: b.n * isz]
+    out[b.n * isz: (a.n + b.n) * isz] = a.buf[: a.n * isz]
+    return DevArray(out, a.dtype, a.n + b.n)
+
+
+def _ismember(a_cols, b_cols):
+    """Hash-group the rows of b followed by the rows of a: a row of `a` is a member iff its bin's first row lies in
+    the b part, and that first row is the index of its first occurrence in b.  NaN keys never match."""
+    from .enums import int_dtype_from_len, invalid_for
+
+    device_mode = any(_is_device(c) for c in list(a_cols) + list(b_cols))
+    if len(a_cols) != len(b_cols) or not a_cols:
+        raise ValueError("ismember: a and b must have the same number of key columns")
+    acs, bcs = [_to_dev(c) for c in a_cols], [_to_dev(c) for c in b_cols]
+    na, nb = acs[0].n, bcs[0].n
+    idt = int_dtype_from_len(nb)
+    tdt = _TORCH_OF[idt]
+    inv = int(invalid_for(idt))
+    dev = _device()
+    if na == 0 or nb == 0:
+        found = torch.zeros(na, dtype=torch.bool, device=dev)
+        idx = torch.full((na,), inv, dtype=tdt, device=dev)
+    else:
+        cat = [_concat_dev(bc, ac) for ac, bc in zip(acs, bcs)]
+        valid = None
+        for c in cat:
+            if c.dtype.kind == "f":
+                ok = ~torch.isnan(c.torch())
+                valid = ok if valid is None else valid & ok
+        ik, ifk, u = MultiKeyGroupBy32(cat, 0, valid, 2)
+        ika = ik[nb:].to(torch.int64)
+        first = ifk.to(torch.int64)[(ika - 1).clamp(min=0)] if u else torch.zeros(na, dtype=torch.int64, device=dev)
+        found = (ika > 0) & (first < nb)
+        idx = torch.where(found, first, torch.full_like(first, inv)).to(tdt)
+    if device_mode:
+        return found, idx
+    return found.cpu().numpy(), idx.cpu().numpy()
+
+
+def IsMember32(a, b, h=2, hint_size=0):
+    """-> (bool[len(a)], index of the first occurrence of a[i] in b; the index dtype (by len(b)) 's invalid where absent)."""
+    return _ismember([a], [b])
+
+
+def MultiKeyIsMember32(a_tuple, b_tuple, hint_size=0):
+    """rc.MultiKeyIsMember32((a_cols,), (b_cols,), hint_size) (riptable/rt_numpy.py:1325)."""
+    return _ismember(list(a_tuple[0]), list(b_tuple[0]))
 
 
 def LedgerFunction(func, *args, **kwargs):

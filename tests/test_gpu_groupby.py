@@ -293,3 +293,37 @@ def test_groupby_stream_chunks_equal_one_shot(rc):
             assert st.unique_count == eu
             np.testing.assert_array_equal(np.concatenate(parts), eik)
             np.testing.assert_array_equal(st.ifirstkey.cpu().numpy(), eifk)
+
+
+def test_ismember_vs_oracle(rc):
+    # 8f.1: rc.IsMember32 / rc.MultiKeyIsMember32 (tests/test_ismember.py semantics)
+    rng = np.random.default_rng(44)
+    for dt in (np.int8, np.uint16, np.int32, np.int64, np.uint64, np.float32, np.float64):
+        a = rng.integers(0, 100, 50_000).astype(dt)
+        b = rng.integers(50, 120, 777).astype(dt)
+        if np.dtype(dt).kind == "f":
+            a[::7] = np.nan
+            b[::5] = np.nan
+        m, idx = rc.IsMember32(a, b)
+        em, eidx = orc.IsMember32(a, b)
+        assert idx.dtype == eidx.dtype
+        np.testing.assert_array_equal(m, em)
+        np.testing.assert_array_equal(idx, eidx)
+    a = np.array([b"b", b"a", b"a", b"Inv", b"c", b"a", b"b"], dtype="S")
+    b = np.array([b"a", b"b", b"c"], dtype="S")
+    m, idx = rc.IsMember32(a, b)
+    assert m.tolist() == [True, True, True, False, True, True, True] and idx.tolist() == [1, 0, 0, -128, 2, 0, 1]
+    for sz, dt in ((5, np.int8), (29_000, np.int16), (60_000, np.int32)):
+        _, idx = rc.IsMember32(np.array([b"a", b"b"]), np.full(sz, b"a"))
+        assert idx.dtype == dt and idx[0] == 0 and idx[1] == np.iinfo(dt).min
+    n = 200_000
+    a1, a2 = rng.integers(0, 300, n), rng.choice(np.array(["x", "yy", "zzz", ""]), n)
+    b1, b2 = rng.integers(100, 400, 5000), rng.choice(np.array(["x", "yy", "w"]), 5000)
+    m, idx = rc.MultiKeyIsMember32(([a1, a2],), ([b1, b2],))
+    em, eidx = orc.MultiKeyIsMember32(([a1, a2],), ([b1, b2],))
+    np.testing.assert_array_equal(m, em)
+    np.testing.assert_array_equal(idx, eidx)
+    m, idx = rc.IsMember32(np.zeros(0, np.int32), np.arange(3, dtype=np.int32))
+    assert len(m) == 0 and len(idx) == 0
+    m, idx = rc.IsMember32(np.arange(3, dtype=np.int32), np.zeros(0, np.int32))
+    assert not m.any() and (idx == np.iinfo(np.int8).min).all()

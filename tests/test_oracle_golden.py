@@ -259,3 +259,25 @@ def test_projections_455654_groups():
     assert (np.diff(r["iFirstKey"]) > 0).all()
     cnt = orc.BinCount(r["iKey"], r["unique_count"] + 1)
     assert cnt[0] == 0 and cnt.sum() == n
+
+
+def test_ismember_reference_kats():
+    # tests/test_ismember.py:14-70 (numbers), :313-322 (strings of different itemsize), :288-300 (index downcast)
+    for dt in "bhilqBHILQfd":
+        a, b = np.array([1, 2, 3, 4, 5], dtype=dt), np.array([1, 2], dtype=dt)
+        m, idx = orc.IsMember32(a, b)
+        assert m.tolist() == [True, True, False, False, False] and idx[:2].tolist() == [0, 1]
+        assert idx.dtype == np.int8 and (idx[2:] == np.iinfo(np.int8).min).all()
+    a = np.array([b"b", b"a", b"a", b"Inv", b"c", b"a", b"b"], dtype="S")
+    b = np.array([b"a", b"b", b"c"], dtype="S")
+    m, idx = orc.IsMember32(a, b)
+    assert m.tolist() == [True, True, True, False, True, True, True]
+    assert idx.tolist() == [1, 0, 0, -128, 2, 0, 1] and idx.dtype == np.int8
+    for sz, dt in ((5, np.int8), (29_000, np.int16), (60_000, np.int32)):
+        _, idx = orc.IsMember32(np.array([b"a", b"b"]), np.full(sz, b"a"))
+        assert idx.dtype == dt and idx[0] == 0
+    m, idx = orc.IsMember32(np.array([np.nan, 1.0]), np.array([np.nan, 1.0]))
+    assert m.tolist() == [False, True] and idx[1] == 1
+    m, idx = orc.MultiKeyIsMember32(([np.array([1, 2, 1]), np.array([b"x", b"y", b"z"])],),
+                                   ([np.array([1, 1]), np.array([b"z", b"x"])],))
+    assert m.tolist() == [True, False, True] and idx[[0, 2]].tolist() == [1, 0]

@@ -46,7 +46,8 @@ typedef enum {
   RTB_GB_NANSUM = 50, RTB_GB_NANMEAN = 51, RTB_GB_NANMIN = 52, RTB_GB_NANMAX = 53, RTB_GB_NANVAR = 54,
   RTB_GB_NANSTD = 55,
   RTB_GB_FIRST = 100, RTB_GB_NTH = 101, RTB_GB_LAST = 102,
-  RTB_GB_CUMSUM = 300
+  RTB_GB_CUMSUM = 300, RTB_GB_CUMPROD = 302, RTB_GB_CUMNANMAX = 306, RTB_GB_CUMNANMIN = 307, RTB_GB_CUMMAX = 308,
+  RTB_GB_CUMMIN = 309
 } rtb_gb_func;
 
 /* One key / value column: `itemsize` bytes per row, rows contiguous. */
@@ -153,6 +154,17 @@ size_t rtb_cumsum_workspace_bytes(int64_t nrows, int64_t unique_rows);
 int rtb_groupby_cumsum(const void* values, int vdtype, const void* ikey, int kdtype, int64_t nrows,
                        int64_t unique_rows, const uint8_t* filter, const uint8_t* reset_filter, void* out,
                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- 8f.2: the other cumulative functions of rc.EmaAll32 — riptable/rt_groupbyops.py:3182-3258, function numbers
+ * riptable/rt_enum.py (GB_CUMPROD 302, GB_CUMNANMAX 306, GB_CUMNANMIN 307, GB_CUMMAX 308, GB_CUMMIN 309).
+ * func = RTB_GB_CUM*.  cumprod: out dtype as cumsum.  cummin / cummax: out dtype = vdtype
+ * (riptable/tests/test_groupbyops.py:524-525); the NAN variants skip NaN / integer sentinels (np.fmin.accumulate),
+ * the plain ones turn the rest of the group invalid after the first one (np.minimum.accumulate); a row before the
+ * group's first valid value gets the invalid.  Workspace: rtb_cumsum_workspace_bytes. */
+int rtb_cumop_out_dtype(int func, int vdtype);
+int rtb_groupby_cumop(int func, const void* values, int vdtype, const void* ikey, int kdtype, int64_t nrows,
+                      int64_t unique_rows, const uint8_t* filter, const uint8_t* reset_filter, void* out,
+                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a10: rc.MakeiFirst(key, n, filter, mode) / rc.MakeiNext(key, n, mode) — riptable/rt_numpy.py:1791-1854 */
 int rtb_make_ifirst(const void* ikey, int kdtype, int64_t nrows, int64_t n, const uint8_t* filter, int mode,

@@ -322,58 +322,94 @@ def GroupByAllPack32(
 
 
 # ----------------------------------------------------------------------------------------------
-# a9  rc.EmaAll32, GB_CUMSUM only (rt_grouping.py:3427-3430; rt_groupbyops.py:3158-3178)
+# a9 / 8f.2  rc.EmaAll32: GB_CUMSUM, GB_CUMPROD, GB_CUM[NAN]MIN / MAX
+#   (rt_grouping.py:3427-3430; rt_groupbyops.py:3158-3258; function numbers rt_enum.py:523-532)
+GB_CUMPROD, GB_CUMNANMAX, GB_CUMNANMIN, GB_CUMMAX, GB_CUMMIN = 302, 306, 307, 308, 309
+
+
+def _is_invalid(v):
+    """NaN for floats, the riptable sentinel for integers, nothing for bool (rt_enum.py INVALID_DICT)."""
+    if v.dtype.kind == "f":
+        return np.isnan(v)
+    if v.dtype.kind in "iu":
+        return v == invalid_for(v.dtype)
+    return np.zeros(len(v), bool)
+
+
 def EmaAll32(values, ikey, unique_rows, funcNum, func_param):
-    """Per-group running sum in original row order (tests/test_groupby.py:555-602).
+    """Per-group running sum / product / min / max in original row order (tests/test_groupby.py:555-602,
+    tests/test_groupbyops.py:458-538).
     func_param = (decay, time, filter, reset_filter).  Op-filter False -> the row gets the group's
-    current running value; bin 0 row -> invalid of the OUTPUT dtype.  Output dtype: ints -> int64
-    (uint64 stays), floats keep theirs (UNPINNED).  reset_filter (UNPINNED): on a row that passes
-    the filter and has reset set, zero the accumulator before adding (rt_fastarraynumba.py:506-524).
-    Integer sentinels are not skipped (tests/test_merge.py:6425-6426)."""
-    if int(funcNum) != GB_CUMSUM:
+    current running value; bin 0 row -> invalid of the OUTPUT dtype.
+    cumsum / cumprod: output dtype ints -> int64 (uint64 stays), floats keep theirs (UNPINNED);
+    integer sentinels are not skipped (tests/test_merge.py:6425-6426).
+    cummin / cummax: output dtype == input dtype (test_groupbyops.py:524-525); GB_CUMNAN* skip NaN /
+    sentinels like np.fmin/fmax.accumulate, GB_CUMMIN/MAX propagate them like np.minimum/maximum
+    .accumulate (test_groupbyops.py:529-537); before a group's first valid value the result is invalid.
+    reset_filter (UNPINNED): on a row that passes the filter and has reset set, restart the
+    accumulator before applying the row (rt_fastarraynumba.py:506-524)."""
+    f = int(funcNum)
+    if f not in (GB_CUMSUM, GB_CUMPROD, GB_CUMNANMAX, GB_CUMNANMIN, GB_CUMMAX, GB_CUMMIN):
         raise ValueError(f"EmaAll32: unsupported function {funcNum}")
     filt = reset = None
     if isinstance(func_param, (tuple, list)) and len(func_param) >= 4:
         filt, reset = func_param[2], func_param[3]
     ik = np.asarray(ikey).astype(np.int64)
     n = len(ik)
+    active = ik > 0
+    add = active & np.asarray(filt, dtype=bool) if filt is not None else active
+    order = np.argsort(ik, kind="stable")
+    iks = ik[order]
+    seg_start = np.r_[True, iks[1:] != iks[:-1]] if n else np.zeros(0, bool)
+    if reset is not None:
+        seg_start = seg_start | (np.asarray(reset, dtype=bool) & add)[order]
+    start_idx = np.flatnonzero(seg_start)
+    ends = np.r_[start_idx[1:], n] if n else np.zeros(0, np.int64)
+    adds = add[order]
     res = []
     for v in values:
         v = np.asarray(v)
         if v.dtype.kind not in "biuf":
             res.append(None)
             continue
-        odt = _sum_out_dtype(v.dtype)
-        acc_dt = np.dtype(np.float64) if v.dtype.kind == "f" else np.dtype(odt)
-        x = v.astype(acc_dt)
-        active = ik > 0
-        if filt is not None:
-            add = active & np.asarray(filt, dtype=bool)
-        else:
-            add = active
-        # stable bucket by bin, then a segmented running sum
-        order = np.argsort(ik, kind="stable")
-        iks = ik[order]
-        xs = np.where(add[order], x[order], acc_dt.type(0))
-        seg_start = np.r_[True, iks[1:] != iks[:-1]] if n else np.zeros(0, bool)
-        if reset is not None:
-            rs = (np.asarray(reset, dtype=bool) & add)[order]
-            seg_start = seg_start | rs
-        with np.errstate(over="ignore", invalid="ignore"):
-            cs = np.cumsum(xs)
-            start_idx = np.flatnonzero(seg_start)
-            seg_id = np.cumsum(seg_start) - 1
-            if acc_dt.kind == "f":
-                # exact per-segment sequential sums (no cancellation against earlier segments)
-                run = np.empty(n, np.float64)
-                ends = np.r_[start_idx[1:], n]
+        if f in (GB_CUMSUM, GB_CUMPROD):
+            odt = _sum_out_dtype(v.dtype)
+            acc_dt = np.dtype(np.float64) if v.dtype.kind == "f" else np.dtype(odt)
+            ident = acc_dt.type(0 if f == GB_CUMSUM else 1)
+            xs = np.where(adds, v.astype(acc_dt)[order], ident)
+            run = np.empty(n, acc_dt)
+            acc = np.cumsum if f == GB_CUMSUM else np.cumprod
+            with np.errstate(over="ignore", invalid="ignore"):
+                # exact per-segment sequential accumulation (no cancellation against earlier segments)
                 for s, e in zip(start_idx, ends):
-                    run[s:e] = np.cumsum(xs[s:e])
+                    run[s:e] = acc(xs[s:e])
+                out = np.empty(n, dtype=odt)
+                out[order] = run.astype(odt)
+        else:
+            odt = v.dtype
+            ismin = f in (GB_CUMMIN, GB_CUMNANMIN)
+            skipna = f in (GB_CUMNANMIN, GB_CUMNANMAX)
+            vs = v[order]
+            bad = _is_invalid(vs) & adds
+            good = adds & ~bad
+            if v.dtype.kind == "f":
+                fill = v.dtype.type(np.inf if ismin else -np.inf)
+            elif v.dtype.kind == "b":
+                fill = np.bool_(ismin)
             else:
-                base = cs[start_idx] - xs[start_idx]
-                run = cs - base[seg_id]
-        out = np.empty(n, dtype=odt)
-        out[order] = run.astype(odt)
+                fill = v.dtype.type(np.iinfo(v.dtype).max if ismin else np.iinfo(v.dtype).min)
+            cand = np.where(good, vs, fill)
+            run = np.empty(n, v.dtype)
+            ok = np.empty(n, bool)
+            acc = np.minimum.accumulate if ismin else np.maximum.accumulate
+            for s, e in zip(start_idx, ends):
+                run[s:e] = acc(cand[s:e])
+                ok[s:e] = np.logical_or.accumulate(good[s:e])
+                if not skipna:
+                    ok[s:e] &= ~np.logical_or.accumulate(bad[s:e])
+            run[~ok] = invalid_for(odt)
+            out = np.empty(n, dtype=odt)
+            out[order] = run
         out[~active] = invalid_for(odt)
         res.append(out)
     return res

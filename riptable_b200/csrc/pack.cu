@@ -107,31 +107,57 @@ __global__ void __launch_bounds__(256) pick_kernel(const uint8_t* __restrict__ v
   }
 }
 
-// ---- a9: cumsum ------------------------------------------------------------------------------------------
+// ---- a9: cumulative ops (cumsum / cumprod / cummin / cummax) -----------------------------------------------
 constexpr int kSegThreads = 256;
 constexpr int kSegItems = 8;
 constexpr int kSegTile = kSegThreads * kSegItems;
 
+// Scan operators.  Sums and products run on int64 / f64 payloads with plain identities; min / max run on the
+// order-preserving uint64 codes of values.cuh and carry two state bits next to the segment-head flag, because
+// "nothing seen yet" and "a NaN / sentinel was seen" (skipna=False) both have to come out as the invalid value.
+enum { CUM_SUM_I = 0, CUM_SUM_F = 1, CUM_PROD_I = 2, CUM_PROD_F = 3, CUM_MIN = 4, CUM_MAX = 5 };
+constexpr uint32_t SEG_HEAD = 1u, SEG_HAS = 2u, SEG_POISON = 4u;
+
 struct SegPair {
-  unsigned long long v;  // f64 bits or 64-bit integer
-  uint32_t f;            // a segment head lies inside the summarised range
+  unsigned long long v;  // f64 bits, 64-bit integer, or value code
+  uint32_t f;            // SEG_HEAD: a segment head lies inside the summarised range; SEG_HAS / SEG_POISON: min/max state
 };
 
-template <bool FLOAT>
-__device__ __forceinline__ unsigned long long seg_add(unsigned long long a, unsigned long long b) {
-  if (FLOAT) return (unsigned long long)__double_as_longlong(__longlong_as_double((long long)a) + __longlong_as_double((long long)b));
+__device__ __forceinline__ unsigned long long f64_bits(double d) { return (unsigned long long)__double_as_longlong(d); }
+__device__ __forceinline__ double bits_f64(unsigned long long u) { return __longlong_as_double((long long)u); }
+
+template <int OP>
+__device__ __forceinline__ unsigned long long seg_op(unsigned long long a, unsigned long long b) {
+  if (OP == CUM_SUM_F) return f64_bits(bits_f64(a) + bits_f64(b));
+  if (OP == CUM_PROD_F) return f64_bits(bits_f64(a) * bits_f64(b));
+  if (OP == CUM_PROD_I) return a * b;
+  if (OP == CUM_MIN) return a < b ? a : b;
+  if (OP == CUM_MAX) return a > b ? a : b;
   return a + b;
 }
-template <bool FLOAT>
+template <int OP>
+__device__ __forceinline__ SegPair seg_identity() {
+  SegPair r;
+  r.f = 0;
+  r.v = OP == CUM_PROD_I ? 1ull : OP == CUM_PROD_F ? 0x3FF0000000000000ull : 0ull;
+  return r;
+}
+template <int OP>
 __device__ __forceinline__ SegPair seg_combine(SegPair a, SegPair b) {  // a precedes b
   SegPair r;
-  r.f = a.f | b.f;
-  r.v = b.f ? b.v : seg_add<FLOAT>(a.v, b.v);
+  if (OP < CUM_MIN) {
+    r.f = a.f | b.f;
+    r.v = b.f ? b.v : seg_op<OP>(a.v, b.v);
+  } else {
+    if (b.f & SEG_HEAD) return b;
+    r.f = a.f | b.f;
+    r.v = (a.f & b.f & SEG_HAS) ? seg_op<OP>(a.v, b.v) : (a.f & SEG_HAS) ? a.v : b.v;
+  }
   return r;
 }
 
 // inclusive scan of SegPair across the block; returns this thread's EXCLUSIVE prefix and the block total
-template <bool FLOAT>
+template <int OP>
 __device__ __forceinline__ SegPair seg_block_exclusive(SegPair x, SegPair* total) {
   __shared__ SegPair wtot[kSegThreads / 32];
   __shared__ SegPair btot;
@@ -142,18 +168,17 @@ __device__ __forceinline__ SegPair seg_block_exclusive(SegPair x, SegPair* total
     SegPair t;
     t.v = __shfl_up_sync(0xffffffffu, inc.v, d);
     t.f = __shfl_up_sync(0xffffffffu, inc.f, d);
-    if (lane >= d) inc = seg_combine<FLOAT>(t, inc);
+    if (lane >= d) inc = seg_combine<OP>(t, inc);
   }
   if (lane == 31) wtot[w] = inc;
   __syncthreads();
-  SegPair ex;  // exclusive prefix = (previous warps) o (previous lanes)
-  ex.v = 0; ex.f = 0;
-  for (int i = 0; i < w; i++) ex = seg_combine<FLOAT>(ex, wtot[i]);
+  SegPair ex = seg_identity<OP>();  // exclusive prefix = (previous warps) o (previous lanes)
+  for (int i = 0; i < w; i++) ex = seg_combine<OP>(ex, wtot[i]);
   SegPair prev;
   prev.v = __shfl_up_sync(0xffffffffu, inc.v, 1);
   prev.f = __shfl_up_sync(0xffffffffu, inc.f, 1);
-  if (lane > 0) ex = seg_combine<FLOAT>(ex, prev);
-  if (threadIdx.x == kSegThreads - 1) btot = seg_combine<FLOAT>(ex, x);
+  if (lane > 0) ex = seg_combine<OP>(ex, prev);
+  if (threadIdx.x == kSegThreads - 1) btot = seg_combine<OP>(ex, x);
   __syncthreads();
   *total = btot;
   __syncthreads();
@@ -163,23 +188,23 @@ __device__ __forceinline__ SegPair seg_block_exclusive(SegPair x, SegPair* total
 struct CumArgs {
   const void* values;
   int vdt, odt;
+  int skipna;              // min/max: invalid values are skipped (1) or poison the rest of the segment (0)
   const uint32_t* skeys;   // bins in packed order
   const uint32_t* igroup;  // packed row ids
   const uint8_t* filter;
   const uint8_t* reset;
   int64_t n;
-  unsigned long long* xs;  // gathered addends in packed order
-  uint8_t* heads;          // segment-head flags in packed order
+  unsigned long long* xs;  // gathered operands in packed order
+  uint8_t* heads;          // SEG_* flags in packed order
   SegPair* tile_agg;
   void* out;
 };
 
-// pass 1: gather addends, mark heads, reduce each tile
-template <bool FLOAT>
-__global__ void __launch_bounds__(kSegThreads) cumsum_gather_kernel(CumArgs a) {
+// pass 1: gather operands, mark heads, reduce each tile
+template <int OP>
+__global__ void __launch_bounds__(kSegThreads) cumop_gather_kernel(CumArgs a) {
   const int64_t base = (int64_t)blockIdx.x * kSegTile + (int64_t)threadIdx.x * kSegItems;
-  SegPair acc;
-  acc.v = 0; acc.f = 0;
+  SegPair acc = seg_identity<OP>();
   const int vsz = dsize(a.vdt);
 #pragma unroll
   for (int i = 0; i < kSegItems; i++) {
@@ -189,76 +214,84 @@ __global__ void __launch_bounds__(kSegThreads) cumsum_gather_kernel(CumArgs a) {
       uint32_t k = a.skeys[j];
       bool add = k != 0 && (!a.filter || a.filter[row]);
       bool head = j == 0 || a.skeys[j - 1] != k || (a.reset && add && a.reset[row]);
-      unsigned long long x = 0;
+      SegPair p = seg_identity<OP>();
+      p.f = head ? SEG_HEAD : 0u;
       if (add) {
         unsigned long long raw = load_raw1(a.values, vsz, row);
-        x = FLOAT ? (unsigned long long)__double_as_longlong(raw_to_f64(raw, a.vdt)) : (unsigned long long)raw_to_i64(raw, a.vdt);
+        if (OP == CUM_SUM_F || OP == CUM_PROD_F) p.v = f64_bits(raw_to_f64(raw, a.vdt));
+        else if (OP == CUM_SUM_I || OP == CUM_PROD_I) p.v = (unsigned long long)raw_to_i64(raw, a.vdt);
+        else if (raw_invalid(raw, a.vdt)) p.f |= a.skipna ? 0u : SEG_POISON;
+        else { p.v = raw_to_code(raw, a.vdt, OP == CUM_MAX); p.f |= SEG_HAS; }
       }
-      a.xs[j] = x;
-      a.heads[j] = head;
-      SegPair p;
-      p.v = x; p.f = head;
-      acc = seg_combine<FLOAT>(acc, p);
+      a.xs[j] = p.v;
+      a.heads[j] = (uint8_t)p.f;
+      acc = seg_combine<OP>(acc, p);
     }
   }
   SegPair total;
-  seg_block_exclusive<FLOAT>(acc, &total);
+  seg_block_exclusive<OP>(acc, &total);
   if (threadIdx.x == 0) a.tile_agg[blockIdx.x] = total;
 }
 
 // pass 2 (one block): tile_agg[t] <- combination of all tiles before t
-template <bool FLOAT>
-__global__ void __launch_bounds__(kSegThreads) cumsum_tiles_kernel(SegPair* tile_agg, int64_t ntiles) {
-  SegPair carry;
-  carry.v = 0; carry.f = 0;
+template <int OP>
+__global__ void __launch_bounds__(kSegThreads) cumop_tiles_kernel(SegPair* tile_agg, int64_t ntiles) {
+  SegPair carry = seg_identity<OP>();
   for (int64_t b = 0; b < ntiles; b += kSegThreads) {
     int64_t t = b + threadIdx.x;
-    SegPair x;
-    x.v = 0; x.f = 0;
+    SegPair x = seg_identity<OP>();
     if (t < ntiles) x = tile_agg[t];
     SegPair total;
-    SegPair ex = seg_block_exclusive<FLOAT>(x, &total);
-    if (t < ntiles) tile_agg[t] = seg_combine<FLOAT>(carry, ex);
-    carry = seg_combine<FLOAT>(carry, total);
+    SegPair ex = seg_block_exclusive<OP>(x, &total);
+    if (t < ntiles) tile_agg[t] = seg_combine<OP>(carry, ex);
+    carry = seg_combine<OP>(carry, total);
   }
 }
 
-// pass 3: running sums inside each tile, scattered to row order
-template <bool FLOAT>
-__global__ void __launch_bounds__(kSegThreads) cumsum_apply_kernel(CumArgs a) {
+// pass 3: running values inside each tile, scattered to row order
+template <int OP>
+__global__ void __launch_bounds__(kSegThreads) cumop_apply_kernel(CumArgs a) {
   const int64_t base = (int64_t)blockIdx.x * kSegTile + (int64_t)threadIdx.x * kSegItems;
-  unsigned long long x[kSegItems];
-  uint8_t h[kSegItems];
-  SegPair acc;
-  acc.v = 0; acc.f = 0;
+  SegPair p[kSegItems];
+  SegPair acc = seg_identity<OP>();
 #pragma unroll
   for (int i = 0; i < kSegItems; i++) {
     int64_t j = base + i;
-    x[i] = 0; h[i] = 0;
+    p[i] = seg_identity<OP>();
     if (j < a.n) {
-      x[i] = a.xs[j];
-      h[i] = a.heads[j];
-      SegPair p;
-      p.v = x[i]; p.f = h[i];
-      acc = seg_combine<FLOAT>(acc, p);
+      p[i].v = a.xs[j];
+      p[i].f = a.heads[j];
+      acc = seg_combine<OP>(acc, p[i]);
     }
   }
   SegPair total;
-  SegPair run = seg_combine<FLOAT>(a.tile_agg[blockIdx.x], seg_block_exclusive<FLOAT>(acc, &total));
-  unsigned long long cur = run.v;
+  SegPair run = seg_combine<OP>(a.tile_agg[blockIdx.x], seg_block_exclusive<OP>(acc, &total));
 #pragma unroll
   for (int i = 0; i < kSegItems; i++) {
     int64_t j = base + i;
     if (j < a.n) {
-      cur = h[i] ? x[i] : seg_add<FLOAT>(cur, x[i]);
+      run = seg_combine<OP>(run, p[i]);
       uint32_t row = a.igroup[j];
       unsigned long long raw;
       if (a.skeys[j] == 0) raw = invalid_raw(a.odt);
-      else if (a.odt == RTB_F32) raw = __float_as_uint((float)__longlong_as_double((long long)cur));
-      else raw = cur;
+      else if (OP >= CUM_MIN) {
+        raw = (run.f & (SEG_HAS | SEG_POISON)) == SEG_HAS ? code_to_raw(run.v, a.vdt, OP == CUM_MAX) : invalid_raw(a.odt);
+      } else if (a.odt == RTB_F32) raw = __float_as_uint((float)bits_f64(run.v));
+      else raw = run.v;
       store_raw(a.out, a.odt, row, raw);
     }
   }
+}
+
+template <int OP>
+static int cumop_launch(const CumArgs& a, int64_t ntiles, cudaStream_t stream) {
+  cumop_gather_kernel<OP><<<(unsigned)ntiles, kSegThreads, 0, stream>>>(a);
+  RTB_LAUNCH_CHECK();
+  cumop_tiles_kernel<OP><<<1, kSegThreads, 0, stream>>>(a.tile_agg, ntiles);
+  RTB_LAUNCH_CHECK();
+  cumop_apply_kernel<OP><<<(unsigned)ntiles, kSegThreads, 0, stream>>>(a);
+  RTB_LAUNCH_CHECK();
+  return RTB_OK;
 }
 
 struct CumLayout {
@@ -369,11 +402,17 @@ extern "C" int rtb_groupby_pick(const void* values, int vdt, int32_t itemsize, c
   return RTB_OK;
 }
 
-extern "C" int rtb_cumsum_out_dtype(int vdt) {
+extern "C" int rtb_cumop_out_dtype(int func, int vdt) {
   if (vdt < RTB_BOOL || vdt > RTB_F64) return RTB_ERR_UNSUPPORTED;
-  if (vdt == RTB_F32 || vdt == RTB_F64 || vdt == RTB_U64) return vdt;
-  return RTB_I64;
+  switch (func) {
+    case RTB_GB_CUMSUM: case RTB_GB_CUMPROD:
+      if (vdt == RTB_F32 || vdt == RTB_F64 || vdt == RTB_U64) return vdt;
+      return RTB_I64;
+    case RTB_GB_CUMMIN: case RTB_GB_CUMMAX: case RTB_GB_CUMNANMIN: case RTB_GB_CUMNANMAX: return vdt;
+    default: return RTB_ERR_UNSUPPORTED;
+  }
 }
+extern "C" int rtb_cumsum_out_dtype(int vdt) { return rtb_cumop_out_dtype(RTB_GB_CUMSUM, vdt); }
 
 extern "C" size_t rtb_cumsum_workspace_bytes(int64_t nrows, int64_t unique_rows) {
   (void)unique_rows;
@@ -381,14 +420,14 @@ extern "C" size_t rtb_cumsum_workspace_bytes(int64_t nrows, int64_t unique_rows)
   return cum_layout(nullptr, 0, nrows).bytes + 256;
 }
 
-extern "C" int rtb_groupby_cumsum(const void* values, int vdt, const void* ikey, int kdt, int64_t nrows, int64_t unique_rows,
-                                  const uint8_t* filter, const uint8_t* reset_filter, void* out, void* workspace,
-                                  size_t workspace_bytes, void* stream_) {
+extern "C" int rtb_groupby_cumop(int func, const void* values, int vdt, const void* ikey, int kdt, int64_t nrows,
+                                 int64_t unique_rows, const uint8_t* filter, const uint8_t* reset_filter, void* out,
+                                 void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   RTB_ARG(is_ikey_dtype(kdt), "EmaAll32: ikey must be int8/16/32/64");
-  int odt = rtb_cumsum_out_dtype(vdt);
+  int odt = rtb_cumop_out_dtype(func, vdt);
   if (odt < 0) {
-    set_error("EmaAll32: cumsum is not provided for dtype %d", vdt);
+    set_error("EmaAll32: function %d is not provided for dtype %d", func, vdt);
     return RTB_ERR_UNSUPPORTED;
   }
   RTB_ARG(nrows >= 0 && nrows <= 2147483646ll && unique_rows >= 0, "EmaAll32: bad sizes");
@@ -402,27 +441,27 @@ extern "C" int rtb_groupby_cumsum(const void* values, int vdt, const void* ikey,
   if (rc != RTB_OK) return rc;
   CumArgs a;
   a.values = values; a.vdt = vdt; a.odt = odt; a.skeys = skeys; a.igroup = ig; a.filter = filter; a.reset = reset_filter;
+  a.skipna = func == RTB_GB_CUMNANMIN || func == RTB_GB_CUMNANMAX;
   a.n = nrows; a.xs = L.xs; a.heads = L.heads; a.tile_agg = L.tile_agg; a.out = out;
   const int64_t ntiles = (nrows + kSegTile - 1) / kSegTile;
   const bool fl = vdt == RTB_F32 || vdt == RTB_F64;
   prof_begin(PROF_SEGSCAN, stream);
-  if (fl) {
-    cumsum_gather_kernel<true><<<(unsigned)ntiles, kSegThreads, 0, stream>>>(a);
-    RTB_LAUNCH_CHECK();
-    cumsum_tiles_kernel<true><<<1, kSegThreads, 0, stream>>>(L.tile_agg, ntiles);
-    RTB_LAUNCH_CHECK();
-    cumsum_apply_kernel<true><<<(unsigned)ntiles, kSegThreads, 0, stream>>>(a);
-    RTB_LAUNCH_CHECK();
-  } else {
-    cumsum_gather_kernel<false><<<(unsigned)ntiles, kSegThreads, 0, stream>>>(a);
-    RTB_LAUNCH_CHECK();
-    cumsum_tiles_kernel<false><<<1, kSegThreads, 0, stream>>>(L.tile_agg, ntiles);
-    RTB_LAUNCH_CHECK();
-    cumsum_apply_kernel<false><<<(unsigned)ntiles, kSegThreads, 0, stream>>>(a);
-    RTB_LAUNCH_CHECK();
+  switch (func) {
+    case RTB_GB_CUMSUM: rc = fl ? cumop_launch<CUM_SUM_F>(a, ntiles, stream) : cumop_launch<CUM_SUM_I>(a, ntiles, stream); break;
+    case RTB_GB_CUMPROD: rc = fl ? cumop_launch<CUM_PROD_F>(a, ntiles, stream) : cumop_launch<CUM_PROD_I>(a, ntiles, stream); break;
+    case RTB_GB_CUMMIN: case RTB_GB_CUMNANMIN: rc = cumop_launch<CUM_MIN>(a, ntiles, stream); break;
+    default: rc = cumop_launch<CUM_MAX>(a, ntiles, stream); break;
   }
+  if (rc != RTB_OK) return rc;
   prof_end(PROF_SEGSCAN, stream, (uint64_t)nrows);
   return RTB_OK;
+}
+
+extern "C" int rtb_groupby_cumsum(const void* values, int vdt, const void* ikey, int kdt, int64_t nrows, int64_t unique_rows,
+                                  const uint8_t* filter, const uint8_t* reset_filter, void* out, void* workspace,
+                                  size_t workspace_bytes, void* stream_) {
+  return rtb_groupby_cumop(RTB_GB_CUMSUM, values, vdt, ikey, kdt, nrows, unique_rows, filter, reset_filter, out, workspace,
+                           workspace_bytes, stream_);
 }
 
 extern "C" int rtb_make_ifirst(const void* ikey, int kdt, int64_t nrows, int64_t n, const uint8_t* filter, int mode,

@@ -447,10 +447,15 @@ def GroupByAllPack32(values, ikey, iGroup, iFirstGroup, nCountGroup, unique_rows
 
 
 # ==================================================================================================
-# a9  rc.EmaAll32 (riptable/rt_grouping.py:3430), GB_CUMSUM
+# a9 / 8f.2  rc.EmaAll32 (riptable/rt_grouping.py:3430): GB_CUMSUM, GB_CUMPROD, GB_CUM[NAN]MIN, GB_CUM[NAN]MAX
+_CUM_FUNCS = (GB_FUNCTIONS.GB_CUMSUM, GB_FUNCTIONS.GB_CUMPROD, GB_FUNCTIONS.GB_CUMNANMAX, GB_FUNCTIONS.GB_CUMNANMIN,
+              GB_FUNCTIONS.GB_CUMMAX, GB_FUNCTIONS.GB_CUMMIN)
+
+
 def EmaAll32(values, ikey, unique_rows, funcNum, func_param):
-    if int(funcNum) != GB_FUNCTIONS.GB_CUMSUM:
+    if int(funcNum) not in _CUM_FUNCS:
         raise NotImplementedError(f"EmaAll32: function {int(funcNum)} is outside this build's hot path")
+    func = int(funcNum)
     values = _as_list(values)
     filt = reset = None
     if isinstance(func_param, (tuple, list)) and len(func_param) >= 4:
@@ -463,16 +468,16 @@ def EmaAll32(values, ikey, unique_rows, funcNum, func_param):
     for v in values:
         d = _to_dev(v)
         vcode = dtype_code(d.dtype) if d.dtype.kind in "biuf" and d.dtype != np.float16 else RTB_BYTES
-        ocode = lib.rtb_cumsum_out_dtype(vcode) if vcode < RTB_BYTES else -1
+        ocode = lib.rtb_cumop_out_dtype(func, vcode) if vcode < RTB_BYTES else -1
         if ocode < 0:
             out.append(None)
             continue
         res = DevArray.empty(k.n, code_dtype(ocode))
         ws = _ws(lib.rtb_cumsum_workspace_bytes(k.n, int(unique_rows)))
-        check(lib.rtb_groupby_cumsum(C.c_void_p(d.ptr), vcode, C.c_void_p(k.ptr), dtype_code(k.dtype), k.n, int(unique_rows),
-                                     C.c_void_p(fdev.ptr) if fdev is not None else None,
-                                     C.c_void_p(rdev.ptr) if rdev is not None else None,
-                                     C.c_void_p(res.ptr), C.c_void_p(ws.data_ptr()), ws.numel(), _stream()))
+        check(lib.rtb_groupby_cumop(func, C.c_void_p(d.ptr), vcode, C.c_void_p(k.ptr), dtype_code(k.dtype), k.n,
+                                    int(unique_rows), C.c_void_p(fdev.ptr) if fdev is not None else None,
+                                    C.c_void_p(rdev.ptr) if rdev is not None else None,
+                                    C.c_void_p(res.ptr), C.c_void_p(ws.data_ptr()), ws.numel(), _stream()))
         out.append(_from_dev(res, device_mode))
     return out
 

@@ -148,6 +148,63 @@ def test_cumsum_kat(rc):
     assert rc.EmaAll32([s], ikey, 2, 300, (0.0, None, None, None))[0] is None
 
 
+# ---------------------------------------------------------------------------------------------------- 8f.2
+_ALL_NUM = [np.bool_, np.int8, np.uint8, np.int16, np.uint16, np.int32, np.uint32, np.int64, np.uint64, np.float32, np.float64]
+
+
+@pytest.mark.parametrize("vdt", _ALL_NUM)
+@pytest.mark.parametrize("nb,bad_frac", [(1, 0.0), (40, 0.02), (25_000, 0.3), (40, 1.0)])
+def test_cum_min_max(rc, vdt, nb, bad_frac):
+    rng = np.random.default_rng(nb * 7 + int(bad_frac * 100))
+    n = 150_001
+    ikey = rng.integers(0, nb + 1, n).astype(np.int32)
+    dt = np.dtype(vdt)
+    if dt.kind == "f":
+        v = rng.normal(0, 1e4, n).astype(vdt)
+        v[rng.random(n) < bad_frac / 2] = np.inf
+        v[rng.random(n) < bad_frac / 2] = -np.inf
+    elif dt.kind == "b":
+        v = rng.integers(0, 2, n).astype(vdt)
+    else:
+        info = np.iinfo(dt)
+        v = rng.integers(info.min, info.max, n, dtype=dt, endpoint=True)
+    if dt.kind != "b":
+        v[rng.random(n) < bad_frac] = orc.invalid_for(dt)
+    filt = rng.random(n) < 0.7
+    reset = rng.random(n) < 0.01
+    for func in (306, 307, 308, 309):
+        for fp in [(0.0, None, None, None), (0.0, None, filt, reset)]:
+            got = rc.EmaAll32([v], ikey, nb, func, fp)[0]
+            exp = orc.EmaAll32([v], ikey, nb, func, fp)[0]
+            assert got.dtype == exp.dtype == dt
+            np.testing.assert_array_equal(got, exp)
+
+
+@pytest.mark.parametrize("vdt", [np.bool_, np.int8, np.int32, np.int64, np.uint64, np.float32, np.float64])
+@pytest.mark.parametrize("nb", [1, 40, 25_000])
+def test_cumprod(rc, vdt, nb):
+    rng = np.random.default_rng(nb + 5)
+    n = 120_007
+    ikey = rng.integers(0, nb + 1, n).astype(np.int32)
+    if np.dtype(vdt).kind == "f":
+        v = np.exp(rng.normal(0, 0.01, n)).astype(vdt)  # running products stay in range
+    elif np.dtype(vdt).kind == "b":
+        v = (rng.random(n) < 0.999).astype(vdt)
+    else:
+        v = rng.integers(1, 4, n).astype(vdt)  # int64 products wrap; the wrap is part of the contract
+    filt = rng.random(n) < 0.7
+    reset = rng.random(n) < 0.05
+    for fp in [(0.0, None, None, None), (0.0, None, filt, reset)]:
+        got = rc.EmaAll32([v], ikey, nb, 302, fp)[0]
+        exp = orc.EmaAll32([v], ikey, nb, 302, fp)[0]
+        assert got.dtype == exp.dtype
+        if exp.dtype.kind == "f":
+            # the scan multiplies in tree order: a few ulp per 2x of segment length
+            np.testing.assert_allclose(got, exp, rtol=2e-5 if exp.dtype == np.float32 else 1e-11, equal_nan=True)
+        else:
+            np.testing.assert_array_equal(got, exp)
+
+
 # ---------------------------------------------------------------------------------------------------- a10
 def test_makeifirst_ilast_inext(rc):
     rng = np.random.default_rng(8)

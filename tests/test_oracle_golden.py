@@ -172,6 +172,62 @@ def test_cumsum_kat():
     assert out[1].tolist() == [50, inv, 72, inv, 162, inv, 145, inv, 260, inv, 376, inv]
 
 
+def _as_float_with_nan(a):
+    """FastArray.astype(float): integer sentinels become NaN (what the reference test compares in)."""
+    out = a.astype(np.float64)
+    if a.dtype.kind in "iu":
+        out[a == orc.invalid_for(a.dtype)] = np.nan
+    return out
+
+
+@pytest.mark.parametrize("N,N_cat", [(1, 1), (5, 10), (97, 10), (2643, 45)])
+@pytest.mark.parametrize("nan_fraction", [0.0, 0.5, 1.0])
+@pytest.mark.parametrize("skipna", [True, False])
+def test_cum_min_max_replays_reference_test(N, N_cat, nan_fraction, skipna):
+    # tests/test_groupbyops.py:458-538, with numpy in place of Dataset / Categorical
+    rng = np.random.default_rng((N * N_cat * int(nan_fraction * 1000)) % 10_000)
+    categ = rng.integers(0, N_cat, size=N)
+    g = orc.groupbyhash(categ)
+    ik, U = g["iKey"], g["unique_count"]
+    cols = []
+    for dt in [np.float32, np.float64]:
+        d = rng.normal(rng.uniform(-10_000, 10_000), rng.uniform(0.0, 10_000), size=N).astype(dt)
+        if nan_fraction > 0:
+            d[rng.random(N) < nan_fraction / 3] = np.nan
+            d[rng.random(N) < nan_fraction / 3] = np.inf
+            d[rng.random(N) < nan_fraction / 3] = -np.inf
+        cols.append(d)
+    for dt in [np.int8, np.uint8, np.int16, np.uint16, np.int32, np.uint32, np.int64, np.uint64]:
+        d = rng.integers(-10_000, 10_000, size=N).astype(dt)
+        d[rng.random(N) < nan_fraction] = orc.invalid_for(dt)
+        cols.append(d)
+    cols.append(rng.choice([True, False], size=N))
+    fmin, fmax = (orc.GB_CUMNANMIN, orc.GB_CUMNANMAX) if skipna else (orc.GB_CUMMIN, orc.GB_CUMMAX)
+    cmin = orc.EmaAll32(cols, ik, U, fmin, (0.0, None, None, None))
+    cmax = orc.EmaAll32(cols, ik, U, fmax, (0.0, None, None, None))
+    for c, lo, hi in zip(cols, cmin, cmax):
+        assert lo.dtype == c.dtype and hi.dtype == c.dtype
+        for b in range(1, U + 1):
+            sl = _as_float_with_nan(c[ik == b])
+            with np.errstate(invalid="ignore"):
+                if skipna:
+                    elo, ehi = np.fmin.accumulate(sl), np.fmax.accumulate(sl)
+                else:
+                    elo, ehi = np.minimum.accumulate(sl), np.maximum.accumulate(sl)
+            np.testing.assert_array_equal(_as_float_with_nan(lo[ik == b]), elo)
+            np.testing.assert_array_equal(_as_float_with_nan(hi[ik == b]), ehi)
+
+
+def test_cumprod_small():
+    ik = np.array([1, 2, 1, 0, 2, 1], dtype=np.int8)
+    v = np.array([2, 3, 4, 9, 5, 6], dtype=np.int32)
+    out = orc.EmaAll32([v, v.astype(np.float32)], ik, 2, orc.GB_CUMPROD, (0.0, None, None, None))
+    assert out[0].dtype == np.int64 and out[0].tolist() == [2, 3, 8, np.iinfo(np.int64).min, 15, 48]
+    assert out[1].dtype == np.float32 and out[1][[0, 1, 2, 4, 5]].tolist() == [2.0, 3.0, 8.0, 15.0, 48.0] and np.isnan(out[1][3])
+    f = np.array([True, True, False, True, True, True])
+    assert orc.EmaAll32([v], ik, 2, orc.GB_CUMPROD, (0.0, None, f, None))[0].tolist() == [2, 3, 2, np.iinfo(np.int64).min, 15, 12]
+
+
 def test_cutoffs_kat():
     # tests/test_pgroupby.py:7-86
     rng = np.random.default_rng(0)

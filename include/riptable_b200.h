@@ -204,6 +204,13 @@ int rtb_reverse_shuffle(const int32_t* perm, int64_t n, int32_t* out, void* stre
 /* ---- multi-GPU helper: out[i] = map[ikey[i]] (rc.ReIndexGroups semantics, riptable/rt_grouping.py:378-407) */
 int rtb_remap_ikey(const int32_t* ikey, int64_t nrows, const int32_t* map, int64_t nmap, int32_t* out, void* stream);
 
+/* ---- 8f.3: rc.ReIndexGroups(ikey, uikey, u_cutoffs, i_cutoffs) — riptable/rt_grouping.py:378 (semantics spelled out by
+ * the Python fallback at :380-407).  Partition p owns ikey rows [i_cutoffs[p-1], i_cutoffs[p]) and uikey entries
+ * [u_cutoffs[p-1], u_cutoffs[p]); out[r] = uikey_slice_p[ikey[r] - 1], and 0 stays 0.  Rows past the last cutoff -> 0. */
+int rtb_reindex_groups(const int32_t* ikey, int64_t nrows, const int32_t* uikey, int64_t nuikey,
+                       const int64_t* u_cutoffs_host, const int64_t* i_cutoffs_host, int64_t ncutoffs, int32_t* out,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -645,3 +645,22 @@ def IsMember32(a, b, h=2, hint_size=0):
 def MultiKeyIsMember32(a_tuple, b_tuple, hint_size=0):
     """rt_numpy.py:1325: rc.MultiKeyIsMember32((a_cols,), (b_cols,), hint_size) -- tuple equality across the columns."""
     return _ismember_cols(list(a_tuple[0]), list(b_tuple[0]))
+
+
+# ----------------------------------------------------------------------------------------------
+# 8f.3  rc.ReIndexGroups (rt_grouping.py:378; restates the Python fallback at rt_grouping.py:380-407, base_index 1)
+def ReIndexGroups(ikey, uikey, u_cutoffs, i_cutoffs):
+    """Per partition p: newikey[rows of p] = uikey[entries of p][old - 1]; a 0 stays 0."""
+    ikey = np.asarray(ikey)
+    uikey = np.asarray(uikey)
+    new = np.zeros(len(ikey), dtype=ikey.dtype)
+    start = starti = 0
+    for stop, stopi in zip(np.asarray(u_cutoffs, np.int64), np.asarray(i_cutoffs, np.int64)):
+        us = uikey[start:stop]
+        old = ikey[starti:stopi].astype(np.int64)
+        ok = (old > 0) & (old <= len(us))
+        seg = np.zeros(len(old), dtype=ikey.dtype)
+        seg[ok] = us[old[ok] - 1]
+        new[starti:stopi] = seg
+        start, starti = stop, stopi
+    return new

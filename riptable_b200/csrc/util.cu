@@ -224,6 +224,17 @@ __global__ void __launch_bounds__(256) remap_kernel(const int32_t* __restrict__ 
   }
 }
 
+// one partition of rc.ReIndexGroups: base-1 local bins -> global bins through that partition's slice of uikey
+__global__ void __launch_bounds__(256) reindex_kernel(const int32_t* __restrict__ ikey, int64_t n,
+                                                       const int32_t* __restrict__ uikey, int64_t nu,
+                                                       int32_t* __restrict__ out) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int32_t k = ikey[i];
+    out[i] = (k > 0 && k <= nu) ? __ldg(uikey + (k - 1)) : 0;
+  }
+}
+
 }  // namespace rtb
 
 using namespace rtb;
@@ -286,6 +297,29 @@ int rtb_remap_ikey(const int32_t* ikey, int64_t nrows, const int32_t* map, int64
   RTB_ARG(((uintptr_t)ikey % 16) == 0 && ((uintptr_t)out % 16) == 0, "remap: buffers must be 16-byte aligned");
   remap_kernel<<<grid_for(nrows, 256, 4, 32), 256, 0, (cudaStream_t)stream>>>(ikey, nrows, map, nmap, out);
   RTB_LAUNCH_CHECK();
+  return RTB_OK;
+}
+
+int rtb_reindex_groups(const int32_t* ikey, int64_t nrows, const int32_t* uikey, int64_t nuikey,
+                       const int64_t* u_cutoffs_host, const int64_t* i_cutoffs_host, int64_t ncutoffs, int32_t* out,
+                       void* stream) {
+  RTB_ARG(nrows >= 0 && nuikey >= 0 && ncutoffs >= 0, "ReIndexGroups: bad sizes");
+  RTB_ARG(ncutoffs == 0 || (u_cutoffs_host && i_cutoffs_host), "ReIndexGroups: null cutoffs");
+  int64_t ustart = 0, istart = 0;
+  for (int64_t p = 0; p < ncutoffs; p++) {
+    int64_t ustop = u_cutoffs_host[p], istop = i_cutoffs_host[p];
+    RTB_ARG(ustop >= ustart && ustop <= nuikey && istop >= istart && istop <= nrows,
+            "ReIndexGroups: cutoffs must be non-decreasing and within the arrays");
+    if (istop > istart) {
+      RTB_ARG(ikey && out && (uikey || ustop == ustart), "ReIndexGroups: null pointer");
+      reindex_kernel<<<grid_for(istop - istart, 256, 4, 32), 256, 0, (cudaStream_t)stream>>>(
+          ikey + istart, istop - istart, uikey + ustart, ustop - ustart, out + istart);
+      RTB_LAUNCH_CHECK();
+    }
+    ustart = ustop;
+    istart = istop;
+  }
+  if (istart < nrows) RTB_CUDA(cudaMemsetAsync(out + istart, 0, sizeof(int32_t) * (size_t)(nrows - istart), (cudaStream_t)stream));
   return RTB_OK;
 }
 

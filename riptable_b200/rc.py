@@ -612,7 +612,30 @@ def ReverseShuffle(perm):
     return _from_dev(out, device_mode)
 
 
-__all__ = ["GroupByStream", "LexPartition", "MultiKeyGroupBy32", "CombineFilter", "CombineAccum1Filter", "CombineAccum2Filter", "GroupByAll32", "BinCount",
+# 8f.3  rc.ReIndexGroups (riptable/rt_grouping.py:378; semantics: the Python fallback at :380-407)
+def ReIndexGroups(ikey, uikey, u_cutoffs, i_cutoffs):
+    device_mode = _is_device(ikey) or _is_device(uikey)
+    k = _to_dev(ikey)
+    u = _to_dev(uikey)
+    if k.dtype.kind != "i" or u.dtype.kind != "i":
+        raise TypeError("ReIndexGroups: ikey and uikey must be signed integer arrays")
+    kdt = k.dtype
+    if k.dtype != np.dtype(np.int32):
+        k = _to_dev(k.numpy().astype(np.int32))
+    if u.dtype != np.dtype(np.int32):
+        u = _to_dev(u.numpy().astype(np.int32))
+    uc = np.ascontiguousarray(np.asarray(u_cutoffs, dtype=np.int64))
+    ic = np.ascontiguousarray(np.asarray(i_cutoffs, dtype=np.int64))
+    if uc.ndim != 1 or uc.shape != ic.shape:
+        raise ValueError("ReIndexGroups: u_cutoffs and i_cutoffs must be 1-d arrays of the same length")
+    out = DevArray.empty(k.n, np.int32)
+    check(lib.rtb_reindex_groups(C.c_void_p(k.ptr), k.n, C.c_void_p(u.ptr), u.n, uc.ctypes.data_as(C.POINTER(C.c_int64)),
+                                 ic.ctypes.data_as(C.POINTER(C.c_int64)), len(uc), C.c_void_p(out.ptr), _stream()))
+    res = _from_dev(out, device_mode)
+    return res if device_mode or kdt == np.dtype(np.int32) else res.astype(kdt)
+
+
+__all__ = ["GroupByStream", "ReIndexGroups", "LexPartition", "MultiKeyGroupBy32", "CombineFilter", "CombineAccum1Filter", "CombineAccum2Filter", "GroupByAll32", "BinCount",
            "GroupFromBinCount", "GroupByPack32", "GroupByAllPack32", "EmaAll32", "MakeiFirst", "MakeiNext", "LexSort32",
            "LexSort64", "GroupFromLexSort", "ReverseShuffle", "IsMember32", "MultiKeyIsMember32", "LedgerFunction"]
 

@@ -76,3 +76,13 @@ def groupbylex(rc, list_arrays, filter=None, cutoffs=None, base_index=1, rec=Fal
         iFirstGroup[0] = len(index)
     return {"iKey": iKey, "iFirstKey": iFirstKey, "unique_count": len(iFirstKey), "iGroup": iGroup,
             "iFirstGroup": iFirstGroup, "nCountGroup": nCountGroup}
+
+
+def hstack_reindex(mod_groupby, mod_reindex, keys, cuts):
+    """The hstack_groupings recipe (rt_grouping.py:277-413): per-partition grouping -> group the stacked uniques ->
+    ReIndexGroups.  Returns (new ikey, global unique count)."""
+    ik, (ifk, ucuts), _ = mod_groupby([keys], 0, None, 2, cutoffs=cuts)
+    offs = np.repeat(np.r_[0, cuts[:-1]], np.diff(np.r_[0, ucuts]))
+    stacked = np.asarray(keys)[np.asarray(ifk, np.int64) + offs]  # iFirstKey is partition-relative
+    uik, _, U = mod_groupby([stacked], 0, None, 2)
+    return mod_reindex(ik, uik, ucuts, cuts), U

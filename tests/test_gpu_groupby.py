@@ -118,6 +118,27 @@ def test_projections_fixture(rc):
     assert u == 455654
 
 
+def test_reindex_groups(rc):
+    # 8f.3: the hstack_groupings recipe (rt_grouping.py:277-413) must land on the global grouping
+    import rt_glue
+    rng = np.random.default_rng(3)
+    keys = rng.integers(0, 50_000, 700_001)
+    cuts = np.array([1, 1, 40_000, 95_000, 500_003, 700_001], dtype=np.int64)
+    new, U = rt_glue.hstack_reindex(rc.MultiKeyGroupBy32, rc.ReIndexGroups, keys, cuts)
+    gik, _, gU = orc.MultiKeyGroupBy32([keys], 0, None, 2)
+    assert U == gU and np.array_equal(new, gik)
+    ik, (ifk, ucuts), _ = orc.MultiKeyGroupBy32([keys], 0, None, 2, cutoffs=cuts)
+    uik = rng.integers(1, 1000, int(ucuts[-1])).astype(np.int32)
+    ik = ik.copy()
+    ik[rng.random(len(ik)) < 0.1] = 0
+    for dt in (np.int32, np.int64):
+        got = rc.ReIndexGroups(ik.astype(dt), uik, ucuts, cuts)
+        exp = orc.ReIndexGroups(ik.astype(dt), uik, ucuts, cuts)
+        assert got.dtype == exp.dtype and np.array_equal(got, exp)
+    out = rc.ReIndexGroups(np.array([2, 0, 1, 1, 2], np.int32), np.array([7, 9, 4], np.int32), [2, 3], [3, 4])
+    assert out.tolist() == [9, 0, 7, 4, 0]
+
+
 def test_cutoffs(rc):
     # tests/test_pgroupby.py:7-86
     rng = np.random.default_rng(0)

@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from oracle import riptide_oracle as orc
+import rt_glue
 
 
 @pytest.fixture(scope="module")
@@ -248,6 +249,18 @@ def test_cutoffs_kat():
     pgb = orc.groupbyhash([np.ones(10)], filter=(a % 2).astype(bool), cutoffs=a.astype(np.int64) + 1)
     assert np.array_equal(pgb["iKey"], a % 2)
     assert pgb["iFirstKey"][1].tolist() == [0, 1, 1, 2, 2, 3, 3, 4, 4, 5]
+
+
+def test_reindex_groups_equals_global_grouping():
+    rng = np.random.default_rng(3)
+    keys = rng.integers(0, 500, 20_000)
+    cuts = np.array([1, 1, 4_000, 9_500, 20_000], dtype=np.int64)
+    new, U = rt_glue.hstack_reindex(orc.MultiKeyGroupBy32, orc.ReIndexGroups, keys, cuts)
+    gik, _, gU = orc.MultiKeyGroupBy32([keys], 0, None, 2)
+    assert U == gU and np.array_equal(new, gik)
+    # a 0 (filtered row) stays 0; rows past the last cutoff come back 0
+    out = orc.ReIndexGroups(np.array([2, 0, 1, 1, 2], np.int32), np.array([7, 9, 4], np.int32), [2, 3], [3, 4])
+    assert out.tolist() == [9, 0, 7, 4, 0]
 
 
 def test_makeifirst_kat():

@@ -63,15 +63,49 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled from a thread every ~2 ms (an
+    `nvidia-smi -lms` child needs about a second to start on an 8-GPU box, longer than the timed region), with the
+    nvidia-smi loop as the fallback when the NVML binding is missing."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, index, uuid=None):
+        self.index, self.uuid, self.proc, self.lines = index, uuid, None, []
+        self.nvml = self.handle = None
+        self.sm, self.mx, self.reason_bits, self.run = [], None, 0, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+                except Exception:
+                    h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml, self.handle = pynvml, h
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        nv, h = self.nvml, self.handle
+        while self.run:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nvml:
+            self.run = True
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "10", "-i", str(self.index)],
@@ -86,6 +120,14 @@ class ClockSampler:
             self.lines.append(ln.strip())
 
     def stop(self):
+        if self.nvml:
+            self.run = False
+            self.t.join(timeout=1)
+            nv = self.nvml
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            reasons = sorted(k for k, b in bits.items() if self.reason_bits & b)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx,
+                    "samples": len(self.sm), "reasons": reasons, "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -108,7 +150,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -136,7 +178,8 @@ def cpu_arm(rows, uniques, steps, warmup, sample_rows=0):
     from oracle import c_oracle
 
     c_oracle.build()
-    threads = c_oracle.max_threads()
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every core this process may run on
+    threads = max(1, len(os.sched_getaffinity(0)))
     rng = np.random.default_rng(12345)
     uvals = rng.integers(-(2**63), 2**63 - 1, uniques, dtype=np.int64)
 
@@ -247,7 +290,11 @@ def main():
     _lib.lib.rtb_profile_enable(1)
     _lib.lib.rtb_profile_reset()
     launches0 = _lib.launch_count()
-    sampler = ClockSampler(local)
+    try:
+        dev_uuid = torch.cuda.get_device_properties(local).uuid
+    except Exception:
+        dev_uuid = None
+    sampler = ClockSampler(local, dev_uuid)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -362,7 +409,9 @@ def main():
                 pass
     step_bytes = (ALG_BYTES_HASH + ALG_BYTES_SUM) * rows
     cb = None
-    if not a.no_cpu:
+    if world > 1:
+        cb = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "timed at N=1 only (see --impl reference)"}
+    elif not a.no_cpu:  # the CPU leg is an N=1 item (rank 0 alone); --impl reference times it at any N
         try:
             cb = cpu_arm(rows, U, 2, 1, a.cpu_rows)
             cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -165,6 +165,12 @@ class CudaOps:
     def lex_partition(self, cols, splitters, splitter_rows, row_offset, ascending):
         return self.rc.LexPartition(list(cols), list(splitters), splitter_rows, row_offset, ascending)
 
+    def group_from_sorted(self, cols):
+        """rc.GroupFromLexSort over columns that are already in sorted order -> (bin per position, base 1;
+        first position of each bin; nCountGroup)."""
+        ident = torch.arange(cols[0].n, dtype=torch.int32, device=self.device)
+        return self.rc.GroupFromLexSort(ident, list(cols))
+
     def rows_col(self, rows_i64):
         """An int64 tensor of global row ids as a key column."""
         return self.rc._to_dev(rows_i64.contiguous())
@@ -721,6 +727,11 @@ def sharded_lexsort(ops, key_cols, ascending=True, group=None):
     keys (stable: ties are broken by global row id).  Steps: sample the shards, all-gather the samples, every rank
     picks the same G-1 splitters, rows are routed by `rtb_lex_partition`, bucketed (rc.BinCount pack), exchanged with
     one all-to-all per column, and the received rows are sorted locally with the global row id as the last key."""
+    return _sample_sort(ops, key_cols, ascending, group, False)[0]
+
+
+def _sample_sort(ops, key_cols, ascending, group, want_cols):
+    """-> (sorted global row ids of this rank's slice, the key columns in that order (want_cols), row offsets, shard sizes)"""
     G, rank = _world(group)
     cols = [ops.as_col(c) for c in key_cols]
     n = ops.nrows(cols[0])
@@ -734,7 +745,8 @@ def sharded_lexsort(ops, key_cols, ascending=True, group=None):
         row_off[r] = row_off[r - 1] + ns[r - 1]
     dev = meta.device
     if G == 1:
-        return ops.to_torch(ops.lexsort(cols, asc)).to(torch.int64)
+        perm = ops.to_torch(ops.lexsort(cols, asc)).to(torch.int64)
+        return perm, ([ops.take_rows(c, perm) for c in cols] if want_cols else None), row_off, ns
 
     # 1. samples -> splitters (identical on every rank)
     s_n = min(n, SAMPLES_PER_RANK)
@@ -780,9 +792,118 @@ def sharded_lexsort(ops, key_cols, ascending=True, group=None):
 
     # 4. local sort of what arrived; the global row id is the least significant key
     if m == 0:
-        return recv_rows
+        return recv_rows, (recv_cols if want_cols else None), row_off, ns
     perm = ops.to_torch(ops.lexsort([ops.rows_col(recv_rows)] + recv_cols, [True] + asc)).to(torch.int64)
-    return recv_rows[perm]
+    return recv_rows[perm], ([ops.take_rows(c, perm) for c in recv_cols] if want_cols else None), row_off, ns
+
+
+def sharded_group_from_lexsort(ops, key_cols, ascending=True, group=None, replicate=True):
+    """rc.GroupFromLexSort over row-sharded keys: sample-sort the rows, flag the bin boundaries inside
+    each rank's sorted slice, settle the one boundary between neighbouring slices by exchanging their first / last key
+    rows, number the bins by an exclusive scan of the per-rank distinct counts, and send every (row, bin) pair back to
+    the rank that owns the row.  Bins are numbered in sorted order, base 1, exactly as the single-GPU call numbers them.
+    -> dict: ikey (int32, this rank's rows), unique_count, igroup_slice (this rank's slice of the sorted global row
+    ids), bin_lo / nCountGroup_owned / iFirstKey_owned (the bins that START in this rank's slice: global bin ids
+    bin_lo+1 ...), and with replicate=True the full nCountGroup [U+1] and iFirstKey [U] (global row ids)."""
+    G, rank = _world(group)
+    rows, scols, row_off, ns = _sample_sort(ops, key_cols, ascending, group, True)
+    m = int(rows.numel())
+    dev = rows.device
+    n_local = ns[rank]
+
+    # 1. bins inside the slice (identity iGroup: the columns are already in sorted order)
+    if m:
+        lbin, lfirst, lcount = (ops.to_torch(x) for x in ops.group_from_sorted(scols))
+        lbin, lfirst, lcount = lbin.to(torch.int64), lfirst.to(torch.int64), lcount.to(torch.int64)
+        uloc = int(lfirst.numel())
+        ends = torch.tensor([0, m - 1], dtype=torch.int64, device=dev)
+        edge = torch.cat([ops.col_bytes(ops.take_rows(c, ends)).reshape(2, -1) for c in scols], dim=1).contiguous()
+        first_cnt, last_cnt = int(lcount[1]), int(lcount[uloc])
+    else:
+        uloc, first_cnt, last_cnt = 0, 0, 0
+        edge = None
+    row_bytes = sum(ops.col_dtype(c).itemsize for c in scols)
+
+    # 2. neighbour boundaries: every rank sees every slice's (size, local bins, edge counts, first / last key row)
+    meta = ops.tensor([m, uloc, first_cnt, last_cnt], dtype=torch.int64)
+    allmeta = meta.new_empty(4 * G)
+    tdist.all_gather_into_tensor(allmeta, meta, group=group)
+    allmeta = allmeta.cpu().view(G, 4).tolist()
+    payload = edge.reshape(-1) if m else ops.tensor([0], dtype=torch.uint8).new_empty(0)
+    alledge = _all_gather_var(payload, [2 * row_bytes if x[0] else 0 for x in allmeta], group).cpu()
+    edges, pos = [], 0
+    for x in allmeta:
+        if x[0]:
+            edges.append((alledge[pos: pos + row_bytes], alledge[pos + row_bytes: pos + 2 * row_bytes]))
+            pos += 2 * row_bytes
+        else:
+            edges.append(None)
+    cont, prev = [0] * G, None
+    for r in range(G):
+        if edges[r] is None:
+            continue
+        if prev is not None and torch.equal(edges[prev][1], edges[r][0]):
+            cont[r] = 1  # this slice opens inside the bin the previous slice closed in
+        prev = r
+    distinct = [allmeta[r][1] - cont[r] for r in range(G)]
+    offset = [0] * G
+    for r in range(1, G):
+        offset[r] = offset[r - 1] + distinct[r - 1]
+    U = offset[-1] + distinct[-1]
+
+    # 3. (row, bin) back to the owner of the row
+    ikey = torch.zeros(max(n_local, 1), dtype=torch.int32, device=dev)[:n_local]
+    if m:
+        gbin = (lbin + (offset[rank] - cont[rank])).to(torch.int32)
+        bounds = torch.tensor([row_off[r] + ns[r] for r in range(G - 1)], dtype=torch.int64, device=dev)
+        dest = torch.bucketize(rows, bounds, right=True).to(torch.int32) if G > 1 else torch.zeros(m, dtype=torch.int32, device=dev)
+        cnt, ig, _ = (ops.to_torch(x) for x in ops.pack(dest, G))
+        send_counts = cnt.to(torch.int64).cpu().tolist()
+        ig = ig.to(torch.int64)
+        send_rows, send_bins = rows[ig], gbin[ig]
+    else:
+        send_counts = [0] * G
+        send_rows, send_bins = rows, torch.zeros(0, dtype=torch.int32, device=dev)
+    if G > 1:
+        sc = ops.tensor(send_counts, dtype=torch.int64)
+        rc_ = torch.empty_like(sc)
+        tdist.all_to_all_single(rc_, sc, group=group)
+        recv_counts = rc_.cpu().tolist()
+        got_rows = _all_to_all_var(send_rows, send_counts, recv_counts, group)
+        got_bins = _all_to_all_var(send_bins, send_counts, recv_counts, group)
+    else:
+        got_rows, got_bins = send_rows, send_bins
+    if got_rows.numel():
+        ikey[got_rows - row_off[rank]] = got_bins
+
+    # 4. the bins that start here: counts (a bin may run on through the following slices) and first rows
+    if m and distinct[rank] > 0:
+        own_cnt = lcount[1 + cont[rank]:].clone()
+        q = rank + 1
+        extra = 0
+        while q < G:
+            if allmeta[q][0] == 0:
+                q += 1
+                continue
+            if not cont[q]:
+                break
+            extra += allmeta[q][2]
+            if allmeta[q][1] > 1:
+                break
+            q += 1
+        own_cnt[-1] += extra
+        own_first = rows[lfirst[cont[rank]:]]
+    else:
+        own_cnt = torch.zeros(0, dtype=torch.int64, device=dev)
+        own_first = torch.zeros(0, dtype=torch.int64, device=dev)
+    out = {"ikey": ikey, "unique_count": int(U), "igroup_slice": rows, "bin_lo": offset[rank],
+           "nCountGroup_owned": own_cnt.to(torch.int32), "iFirstKey_owned": own_first}
+    if replicate:
+        allc = _all_gather_var(own_cnt.to(torch.int32), distinct, group) if G > 1 else own_cnt.to(torch.int32)
+        allf = _all_gather_var(own_first, distinct, group) if G > 1 else own_first
+        out["nCountGroup"] = torch.cat([allc.new_zeros(1), allc])
+        out["iFirstKey"] = allf
+    return out
 
 
 def sharded_groupby_sum(key_cols, values, group=None, ops=None):

@@ -103,6 +103,11 @@ class OracleOps:
     def rows_col(self, rows_i64):
         return _np(rows_i64).astype(np.int64)
 
+    def group_from_sorted(self, cols):
+        cols = [_np(c) for c in cols]
+        ik, ifk, cnt = orc.GroupFromLexSort(np.arange(len(cols[0]), dtype=np.int32), cols)
+        return torch.from_numpy(ik.copy()), torch.from_numpy(ifk.copy()), torch.from_numpy(cnt.copy())
+
     def is_f32(self, col):
         return _np(col).dtype == np.float32
 
@@ -229,6 +234,9 @@ def _sort_worker(rank, world, port, cuts, q):
         out["afs"] = _np(rd.sharded_lexsort(ops, [a[lo:hi], f[lo:hi], s[lo:hi]])).copy()
         out["desc"] = _np(rd.sharded_lexsort(ops, [f[lo:hi], a[lo:hi]], ascending=[False, True])).copy()
         out["one"] = _np(rd.sharded_lexsort(ops, [a[lo:hi]])).copy()
+        for name, cols in (("g_afs", [a[lo:hi], f[lo:hi], s[lo:hi]]), ("g_one", [a[lo:hi]]), ("g_const", [np.zeros(hi - lo, np.int8)])):
+            g = rd.sharded_group_from_lexsort(ops, cols)
+            out[name] = {k: (_np(v).copy() if isinstance(v, torch.Tensor) else v) for k, v in g.items()}
         q.put((rank, out))
     finally:
         tdist.destroy_process_group()
@@ -262,6 +270,18 @@ def test_sharded_lexsort_world2(cuts):
                                   orc.LexSort32([f, a], ascending=[False, True]))
     np.testing.assert_array_equal(np.concatenate([got[0]["one"], got[1]["one"]]), np.lexsort([a]))
     assert len(got[0]["afs"]) > 0 and len(got[1]["afs"]) > 0  # the splitter really splits the rows
+    # GroupFromLexSort across the ranks == the single-process call on the concatenated columns
+    for name, cols in (("g_afs", [a, f, s]), ("g_one", [a]), ("g_const", [np.zeros(len(a), np.int8)])):
+        eik, eifk, ecnt = orc.GroupFromLexSort(orc.LexSort32(cols), cols)
+        g0, g1 = got[0][name], got[1][name]
+        np.testing.assert_array_equal(np.concatenate([g0["ikey"], g1["ikey"]]), eik)
+        assert g0["unique_count"] == g1["unique_count"] == len(eifk)
+        for g in (g0, g1):
+            np.testing.assert_array_equal(g["iFirstKey"], eifk)
+            np.testing.assert_array_equal(g["nCountGroup"], ecnt)
+        np.testing.assert_array_equal(np.concatenate([g0["iFirstKey_owned"], g1["iFirstKey_owned"]]), eifk)
+        np.testing.assert_array_equal(np.concatenate([g0["nCountGroup_owned"], g1["nCountGroup_owned"]]), ecnt[1:])
+        assert g0["bin_lo"] == 0 and g1["bin_lo"] == len(g0["iFirstKey_owned"])
 
 
 def _free_port():

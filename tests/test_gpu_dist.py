@@ -72,5 +72,10 @@ def test_sharded_groupby_reduce_single_rank(group, a2a):
     np.testing.assert_array_equal(got, orc.EmaAll32([vi], eik, eu, 300, (0.0, None, f, None))[0])
     got = rd.sharded_cumsum(ops, torch.from_numpy(np.nan_to_num(v)).cuda(), g, None, group).cpu().numpy()
     np.testing.assert_allclose(got, orc.EmaAll32([np.nan_to_num(v)], eik, eu, 300, (0.0, None, None, None))[0], rtol=1e-12, atol=1e-9)
+    gl = rd.sharded_group_from_lexsort(ops, [torch.from_numpy(k1).cuda(), k2], group=group)
+    eik, eifk, ecnt = orc.GroupFromLexSort(orc.LexSort32([k1, k2]), [k1, k2])
+    np.testing.assert_array_equal(gl["ikey"].cpu().numpy(), eik)
+    np.testing.assert_array_equal(gl["iFirstKey"].cpu().numpy(), eifk)
+    np.testing.assert_array_equal(gl["nCountGroup"].cpu().numpy(), ecnt)
     ik, ifk, u, s = rd.sharded_groupby_sum([torch.from_numpy(k1).cuda()], torch.from_numpy(v).cuda(), group, ops)
     assert u == len(np.unique(k1)) and s.shape[0] == u + 1

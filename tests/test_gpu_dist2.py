@@ -51,6 +51,9 @@ def _worker(rank, world, port, n, q):
         out["ikey2"] = g2.ikey.cpu().numpy()
         out["sum2"] = rd.sharded_reduce(ops, vt, g2, 0).cpu().numpy()
         out["sort"] = rd.sharded_lexsort(ops, [torch.from_numpy(f[lo:hi]).cuda(), s[lo:hi], torch.from_numpy(k[lo:hi]).cuda()]).cpu().numpy()
+        fs = [torch.from_numpy(f[lo:hi]).cuda(), s[lo:hi]]
+        g = rd.sharded_group_from_lexsort(ops, fs)
+        out["gfl"] = {k_: (v_.cpu().numpy() if isinstance(v_, torch.Tensor) else v_) for k_, v_ in g.items()}
         q.put((rank, out))
     finally:
         tdist.destroy_process_group()
@@ -101,3 +104,10 @@ def test_two_rank_nccl_paths():
     np.testing.assert_array_equal(np.concatenate([got[0]["ikey2"], got[1]["ikey2"]]), eik2)
     np.testing.assert_allclose(got[0]["sum2"], orc.GroupByAll32([v], eik2, eu2, [0], [0], [eu2 + 2], 0)[0], rtol=1e-11, atol=1e-9)
     np.testing.assert_array_equal(np.concatenate([got[0]["sort"], got[1]["sort"]]), np.lexsort([f, s, k]))
+    eik, eifk, ecnt = orc.GroupFromLexSort(orc.LexSort32([f, s]), [f, s])
+    g0, g1 = got[0]["gfl"], got[1]["gfl"]
+    np.testing.assert_array_equal(np.concatenate([g0["ikey"], g1["ikey"]]), eik)
+    assert g0["unique_count"] == g1["unique_count"] == len(eifk)
+    np.testing.assert_array_equal(g1["iFirstKey"], eifk)
+    np.testing.assert_array_equal(g0["nCountGroup"], ecnt)
+    np.testing.assert_array_equal(np.concatenate([g0["nCountGroup_owned"], g1["nCountGroup_owned"]]), ecnt[1:])

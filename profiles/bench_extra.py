@@ -54,6 +54,20 @@ def main():
     line("C1 mean f64 by int16 iKey", n, ms, 10)
     del k32, ik16
 
+    # C2: int64 key with 1M uniques; the other reductions the config names (sum f64 is the headline bench)
+    k = keys(1_000_000)
+    ms, (ik, ifk, u) = timed(lambda: rc.MultiKeyGroupBy32([k], 0, None, 2))
+    line("C2 hash int64 key 1M uniques", n, ms, 12, uniques=u)
+    del k
+    val32 = val.to(torch.float32)
+    for name, v, fn, b in (("sum f64", val, 0, 12), ("sum f32", val32, 0, 8), ("min f64", val, 2, 12), ("max f32", val32, 3, 8),
+                           ("mean f64", val, 1, 12), ("nansum f64", val, 50, 12), ("var f64 (two passes)", val, 4, 12)):
+        ms, _ = timed(lambda: rc.GroupByAll32([v], ik, u, [fn], [1], [u + 1], 0))
+        line("C2 " + name, n, ms, b)
+    ms, _ = timed(lambda: rc.BinCount(ik, u + 1))
+    line("C2 count (BinCount)", n, ms, 4)
+    del val32, ik
+
     # C5: 100M uniques (scaled with n), cumsum / pack / first / last
     u5 = max(n // 10, 1)
     k = keys(u5)

@@ -46,6 +46,8 @@ typedef enum {
   RTB_GB_NANSUM = 50, RTB_GB_NANMEAN = 51, RTB_GB_NANMIN = 52, RTB_GB_NANMAX = 53, RTB_GB_NANVAR = 54,
   RTB_GB_NANSTD = 55,
   RTB_GB_FIRST = 100, RTB_GB_NTH = 101, RTB_GB_LAST = 102,
+  RTB_GB_ROLLING_SUM = 200, RTB_GB_ROLLING_NANSUM = 201, RTB_GB_ROLLING_DIFF = 202, RTB_GB_ROLLING_SHIFT = 203,
+  RTB_GB_ROLLING_COUNT = 204, RTB_GB_ROLLING_MEAN = 205, RTB_GB_ROLLING_NANMEAN = 206,
   RTB_GB_CUMSUM = 300, RTB_GB_CUMPROD = 302, RTB_GB_CUMNANMAX = 306, RTB_GB_CUMNANMIN = 307, RTB_GB_CUMMAX = 308,
   RTB_GB_CUMMIN = 309
 } rtb_gb_func;
@@ -165,6 +167,17 @@ int rtb_cumop_out_dtype(int func, int vdtype);
 int rtb_groupby_cumop(int func, const void* values, int vdtype, const void* ikey, int kdtype, int64_t nrows,
                       int64_t unique_rows, const uint8_t* filter, const uint8_t* reset_filter, void* out,
                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- 8f.2: the rolling functions of rc.GroupByAllPack32 (function numbers 200-206, riptable/rt_enum.py:513-519;
+ * riptable/rt_groupbyops.py:2941-3153, 3500-3670).  Row-shaped output (nrows items) in original row order; bin 0 is
+ * computed as a group of its own (riptable/rt_grouping.py:3324-3326) except for ROLLING_COUNT (cumcount), where it gets
+ * the invalid.  `window`: the window length for SUM / NANSUM / MEAN / NANMEAN (partial windows at the start of a group
+ * use what is there, riptable/tests/test_fastarray.py:1297-1305), the period for SHIFT / DIFF (may be negative), the
+ * direction for COUNT (>= 0 ascending, < 0 descending).  Output dtype: rtb_rolling_out_dtype. */
+int rtb_rolling_out_dtype(int func, int vdtype);
+int rtb_groupby_rolling(int func, const void* values, int vdtype, int32_t itemsize, const void* ikey, int kdtype,
+                        const int32_t* igroup, const int32_t* ifirstgroup, const int32_t* ncountgroup, int64_t nrows,
+                        int64_t unique_rows, int64_t window, void* out, void* stream);
 
 /* ---- a10: rc.MakeiFirst(key, n, filter, mode) / rc.MakeiNext(key, n, mode) — riptable/rt_numpy.py:1791-1854 */
 int rtb_make_ifirst(const void* ikey, int kdtype, int64_t nrows, int64_t n, const uint8_t* filter, int mode,

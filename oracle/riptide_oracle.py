@@ -289,6 +289,77 @@ def GroupByAll32(values, ikey, unique_rows, funcList, binLowList, binHighList, f
 
 # ----------------------------------------------------------------------------------------------
 # a8  rc.GroupByAllPack32 (rt_numpy.py:1875-1891; rt_grouping.py:3442-3454)
+# 8f.2  rolling functions of rc.GroupByAllPack32 (rt_enum.py:513-519; rt_groupbyops.py:2941-3153, 3500-3670)
+GB_ROLLING_SUM, GB_ROLLING_NANSUM, GB_ROLLING_DIFF, GB_ROLLING_SHIFT = 200, 201, 202, 203
+GB_ROLLING_COUNT, GB_ROLLING_MEAN, GB_ROLLING_NANMEAN = 204, 205, 206
+
+
+def _rolling(v, ikey, iGroup, iFirstGroup, nCountGroup, nb, f, window):
+    """Row-shaped rolling results in original row order.  Bin 0 is computed as a group of its own
+    (rt_grouping.py:3324-3326: base_bin = 0) except for cumcount, whose filtered rows are invalid
+    (tests/test_categorical_groupby.py:760-763).
+    shift / diff: the value `window` places earlier in the group (later if negative); invalid where
+    there is none (pandas groupby.shift / diff, tests/test_groupby.py:652-708).
+    sum / nansum / mean / nanmean: over the last `window` rows of the group including this one;
+    partial windows use what is there (tests/test_fastarray.py:1297-1305 pins this for the
+    ungrouped rc.Rolling: nansum([1,2,3,nan,nan,nan], 3) == [1,3,6,5,3,0], also with int64
+    sentinels); nan variants skip NaN / sentinels, nanmean of nothing is NaN.
+    UNPINNED: output dtypes (sum as cumsum; mean float64; diff keeps the input dtype; cumcount int32)."""
+    n = len(iGroup)
+    rows = iGroup.astype(np.int64)
+    b = ikey.astype(np.int64)[rows]
+    b[(b < 0) | (b >= nb)] = 0
+    start = iFirstGroup.astype(np.int64)[b]
+    cnt = nCountGroup.astype(np.int64)[b]
+    j = np.arange(n, dtype=np.int64)
+    if f == GB_ROLLING_COUNT:
+        p = j - start
+        out = np.empty(n, np.int32)
+        out[rows] = np.where(b == 0, np.iinfo(np.int32).min, p if window >= 0 else cnt - 1 - p)
+        return out
+    if f in (GB_ROLLING_SHIFT, GB_ROLLING_DIFF):
+        if f == GB_ROLLING_DIFF and v.dtype.kind not in "iuf":
+            return None
+        q = j - window
+        ok = (q >= start) & (q < start + cnt)
+        out = np.empty(n, v.dtype)
+        out[:] = invalid_for(v.dtype)
+        src = v[rows[q[ok]]]
+        if f == GB_ROLLING_SHIFT:
+            out[rows[ok]] = src
+        else:
+            with np.errstate(over="ignore", invalid="ignore"):
+                out[rows[ok]] = v[rows[ok]] - src
+        return out
+    if v.dtype.kind not in "biuf":
+        return None
+    if window < 1:
+        raise ValueError("rolling window must be >= 1")
+    skip = f in (GB_ROLLING_NANSUM, GB_ROLLING_NANMEAN)
+    mean = f in (GB_ROLLING_MEAN, GB_ROLLING_NANMEAN)
+    odt = np.dtype(np.float64) if mean else _sum_out_dtype(v.dtype)
+    acc_dt = np.dtype(np.float64) if (mean or v.dtype.kind == "f") else np.dtype(odt)
+    acc = np.zeros(n, acc_dt)
+    used = np.zeros(n, np.int64)
+    bad = _is_invalid(v)
+    with np.errstate(over="ignore", invalid="ignore"):
+        for back in range(min(window, int(cnt.max()) if n else 0) - 1, -1, -1):  # oldest -> newest
+            q = j - back
+            ok = q >= start
+            src_rows = rows[np.where(ok, q, 0)]
+            if skip:
+                ok &= ~bad[src_rows]
+            acc = np.where(ok, acc + v[src_rows].astype(acc_dt), acc)
+            used += ok
+        if mean:
+            vals = np.where(used > 0, acc / np.maximum(used, 1), np.nan)
+        else:
+            vals = acc
+    out = np.empty(n, odt)
+    out[rows] = vals.astype(odt)
+    return out
+
+
 def GroupByAllPack32(
     values, ikey, iGroup, iFirstGroup, nCountGroup, unique_rows, funcList, binLowList, binHighList, func_param=0
 ):
@@ -300,6 +371,9 @@ def GroupByAllPack32(
     for v, f, lo, hi in zip(values, funcList, binLowList, binHighList):
         v = np.asarray(v)
         f = int(f)
+        if GB_ROLLING_SUM <= f <= GB_ROLLING_NANMEAN:
+            res.append(_rolling(v, np.asarray(ikey), iGroup, iFirstGroup, nCountGroup, nb, f, int(func_param)))
+            continue
         if f not in (GB_FIRST, GB_NTH, GB_LAST):
             raise ValueError(f"GroupByAllPack32: unsupported function {f}")
         cnt = nCountGroup[:nb].astype(np.int64)

@@ -107,6 +107,100 @@ __global__ void __launch_bounds__(256) pick_kernel(const uint8_t* __restrict__ v
   }
 }
 
+__device__ __forceinline__ unsigned long long f64_bits(double d) { return (unsigned long long)__double_as_longlong(d); }
+__device__ __forceinline__ double bits_f64(unsigned long long u) { return __longlong_as_double((long long)u); }
+
+// ---- 8f.2: rolling ops on the packed layout (GroupByAllPack32 functions 200-206) ---------------------------
+// One thread per packed position j: its row, its bin, and the window [max(start, j - w + 1), j] of the bin's run of
+// iGroup.  Sums run oldest -> newest in f64 / int64, which is also the oracle's order (bit-exact).
+struct RollArgs {
+  const uint8_t* values;
+  int vdt, itemsize, odt;
+  const void* ikey;
+  int kdt;
+  const int32_t *igroup, *ifirst, *ncount;
+  int64_t n, nb;
+  int func;
+  int64_t window;
+  uint8_t* out;
+};
+
+__device__ __forceinline__ void store_invalid_item(uint8_t* dst, int dt, int itemsize) {
+  if (dt <= RTB_F64) {
+    unsigned long long inv = invalid_raw(dt);
+    for (int i = 0; i < itemsize; i++) dst[i] = (uint8_t)(inv >> (8 * i));
+  } else {
+    for (int i = 0; i < itemsize; i++) dst[i] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) rolling_kernel(RollArgs a) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int vsz = a.vdt <= RTB_F64 ? dsize(a.vdt) : a.itemsize;
+  const bool flt = a.vdt == RTB_F32 || a.vdt == RTB_F64;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.n; j += stride) {
+    const int64_t row = a.igroup[j];
+    int64_t bin = load_ikey(a.ikey, a.kdt, row);
+    if (bin < 0 || bin >= a.nb) bin = 0;
+    const int64_t start = a.ifirst[bin], cnt = a.ncount[bin];
+    switch (a.func) {
+      case RTB_GB_ROLLING_COUNT: {
+        const int64_t p = j - start;
+        ((int32_t*)a.out)[row] = bin == 0 ? INT32_MIN : (int32_t)(a.window >= 0 ? p : cnt - 1 - p);
+        break;
+      }
+      case RTB_GB_ROLLING_SHIFT: {
+        const int64_t q = j - a.window;
+        uint8_t* dst = a.out + row * (int64_t)a.itemsize;
+        if (q >= start && q < start + cnt) {
+          const uint8_t* src = a.values + (int64_t)a.igroup[q] * a.itemsize;
+          for (int i = 0; i < a.itemsize; i++) dst[i] = src[i];
+        } else {
+          store_invalid_item(dst, a.vdt, a.itemsize);
+        }
+        break;
+      }
+      case RTB_GB_ROLLING_DIFF: {
+        const int64_t q = j - a.window;
+        unsigned long long raw = invalid_raw(a.odt);
+        if (q >= start && q < start + cnt) {
+          const unsigned long long x = load_raw1(a.values, vsz, row), y = load_raw1(a.values, vsz, a.igroup[q]);
+          if (flt) {
+            const double d = raw_to_f64(x, a.vdt) - raw_to_f64(y, a.vdt);
+            raw = a.odt == RTB_F32 ? (unsigned long long)__float_as_uint((float)d) : f64_bits(d);
+          } else {
+            raw = (unsigned long long)(raw_to_i64(x, a.vdt) - raw_to_i64(y, a.vdt));
+          }
+        }
+        store_raw(a.out, a.odt, row, raw);
+        break;
+      }
+      default: {  // ROLLING_SUM / NANSUM / MEAN / NANMEAN
+        const bool skip = a.func == RTB_GB_ROLLING_NANSUM || a.func == RTB_GB_ROLLING_NANMEAN;
+        const bool mean = a.func == RTB_GB_ROLLING_MEAN || a.func == RTB_GB_ROLLING_NANMEAN;
+        int64_t q = j - a.window + 1;
+        if (q < start) q = start;
+        double fs = 0.0;
+        long long is = 0;
+        int64_t used = 0;
+        for (; q <= j; q++) {
+          const unsigned long long x = load_raw1(a.values, vsz, a.igroup[q]);
+          if (skip && raw_invalid(x, a.vdt)) continue;
+          used++;
+          if (flt || mean) fs += raw_to_f64(x, a.vdt);
+          else is += raw_to_i64(x, a.vdt);
+        }
+        unsigned long long raw;
+        if (mean) raw = f64_bits(used ? fs / (double)used : __longlong_as_double(0x7FF8000000000000ll));
+        else if (a.odt == RTB_F32) raw = (unsigned long long)__float_as_uint((float)fs);
+        else if (flt) raw = f64_bits(fs);
+        else raw = (unsigned long long)is;
+        store_raw(a.out, a.odt, row, raw);
+      }
+    }
+  }
+}
+
 // ---- a9: cumulative ops (cumsum / cumprod / cummin / cummax) -----------------------------------------------
 constexpr int kSegThreads = 256;
 constexpr int kSegItems = 8;
@@ -123,8 +217,6 @@ struct SegPair {
   uint32_t f;            // SEG_HEAD: a segment head lies inside the summarised range; SEG_HAS / SEG_POISON: min/max state
 };
 
-__device__ __forceinline__ unsigned long long f64_bits(double d) { return (unsigned long long)__double_as_longlong(d); }
-__device__ __forceinline__ double bits_f64(unsigned long long u) { return __longlong_as_double((long long)u); }
 
 template <int OP>
 __device__ __forceinline__ unsigned long long seg_op(unsigned long long a, unsigned long long b) {
@@ -398,6 +490,43 @@ extern "C" int rtb_groupby_pick(const void* values, int vdt, int32_t itemsize, c
   int64_t nb = unique_rows + 1;
   pick_kernel<<<grid_for(nb, 256, 1), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)values, vdt, itemsize, igroup, ifirstgroup,
                                                                       ncountgroup, nb, func, nth, bin_low, bin_high, (uint8_t*)out);
+  RTB_LAUNCH_CHECK();
+  return RTB_OK;
+}
+
+extern "C" int rtb_cumop_out_dtype(int func, int vdt);
+extern "C" int rtb_rolling_out_dtype(int func, int vdt) {
+  switch (func) {
+    case RTB_GB_ROLLING_COUNT: return RTB_I32;
+    case RTB_GB_ROLLING_SHIFT: return (vdt >= RTB_BOOL && vdt <= RTB_UCS4) ? vdt : RTB_ERR_UNSUPPORTED;
+    case RTB_GB_ROLLING_DIFF: return (vdt > RTB_BOOL && vdt <= RTB_F64) ? vdt : RTB_ERR_UNSUPPORTED;
+    case RTB_GB_ROLLING_SUM: case RTB_GB_ROLLING_NANSUM: return rtb_cumop_out_dtype(RTB_GB_CUMSUM, vdt);
+    case RTB_GB_ROLLING_MEAN: case RTB_GB_ROLLING_NANMEAN: return (vdt >= RTB_BOOL && vdt <= RTB_F64) ? RTB_F64 : RTB_ERR_UNSUPPORTED;
+    default: return RTB_ERR_UNSUPPORTED;
+  }
+}
+
+extern "C" int rtb_groupby_rolling(int func, const void* values, int vdt, int32_t itemsize, const void* ikey, int kdt,
+                                   const int32_t* igroup, const int32_t* ifirstgroup, const int32_t* ncountgroup,
+                                   int64_t nrows, int64_t unique_rows, int64_t window, void* out, void* stream) {
+  RTB_ARG(is_ikey_dtype(kdt), "GroupByAllPack32: ikey must be int8/16/32/64");
+  const int odt = rtb_rolling_out_dtype(func, func == RTB_GB_ROLLING_COUNT ? RTB_I32 : vdt);
+  if (odt < 0) {
+    set_error("GroupByAllPack32: rolling function %d is not provided for dtype %d", func, vdt);
+    return RTB_ERR_UNSUPPORTED;
+  }
+  RTB_ARG(nrows >= 0 && nrows <= 2147483646ll && unique_rows >= 0, "GroupByAllPack32: bad sizes");
+  const bool windowed = func != RTB_GB_ROLLING_SHIFT && func != RTB_GB_ROLLING_DIFF && func != RTB_GB_ROLLING_COUNT;
+  RTB_ARG(!windowed || window >= 1, "GroupByAllPack32: rolling window must be >= 1");
+  if (nrows == 0) return RTB_OK;
+  RTB_ARG(ikey && igroup && ifirstgroup && ncountgroup && out, "GroupByAllPack32: null pointer");
+  RTB_ARG(func == RTB_GB_ROLLING_COUNT || values, "GroupByAllPack32: null values");
+  RTB_ARG(func == RTB_GB_ROLLING_COUNT || vdt > RTB_F64 || itemsize == dtype_size(vdt), "GroupByAllPack32: itemsize does not match dtype");
+  RollArgs a;
+  a.values = (const uint8_t*)values; a.vdt = vdt; a.itemsize = itemsize; a.odt = odt; a.ikey = ikey; a.kdt = kdt;
+  a.igroup = igroup; a.ifirst = ifirstgroup; a.ncount = ncountgroup; a.n = nrows; a.nb = unique_rows + 1; a.func = func;
+  a.window = window; a.out = (uint8_t*)out;
+  rolling_kernel<<<grid_for(nrows, 256, 1), 256, 0, (cudaStream_t)stream>>>(a);
   RTB_LAUNCH_CHECK();
   return RTB_OK;
 }

@@ -559,7 +559,7 @@ def sharded_count(ops, grouping: ShardedGrouping, group=None, alltoall_min_bins=
     return _combine("count", {"v": full}, grouping.unique_count + 1, False, group, alltoall_min_bins)["v"]
 
 
-_TRACE = os.environ.get("RTB_DIST_TRACE") == "1"
+_TRACE = os.environ.get("RTB_DIST_TRACE") == "1"  # per-phase device times of every sharded step, per rank
 
 
 class _Tick:
@@ -577,10 +577,10 @@ class _Tick:
             self.names.append(name)
 
     def report(self):
-        if _TRACE and tdist.get_rank() == 0:
+        if _TRACE:
             torch.cuda.synchronize()
             parts = [f"{self.names[i]} {self.ev[i - 1].elapsed_time(self.ev[i]):.2f}" for i in range(1, len(self.ev))]
-            print("[rtb dist] ms: " + ", ".join(parts), flush=True)
+            print(f"[rtb dist r{tdist.get_rank()}] ms: " + ", ".join(parts), flush=True)
 
 
 def sharded_pick(ops, values, grouping: ShardedGrouping, func, nth=0, group=None):

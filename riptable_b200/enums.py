@@ -30,6 +30,14 @@ class GB_FUNCTIONS(IntEnum):
     GB_FIRST = 100
     GB_NTH = 101
     GB_LAST = 102
+    # rolling ops on the packed layout (rc.GroupByAllPack32, row-shaped results)
+    GB_ROLLING_SUM = 200
+    GB_ROLLING_NANSUM = 201
+    GB_ROLLING_DIFF = 202
+    GB_ROLLING_SHIFT = 203
+    GB_ROLLING_COUNT = 204
+    GB_ROLLING_MEAN = 205
+    GB_ROLLING_NANMEAN = 206
     # row-shaped accumulations (rc.EmaAll32)
     GB_CUMSUM = 300
     GB_CUMPROD = 302

@@ -432,8 +432,31 @@ def GroupByAllPack32(values, ikey, iGroup, iFirstGroup, nCountGroup, unique_rows
     if ifg.n < nb or cnt.n < nb:
         raise ValueError("GroupByAllPack32: iFirstGroup / nCountGroup shorter than unique_rows + 1")
     out = []
+    kdev = None
     for v, f, lo, hi in zip(values, funcList, binLowList, binHighList):
         f = int(f)
+        if GB_FUNCTIONS.GB_ROLLING_SUM <= f <= GB_FUNCTIONS.GB_ROLLING_NANMEAN:
+            # 8f.2: row-shaped rolling results; func_param is the window / period (riptable/rt_groupbyops.py:2941-3153)
+            if kdev is None:
+                kdev = _ikey_dev(ikey)
+            if f == GB_FUNCTIONS.GB_ROLLING_COUNT:
+                d, vcode, isz = None, RTB_BYTES, 0
+                ocode = lib.rtb_rolling_out_dtype(f, 0)
+            else:
+                d = _to_dev(v)
+                vcode = dtype_code(d.dtype) if d.dtype != np.float16 else -1
+                isz = d.dtype.itemsize
+                ocode = lib.rtb_rolling_out_dtype(f, vcode) if vcode >= 0 else -1
+            if ocode < 0:
+                out.append(None)
+                continue
+            odt = d.dtype if f == GB_FUNCTIONS.GB_ROLLING_SHIFT else code_dtype(ocode)
+            res = DevArray.empty(kdev.n, odt)
+            check(lib.rtb_groupby_rolling(f, C.c_void_p(d.ptr) if d is not None else None, vcode, isz, C.c_void_p(kdev.ptr),
+                                          dtype_code(kdev.dtype), C.c_void_p(ig.ptr), C.c_void_p(ifg.ptr), C.c_void_p(cnt.ptr),
+                                          kdev.n, int(unique_rows), int(func_param), C.c_void_p(res.ptr), _stream()))
+            out.append(_from_dev(res, device_mode))
+            continue
         if f not in (GB_FUNCTIONS.GB_FIRST, GB_FUNCTIONS.GB_NTH, GB_FUNCTIONS.GB_LAST):
             raise NotImplementedError(f"GroupByAllPack32: function {f} is outside this build's hot path")
         d = _to_dev(v)

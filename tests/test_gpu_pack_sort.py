@@ -205,6 +205,49 @@ def test_cumprod(rc, vdt, nb):
             np.testing.assert_array_equal(got, exp)
 
 
+@pytest.mark.parametrize("vdt", _ALL_NUM + ["S5", "U3"])
+@pytest.mark.parametrize("nb", [1, 37, 20_000])
+def test_rolling_ops(rc, vdt, nb):
+    rng = np.random.default_rng(nb + 11)
+    n = 90_001
+    ikey = rng.integers(0, nb + 1, n).astype(np.int32)  # bin 0 present: it is rolled as a group of its own
+    dt = np.dtype(vdt)
+    if dt.kind == "f":
+        v = rng.normal(0, 100, n).astype(dt)
+        v[rng.random(n) < 0.1] = np.nan
+    elif dt.kind == "b":
+        v = rng.integers(0, 2, n).astype(dt)
+    elif dt.kind in "iu":
+        info = np.iinfo(dt)
+        v = rng.integers(max(info.min, -1000), min(info.max, 1000), n).astype(dt)
+        v[rng.random(n) < 0.1] = orc.invalid_for(dt)
+    else:
+        v = rng.choice(np.array(["", "a", "bc", "xyz", "hello"]), n).astype(dt)
+    cnt, ig, ifg = orc.BinCount(ikey, nb + 1, pack=True)
+    cases = [(203, -2), (203, 3), (203, 0), (202, 1), (202, -3), (200, 3), (201, 1), (201, 40), (205, 5), (206, 4), (204, 1), (204, -1)]
+    for fn, p in cases:
+        exp = orc.GroupByAllPack32([v], ikey, ig, ifg, cnt, nb, [fn], [0], [nb + 1], p)[0]
+        got = rc.GroupByAllPack32([v], ikey, ig, ifg, cnt, nb, [fn], [0], [nb + 1], p)[0]
+        if exp is None:
+            assert got is None, (fn, vdt)
+            continue
+        assert got.dtype == exp.dtype, (fn, vdt)
+        if exp.dtype == np.float32 and fn in (200, 201):
+            np.testing.assert_allclose(got, exp, rtol=1e-6, equal_nan=True)  # f64 accumulation, one rounding to f32
+        else:
+            np.testing.assert_array_equal(got, exp, err_msg=f"func {fn} param {p} dtype {vdt}")
+
+
+def test_rolling_kat(rc):
+    # tests/test_fastarray.py:1297-1305 through a single group
+    x = np.array([1, 2, 3, np.nan, np.nan, np.nan])
+    one = np.ones(6, np.int8)
+    c1, g1, f1 = orc.BinCount(one, 2, pack=True)
+    assert rc.GroupByAllPack32([x], one, g1, f1, c1, 1, [201], [0], [2], 3)[0].tolist() == [1, 3, 6, 5, 3, 0]
+    with pytest.raises(ValueError):
+        rc.GroupByAllPack32([x], one, g1, f1, c1, 1, [200], [0], [2], 0)
+
+
 # ---------------------------------------------------------------------------------------------------- a10
 def test_makeifirst_ilast_inext(rc):
     rng = np.random.default_rng(8)

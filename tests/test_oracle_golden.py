@@ -229,6 +229,46 @@ def test_cumprod_small():
     assert orc.EmaAll32([v], ik, 2, orc.GB_CUMPROD, (0.0, None, f, None))[0].tolist() == [2, 3, 2, np.iinfo(np.int64).min, 15, 12]
 
 
+def test_rolling_ops_pinned_to_pandas_and_kat():
+    # tests/test_groupby.py:652-708 compare shift / diff with pandas; tests/test_categorical_groupby.py:749-763 cumcount;
+    # tests/test_fastarray.py:1297-1305 the partial-window nansum KAT
+    pd = pytest.importorskip("pandas")
+    rng = np.random.default_rng(0)
+    n = 300
+    key = rng.choice(np.array(["a", "b", "c"]), n)
+    g = orc.groupbyhash(key)
+    ik, U = g["iKey"], g["unique_count"]
+    cnt, ig, ifg = orc.BinCount(ik, U + 1, pack=True)
+    v = rng.random(n)
+    v[rng.random(n) < 0.1] = np.nan
+    df = pd.DataFrame({"k": key, "v": v})
+    call = lambda vals, fn, p: orc.GroupByAllPack32([vals], ik, ig, ifg, cnt, U, [fn], [0], [U + 1], p)[0]
+    for per in (-2, 3, 1):
+        np.testing.assert_array_equal(call(v, orc.GB_ROLLING_SHIFT, per), df.groupby("k")["v"].shift(per).to_numpy())
+        np.testing.assert_allclose(call(v, orc.GB_ROLLING_DIFF, per), df.groupby("k")["v"].diff(per).to_numpy(), rtol=0, atol=0)
+    for w in (1, 3, 7):
+        roll = lambda mp: df.groupby("k")["v"].rolling(w, min_periods=mp)
+        flat = lambda r: r.reset_index(level=0, drop=True).sort_index().to_numpy()
+        np.testing.assert_allclose(call(v, orc.GB_ROLLING_NANSUM, w), np.nan_to_num(flat(roll(0).sum())), rtol=1e-12)
+        np.testing.assert_allclose(call(v, orc.GB_ROLLING_NANMEAN, w), flat(roll(1).mean()), rtol=1e-12)
+    np.testing.assert_array_equal(call(ik, orc.GB_ROLLING_COUNT, 1), df.groupby("k").cumcount().to_numpy())
+    np.testing.assert_array_equal(call(ik, orc.GB_ROLLING_COUNT, -1), df.groupby("k").cumcount(ascending=False).to_numpy())
+    # cumcount with filtered rows: invalid there (test_categorical_groupby.py:760-763)
+    f = np.arange(n) % 2 == 1
+    ikf = orc.CombineFilter(ik, f)
+    cf, igf, iff = orc.BinCount(ikf, U + 1, pack=True)
+    cc = orc.GroupByAllPack32([ikf], ikf, igf, iff, cf, U, [orc.GB_ROLLING_COUNT], [0], [U + 1], 1)[0]
+    assert (cc[~f] == np.iinfo(np.int32).min).all() and (cc[f] >= 0).all()
+    x = np.array([1, 2, 3, np.nan, np.nan, np.nan])
+    one = np.ones(6, np.int8)
+    c1, g1, f1 = orc.BinCount(one, 2, pack=True)
+    assert orc.GroupByAllPack32([x], one, g1, f1, c1, 1, [orc.GB_ROLLING_NANSUM], [0], [2], 3)[0].tolist() == [1, 3, 6, 5, 3, 0]
+    xi = np.array([1, 2, 3, 0, 0, 0], np.int64)
+    xi[3:] = np.iinfo(np.int64).min
+    r = orc.GroupByAllPack32([xi], one, g1, f1, c1, 1, [orc.GB_ROLLING_NANSUM], [0], [2], 3)[0]
+    assert r.dtype == np.int64 and r.tolist() == [1, 3, 6, 5, 3, 0]
+
+
 def test_cutoffs_kat():
     # tests/test_pgroupby.py:7-86
     rng = np.random.default_rng(0)

@@ -45,7 +45,7 @@ typedef enum {
   RTB_GB_SUM = 0, RTB_GB_MEAN = 1, RTB_GB_MIN = 2, RTB_GB_MAX = 3, RTB_GB_VAR = 4, RTB_GB_STD = 5,
   RTB_GB_NANSUM = 50, RTB_GB_NANMEAN = 51, RTB_GB_NANMIN = 52, RTB_GB_NANMAX = 53, RTB_GB_NANVAR = 54,
   RTB_GB_NANSTD = 55,
-  RTB_GB_FIRST = 100, RTB_GB_NTH = 101, RTB_GB_LAST = 102,
+  RTB_GB_FIRST = 100, RTB_GB_NTH = 101, RTB_GB_LAST = 102, RTB_GB_MEDIAN = 103, RTB_GB_QUANTILE_MULT = 106,
   RTB_GB_ROLLING_SUM = 200, RTB_GB_ROLLING_NANSUM = 201, RTB_GB_ROLLING_DIFF = 202, RTB_GB_ROLLING_SHIFT = 203,
   RTB_GB_ROLLING_COUNT = 204, RTB_GB_ROLLING_MEAN = 205, RTB_GB_ROLLING_NANMEAN = 206,
   RTB_GB_CUMSUM = 300, RTB_GB_CUMPROD = 302, RTB_GB_CUMNANMAX = 306, RTB_GB_CUMNANMIN = 307, RTB_GB_CUMMAX = 308,
@@ -178,6 +178,17 @@ int rtb_rolling_out_dtype(int func, int vdtype);
 int rtb_groupby_rolling(int func, const void* values, int vdtype, int32_t itemsize, const void* ikey, int kdtype,
                         const int32_t* igroup, const int32_t* ifirstgroup, const int32_t* ncountgroup, int64_t nrows,
                         int64_t unique_rows, int64_t window, void* out, void* stream);
+
+/* ---- 8f.2: per-group quantiles — rc.GroupByAllPack32 with GB_MEDIAN (103) / GB_QUANTILE_MULT (106),
+ * riptable/rt_groupbyops.py:1560-1731 (func_param = int(q * 1e9) + is_nan * (1e9 + 1)), 2498-2513 (median = q 0.5).
+ * out: unique_rows+1 float64; numpy "midpoint" rule on the group's valid values (riptable/rt_numpy.py:4153-4245);
+ * nan_aware = 0: a group holding a NaN / integer sentinel gives NaN.  Bins outside [bin_low, bin_high) and empty
+ * groups give NaN.  iFirstGroup / nCountGroup are the packed layout's (rtb_groupby_pack). */
+size_t rtb_quantile_workspace_bytes(int64_t nrows, int64_t unique_rows);
+int rtb_groupby_quantile(const void* values, int vdtype, const void* ikey, int kdtype, const int32_t* ifirstgroup,
+                         const int32_t* ncountgroup, int64_t nrows, int64_t unique_rows, double q, int nan_aware,
+                         int64_t bin_low, int64_t bin_high, double* out, void* workspace, size_t workspace_bytes,
+                         void* stream);
 
 /* ---- a10: rc.MakeiFirst(key, n, filter, mode) / rc.MakeiNext(key, n, mode) — riptable/rt_numpy.py:1791-1854 */
 int rtb_make_ifirst(const void* ikey, int kdtype, int64_t nrows, int64_t n, const uint8_t* filter, int mode,

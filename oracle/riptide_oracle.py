@@ -289,6 +289,53 @@ def GroupByAll32(values, ikey, unique_rows, funcList, binLowList, binHighList, f
 
 # ----------------------------------------------------------------------------------------------
 # a8  rc.GroupByAllPack32 (rt_numpy.py:1875-1891; rt_grouping.py:3442-3454)
+# 8f.2  per-group quantiles: GB_MEDIAN / GB_QUANTILE_MULT (rt_enum.py:506-509; rt_groupbyops.py:1560-1745, 2498-2513)
+GB_MEDIAN, GB_QUANTILE_MULT = 103, 106
+QUANTILE_MULTIPLIER = 10**9
+
+
+def quantile_func_param(q, is_nan_function):
+    """rt_groupbyops.py:1720-1731."""
+    return int(q * 1e9) + int(bool(is_nan_function)) * (QUANTILE_MULTIPLIER + 1)
+
+
+def _quantile(v, ikey, nb, f, func_param, lo, hi):
+    """float64[nb]; numpy's "midpoint" rule written as (lower + higher) / 2 so that infinities behave
+    (rt_numpy.py:4153-4245, tests/test_groupbyops.py:540-700).  NaN and integer sentinels are invalid:
+    the nan version skips them, the plain one returns NaN for a group that holds one (the reference test
+    compares integer columns through their float copy with NaN at the sentinels).  GB_MEDIAN
+    "auto handles nan" (rt_enum.py:506).  Empty group, or bin outside [lo, hi) -> NaN."""
+    if v.dtype.kind not in "biuf":
+        return None
+    if f == GB_MEDIAN:
+        q, nan_aware = 0.5, True
+    else:
+        nan_aware = func_param >= QUANTILE_MULTIPLIER + 1
+        q = (func_param - nan_aware * (QUANTILE_MULTIPLIER + 1)) / 1e9
+    out = np.full(nb, np.nan)
+    ik = ikey.astype(np.int64)
+    ik[(ik < 0) | (ik >= nb)] = 0
+    bad = _is_invalid(v)
+    x = v.astype(np.float64)
+    order = np.argsort(ik, kind="stable")
+    bounds = np.searchsorted(ik[order], np.arange(nb + 1))
+    for b in range(max(lo, 0), min(hi, nb)):
+        rows = order[bounds[b]: bounds[b + 1]]
+        if len(rows) == 0:
+            continue
+        ok = ~bad[rows]
+        if not nan_aware and not ok.all():
+            continue
+        vals = np.sort(x[rows][ok])
+        m = len(vals)
+        if m == 0:
+            continue
+        idx = (m - 1) * q  # numpy's virtual index, in float64 and unsnapped as np.quantile leaves it
+        with np.errstate(invalid="ignore"):
+            out[b] = (vals[int(np.floor(idx))] + vals[int(np.ceil(idx))]) / 2
+    return out
+
+
 # 8f.2  rolling functions of rc.GroupByAllPack32 (rt_enum.py:513-519; rt_groupbyops.py:2941-3153, 3500-3670)
 GB_ROLLING_SUM, GB_ROLLING_NANSUM, GB_ROLLING_DIFF, GB_ROLLING_SHIFT = 200, 201, 202, 203
 GB_ROLLING_COUNT, GB_ROLLING_MEAN, GB_ROLLING_NANMEAN = 204, 205, 206
@@ -373,6 +420,9 @@ def GroupByAllPack32(
         f = int(f)
         if GB_ROLLING_SUM <= f <= GB_ROLLING_NANMEAN:
             res.append(_rolling(v, np.asarray(ikey), iGroup, iFirstGroup, nCountGroup, nb, f, int(func_param)))
+            continue
+        if f in (GB_MEDIAN, GB_QUANTILE_MULT):
+            res.append(_quantile(v, np.asarray(ikey), nb, f, int(func_param), int(lo), int(hi)))
             continue
         if f not in (GB_FIRST, GB_NTH, GB_LAST):
             raise ValueError(f"GroupByAllPack32: unsupported function {f}")

@@ -30,6 +30,8 @@ class GB_FUNCTIONS(IntEnum):
     GB_FIRST = 100
     GB_NTH = 101
     GB_LAST = 102
+    GB_MEDIAN = 103
+    GB_QUANTILE_MULT = 106
     # rolling ops on the packed layout (rc.GroupByAllPack32, row-shaped results)
     GB_ROLLING_SUM = 200
     GB_ROLLING_NANSUM = 201

@@ -238,6 +238,38 @@ def test_rolling_ops(rc, vdt, nb):
             np.testing.assert_array_equal(got, exp, err_msg=f"func {fn} param {p} dtype {vdt}")
 
 
+@pytest.mark.parametrize("vdt", _ALL_NUM)
+@pytest.mark.parametrize("nb", [1, 37, 20_000])
+def test_quantile(rc, vdt, nb):
+    rng = np.random.default_rng(nb + 3)
+    n = 120_001
+    ikey = rng.integers(0, nb + 1, n).astype(np.int32)
+    dt = np.dtype(vdt)
+    if dt.kind == "f":
+        v = rng.normal(0, 1e4, n).astype(dt)
+        v[rng.random(n) < 0.05] = np.inf
+        v[rng.random(n) < 0.05] = -np.inf
+        v[rng.random(n) < 0.1] = np.nan
+    elif dt.kind == "b":
+        v = rng.integers(0, 2, n).astype(dt)
+    else:
+        info = np.iinfo(dt)
+        v = rng.integers(info.min, info.max, n, dtype=dt, endpoint=True)
+        v[rng.random(n) < 0.1] = orc.invalid_for(dt)
+    cnt, ig, ifg = orc.BinCount(ikey, nb + 1, pack=True)
+    for q, is_nan in ((0.5, True), (0.5, False), (0.0, True), (1.0, True), (0.29, True), (0.999, False)):
+        fp = orc.quantile_func_param(q, is_nan)
+        for lo in (0, 1):
+            exp = orc.GroupByAllPack32([v], ikey, ig, ifg, cnt, nb, [106], [lo], [nb + 1], fp)[0]
+            got = rc.GroupByAllPack32([v], ikey, ig, ifg, cnt, nb, [106], [lo], [nb + 1], fp)[0]
+            assert got.dtype == np.float64
+            np.testing.assert_array_equal(got, exp, err_msg=f"q {q} nan {is_nan} dtype {vdt}")
+    np.testing.assert_array_equal(rc.GroupByAllPack32([v], ikey, ig, ifg, cnt, nb, [103], [1], [nb + 1], 0)[0],
+                                  orc.GroupByAllPack32([v], ikey, ig, ifg, cnt, nb, [103], [1], [nb + 1], 0)[0])
+    s = np.array([b"a"] * n)
+    assert rc.GroupByAllPack32([s], ikey, ig, ifg, cnt, nb, [103], [1], [nb + 1], 0)[0] is None
+
+
 def test_rolling_kat(rc):
     # tests/test_fastarray.py:1297-1305 through a single group
     x = np.array([1, 2, 3, np.nan, np.nan, np.nan])

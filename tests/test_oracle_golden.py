@@ -269,6 +269,50 @@ def test_rolling_ops_pinned_to_pandas_and_kat():
     assert r.dtype == np.int64 and r.tolist() == [1, 3, 6, 5, 3, 0]
 
 
+@pytest.mark.parametrize("N,N_cat,q,nan_fraction,dtype", [
+    (1000, 7, 0.5, 0.1, np.float64), (5000, 45, 0.29, 0.0, np.int32), (97, 1, 0.9, 0.3, np.float64),
+    (2643, 10, 0.0, 0.2, np.int32), (500, 3, 1.0, 0.5, np.float64), (10_000, 100, 0.123, 0.05, np.float64)])
+@pytest.mark.parametrize("with_infs", [False, True])
+def test_quantile_replays_reference_test(N, N_cat, q, nan_fraction, dtype, with_infs):
+    # tests/test_groupbyops.py:540-700: quantile / nanquantile against np.quantile / np.nanquantile ("midpoint"),
+    # infinities through (lower + higher) / 2 (rt_numpy.py:4202-4245); integer columns carry sentinels for NaN
+    import warnings
+    rng = np.random.default_rng((N * N_cat * int(q * 1000) * int(nan_fraction * 1000)) % 10_000)
+    cat = rng.integers(0, N_cat, N)
+    g = orc.groupbyhash(cat)
+    ik, U = g["iKey"], g["unique_count"]
+    cnt, ig, ifg = orc.BinCount(ik, U + 1, pack=True)
+    data = rng.normal(rng.uniform(-10_000, 10_000), rng.uniform(0.0, 10_000), size=N).astype(dtype)
+    ref = data.astype(np.float64)
+    if with_infs and np.dtype(dtype).kind == "f":
+        for val in (np.inf, -np.inf):
+            m = rng.random(N) < 0.1
+            data[m] = val
+            ref[m] = val
+    nan_idx = rng.random(N) < nan_fraction
+    ref[nan_idx] = np.nan
+    data[nan_idx] = orc.invalid_for(dtype)
+    for is_nan, npf in ((False, np.quantile), (True, np.nanquantile)):
+        got = orc.GroupByAllPack32([data], ik, ig, ifg, cnt, U, [orc.GB_QUANTILE_MULT], [1], [U + 1], orc.quantile_func_param(q, is_nan))[0]
+        assert got.dtype == np.float64 and np.isnan(got[0])
+        for b in range(1, U + 1):
+            sl = ref[ik == b]
+            with np.errstate(all="ignore"), warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                exp = (npf(sl, q, method="lower") + npf(sl, q, method="higher")) / 2
+            np.testing.assert_allclose(got[b], exp, rtol=1e-12, equal_nan=True)
+    # GB_MEDIAN "auto handles nan" (rt_enum.py:506); tests/test_groupby.py:83 median KAT
+    med = orc.GroupByAllPack32([data], ik, ig, ifg, cnt, U, [orc.GB_MEDIAN], [1], [U + 1], 0)[0]
+    nanmed = orc.GroupByAllPack32([data], ik, ig, ifg, cnt, U, [orc.GB_QUANTILE_MULT], [1], [U + 1], orc.quantile_func_param(0.5, True))[0]
+    np.testing.assert_array_equal(med, nanmed)
+    # tests/test_groupby.py:13-104: key bool [T,F,T,F,T] (bins False=1, True=2), values [3,4,5,1,2] -> medians [2.5, 3]
+    kb = np.array([2, 1, 2, 1, 2], np.int8)
+    c2, g2, f2 = orc.BinCount(kb, 3, pack=True)
+    for vdt in (np.int8, np.uint16, np.int64, np.float32, np.float64):
+        vals = np.array([3, 4, 5, 1, 2], vdt)
+        assert orc.GroupByAllPack32([vals], kb, g2, f2, c2, 2, [orc.GB_MEDIAN], [1], [3], 0)[0][1:].tolist() == [2.5, 3.0]
+
+
 def test_cutoffs_kat():
     # tests/test_pgroupby.py:7-86
     rng = np.random.default_rng(0)

@@ -48,7 +48,7 @@ typedef enum {
   RTB_GB_FIRST = 100, RTB_GB_NTH = 101, RTB_GB_LAST = 102, RTB_GB_MEDIAN = 103, RTB_GB_QUANTILE_MULT = 106,
   RTB_GB_ROLLING_SUM = 200, RTB_GB_ROLLING_NANSUM = 201, RTB_GB_ROLLING_DIFF = 202, RTB_GB_ROLLING_SHIFT = 203,
   RTB_GB_ROLLING_COUNT = 204, RTB_GB_ROLLING_MEAN = 205, RTB_GB_ROLLING_NANMEAN = 206,
-  RTB_GB_CUMSUM = 300, RTB_GB_CUMPROD = 302, RTB_GB_CUMNANMAX = 306, RTB_GB_CUMNANMIN = 307, RTB_GB_CUMMAX = 308,
+  RTB_GB_CUMSUM = 300, RTB_GB_EMADECAY = 301, RTB_GB_CUMPROD = 302, RTB_GB_EMANORMAL = 304, RTB_GB_EMAWEIGHTED = 305, RTB_GB_CUMNANMAX = 306, RTB_GB_CUMNANMIN = 307, RTB_GB_CUMMAX = 308,
   RTB_GB_CUMMIN = 309
 } rtb_gb_func;
 
@@ -189,6 +189,20 @@ int rtb_groupby_quantile(const void* values, int vdtype, const void* ikey, int k
                          const int32_t* ncountgroup, int64_t nrows, int64_t unique_rows, double q, int nan_aware,
                          int64_t bin_low, int64_t bin_high, double* out, void* workspace, size_t workspace_bytes,
                          void* stream);
+
+/* ---- 8f.2: rc.EmaAll32 time-decayed averages — GB_EMADECAY (301), GB_EMANORMAL (304), GB_EMAWEIGHTED (305),
+ * func_param = (decay_rate, time, filter, reset_filter); formulas in riptable/rt_groupbyops.py:3306-3498:
+ *   decay:    out = x + last * exp(-rate * (t - t_last))
+ *   normal:   w = exp(-rate * (t - t_last)); out = x * (1 - w) + last * w      (a group starts at its first value)
+ *   weighted: out = x * (1 - rate) + last * rate                               (no time array)
+ * Rows the op-filter excludes show the group's current value (0 before the first included row) and do not advance
+ * t_last; reset_filter restarts the group at that row; bin-0 rows get the invalid.  out: float32 for float32 values,
+ * float64 otherwise (rtb_ema_out_dtype).  time: any numeric dtype (tdtype). */
+int rtb_ema_out_dtype(int func, int vdtype);
+size_t rtb_ema_workspace_bytes(int64_t nrows, int64_t unique_rows);
+int rtb_groupby_ema(int func, const void* values, int vdtype, const void* ikey, int kdtype, int64_t nrows,
+                    int64_t unique_rows, const void* time, int tdtype, double decay_rate, const uint8_t* filter,
+                    const uint8_t* reset_filter, void* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a10: rc.MakeiFirst(key, n, filter, mode) / rc.MakeiNext(key, n, mode) — riptable/rt_numpy.py:1791-1854 */
 int rtb_make_ifirst(const void* ikey, int kdtype, int64_t nrows, int64_t n, const uint8_t* filter, int mode,

@@ -460,6 +460,61 @@ def _is_invalid(v):
     return np.zeros(len(v), bool)
 
 
+GB_EMADECAY, GB_EMANORMAL, GB_EMAWEIGHTED = 301, 304, 305
+
+
+def _ema(values, ikey, funcNum, func_param):
+    """rt_groupbyops.py:3306-3498, the docstring formulas walked row by row:
+      decay:    Output[i] = Column[i] + LastEma[grp] * exp(-decay_rate * (Time[i] - LastTime[grp]))
+      normal:   w = exp(-decay_rate * (Time[i] - LastTime[grp])); LastEma = Column[i] * (1 - w) + LastEma * w
+      weighted: LastEma = Column[i] * (1 - decay_rate) + LastEma * decay_rate
+    The docstring tables pin the start of a group: ema_normal / ema_weighted give the first value back
+    (group2 == 1: 1.00, 2.50, 4.75 with decay 0.5), ema_decay starts from LastEma = 0.
+    UNPINNED (this restatement's choice, documented in the C header): a row the op-filter excludes
+    shows LastEma (0 before the first included row) and leaves LastTime alone; reset_filter restarts
+    the group at that row; bin-0 rows get the invalid; output float32 for float32 input, else float64."""
+    f = int(funcNum)
+    rate, time, filt, reset = func_param[0], func_param[1], func_param[2], func_param[3]
+    ik = np.asarray(ikey).astype(np.int64)
+    n = len(ik)
+    t = None if f == GB_EMAWEIGHTED else np.asarray(time).astype(np.float64)
+    inc = ik > 0
+    if filt is not None:
+        inc &= np.asarray(filt, dtype=bool)
+    rst = np.zeros(n, bool) if reset is None else np.asarray(reset, dtype=bool)
+    res = []
+    for v in values:
+        v = np.asarray(v)
+        if v.dtype.kind not in "biuf":
+            res.append(None)
+            continue
+        x = v.astype(np.float64)
+        odt = np.dtype(np.float32) if v.dtype == np.float32 else np.dtype(np.float64)
+        out = np.full(n, np.nan)
+        last, lastt, started = {}, {}, {}
+        with np.errstate(over="ignore", invalid="ignore"):
+            for i in range(n):
+                g = ik[i]
+                if g <= 0:
+                    continue
+                if not inc[i]:
+                    out[i] = last.get(g, 0.0)
+                    continue
+                if rst[i] or not started.get(g, False):
+                    y = x[i]
+                elif f == GB_EMAWEIGHTED:
+                    y = x[i] * (1.0 - rate) + last[g] * rate
+                else:
+                    w = np.exp(-rate * (t[i] - lastt[g]))
+                    y = x[i] + last[g] * w if f == GB_EMADECAY else x[i] * (1.0 - w) + last[g] * w
+                last[g], started[g] = y, True
+                if t is not None:
+                    lastt[g] = t[i]
+                out[i] = y
+        res.append(out.astype(odt))
+    return res
+
+
 def EmaAll32(values, ikey, unique_rows, funcNum, func_param):
     """Per-group running sum / product / min / max in original row order (tests/test_groupby.py:555-602,
     tests/test_groupbyops.py:458-538).
@@ -473,6 +528,8 @@ def EmaAll32(values, ikey, unique_rows, funcNum, func_param):
     reset_filter (UNPINNED): on a row that passes the filter and has reset set, restart the
     accumulator before applying the row (rt_fastarraynumba.py:506-524)."""
     f = int(funcNum)
+    if f in (GB_EMADECAY, GB_EMANORMAL, GB_EMAWEIGHTED):
+        return _ema(values, ikey, f, func_param)
     if f not in (GB_CUMSUM, GB_CUMPROD, GB_CUMNANMAX, GB_CUMNANMIN, GB_CUMMAX, GB_CUMMIN):
         raise ValueError(f"EmaAll32: unsupported function {funcNum}")
     filt = reset = None

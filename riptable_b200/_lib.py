@@ -60,6 +60,9 @@ PROTOTYPES = {
     "rtb_reindex_groups": (C.c_int, [_vp, _i64, _vp, _i64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _i64, _vp, _vp]),
     "rtb_quantile_workspace_bytes": (_sz, [_i64, _i64]),
     "rtb_groupby_quantile": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _i64, _i64, C.c_double, _i32, _i64, _i64, _vp, _vp, _sz, _vp]),
+    "rtb_ema_out_dtype": (C.c_int, [_i32, _i32]),
+    "rtb_ema_workspace_bytes": (_sz, [_i64, _i64]),
+    "rtb_groupby_ema": (C.c_int, [_i32, _vp, _i32, _vp, _i32, _i64, _i64, _vp, _i32, C.c_double, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rtb_rolling_out_dtype": (C.c_int, [_i32, _i32]),
     "rtb_groupby_rolling": (C.c_int, [_i32, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "rtb_cumop_out_dtype": (C.c_int, [_i32, _i32]),

@@ -386,6 +386,197 @@ static int cumop_launch(const CumArgs& a, int64_t ntiles, cudaStream_t stream) {
   return RTB_OK;
 }
 
+// ---- 8f.2: time-decayed moving averages (EmaAll32 functions 301 / 304 / 305) ---------------------------------
+// Every recurrence is y_i = a_i * y_{i-1} + b_i over the packed order.  A row that restarts its group's state (first
+// included row of a bin, or reset_filter) has a_i = 0, so a PLAIN inclusive scan of the affine maps under composition
+// (a1, b1) o (a2, b2) = (a1 a2, a2 b1 + b2) needs no segment flags.  Rows the op-filter excludes are the identity
+// (1, 0): they show the group's current value and leave its clock alone, so the decay of the next included row spans
+// the time since the previous INCLUDED row -- found with a plain max-scan over (included ? position : -1).
+struct Affine {
+  double a, b;
+};
+struct AffineOp {
+  typedef Affine T;
+  __device__ static Affine identity() { return Affine{1.0, 0.0}; }
+  __device__ static Affine combine(Affine x, Affine y) { return Affine{x.a * y.a, y.a * x.b + y.b}; }  // x first
+  __device__ static Affine shfl_up(Affine v, int d) { return Affine{__shfl_up_sync(0xffffffffu, v.a, d), __shfl_up_sync(0xffffffffu, v.b, d)}; }
+};
+struct MaxI32Op {
+  typedef int32_t T;
+  __device__ static int32_t identity() { return -1; }
+  __device__ static int32_t combine(int32_t x, int32_t y) { return x > y ? x : y; }
+  __device__ static int32_t shfl_up(int32_t v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+};
+
+// exclusive prefix of this thread's value across the block (block total in *total)
+template <typename Op>
+__device__ __forceinline__ typename Op::T plain_block_exclusive(typename Op::T x, typename Op::T* total) {
+  typedef typename Op::T T;
+  __shared__ T wtot[kSegThreads / 32];
+  __shared__ T btot;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  T inc = x;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    T t = Op::shfl_up(inc, d);
+    if (lane >= d) inc = Op::combine(t, inc);
+  }
+  if (lane == 31) wtot[w] = inc;
+  __syncthreads();
+  T ex = Op::identity();
+  for (int i = 0; i < w; i++) ex = Op::combine(ex, wtot[i]);
+  T prev = Op::shfl_up(inc, 1);
+  if (lane > 0) ex = Op::combine(ex, prev);
+  if (threadIdx.x == kSegThreads - 1) btot = Op::combine(ex, x);
+  __syncthreads();
+  *total = btot;
+  __syncthreads();
+  return ex;
+}
+
+// Plain inclusive scan, in place, three launches: tile totals, scan of the totals (one block), apply.
+template <typename Op>
+__global__ void __launch_bounds__(kSegThreads) plain_tiles_kernel(const typename Op::T* __restrict__ x, int64_t n, typename Op::T* tile_agg) {
+  typedef typename Op::T T;
+  const int64_t base = (int64_t)blockIdx.x * kSegTile + (int64_t)threadIdx.x * kSegItems;
+  T acc = Op::identity();
+#pragma unroll
+  for (int i = 0; i < kSegItems; i++)
+    if (base + i < n) acc = Op::combine(acc, x[base + i]);
+  T total;
+  plain_block_exclusive<Op>(acc, &total);
+  if (threadIdx.x == 0) tile_agg[blockIdx.x] = total;
+}
+template <typename Op>
+__global__ void __launch_bounds__(kSegThreads) plain_scan_tiles_kernel(typename Op::T* tile_agg, int64_t ntiles) {
+  typedef typename Op::T T;
+  T carry = Op::identity();
+  for (int64_t b = 0; b < ntiles; b += kSegThreads) {
+    const int64_t t = b + threadIdx.x;
+    T x = t < ntiles ? tile_agg[t] : Op::identity();
+    T total;
+    T ex = plain_block_exclusive<Op>(x, &total);
+    if (t < ntiles) tile_agg[t] = Op::combine(carry, ex);
+    carry = Op::combine(carry, total);
+  }
+}
+template <typename Op>
+__global__ void __launch_bounds__(kSegThreads) plain_apply_kernel(typename Op::T* __restrict__ x, int64_t n, const typename Op::T* __restrict__ tile_agg) {
+  typedef typename Op::T T;
+  const int64_t base = (int64_t)blockIdx.x * kSegTile + (int64_t)threadIdx.x * kSegItems;
+  T v[kSegItems];
+  T acc = Op::identity();
+#pragma unroll
+  for (int i = 0; i < kSegItems; i++) {
+    v[i] = base + i < n ? x[base + i] : Op::identity();
+    acc = Op::combine(acc, v[i]);
+  }
+  T total;
+  T run = Op::combine(tile_agg[blockIdx.x], plain_block_exclusive<Op>(acc, &total));
+#pragma unroll
+  for (int i = 0; i < kSegItems; i++)
+    if (base + i < n) {
+      run = Op::combine(run, v[i]);
+      x[base + i] = run;
+    }
+}
+template <typename Op>
+static int plain_inclusive_scan(typename Op::T* x, int64_t n, typename Op::T* tile_agg, cudaStream_t stream) {
+  const int64_t ntiles = (n + kSegTile - 1) / kSegTile;
+  plain_tiles_kernel<Op><<<(unsigned)ntiles, kSegThreads, 0, stream>>>(x, n, tile_agg);
+  RTB_LAUNCH_CHECK();
+  plain_scan_tiles_kernel<Op><<<1, kSegThreads, 0, stream>>>(tile_agg, ntiles);
+  RTB_LAUNCH_CHECK();
+  plain_apply_kernel<Op><<<(unsigned)ntiles, kSegThreads, 0, stream>>>(x, n, tile_agg);
+  RTB_LAUNCH_CHECK();
+  return RTB_OK;
+}
+
+struct EmaArgs {
+  const void* values;
+  int vdt, odt;
+  const void* time;
+  int tdt;
+  int func;
+  double rate;
+  const uint32_t* skeys;
+  const uint32_t* igroup;
+  const uint8_t* filter;
+  const uint8_t* reset;
+  int64_t n;
+  int32_t* lastinc;  // in: included ? position : -1; after the max-scan: last included position <= j
+  Affine* maps;
+  void* out;
+};
+
+__global__ void __launch_bounds__(256) ema_mark_kernel(EmaArgs a) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.n; j += (int64_t)gridDim.x * blockDim.x) {
+    const bool inc = a.skeys[j] != 0 && (!a.filter || a.filter[a.igroup[j]]);
+    a.lastinc[j] = inc ? (int32_t)j : -1;
+  }
+}
+
+__global__ void __launch_bounds__(256) ema_maps_kernel(EmaArgs a) {
+  const int vsz = dsize(a.vdt), tsz = a.time ? dsize(a.tdt) : 0;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.n; j += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t k = a.skeys[j];
+    const bool seg_first = j == 0 || a.skeys[j - 1] != k;
+    Affine m;
+    if (a.lastinc[j] != (int32_t)j) {  // bin 0, or excluded by the op-filter: show the running value
+      m = seg_first ? Affine{0.0, 0.0} : Affine{1.0, 0.0};
+    } else {
+      const uint32_t row = a.igroup[j];
+      const double x = raw_to_f64(load_raw1(a.values, vsz, row), a.vdt);
+      const int32_t prev = j > 0 ? a.lastinc[j - 1] : -1;
+      const bool restart = prev < 0 || a.skeys[prev] != k || (a.reset && a.reset[row]);
+      if (restart) {
+        m = Affine{0.0, x};
+      } else if (a.func == RTB_GB_EMAWEIGHTED) {
+        m = Affine{a.rate, x * (1.0 - a.rate)};
+      } else {
+        const double t = raw_to_f64(load_raw1(a.time, tsz, row), a.tdt);
+        const double tp = raw_to_f64(load_raw1(a.time, tsz, a.igroup[prev]), a.tdt);
+        const double w = exp(-a.rate * (t - tp));
+        m = a.func == RTB_GB_EMADECAY ? Affine{w, x} : Affine{w, x * (1.0 - w)};
+      }
+    }
+    a.maps[j] = m;
+  }
+}
+
+__global__ void __launch_bounds__(256) ema_store_kernel(EmaArgs a) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.n; j += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t row = a.igroup[j];
+    unsigned long long raw;
+    if (a.skeys[j] == 0) raw = invalid_raw(a.odt);
+    else if (a.odt == RTB_F32) raw = __float_as_uint((float)a.maps[j].b);
+    else raw = f64_bits(a.maps[j].b);
+    store_raw(a.out, a.odt, row, raw);
+  }
+}
+
+struct EmaLayout {
+  PackLayout pack;
+  void* pack_ws;
+  int32_t *lastinc, *tile_i;
+  Affine *maps, *tile_a;
+  size_t pack_bytes, bytes;
+};
+static EmaLayout ema_layout(void* ws, size_t wsbytes, int64_t n) {
+  Arena a(ws, wsbytes);
+  EmaLayout L;
+  L.pack_bytes = pack_layout(nullptr, 0, n, 1).bytes + 256;
+  L.pack_ws = a.take<uint8_t>(L.pack_bytes);
+  L.pack = pack_layout(L.pack_ws, L.pack_bytes, n, 1);
+  const size_t m = (size_t)(n > 0 ? n : 1), tiles = (m + kSegTile - 1) / kSegTile + 1;
+  L.lastinc = a.take<int32_t>(m);
+  L.maps = a.take<Affine>(m);
+  L.tile_i = a.take<int32_t>(tiles);
+  L.tile_a = a.take<Affine>(tiles);
+  L.bytes = a.off;
+  return L;
+}
+
 struct CumLayout {
   PackLayout pack;
   void* pack_ws;
@@ -591,6 +782,58 @@ extern "C" int rtb_groupby_cumsum(const void* values, int vdt, const void* ikey,
                                   size_t workspace_bytes, void* stream_) {
   return rtb_groupby_cumop(RTB_GB_CUMSUM, values, vdt, ikey, kdt, nrows, unique_rows, filter, reset_filter, out, workspace,
                            workspace_bytes, stream_);
+}
+
+extern "C" int rtb_ema_out_dtype(int func, int vdt) {
+  if (func != RTB_GB_EMADECAY && func != RTB_GB_EMANORMAL && func != RTB_GB_EMAWEIGHTED) return RTB_ERR_UNSUPPORTED;
+  if (vdt < RTB_BOOL || vdt > RTB_F64) return RTB_ERR_UNSUPPORTED;
+  return vdt == RTB_F32 ? RTB_F32 : RTB_F64;
+}
+
+extern "C" size_t rtb_ema_workspace_bytes(int64_t nrows, int64_t unique_rows) {
+  (void)unique_rows;
+  if (nrows < 0) return 0;
+  return ema_layout(nullptr, 0, nrows).bytes + 256;
+}
+
+extern "C" int rtb_groupby_ema(int func, const void* values, int vdt, const void* ikey, int kdt, int64_t nrows,
+                               int64_t unique_rows, const void* time, int tdt, double decay_rate, const uint8_t* filter,
+                               const uint8_t* reset_filter, void* out, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RTB_ARG(is_ikey_dtype(kdt), "EmaAll32: ikey must be int8/16/32/64");
+  const int odt = rtb_ema_out_dtype(func, vdt);
+  if (odt < 0) {
+    set_error("EmaAll32: function %d is not provided for dtype %d", func, vdt);
+    return RTB_ERR_UNSUPPORTED;
+  }
+  RTB_ARG(nrows >= 0 && nrows <= 2147483646ll && unique_rows >= 0, "EmaAll32: bad sizes");
+  RTB_ARG(func == RTB_GB_EMAWEIGHTED || (time && tdt >= RTB_BOOL && tdt <= RTB_F64), "EmaAll32: ema_decay / ema_normal need a numeric time array");
+  if (nrows == 0) return RTB_OK;
+  RTB_ARG(values && ikey && out, "EmaAll32: null pointer");
+  RTB_ARG(((uintptr_t)ikey % (4 * dtype_size(kdt))) == 0, "EmaAll32: ikey must be aligned to 4 rows");
+  EmaLayout L = ema_layout(workspace, workspace_bytes, nrows);
+  RTB_ARG(workspace && L.bytes <= workspace_bytes, "EmaAll32: workspace too small");
+  uint32_t *skeys, *ig;
+  int rc = pack_sort(ikey, kdt, nrows, unique_rows + 1, L.pack, stream, &skeys, &ig, "EmaAll32");
+  if (rc != RTB_OK) return rc;
+  EmaArgs a;
+  a.values = values; a.vdt = vdt; a.odt = odt; a.time = func == RTB_GB_EMAWEIGHTED ? nullptr : time; a.tdt = tdt; a.func = func;
+  a.rate = decay_rate; a.skeys = skeys; a.igroup = ig; a.filter = filter; a.reset = reset_filter; a.n = nrows;
+  a.lastinc = L.lastinc; a.maps = L.maps; a.out = out;
+  const int g = grid_for(nrows, 256, 4);
+  prof_begin(PROF_SEGSCAN, stream);
+  ema_mark_kernel<<<g, 256, 0, stream>>>(a);
+  RTB_LAUNCH_CHECK();
+  rc = plain_inclusive_scan<MaxI32Op>(L.lastinc, nrows, L.tile_i, stream);
+  if (rc != RTB_OK) return rc;
+  ema_maps_kernel<<<g, 256, 0, stream>>>(a);
+  RTB_LAUNCH_CHECK();
+  rc = plain_inclusive_scan<AffineOp>(L.maps, nrows, L.tile_a, stream);
+  if (rc != RTB_OK) return rc;
+  ema_store_kernel<<<g, 256, 0, stream>>>(a);
+  RTB_LAUNCH_CHECK();
+  prof_end(PROF_SEGSCAN, stream, (uint64_t)nrows);
+  return RTB_OK;
 }
 
 extern "C" int rtb_make_ifirst(const void* ikey, int kdt, int64_t nrows, int64_t n, const uint8_t* filter, int mode,

@@ -42,6 +42,9 @@ class GB_FUNCTIONS(IntEnum):
     GB_ROLLING_NANMEAN = 206
     # row-shaped accumulations (rc.EmaAll32)
     GB_CUMSUM = 300
+    GB_EMADECAY = 301
+    GB_EMANORMAL = 304
+    GB_EMAWEIGHTED = 305
     GB_CUMPROD = 302
     GB_CUMNANMAX = 306
     GB_CUMNANMIN = 307

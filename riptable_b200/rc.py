@@ -497,32 +497,61 @@ _CUM_FUNCS = (GB_FUNCTIONS.GB_CUMSUM, GB_FUNCTIONS.GB_CUMPROD, GB_FUNCTIONS.GB_C
               GB_FUNCTIONS.GB_CUMMAX, GB_FUNCTIONS.GB_CUMMIN)
 
 
+_EMA_FUNCS = (GB_FUNCTIONS.GB_EMADECAY, GB_FUNCTIONS.GB_EMANORMAL, GB_FUNCTIONS.GB_EMAWEIGHTED)
+
+
 def EmaAll32(values, ikey, unique_rows, funcNum, func_param):
-    if int(funcNum) not in _CUM_FUNCS:
-        raise NotImplementedError(f"EmaAll32: function {int(funcNum)} is outside this build's hot path")
     func = int(funcNum)
+    if func not in _CUM_FUNCS and func not in _EMA_FUNCS:
+        raise NotImplementedError(f"EmaAll32: function {func} is outside this build's hot path")
     values = _as_list(values)
-    filt = reset = None
+    rate, time, filt, reset = 0.0, None, None, None
     if isinstance(func_param, (tuple, list)) and len(func_param) >= 4:
-        filt, reset = func_param[2], func_param[3]
+        rate, time, filt, reset = func_param[0], func_param[1], func_param[2], func_param[3]
     device_mode = _is_device(ikey) or any(_is_device(v) for v in values)
     k = _ikey_dev(ikey)
     fdev = _bool_dev(filt, k.n) if filt is not None else None
     rdev = _bool_dev(reset, k.n, "reset_filter") if reset is not None else None
+    tdev = None
+    if func in _EMA_FUNCS:
+        # 8f.2: riptable/rt_groupbyops.py:3279-3498 — func_param = (decay_rate, time, filter, reset_filter)
+        if rate is None:
+            raise ValueError("EmaAll32: the ema functions need a decay_rate")
+        if func != GB_FUNCTIONS.GB_EMAWEIGHTED:
+            if time is None:
+                raise ValueError("EmaAll32: ema_decay / ema_normal need a time array")
+            tdev = _to_dev(time)
+            if tdev.n != k.n:
+                raise ValueError(f"EmaAll32: the time array length {tdev.n} must match the key length {k.n}")
+            if tdev.dtype.kind not in "iuf" or tdev.dtype == np.float16:
+                raise TypeError("EmaAll32: the time array must be an integer or floating point array")
     out = []
     for v in values:
         d = _to_dev(v)
         vcode = dtype_code(d.dtype) if d.dtype.kind in "biuf" and d.dtype != np.float16 else RTB_BYTES
-        ocode = lib.rtb_cumop_out_dtype(func, vcode) if vcode < RTB_BYTES else -1
+        if func in _EMA_FUNCS:
+            ocode = lib.rtb_ema_out_dtype(func, vcode) if vcode < RTB_BYTES else -1
+        else:
+            ocode = lib.rtb_cumop_out_dtype(func, vcode) if vcode < RTB_BYTES else -1
         if ocode < 0:
             out.append(None)
             continue
+        if d.n != k.n:
+            raise ValueError("EmaAll32: value and key lengths differ")
         res = DevArray.empty(k.n, code_dtype(ocode))
-        ws = _ws(lib.rtb_cumsum_workspace_bytes(k.n, int(unique_rows)))
-        check(lib.rtb_groupby_cumop(func, C.c_void_p(d.ptr), vcode, C.c_void_p(k.ptr), dtype_code(k.dtype), k.n,
-                                    int(unique_rows), C.c_void_p(fdev.ptr) if fdev is not None else None,
-                                    C.c_void_p(rdev.ptr) if rdev is not None else None,
-                                    C.c_void_p(res.ptr), C.c_void_p(ws.data_ptr()), ws.numel(), _stream()))
+        fptr = C.c_void_p(fdev.ptr) if fdev is not None else None
+        rptr = C.c_void_p(rdev.ptr) if rdev is not None else None
+        if func in _EMA_FUNCS:
+            ws = _ws(lib.rtb_ema_workspace_bytes(k.n, int(unique_rows)))
+            check(lib.rtb_groupby_ema(func, C.c_void_p(d.ptr), vcode, C.c_void_p(k.ptr), dtype_code(k.dtype), k.n, int(unique_rows),
+                                      C.c_void_p(tdev.ptr) if tdev is not None else None,
+                                      dtype_code(tdev.dtype) if tdev is not None else 0, float(rate), fptr, rptr,
+                                      C.c_void_p(res.ptr), C.c_void_p(ws.data_ptr()), ws.numel(), _stream()))
+        else:
+            ws = _ws(lib.rtb_cumsum_workspace_bytes(k.n, int(unique_rows)))
+            check(lib.rtb_groupby_cumop(func, C.c_void_p(d.ptr), vcode, C.c_void_p(k.ptr), dtype_code(k.dtype), k.n,
+                                        int(unique_rows), fptr, rptr,
+                                        C.c_void_p(res.ptr), C.c_void_p(ws.data_ptr()), ws.numel(), _stream()))
         out.append(_from_dev(res, device_mode))
     return out
 

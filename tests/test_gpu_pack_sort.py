@@ -270,6 +270,42 @@ def test_quantile(rc, vdt, nb):
     assert rc.GroupByAllPack32([s], ikey, ig, ifg, cnt, nb, [103], [1], [nb + 1], 0)[0] is None
 
 
+@pytest.mark.parametrize("vdt", [np.bool_, np.int8, np.int32, np.uint64, np.float32, np.float64])
+@pytest.mark.parametrize("nb", [1, 9, 4000])
+def test_ema(rc, vdt, nb):
+    rng = np.random.default_rng(nb + 17)
+    n = 30_011  # the oracle walks the rows in Python
+    ikey = rng.integers(0, nb + 1, n).astype(np.int32)
+    dt = np.dtype(vdt)
+    v = (rng.normal(0, 10, n).astype(dt) if dt.kind == "f" else rng.integers(0, 2 if dt.kind == "b" else 100, n).astype(dt))
+    filt = rng.random(n) < 0.8
+    reset = rng.random(n) < 0.01
+    for tdt in (np.float64, np.int64, np.int32):
+        t = np.cumsum(rng.integers(0, 5, n)).astype(tdt)
+        for fn, rate in ((301, 0.05), (304, 0.3), (305, 0.9)):
+            for fp in [(rate, t, None, None), (rate, t, filt, reset)]:
+                exp = orc.EmaAll32([v], ikey, nb, fn, fp)[0]
+                got = rc.EmaAll32([v], ikey, nb, fn, fp)[0]
+                assert got.dtype == exp.dtype
+                tol = 2e-5 if exp.dtype == np.float32 else 1e-11
+                scale = float(np.nanmax(np.abs(exp))) + 1.0
+                np.testing.assert_allclose(got, exp, rtol=tol, atol=tol * scale, equal_nan=True, err_msg=f"func {fn} time {tdt}")
+        if tdt is not np.float64:
+            continue
+    assert rc.EmaAll32([np.array([b"a"] * n)], ikey, nb, 305, (0.5, None, None, None))[0] is None
+    with pytest.raises(ValueError):
+        rc.EmaAll32([v], ikey, nb, 301, (0.5, None, None, None))
+
+
+def test_ema_docstring_kats(rc):
+    test = np.arange(10)
+    g = (np.arange(10) % 3 + 1).astype(np.int8)
+    normal = rc.EmaAll32([test], g, 3, 304, (1.0, np.arange(10), None, None))[0]
+    weighted = rc.EmaAll32([test], g, 3, 305, (0.5, None, None, None))[0]
+    assert np.round(normal, 2).tolist() == [0.00, 1.00, 2.00, 2.85, 3.85, 4.85, 5.84, 6.84, 7.84, 8.84]
+    assert np.round(weighted, 2).tolist() == [0.00, 1.00, 2.00, 1.50, 2.50, 3.50, 3.75, 4.75, 5.75, 6.38]
+
+
 def test_rolling_kat(rc):
     # tests/test_fastarray.py:1297-1305 through a single group
     x = np.array([1, 2, 3, np.nan, np.nan, np.nan])

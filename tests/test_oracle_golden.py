@@ -313,6 +313,25 @@ def test_quantile_replays_reference_test(N, N_cat, q, nan_fraction, dtype, with_
         assert orc.GroupByAllPack32([vals], kb, g2, f2, c2, 2, [orc.GB_MEDIAN], [1], [3], 0)[0][1:].tolist() == [2.5, 3.0]
 
 
+def test_ema_docstring_kats():
+    # rt_groupbyops.py:3378-3386 (ema_decay; the table shows its inputs rounded to 2 decimals) and :3424-3446 /
+    # :3486-3508 (ema_normal / ema_weighted on rt.arange(10) grouped by arange(10) % 3, printed to 2 decimals)
+    ik = np.ones(3, np.int8)
+    r = orc.EmaAll32([np.array([-3.11, 210.54, 49.97])], ik, 1, orc.GB_EMADECAY,
+                     (np.log(2) / (1e3 * 100), np.array([25.65, 38.37, 41.66]), None, None))[0]
+    np.testing.assert_allclose(r, [-3.11271882, 207.42784495, 257.39155897], rtol=1e-3)
+    test = np.arange(10)
+    g = (np.arange(10) % 3 + 1).astype(np.int8)
+    normal = orc.EmaAll32([test], g, 3, orc.GB_EMANORMAL, (1.0, np.arange(10), None, None))[0]
+    weighted = orc.EmaAll32([test], g, 3, orc.GB_EMAWEIGHTED, (0.5, None, None, None))[0]
+    assert np.round(normal, 2).tolist() == [0.00, 1.00, 2.00, 2.85, 3.85, 4.85, 5.84, 6.84, 7.84, 8.84]
+    assert np.round(weighted, 2).tolist() == [0.00, 1.00, 2.00, 1.50, 2.50, 3.50, 3.75, 4.75, 5.75, 6.38]
+    # this restatement's choices for what the reference leaves open: excluded rows show the running value
+    f = np.array([True, True, True, False, True, True, True, True, True, True])
+    w = orc.EmaAll32([test], g, 3, orc.GB_EMAWEIGHTED, (0.5, None, f, None))[0]
+    assert w[3] == 0.0 and w[6] == 3.0  # row 3 excluded: group 1 still at 0; row 6: 6 * .5 + 0 * .5
+
+
 def test_cutoffs_kat():
     # tests/test_pgroupby.py:7-86
     rng = np.random.default_rng(0)

@@ -823,6 +823,17 @@ def IsMember32(a, b, h=2, hint_size=0):
     return _ismember_cols([a], [b])
 
 
+def IsMemberCategorical(a, b, h=2, hint_size=0):
+    """rt_numpy.py:1388-1389 (`ismember(a, b, base_index=1)`): 1-based position of the first occurrence in b, 0 where
+    absent -- the shape rt_grouping.py:959-963 feeds straight back in as Categorical codes.  UNPINNED: the index dtype
+    (here int_dtype_from_len(len(b) + 1))."""
+    found, idx = _ismember_cols([a], [b])
+    odt = np.dtype(_index_dtype_from_len(len(np.asarray(b)) + 1))
+    out = np.zeros(len(idx), odt)
+    out[found] = idx[found].astype(np.int64) + 1
+    return found, out
+
+
 def MultiKeyIsMember32(a_tuple, b_tuple, hint_size=0):
     """rt_numpy.py:1325: rc.MultiKeyIsMember32((a_cols,), (b_cols,), hint_size) -- tuple equality across the columns."""
     return _ismember_cols(list(a_tuple[0]), list(b_tuple[0]))

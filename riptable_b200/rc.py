@@ -711,7 +711,7 @@ def ReIndexGroups(ikey, uikey, u_cutoffs, i_cutoffs):
 
 __all__ = ["GroupByStream", "ReIndexGroups", "LexPartition", "MultiKeyGroupBy32", "CombineFilter", "CombineAccum1Filter", "CombineAccum2Filter", "GroupByAll32", "BinCount",
            "GroupFromBinCount", "GroupByPack32", "GroupByAllPack32", "EmaAll32", "MakeiFirst", "MakeiNext", "LexSort32",
-           "LexSort64", "GroupFromLexSort", "ReverseShuffle", "IsMember32", "MultiKeyIsMember32", "LedgerFunction"]
+           "LexSort64", "GroupFromLexSort", "ReverseShuffle", "IsMember32", "IsMemberCategorical", "MultiKeyIsMember32", "LedgerFunction"]
 
 
 # ==================================================================================================
@@ -738,7 +738,7 @@ def _concat_dev(b: DevArray, a: DevArray) -> DevArray:
     return DevArray(out, a.dtype, a.n + b.n)
 
 
-def _ismember(a_cols, b_cols):
+def _ismember(a_cols, b_cols, base_index=0):
     """Hash-group the rows of b followed by the rows of a: a row of `a` is a member iff its bin's first row lies in
     the b part, and that first row is the index of its first occurrence in b.  NaN keys never match."""
     from .enums import int_dtype_from_len, invalid_for
@@ -748,9 +748,9 @@ def _ismember(a_cols, b_cols):
         raise ValueError("ismember: a and b must have the same number of key columns")
     acs, bcs = [_to_dev(c) for c in a_cols], [_to_dev(c) for c in b_cols]
     na, nb = acs[0].n, bcs[0].n
-    idt = int_dtype_from_len(nb)
+    idt = int_dtype_from_len(nb + base_index)
     tdt = _TORCH_OF[idt]
-    inv = int(invalid_for(idt))
+    inv = 0 if base_index else int(invalid_for(idt))  # base_index 1: positions count from 1 and 0 means absent
     dev = _device()
     if na == 0 or nb == 0:
         found = torch.zeros(na, dtype=torch.bool, device=dev)
@@ -766,7 +766,7 @@ def _ismember(a_cols, b_cols):
         ika = ik[nb:].to(torch.int64)
         first = ifk.to(torch.int64)[(ika - 1).clamp(min=0)] if u else torch.zeros(na, dtype=torch.int64, device=dev)
         found = (ika > 0) & (first < nb)
-        idx = torch.where(found, first, torch.full_like(first, inv)).to(tdt)
+        idx = torch.where(found, first + base_index, torch.full_like(first, inv)).to(tdt)
     if device_mode:
         return found, idx
     return found.cpu().numpy(), idx.cpu().numpy()
@@ -775,6 +775,12 @@ def _ismember(a_cols, b_cols):
 def IsMember32(a, b, h=2, hint_size=0):
     """-> (bool[len(a)], index of the first occurrence of a[i] in b; the index dtype (by len(b)) 's invalid where absent)."""
     return _ismember([a], [b])
+
+
+def IsMemberCategorical(a, b, h=2, hint_size=0):
+    """rc.IsMemberCategorical (riptable/rt_numpy.py:1388-1389, `ismember(..., base_index=1)`): the position is 1-based
+    and 0 where absent, ready to be used as a Categorical's codes (riptable/rt_grouping.py:959-963)."""
+    return _ismember([a], [b], 1)
 
 
 def MultiKeyIsMember32(a_tuple, b_tuple, hint_size=0):

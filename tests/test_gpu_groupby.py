@@ -118,6 +118,23 @@ def test_projections_fixture(rc):
     assert u == 455654
 
 
+def test_ismember_categorical(rc):
+    rng = np.random.default_rng(21)
+    for na, nb in ((50_000, 80), (20_000, 40_000), (10, 0), (0, 10)):
+        b = rng.permutation(max(nb, 1) * 2)[:nb].astype(np.int32)
+        a = rng.integers(-1, max(nb, 1) * 2, na).astype(np.int32)
+        ef, ei = orc.IsMemberCategorical(a, b)
+        gf, gi = rc.IsMemberCategorical(a, b)
+        assert gi.dtype == ei.dtype
+        np.testing.assert_array_equal(gf, ef)
+        np.testing.assert_array_equal(gi, ei)
+    keys = np.array(["pear", "apple", "fig", "apple", "pear", "kiwi"])
+    ik, ifk, U = rc.MultiKeyGroupBy32([keys], 0, np.array([True, True, True, True, True, False]), 2)
+    sortidx = np.argsort(keys[ifk], kind="stable")
+    _, new = rc.IsMemberCategorical(ik.astype(np.int32) - 1, sortidx.astype(np.int32))
+    assert new.tolist() == [3, 1, 2, 1, 3, 0]
+
+
 def test_reindex_groups(rc):
     # 8f.3: the hstack_groupings recipe (rt_grouping.py:277-413) must land on the global grouping
     import rt_glue

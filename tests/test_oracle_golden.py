@@ -332,6 +332,18 @@ def test_ema_docstring_kats():
     assert w[3] == 0.0 and w[6] == 3.0  # row 3 excluded: group 1 still at 0; row 6: 6 * .5 + 0 * .5
 
 
+def test_ismember_categorical_ordered_remap():
+    # rt_grouping.py:955-963: an ordered Categorical turns first-appearance codes into sorted-order codes with
+    # ismember(tempikey - 1, sortidx, base_index=1); a filtered row (code 0 -> -1) stays 0
+    keys = np.array(["pear", "apple", "fig", "apple", "pear", "kiwi"])
+    ik, ifk, U = orc.MultiKeyGroupBy32([keys], 0, np.array([True, True, True, True, True, False]), 2)
+    uniq = keys[ifk]
+    sortidx = np.argsort(uniq, kind="stable")
+    found, new = orc.IsMemberCategorical(ik.astype(np.int32) - 1, sortidx.astype(np.int32))
+    assert new.tolist() == [3, 1, 2, 1, 3, 0] and found.tolist() == [True] * 5 + [False]
+    assert uniq[sortidx][new[:5] - 1].tolist() == keys[:5].tolist()
+
+
 def test_cutoffs_kat():
     # tests/test_pgroupby.py:7-86
     rng = np.random.default_rng(0)

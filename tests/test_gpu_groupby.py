@@ -118,6 +118,23 @@ def test_projections_fixture(rc):
     assert u == 455654
 
 
+def test_host_mode_large_pageable_inputs(rc):
+    # NumPy inputs above 8 MB travel through the staged page-locked ring (rc._h2d_staged); sizes straddle chunk edges
+    rng = np.random.default_rng(77)
+    for n in (1 << 20, (1 << 21) + 12_345, 3_000_001):
+        key = rng.integers(0, 5000, n).astype(np.int64) * 104_729
+        val = rng.random(n)
+        ik, ifk, u = rc.MultiKeyGroupBy32([key], 0, None, 2)
+        eik, eifk, eu = orc.MultiKeyGroupBy32([key], 0, None, 2)
+        assert u == eu
+        np.testing.assert_array_equal(ik, eik)
+        np.testing.assert_array_equal(ifk, eifk)
+        got = rc.GroupByAll32([val], ik, u, [0], [1], [u + 1], 0)[0]
+        np.testing.assert_allclose(got[1:], np.bincount(eik, weights=val, minlength=eu + 1)[1:], rtol=1e-12)
+        d = rc._to_dev(key)
+        assert (d.torch().cpu().numpy() == key).all()
+
+
 def test_ismember_categorical(rc):
     rng = np.random.default_rng(21)
     for na, nb in ((50_000, 80), (20_000, 40_000), (10, 0), (0, 10)):

@@ -66,7 +66,26 @@ def main():
         line("C2 " + name, n, ms, b)
     ms, _ = timed(lambda: rc.BinCount(ik, u + 1))
     line("C2 count (BinCount)", n, ms, 4)
-    del val32, ik
+    del val32
+
+    # SURVEY 8f rows on the C2 grouping (1M bins): algorithmic bytes = inputs read once + outputs written once
+    ms, (cnt, ig, ifg) = timed(lambda: rc.BinCount(ik, u + 1, pack=True), reps=2)
+    line("8f C2 pack (BinCount pack=True, 20-bit bins)", n, ms, 8)
+    t64 = torch.arange(n, device="cuda", dtype=torch.int64)
+    for name, fn, b in (("cumsum f64", lambda: rc.EmaAll32([val], ik, u, 300, (0.0, None, None, None)), 20),
+                        ("cummax f64 (skipna)", lambda: rc.EmaAll32([val], ik, u, 306, (0.0, None, None, None)), 20),
+                        ("ema_normal f64, int64 time", lambda: rc.EmaAll32([val], ik, u, 304, (1e-6, t64, None, None)), 28),
+                        ("rolling_sum f64 window 3 (packed layout given)", lambda: rc.GroupByAllPack32([val], ik, ig, ifg, cnt, u, [200], [0], [u + 1], 3), 24),
+                        ("shift f64 by 1 (packed layout given)", lambda: rc.GroupByAllPack32([val], ik, ig, ifg, cnt, u, [203], [0], [u + 1], 1), 24),
+                        ("median f64 (packed layout given)", lambda: rc.GroupByAllPack32([val], ik, ig, ifg, cnt, u, [103], [1], [u + 1], 0), 12)):
+        ms, _ = timed(fn, reps=2)
+        line("8f C2 " + name, n, ms, b)
+    del t64, ig, ifg, cnt
+    probe = torch.randint(-(2**62), 2**62, (1_000_000,), dtype=torch.int64, device="cuda", generator=g)
+    kk = keys(1_000_000)
+    ms, _ = timed(lambda: rc.IsMember32(kk, probe), reps=2)
+    line("8f IsMember32: 1B int64 rows in a 1M-row set", n, ms, 8 + 1 + 4)
+    del kk, probe, ik
 
     # C5: 100M uniques (scaled with n), cumsum / pack / first / last
     u5 = max(n // 10, 1)

@@ -85,6 +85,19 @@ static int pack_sort(const void* ikey, int kdt, int64_t n, int64_t nbins, const 
   return RTB_OK;
 }
 
+// item copy in the widest unit the item size allows (items start at multiples of their size inside 16-byte aligned buffers)
+__device__ __forceinline__ void copy_item(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int itemsize) {
+  if ((itemsize & 7) == 0) {
+    for (int i = 0; i < itemsize; i += 8) *(unsigned long long*)(dst + i) = *(const unsigned long long*)(src + i);
+  } else if ((itemsize & 3) == 0) {
+    for (int i = 0; i < itemsize; i += 4) *(uint32_t*)(dst + i) = *(const uint32_t*)(src + i);
+  } else if ((itemsize & 1) == 0) {
+    for (int i = 0; i < itemsize; i += 2) *(uint16_t*)(dst + i) = *(const uint16_t*)(src + i);
+  } else {
+    for (int i = 0; i < itemsize; i++) dst[i] = src[i];
+  }
+}
+
 // ---- a8: first / nth / last ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pick_kernel(const uint8_t* __restrict__ values, int vdt, int itemsize,
                                                    const int32_t* __restrict__ igroup, const int32_t* __restrict__ ifirst,
@@ -96,8 +109,7 @@ __global__ void __launch_bounds__(256) pick_kernel(const uint8_t* __restrict__ v
     bool ok = off >= 0 && off < cnt && b >= lo && b < hi;
     uint8_t* dst = out + b * (int64_t)itemsize;
     if (ok) {
-      const uint8_t* src = values + (int64_t)igroup[(int64_t)ifirst[b] + off] * itemsize;
-      for (int i = 0; i < itemsize; i++) dst[i] = src[i];
+      copy_item(dst, values + (int64_t)igroup[(int64_t)ifirst[b] + off] * itemsize, itemsize);
     } else if (vdt <= RTB_F64) {
       unsigned long long inv = invalid_raw(vdt);
       for (int i = 0; i < itemsize; i++) dst[i] = (uint8_t)(inv >> (8 * i));
@@ -127,8 +139,13 @@ struct RollArgs {
 
 __device__ __forceinline__ void store_invalid_item(uint8_t* dst, int dt, int itemsize) {
   if (dt <= RTB_F64) {
-    unsigned long long inv = invalid_raw(dt);
-    for (int i = 0; i < itemsize; i++) dst[i] = (uint8_t)(inv >> (8 * i));
+    const unsigned long long inv = invalid_raw(dt);
+    switch (itemsize) {
+      case 8: *(unsigned long long*)dst = inv; break;
+      case 4: *(uint32_t*)dst = (uint32_t)inv; break;
+      case 2: *(uint16_t*)dst = (uint16_t)inv; break;
+      default: dst[0] = (uint8_t)inv;
+    }
   } else {
     for (int i = 0; i < itemsize; i++) dst[i] = 0;
   }
@@ -153,8 +170,7 @@ __global__ void __launch_bounds__(256) rolling_kernel(RollArgs a) {
         const int64_t q = j - a.window;
         uint8_t* dst = a.out + row * (int64_t)a.itemsize;
         if (q >= start && q < start + cnt) {
-          const uint8_t* src = a.values + (int64_t)a.igroup[q] * a.itemsize;
-          for (int i = 0; i < a.itemsize; i++) dst[i] = src[i];
+          copy_item(dst, a.values + (int64_t)a.igroup[q] * a.itemsize, a.itemsize);
         } else {
           store_invalid_item(dst, a.vdt, a.itemsize);
         }

@@ -112,6 +112,15 @@ int rtb_multikey_groupby32_chunk(const rtb_column* key, int64_t nrows, const uin
                                  int resume, int64_t* needed_unique_host, void* workspace, size_t workspace_bytes,
                                  void* stream);
 
+/* ---- 8f.1: rc.IsMember32(a, b, h, hint) / rc.IsMemberCategorical — riptable/rt_numpy.py:1388-1391, one numeric key
+ * column of the same dtype on both sides.  found_out uint8[na]; index_out (index_dtype: an int rtb_dtype chosen by
+ * len(b), riptable/rt_enum.py:666-679) = position of the first occurrence of a[i] in b, + base_index; absent rows get
+ * the index dtype's invalid (base_index 0) or 0 (base_index 1).  NaN never matches.  The table is built by grouping b
+ * (a1's kernels); the rows of a are looked up without inserting.  RTB_ERR_UNSUPPORTED for an unaligned key column. */
+size_t rtb_ismember_workspace_bytes(int64_t nb);
+int rtb_ismember32(const void* a, int64_t na, const void* b, int64_t nb, int dtype, int base_index, int index_dtype,
+                   uint8_t* found_out, void* index_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a4: rc.CombineFilter(key, filter) — riptable/rt_numpy.py:1508.  out = filter ? key : 0, key dtype kept. */
 int rtb_combine_filter(const void* ikey, int kdtype, const uint8_t* filter, int64_t nrows, void* out, void* stream);
 

@@ -936,6 +936,70 @@ static GbLayout layout(void* ws, size_t wsbytes, int64_t nrows, int64_t max_uniq
   return L;
 }
 
+// ---- 8f.1: membership lookup against a finished table -----------------------------------------------------
+// rc.IsMember32 on one numeric key column: the table is built by grouping `b` (its slots keep the FIRST row of every
+// key, which is the answer ismember wants), then every row of `a` is looked up without inserting anything.
+__global__ void __launch_bounds__(256) ismember_valid_kernel(const void* __restrict__ b, int dt, int64_t n, uint8_t* __restrict__ valid) {
+  const int sz = dt <= RTB_U8 ? 1 : dt <= RTB_U16 ? 2 : (dt <= RTB_U32 || dt == RTB_F32) ? 4 : 8;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    bool ok = true;
+    if (dt == RTB_F64) ok = (((const unsigned long long*)b)[r] & 0x7FFFFFFFFFFFFFFFull) <= 0x7FF0000000000000ull;
+    else if (dt == RTB_F32) ok = (((const uint32_t*)b)[r] & 0x7FFFFFFFu) <= 0x7F800000u;
+    (void)sz;
+    valid[r] = ok;
+  }
+}
+
+template <int ISZ>
+__global__ void __launch_bounds__(256) ismember_lookup_kernel(const void* __restrict__ a, int64_t n, const Slot* __restrict__ table,
+                                                              uint32_t mask, int base_index, int idt, long long absent,
+                                                              uint8_t* __restrict__ found, void* __restrict__ index_out) {
+  const uint32_t bmask = mask >> 1;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t r0 = (int64_t)blockIdx.x * blockDim.x * 4 + threadIdx.x; r0 < n; r0 += stride) {
+    unsigned long long k[4];
+    uint32_t b[4];
+    Bucket p[4];
+    bool live[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int64_t r = r0 + (int64_t)i * blockDim.x;
+      live[i] = r < n;
+      k[i] = live[i] ? load_key1<ISZ>(a, r) : 0ull;
+      b[i] = hash_u64(k[i]) & bmask;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if (live[i]) p[i] = load_bucket(table, b[i]);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (!live[i]) continue;
+      const int64_t r = r0 + (int64_t)i * blockDim.x;
+      long long pos = -1;
+      if (k[i] == kEmpty) {
+        const Slot s = table[mask + 1];  // the key that equals the empty marker lives in the extra slot
+        if (s.key != kEmpty && s.bin()) pos = s.minrow;
+      } else {
+        for (uint32_t hops = 0; hops <= bmask; hops++) {
+          if (p[i].k0 == k[i]) { pos = (uint32_t)p[i].w0; break; }
+          if (p[i].k1 == k[i]) { pos = (uint32_t)p[i].w1; break; }
+          if (p[i].k0 == kEmpty || p[i].k1 == kEmpty) break;
+          b[i] = (b[i] + 1) & bmask;
+          p[i] = load_bucket(table, b[i]);
+        }
+      }
+      found[r] = pos >= 0;
+      const long long v = pos >= 0 ? pos + base_index : absent;
+      switch (idt) {
+        case RTB_I8: ((int8_t*)index_out)[r] = (int8_t)v; break;
+        case RTB_I16: ((int16_t*)index_out)[r] = (int16_t)v; break;
+        case RTB_I32: ((int32_t*)index_out)[r] = (int32_t)v; break;
+        default: ((long long*)index_out)[r] = v;
+      }
+    }
+  }
+}
+
 }  // namespace rtb
 
 using namespace rtb;
@@ -1309,4 +1373,83 @@ extern "C" int rtb_multikey_groupby32_chunk(const rtb_column* key, int64_t nrows
   int64_t u = 0;
   return gb_core(key, 1, nrows, filter, nullptr, 0, ikey_out, ifirstkey_out, max_unique, &u, nullptr, needed_unique_host,
                  workspace, workspace_bytes, (cudaStream_t)stream_, state, row_offset);
+}
+
+struct IsMemberLayout {
+  void* gb_ws;
+  size_t gb_bytes;
+  int32_t *ikey_b, *ifirst_b;
+  uint8_t* valid_b;
+  size_t bytes;
+};
+static IsMemberLayout ismember_layout(void* ws, size_t wsbytes, int64_t nb) {
+  Arena a(ws, wsbytes);
+  IsMemberLayout L;
+  const int64_t m = nb > 0 ? nb : 1;
+  L.gb_bytes = layout(nullptr, 0, m, m, false, 0).bytes + 256;
+  L.gb_ws = a.take<uint8_t>(L.gb_bytes);
+  L.ikey_b = a.take<int32_t>((size_t)m + 4);
+  L.ifirst_b = a.take<int32_t>((size_t)m + 4);
+  L.valid_b = a.take<uint8_t>((size_t)m + 4);
+  L.bytes = a.off;
+  return L;
+}
+
+extern "C" size_t rtb_ismember_workspace_bytes(int64_t nb) {
+  if (nb < 0) return 0;
+  return ismember_layout(nullptr, 0, nb).bytes + 256;
+}
+
+extern "C" int rtb_ismember32(const void* a, int64_t na, const void* b, int64_t nb, int dtype, int base_index, int index_dtype,
+                              uint8_t* found_out, void* index_out, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RTB_ARG(dtype >= RTB_BOOL && dtype <= RTB_F64, "IsMember32: one numeric key column");
+  RTB_ARG(index_dtype == RTB_I8 || index_dtype == RTB_I16 || index_dtype == RTB_I32 || index_dtype == RTB_I64, "IsMember32: bad index dtype");
+  RTB_ARG(base_index == 0 || base_index == 1, "IsMember32: base_index must be 0 or 1");
+  RTB_ARG(na >= 0 && nb >= 0 && nb <= 2147483646ll, "IsMember32: bad sizes");
+  if (na == 0) return RTB_OK;
+  RTB_ARG(a && found_out && index_out, "IsMember32: null pointer");
+  const int isz = dtype_size(dtype);
+  long long absent = 0;
+  if (!base_index) absent = index_dtype == RTB_I8 ? -128ll : index_dtype == RTB_I16 ? -32768ll : index_dtype == RTB_I32 ? -2147483648ll : (long long)0x8000000000000000ull;
+  IsMemberLayout L = ismember_layout(workspace, workspace_bytes, nb);
+  RTB_ARG(workspace && L.bytes <= workspace_bytes, "IsMember32: workspace too small");
+  RTB_ARG(((uintptr_t)workspace % 256) == 0, "IsMember32: workspace must be 256-byte aligned");
+  uint32_t cap = 1024;
+  Slot* table = (Slot*)L.gb_ws;  // layout() puts the table first
+  if (nb > 0) {
+    RTB_ARG(b, "IsMember32: null pointer");
+    if (((uintptr_t)b % (4 * isz)) != 0) {
+      set_error("IsMember32: the key column must be aligned to 4 items");
+      return RTB_ERR_UNSUPPORTED;
+    }
+    const uint8_t* filt = nullptr;
+    if (dtype == RTB_F32 || dtype == RTB_F64) {  // NaN never matches: keep it out of the table
+      ismember_valid_kernel<<<grid_for(nb, 256, 4), 256, 0, stream>>>(b, dtype, nb, L.valid_b);
+      RTB_LAUNCH_CHECK();
+      filt = L.valid_b;
+    }
+    rtb_column col{const_cast<void*>(b), dtype, isz};
+    rtb_gb_state st;
+    memset(&st, 0, sizeof(st));
+    int64_t u = 0;
+    int rc = gb_core(&col, 1, nb, filt, nullptr, 0, L.ikey_b, L.ifirst_b, nb, &u, nullptr, nullptr, L.gb_ws, L.gb_bytes, stream, &st, 0);
+    if (rc != RTB_OK) return rc;
+    cap = st.cap;
+    if (cap == 0) {  // every row of b was filtered out: an empty table
+      cap = 1024;
+      RTB_CUDA(cudaMemsetAsync(table, 0xFF, sizeof(Slot) * ((size_t)cap + 1), stream));
+    }
+  } else {
+    RTB_CUDA(cudaMemsetAsync(table, 0xFF, sizeof(Slot) * ((size_t)cap + 1), stream));
+  }
+  const int grid = grid_for(na, 256, 4, 8);
+  switch (isz) {
+    case 8: ismember_lookup_kernel<8><<<grid, 256, 0, stream>>>(a, na, table, cap - 1, base_index, index_dtype, absent, found_out, index_out); break;
+    case 4: ismember_lookup_kernel<4><<<grid, 256, 0, stream>>>(a, na, table, cap - 1, base_index, index_dtype, absent, found_out, index_out); break;
+    case 2: ismember_lookup_kernel<2><<<grid, 256, 0, stream>>>(a, na, table, cap - 1, base_index, index_dtype, absent, found_out, index_out); break;
+    default: ismember_lookup_kernel<1><<<grid, 256, 0, stream>>>(a, na, table, cap - 1, base_index, index_dtype, absent, found_out, index_out);
+  }
+  RTB_LAUNCH_CHECK();
+  return RTB_OK;
 }

@@ -822,6 +822,16 @@ def _ismember(a_cols, b_cols, base_index=0):
     if na == 0 or nb == 0:
         found = torch.zeros(na, dtype=torch.bool, device=dev)
         idx = torch.full((na,), inv, dtype=tdt, device=dev)
+    elif (len(acs) == 1 and acs[0].dtype == bcs[0].dtype and acs[0].dtype.kind in "biufmM" and acs[0].dtype.itemsize in (1, 2, 4, 8)
+          and acs[0].dtype != np.float16):
+        # one numeric key column: build the table from b, look the rows of a up (no concatenation, no inserts)
+        found_u8 = torch.empty(max(na, 1), dtype=torch.uint8, device=dev)[:na]
+        idx = torch.empty(max(na, 1), dtype=tdt, device=dev)[:na]
+        ws = _ws(lib.rtb_ismember_workspace_bytes(nb))
+        check(lib.rtb_ismember32(C.c_void_p(acs[0].ptr), na, C.c_void_p(bcs[0].ptr), nb, dtype_code(acs[0].dtype), int(base_index),
+                                 dtype_code(idt), C.c_void_p(found_u8.data_ptr()), C.c_void_p(idx.data_ptr()),
+                                 C.c_void_p(ws.data_ptr()), ws.numel(), _stream()))
+        found = found_u8.view(torch.bool)
     else:
         cat = [_concat_dev(bc, ac) for ac, bc in zip(acs, bcs)]
         valid = None

@@ -364,6 +364,26 @@ def test_ismember_vs_oracle(rc):
         assert idx.dtype == eidx.dtype
         np.testing.assert_array_equal(m, em)
         np.testing.assert_array_equal(idx, eidx)
+    # the lookup path: large tables, the all-ones key (the table's empty marker), all-NaN b, bool keys, device mode
+    for dt, lo, hi in ((np.int64, -3, 200_000), (np.uint64, 0, 90_000), (np.int32, -70_000, 70_000)):
+        a = rng.integers(lo, hi, 300_001).astype(dt)
+        b = rng.integers(lo, hi, 120_000).astype(dt)
+        a[::11] = np.array(-1).astype(dt) if np.dtype(dt).kind == "i" else np.iinfo(dt).max
+        for bb in (b, np.r_[b, a[:1].repeat(3)]):
+            m, idx = rc.IsMember32(a, bb)
+            em, eidx = orc.IsMember32(a, bb)
+            assert idx.dtype == eidx.dtype
+            np.testing.assert_array_equal(m, em)
+            np.testing.assert_array_equal(idx, eidx)
+    m, idx = rc.IsMember32(np.array([1.0, np.nan]), np.array([np.nan, np.nan]))
+    assert m.tolist() == [False, False]
+    m, idx = rc.IsMember32(np.array([True, False, True]), np.array([True]))
+    assert m.tolist() == [True, False, True] and idx.tolist() == [0, -128, 0]
+    import torch
+    ta, tb = torch.arange(10, device="cuda", dtype=torch.int64), torch.tensor([7, 3, 3], device="cuda", dtype=torch.int64)
+    m, idx = rc.IsMember32(ta, tb)
+    assert m.is_cuda and m.cpu().tolist() == [False, False, False, True, False, False, False, True, False, False]
+    assert idx.cpu().tolist()[3] == 1 and idx.cpu().tolist()[7] == 0
     a = np.array([b"b", b"a", b"a", b"Inv", b"c", b"a", b"b"], dtype="S")
     b = np.array([b"a", b"b", b"c"], dtype="S")
     m, idx = rc.IsMember32(a, b)

@@ -45,7 +45,7 @@ typedef enum {
   RTB_GB_SUM = 0, RTB_GB_MEAN = 1, RTB_GB_MIN = 2, RTB_GB_MAX = 3, RTB_GB_VAR = 4, RTB_GB_STD = 5,
   RTB_GB_NANSUM = 50, RTB_GB_NANMEAN = 51, RTB_GB_NANMIN = 52, RTB_GB_NANMAX = 53, RTB_GB_NANVAR = 54,
   RTB_GB_NANSTD = 55,
-  RTB_GB_FIRST = 100, RTB_GB_NTH = 101, RTB_GB_LAST = 102, RTB_GB_MEDIAN = 103, RTB_GB_QUANTILE_MULT = 106,
+  RTB_GB_FIRST = 100, RTB_GB_NTH = 101, RTB_GB_LAST = 102, RTB_GB_MEDIAN = 103, RTB_GB_MODE = 104, RTB_GB_QUANTILE_MULT = 106,
   RTB_GB_ROLLING_SUM = 200, RTB_GB_ROLLING_NANSUM = 201, RTB_GB_ROLLING_DIFF = 202, RTB_GB_ROLLING_SHIFT = 203,
   RTB_GB_ROLLING_COUNT = 204, RTB_GB_ROLLING_MEAN = 205, RTB_GB_ROLLING_NANMEAN = 206,
   RTB_GB_CUMSUM = 300, RTB_GB_EMADECAY = 301, RTB_GB_CUMPROD = 302, RTB_GB_EMANORMAL = 304, RTB_GB_EMAWEIGHTED = 305, RTB_GB_CUMNANMAX = 306, RTB_GB_CUMNANMIN = 307, RTB_GB_CUMMAX = 308,
@@ -212,6 +212,14 @@ size_t rtb_ema_workspace_bytes(int64_t nrows, int64_t unique_rows);
 int rtb_groupby_ema(int func, const void* values, int vdtype, const void* ikey, int kdtype, int64_t nrows,
                     int64_t unique_rows, const void* time, int tdtype, double decay_rate, const uint8_t* filter,
                     const uint8_t* reset_filter, void* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- 8f.2: rc.GroupByAllPack32 GB_MODE (104, "auto handles nan", riptable/rt_enum.py:507; riptable/rt_groupbyops.py:1297-1363).
+ * out: unique_rows+1 items of the value dtype: the most frequent valid value of each bin, the smallest one among
+ * equally frequent values; a bin with no valid value, or outside [bin_low, bin_high), gets the invalid.
+ * Workspace: rtb_quantile_workspace_bytes. */
+int rtb_groupby_mode(const void* values, int vdtype, const void* ikey, int kdtype, const int32_t* ifirstgroup,
+                     const int32_t* ncountgroup, int64_t nrows, int64_t unique_rows, int64_t bin_low, int64_t bin_high,
+                     void* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a10: rc.MakeiFirst(key, n, filter, mode) / rc.MakeiNext(key, n, mode) — riptable/rt_numpy.py:1791-1854 */
 int rtb_make_ifirst(const void* ikey, int kdtype, int64_t nrows, int64_t n, const uint8_t* filter, int mode,

@@ -294,6 +294,32 @@ GB_MEDIAN, GB_QUANTILE_MULT = 103, 106
 QUANTILE_MULTIPLIER = 10**9
 
 
+GB_MODE = 104
+
+
+def _mode(v, ikey, nb, lo, hi):
+    """GB_MODE "auto handles nan" (rt_enum.py:507): the most frequent valid value of each bin in the value's own dtype
+    (tests/test_groupby.py:838-861: [1, 2, 2] -> 2).  UNPINNED: among equally frequent values the smallest wins (what
+    pandas' mode()[0] gives); a bin without a valid value gets the invalid."""
+    if v.dtype.kind not in "biuf":
+        return None
+    out = np.empty(nb, v.dtype)
+    out[:] = invalid_for(v.dtype)
+    ik = ikey.astype(np.int64)
+    ik[(ik < 0) | (ik >= nb)] = 0
+    bad = _is_invalid(v)
+    order = np.argsort(ik, kind="stable")
+    bounds = np.searchsorted(ik[order], np.arange(nb + 1))
+    for b in range(max(lo, 0), min(hi, nb)):
+        rows = order[bounds[b]: bounds[b + 1]]
+        vals = v[rows][~bad[rows]]
+        if len(vals) == 0:
+            continue
+        u, c = np.unique(vals, return_counts=True)
+        out[b] = u[np.argmax(c)]  # first maximum = smallest value
+    return out
+
+
 def quantile_func_param(q, is_nan_function):
     """rt_groupbyops.py:1720-1731."""
     return int(q * 1e9) + int(bool(is_nan_function)) * (QUANTILE_MULTIPLIER + 1)
@@ -420,6 +446,9 @@ def GroupByAllPack32(
         f = int(f)
         if GB_ROLLING_SUM <= f <= GB_ROLLING_NANMEAN:
             res.append(_rolling(v, np.asarray(ikey), iGroup, iFirstGroup, nCountGroup, nb, f, int(func_param)))
+            continue
+        if f == GB_MODE:
+            res.append(_mode(v, np.asarray(ikey), nb, int(lo), int(hi)))
             continue
         if f in (GB_MEDIAN, GB_QUANTILE_MULT):
             res.append(_quantile(v, np.asarray(ikey), nb, f, int(func_param), int(lo), int(hi)))

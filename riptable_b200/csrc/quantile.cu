@@ -78,6 +78,37 @@ __global__ void __launch_bounds__(256) quantile_pick_kernel(const void* __restri
   }
 }
 
+// GB_MODE: the most frequent valid value of each bin; among equally frequent values the smallest (the first longest run
+// of the ascending order).  One thread walks its bin's run.
+__global__ void __launch_bounds__(256) mode_pick_kernel(const void* __restrict__ values, int vdt, const uint32_t* __restrict__ rows,
+                                                        const int32_t* __restrict__ ifirst, const int32_t* __restrict__ ncount,
+                                                        int64_t nb, int64_t lo, int64_t hi, void* __restrict__ out) {
+  const int vsz = dsize(vdt);
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (int64_t)gridDim.x * blockDim.x) {
+    unsigned long long best = invalid_raw(vdt);
+    const int64_t start = ifirst[b], cnt = ncount[b];
+    if (b >= lo && b < hi && cnt > 0) {
+      int64_t best_len = 0, run_len = 0;
+      unsigned long long run_raw = 0;
+      for (int64_t i = 0; i < cnt; i++) {
+        const unsigned long long raw = load_raw1(values, vsz, rows[start + i]);
+        if (raw_invalid(raw, vdt)) break;  // invalid values close the run of the bin
+        if (run_len > 0 && raw == run_raw) {
+          run_len++;
+        } else {
+          run_raw = raw;
+          run_len = 1;
+        }
+        if (run_len > best_len) {
+          best_len = run_len;
+          best = run_raw;
+        }
+      }
+    }
+    store_raw(out, vdt, b, best);
+  }
+}
+
 struct QuantLayout {
   unsigned long long *codes_a, *codes_b;
   uint32_t *rows_a, *rows_b, *bins_a, *bins_b;
@@ -117,6 +148,30 @@ extern "C" size_t rtb_quantile_workspace_bytes(int64_t nrows, int64_t unique_row
   return quant_layout(nullptr, 0, nrows).bytes + 256;
 }
 
+// Orders the rows by (bin, value); *rows_out points into the workspace.
+static int sort_rows_by_bin_value(const void* values, int vdt, const void* ikey, int kdt, int64_t nrows, int64_t nb,
+                                  const QuantLayout& L, cudaStream_t stream, const uint32_t** rows_out) {
+  *rows_out = L.rows_a;
+  if (nrows == 0) return RTB_OK;
+  quantile_codes_kernel<<<grid_for(nrows, 256, 4), 256, 0, stream>>>(values, vdt, nrows, L.codes_a);
+  RTB_LAUNCH_CHECK();
+  int in_b = 0;
+  const int vbits = dtype_size(vdt) < 8 ? 34 : 64;
+  int rc = radix_sort_pairs<uint64_t>((uint64_t*)L.codes_a, L.rows_a, (uint64_t*)L.codes_b, L.rows_b, nrows, vbits, true,
+                                      L.radix_ws, L.radix_bytes, stream, &in_b);
+  if (rc != RTB_OK) return rc;
+  uint32_t* by_value = in_b ? L.rows_b : L.rows_a;
+  uint32_t* spare = in_b ? L.rows_a : L.rows_b;
+  quantile_bins_kernel<<<grid_for(nrows, 256, 4), 256, 0, stream>>>(ikey, kdt, by_value, nrows, nb, L.bins_a);
+  RTB_LAUNCH_CHECK();
+  // the pair buffers of the second sort: (bins_a, by_value) <-> (bins_b, spare)
+  rc = radix_sort_pairs<uint32_t>(L.bins_a, by_value, L.bins_b, spare, nrows, bits_for_bins(nb), false, L.radix_ws,
+                                  L.radix_bytes, stream, &in_b);
+  if (rc != RTB_OK) return rc;
+  *rows_out = in_b ? spare : by_value;
+  return RTB_OK;
+}
+
 extern "C" int rtb_groupby_quantile(const void* values, int vdt, const void* ikey, int kdt, const int32_t* ifirstgroup,
                                     const int32_t* ncountgroup, int64_t nrows, int64_t unique_rows, double q, int nan_aware,
                                     int64_t bin_low, int64_t bin_high, double* out, void* workspace, size_t workspace_bytes,
@@ -129,31 +184,37 @@ extern "C" int rtb_groupby_quantile(const void* values, int vdt, const void* ike
   }
   RTB_ARG(q >= 0.0 && q <= 1.0, "GroupByAllPack32: quantile must lie in [0, 1]");
   RTB_ARG(nrows >= 0 && nrows <= 2147483646ll && unique_rows >= 0 && out && ifirstgroup && ncountgroup, "GroupByAllPack32: bad arguments");
+  RTB_ARG(nrows == 0 || (values && ikey), "GroupByAllPack32: null pointer");
   const int64_t nb = unique_rows + 1;
   QuantLayout L = quant_layout(workspace, workspace_bytes, nrows);
   RTB_ARG(workspace && L.bytes <= workspace_bytes, "GroupByAllPack32: workspace too small");
-  const uint32_t* rows = L.rows_a;
-  if (nrows > 0) {
-    RTB_ARG(values && ikey, "GroupByAllPack32: null pointer");
-    quantile_codes_kernel<<<grid_for(nrows, 256, 4), 256, 0, stream>>>(values, vdt, nrows, L.codes_a);
-    RTB_LAUNCH_CHECK();
-    int in_b = 0;
-    const int vbits = dtype_size(vdt) < 8 ? 34 : 64;
-    int rc = radix_sort_pairs<uint64_t>((uint64_t*)L.codes_a, L.rows_a, (uint64_t*)L.codes_b, L.rows_b, nrows, vbits, true,
-                                        L.radix_ws, L.radix_bytes, stream, &in_b);
-    if (rc != RTB_OK) return rc;
-    uint32_t* by_value = in_b ? L.rows_b : L.rows_a;
-    uint32_t* spare = in_b ? L.rows_a : L.rows_b;
-    quantile_bins_kernel<<<grid_for(nrows, 256, 4), 256, 0, stream>>>(ikey, kdt, by_value, nrows, nb, L.bins_a);
-    RTB_LAUNCH_CHECK();
-    // the pair buffers of the second sort: (bins_a, by_value) <-> (bins_b, spare)
-    rc = radix_sort_pairs<uint32_t>(L.bins_a, by_value, L.bins_b, spare, nrows, bits_for_bins(nb), false, L.radix_ws,
-                                    L.radix_bytes, stream, &in_b);
-    if (rc != RTB_OK) return rc;
-    rows = in_b ? spare : by_value;
-  }
+  const uint32_t* rows = nullptr;
+  int rc = sort_rows_by_bin_value(values, vdt, ikey, kdt, nrows, nb, L, stream, &rows);
+  if (rc != RTB_OK) return rc;
   quantile_pick_kernel<<<grid_for(nb, 256, 1), 256, 0, stream>>>(values, vdt, rows, ifirstgroup, ncountgroup, nb, q, nan_aware,
                                                                  bin_low, bin_high, out);
+  RTB_LAUNCH_CHECK();
+  return RTB_OK;
+}
+
+extern "C" int rtb_groupby_mode(const void* values, int vdt, const void* ikey, int kdt, const int32_t* ifirstgroup,
+                                const int32_t* ncountgroup, int64_t nrows, int64_t unique_rows, int64_t bin_low,
+                                int64_t bin_high, void* out, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RTB_ARG(is_ikey_dtype(kdt), "GroupByAllPack32: ikey must be int8/16/32/64");
+  if (vdt < RTB_BOOL || vdt > RTB_F64) {
+    set_error("GroupByAllPack32: mode is not provided for dtype %d", vdt);
+    return RTB_ERR_UNSUPPORTED;
+  }
+  RTB_ARG(nrows >= 0 && nrows <= 2147483646ll && unique_rows >= 0 && out && ifirstgroup && ncountgroup, "GroupByAllPack32: bad arguments");
+  RTB_ARG(nrows == 0 || (values && ikey), "GroupByAllPack32: null pointer");
+  const int64_t nb = unique_rows + 1;
+  QuantLayout L = quant_layout(workspace, workspace_bytes, nrows);
+  RTB_ARG(workspace && L.bytes <= workspace_bytes, "GroupByAllPack32: workspace too small");
+  const uint32_t* rows = nullptr;
+  int rc = sort_rows_by_bin_value(values, vdt, ikey, kdt, nrows, nb, L, stream, &rows);
+  if (rc != RTB_OK) return rc;
+  mode_pick_kernel<<<grid_for(nb, 256, 1), 256, 0, stream>>>(values, vdt, rows, ifirstgroup, ncountgroup, nb, bin_low, bin_high, out);
   RTB_LAUNCH_CHECK();
   return RTB_OK;
 }

@@ -31,6 +31,7 @@ class GB_FUNCTIONS(IntEnum):
     GB_NTH = 101
     GB_LAST = 102
     GB_MEDIAN = 103
+    GB_MODE = 104
     GB_QUANTILE_MULT = 106
     # rolling ops on the packed layout (rc.GroupByAllPack32, row-shaped results)
     GB_ROLLING_SUM = 200

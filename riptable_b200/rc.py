@@ -524,6 +524,21 @@ def GroupByAllPack32(values, ikey, iGroup, iFirstGroup, nCountGroup, unique_rows
                                           kdev.n, int(unique_rows), int(func_param), C.c_void_p(res.ptr), _stream()))
             out.append(_from_dev(res, device_mode))
             continue
+        if f == GB_FUNCTIONS.GB_MODE:
+            # 8f.2: most frequent valid value per bin, in the value's own dtype (riptable/rt_groupbyops.py:1297-1363)
+            if kdev is None:
+                kdev = _ikey_dev(ikey)
+            d = _to_dev(v)
+            if d.dtype.kind not in "biuf" or d.dtype == np.float16:
+                out.append(None)
+                continue
+            res = DevArray.empty(nb, d.dtype)
+            ws = _ws(lib.rtb_quantile_workspace_bytes(kdev.n, int(unique_rows)))
+            check(lib.rtb_groupby_mode(C.c_void_p(d.ptr), dtype_code(d.dtype), C.c_void_p(kdev.ptr), dtype_code(kdev.dtype),
+                                       C.c_void_p(ifg.ptr), C.c_void_p(cnt.ptr), kdev.n, int(unique_rows), int(lo), int(hi),
+                                       C.c_void_p(res.ptr), C.c_void_p(ws.data_ptr()), ws.numel(), _stream()))
+            out.append(_from_dev(res, device_mode))
+            continue
         if f in (GB_FUNCTIONS.GB_MEDIAN, GB_FUNCTIONS.GB_QUANTILE_MULT):
             # 8f.2: median "auto handles nan"; quantile decodes riptable's integer parameter
             # (riptable/rt_groupbyops.py:1717-1745: int(q * 1e9) + is_nan * (1e9 + 1))

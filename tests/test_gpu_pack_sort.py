@@ -306,6 +306,25 @@ def test_ema_docstring_kats(rc):
     assert np.round(weighted, 2).tolist() == [0.00, 1.00, 2.00, 1.50, 2.50, 3.50, 3.75, 4.75, 5.75, 6.38]
 
 
+@pytest.mark.parametrize("vdt", [np.bool_, np.int8, np.uint16, np.int32, np.int64, np.uint64, np.float32, np.float64])
+@pytest.mark.parametrize("nb", [1, 37, 5000])
+def test_mode(rc, vdt, nb):
+    rng = np.random.default_rng(nb + 29)
+    n = 80_001
+    ikey = rng.integers(0, nb + 1, n).astype(np.int32)
+    dt = np.dtype(vdt)
+    v = rng.integers(0, 2 if dt.kind == "b" else 12, n).astype(dt)
+    if dt.kind != "b":
+        v[rng.random(n) < 0.2] = orc.invalid_for(dt)
+    cnt, ig, ifg = orc.BinCount(ikey, nb + 1, pack=True)
+    for lo in (0, 1):
+        exp = orc.GroupByAllPack32([v], ikey, ig, ifg, cnt, nb, [104], [lo], [nb + 1], 0)[0]
+        got = rc.GroupByAllPack32([v], ikey, ig, ifg, cnt, nb, [104], [lo], [nb + 1], 0)[0]
+        assert got.dtype == exp.dtype == dt
+        np.testing.assert_array_equal(got, exp)
+    assert rc.GroupByAllPack32([np.array([b"a"] * n)], ikey, ig, ifg, cnt, nb, [104], [1], [nb + 1], 0)[0] is None
+
+
 def test_rolling_kat(rc):
     # tests/test_fastarray.py:1297-1305 through a single group
     x = np.array([1, 2, 3, np.nan, np.nan, np.nan])

@@ -344,6 +344,19 @@ def test_ismember_categorical_ordered_remap():
     assert uniq[sortidx][new[:5] - 1].tolist() == keys[:5].tolist()
 
 
+def test_mode_kat():
+    # tests/test_groupby.py:838-861: key [a, b, b, b], v_int [1, 1, 2, 2] -> mode per key [1, 2]
+    ik = np.array([1, 2, 2, 2], np.int8)
+    cnt, ig, ifg = orc.BinCount(ik, 3, pack=True)
+    for dt in (np.int32, np.int64, np.float64):
+        v = np.array([1, 1, 2, 2], dt)
+        r = orc.GroupByAllPack32([v], ik, ig, ifg, cnt, 2, [orc.GB_MODE], [1], [3], 0)[0]
+        assert r.dtype == dt and r[1:].tolist() == [1, 2]
+    v = np.array([np.nan, 3.0, np.nan, np.nan])
+    r = orc.GroupByAllPack32([v], ik, ig, ifg, cnt, 2, [orc.GB_MODE], [1], [3], 0)[0]
+    assert np.isnan(r[1]) and r[2] == 3.0  # "auto handles nan": NaN never counts
+
+
 def test_cutoffs_kat():
     # tests/test_pgroupby.py:7-86
     rng = np.random.default_rng(0)

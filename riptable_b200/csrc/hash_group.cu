@@ -950,52 +950,91 @@ __global__ void __launch_bounds__(256) ismember_valid_kernel(const void* __restr
   }
 }
 
+__device__ __forceinline__ void store_index(void* out, int idt, int64_t r, long long v) {
+  switch (idt) {
+    case RTB_I8: ((int8_t*)out)[r] = (int8_t)v; break;
+    case RTB_I16: ((int16_t*)out)[r] = (int16_t)v; break;
+    case RTB_I32: ((int32_t*)out)[r] = (int32_t)v; break;
+    default: ((long long*)out)[r] = v;
+  }
+}
+// two / four consecutive rows in one store
+__device__ __forceinline__ void store_index2(void* out, int idt, int64_t r, long long v0, long long v1) {
+  switch (idt) {
+    case RTB_I8: *(uchar2*)((int8_t*)out + r) = make_uchar2((uint8_t)v0, (uint8_t)v1); break;
+    case RTB_I16: *(ushort2*)((int16_t*)out + r) = make_ushort2((uint16_t)v0, (uint16_t)v1); break;
+    case RTB_I32: *(int2*)((int32_t*)out + r) = make_int2((int32_t)v0, (int32_t)v1); break;
+    default: *(longlong2*)((long long*)out + r) = make_longlong2(v0, v1);
+  }
+}
+
+// Looks one key up from bucket `b` on (already fetched as `p`): position of its first occurrence in b, or -1.
+__device__ __forceinline__ long long ismember_probe(const Slot* table, uint32_t mask, unsigned long long k, uint32_t b, Bucket p) {
+  const uint32_t bmask = mask >> 1;
+  if (k == kEmpty) {
+    const Slot s = table[mask + 1];  // the key that equals the empty marker lives in the extra slot
+    return (s.key != kEmpty && s.bin()) ? (long long)s.minrow : -1;
+  }
+  for (uint32_t hops = 0; hops <= bmask; hops++) {
+    if (p.k0 == k) return (uint32_t)p.w0;
+    if (p.k1 == k) return (uint32_t)p.w1;
+    if (p.k0 == kEmpty || p.k1 == kEmpty) return -1;
+    b = (b + 1) & bmask;
+    p = load_bucket(table, b);
+  }
+  return -1;
+}
+
+// Same tiling as gb_round_direct: a warp owns 128-row tiles, every lane four keys, the next tile's keys in flight.
 template <int ISZ>
 __global__ void __launch_bounds__(256) ismember_lookup_kernel(const void* __restrict__ a, int64_t n, const Slot* __restrict__ table,
                                                               uint32_t mask, int base_index, int idt, long long absent,
                                                               uint8_t* __restrict__ found, void* __restrict__ index_out) {
+  const int lane = threadIdx.x & 31;
   const uint32_t bmask = mask >> 1;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
-  for (int64_t r0 = (int64_t)blockIdx.x * blockDim.x * 4 + threadIdx.x; r0 < n; r0 += stride) {
-    unsigned long long k[4];
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t step = nwarps * 128;
+  int64_t tb = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 128;
+  unsigned long long k[4], kn[4] = {0, 0, 0, 0};
+  if (tb + 128 <= n) load_tile_keys<ISZ>(a, tb, lane, k);
+  for (; tb + 128 <= n; tb += step) {
+    if (tb + step + 128 <= n) load_tile_keys<ISZ>(a, tb + step, lane, kn);
     uint32_t b[4];
     Bucket p[4];
-    bool live[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) b[i] = hash_u64(k[i]) & bmask;
+#pragma unroll
+    for (int i = 0; i < 4; i++) p[i] = load_bucket(table, b[i]);
+    long long v[4];
+    uint8_t f[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      const int64_t r = r0 + (int64_t)i * blockDim.x;
-      live[i] = r < n;
-      k[i] = live[i] ? load_key1<ISZ>(a, r) : 0ull;
-      b[i] = hash_u64(k[i]) & bmask;
+      const long long pos = ismember_probe(table, mask, k[i], b[i], p[i]);
+      f[i] = pos >= 0;
+      v[i] = pos >= 0 ? pos + base_index : absent;
+    }
+    if (ISZ == 8) {
+      const int64_t r0 = tb + 2 * lane, r1 = tb + 64 + 2 * lane;
+      *(uchar2*)(found + r0) = make_uchar2(f[0], f[1]);
+      *(uchar2*)(found + r1) = make_uchar2(f[2], f[3]);
+      store_index2(index_out, idt, r0, v[0], v[1]);
+      store_index2(index_out, idt, r1, v[2], v[3]);
+    } else {
+      const int64_t r0 = tb + 4 * lane;
+      *(uchar4*)(found + r0) = make_uchar4(f[0], f[1], f[2], f[3]);
+      store_index2(index_out, idt, r0, v[0], v[1]);
+      store_index2(index_out, idt, r0 + 2, v[2], v[3]);
     }
 #pragma unroll
-    for (int i = 0; i < 4; i++)
-      if (live[i]) p[i] = load_bucket(table, b[i]);
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      if (!live[i]) continue;
-      const int64_t r = r0 + (int64_t)i * blockDim.x;
-      long long pos = -1;
-      if (k[i] == kEmpty) {
-        const Slot s = table[mask + 1];  // the key that equals the empty marker lives in the extra slot
-        if (s.key != kEmpty && s.bin()) pos = s.minrow;
-      } else {
-        for (uint32_t hops = 0; hops <= bmask; hops++) {
-          if (p[i].k0 == k[i]) { pos = (uint32_t)p[i].w0; break; }
-          if (p[i].k1 == k[i]) { pos = (uint32_t)p[i].w1; break; }
-          if (p[i].k0 == kEmpty || p[i].k1 == kEmpty) break;
-          b[i] = (b[i] + 1) & bmask;
-          p[i] = load_bucket(table, b[i]);
-        }
-      }
+    for (int i = 0; i < 4; i++) k[i] = kn[i];
+  }
+  if (tb < n) {  // the warp whose next tile is the partial one
+    for (int64_t r = tb + lane; r < n; r += 32) {
+      const unsigned long long kk = load_key1<ISZ>(a, r);
+      const uint32_t bb = hash_u64(kk) & bmask;
+      const long long pos = ismember_probe(table, mask, kk, bb, load_bucket(table, bb));
       found[r] = pos >= 0;
-      const long long v = pos >= 0 ? pos + base_index : absent;
-      switch (idt) {
-        case RTB_I8: ((int8_t*)index_out)[r] = (int8_t)v; break;
-        case RTB_I16: ((int16_t*)index_out)[r] = (int16_t)v; break;
-        case RTB_I32: ((int32_t*)index_out)[r] = (int32_t)v; break;
-        default: ((long long*)index_out)[r] = v;
-      }
+      store_index(index_out, idt, r, pos >= 0 ? pos + base_index : absent);
     }
   }
 }
@@ -1443,7 +1482,11 @@ extern "C" int rtb_ismember32(const void* a, int64_t na, const void* b, int64_t 
   } else {
     RTB_CUDA(cudaMemsetAsync(table, 0xFF, sizeof(Slot) * ((size_t)cap + 1), stream));
   }
-  const int grid = grid_for(na, 256, 4, 8);
+  if (((uintptr_t)a % 16) != 0 || ((uintptr_t)found_out % 16) != 0 || ((uintptr_t)index_out % 16) != 0) {
+    set_error("IsMember32: a, found and index buffers must be 16-byte aligned");
+    return RTB_ERR_UNSUPPORTED;
+  }
+  const int grid = grid_for(na, 256, 4, 4);
   switch (isz) {
     case 8: ismember_lookup_kernel<8><<<grid, 256, 0, stream>>>(a, na, table, cap - 1, base_index, index_dtype, absent, found_out, index_out); break;
     case 4: ismember_lookup_kernel<4><<<grid, 256, 0, stream>>>(a, na, table, cap - 1, base_index, index_dtype, absent, found_out, index_out); break;

@@ -12,7 +12,7 @@ import riptable_b200.rc as rc  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000_000
 g = torch.Generator(device="cuda")
 g.manual_seed(12345)
-u = n // 10
+u = int(sys.argv[2]) if len(sys.argv) > 2 else n // 10
 uv = torch.randint(-(2**62), 2**62, (u,), dtype=torch.int64, device="cuda", generator=g)
 k = torch.empty(n, dtype=torch.int64, device="cuda")
 for s in range(0, n, 1 << 27):

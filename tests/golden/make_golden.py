@@ -65,7 +65,59 @@ def build():
     return g
 
 
+def build_v2():
+    """hotpath_v2.npz: the SURVEY 8f rows (ismember, cumulative / rolling / quantile / mode / ema functions, ReIndexGroups,
+    CombineAccum1/2Filter) on the inputs of v1."""
+    v1 = build()
+    rng = np.random.default_rng(20240602)
+    g = {}
+    k64, k32, ks, kf, filt, v64, v32, vi = (v1[x] for x in ("k64", "k32", "ks", "kf", "filt", "v64", "v32", "vi"))
+    n = len(k64)
+    ik, u = v1["gb_b_ikey"], int(v1["gb_b_u"])
+    cnt, ig, ifg = v1["pack_ncount"], v1["pack_igroup"], v1["pack_ifirstgroup"]
+    reset = rng.random(n) < 0.02
+    t = np.cumsum(rng.integers(0, 4, n)).astype(np.int64)
+    g.update(reset=reset, time=t)
+    probe64 = np.concatenate([k64[:300], rng.integers(-(2**62), 2**62, 200, dtype=np.int64)])
+    g["probe64"] = probe64
+    g["ism_found"], g["ism_idx"] = orc.IsMember32(k64, probe64)
+    g["ismcat_found"], g["ismcat_idx"] = orc.IsMemberCategorical(k32, np.arange(50, 130, dtype=np.int32))
+    g["mkism_found"], g["mkism_idx"] = orc.MultiKeyIsMember32(([k32, ks],), ([k32[:500], ks[:500]],))
+    for fn in (302, 306, 307, 308, 309):
+        for vn, v in (("v64", v64), ("v32", v32), ("vi", vi)):
+            vv = np.clip(np.nan_to_num(v, nan=1.0) / 50 + 1, 0.5, 1.5).astype(v.dtype) if fn == 302 and v.dtype.kind == "f" else v
+            g[f"cum_{fn}_{vn}"] = orc.EmaAll32([vv], ik, u, fn, (0.0, None, filt, reset))[0]
+    for fn, rate in ((301, 0.01), (304, 0.05), (305, 0.8)):
+        g[f"ema_{fn}_v64"] = orc.EmaAll32([np.nan_to_num(v64)], ik, u, fn, (rate, t, filt, reset))[0]
+        g[f"ema_{fn}_vi"] = orc.EmaAll32([vi], ik, u, fn, (rate, t, None, None))[0]
+    for fn, p in ((200, 3), (201, 5), (202, 1), (202, -2), (203, 2), (203, -1), (204, 1), (204, -1), (205, 4), (206, 4)):
+        for vn, v in (("v64", v64), ("vi", vi)):
+            g[f"roll_{fn}_{p}_{vn}"] = orc.GroupByAllPack32([v], ik, ig, ifg, cnt, u, [fn], [0], [u + 1], p)[0]
+    g["roll_203_1_ks"] = orc.GroupByAllPack32([ks], ik, ig, ifg, cnt, u, [203], [0], [u + 1], 1)[0]
+    for q, isnan in ((0.5, True), (0.5, False), (0.1, True), (0.9, False), (0.0, True), (1.0, True)):
+        fp = orc.quantile_func_param(q, isnan)
+        for vn, v in (("v64", v64), ("v32", v32), ("vi", vi)):
+            g[f"quant_{fp}_{vn}"] = orc.GroupByAllPack32([v], ik, ig, ifg, cnt, u, [106], [1], [u + 1], fp)[0]
+    vm = rng.integers(0, 6, n).astype(np.int32)
+    g["vm"] = vm
+    g["median_v64"] = orc.GroupByAllPack32([v64], ik, ig, ifg, cnt, u, [103], [1], [u + 1], 0)[0]
+    g["mode_vm"] = orc.GroupByAllPack32([vm], ik, ig, ifg, cnt, u, [104], [1], [u + 1], 0)[0]
+    g["mode_vi"] = orc.GroupByAllPack32([vi], ik, ig, ifg, cnt, u, [104], [1], [u + 1], 0)[0]
+    cuts = np.array([1500, 1500, 4000, n], dtype=np.int64)
+    pik, (pifk, ucut), pu = orc.MultiKeyGroupBy32([k32], 0, None, 2, cutoffs=cuts)
+    uik = rng.integers(1, 500, int(ucut[-1])).astype(np.int32)
+    g.update(reidx_cuts=cuts, reidx_ucut=ucut, reidx_uik=uik, reidx_ikey=pik)
+    g["reidx_out"] = orc.ReIndexGroups(pik, uik, ucut, cuts)
+    k1 = (k32 % 7 + 1).astype(np.int8)
+    k2 = (vm + 1).astype(np.int8)
+    g["acc1_ikey"], g["acc1_ifk"], g["acc1_u"] = orc.CombineAccum1Filter(k1, 7, filt)
+    g["acc2_ikey"], g["acc2_cnt"] = orc.CombineAccum2Filter(k1, k2, 7, 6, filt)
+    return g
+
+
 if __name__ == "__main__":
-    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hotpath_v1.npz")
-    np.savez_compressed(out, **build())
-    print(out, os.path.getsize(out), "bytes")
+    here = os.path.dirname(os.path.abspath(__file__))
+    for name, fn in (("hotpath_v1.npz", build), ("hotpath_v2.npz", build_v2)):
+        out = os.path.join(here, name)
+        np.savez_compressed(out, **fn())
+        print(out, os.path.getsize(out), "bytes")

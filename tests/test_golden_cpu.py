@@ -7,3 +7,7 @@ import golden_cases
 
 def test_oracle_matches_golden_fixtures():
     golden_cases.run(orc)
+
+
+def test_oracle_matches_golden_fixtures_v2():
+    golden_cases.run_v2(orc)

@@ -10,3 +10,11 @@ def test_cuda_path_matches_golden_fixtures():
     import golden_cases
 
     golden_cases.run(rc)
+
+
+def test_cuda_path_matches_golden_fixtures_v2():
+    import riptable_b200.rc as rc
+
+    import golden_cases
+
+    golden_cases.run_v2(rc)

@@ -869,10 +869,12 @@ struct GbPlan {
   double load_abort;   // a round aborts when uniques / capacity would exceed this
   int ratio;
   double big_table_bytes;  // above this table size every round uses the slot-wise kernel
+  int64_t finish_rows;     // a settled table finishes a remainder of at most this many rows in one round
 };
 
 static GbPlan get_plan() {
-  GbPlan p{0, 1, 1, 1, 0.002, 4, 1 << 20, 0.25, 0.75, 4, 8.0 * 1024 * 1024 * 1024};
+  GbPlan p{0, 1, 1, 1, 0.002, 4, 1 << 20, 0.25, 0.75, 4, 8.0 * 1024 * 1024 * 1024, 64ll << 20};
+  if (const char* e = getenv("RTB_GB_FINISH")) p.finish_rows = atoll(e);
   if (const char* e = getenv("RTB_GB_BIGTABLE")) p.big_table_bytes = atof(e);
   if (const char* e = getenv("RTB_GB_L2WIN")) p.l2_window = atoi(e);
   if (const char* e = getenv("RTB_GB_DISCOVERY")) p.discovery_frac = atof(e);
@@ -1158,6 +1160,9 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
   int cround = 0;          // rounds of this chunk: every chunk restarts the geometric schedule with a small probe round
   while (lo < nrows) {
     int64_t hi = cround == 0 ? plan.round0 : lo * plan.ratio;
+    // a settled table and a short remainder: one round to the end saves the host round trips of the schedule (a burst of
+    // late keys then costs at most one repeat of this short round)
+    if (cround > 0 && nrows - lo <= plan.finish_rows && (double)prev_new <= plan.discovery_frac * (double)prev_rows) hi = nrows;
     if (hi > nrows || hi <= lo) hi = nrows;
     int64_t rows = hi - lo;
     // projected new keys in this round: discovery rate of the previous round, never above the row count

@@ -290,8 +290,6 @@ def test_ema(rc, vdt, nb):
                 tol = 2e-5 if exp.dtype == np.float32 else 1e-11
                 scale = float(np.nanmax(np.abs(exp))) + 1.0
                 np.testing.assert_allclose(got, exp, rtol=tol, atol=tol * scale, equal_nan=True, err_msg=f"func {fn} time {tdt}")
-        if tdt is not np.float64:
-            continue
     assert rc.EmaAll32([np.array([b"a"] * n)], ikey, nb, 305, (0.5, None, None, None))[0] is None
     with pytest.raises(ValueError):
         rc.EmaAll32([v], ikey, nb, 301, (0.5, None, None, None))

@@ -47,7 +47,7 @@ typedef enum {
   RTB_GB_NANSTD = 55,
   RTB_GB_FIRST = 100, RTB_GB_NTH = 101, RTB_GB_LAST = 102, RTB_GB_MEDIAN = 103, RTB_GB_MODE = 104, RTB_GB_QUANTILE_MULT = 106,
   RTB_GB_ROLLING_SUM = 200, RTB_GB_ROLLING_NANSUM = 201, RTB_GB_ROLLING_DIFF = 202, RTB_GB_ROLLING_SHIFT = 203,
-  RTB_GB_ROLLING_COUNT = 204, RTB_GB_ROLLING_MEAN = 205, RTB_GB_ROLLING_NANMEAN = 206,
+  RTB_GB_ROLLING_COUNT = 204, RTB_GB_ROLLING_MEAN = 205, RTB_GB_ROLLING_NANMEAN = 206, RTB_GB_ROLLING_QUANTILE = 207,
   RTB_GB_CUMSUM = 300, RTB_GB_EMADECAY = 301, RTB_GB_CUMPROD = 302, RTB_GB_EMANORMAL = 304, RTB_GB_EMAWEIGHTED = 305, RTB_GB_CUMNANMAX = 306, RTB_GB_CUMNANMIN = 307, RTB_GB_CUMMAX = 308,
   RTB_GB_CUMMIN = 309
 } rtb_gb_func;
@@ -220,6 +220,15 @@ int rtb_groupby_ema(int func, const void* values, int vdtype, const void* ikey, 
 int rtb_groupby_mode(const void* values, int vdtype, const void* ikey, int kdtype, const int32_t* ifirstgroup,
                      const int32_t* ncountgroup, int64_t nrows, int64_t unique_rows, int64_t bin_low, int64_t bin_high,
                      void* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- 8f.2: rolling nan-quantile — rc.GroupByAllPack32 function 207, func_param = int(q * 1e9) + window * (1e9 + 1)
+ * (riptable/rt_utils.py:1172-1184; riptable/rt_groupbyops.py:2997-3080).  out: nrows float64 in original row order: the
+ * midpoint quantile of the valid values among the last `window` rows of the row's group (fewer at the start of a
+ * group; NaN when none is valid), pinned by riptable/tests/test_groupbyops.py:901-1110 against np_rolling_nanquantile.
+ * Windows up to 1024 rows. */
+int rtb_groupby_rolling_quantile(const void* values, int vdtype, const void* ikey, int kdtype, const int32_t* igroup,
+                                 const int32_t* ifirstgroup, const int32_t* ncountgroup, int64_t nrows,
+                                 int64_t unique_rows, int64_t window, double q, double* out, void* stream);
 
 /* ---- a10: rc.MakeiFirst(key, n, filter, mode) / rc.MakeiNext(key, n, mode) — riptable/rt_numpy.py:1791-1854 */
 int rtb_make_ifirst(const void* ikey, int kdtype, int64_t nrows, int64_t n, const uint8_t* filter, int mode,

@@ -367,6 +367,53 @@ GB_ROLLING_SUM, GB_ROLLING_NANSUM, GB_ROLLING_DIFF, GB_ROLLING_SHIFT = 200, 201,
 GB_ROLLING_COUNT, GB_ROLLING_MEAN, GB_ROLLING_NANMEAN = 204, 205, 206
 
 
+GB_ROLLING_QUANTILE = 207
+ROLLING_QUANTILE_MULTIPLIER = 10**9
+
+
+def rolling_quantile_func_param(q, window):
+    """rt_utils.py:1172-1184."""
+    return int(q * 1e9) + int(window) * (ROLLING_QUANTILE_MULTIPLIER + 1)
+
+
+def _rolling_quantile(v, ikey, iGroup, iFirstGroup, nCountGroup, nb, func_param):
+    """float64[nrows] in original row order: the nan-quantile (midpoint rule as (lower + higher) / 2,
+    rt_numpy.py:4202-4254) of the last `window` rows of the row's group; NaN / integer sentinels are
+    skipped, a window without a valid value gives NaN (tests/test_groupbyops.py:901-1110 compare the rows
+    from the first full window on with np_rolling_nanquantile).  UNPINNED: rows before the first full
+    window use the rows that are there, like the rolling sums."""
+    import warnings
+    if v.dtype.kind not in "biuf":
+        return None
+    window = func_param // (ROLLING_QUANTILE_MULTIPLIER + 1)
+    q = (func_param % (ROLLING_QUANTILE_MULTIPLIER + 1)) / 1e9
+    if window < 1:
+        raise ValueError("rolling window must be >= 1")
+    n = len(iGroup)
+    rows = iGroup.astype(np.int64)
+    x = v.astype(np.float64)
+    x[_is_invalid(v)] = np.nan
+    xs = x[rows]  # packed order
+    b = ikey.astype(np.int64)[rows]
+    b[(b < 0) | (b >= nb)] = 0
+    out_packed = np.full(n, np.nan)
+    bounds = np.flatnonzero(np.r_[True, b[1:] != b[:-1], True]) if n else np.zeros(1, np.int64)
+    with np.errstate(all="ignore"), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for s, e in zip(bounds[:-1], bounds[1:]):
+            seg = xs[s:e]
+            w = min(window, len(seg))
+            padded = np.r_[np.full(w - 1, np.nan), seg]
+            for c0 in range(0, len(seg), 4096):  # bounded memory: 4096 windows at a time
+                win = np.lib.stride_tricks.sliding_window_view(padded[c0: c0 + 4096 + w - 1], w)
+                lo = np.nanquantile(win, q, axis=-1, method="lower")
+                hi = np.nanquantile(win, q, axis=-1, method="higher")
+                out_packed[s + c0: s + c0 + len(lo)] = (lo + hi) / 2
+    out = np.empty(n, np.float64)
+    out[rows] = out_packed
+    return out
+
+
 def _rolling(v, ikey, iGroup, iFirstGroup, nCountGroup, nb, f, window):
     """Row-shaped rolling results in original row order.  Bin 0 is computed as a group of its own
     (rt_grouping.py:3324-3326: base_bin = 0) except for cumcount, whose filtered rows are invalid
@@ -444,6 +491,9 @@ def GroupByAllPack32(
     for v, f, lo, hi in zip(values, funcList, binLowList, binHighList):
         v = np.asarray(v)
         f = int(f)
+        if f == GB_ROLLING_QUANTILE:
+            res.append(_rolling_quantile(v, np.asarray(ikey), iGroup, iFirstGroup, nCountGroup, nb, int(func_param)))
+            continue
         if GB_ROLLING_SUM <= f <= GB_ROLLING_NANMEAN:
             res.append(_rolling(v, np.asarray(ikey), iGroup, iFirstGroup, nCountGroup, nb, f, int(func_param)))
             continue

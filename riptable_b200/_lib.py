@@ -66,6 +66,7 @@ PROTOTYPES = {
     "rtb_ismember_workspace_bytes": (_sz, [_i64]),
     "rtb_ismember32": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "rtb_groupby_mode": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _sz, _vp]),
+    "rtb_groupby_rolling_quantile": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _i64, _i64, _i64, C.c_double, _vp, _vp]),
     "rtb_rolling_out_dtype": (C.c_int, [_i32, _i32]),
     "rtb_groupby_rolling": (C.c_int, [_i32, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "rtb_cumop_out_dtype": (C.c_int, [_i32, _i32]),

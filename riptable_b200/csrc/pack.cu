@@ -217,6 +217,57 @@ __global__ void __launch_bounds__(256) rolling_kernel(RollArgs a) {
   }
 }
 
+// ---- 8f.2: rolling nan-quantile (GroupByAllPack32 function 207) ---------------------------------------------
+// One thread per packed position: the valid values of its window go to a local buffer, are sorted (insertion sort up
+// to 32 values, Shell sort above) and the two order statistics around (m - 1) * q are averaged — numpy's "midpoint"
+// rule in the (lower + higher) / 2 form riptable's own check uses (riptable/rt_numpy.py:4202-4254).
+constexpr int kMaxQuantileWindow = 1024;
+
+__global__ void __launch_bounds__(128) rolling_quantile_kernel(RollArgs a, double q) {
+  double buf[kMaxQuantileWindow];
+  const int vsz = dsize(a.vdt);
+  const double nan = __longlong_as_double(0x7FF8000000000000ll);
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.n; j += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = a.igroup[j];
+    int64_t bin = load_ikey(a.ikey, a.kdt, row);
+    if (bin < 0 || bin >= a.nb) bin = 0;
+    const int64_t start = a.ifirst[bin];
+    int64_t p = j - a.window + 1;
+    if (p < start) p = start;
+    int m = 0;
+    for (; p <= j; p++) {
+      const unsigned long long x = load_raw1(a.values, vsz, a.igroup[p]);
+      if (!raw_invalid(x, a.vdt)) buf[m++] = raw_to_f64(x, a.vdt);
+    }
+    double r = nan;
+    if (m > 0) {
+      if (m <= 32) {
+        for (int i = 1; i < m; i++) {
+          const double x = buf[i];
+          int k = i - 1;
+          while (k >= 0 && buf[k] > x) { buf[k + 1] = buf[k]; k--; }
+          buf[k + 1] = x;
+        }
+      } else {
+        const int gaps[8] = {701, 301, 132, 57, 23, 10, 4, 1};
+        for (int gi = 0; gi < 8; gi++) {
+          const int gap = gaps[gi];
+          for (int i = gap; i < m; i++) {
+            const double x = buf[i];
+            int k = i;
+            while (k >= gap && buf[k - gap] > x) { buf[k] = buf[k - gap]; k -= gap; }
+            buf[k] = x;
+          }
+        }
+      }
+      const double idx = (double)(m - 1) * q;
+      const int il = (int)floor(idx), ih = (int)ceil(idx);
+      r = (buf[il] + buf[ih]) / 2;
+    }
+    ((double*)a.out)[row] = r;
+  }
+}
+
 // ---- a9: cumulative ops (cumsum / cumprod / cummin / cummax) -----------------------------------------------
 constexpr int kSegThreads = 256;
 constexpr int kSegItems = 8;
@@ -697,6 +748,29 @@ extern "C" int rtb_groupby_pick(const void* values, int vdt, int32_t itemsize, c
   int64_t nb = unique_rows + 1;
   pick_kernel<<<grid_for(nb, 256, 1), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)values, vdt, itemsize, igroup, ifirstgroup,
                                                                       ncountgroup, nb, func, nth, bin_low, bin_high, (uint8_t*)out);
+  RTB_LAUNCH_CHECK();
+  return RTB_OK;
+}
+
+extern "C" int rtb_groupby_rolling_quantile(const void* values, int vdt, const void* ikey, int kdt, const int32_t* igroup,
+                                            const int32_t* ifirstgroup, const int32_t* ncountgroup, int64_t nrows,
+                                            int64_t unique_rows, int64_t window, double q, double* out, void* stream) {
+  RTB_ARG(is_ikey_dtype(kdt), "GroupByAllPack32: ikey must be int8/16/32/64");
+  if (vdt < RTB_BOOL || vdt > RTB_F64) {
+    set_error("GroupByAllPack32: rolling_quantile is not provided for dtype %d", vdt);
+    return RTB_ERR_UNSUPPORTED;
+  }
+  RTB_ARG(q >= 0.0 && q <= 1.0, "GroupByAllPack32: quantile must lie in [0, 1]");
+  RTB_ARG(window >= 1, "GroupByAllPack32: rolling window must be >= 1");
+  RTB_ARG(window <= kMaxQuantileWindow, "GroupByAllPack32: rolling_quantile windows above %d rows are not provided", kMaxQuantileWindow);
+  RTB_ARG(nrows >= 0 && nrows <= 2147483646ll && unique_rows >= 0, "GroupByAllPack32: bad sizes");
+  if (nrows == 0) return RTB_OK;
+  RTB_ARG(values && ikey && igroup && ifirstgroup && ncountgroup && out, "GroupByAllPack32: null pointer");
+  RollArgs a;
+  a.values = (const uint8_t*)values; a.vdt = vdt; a.itemsize = dtype_size(vdt); a.odt = RTB_F64; a.ikey = ikey; a.kdt = kdt;
+  a.igroup = igroup; a.ifirst = ifirstgroup; a.ncount = ncountgroup; a.n = nrows; a.nb = unique_rows + 1;
+  a.func = RTB_GB_ROLLING_QUANTILE; a.window = window; a.out = (uint8_t*)out;
+  rolling_quantile_kernel<<<grid_for(nrows, 128, 1), 128, 0, (cudaStream_t)stream>>>(a, q);
   RTB_LAUNCH_CHECK();
   return RTB_OK;
 }

@@ -41,6 +41,7 @@ class GB_FUNCTIONS(IntEnum):
     GB_ROLLING_COUNT = 204
     GB_ROLLING_MEAN = 205
     GB_ROLLING_NANMEAN = 206
+    GB_ROLLING_QUANTILE = 207
     # row-shaped accumulations (rc.EmaAll32)
     GB_CUMSUM = 300
     GB_EMADECAY = 301

@@ -502,6 +502,22 @@ def GroupByAllPack32(values, ikey, iGroup, iFirstGroup, nCountGroup, unique_rows
     kdev = None
     for v, f, lo, hi in zip(values, funcList, binLowList, binHighList):
         f = int(f)
+        if f == GB_FUNCTIONS.GB_ROLLING_QUANTILE:
+            # 8f.2: func_param = int(q * 1e9) + window * (1e9 + 1)  (riptable/rt_utils.py:1172-1184)
+            if kdev is None:
+                kdev = _ikey_dev(ikey)
+            d = _to_dev(v)
+            if d.dtype.kind not in "biuf" or d.dtype == np.float16:
+                out.append(None)
+                continue
+            fp = int(func_param)
+            window, q = fp // 1_000_000_001, (fp % 1_000_000_001) / 1e9
+            res = DevArray.empty(kdev.n, np.float64)
+            check(lib.rtb_groupby_rolling_quantile(C.c_void_p(d.ptr), dtype_code(d.dtype), C.c_void_p(kdev.ptr), dtype_code(kdev.dtype),
+                                                   C.c_void_p(ig.ptr), C.c_void_p(ifg.ptr), C.c_void_p(cnt.ptr), kdev.n,
+                                                   int(unique_rows), int(window), float(q), C.c_void_p(res.ptr), _stream()))
+            out.append(_from_dev(res, device_mode))
+            continue
         if GB_FUNCTIONS.GB_ROLLING_SUM <= f <= GB_FUNCTIONS.GB_ROLLING_NANMEAN:
             # 8f.2: row-shaped rolling results; func_param is the window / period (riptable/rt_groupbyops.py:2941-3153)
             if kdev is None:

@@ -323,6 +323,34 @@ def test_mode(rc, vdt, nb):
     assert rc.GroupByAllPack32([np.array([b"a"] * n)], ikey, ig, ifg, cnt, nb, [104], [1], [nb + 1], 0)[0] is None
 
 
+@pytest.mark.parametrize("vdt", [np.float64, np.float32, np.int32, np.uint8, np.bool_])
+@pytest.mark.parametrize("nb,window", [(1, 150), (37, 3), (37, 40), (300, 900), (5000, 1)])
+def test_rolling_quantile(rc, vdt, nb, window):
+    rng = np.random.default_rng(nb + window)
+    n = 20_011
+    ikey = rng.integers(0, nb + 1, n).astype(np.int32)
+    dt = np.dtype(vdt)
+    if dt.kind == "f":
+        v = rng.normal(0, 100, n).astype(dt)
+        v[rng.random(n) < 0.05] = np.inf
+        v[rng.random(n) < 0.05] = -np.inf
+        v[rng.random(n) < 0.15] = np.nan
+    elif dt.kind == "b":
+        v = rng.integers(0, 2, n).astype(dt)
+    else:
+        v = rng.integers(0, 200, n).astype(dt)
+        v[rng.random(n) < 0.15] = orc.invalid_for(dt)
+    cnt, ig, ifg = orc.BinCount(ikey, nb + 1, pack=True)
+    for q in (0.5, 0.0, 1.0, 0.29):
+        fp = orc.rolling_quantile_func_param(q, window)
+        exp = orc.GroupByAllPack32([v], ikey, ig, ifg, cnt, nb, [207], [0], [nb + 1], fp)[0]
+        got = rc.GroupByAllPack32([v], ikey, ig, ifg, cnt, nb, [207], [0], [nb + 1], fp)[0]
+        assert got.dtype == np.float64
+        np.testing.assert_array_equal(got, exp, err_msg=f"q {q} window {window} dtype {vdt}")
+    with pytest.raises(ValueError):
+        rc.GroupByAllPack32([v], ikey, ig, ifg, cnt, nb, [207], [0], [nb + 1], orc.rolling_quantile_func_param(0.5, 5000))
+
+
 def test_rolling_kat(rc):
     # tests/test_fastarray.py:1297-1305 through a single group
     x = np.array([1, 2, 3, np.nan, np.nan, np.nan])

@@ -344,6 +344,38 @@ def test_ismember_categorical_ordered_remap():
     assert uniq[sortidx][new[:5] - 1].tolist() == keys[:5].tolist()
 
 
+@pytest.mark.parametrize("N,N_cat,window,q,nan_fraction,dtype", [
+    (500, 1, 150, 0.5, 0.1, np.float64), (2000, 40, 1, 0.3, 0.2, np.float64), (300, 35, 800, 0.75, 0.0, np.int32),
+    (1500, 12, 3, 0.0, 0.3, np.float64), (1500, 12, 17, 1.0, 0.05, np.int32), (800, 5, 25, 0.123, 1.0, np.float64)])
+def test_rolling_quantile_replays_reference_test(N, N_cat, window, q, nan_fraction, dtype):
+    # tests/test_groupbyops.py:901-963: from the first full window on, every row equals the nan-quantile (midpoint) of the
+    # last `window` rows of its category; window is capped by the category's size
+    rng = np.random.default_rng((N * N_cat * int(q * 1000) * int(nan_fraction * 1000)) % 10_000)
+    cat = rng.integers(0, N_cat, N)
+    g = orc.groupbyhash(cat)
+    ik, U = g["iKey"], g["unique_count"]
+    cnt, ig, ifg = orc.BinCount(ik, U + 1, pack=True)
+    data = rng.normal(rng.uniform(-100, 100), rng.uniform(0.0, 100), size=N).astype(dtype)
+    ref = data.astype(np.float64)
+    nan_idx = rng.random(N) < nan_fraction
+    ref[nan_idx] = np.nan
+    data[nan_idx] = orc.invalid_for(dtype)
+    got = orc.GroupByAllPack32([data], ik, ig, ifg, cnt, U, [orc.GB_ROLLING_QUANTILE], [0], [U + 1],
+                               orc.rolling_quantile_func_param(q, window))[0]
+    assert got.dtype == np.float64 and len(got) == N
+    for b in range(1, U + 1):
+        sl, res = ref[ik == b], got[ik == b]
+        w = min(window, len(sl))
+        for p in range(w - 1, len(sl)):
+            vals = np.sort(sl[p - w + 1: p + 1][~np.isnan(sl[p - w + 1: p + 1])])
+            if len(vals) == 0:
+                assert np.isnan(res[p])
+                continue
+            idx = (len(vals) - 1) * q
+            exp = (vals[int(np.floor(idx))] + vals[int(np.ceil(idx))]) / 2
+            assert res[p] == exp, (b, p, res[p], exp)
+
+
 def test_mode_kat():
     # tests/test_groupby.py:838-861: key [a, b, b, b], v_int [1, 1, 2, 2] -> mode per key [1, 2]
     ik = np.array([1, 2, 2, 2], np.int8)

@@ -85,6 +85,20 @@ static int pack_sort(const void* ikey, int kdt, int64_t n, int64_t nbins, const 
   return RTB_OK;
 }
 
+// run starts / ends of the sorted bins: start[k] = first packed position of bin k, end[k] = one past its last
+__global__ void __launch_bounds__(256) run_bounds_kernel(const uint32_t* __restrict__ skeys, int64_t n, uint32_t* __restrict__ start,
+                                                         uint32_t* __restrict__ end) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t k = skeys[j];
+    if (j == 0 || skeys[j - 1] != k) start[k] = (uint32_t)j;
+    if (j == n - 1 || skeys[j + 1] != k) end[k] = (uint32_t)(j + 1);
+  }
+}
+__global__ void __launch_bounds__(256) run_lengths_kernel(const uint32_t* __restrict__ start, uint32_t* __restrict__ end_then_count, int64_t nbins) {
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nbins; b += (int64_t)gridDim.x * blockDim.x)
+    end_then_count[b] -= start[b];  // absent bins: 0 - 0
+}
+
 // item copy in the widest unit the item size allows (items start at multiples of their size inside 16-byte aligned buffers)
 __device__ __forceinline__ void copy_item(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int itemsize) {
   if ((itemsize & 7) == 0) {
@@ -722,20 +736,25 @@ extern "C" int rtb_groupby_pack(const void* ikey, int kdt, int64_t nrows, int64_
   RTB_ARG(is_ikey_dtype(kdt), "pack: ikey must be int8/16/32/64");
   RTB_ARG(nrows >= 0 && nrows <= 2147483646ll && nbins >= 1 && nbins < (1ll << 31), "pack: bad sizes");
   RTB_ARG(ifirstgroup_out && ncountgroup_out, "pack: null output");
-  int rc = rtb_bincount(ikey, kdt, nrows, nbins, ncountgroup_out, stream_);
-  if (rc != RTB_OK) return rc;
   PackLayout L = pack_layout(workspace, workspace_bytes, nrows, nbins);
   RTB_ARG(workspace && L.bytes <= workspace_bytes, "pack: workspace too small");
+  // nCountGroup from the run lengths of the sorted bins (two streaming passes) instead of one atomic per row
+  RTB_CUDA(cudaMemsetAsync(ncountgroup_out, 0, sizeof(int32_t) * (size_t)nbins, stream));
+  RTB_CUDA(cudaMemsetAsync(ifirstgroup_out, 0, sizeof(int32_t) * (size_t)nbins, stream));
+  int rc = RTB_OK;
+  if (nrows > 0) {
+    RTB_ARG(ikey && igroup_out, "pack: null pointer");
+    uint32_t *skeys, *ig;
+    rc = pack_sort(ikey, kdt, nrows, nbins, L, stream, &skeys, &ig, "pack");
+    if (rc != RTB_OK) return rc;
+    RTB_CUDA(cudaMemcpyAsync(igroup_out, ig, sizeof(int32_t) * (size_t)nrows, cudaMemcpyDeviceToDevice, stream));
+    run_bounds_kernel<<<grid_for(nrows, 256, 4), 256, 0, stream>>>(skeys, nrows, (uint32_t*)ifirstgroup_out, (uint32_t*)ncountgroup_out);
+    RTB_LAUNCH_CHECK();
+    run_lengths_kernel<<<grid_for(nbins, 256, 4), 256, 0, stream>>>((const uint32_t*)ifirstgroup_out, (uint32_t*)ncountgroup_out, nbins);
+    RTB_LAUNCH_CHECK();
+  }
   // iFirstGroup = exclusive cumsum(nCountGroup)
-  rc = exclusive_scan_u32((const uint32_t*)ncountgroup_out, (uint32_t*)ifirstgroup_out, nbins, SCAN_IDENTITY, L.scan_scratch, nullptr, stream);
-  if (rc != RTB_OK) return rc;
-  if (nrows == 0) return RTB_OK;
-  RTB_ARG(igroup_out, "pack: null iGroup output");
-  uint32_t *skeys, *ig;
-  rc = pack_sort(ikey, kdt, nrows, nbins, L, stream, &skeys, &ig, "pack");
-  if (rc != RTB_OK) return rc;
-  RTB_CUDA(cudaMemcpyAsync(igroup_out, ig, sizeof(int32_t) * (size_t)nrows, cudaMemcpyDeviceToDevice, stream));
-  return RTB_OK;
+  return exclusive_scan_u32((const uint32_t*)ncountgroup_out, (uint32_t*)ifirstgroup_out, nbins, SCAN_IDENTITY, L.scan_scratch, nullptr, stream);
 }
 
 extern "C" int rtb_groupby_pick(const void* values, int vdt, int32_t itemsize, const int32_t* igroup,

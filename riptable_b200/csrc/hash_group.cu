@@ -712,6 +712,75 @@ __global__ void __launch_bounds__(256) gb_round_packed(const uint8_t* __restrict
   }
 }
 
+// ---- packed rows, low cardinality: every key of the table in shared memory --------------------------------
+// Once the table is settled and its keys fit (U * row bytes up to about 160 KB: 10 K 16-byte keys, 5 K 32-byte keys),
+// every CTA copies the U representative rows into shared memory in bin order (entry b holds the key of bin b + 1,
+// so the bin needs no storage) behind a 16-bit open-addressing index, and the round is bound by the key / iKey
+// streams instead of two dependent global gathers per row.  Keys missing from the snapshot (first seen in this round)
+// fall back to the global table.
+constexpr uint32_t kPackedSmemBytes = 224 * 1024;
+
+__device__ __forceinline__ bool smem_index_claim(uint16_t* sidx, uint32_t slot, uint16_t val) {
+  // 16-bit compare-and-swap of 0xFFFF -> val through the containing 32-bit word
+  uint32_t* word = (uint32_t*)(sidx + (slot & ~1u));
+  const int sh = (slot & 1u) * 16;
+  uint32_t old = *(volatile uint32_t*)word;
+  for (;;) {
+    if (((old >> sh) & 0xFFFFu) != 0xFFFFu) return false;
+    const uint32_t want = (old & ~(0xFFFFu << sh)) | ((uint32_t)val << sh);
+    const uint32_t got = atomicCAS(word, old, want);
+    if (got == old) return true;
+    old = got;
+  }
+}
+
+template <int W16>
+__global__ void __launch_bounds__(1024, 1) gb_round_packed_smem(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ filter,
+                                                                int32_t* __restrict__ ikey, Slot* table, uint32_t mask,
+                                                                int64_t lo, int64_t hi, uint32_t* newlist, GbCounters* ctr,
+                                                                uint32_t new_limit, const int32_t* __restrict__ ifirstkey,
+                                                                uint32_t U, uint32_t icap) {
+  extern __shared__ __align__(16) unsigned char gb_smem[];
+  uint4* skeys = (uint4*)gb_smem;                            // [U][W16]
+  uint16_t* sidx = (uint16_t*)(skeys + (size_t)U * W16);     // [icap], 0xFFFF = empty
+  for (uint32_t i = threadIdx.x; i < icap / 2; i += blockDim.x) ((uint32_t*)sidx)[i] = 0xFFFFFFFFu;
+  __syncthreads();
+  const uint32_t imask = icap - 1;
+  for (uint32_t b = threadIdx.x; b < U; b += blockDim.x) {
+    const PackedRow<W16> k = load_packed<W16>(packed, (int64_t)ifirstkey[b]);
+#pragma unroll
+    for (int j = 0; j < W16; j++) skeys[(size_t)b * W16 + j] = k.w[j];
+    uint32_t slot = (uint32_t)hash_packed<W16>(k) & imask;
+    while (!smem_index_claim(sidx, slot, (uint16_t)b)) slot = (slot + 1) & imask;
+  }
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < hi; r += stride) {
+    int32_t o = 0;
+    if (!filter || filter[r]) {
+      const PackedRow<W16> me = load_packed<W16>(packed, r);
+      const unsigned long long h = hash_packed<W16>(me);
+      uint32_t slot = (uint32_t)h & imask;
+      for (;;) {
+        const uint32_t e = sidx[slot];
+        if (e == 0xFFFFu) {  // not in the snapshot: the general path on the global table
+          o = resolve_packed<W16>(packed, table, mask, r, (uint32_t)(h >> 32), ((uint32_t)h & (mask >> 1)) * 2, newlist, ctr, new_limit);
+          break;
+        }
+        PackedRow<W16> k;
+#pragma unroll
+        for (int j = 0; j < W16; j++) k.w[j] = skeys[(size_t)e * W16 + j];
+        if (packed_equal<W16>(me, k)) {
+          o = (int32_t)(e + 1);
+          break;
+        }
+        slot = (slot + 1) & imask;
+      }
+    }
+    ikey[r] = o;
+  }
+}
+
 template <int W16>
 __global__ void __launch_bounds__(256) gb_reinsert_packed(const uint8_t* __restrict__ packed, Slot* table, uint32_t mask,
                                                           const Slot* staged, uint32_t n) {
@@ -1093,6 +1162,13 @@ static void set_table_l2_window(cudaStream_t stream, const void* table, size_t b
   cudaGetLastError();
 }
 
+static uint32_t packed_smem_icap(int64_t U) {
+  uint32_t c = 1024;
+  while ((int64_t)c < 2 * U) c <<= 1;
+  return c;
+}
+static size_t packed_smem_bytes(int64_t U, int W) { return (size_t)U * W + (size_t)packed_smem_icap(U) * 2 + 16; }
+
 // The round loop shared by the one-shot entry point and the resumable (chunked) one.  `st` carries the table state
 // (capacity, unique count, discovery rate) from one chunk to the next; the table itself lives at the start of the
 // workspace, whose layout depends only on max_unique.  `row_offset` is added to the first rows written to iFirstKey.
@@ -1270,6 +1346,32 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
 #undef RTB_ROUND
         }
         }
+      } else if (W && !has_cut && round > 0 && (double)prev_new <= plan.discovery_frac * (double)prev_rows && attempt == 0 &&
+                 plan.smem_table && U > 0 && U < 65535 &&
+                 row_offset == 0 && packed_smem_bytes(U, W) <= kPackedSmemBytes) {
+        // settled, and every key fits in shared memory: stream-bound round (ifirstkey holds the representative rows)
+        const uint32_t icap = packed_smem_icap(U);
+        const size_t smem = packed_smem_bytes(U, W);
+        int g3 = (int)((rows + 1024 * 8 - 1) / (1024 * 8));
+        if (g3 > kSMs) g3 = kSMs;
+        if (g3 < 1) g3 = 1;
+#define RTB_PSMEM_ROUND(W16_)                                                                                             \
+  do {                                                                                                                    \
+    static bool attr = false;                                                                                             \
+    if (!attr) {                                                                                                          \
+      RTB_CUDA(cudaFuncSetAttribute(gb_round_packed_smem<W16_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPackedSmemBytes)); \
+      attr = true;                                                                                                        \
+    }                                                                                                                     \
+    gb_round_packed_smem<W16_><<<g3, 1024, smem, stream>>>(L.packed, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, \
+                                                          new_limit, ifirstkey_out, (uint32_t)U, icap);                 \
+  } while (0)
+        switch (W) {
+          case 16: RTB_PSMEM_ROUND(1); break;
+          case 32: RTB_PSMEM_ROUND(2); break;
+          case 48: RTB_PSMEM_ROUND(3); break;
+          default: RTB_PSMEM_ROUND(4);
+        }
+#undef RTB_PSMEM_ROUND
       } else {
         switch (W) {
           case 16: gb_round_packed<1><<<grid_for(rows, 256, 2, 8), 256, 0, stream>>>(L.packed, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit); break;

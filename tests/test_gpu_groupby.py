@@ -103,6 +103,29 @@ def test_multikey_and_strings(rc):
     _check_gb(rc, [a.astype(np.int64), s16, i4])
 
 
+def test_packed_rows_in_shared_memory(rc):
+    # settled string / multi-key tables small enough for shared memory (gb_round_packed_smem): rounds past the first 1 Mi
+    # rows, with a filter, and with keys that first appear after the table had settled (they take the global fallback)
+    rng = np.random.default_rng(31)
+    n = 3_300_001
+    s10 = rng.choice(rng.integers(65, 91, 300 * 10, dtype=np.uint8).view("S10"), n)
+    u8 = rng.choice(rng.integers(65, 91, 200 * 8, dtype=np.int32).view("<U8"), n)
+    i8 = rng.integers(0, 40, n).astype(np.int64)
+    i4 = rng.integers(0, 5, n).astype(np.int32)
+    s16 = rng.choice(rng.integers(65, 91, 50 * 16, dtype=np.uint8).view("S16"), n)
+    filt = rng.random(n) < 0.6
+    _check_gb(rc, [s10])
+    _check_gb(rc, [u8], filter=filt)
+    _check_gb(rc, [s16])
+    _check_gb(rc, [i8, s16, i4])
+    _check_gb(rc, [s10, i4], filter=filt)
+    late = s10.copy()
+    late[2_600_000:] = rng.choice(rng.integers(97, 123, 700 * 10, dtype=np.uint8).view("S10"), n - 2_600_000)
+    _check_gb(rc, [late])
+    many = rng.choice(rng.integers(65, 91, 9_000 * 16, dtype=np.uint8).view("S16"), n)  # 9 000 keys of 16 bytes: 144 KB
+    _check_gb(rc, [many])
+
+
 def test_projections_fixture(rc):
     # tests/test_groupby.py:419-459 -> exactly 455 654 groups
     n, num_symbols = 1_000_000, 450

@@ -612,12 +612,38 @@ template <int W16>
 struct PackedRow {
   uint4 w[W16];
 };
+// rowsz = bytes a row occupies in memory.  16 * W16: the packed buffer (or a column whose items are 16-byte multiples),
+// 128-bit loads.  Anything smaller: ONE key column read in place (S10, S12, U3 ...), rows at arbitrary byte offsets of a
+// 4-byte aligned base; the row is assembled from aligned 32-bit words with funnel shifts and zero-padded, which is
+// exactly what the packing pass would have written -- without its extra read and write of the whole column.
 template <int W16>
-__device__ __forceinline__ PackedRow<W16> load_packed(const uint8_t* packed, int64_t r) {
+__device__ __forceinline__ PackedRow<W16> load_packed(const uint8_t* packed, int64_t r, int rowsz) {
   PackedRow<W16> x;
-  const uint4* p = (const uint4*)(packed + r * (int64_t)(16 * W16));
+  if (rowsz == 16 * W16) {
+    const uint4* p = (const uint4*)(packed + r * (int64_t)(16 * W16));
 #pragma unroll
-  for (int j = 0; j < W16; j++) x.w[j] = p[j];
+    for (int j = 0; j < W16; j++) x.w[j] = p[j];
+    return x;
+  }
+  const int64_t b = r * (int64_t)rowsz;
+  const uint32_t* wp = (const uint32_t*)(packed + (b & ~3ll));
+  const int lead = (int)(b & 3);  // bytes of the first word that belong to the previous row
+  uint32_t o[4 * W16];
+#pragma unroll
+  for (int j = 0; j < 4 * W16; j++) {
+    uint32_t v = 0;
+    const int have = rowsz - 4 * j;  // bytes of the row from output word j on
+    if (have > 0) {
+      const uint32_t lo = wp[j];
+      const int need = have < 4 ? have : 4;
+      const uint32_t hi = (lead + need > 4) ? wp[j + 1] : 0u;  // only touched when the row really reaches into it
+      v = __funnelshift_r(lo, hi, lead * 8);
+      if (have < 4) v &= (1u << (8 * have)) - 1u;
+    }
+    o[j] = v;
+  }
+#pragma unroll
+  for (int j = 0; j < W16; j++) x.w[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
   return x;
 }
 template <int W16>
@@ -643,9 +669,9 @@ __device__ __forceinline__ bool packed_equal(const PackedRow<W16>& a, const Pack
 
 template <int W16>
 __device__ __noinline__ int32_t resolve_packed(const uint8_t* packed, Slot* table, uint32_t mask, int64_t r, uint32_t tag,
-                                               uint32_t idx, uint32_t* newlist, GbCounters* ctr, uint32_t new_limit) {
+                                               uint32_t idx, uint32_t* newlist, GbCounters* ctr, uint32_t new_limit, int rowsz) {
   const unsigned long long mine = ((unsigned long long)tag << 32) | (uint32_t)r;
-  const PackedRow<W16> me = load_packed<W16>(packed, r);
+  const PackedRow<W16> me = load_packed<W16>(packed, r, rowsz);
   for (uint32_t probes = 0; probes <= mask; probes++) {
     Slot s = load_slot(&table[idx]);
     if (s.key == kEmpty) {
@@ -656,7 +682,7 @@ __device__ __noinline__ int32_t resolve_packed(const uint8_t* packed, Slot* tabl
       s.minrow = 0xFFFFFFFFu;
       s.nbin = 0xFFFFFFFFu;
     }
-    if ((uint32_t)(s.key >> 32) == tag && packed_equal<W16>(me, load_packed<W16>(packed, (int64_t)(uint32_t)s.key)))
+    if ((uint32_t)(s.key >> 32) == tag && packed_equal<W16>(me, load_packed<W16>(packed, (int64_t)(uint32_t)s.key, rowsz)))
       return s.bin() ? (int32_t)s.bin() : provisional(table, idx, (uint32_t)r, s.minrow);
     idx = (idx + 1) & mask;
   }
@@ -668,7 +694,7 @@ __device__ __noinline__ int32_t resolve_packed(const uint8_t* packed, Slot* tabl
 template <int W16>
 __global__ void __launch_bounds__(256) gb_round_packed(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ filter,
                                                        int32_t* __restrict__ ikey, Slot* table, uint32_t mask, int64_t lo,
-                                                       int64_t hi, uint32_t* newlist, GbCounters* ctr, uint32_t new_limit) {
+                                                       int64_t hi, uint32_t* newlist, GbCounters* ctr, uint32_t new_limit, int rowsz) {
   constexpr int R = 2;  // rows per lane (4 measured 2.4x slower: 128 registers, two CTAs per SM)
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -684,7 +710,7 @@ __global__ void __launch_bounds__(256) gb_round_packed(const uint8_t* __restrict
     for (int i = 0; i < R; i++) {
       r[i] = tb + i * 32 + lane;
       live[i] = r[i] < hi && (!filter || filter[r[i]]);
-      if (live[i]) me[i] = load_packed<W16>(packed, r[i]);
+      if (live[i]) me[i] = load_packed<W16>(packed, r[i], rowsz);
     }
     Slot s[R];
 #pragma unroll
@@ -697,7 +723,7 @@ __global__ void __launch_bounds__(256) gb_round_packed(const uint8_t* __restrict
 #pragma unroll
     for (int i = 0; i < R; i++) {
       cand[i] = live[i] && s[i].key != kEmpty && (uint32_t)(s[i].key >> 32) == (uint32_t)(h[i] >> 32) && s[i].bin() != 0;
-      if (cand[i]) rep[i] = load_packed<W16>(packed, (int64_t)(uint32_t)s[i].key);
+      if (cand[i]) rep[i] = load_packed<W16>(packed, (int64_t)(uint32_t)s[i].key, rowsz);
     }
 #pragma unroll
     for (int i = 0; i < R; i++) {
@@ -705,7 +731,7 @@ __global__ void __launch_bounds__(256) gb_round_packed(const uint8_t* __restrict
       int32_t o = 0;
       if (live[i]) {
         if (cand[i] && packed_equal<W16>(me[i], rep[i])) o = (int32_t)s[i].bin();
-        else o = resolve_packed<W16>(packed, table, mask, r[i], (uint32_t)(h[i] >> 32), ((uint32_t)h[i] & bmask) * 2, newlist, ctr, new_limit);
+        else o = resolve_packed<W16>(packed, table, mask, r[i], (uint32_t)(h[i] >> 32), ((uint32_t)h[i] & bmask) * 2, newlist, ctr, new_limit, rowsz);
       }
       ikey[r[i]] = o;
     }
@@ -739,7 +765,7 @@ __global__ void __launch_bounds__(1024, 1) gb_round_packed_smem(const uint8_t* _
                                                                 int32_t* __restrict__ ikey, Slot* table, uint32_t mask,
                                                                 int64_t lo, int64_t hi, uint32_t* newlist, GbCounters* ctr,
                                                                 uint32_t new_limit, const int32_t* __restrict__ ifirstkey,
-                                                                uint32_t U, uint32_t icap) {
+                                                                uint32_t U, uint32_t icap, int rowsz) {
   extern __shared__ __align__(16) unsigned char gb_smem[];
   uint4* skeys = (uint4*)gb_smem;                            // [U][W16]
   uint16_t* sidx = (uint16_t*)(skeys + (size_t)U * W16);     // [icap], 0xFFFF = empty
@@ -747,7 +773,7 @@ __global__ void __launch_bounds__(1024, 1) gb_round_packed_smem(const uint8_t* _
   __syncthreads();
   const uint32_t imask = icap - 1;
   for (uint32_t b = threadIdx.x; b < U; b += blockDim.x) {
-    const PackedRow<W16> k = load_packed<W16>(packed, (int64_t)ifirstkey[b]);
+    const PackedRow<W16> k = load_packed<W16>(packed, (int64_t)ifirstkey[b], rowsz);
 #pragma unroll
     for (int j = 0; j < W16; j++) skeys[(size_t)b * W16 + j] = k.w[j];
     uint32_t slot = (uint32_t)hash_packed<W16>(k) & imask;
@@ -758,13 +784,13 @@ __global__ void __launch_bounds__(1024, 1) gb_round_packed_smem(const uint8_t* _
   for (int64_t r = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < hi; r += stride) {
     int32_t o = 0;
     if (!filter || filter[r]) {
-      const PackedRow<W16> me = load_packed<W16>(packed, r);
+      const PackedRow<W16> me = load_packed<W16>(packed, r, rowsz);
       const unsigned long long h = hash_packed<W16>(me);
       uint32_t slot = (uint32_t)h & imask;
       for (;;) {
         const uint32_t e = sidx[slot];
         if (e == 0xFFFFu) {  // not in the snapshot: the general path on the global table
-          o = resolve_packed<W16>(packed, table, mask, r, (uint32_t)(h >> 32), ((uint32_t)h & (mask >> 1)) * 2, newlist, ctr, new_limit);
+          o = resolve_packed<W16>(packed, table, mask, r, (uint32_t)(h >> 32), ((uint32_t)h & (mask >> 1)) * 2, newlist, ctr, new_limit, rowsz);
           break;
         }
         PackedRow<W16> k;
@@ -783,10 +809,10 @@ __global__ void __launch_bounds__(1024, 1) gb_round_packed_smem(const uint8_t* _
 
 template <int W16>
 __global__ void __launch_bounds__(256) gb_reinsert_packed(const uint8_t* __restrict__ packed, Slot* table, uint32_t mask,
-                                                          const Slot* staged, uint32_t n) {
+                                                          const Slot* staged, uint32_t n, int rowsz) {
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     Slot s = staged[j];
-    unsigned long long h = hash_packed<W16>(load_packed<W16>(packed, (int64_t)(uint32_t)s.key));
+    unsigned long long h = hash_packed<W16>(load_packed<W16>(packed, (int64_t)(uint32_t)s.key, rowsz));
     uint32_t idx = ((uint32_t)h & (mask >> 1)) * 2;
     while (atomicCAS(&table[idx].key, kEmpty, s.key) != kEmpty) idx = (idx + 1) & mask;
     table[idx].minrow = s.minrow;
@@ -1208,9 +1234,14 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
     kc.chunk[nkeys] = 4;
     kc.ncols = nkeys + 1;
   }
+  int rowsz = W;  // bytes per row as the kernels read them
   if (W && kc.ncols == 1 && kc.itemsize[0] == W && ((uintptr_t)kc.ptr[0] % 16) == 0) {
     // one column whose items already are the packed rows (S16, S32, U4 ...): probe it in place
     L.packed = const_cast<uint8_t*>(kc.ptr[0]);
+  } else if (W && kc.ncols == 1 && ((uintptr_t)kc.ptr[0] % 4) == 0) {
+    // one column of any other item size (S10, S12, U3 ...): also in place, rows assembled from unaligned words
+    L.packed = const_cast<uint8_t*>(kc.ptr[0]);
+    rowsz = kc.itemsize[0];
   } else if (W) {
     if (row_bytes < W) RTB_CUDA(cudaMemsetAsync(L.packed, 0, (size_t)nrows * W, stream));  // zero the padding
     int off = 0;
@@ -1275,10 +1306,10 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
             gb_reinsert_direct<<<grid_for(staged_n, 256, 1), 256, 0, stream>>>(L.table, want - 1, L.staged, staged_n);
           else
             switch (W) {
-              case 16: gb_reinsert_packed<1><<<grid_for(staged_n, 256, 1), 256, 0, stream>>>(L.packed, L.table, want - 1, L.staged, staged_n); break;
-              case 32: gb_reinsert_packed<2><<<grid_for(staged_n, 256, 1), 256, 0, stream>>>(L.packed, L.table, want - 1, L.staged, staged_n); break;
-              case 48: gb_reinsert_packed<3><<<grid_for(staged_n, 256, 1), 256, 0, stream>>>(L.packed, L.table, want - 1, L.staged, staged_n); break;
-              case 64: gb_reinsert_packed<4><<<grid_for(staged_n, 256, 1), 256, 0, stream>>>(L.packed, L.table, want - 1, L.staged, staged_n); break;
+              case 16: gb_reinsert_packed<1><<<grid_for(staged_n, 256, 1), 256, 0, stream>>>(L.packed, L.table, want - 1, L.staged, staged_n, rowsz); break;
+              case 32: gb_reinsert_packed<2><<<grid_for(staged_n, 256, 1), 256, 0, stream>>>(L.packed, L.table, want - 1, L.staged, staged_n, rowsz); break;
+              case 48: gb_reinsert_packed<3><<<grid_for(staged_n, 256, 1), 256, 0, stream>>>(L.packed, L.table, want - 1, L.staged, staged_n, rowsz); break;
+              case 64: gb_reinsert_packed<4><<<grid_for(staged_n, 256, 1), 256, 0, stream>>>(L.packed, L.table, want - 1, L.staged, staged_n, rowsz); break;
               default: gb_reinsert_byref<<<grid_for(staged_n, 256, 1), 256, 0, stream>>>(kc, L.table, want - 1, L.staged, staged_n);
             }
           RTB_LAUNCH_CHECK();
@@ -1363,7 +1394,7 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
       attr = true;                                                                                                        \
     }                                                                                                                     \
     gb_round_packed_smem<W16_><<<g3, 1024, smem, stream>>>(L.packed, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, \
-                                                          new_limit, ifirstkey_out, (uint32_t)U, icap);                 \
+                                                          new_limit, ifirstkey_out, (uint32_t)U, icap, rowsz);          \
   } while (0)
         switch (W) {
           case 16: RTB_PSMEM_ROUND(1); break;
@@ -1374,10 +1405,10 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
 #undef RTB_PSMEM_ROUND
       } else {
         switch (W) {
-          case 16: gb_round_packed<1><<<grid_for(rows, 256, 2, 8), 256, 0, stream>>>(L.packed, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit); break;
-          case 32: gb_round_packed<2><<<grid_for(rows, 256, 2, 8), 256, 0, stream>>>(L.packed, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit); break;
-          case 48: gb_round_packed<3><<<grid_for(rows, 256, 2, 8), 256, 0, stream>>>(L.packed, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit); break;
-          case 64: gb_round_packed<4><<<grid_for(rows, 256, 2, 8), 256, 0, stream>>>(L.packed, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit); break;
+          case 16: gb_round_packed<1><<<grid_for(rows, 256, 2, 8), 256, 0, stream>>>(L.packed, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit, rowsz); break;
+          case 32: gb_round_packed<2><<<grid_for(rows, 256, 2, 8), 256, 0, stream>>>(L.packed, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit, rowsz); break;
+          case 48: gb_round_packed<3><<<grid_for(rows, 256, 2, 8), 256, 0, stream>>>(L.packed, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit, rowsz); break;
+          case 64: gb_round_packed<4><<<grid_for(rows, 256, 2, 8), 256, 0, stream>>>(L.packed, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit, rowsz); break;
           default: gb_round_byref<<<grid_for(rows, 256, 4, 6), 256, 0, stream>>>(kc, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit);
         }
       }

@@ -968,7 +968,7 @@ struct GbPlan {
 };
 
 static GbPlan get_plan() {
-  GbPlan p{0, 1, 1, 1, 0.002, 4, 1 << 20, 0.25, 0.75, 4, 8.0 * 1024 * 1024 * 1024, 64ll << 20};
+  GbPlan p{0, 1, 1, 1, 0.002, 4, 1 << 20, 0.25, 0.75, 4, 8.0 * 1024 * 1024 * 1024, 256ll << 20};
   if (const char* e = getenv("RTB_GB_FINISH")) p.finish_rows = atoll(e);
   if (const char* e = getenv("RTB_GB_BIGTABLE")) p.big_table_bytes = atof(e);
   if (const char* e = getenv("RTB_GB_L2WIN")) p.l2_window = atoi(e);

@@ -103,6 +103,27 @@ def test_multikey_and_strings(rc):
     _check_gb(rc, [a.astype(np.int64), s16, i4])
 
 
+def test_small_rows_composed_into_one_key(rc):
+    # key rows of at most 8 bytes (several small columns, or one 3/5/6/7-byte column) run as one composed 64-bit key
+    rng = np.random.default_rng(41)
+    n = 2_400_007
+    a4, b4 = rng.integers(-50, 50, n).astype(np.int32), rng.integers(0, 300, n).astype(np.int32)
+    a2, a1 = rng.integers(-5, 5, n).astype(np.int16), rng.integers(0, 3, n).astype(np.int8)
+    f4 = rng.choice(np.array([0.0, -0.0, 1.5, np.nan], dtype=np.float32), n)
+    s3 = rng.choice(np.array([b"", b"a", b"ab", b"abc", b"zzz"], dtype="S3"), n)
+    s5 = rng.choice(rng.integers(65, 91, 700 * 5, dtype=np.uint8).view("S5"), n)
+    filt = rng.random(n) < 0.7
+    _check_gb(rc, [a4, b4])
+    _check_gb(rc, [a4, b4], filter=filt)
+    _check_gb(rc, [a2, a4, a1])
+    _check_gb(rc, [f4, a2])
+    _check_gb(rc, [s3, a4])
+    _check_gb(rc, [s5])
+    _check_gb(rc, [s3], filter=filt)
+    _check_gb(rc, [np.full(n, -1, np.int32), np.full(n, -1, np.int32)])  # composed key == the table's empty marker
+    _check_gb(rc, [a4[:777], b4[:777]])
+
+
 def test_packed_rows_in_shared_memory(rc):
     # settled string / multi-key tables small enough for shared memory (gb_round_packed_smem): rounds past the first 1 Mi
     # rows, with a filter, and with keys that first appear after the table had settled (they take the global fallback)

@@ -693,6 +693,58 @@ __device__ __forceinline__ bool packed_equal(const PackedRow<W16>& a, const Pack
   return d == 0;
 }
 
+// up to four bytes at an arbitrary byte offset of a 4-byte aligned buffer, zero-extended
+__device__ __forceinline__ uint32_t load_bytes4(const uint8_t* base, int64_t off, int nbytes) {
+  const uint32_t* wp = (const uint32_t*)(base + (off & ~3ll));
+  const int lead = (int)(off & 3);
+  const uint32_t lo = wp[0];
+  const uint32_t hi = (lead + nbytes > 4) ? wp[1] : 0u;
+  uint32_t v = __funnelshift_r(lo, hi, lead * 8);
+  if (nbytes < 4) v &= (1u << (8 * nbytes)) - 1u;
+  return v;
+}
+// The packed row of row r assembled straight from the key columns (what gb_pack_column would have written): used by
+// the shared-memory round, whose rows then never need the packed buffer.
+template <int W16>
+__device__ __forceinline__ PackedRow<W16> load_row_cols(const KeyCols& kc, int64_t r, bool whole_words) {
+  uint32_t o[4 * W16];
+#pragma unroll
+  for (int w = 0; w < 4 * W16; w++) o[w] = 0u;
+  int off = 0;
+  if (whole_words) {  // every item is a multiple of 4 bytes (int32, int64, float columns): aligned loads, no shifting
+    int word = 0;
+    for (int c = 0; c < kc.ncols; c++) {
+      const int nw = kc.itemsize[c] >> 2;
+      const uint32_t* src = (const uint32_t*)(kc.ptr[c] + r * (int64_t)kc.itemsize[c]);
+      for (int k = 0; k < nw; k++, word++) {
+        const uint32_t v = src[k];
+#pragma unroll
+        for (int w = 0; w < 4 * W16; w++) o[w] = (w == word) ? v : o[w];
+      }
+    }
+    PackedRow<W16> y;
+#pragma unroll
+    for (int j = 0; j < W16; j++) y.w[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    return y;
+  }
+  for (int c = 0; c < kc.ncols; c++) {
+    const int sz = kc.itemsize[c];
+    const int64_t b = r * (int64_t)sz;
+    for (int k = 0; k < sz; k += 4) {
+      const uint32_t v = load_bytes4(kc.ptr[c], b + k, sz - k < 4 ? sz - k : 4);
+      const int pos = off + k, word = pos >> 2, sh = (pos & 3) * 8;
+      const uint32_t lo = v << sh, hi = sh ? (v >> (32 - sh)) : 0u;
+#pragma unroll
+      for (int w = 0; w < 4 * W16; w++) o[w] |= (w == word ? lo : 0u) | (w == word + 1 ? hi : 0u);
+    }
+    off += sz;
+  }
+  PackedRow<W16> x;
+#pragma unroll
+  for (int j = 0; j < W16; j++) x.w[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+  return x;
+}
+
 template <int W16>
 __device__ __noinline__ int32_t resolve_packed(const uint8_t* packed, Slot* table, uint32_t mask, int64_t r, uint32_t tag,
                                                uint32_t idx, uint32_t* newlist, GbCounters* ctr, uint32_t new_limit, int rowsz) {
@@ -791,7 +843,7 @@ __global__ void __launch_bounds__(1024, 1) gb_round_packed_smem(const uint8_t* _
                                                                 int32_t* __restrict__ ikey, Slot* table, uint32_t mask,
                                                                 int64_t lo, int64_t hi, uint32_t* newlist, GbCounters* ctr,
                                                                 uint32_t new_limit, const int32_t* __restrict__ ifirstkey,
-                                                                uint32_t U, uint32_t icap, int rowsz) {
+                                                                uint32_t U, uint32_t icap, int rowsz, KeyCols kc, int from_cols) {
   extern __shared__ __align__(16) unsigned char gb_smem[];
   uint4* skeys = (uint4*)gb_smem;                            // [U][W16]
   uint16_t* sidx = (uint16_t*)(skeys + (size_t)U * W16);     // [icap], 0xFFFF = empty
@@ -807,29 +859,49 @@ __global__ void __launch_bounds__(1024, 1) gb_round_packed_smem(const uint8_t* _
   }
   __syncthreads();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t r = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < hi; r += stride) {
-    int32_t o = 0;
-    if (!filter || filter[r]) {
-      const PackedRow<W16> me = load_packed<W16>(packed, r, rowsz);
-      const unsigned long long h = hash_packed<W16>(me);
-      uint32_t slot = (uint32_t)h & imask;
-      for (;;) {
-        const uint32_t e = sidx[slot];
-        if (e == 0xFFFFu) {  // not in the snapshot: the general path on the global table
-          o = resolve_packed<W16>(packed, table, mask, r, (uint32_t)(h >> 32), ((uint32_t)h & (mask >> 1)) * 2, newlist, ctr, new_limit, rowsz);
-          break;
-        }
-        PackedRow<W16> k;
+  constexpr int R = W16 <= 2 ? 2 : 1;  // rows in flight per thread
+  for (int64_t r0 = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r0 < hi; r0 += stride * R) {
+    PackedRow<W16> me[R];
+    bool live[R];
 #pragma unroll
-        for (int j = 0; j < W16; j++) k.w[j] = skeys[(size_t)e * W16 + j];
-        if (packed_equal<W16>(me, k)) {
-          o = (int32_t)(e + 1);
-          break;
-        }
-        slot = (slot + 1) & imask;
-      }
+    for (int i = 0; i < R; i++) {
+      const int64_t r = r0 + i * stride;
+      live[i] = r < hi && (!filter || filter[r]);
+      if (live[i]) me[i] = from_cols ? load_row_cols<W16>(kc, r, from_cols == 2) : load_packed<W16>(packed, r, rowsz);
     }
-    ikey[r] = o;
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+      const int64_t r = r0 + i * stride;
+      if (r >= hi) continue;
+      int32_t o = 0;
+      if (live[i]) {
+        const unsigned long long h = hash_packed<W16>(me[i]);
+        uint32_t slot = (uint32_t)h & imask;
+        for (;;) {
+          const uint32_t e = sidx[slot];
+          if (e == 0xFFFFu) {  // not in the snapshot: the general path on the global table
+            if (from_cols) {
+              // this round's rows were never packed: publish this one before it can become a group's representative
+              uint4* dst = (uint4*)(const_cast<uint8_t*>(packed) + r * (int64_t)(16 * W16));
+#pragma unroll
+              for (int j = 0; j < W16; j++) dst[j] = me[i].w[j];
+              __threadfence();
+            }
+            o = resolve_packed<W16>(packed, table, mask, r, (uint32_t)(h >> 32), ((uint32_t)h & (mask >> 1)) * 2, newlist, ctr, new_limit, rowsz);
+            break;
+          }
+          PackedRow<W16> k;
+#pragma unroll
+          for (int j = 0; j < W16; j++) k.w[j] = skeys[(size_t)e * W16 + j];
+          if (packed_equal<W16>(me[i], k)) {
+            o = (int32_t)(e + 1);
+            break;
+          }
+          slot = (slot + 1) & imask;
+        }
+      }
+      ikey[r] = o;
+    }
   }
 }
 
@@ -1284,25 +1356,35 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
     // one column of any other item size (S10, S12, U3 ...): also in place, rows assembled from unaligned words
     L.packed = const_cast<uint8_t*>(kc.ptr[0]);
     rowsz = kc.itemsize[0];
-  } else if (W) {
-    if (row_bytes < W) RTB_CUDA(cudaMemsetAsync(L.packed, 0, (size_t)nrows * W, stream));  // zero the padding
+  }
+  // several columns: rows are packed round by round, right before a packed-row kernel reads them -- the shared-memory
+  // rounds (most rows of a low-cardinality multi-key grouping) assemble their rows from the columns and skip the pass
+  const bool lazy_pack = W != 0 && L.packed != nullptr && !(kc.ncols == 1 && ((uintptr_t)kc.ptr[0] % 4) == 0);
+  bool cols_aligned = true;
+  for (int c = 0; c < kc.ncols; c++) cols_aligned = cols_aligned && ((uintptr_t)kc.ptr[c] % 4) == 0;
+  auto pack_range = [&](int64_t a, int64_t b) -> int {
+    if (b <= a) return RTB_OK;
+    uint8_t* dst = L.packed + a * (int64_t)W;
+    if (row_bytes < W) RTB_CUDA(cudaMemsetAsync(dst, 0, (size_t)(b - a) * W, stream));  // zero the padding
     int off = 0;
     for (int c = 0; c < kc.ncols; c++) {
       const int sz = kc.itemsize[c];
       int g = kc.chunk[c];
-      while (g > 1 && (off % g) != 0) g >>= 1;
-      const int grid = grid_for(nrows, 256, 2, 16);
+      while (g > 1 && ((off % g) != 0 || ((a * (int64_t)sz) % g) != 0)) g >>= 1;
+      const int grid = grid_for(b - a, 256, 2, 16);
+      const uint8_t* src = kc.ptr[c] + a * (int64_t)sz;
       switch (g) {
-        case 16: gb_pack_column<16><<<grid, 256, 0, stream>>>(kc.ptr[c], sz, nrows, W, off, L.packed); break;
-        case 8: gb_pack_column<8><<<grid, 256, 0, stream>>>(kc.ptr[c], sz, nrows, W, off, L.packed); break;
-        case 4: gb_pack_column<4><<<grid, 256, 0, stream>>>(kc.ptr[c], sz, nrows, W, off, L.packed); break;
-        case 2: gb_pack_column<2><<<grid, 256, 0, stream>>>(kc.ptr[c], sz, nrows, W, off, L.packed); break;
-        default: gb_pack_column<1><<<grid, 256, 0, stream>>>(kc.ptr[c], sz, nrows, W, off, L.packed);
+        case 16: gb_pack_column<16><<<grid, 256, 0, stream>>>(src, sz, b - a, W, off, dst); break;
+        case 8: gb_pack_column<8><<<grid, 256, 0, stream>>>(src, sz, b - a, W, off, dst); break;
+        case 4: gb_pack_column<4><<<grid, 256, 0, stream>>>(src, sz, b - a, W, off, dst); break;
+        case 2: gb_pack_column<2><<<grid, 256, 0, stream>>>(src, sz, b - a, W, off, dst); break;
+        default: gb_pack_column<1><<<grid, 256, 0, stream>>>(src, sz, b - a, W, off, dst);
       }
       RTB_LAUNCH_CHECK();
       off += sz;
     }
-  }
+    return RTB_OK;
+  };
 
   uint32_t cap = st->cap;
   int64_t U = st->unique;
@@ -1333,6 +1415,7 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
       if (fits && !(settled && (uint64_t)cap >= 2ull * ideal)) want = cap;
     }
 
+    bool packed_this_round = false;
     for (int attempt = 0;; attempt++) {  // attempt loop: (re)size, run the round, grow on abort
       if (want != cap) {
         uint32_t staged_n = 0;
@@ -1425,6 +1508,14 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
         // settled, and every key fits in shared memory: stream-bound round (ifirstkey holds the representative rows)
         const uint32_t icap = packed_smem_icap(U);
         const size_t smem = packed_smem_bytes(U, W);
+        bool whole_words = true;
+        for (int c = 0; c < kc.ncols; c++) whole_words = whole_words && (kc.itemsize[c] % 4) == 0;
+        const int from_cols = (lazy_pack && W <= 32 && cols_aligned) ? (whole_words ? 2 : 1) : 0;
+        if (lazy_pack && !from_cols && !packed_this_round) {
+          int prc = pack_range(lo, hi);
+          if (prc != RTB_OK) return prc;
+          packed_this_round = true;
+        }
         int g3 = (int)((rows + 1024 * 8 - 1) / (1024 * 8));
         if (g3 > kSMs) g3 = kSMs;
         if (g3 < 1) g3 = 1;
@@ -1436,7 +1527,7 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
       attr = true;                                                                                                        \
     }                                                                                                                     \
     gb_round_packed_smem<W16_><<<g3, 1024, smem, stream>>>(L.packed, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, \
-                                                          new_limit, ifirstkey_out, (uint32_t)U, icap, rowsz);          \
+                                                          new_limit, ifirstkey_out, (uint32_t)U, icap, rowsz, kc, from_cols); \
   } while (0)
         switch (W) {
           case 16: RTB_PSMEM_ROUND(1); break;
@@ -1446,6 +1537,11 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
         }
 #undef RTB_PSMEM_ROUND
       } else {
+        if (lazy_pack && !packed_this_round) {
+          int prc = pack_range(lo, hi);
+          if (prc != RTB_OK) return prc;
+          packed_this_round = true;
+        }
         switch (W) {
           case 16: gb_round_packed<1><<<grid_for(rows, 256, 2, 8), 256, 0, stream>>>(L.packed, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit, rowsz); break;
           case 32: gb_round_packed<2><<<grid_for(rows, 256, 2, 8), 256, 0, stream>>>(L.packed, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit, rowsz); break;

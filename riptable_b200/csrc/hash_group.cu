@@ -716,6 +716,13 @@ __device__ __forceinline__ PackedRow<W16> load_row_cols(const KeyCols& kc, int64
     for (int c = 0; c < kc.ncols; c++) {
       const int nw = kc.itemsize[c] >> 2;
       const uint32_t* src = (const uint32_t*)(kc.ptr[c] + r * (int64_t)kc.itemsize[c]);
+      if (nw == 2 && kc.chunk[c] >= 8) {  // one 64-bit load for int64 / float64 items
+        const uint2 v = *(const uint2*)src;
+#pragma unroll
+        for (int w = 0; w < 4 * W16; w++) o[w] = (w == word) ? v.x : (w == word + 1) ? v.y : o[w];
+        word += 2;
+        continue;
+      }
       for (int k = 0; k < nw; k++, word++) {
         const uint32_t v = src[k];
 #pragma unroll
@@ -905,6 +912,87 @@ __global__ void __launch_bounds__(1024, 1) gb_round_packed_smem(const uint8_t* _
   }
 }
 
+// ---- packed 16-byte rows, any cardinality: a global-memory snapshot with the key inline ----------------------
+// The packed-row table stores a tag and the row id of a representative, so a probe is two dependent random accesses
+// (slot, then the representative's row somewhere in the packed buffer).  For settled tables of 16-byte rows whose keys do
+// not fit in shared memory, the finalised keys are also kept in a snapshot table of 32-byte entries {key, bin} -- one
+// sector, one access per probe.  The snapshot is only an accelerator: it holds finalised keys with their final bins, it is
+// extended between rounds from iFirstKey, and a row that misses it takes the exact path on the main table.
+struct SnapEntry {
+  uint4 key;
+  uint32_t bin;  // 0 = empty
+  uint32_t pad[3];
+};
+static_assert(sizeof(SnapEntry) == 32, "one sector per entry");
+
+__global__ void __launch_bounds__(256) gb_snap_build(const uint8_t* __restrict__ packed, int rowsz, const int32_t* __restrict__ ifirstkey,
+                                                     uint32_t b0, uint32_t b1, SnapEntry* snap, uint32_t smask) {
+  for (uint32_t b = b0 + blockIdx.x * blockDim.x + threadIdx.x; b < b1; b += gridDim.x * blockDim.x) {
+    const PackedRow<1> k = load_packed<1>(packed, (int64_t)ifirstkey[b], rowsz);
+    uint32_t slot = (uint32_t)(hash_packed<1>(k) >> 7) & smask;
+    while (atomicCAS(&snap[slot].bin, 0u, b + 1u) != 0u) slot = (slot + 1) & smask;
+    snap[slot].key = k.w[0];
+  }
+}
+
+__global__ void __launch_bounds__(256, 3) gb_round_packed_snap(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ filter,
+                                                               int32_t* __restrict__ ikey, Slot* table, uint32_t mask, int64_t lo,
+                                                               int64_t hi, uint32_t* newlist, GbCounters* ctr, uint32_t new_limit,
+                                                               const SnapEntry* __restrict__ snap, uint32_t smask, int rowsz,
+                                                               KeyCols kc, int from_cols) {
+  constexpr int R = 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r0 = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r0 < hi; r0 += stride * R) {
+    PackedRow<1> me[R];
+    bool live[R];
+    unsigned long long h[R];
+    uint32_t slot[R];
+    uint4 ek[R];
+    uint32_t ebin[R];
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+      const int64_t r = r0 + i * stride;
+      live[i] = r < hi && (!filter || filter[r]);
+      if (live[i]) me[i] = from_cols ? load_row_cols<1>(kc, r, from_cols == 2) : load_packed<1>(packed, r, rowsz);
+    }
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+      h[i] = live[i] ? hash_packed<1>(me[i]) : 0ull;
+      slot[i] = (uint32_t)(h[i] >> 7) & smask;
+      if (live[i]) {
+        ek[i] = snap[slot[i]].key;
+        ebin[i] = snap[slot[i]].bin;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+      const int64_t r = r0 + i * stride;
+      if (r >= hi) continue;
+      int32_t o = 0;
+      if (live[i]) {
+        for (;;) {
+          if (ebin[i] == 0u) {  // not in the snapshot: the exact path on the main table
+            if (from_cols) {
+              *(uint4*)(const_cast<uint8_t*>(packed) + r * 16) = me[i].w[0];
+              __threadfence();
+            }
+            o = resolve_packed<1>(packed, table, mask, r, (uint32_t)(h[i] >> 32), ((uint32_t)h[i] & (mask >> 1)) * 2, newlist, ctr, new_limit, rowsz);
+            break;
+          }
+          if (ek[i].x == me[i].w[0].x && ek[i].y == me[i].w[0].y && ek[i].z == me[i].w[0].z && ek[i].w == me[i].w[0].w) {
+            o = (int32_t)ebin[i];
+            break;
+          }
+          slot[i] = (slot[i] + 1) & smask;
+          ek[i] = snap[slot[i]].key;
+          ebin[i] = snap[slot[i]].bin;
+        }
+      }
+      ikey[r] = o;
+    }
+  }
+}
+
 template <int W16>
 __global__ void __launch_bounds__(256) gb_reinsert_packed(const uint8_t* __restrict__ packed, Slot* table, uint32_t mask,
                                                           const Slot* staged, uint32_t n, int rowsz) {
@@ -1063,10 +1151,14 @@ struct GbPlan {
   int ratio;
   double big_table_bytes;  // above this table size every round uses the slot-wise kernel
   int64_t finish_rows;     // a settled table finishes a remainder of at most this many rows in one round
+  int snapshot;            // 16-byte packed rows: inline-key snapshot table for the settled rounds
+  double snap_fill;        // snapshot entries per key (power of two above it)
 };
 
 static GbPlan get_plan() {
-  GbPlan p{0, 1, 1, 1, 0.002, 4, 1 << 20, 0.25, 0.75, 4, 8.0 * 1024 * 1024 * 1024, 256ll << 20};
+  GbPlan p{0, 1, 1, 1, 0.002, 4, 1 << 20, 0.25, 0.75, 4, 8.0 * 1024 * 1024 * 1024, 256ll << 20, 1, 2.0};
+  if (const char* e = getenv("RTB_GB_SNAPSHOT")) p.snapshot = atoi(e);
+  if (const char* e = getenv("RTB_GB_SNAPFILL")) p.snap_fill = atof(e);
   if (const char* e = getenv("RTB_GB_FINISH")) p.finish_rows = atoll(e);
   if (const char* e = getenv("RTB_GB_BIGTABLE")) p.big_table_bytes = atof(e);
   if (const char* e = getenv("RTB_GB_L2WIN")) p.l2_window = atoi(e);
@@ -1097,9 +1189,19 @@ struct GbLayout {
   int64_t* cutoffs_dev;
   uint32_t* ucount;   // per-partition unique counts, then exclusive bases
   uint8_t* packed;    // row-major packed key rows (multi-key / string rows up to 64 bytes), or nullptr
+  SnapEntry* snap;    // inline-key snapshot for 16-byte rows (kSnapCapMax entries), or nullptr
   size_t bytes_without_packed;
   size_t bytes;
 };
+
+constexpr uint32_t kSnapCapMax = 1u << 25;  // 32 Mi entries = 1 GB
+static uint32_t snap_cap_for(int64_t max_unique) {
+  const uint64_t want = 4ull * (uint64_t)max_unique + 1024;
+  if (want >= kSnapCapMax) return kSnapCapMax;
+  uint32_t c = 1024;
+  while (c < want) c <<= 1;
+  return c;
+}
 
 static int64_t largest_round(int64_t n, const GbPlan& p) {
   int64_t lo = 0, hi = p.round0 < n ? p.round0 : n, best = hi;
@@ -1130,6 +1232,7 @@ static GbLayout layout(void* ws, size_t wsbytes, int64_t nrows, int64_t max_uniq
   L.ucount = cutoffs ? a.take<uint32_t>((size_t)ncut) : nullptr;
   L.bytes_without_packed = a.off;
   L.packed = packed_row_bytes > 0 ? a.take<uint8_t>((size_t)nrows * packed_row_bytes + 64) : nullptr;
+  L.snap = packed_row_bytes == 16 ? a.take<SnapEntry>(snap_cap_for(max_unique)) : nullptr;
   L.bytes = a.off;
   return L;
 }
@@ -1386,6 +1489,8 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
     return RTB_OK;
   };
 
+  uint32_t snap_cap = 0;   // inline-key snapshot (16-byte packed rows): entries in use, bins it holds
+  int64_t snap_built = 0;
   uint32_t cap = st->cap;
   int64_t U = st->unique;
   int64_t prev_new = st->prev_new, prev_rows = st->prev_rows;
@@ -1536,6 +1641,28 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
           default: RTB_PSMEM_ROUND(4);
         }
 #undef RTB_PSMEM_ROUND
+      } else if (W == 16 && L.snap != nullptr && plan.snapshot && !has_cut && round > 0 && attempt == 0 && row_offset == 0 && U > 0 &&
+                 (double)prev_new <= plan.discovery_frac * (double)prev_rows && 2 * U <= (int64_t)snap_cap_for(max_unique)) {
+        // settled 16-byte rows beyond shared memory: one-access probes of the inline-key snapshot
+        if (snap_cap == 0 || 2 * U > (int64_t)snap_cap) {
+          uint32_t c = 1024;
+          while ((int64_t)c < (int64_t)(plan.snap_fill * (double)U)) c <<= 1;
+          const uint32_t cmax = snap_cap_for(max_unique);
+          snap_cap = c > cmax ? cmax : c;
+          RTB_CUDA(cudaMemsetAsync(L.snap, 0, sizeof(SnapEntry) * (size_t)snap_cap, stream));
+          snap_built = 0;
+        }
+        if (snap_built < U) {
+          gb_snap_build<<<grid_for(U - snap_built, 256, 1), 256, 0, stream>>>(L.packed, rowsz, ifirstkey_out, (uint32_t)snap_built,
+                                                                              (uint32_t)U, L.snap, snap_cap - 1);
+          RTB_LAUNCH_CHECK();
+          snap_built = U;
+        }
+        bool whole_words = true;
+        for (int c = 0; c < kc.ncols; c++) whole_words = whole_words && (kc.itemsize[c] % 4) == 0;
+        const int from_cols = (lazy_pack && cols_aligned) ? (whole_words ? 2 : 1) : 0;
+        gb_round_packed_snap<<<grid_for(rows, 256, 4, 3), 256, 0, stream>>>(L.packed, filter, ikey_out, L.table, mask, lo, hi, newlist,
+                                                                          L.ctr, new_limit, L.snap, snap_cap - 1, rowsz, kc, from_cols);
       } else {
         if (lazy_pack && !packed_this_round) {
           int prc = pack_range(lo, hi);

@@ -147,6 +147,24 @@ def test_packed_rows_in_shared_memory(rc):
     _check_gb(rc, [many])
 
 
+def test_packed_rows_snapshot_table(rc):
+    # 16-byte rows with more keys than shared memory holds: settled rounds probe the inline-key snapshot; keys that
+    # first appear later take the exact path and are added to the snapshot for the following rounds
+    rng = np.random.default_rng(53)
+    n = 6_000_011
+    a8 = rng.integers(0, 3000, n).astype(np.int64) * 1_000_003
+    b4 = rng.integers(0, 40, n).astype(np.int32)
+    _check_gb(rc, [a8, b4])  # 120 000 pairs
+    _check_gb(rc, [a8, b4], filter=rng.random(n) < 0.5)
+    s12 = rng.choice(rng.integers(65, 91, 40_000 * 12, dtype=np.uint8).view("S12"), n)
+    _check_gb(rc, [s12])
+    late = a8.copy()
+    late[4_500_000:] += rng.integers(0, 2, n - 4_500_000) * 17  # new pairs appear after the table had settled
+    _check_gb(rc, [late, b4])
+    s8 = rng.choice(rng.integers(65, 91, 5000 * 8, dtype=np.uint8).view("S8"), n)
+    _check_gb(rc, [s8, b4])
+
+
 def test_projections_fixture(rc):
     # tests/test_groupby.py:419-459 -> exactly 455 654 groups
     n, num_symbols = 1_000_000, 450

@@ -705,29 +705,25 @@ __device__ __forceinline__ uint32_t load_bytes4(const uint8_t* base, int64_t off
 }
 // The packed row of row r assembled straight from the key columns (what gb_pack_column would have written): used by
 // the shared-memory round, whose rows then never need the packed buffer.
+// Where every 32-bit word of a packed row comes from when all items are multiples of 4 bytes (int32, int64, float
+// columns): column index and word inside the item, -1 for padding.  Built on the host, so the device code indexes its
+// registers statically and needs one aligned 4-byte load per word.
+struct WordMap {
+  int8_t col[8];
+  int8_t k[8];
+};
+
 template <int W16>
-__device__ __forceinline__ PackedRow<W16> load_row_cols(const KeyCols& kc, int64_t r, bool whole_words) {
+__device__ __forceinline__ PackedRow<W16> load_row_cols(const KeyCols& kc, int64_t r, bool whole_words, const WordMap& wm) {
   uint32_t o[4 * W16];
 #pragma unroll
   for (int w = 0; w < 4 * W16; w++) o[w] = 0u;
   int off = 0;
-  if (whole_words) {  // every item is a multiple of 4 bytes (int32, int64, float columns): aligned loads, no shifting
-    int word = 0;
-    for (int c = 0; c < kc.ncols; c++) {
-      const int nw = kc.itemsize[c] >> 2;
-      const uint32_t* src = (const uint32_t*)(kc.ptr[c] + r * (int64_t)kc.itemsize[c]);
-      if (nw == 2 && kc.chunk[c] >= 8) {  // one 64-bit load for int64 / float64 items
-        const uint2 v = *(const uint2*)src;
+  if (whole_words) {
 #pragma unroll
-        for (int w = 0; w < 4 * W16; w++) o[w] = (w == word) ? v.x : (w == word + 1) ? v.y : o[w];
-        word += 2;
-        continue;
-      }
-      for (int k = 0; k < nw; k++, word++) {
-        const uint32_t v = src[k];
-#pragma unroll
-        for (int w = 0; w < 4 * W16; w++) o[w] = (w == word) ? v : o[w];
-      }
+    for (int w = 0; w < 4 * W16; w++) {
+      const int c = wm.col[w];
+      if (c >= 0) o[w] = ((const uint32_t*)(kc.ptr[c] + r * (int64_t)kc.itemsize[c]))[wm.k[w]];
     }
     PackedRow<W16> y;
 #pragma unroll
@@ -850,7 +846,7 @@ __global__ void __launch_bounds__(1024, 1) gb_round_packed_smem(const uint8_t* _
                                                                 int32_t* __restrict__ ikey, Slot* table, uint32_t mask,
                                                                 int64_t lo, int64_t hi, uint32_t* newlist, GbCounters* ctr,
                                                                 uint32_t new_limit, const int32_t* __restrict__ ifirstkey,
-                                                                uint32_t U, uint32_t icap, int rowsz, KeyCols kc, int from_cols) {
+                                                                uint32_t U, uint32_t icap, int rowsz, KeyCols kc, int from_cols, WordMap wm) {
   extern __shared__ __align__(16) unsigned char gb_smem[];
   uint4* skeys = (uint4*)gb_smem;                            // [U][W16]
   uint16_t* sidx = (uint16_t*)(skeys + (size_t)U * W16);     // [icap], 0xFFFF = empty
@@ -874,7 +870,7 @@ __global__ void __launch_bounds__(1024, 1) gb_round_packed_smem(const uint8_t* _
     for (int i = 0; i < R; i++) {
       const int64_t r = r0 + i * stride;
       live[i] = r < hi && (!filter || filter[r]);
-      if (live[i]) me[i] = from_cols ? load_row_cols<W16>(kc, r, from_cols == 2) : load_packed<W16>(packed, r, rowsz);
+      if (live[i]) me[i] = from_cols ? load_row_cols<W16>(kc, r, from_cols == 2, wm) : load_packed<W16>(packed, r, rowsz);
     }
 #pragma unroll
     for (int i = 0; i < R; i++) {
@@ -939,7 +935,7 @@ __global__ void __launch_bounds__(256, 3) gb_round_packed_snap(const uint8_t* __
                                                                int32_t* __restrict__ ikey, Slot* table, uint32_t mask, int64_t lo,
                                                                int64_t hi, uint32_t* newlist, GbCounters* ctr, uint32_t new_limit,
                                                                const SnapEntry* __restrict__ snap, uint32_t smask, int rowsz,
-                                                               KeyCols kc, int from_cols) {
+                                                               KeyCols kc, int from_cols, WordMap wm) {
   constexpr int R = 4;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t r0 = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r0 < hi; r0 += stride * R) {
@@ -953,7 +949,7 @@ __global__ void __launch_bounds__(256, 3) gb_round_packed_snap(const uint8_t* __
     for (int i = 0; i < R; i++) {
       const int64_t r = r0 + i * stride;
       live[i] = r < hi && (!filter || filter[r]);
-      if (live[i]) me[i] = from_cols ? load_row_cols<1>(kc, r, from_cols == 2) : load_packed<1>(packed, r, rowsz);
+      if (live[i]) me[i] = from_cols ? load_row_cols<1>(kc, r, from_cols == 2, wm) : load_packed<1>(packed, r, rowsz);
     }
 #pragma unroll
     for (int i = 0; i < R; i++) {
@@ -1465,6 +1461,16 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
   const bool lazy_pack = W != 0 && L.packed != nullptr && !(kc.ncols == 1 && ((uintptr_t)kc.ptr[0] % 4) == 0);
   bool cols_aligned = true;
   for (int c = 0; c < kc.ncols; c++) cols_aligned = cols_aligned && ((uintptr_t)kc.ptr[c] % 4) == 0;
+  WordMap wm;
+  bool whole_words_all = W != 0 && W <= 32;
+  for (int w = 0; w < 8; w++) wm.col[w] = -1, wm.k[w] = 0;
+  {
+    int word = 0;
+    for (int c = 0; c < kc.ncols && whole_words_all; c++) {
+      if (kc.itemsize[c] % 4 != 0) { whole_words_all = false; break; }
+      for (int k = 0; k < kc.itemsize[c] / 4 && word < 8; k++, word++) wm.col[word] = (int8_t)c, wm.k[word] = (int8_t)k;
+    }
+  }
   auto pack_range = [&](int64_t a, int64_t b) -> int {
     if (b <= a) return RTB_OK;
     uint8_t* dst = L.packed + a * (int64_t)W;
@@ -1613,9 +1619,7 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
         // settled, and every key fits in shared memory: stream-bound round (ifirstkey holds the representative rows)
         const uint32_t icap = packed_smem_icap(U);
         const size_t smem = packed_smem_bytes(U, W);
-        bool whole_words = true;
-        for (int c = 0; c < kc.ncols; c++) whole_words = whole_words && (kc.itemsize[c] % 4) == 0;
-        const int from_cols = (lazy_pack && W <= 32 && cols_aligned) ? (whole_words ? 2 : 1) : 0;
+        const int from_cols = (lazy_pack && W <= 32 && cols_aligned) ? (whole_words_all ? 2 : 1) : 0;
         if (lazy_pack && !from_cols && !packed_this_round) {
           int prc = pack_range(lo, hi);
           if (prc != RTB_OK) return prc;
@@ -1632,7 +1636,7 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
       attr = true;                                                                                                        \
     }                                                                                                                     \
     gb_round_packed_smem<W16_><<<g3, 1024, smem, stream>>>(L.packed, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, \
-                                                          new_limit, ifirstkey_out, (uint32_t)U, icap, rowsz, kc, from_cols); \
+                                                          new_limit, ifirstkey_out, (uint32_t)U, icap, rowsz, kc, from_cols, wm); \
   } while (0)
         switch (W) {
           case 16: RTB_PSMEM_ROUND(1); break;
@@ -1658,11 +1662,9 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
           RTB_LAUNCH_CHECK();
           snap_built = U;
         }
-        bool whole_words = true;
-        for (int c = 0; c < kc.ncols; c++) whole_words = whole_words && (kc.itemsize[c] % 4) == 0;
-        const int from_cols = (lazy_pack && cols_aligned) ? (whole_words ? 2 : 1) : 0;
+        const int from_cols = (lazy_pack && cols_aligned) ? (whole_words_all ? 2 : 1) : 0;
         gb_round_packed_snap<<<grid_for(rows, 256, 4, 3), 256, 0, stream>>>(L.packed, filter, ikey_out, L.table, mask, lo, hi, newlist,
-                                                                          L.ctr, new_limit, L.snap, snap_cap - 1, rowsz, kc, from_cols);
+                                                                          L.ctr, new_limit, L.snap, snap_cap - 1, rowsz, kc, from_cols, wm);
       } else {
         if (lazy_pack && !packed_this_round) {
           int prc = pack_range(lo, hi);

@@ -914,49 +914,54 @@ __global__ void __launch_bounds__(1024, 1) gb_round_packed_smem(const uint8_t* _
 // not fit in shared memory, the finalised keys are also kept in a snapshot table of 32-byte entries {key, bin} -- one
 // sector, one access per probe.  The snapshot is only an accelerator: it holds finalised keys with their final bins, it is
 // extended between rounds from iFirstKey, and a row that misses it takes the exact path on the main table.
-struct SnapEntry {
-  uint4 key;
+template <int W16>
+struct SnapEntry {  // 32 bytes for 16-byte rows (one sector), 64 bytes for 32-byte rows
+  uint4 key[W16];
   uint32_t bin;  // 0 = empty
-  uint32_t pad[3];
+  uint32_t pad[4 * W16 - 1];
 };
-static_assert(sizeof(SnapEntry) == 32, "one sector per entry");
+static_assert(sizeof(SnapEntry<1>) == 32 && sizeof(SnapEntry<2>) == 64, "snapshot entries are whole sectors");
 
+template <int W16>
 __global__ void __launch_bounds__(256) gb_snap_build(const uint8_t* __restrict__ packed, int rowsz, const int32_t* __restrict__ ifirstkey,
-                                                     uint32_t b0, uint32_t b1, SnapEntry* snap, uint32_t smask) {
+                                                     uint32_t b0, uint32_t b1, SnapEntry<W16>* snap, uint32_t smask) {
   for (uint32_t b = b0 + blockIdx.x * blockDim.x + threadIdx.x; b < b1; b += gridDim.x * blockDim.x) {
-    const PackedRow<1> k = load_packed<1>(packed, (int64_t)ifirstkey[b], rowsz);
-    uint32_t slot = (uint32_t)(hash_packed<1>(k) >> 7) & smask;
+    const PackedRow<W16> k = load_packed<W16>(packed, (int64_t)ifirstkey[b], rowsz);
+    uint32_t slot = (uint32_t)(hash_packed<W16>(k) >> 7) & smask;
     while (atomicCAS(&snap[slot].bin, 0u, b + 1u) != 0u) slot = (slot + 1) & smask;
-    snap[slot].key = k.w[0];
+#pragma unroll
+    for (int j = 0; j < W16; j++) snap[slot].key[j] = k.w[j];
   }
 }
 
+template <int W16>
 __global__ void __launch_bounds__(256, 3) gb_round_packed_snap(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ filter,
                                                                int32_t* __restrict__ ikey, Slot* table, uint32_t mask, int64_t lo,
                                                                int64_t hi, uint32_t* newlist, GbCounters* ctr, uint32_t new_limit,
-                                                               const SnapEntry* __restrict__ snap, uint32_t smask, int rowsz,
+                                                               const SnapEntry<W16>* __restrict__ snap, uint32_t smask, int rowsz,
                                                                KeyCols kc, int from_cols, WordMap wm) {
-  constexpr int R = 4;
+  constexpr int R = W16 == 1 ? 4 : 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t r0 = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r0 < hi; r0 += stride * R) {
-    PackedRow<1> me[R];
+    PackedRow<W16> me[R];
     bool live[R];
     unsigned long long h[R];
     uint32_t slot[R];
-    uint4 ek[R];
+    PackedRow<W16> ek[R];
     uint32_t ebin[R];
 #pragma unroll
     for (int i = 0; i < R; i++) {
       const int64_t r = r0 + i * stride;
       live[i] = r < hi && (!filter || filter[r]);
-      if (live[i]) me[i] = from_cols ? load_row_cols<1>(kc, r, from_cols == 2, wm) : load_packed<1>(packed, r, rowsz);
+      if (live[i]) me[i] = from_cols ? load_row_cols<W16>(kc, r, from_cols == 2, wm) : load_packed<W16>(packed, r, rowsz);
     }
 #pragma unroll
     for (int i = 0; i < R; i++) {
-      h[i] = live[i] ? hash_packed<1>(me[i]) : 0ull;
+      h[i] = live[i] ? hash_packed<W16>(me[i]) : 0ull;
       slot[i] = (uint32_t)(h[i] >> 7) & smask;
       if (live[i]) {
-        ek[i] = snap[slot[i]].key;
+#pragma unroll
+        for (int j = 0; j < W16; j++) ek[i].w[j] = snap[slot[i]].key[j];
         ebin[i] = snap[slot[i]].bin;
       }
     }
@@ -969,18 +974,21 @@ __global__ void __launch_bounds__(256, 3) gb_round_packed_snap(const uint8_t* __
         for (;;) {
           if (ebin[i] == 0u) {  // not in the snapshot: the exact path on the main table
             if (from_cols) {
-              *(uint4*)(const_cast<uint8_t*>(packed) + r * 16) = me[i].w[0];
+              uint4* dst = (uint4*)(const_cast<uint8_t*>(packed) + r * (int64_t)(16 * W16));
+#pragma unroll
+              for (int j = 0; j < W16; j++) dst[j] = me[i].w[j];
               __threadfence();
             }
-            o = resolve_packed<1>(packed, table, mask, r, (uint32_t)(h[i] >> 32), ((uint32_t)h[i] & (mask >> 1)) * 2, newlist, ctr, new_limit, rowsz);
+            o = resolve_packed<W16>(packed, table, mask, r, (uint32_t)(h[i] >> 32), ((uint32_t)h[i] & (mask >> 1)) * 2, newlist, ctr, new_limit, rowsz);
             break;
           }
-          if (ek[i].x == me[i].w[0].x && ek[i].y == me[i].w[0].y && ek[i].z == me[i].w[0].z && ek[i].w == me[i].w[0].w) {
+          if (packed_equal<W16>(ek[i], me[i])) {
             o = (int32_t)ebin[i];
             break;
           }
           slot[i] = (slot[i] + 1) & smask;
-          ek[i] = snap[slot[i]].key;
+#pragma unroll
+          for (int j = 0; j < W16; j++) ek[i].w[j] = snap[slot[i]].key[j];
           ebin[i] = snap[slot[i]].bin;
         }
       }
@@ -1185,7 +1193,7 @@ struct GbLayout {
   int64_t* cutoffs_dev;
   uint32_t* ucount;   // per-partition unique counts, then exclusive bases
   uint8_t* packed;    // row-major packed key rows (multi-key / string rows up to 64 bytes), or nullptr
-  SnapEntry* snap;    // inline-key snapshot for 16-byte rows (kSnapCapMax entries), or nullptr
+  uint8_t* snap;      // inline-key snapshot for 16- and 32-byte rows (32 / 64 bytes per entry), or nullptr
   size_t bytes_without_packed;
   size_t bytes;
 };
@@ -1228,7 +1236,7 @@ static GbLayout layout(void* ws, size_t wsbytes, int64_t nrows, int64_t max_uniq
   L.ucount = cutoffs ? a.take<uint32_t>((size_t)ncut) : nullptr;
   L.bytes_without_packed = a.off;
   L.packed = packed_row_bytes > 0 ? a.take<uint8_t>((size_t)nrows * packed_row_bytes + 64) : nullptr;
-  L.snap = packed_row_bytes == 16 ? a.take<SnapEntry>(snap_cap_for(max_unique)) : nullptr;
+  L.snap = (packed_row_bytes == 16 || packed_row_bytes == 32) ? a.take<uint8_t>((size_t)snap_cap_for(max_unique) * 2 * packed_row_bytes) : nullptr;
   L.bytes = a.off;
   return L;
 }
@@ -1645,26 +1653,38 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
           default: RTB_PSMEM_ROUND(4);
         }
 #undef RTB_PSMEM_ROUND
-      } else if (W == 16 && L.snap != nullptr && plan.snapshot && !has_cut && round > 0 && attempt == 0 && row_offset == 0 && U > 0 &&
-                 (double)prev_new <= plan.discovery_frac * (double)prev_rows && 2 * U <= (int64_t)snap_cap_for(max_unique)) {
-        // settled 16-byte rows beyond shared memory: one-access probes of the inline-key snapshot
+      } else if ((W == 16 || W == 32) && L.snap != nullptr && plan.snapshot && !has_cut && round > 0 && attempt == 0 && row_offset == 0 &&
+                 U > 0 && (double)prev_new <= plan.discovery_frac * (double)prev_rows && 2 * U <= (int64_t)snap_cap_for(max_unique)) {
+        // settled 16- / 32-byte rows beyond shared memory: one-access probes of the inline-key snapshot
+        const size_t esz = (size_t)2 * W;
         if (snap_cap == 0 || 2 * U > (int64_t)snap_cap) {
           uint32_t c = 1024;
           while ((int64_t)c < (int64_t)(plan.snap_fill * (double)U)) c <<= 1;
           const uint32_t cmax = snap_cap_for(max_unique);
           snap_cap = c > cmax ? cmax : c;
-          RTB_CUDA(cudaMemsetAsync(L.snap, 0, sizeof(SnapEntry) * (size_t)snap_cap, stream));
+          RTB_CUDA(cudaMemsetAsync(L.snap, 0, esz * (size_t)snap_cap, stream));
           snap_built = 0;
         }
-        if (snap_built < U) {
-          gb_snap_build<<<grid_for(U - snap_built, 256, 1), 256, 0, stream>>>(L.packed, rowsz, ifirstkey_out, (uint32_t)snap_built,
-                                                                              (uint32_t)U, L.snap, snap_cap - 1);
-          RTB_LAUNCH_CHECK();
-          snap_built = U;
-        }
         const int from_cols = (lazy_pack && cols_aligned) ? (whole_words_all ? 2 : 1) : 0;
-        gb_round_packed_snap<<<grid_for(rows, 256, 4, 3), 256, 0, stream>>>(L.packed, filter, ikey_out, L.table, mask, lo, hi, newlist,
-                                                                          L.ctr, new_limit, L.snap, snap_cap - 1, rowsz, kc, from_cols, wm);
+        const int gs = grid_for(rows, 256, 4, 3);
+        if (W == 16) {
+          if (snap_built < U) {
+            gb_snap_build<1><<<grid_for(U - snap_built, 256, 1), 256, 0, stream>>>(L.packed, rowsz, ifirstkey_out, (uint32_t)snap_built,
+                                                                                   (uint32_t)U, (SnapEntry<1>*)L.snap, snap_cap - 1);
+            RTB_LAUNCH_CHECK();
+          }
+          gb_round_packed_snap<1><<<gs, 256, 0, stream>>>(L.packed, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit,
+                                                         (const SnapEntry<1>*)L.snap, snap_cap - 1, rowsz, kc, from_cols, wm);
+        } else {
+          if (snap_built < U) {
+            gb_snap_build<2><<<grid_for(U - snap_built, 256, 1), 256, 0, stream>>>(L.packed, rowsz, ifirstkey_out, (uint32_t)snap_built,
+                                                                                   (uint32_t)U, (SnapEntry<2>*)L.snap, snap_cap - 1);
+            RTB_LAUNCH_CHECK();
+          }
+          gb_round_packed_snap<2><<<gs, 256, 0, stream>>>(L.packed, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit,
+                                                         (const SnapEntry<2>*)L.snap, snap_cap - 1, rowsz, kc, from_cols, wm);
+        }
+        snap_built = U;
       } else {
         if (lazy_pack && !packed_this_round) {
           int prc = pack_range(lo, hi);

@@ -163,6 +163,11 @@ def test_packed_rows_snapshot_table(rc):
     _check_gb(rc, [late, b4])
     s8 = rng.choice(rng.integers(65, 91, 5000 * 8, dtype=np.uint8).view("S8"), n)
     _check_gb(rc, [s8, b4])
+    # 32-byte rows: U8 keys, and (int64, S16, int32) = 28 bytes
+    u8 = rng.choice(rng.integers(65, 91, 12_000 * 8, dtype=np.int32).view("<U8"), n)
+    _check_gb(rc, [u8])
+    s16 = rng.choice(rng.integers(65, 91, 300 * 16, dtype=np.uint8).view("S16"), n)
+    _check_gb(rc, [a8, s16, b4 % 3], filter=rng.random(n) < 0.8)
 
 
 def test_projections_fixture(rc):

@@ -1142,25 +1142,27 @@ static uint32_t next_pow2_u64(uint64_t v) {
   return (uint32_t)(p > (1ull << 30) ? (1ull << 30) : p);
 }
 
+// Tunables of the round schedule and the kernel choice; every one has an RTB_GB_* environment override that exists for
+// measurement (profiles/), not for production use.
 struct GbPlan {
-  int l2_window;
-  int packed_rows;
-  int smem_table;
-  int prefetch;
-  double discovery_frac;  // a round whose predecessor found more new keys than this share of its rows is a discovery round
-  int ctas_per_sm;
-  int64_t round0;
-  double load_target;  // table sized so projected uniques / capacity <= this
-  double load_abort;   // a round aborts when uniques / capacity would exceed this
-  int ratio;
-  double big_table_bytes;  // above this table size every round uses the slot-wise kernel
-  int64_t finish_rows;     // a settled table finishes a remainder of at most this many rows in one round
-  int snapshot;            // 16-byte packed rows: inline-key snapshot table for the settled rounds
-  double snap_fill;        // snapshot entries per key (power of two above it)
+  int l2_window = 0;                  // L2 access-policy window on the table (measured slower)
+  int packed_rows = 1;                // packed-row kernels for multi-key / string rows (0: by-reference kernel)
+  int smem_table = 1;                 // shared-memory tables for settled low-cardinality rounds
+  int prefetch = 1;                   // gb_round_direct: next tile's keys in flight during the probes
+  double discovery_frac = 0.002;      // a round whose predecessor found more new keys than this share of its rows is a discovery round
+  int ctas_per_sm = 4;                // gb_round_direct grid = 148 x this
+  int64_t round0 = 1 << 20;           // rows of the first round
+  double load_target = 0.25;          // table sized so projected uniques / capacity <= this
+  double load_abort = 0.75;           // a round aborts when uniques / capacity would exceed this
+  int ratio = 4;                      // growth of the row ranges from round to round
+  double big_table_bytes = 8.0 * 1024 * 1024 * 1024;  // above this table size every round uses the slot-wise kernel
+  int64_t finish_rows = 256ll << 20;  // a settled table finishes a remainder of at most this many rows in one round
+  int snapshot = 1;                   // 16- / 32-byte packed rows: inline-key snapshot table for the settled rounds
+  double snap_fill = 2.0;             // snapshot entries per key (power of two above it)
 };
 
 static GbPlan get_plan() {
-  GbPlan p{0, 1, 1, 1, 0.002, 4, 1 << 20, 0.25, 0.75, 4, 8.0 * 1024 * 1024 * 1024, 256ll << 20, 1, 2.0};
+  GbPlan p;
   if (const char* e = getenv("RTB_GB_SNAPSHOT")) p.snapshot = atoi(e);
   if (const char* e = getenv("RTB_GB_SNAPFILL")) p.snap_fill = atof(e);
   if (const char* e = getenv("RTB_GB_FINISH")) p.finish_rows = atoll(e);

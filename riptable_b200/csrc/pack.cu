@@ -801,7 +801,7 @@ extern "C" int rtb_rolling_out_dtype(int func, int vdt) {
     case RTB_GB_ROLLING_SHIFT: return (vdt >= RTB_BOOL && vdt <= RTB_UCS4) ? vdt : RTB_ERR_UNSUPPORTED;
     case RTB_GB_ROLLING_DIFF: return (vdt > RTB_BOOL && vdt <= RTB_F64) ? vdt : RTB_ERR_UNSUPPORTED;
     case RTB_GB_ROLLING_SUM: case RTB_GB_ROLLING_NANSUM: return rtb_cumop_out_dtype(RTB_GB_CUMSUM, vdt);
-    case RTB_GB_ROLLING_MEAN: case RTB_GB_ROLLING_NANMEAN: return (vdt >= RTB_BOOL && vdt <= RTB_F64) ? RTB_F64 : RTB_ERR_UNSUPPORTED;
+    case RTB_GB_ROLLING_MEAN: case RTB_GB_ROLLING_NANMEAN: return (vdt >= RTB_BOOL && vdt <= RTB_F64) ? (int)RTB_F64 : (int)RTB_ERR_UNSUPPORTED;
     default: return RTB_ERR_UNSUPPORTED;
   }
 }

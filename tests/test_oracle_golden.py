@@ -133,6 +133,82 @@ def test_reductions_kat_test_groupby():
     assert orc.BinCount(ikey, 3)[1:].tolist() == [2, 3]
 
 
+@pytest.mark.parametrize("N,N_cat", [(1, 1), (5, 3), (100, 10), (3467, 1000), (60_000, 10)])
+@pytest.mark.parametrize("nan_fraction", [0.0, 0.3, 0.9999999, 1.0])
+def test_min_max_replays_reference_test(N, N_cat, nan_fraction):
+    # tests/test_groupbyops.py:389-456: min / max propagate NaN (and, for integers, the sentinel), nanmin / nanmax skip them;
+    # compared per category with np.min / np.max / np.nanmin / np.nanmax on a float copy with NaN at the sentinels
+    import warnings
+    rng = np.random.default_rng((N * N_cat * int(nan_fraction * 1000)) % 10_000)
+    cat = rng.integers(0, N_cat, size=N)
+    g = orc.groupbyhash(cat)
+    ik, U = g["iKey"], g["unique_count"]
+    data = rng.normal(rng.uniform(-10_000, 10_000), rng.uniform(0.0, 10_000), size=N)
+    data[rng.random(N) < nan_fraction] = np.nan
+    idata = rng.integers(-10_000, 10_000, size=N)
+    inan = rng.random(N) < nan_fraction
+    idata[inan] = np.iinfo(idata.dtype).min
+    iref = idata.astype(np.float64)
+    iref[inan] = np.nan
+    for col, ref in ((data, data), (idata, iref)):
+        res = {fn: orc.GroupByAll32([col], ik, U, [fn], [1], [U + 1], 0)[0] for fn in (orc.GB_MIN, orc.GB_MAX, orc.GB_NANMIN, orc.GB_NANMAX)}
+        for fn in res:
+            assert res[fn].dtype == col.dtype
+        for b in range(1, U + 1):
+            sl = ref[ik == b]
+            with np.errstate(all="ignore"), warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                exp = {orc.GB_MIN: np.min(sl), orc.GB_MAX: np.max(sl), orc.GB_NANMIN: np.nanmin(sl), orc.GB_NANMAX: np.nanmax(sl)}
+            for fn, e in exp.items():
+                got = float(res[fn][b])
+                if col.dtype.kind == "i" and res[fn][b] == np.iinfo(col.dtype).min:
+                    got = np.nan  # the integer sentinel reads as NaN (FastArray.astype(float))
+                assert (np.isnan(e) and np.isnan(got)) or got == e, (fn, b, got, e)
+
+
+def test_mean_int64_equals_mean_float64_and_empty_bins():
+    # tests/test_groupby.py:393-406: mean of arange(300000) as int64 equals the mean of the same values as float64
+    k = (np.arange(300_000) % 3 + 1).astype(np.int8)
+    mi = orc.GroupByAll32([np.arange(300_000)], k, 3, [orc.GB_MEAN], [1], [4], 0)[0]
+    mf = orc.GroupByAll32([np.arange(300_000.0)], k, 3, [orc.GB_MEAN], [1], [4], 0)[0]
+    assert mi.dtype == np.float64 and (mi[1:] == mf[1:]).all()
+    assert orc.GroupByAll32([(np.arange(300_000) % 3)], k, 3, [orc.GB_MEAN], [1], [4], 0)[0][2] == 1.0
+    # tests/test_categorical_groupby.py:776-808: an empty category gives 0 for sum / nansum and NaN for everything else
+    kk = np.array([1, 2, 4, 5, 1, 2], np.int8)  # bin 3 never occurs
+    v = np.arange(6.0)
+    for fn, exp in ((orc.GB_SUM, 0.0), (orc.GB_NANSUM, 0.0), (orc.GB_MEAN, np.nan), (orc.GB_MIN, np.nan), (orc.GB_MAX, np.nan),
+                    (orc.GB_VAR, np.nan), (orc.GB_STD, np.nan), (orc.GB_NANMEAN, np.nan), (orc.GB_NANMIN, np.nan),
+                    (orc.GB_NANMAX, np.nan), (orc.GB_NANVAR, np.nan), (orc.GB_NANSTD, np.nan)):
+        r = orc.GroupByAll32([v], kk, 5, [fn], [1], [6], 0)[0][3]
+        assert (np.isnan(exp) and np.isnan(r)) or r == exp, fn
+
+
+def test_unique_semantics_of_the_grouping():
+    # tests/test_unique.py:14-48: grouping + iFirstKey reproduce np.unique (items, first index, inverse, counts) for every
+    # numeric dtype, viewing the same random bytes (so denormals, negative zeros and NaN bit patterns are all there for
+    # floats -- keys compare bytewise: distinct bit patterns are distinct keys)
+    rng = np.random.default_rng(9)
+    raw = rng.integers(0, 256, 8 * 4000, dtype=np.uint8)
+    raw[: 8 * 2000] = raw[8 * 2000:]  # every value appears at least twice
+    for dt in "bBhHiIlL":
+        nums = raw.view(np.dtype(dt))
+        ik, ifk, U = orc.MultiKeyGroupBy32([nums], 0, None, 2)
+        np_un, np_idx, np_inv, np_cnt = np.unique(nums, return_index=True, return_inverse=True, return_counts=True)
+        order = np.argsort(nums[ifk], kind="stable")  # hash bins are in first-appearance order; np.unique sorts
+        assert U == len(np_un)
+        np.testing.assert_array_equal(nums[ifk][order], np_un)
+        np.testing.assert_array_equal(ifk[order], np_idx)
+        rank = np.empty(U, np.int64)
+        rank[order] = np.arange(U)
+        np.testing.assert_array_equal(rank[ik - 1], np_inv)
+        np.testing.assert_array_equal(orc.BinCount(ik, U + 1)[1:][order], np_cnt)
+    for dt in "fd":
+        bits = raw.view(np.dtype(dt).str.replace("f", "u"))
+        ik, _, U = orc.MultiKeyGroupBy32([raw.view(np.dtype(dt))], 0, None, 2)
+        ikb, _, Ub = orc.MultiKeyGroupBy32([bits], 0, None, 2)
+        assert U == Ub and np.array_equal(ik, ikb)
+
+
 def test_first_last_kat():
     # tests/test_groupby.py:137-159: first [4,3], last [1,2] for key bool sorted (False, True)
     num = np.array([3, 4, 5, 1, 2])

@@ -226,6 +226,31 @@ def test_first_last_kat():
     assert nthn[1] == np.iinfo(num.dtype).min and nthn[2] == 3
 
 
+def test_nth_offsets_and_filter_kat():
+    # tests/test_categorical_groupby.py:1107-1162: nth(n) for n in -3..2 on groups of 1 and 2 rows, numbers and strings;
+    # out of range -> NaN / empty string; nth with an operation filter (filtered rows fall into bin 0 and are found there
+    # with showfilter)
+    ik = np.array([1, 2, 2], np.int8)
+    num = np.array([123.0, 456.0, 789.0])
+    st = np.array([b"Aa", b"Bb", b"Cc"])
+    cnt, ig, ifg = orc.BinCount(ik, 3, pack=True)
+    offs = [0, 1]
+    for n in range(-3, 3):
+        rn, rs = orc.GroupByAllPack32([num, st], ik, ig, ifg, cnt, 2, [orc.GB_NTH] * 2, [1, 1], [3, 3], n)
+        for grp in range(2):
+            gcount = grp + 1
+            gi = n if n >= 0 else gcount + n
+            if 0 <= gi < gcount:
+                assert rn[grp + 1] == num[offs[grp] + gi] and rs[grp + 1] == st[offs[grp] + gi]
+            else:
+                assert np.isnan(rn[grp + 1]) and len(rs[grp + 1]) == 0
+    f = np.array([True, False, True])
+    ikf = orc.CombineFilter(ik, f)
+    cnt, ig, ifg = orc.BinCount(ikf, 3, pack=True)
+    rn, rs = orc.GroupByAllPack32([num, st], ikf, ig, ifg, cnt, 2, [orc.GB_NTH] * 2, [0, 0], [3, 3], 0)
+    assert rn.tolist() == [456.0, 123.0, 789.0] and rs.tolist() == [b"Bb", b"Aa", b"Cc"]  # slot 0 = the filtered rows
+
+
 def test_cumsum_kat():
     # tests/test_groupby.py:504-602
     order_ids = np.array([1, 1, 2, 1, 2, 2, 1, 2, 2, 2, 2, 1])

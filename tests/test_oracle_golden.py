@@ -573,6 +573,33 @@ def test_lexsort_matches_numpy_and_hash_equals_lex():
     assert np.array_equal(vn[perm][orc.ReverseShuffle(perm)], vn)
 
 
+def test_lex_all_unique_filter_and_reverse_shuffle():
+    # tests/test_lexsort.py:258-283 (all unique: iFirstKey == iGroup == np.lexsort, for int / float / S / U keys),
+    # :311-324 (lex grouping under a filter describes the same groups as hash grouping), :325-332 (ReverseShuffle)
+    import rt_glue
+    rng = np.random.default_rng(4)
+    arr = rng.choice(100_000, 50_000, replace=False)
+    for dt in (np.int32, np.uint32, np.int64, np.uint64, np.float32, np.float64, "S", "U"):
+        a = arr.astype(dt)
+        sortidx = np.lexsort([a])
+        gbh = rt_glue.groupbyhash(orc, arr, pack=True)
+        gbl = rt_glue.groupbylex(orc, a)
+        assert np.array_equal(gbl["iFirstKey"], sortidx) and np.array_equal(gbl["iGroup"], sortidx)
+        assert gbl["unique_count"] == gbh["unique_count"]
+    keys = rng.choice(np.array(["a", "b", "c"]), 20)
+    f = np.arange(20) % 2 == 1
+    gl, gh = rt_glue.groupbylex(orc, keys, filter=f), rt_glue.groupbyhash(orc, keys, filter=f)
+    assert gl["unique_count"] == gh["unique_count"]
+    ul, uh = keys[gl["iFirstKey"]], keys[gh["iFirstKey"]]
+    exp_l = np.where(gl["iKey"] > 0, np.r_[["Filtered"], ul][gl["iKey"]], "Filtered")
+    exp_h = np.where(gh["iKey"] > 0, np.r_[["Filtered"], uh][gh["iKey"]], "Filtered")
+    assert np.array_equal(exp_l, exp_h)  # the expanded arrays agree although the numbering differs
+    values = rng.integers(1, 7, 300_000)
+    sorted_idx = orc.LexSort32([values])
+    rev = orc.ReverseShuffle(sorted_idx)
+    assert np.array_equal(values[sorted_idx][rev], values)
+
+
 def test_projections_455654_groups():
     # tests/test_groupby.py:419-459: 1M rows, 4 keys (int, str, str, int), seed 1234 -> exactly 455 654 groups
     n, num_symbols = 1_000_000, 450

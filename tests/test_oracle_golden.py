@@ -320,6 +320,26 @@ def test_cum_min_max_replays_reference_test(N, N_cat, nan_fraction, skipna):
             np.testing.assert_array_equal(_as_float_with_nan(hi[ik == b]), ehi)
 
 
+def test_cum_ops_against_pandas():
+    # tests/test_categorical_functions.py / test_groupby_functions.py compare the cumulative functions with pandas' groupby
+    pd = pytest.importorskip("pandas")
+    rng = np.random.default_rng(12)
+    n = 5000
+    key = rng.integers(0, 17, n)
+    g = orc.groupbyhash(key)
+    ik, U = g["iKey"], g["unique_count"]
+    v = rng.normal(0, 3, n)
+    vp = np.exp(rng.normal(0, 0.05, n))
+    df = pd.DataFrame({"k": key, "v": v, "vp": vp})
+    none = (0.0, None, None, None)
+    np.testing.assert_allclose(orc.EmaAll32([v], ik, U, orc.GB_CUMSUM, none)[0], df.groupby("k")["v"].cumsum().to_numpy(), rtol=1e-12, atol=1e-10)
+    np.testing.assert_allclose(orc.EmaAll32([vp], ik, U, orc.GB_CUMPROD, none)[0], df.groupby("k")["vp"].cumprod().to_numpy(), rtol=1e-12)
+    np.testing.assert_array_equal(orc.EmaAll32([v], ik, U, orc.GB_CUMNANMIN, none)[0], df.groupby("k")["v"].cummin().to_numpy())
+    np.testing.assert_array_equal(orc.EmaAll32([v], ik, U, orc.GB_CUMNANMAX, none)[0], df.groupby("k")["v"].cummax().to_numpy())
+    vi = rng.integers(-9, 9, n)
+    np.testing.assert_array_equal(orc.EmaAll32([vi], ik, U, orc.GB_CUMSUM, none)[0], pd.Series(vi).groupby(key).cumsum().to_numpy())
+
+
 def test_cumprod_small():
     ik = np.array([1, 2, 1, 0, 2, 1], dtype=np.int8)
     v = np.array([2, 3, 4, 9, 5, 6], dtype=np.int32)

@@ -209,6 +209,38 @@ def test_unique_semantics_of_the_grouping():
         assert U == Ub and np.array_equal(ik, ikb)
 
 
+def test_reductions_against_pandas():
+    # tests/test_groupby_autotest_aggregated_functions.py:26-29, 566-584: sum / mean / min / max / var / std (ddof = 1)
+    # / first / last against pandas' groupby, to 7 places there; exact or 1e-12 here
+    pd = pytest.importorskip("pandas")
+    rng = np.random.default_rng(77)
+    n = 20_000
+    key = rng.integers(0, 60, n)
+    v = rng.normal(5, 100, n)
+    vi = rng.integers(-1000, 1000, n)
+    g = orc.groupbyhash(key)
+    ik, U = g["iKey"], g["unique_count"]
+    uniq = key[g["iFirstKey"]]
+    df = pd.DataFrame({"k": key, "v": v, "vi": vi})
+    gb = df.groupby("k")
+
+    def ours(col, fn):
+        return pd.Series(orc.GroupByAll32([col], ik, U, [fn], [1], [U + 1], 0)[0][1:], index=uniq).sort_index().to_numpy()
+
+    for fn, name in ((orc.GB_SUM, "sum"), (orc.GB_MEAN, "mean"), (orc.GB_MIN, "min"), (orc.GB_MAX, "max"), (orc.GB_VAR, "var"),
+                     (orc.GB_STD, "std")):
+        np.testing.assert_allclose(ours(v, fn), getattr(gb["v"], name)().to_numpy(), rtol=1e-11, err_msg=name)
+    for fn, name in ((orc.GB_SUM, "sum"), (orc.GB_MIN, "min"), (orc.GB_MAX, "max")):
+        np.testing.assert_array_equal(ours(vi, fn), getattr(gb["vi"], name)().to_numpy(), err_msg=name)
+    np.testing.assert_allclose(ours(vi, orc.GB_MEAN), gb["vi"].mean().to_numpy(), rtol=1e-13)
+    cnt, ig, ifg = orc.BinCount(ik, U + 1, pack=True)
+    first = orc.GroupByAllPack32([v], ik, ig, ifg, cnt, U, [orc.GB_FIRST], [1], [U + 1], 0)[0][1:]
+    last = orc.GroupByAllPack32([v], ik, ig, ifg, cnt, U, [orc.GB_LAST], [1], [U + 1], 0)[0][1:]
+    np.testing.assert_array_equal(pd.Series(first, index=uniq).sort_index().to_numpy(), gb["v"].first().to_numpy())
+    np.testing.assert_array_equal(pd.Series(last, index=uniq).sort_index().to_numpy(), gb["v"].last().to_numpy())
+    np.testing.assert_array_equal(pd.Series(orc.BinCount(ik, U + 1)[1:], index=uniq).sort_index().to_numpy(), gb.size().to_numpy())
+
+
 def test_first_last_kat():
     # tests/test_groupby.py:137-159: first [4,3], last [1,2] for key bool sorted (False, True)
     num = np.array([3, 4, 5, 1, 2])

@@ -241,6 +241,25 @@ def test_reductions_against_pandas():
     np.testing.assert_array_equal(pd.Series(orc.BinCount(ik, U + 1)[1:], index=uniq).sort_index().to_numpy(), gb.size().to_numpy())
 
 
+def test_accum2_simple_cats_kat():
+    # tests/test_accum2.py:87-127: Accum2 of two 5-category Categoricals over data = 10, 20 .. 50 puts data[i] on the
+    # diagonal; with an operation filter the filtered rows fall into cell 0
+    data = np.arange(1, 6) * 10
+    k1 = np.arange(1, 6, dtype=np.int8)  # Categorical(["a" .. "e"]) codes
+    k2 = np.arange(1, 6, dtype=np.int8)  # Categorical(arange(5)) codes
+    ik, cnt = orc.CombineAccum2Filter(k1, k2, 5, 5, None)
+    nb = 6 * 6
+    assert len(cnt) == nb
+    cells = orc.GroupByAll32([data], ik, nb - 1, [orc.GB_SUM], [0], [nb], 0)[0].reshape(6, 6)
+    for i in range(5):
+        assert cells[i + 1, i + 1] == data[i]
+    assert cells.sum() == data.sum() and cnt.reshape(6, 6)[1:, 1:].trace() == 5
+    f = np.array([True, False, True, True, False])
+    ikf, cntf = orc.CombineAccum2Filter(k1, k2, 5, 5, f)
+    cells = orc.GroupByAll32([data], ikf, nb - 1, [orc.GB_SUM], [0], [nb], 0)[0].reshape(6, 6)
+    assert cells[0, 0] == 20 + 50 and cells[2, 2] == 0 and cells[1, 1] == 10 and cntf[0] == 2
+
+
 def test_first_last_kat():
     # tests/test_groupby.py:137-159: first [4,3], last [1,2] for key bool sorted (False, True)
     num = np.array([3, 4, 5, 1, 2])

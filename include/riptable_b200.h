@@ -112,6 +112,22 @@ int rtb_multikey_groupby32_chunk(const rtb_column* key, int64_t nrows, const uin
                                  int resume, int64_t* needed_unique_host, void* workspace, size_t workspace_bytes,
                                  void* stream);
 
+/* ---- a1 + a5 fused: rc.MultiKeyGroupBy32(keys, hint, filter) followed by rc.GroupByAll32([values], iKey, U, [GB_SUM |
+ * GB_NANSUM], [bin_low], [U + 1]) — the pair of calls `ds.gb(k).sum()` makes (riptable/rt_groupbyops.py:1161-1225 ->
+ * riptable/rt_grouping.py:3395-3436 -> riptable/rt_numpy.py:2073, 1871) — as ONE pass: the steady-state probe kernel adds
+ * each row's value to its bin as it writes iKey, so the reduction's second sweep (iKey re-read + a second kernel) is gone.
+ * Outputs are exactly those of the two calls: ikey_out / ifirstkey_out / *unique_count_host as rtb_multikey_groupby32,
+ * sum_out[0 .. U] as rtb_groupby_reduce (dtype rtb_reduce_out_dtype(func, vdtype); slot 0 = filtered rows, summed only
+ * when bin_low == 0).  sum_out must hold max_unique + 1 items.  Any key layout is accepted; rounds whose kernel has no
+ * fused form (discovery rounds, shared-memory tables, multi-key rows) sum their rows right after they are grouped.
+ * riptable binding: the lazy `GroupBy.grouping` (riptable/rt_groupby.py) lets `GroupByOps.sum` ask for the grouping and
+ * the sums together when the grouping has not been computed yet. */
+size_t rtb_groupby_sum_workspace_bytes(int64_t nrows, int64_t max_unique, int64_t row_bytes);
+int rtb_multikey_groupby_sum32(const rtb_column* keys, int nkeys, int64_t nrows, const uint8_t* filter,
+                               const void* values, int vdtype, int func, int64_t bin_low, int32_t* ikey_out,
+                               int32_t* ifirstkey_out, int64_t max_unique, void* sum_out, int64_t* unique_count_host,
+                               int64_t* needed_unique_host, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- 8f.1: rc.IsMember32(a, b, h, hint) / rc.IsMemberCategorical — riptable/rt_numpy.py:1388-1391, one numeric key
  * column of the same dtype on both sides.  found_out uint8[na]; index_out (index_dtype: an int rtb_dtype chosen by
  * len(b), riptable/rt_enum.py:666-679) = position of the first occurrence of a[i] in b, + base_index; absent rows get

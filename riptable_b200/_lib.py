@@ -47,6 +47,11 @@ PROTOTYPES = {
     ),
     "rtb_multikey_groupby32_chunk": (
         C.c_int, [C.POINTER(rtb_column), _i64, _vp, _vp, _vp, _i64, _i64, _vp, _i32, _pi64, _vp, _sz, _vp]),
+    "rtb_groupby_sum_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "rtb_multikey_groupby_sum32": (
+        C.c_int,
+        [C.POINTER(rtb_column), _i32, _i64, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _i64, _vp, _pi64, _pi64, _vp, _sz, _vp],
+    ),
     "rtb_combine_filter": (C.c_int, [_vp, _i32, _vp, _i64, _vp, _vp]),
     "rtb_combine_accum2": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i64, _i64, _vp, _i32, _vp]),
     "rtb_reduce_out_dtype": (C.c_int, [_i32, _i32]),

@@ -11,8 +11,8 @@ FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC",
-    "--use_fast_math" if False else "-DRTB_BUILD",
-]
+    "-DRTB_BUILD",
+] + os.environ.get("RTB_NVCC_FLAGS", "").split()  # measurement builds only (e.g. -DRTB_FUSE_MINB=4)
 
 
 def sources():

@@ -77,6 +77,9 @@ inline int dtype_size(int dt) {
     default: return 0;
   }
 }
+// Alignment a column's base pointer needs for the kernels' 4-row vector loads: 4 items, but never more than the widest
+// load there is (16 bytes) -- a 16-byte aligned slice of an int64 / float64 tensor is fine.
+inline size_t vec4_align(int itemsize) { return itemsize >= 4 ? 16 : (size_t)(4 * itemsize); }
 inline bool is_ikey_dtype(int dt) { return dt == RTB_I8 || dt == RTB_I16 || dt == RTB_I32 || dt == RTB_I64; }
 
 inline int grid_for(int64_t work_items, int threads, int items_per_thread, int max_blocks_per_sm = 16) {

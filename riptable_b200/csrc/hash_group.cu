@@ -31,6 +31,8 @@
 
 #include "common.cuh"
 #include "keycols.cuh"
+#include "reduce_internal.cuh"
+#include "values.cuh"
 
 namespace rtb {
 
@@ -173,20 +175,35 @@ __device__ __forceinline__ unsigned long long load_key1(const void* keys, int64_
 }
 
 // A warp owns 128-row tiles; every lane holds 4 keys.  Row of lane `l`, key j inside a tile:
-//   8-byte keys : two 128-bit loads, each covering 512 contiguous bytes per warp -> rows 2l, 2l+1, 64+2l, 65+2l
-//   narrower    : one vector load of 4 consecutive rows                          -> rows 4l .. 4l+3
-template <int ISZ>
+//   PAIR  (8-byte keys, or a fused 8-byte value column): vector loads that each cover contiguous memory per warp
+//                                                        -> rows 2l, 2l+1, 64+2l, 65+2l
+//   else  : one vector load of 4 consecutive rows        -> rows 4l .. 4l+3
+template <int ISZ, bool PAIR = (ISZ == 8)>
 __device__ __forceinline__ int tile_row(int lane, int j) {
-  if (ISZ == 8) return (j < 2 ? 2 * lane + j : 64 + 2 * lane + (j - 2));
+  if (PAIR) return (j < 2 ? 2 * lane + j : 64 + 2 * lane + (j - 2));
   return 4 * lane + j;
 }
-template <int ISZ>
+template <int ISZ, bool PAIR = (ISZ == 8)>
 __device__ __forceinline__ void load_tile_keys(const void* keys, int64_t tb, int lane, unsigned long long k[4]) {
   if (ISZ == 8) {
     uint4 a = ld_stream_u4((const uint8_t*)keys + (tb + 2 * lane) * 8);
     uint4 b = ld_stream_u4((const uint8_t*)keys + (tb + 64 + 2 * lane) * 8);
     k[0] = ((unsigned long long)a.y << 32) | a.x; k[1] = ((unsigned long long)a.w << 32) | a.z;
     k[2] = ((unsigned long long)b.y << 32) | b.x; k[3] = ((unsigned long long)b.w << 32) | b.z;
+  } else if (PAIR) {
+    if (ISZ == 4) {
+      uint2 a = ld_stream_u2((const uint8_t*)keys + (tb + 2 * lane) * 4);
+      uint2 b = ld_stream_u2((const uint8_t*)keys + (tb + 64 + 2 * lane) * 4);
+      k[0] = a.x; k[1] = a.y; k[2] = b.x; k[3] = b.y;
+    } else if (ISZ == 2) {
+      uint32_t a = ld_stream_u32((const uint8_t*)keys + (tb + 2 * lane) * 2);
+      uint32_t b = ld_stream_u32((const uint8_t*)keys + (tb + 64 + 2 * lane) * 2);
+      k[0] = a & 0xffff; k[1] = a >> 16; k[2] = b & 0xffff; k[3] = b >> 16;
+    } else {
+      uint32_t a = *(const uint16_t*)((const uint8_t*)keys + tb + 2 * lane);
+      uint32_t b = *(const uint16_t*)((const uint8_t*)keys + tb + 64 + 2 * lane);
+      k[0] = a & 0xff; k[1] = a >> 8; k[2] = b & 0xff; k[3] = b >> 8;
+    }
   } else if (ISZ == 4) {
     uint4 a = ld_stream_u4((const uint8_t*)keys + (tb + 4 * lane) * 4);
     k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w;
@@ -199,13 +216,38 @@ __device__ __forceinline__ void load_tile_keys(const void* keys, int64_t tb, int
   }
 }
 
+// ---- fused per-bin sum (rtb_multikey_groupby_sum32) ---------------------------------------------------------
+// The steady-state round can add every row's value to its bin in the same pass that writes iKey: the probe already
+// has the final bin in a register, so the separate reduction pass (4 B/row of iKey re-read + the value stream + a
+// second kernel's worth of L2 round trips) disappears.  Rows that land on a provisional slot are added by gb_fixup.
+struct GbFuse {
+  const void* values;        // one value per row
+  unsigned long long* acc;   // per-bin accumulators (f64 bits, or 64-bit wrap-around integers), zeroed as bins are created
+  int vdt;                   // rtb_dtype of the values
+  int vsz;                   // bytes per value
+  int nanskip;               // GB_NANSUM: NaN / integer sentinels are skipped
+  int isfloat;               // accumulate in f64 (float columns), else in int64
+  int bin_low;               // 1: filtered rows are skipped; 0: they are summed into bin 0 (riptable's showfilter)
+};
+__device__ __forceinline__ void fuse_add(const GbFuse& f, int32_t bin, unsigned long long raw) {
+  if (f.nanskip && raw_invalid(raw, f.vdt)) return;
+  if (f.isfloat) atomicAdd((double*)&f.acc[bin], raw_to_f64(raw, f.vdt));
+  else atomicAdd(&f.acc[bin], (unsigned long long)raw_to_i64(raw, f.vdt));
+}
+
 // One round of the direct path over rows [lo, hi).  lo is a multiple of 128; the key / filter / ikey base
 // pointers are 16-byte aligned (checked on the host).
-template <int ISZ, bool PREFETCH>
-__global__ void __launch_bounds__(256) gb_round_direct(const void* __restrict__ keys, const uint8_t* __restrict__ filter,
+// FUSE: 0 = grouping only; 1 / 2 = also sum an 8-byte / 4-byte value column into `fz.acc` (see GbFuse).
+#ifndef RTB_FUSE_MINB
+#define RTB_FUSE_MINB 1
+#endif
+template <int ISZ, bool PREFETCH, int FUSE>
+__global__ void __launch_bounds__(256, FUSE ? RTB_FUSE_MINB : 1) gb_round_direct(const void* __restrict__ keys, const uint8_t* __restrict__ filter,
                                                        int32_t* __restrict__ ikey, Slot* table, uint32_t mask,
                                                        int64_t lo, int64_t hi, uint32_t* newlist, GbCounters* ctr,
-                                                       uint32_t new_limit) {
+                                                       uint32_t new_limit, GbFuse fz) {
+  constexpr bool PAIR = ISZ == 8 || FUSE == 1;
+  constexpr int VSZ = FUSE == 1 ? 8 : 4;
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -213,16 +255,16 @@ __global__ void __launch_bounds__(256) gb_round_direct(const void* __restrict__ 
   const int64_t step = nwarps * 128;
   int64_t tb = lo + gw * 128;
   unsigned long long k[4], kn[4] = {0, 0, 0, 0};
-  if (PREFETCH && tb + 128 <= hi) load_tile_keys<ISZ>(keys, tb, lane, k);
+  if (PREFETCH && tb + 128 <= hi) load_tile_keys<ISZ, PAIR>(keys, tb, lane, k);
   for (; tb + 128 <= hi; tb += step) {
     if (PREFETCH) {
-      if (tb + step + 128 <= hi) load_tile_keys<ISZ>(keys, tb + step, lane, kn);  // in flight during the probes
+      if (tb + step + 128 <= hi) load_tile_keys<ISZ, PAIR>(keys, tb + step, lane, kn);  // in flight during the probes
     } else {
-      load_tile_keys<ISZ>(keys, tb, lane, k);
+      load_tile_keys<ISZ, PAIR>(keys, tb, lane, k);
     }
     uint32_t fbits = 0xF;
     if (filter) {
-      if (ISZ == 8) {
+      if (PAIR) {
         uint32_t fa = *(const uint16_t*)(filter + tb + 2 * lane), fb = *(const uint16_t*)(filter + tb + 64 + 2 * lane);
         fbits = ((fa & 0xff) ? 1u : 0u) | ((fa >> 8) ? 2u : 0u) | ((fb & 0xff) ? 4u : 0u) | ((fb >> 8) ? 8u : 0u);
       } else {
@@ -236,6 +278,15 @@ __global__ void __launch_bounds__(256) gb_round_direct(const void* __restrict__ 
     for (int i = 0; i < 4; i++) b[i] = hash_u64(k[i]) & bmask;
 #pragma unroll
     for (int i = 0; i < 4; i++) p[i] = load_bucket(table, b[i]);
+    unsigned long long v[4] = {0, 0, 0, 0};
+    if (FUSE) {  // the value stream rides behind the probes
+      if (PAIR) {
+        load_raw2(fz.values, VSZ, tb + 2 * lane, v);
+        load_raw2(fz.values, VSZ, tb + 64 + 2 * lane, v + 2);
+      } else {
+        load_raw4(fz.values, VSZ, tb + 4 * lane, v);
+      }
+    }
     int32_t o[4];
     uint32_t pend = 0;
     // branch-free common case: the key sits in its home bucket with a final bin.  (The empty-marker key can
@@ -293,13 +344,19 @@ __global__ void __launch_bounds__(256) gb_round_direct(const void* __restrict__ 
 #pragma unroll
       for (int i = 0; i < 4; i++)
         if ((slow >> i) & 1u)
-          o[i] = resolve_direct(table, mask, k[i], 2 * b[i], (uint32_t)(tb + tile_row<ISZ>(lane, i)), newlist, ctr, new_limit);
+          o[i] = resolve_direct(table, mask, k[i], 2 * b[i], (uint32_t)(tb + tile_row<ISZ, PAIR>(lane, i)), newlist, ctr, new_limit);
     }
-    if (ISZ == 8) {
+    if (PAIR) {
       *(int2*)(ikey + tb + 2 * lane) = make_int2(o[0], o[1]);
       *(int2*)(ikey + tb + 64 + 2 * lane) = make_int2(o[2], o[3]);
     } else {
       st_stream_u4(ikey + tb + 4 * lane, make_uint4((uint32_t)o[0], (uint32_t)o[1], (uint32_t)o[2], (uint32_t)o[3]));
+    }
+    if (FUSE) {
+      // final bins are summed here; provisional rows (o < 0) are summed by gb_fixup once their bin is known
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        if (o[i] >= fz.bin_low) fuse_add(fz, o[i], v[i]);
     }
     if (PREFETCH) {
 #pragma unroll
@@ -315,6 +372,7 @@ __global__ void __launch_bounds__(256) gb_round_direct(const void* __restrict__ 
         o = resolve_direct(table, mask, kk, 2 * (hash_u64(kk) & bmask), (uint32_t)q, newlist, ctr, new_limit);
       }
       ikey[q] = o;
+      if (FUSE && o >= fz.bin_low) fuse_add(fz, o, load_raw1(fz.values, VSZ, q));
     }
   }
 }
@@ -1035,8 +1093,10 @@ __global__ void __launch_bounds__(256) gb_assign_bins(Slot* table, const uint32_
   }
 }
 
+// `fz.values` != nullptr (fused sum): the provisional rows of a fused round were not summed by the round kernel
+// (their bin was unknown); they are summed here, as their bin is looked up.
 __global__ void __launch_bounds__(256) gb_fixup(int32_t* __restrict__ ikey, const Slot* __restrict__ table, int64_t lo,
-                                                int64_t hi, int32_t bin_sub) {
+                                                int64_t hi, int32_t bin_sub, GbFuse fz) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
   for (int64_t r = lo + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; r < hi; r += stride) {
     if (r + 3 < hi) {
@@ -1047,6 +1107,7 @@ __global__ void __launch_bounds__(256) gb_fixup(int32_t* __restrict__ ikey, cons
       for (int i = 0; i < 4; i++) {
         if (o[i] < 0) {
           o[i] = (int32_t)table[-(o[i] + 1)].bin() - bin_sub;
+          if (fz.values) fuse_add(fz, o[i], load_raw1(fz.values, fz.vsz, r + i));
           any = true;
         } else if (bin_sub && o[i] > 0) {
           o[i] -= bin_sub;
@@ -1057,8 +1118,13 @@ __global__ void __launch_bounds__(256) gb_fixup(int32_t* __restrict__ ikey, cons
     } else {
       for (int64_t q = r; q < hi; q++) {
         int32_t v = ikey[q];
-        if (v < 0) ikey[q] = (int32_t)table[-(v + 1)].bin() - bin_sub;
-        else if (bin_sub && v > 0) ikey[q] = v - bin_sub;
+        if (v < 0) {
+          v = (int32_t)table[-(v + 1)].bin() - bin_sub;
+          ikey[q] = v;
+          if (fz.values) fuse_add(fz, v, load_raw1(fz.values, fz.vsz, q));
+        } else if (bin_sub && v > 0) {
+          ikey[q] = v - bin_sub;
+        }
       }
     }
   }
@@ -1408,14 +1474,15 @@ static size_t packed_smem_bytes(int64_t U, int W) { return (size_t)U * W + (size
 static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8_t* filter, const int64_t* cutoffs_host,
                    int64_t ncutoffs, int32_t* ikey_out, int32_t* ifirstkey_out, int64_t max_unique,
                    int64_t* unique_count_host, int64_t* ucutoffs_host, int64_t* needed_unique_host, void* workspace,
-                   size_t workspace_bytes, cudaStream_t stream, rtb_gb_state* st, int64_t row_offset) {
+                   size_t workspace_bytes, cudaStream_t stream, rtb_gb_state* st, int64_t row_offset,
+                   const GbFuse* fuse = nullptr) {
   const bool has_cut = cutoffs_host != nullptr && ncutoffs > 0;
   GbPlan plan = get_plan();
   static const bool trace = getenv("RTB_GB_TRACE") != nullptr;
   // key layout: direct (one numeric column), packed rows (anything else up to 64 bytes per row), generic by-reference
   bool direct = !has_cut && nkeys == 1 && (keys[0].itemsize == 1 || keys[0].itemsize == 2 || keys[0].itemsize == 4 ||
                                            keys[0].itemsize == 8) &&
-                ((uintptr_t)keys[0].data % (4 * keys[0].itemsize)) == 0 && (!filter || ((uintptr_t)filter % 4) == 0);
+                ((uintptr_t)keys[0].data % vec4_align(keys[0].itemsize)) == 0 && (!filter || ((uintptr_t)filter % 4) == 0);
   int64_t row_bytes = has_cut ? 4 : 0;
   for (int c = 0; c < nkeys; c++) row_bytes += keys[c].itemsize;
   int W = (int)((row_bytes + 15) / 16 * 16);
@@ -1505,6 +1572,12 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
     return RTB_OK;
   };
 
+  GbFuse fz_none;
+  memset(&fz_none, 0, sizeof(fz_none));
+  // fused sum: accumulators are zeroed as bins come into existence (bin 0 now, new bins after every round), so the
+  // cost follows the bins actually found, not max_unique
+  if (fuse) RTB_CUDA(cudaMemsetAsync(fuse->acc, 0, sizeof(unsigned long long), stream));
+  const bool fuse_kernel_ok = fuse && (fuse->vsz == 8 || fuse->vsz == 4) && ((uintptr_t)fuse->values % 16) == 0;
   uint32_t snap_cap = 0;   // inline-key snapshot (16-byte packed rows): entries in use, bins it holds
   int64_t snap_built = 0;
   uint32_t cap = st->cap;
@@ -1537,7 +1610,10 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
     }
 
     bool packed_this_round = false;
+    bool fused_round = false;   // this round's kernel summed the rows whose bin was final at probe time
+    bool redo_sums = false;     // a fused round aborted half-way: its partial sums are discarded below
     for (int attempt = 0;; attempt++) {  // attempt loop: (re)size, run the round, grow on abort
+      fused_round = false;
       if (want != cap) {
         uint32_t staged_n = 0;
         if (cap != 0 && U > 0) {
@@ -1613,15 +1689,34 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
           }
 #undef RTB_SMEM_ROUND
         } else {
-        int grid = grid_for(rows, 256, 4, plan.ctas_per_sm);
-#define RTB_ROUND(ISZ_, PF_) gb_round_direct<ISZ_, PF_><<<grid, 256, 0, stream>>>(dkey.data, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit)
+        fused_round = fuse_kernel_ok;
+        const GbFuse fz = fused_round ? *fuse : fz_none;
+        const int fk = !fused_round ? 0 : (fuse->vsz == 8 ? 1 : 2);
+#define RTB_ROUND(ISZ_, PF_, FK_)                                                                                          \
+  do {                                                                                                                    \
+    static int occ = 0;                                                                                                   \
+    if (!occ) {                                                                                                           \
+      RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gb_round_direct<ISZ_, PF_, FK_>, 256, 0));             \
+      if (occ < 1) occ = 1;                                                                                               \
+    }                                                                                                                     \
+    const int grid = grid_for(rows, 256, 4, occ < plan.ctas_per_sm ? occ : plan.ctas_per_sm);                             \
+    gb_round_direct<ISZ_, PF_, FK_><<<grid, 256, 0, stream>>>(dkey.data, filter, ikey_out, L.table, mask, lo, hi, newlist, \
+                                                              L.ctr, new_limit, fz);                                      \
+  } while (0)
+#define RTB_ROUND_F(ISZ_, PF_)                                                                                            \
+  do {                                                                                                                    \
+    if (fk == 1) RTB_ROUND(ISZ_, PF_, 1);                                                                                 \
+    else if (fk == 2) RTB_ROUND(ISZ_, PF_, 2);                                                                            \
+    else RTB_ROUND(ISZ_, PF_, 0);                                                                                         \
+  } while (0)
         switch (dkey.itemsize) {
-          case 8: if (plan.prefetch) RTB_ROUND(8, true); else RTB_ROUND(8, false); break;
-          case 4: if (plan.prefetch) RTB_ROUND(4, true); else RTB_ROUND(4, false); break;
-          case 2: RTB_ROUND(2, false); break;
-          default: RTB_ROUND(1, false);
-#undef RTB_ROUND
+          case 8: if (plan.prefetch) RTB_ROUND_F(8, true); else RTB_ROUND_F(8, false); break;
+          case 4: if (plan.prefetch) RTB_ROUND_F(4, true); else RTB_ROUND_F(4, false); break;
+          case 2: RTB_ROUND_F(2, false); break;
+          default: RTB_ROUND_F(1, false);
         }
+#undef RTB_ROUND_F
+#undef RTB_ROUND
         }
       } else if (W && !has_cut && round > 0 && (double)prev_new <= plan.discovery_frac * (double)prev_rows && attempt == 0 &&
                  plan.smem_table && U > 0 && U < 65535 &&
@@ -1721,6 +1816,7 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
         prev_new = h.newcount;
         break;
       }
+      if (fused_round) redo_sums = true;
       // out of room: grow 4x (provisional entries are dropped by the re-stage) or ask for more workspace
       if (cap >= capmax) {
         double seen = (double)(lo > 0 ? lo : 1);
@@ -1737,6 +1833,17 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
       want = g > capmax ? capmax : (uint32_t)g;
     }
 
+    if (fuse && redo_sums) {
+      // the aborted attempt of this round had already added some of its rows: start the sums over from the rows
+      // grouped so far (their iKey is final); the repeat of the round ran unfused and is added below
+      RTB_CUDA(cudaMemsetAsync(fuse->acc, 0, sizeof(unsigned long long) * (size_t)(U + 1), stream));
+      if (lo > 0) {
+        int rc = accum_sum_rows(fuse->values, fuse->vdt, ikey_out, RTB_I32, lo, U + 1, fuse->bin_low, fuse->nanskip, fuse->acc, stream);
+        if (rc != RTB_OK) return rc;
+      }
+    }
+    if (fuse && prev_new > 0)
+      RTB_CUDA(cudaMemsetAsync(fuse->acc + U + 1, 0, sizeof(unsigned long long) * (size_t)prev_new, stream));
     if (prev_new > 0) {
       int64_t words = (rows + 31) / 32;
       RTB_CUDA(cudaMemsetAsync(L.bitmap, 0, sizeof(uint32_t) * words, stream));
@@ -1747,9 +1854,17 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
       gb_assign_bins<<<grid_for(prev_new, 256, 1), 256, 0, stream>>>(L.table, newlist, L.ctr, lo, L.bitmap, L.prefix,
                                                                     (uint32_t)U, ifirstkey_out, -row_offset);
       RTB_LAUNCH_CHECK();
-      gb_fixup<<<grid_for(rows, 256, 4), 256, 0, stream>>>(ikey_out, L.table, lo, hi, 0);
+      gb_fixup<<<grid_for(rows, 256, 4), 256, 0, stream>>>(ikey_out, L.table, lo, hi, 0, fused_round ? *fuse : fz_none);
       RTB_LAUNCH_CHECK();
       U += prev_new;
+    }
+    if (fuse && !fused_round) {
+      // rounds whose kernel has no fused form (discovery, shared-memory tables, multi-key rows): the round's rows are
+      // summed from the iKey it just wrote, while that is still in L2 for all but the largest rounds
+      const int vsz = fuse->vsz;
+      int rc = accum_sum_rows((const uint8_t*)fuse->values + lo * vsz, fuse->vdt, ikey_out + lo, RTB_I32, rows, U + 1,
+                              fuse->bin_low, fuse->nanskip, fuse->acc, stream);
+      if (rc != RTB_OK) return rc;
     }
     prev_rows = rows;
     lo = hi;
@@ -1851,6 +1966,75 @@ extern "C" int rtb_multikey_groupby32_chunk(const rtb_column* key, int64_t nrows
                  workspace, workspace_bytes, (cudaStream_t)stream_, state, row_offset);
 }
 
+// ---- fused grouping + per-bin sum ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gb_cast_sums_f32(const unsigned long long* __restrict__ acc, float* __restrict__ out, int64_t nb) {
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (int64_t)gridDim.x * blockDim.x)
+    out[b] = (float)__longlong_as_double((long long)acc[b]);
+}
+
+extern "C" size_t rtb_groupby_sum_workspace_bytes(int64_t nrows, int64_t max_unique, int64_t row_bytes) {
+  if (nrows < 0 || max_unique < 0 || row_bytes < 0) return 0;
+  return align_up(rtb_groupby_workspace_bytes_rows(nrows, max_unique, row_bytes, 0), 256) + sizeof(unsigned long long) * ((size_t)max_unique + 1) + 256;
+}
+
+extern "C" int rtb_multikey_groupby_sum32(const rtb_column* keys, int nkeys, int64_t nrows, const uint8_t* filter,
+                                          const void* values, int vdtype, int func, int64_t bin_low, int32_t* ikey_out,
+                                          int32_t* ifirstkey_out, int64_t max_unique, void* sum_out,
+                                          int64_t* unique_count_host, int64_t* needed_unique_host, void* workspace,
+                                          size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RTB_ARG(keys && nkeys >= 1, "MultiKeyGroupBySum32: first argument is not a list of arrays");
+  RTB_ARG(nkeys <= kMaxKeyCols - 1, "MultiKeyGroupBySum32: at most %d key columns", kMaxKeyCols - 1);
+  RTB_ARG(nrows >= 0 && nrows <= 2147483646ll, "MultiKeyGroupBySum32: row count out of range for int32 iKey");
+  RTB_ARG(unique_count_host, "MultiKeyGroupBySum32: null unique_count");
+  RTB_ARG(func == RTB_GB_SUM || func == RTB_GB_NANSUM, "MultiKeyGroupBySum32: GB_SUM or GB_NANSUM");
+  RTB_ARG(bin_low == 0 || bin_low == 1, "MultiKeyGroupBySum32: bin_low must be 0 or 1");
+  const int odt = rtb_reduce_out_dtype(func, vdtype);
+  if (odt < 0) {
+    set_error("MultiKeyGroupBySum32: dtype %d cannot be summed", vdtype);
+    return RTB_ERR_UNSUPPORTED;
+  }
+  *unique_count_host = 0;
+  if (needed_unique_host) *needed_unique_host = 0;
+  RTB_ARG(sum_out, "MultiKeyGroupBySum32: null output");
+  if (nrows == 0) {
+    RTB_CUDA(cudaMemsetAsync(sum_out, 0, dtype_size(odt), stream));
+    return RTB_OK;
+  }
+  RTB_ARG(ikey_out && ifirstkey_out && max_unique >= 1 && values, "MultiKeyGroupBySum32: null pointer");
+  RTB_ARG(((uintptr_t)ikey_out % 16) == 0 && ((uintptr_t)values % 16) == 0 && ((uintptr_t)sum_out % 8) == 0,
+          "MultiKeyGroupBySum32: iKey and value buffers must be 16-byte aligned");
+  for (int c = 0; c < nkeys; c++) RTB_ARG(keys[c].data && keys[c].itemsize >= 1, "MultiKeyGroupBySum32: bad key column %d", c);
+  if (max_unique > nrows) max_unique = nrows;
+  int64_t row_bytes = 0;
+  for (int c = 0; c < nkeys; c++) row_bytes += keys[c].itemsize;
+  const bool single = nkeys == 1 && (keys[0].itemsize == 1 || keys[0].itemsize == 2 || keys[0].itemsize == 4 || keys[0].itemsize == 8);
+  const size_t gb_bytes = align_up(rtb_groupby_workspace_bytes_rows(nrows, max_unique, single ? 0 : row_bytes, 0), 256);
+  RTB_ARG(workspace && ((uintptr_t)workspace % 256) == 0 && gb_bytes + sizeof(unsigned long long) * ((size_t)max_unique + 1) <= workspace_bytes,
+          "MultiKeyGroupBySum32: workspace too small or not 256-byte aligned");
+  GbFuse fz;
+  memset(&fz, 0, sizeof(fz));
+  fz.values = values;
+  fz.vdt = vdtype;
+  fz.vsz = dtype_size(vdtype);
+  fz.nanskip = func == RTB_GB_NANSUM;
+  fz.isfloat = vdtype == RTB_F32 || vdtype == RTB_F64;
+  fz.bin_low = (int)bin_low;
+  // 64-bit outputs accumulate in place; float32 sums accumulate in f64 and are rounded once at the end
+  fz.acc = vdtype == RTB_F32 ? (unsigned long long*)((uint8_t*)workspace + gb_bytes) : (unsigned long long*)sum_out;
+  rtb_gb_state st;
+  memset(&st, 0, sizeof(st));
+  int rc = gb_core(keys, nkeys, nrows, filter, nullptr, 0, ikey_out, ifirstkey_out, max_unique, unique_count_host, nullptr,
+                   needed_unique_host, workspace, gb_bytes, stream, &st, 0, &fz);
+  if (rc != RTB_OK) return rc;
+  if (vdtype == RTB_F32) {
+    const int64_t nb = *unique_count_host + 1;
+    gb_cast_sums_f32<<<grid_for(nb, 256, 1), 256, 0, stream>>>(fz.acc, (float*)sum_out, nb);
+    RTB_LAUNCH_CHECK();
+  }
+  return RTB_OK;
+}
+
 struct IsMemberLayout {
   void* gb_ws;
   size_t gb_bytes;
@@ -1895,7 +2079,7 @@ extern "C" int rtb_ismember32(const void* a, int64_t na, const void* b, int64_t 
   Slot* table = (Slot*)L.gb_ws;  // layout() puts the table first
   if (nb > 0) {
     RTB_ARG(b, "IsMember32: null pointer");
-    if (((uintptr_t)b % (4 * isz)) != 0) {
+    if (((uintptr_t)b % vec4_align(isz)) != 0) {
       set_error("IsMember32: the key column must be aligned to 4 items");
       return RTB_ERR_UNSUPPORTED;
     }

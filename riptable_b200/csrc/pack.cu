@@ -69,6 +69,8 @@ static int bits_for(int64_t nbins) {
 // holding the bins in packed order and the packed row ids.  Synchronises the stream.
 static int pack_sort(const void* ikey, int kdt, int64_t n, int64_t nbins, const PackLayout& L, cudaStream_t stream,
                      uint32_t** sorted_keys, uint32_t** igroup, const char* who) {
+  // pack_keys_kernel reads iKey four rows at a time: a misaligned column would fault and poison the context
+  RTB_ARG(((uintptr_t)ikey % vec4_align(dtype_size(kdt))) == 0, "%s: ikey must be aligned to 4 rows (at most 16 bytes)", who);
   RTB_CUDA(cudaMemsetAsync(L.bad, 0, sizeof(uint32_t), stream));
   pack_keys_kernel<<<grid_for(n, 256, 4), 256, 0, stream>>>(ikey, kdt, n, nbins, L.keys_a, L.bad);
   RTB_LAUNCH_CHECK();
@@ -468,9 +470,14 @@ static int cumop_launch(const CumArgs& a, int64_t ntiles, cudaStream_t stream) {
 }
 
 // ---- 8f.2: time-decayed moving averages (EmaAll32 functions 301 / 304 / 305) ---------------------------------
-// Every recurrence is y_i = a_i * y_{i-1} + b_i over the packed order.  A row that restarts its group's state (first
-// included row of a bin, or reset_filter) has a_i = 0, so a PLAIN inclusive scan of the affine maps under composition
-// (a1, b1) o (a2, b2) = (a1 a2, a2 b1 + b2) needs no segment flags.  Rows the op-filter excludes are the identity
+// Every recurrence is y_i = a_i * y_{i-1} + b_i over the packed order, so one inclusive scan of the affine maps under
+// composition (a1, b1) o (a2, b2) = (a1 a2, a2 b1 + b2) does all groups at once.  A row that restarts its group's state
+// (first row of a bin, or reset_filter) is a HEAD: it must cut off everything before it EXACTLY -- "a = 0" alone does
+// not, because 0 * NaN and 0 * Inf are NaN and one NaN / Inf value (or an overflowing exp(-rate * dt) on unsorted
+// times) would leak into every later bin.  A head is therefore marked by a = -0.0 (no decay weight is ever negative
+// zero), `combine` returns a head on the right-hand side untouched, and -0.0 * w keeps the mark on compositions that
+// start with one.  The identity (1, 0) is likewise passed through exactly (w = Inf would turn its 0 into NaN).  Rows
+// the op-filter excludes are the identity
 // (1, 0): they show the group's current value and leave its clock alone, so the decay of the next included row spans
 // the time since the previous INCLUDED row -- found with a plain max-scan over (included ? position : -1).
 struct Affine {
@@ -479,7 +486,12 @@ struct Affine {
 struct AffineOp {
   typedef Affine T;
   __device__ static Affine identity() { return Affine{1.0, 0.0}; }
-  __device__ static Affine combine(Affine x, Affine y) { return Affine{x.a * y.a, y.a * x.b + y.b}; }  // x first
+  __device__ static bool is_head(Affine m) { return __double_as_longlong(m.a) == (long long)0x8000000000000000ull; }
+  __device__ static Affine head(double b) { return Affine{-0.0, b}; }
+  __device__ static Affine combine(Affine x, Affine y) {  // x first, then y
+    if (is_head(y) || (x.a == 1.0 && x.b == 0.0)) return y;
+    return Affine{x.a * y.a, y.a * x.b + y.b};
+  }
   __device__ static Affine shfl_up(Affine v, int d) { return Affine{__shfl_up_sync(0xffffffffu, v.a, d), __shfl_up_sync(0xffffffffu, v.b, d)}; }
 };
 struct MaxI32Op {
@@ -604,14 +616,14 @@ __global__ void __launch_bounds__(256) ema_maps_kernel(EmaArgs a) {
     const bool seg_first = j == 0 || a.skeys[j - 1] != k;
     Affine m;
     if (a.lastinc[j] != (int32_t)j) {  // bin 0, or excluded by the op-filter: show the running value
-      m = seg_first ? Affine{0.0, 0.0} : Affine{1.0, 0.0};
+      m = seg_first ? AffineOp::head(0.0) : Affine{1.0, 0.0};
     } else {
       const uint32_t row = a.igroup[j];
       const double x = raw_to_f64(load_raw1(a.values, vsz, row), a.vdt);
       const int32_t prev = j > 0 ? a.lastinc[j - 1] : -1;
       const bool restart = prev < 0 || a.skeys[prev] != k || (a.reset && a.reset[row]);
       if (restart) {
-        m = Affine{0.0, x};
+        m = AffineOp::head(x);
       } else if (a.func == RTB_GB_EMAWEIGHTED) {
         m = Affine{a.rate, x * (1.0 - a.rate)};
       } else {
@@ -862,7 +874,7 @@ extern "C" int rtb_groupby_cumop(int func, const void* values, int vdt, const vo
   RTB_ARG(nrows >= 0 && nrows <= 2147483646ll && unique_rows >= 0, "EmaAll32: bad sizes");
   if (nrows == 0) return RTB_OK;
   RTB_ARG(values && ikey && out, "EmaAll32: null pointer");
-  RTB_ARG(((uintptr_t)ikey % (4 * dtype_size(kdt))) == 0, "EmaAll32: ikey must be aligned to 4 rows");
+  RTB_ARG(((uintptr_t)ikey % vec4_align(dtype_size(kdt))) == 0, "EmaAll32: ikey must be aligned to 4 rows");
   CumLayout L = cum_layout(workspace, workspace_bytes, nrows);
   RTB_ARG(workspace && L.bytes <= workspace_bytes, "EmaAll32: workspace too small");
   uint32_t *skeys, *ig;
@@ -919,7 +931,7 @@ extern "C" int rtb_groupby_ema(int func, const void* values, int vdt, const void
   RTB_ARG(func == RTB_GB_EMAWEIGHTED || (time && tdt >= RTB_BOOL && tdt <= RTB_F64), "EmaAll32: ema_decay / ema_normal need a numeric time array");
   if (nrows == 0) return RTB_OK;
   RTB_ARG(values && ikey && out, "EmaAll32: null pointer");
-  RTB_ARG(((uintptr_t)ikey % (4 * dtype_size(kdt))) == 0, "EmaAll32: ikey must be aligned to 4 rows");
+  RTB_ARG(((uintptr_t)ikey % vec4_align(dtype_size(kdt))) == 0, "EmaAll32: ikey must be aligned to 4 rows");
   EmaLayout L = ema_layout(workspace, workspace_bytes, nrows);
   RTB_ARG(workspace && L.bytes <= workspace_bytes, "EmaAll32: workspace too small");
   uint32_t *skeys, *ig;
@@ -976,7 +988,7 @@ extern "C" int rtb_make_inext(const void* ikey, int kdt, int64_t nrows, int64_t 
   RTB_ARG(mode == 0 || mode == 1, "MakeiNext: mode must be 0 (next) or 1 (previous)");
   if (nrows == 0) return RTB_OK;
   RTB_ARG(ikey && out, "MakeiNext: null pointer");
-  RTB_ARG(((uintptr_t)ikey % (4 * dtype_size(kdt))) == 0, "MakeiNext: key must be aligned to 4 rows");
+  RTB_ARG(((uintptr_t)ikey % vec4_align(dtype_size(kdt))) == 0, "MakeiNext: key must be aligned to 4 rows");
   PackLayout L = pack_layout(workspace, workspace_bytes, nrows, 1);
   RTB_ARG(workspace && L.bytes <= workspace_bytes, "MakeiNext: workspace too small");
   uint32_t *skeys, *ig;

@@ -15,6 +15,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "reduce_internal.cuh"
 #include "values.cuh"
 
 namespace rtb {
@@ -236,6 +237,17 @@ static int launch_accum(const AccumArgs& a, cudaStream_t stream) {
   return RTB_OK;
 }
 
+int accum_sum_rows(const void* values, int vdt, const void* ikey, int kdt, int64_t n, int64_t nb, int64_t bin_lo,
+                   int nanskip, unsigned long long* acc, cudaStream_t stream) {
+  AccumArgs a;
+  memset(&a, 0, sizeof(a));
+  a.values = values; a.ikey = ikey; a.vdt = vdt; a.kdt = kdt;
+  a.n = n; a.lo = bin_lo < 0 ? 0 : bin_lo; a.hi = nb; a.nb = nb;
+  a.nanskip = nanskip;
+  a.acc = acc;
+  return (vdt == RTB_F32 || vdt == RTB_F64) ? launch_accum<OP_SUMF>(a, stream) : launch_accum<OP_SUMI>(a, stream);
+}
+
 }  // namespace rtb
 
 using namespace rtb;
@@ -272,7 +284,7 @@ extern "C" int rtb_groupby_reduce(const void* values, int vdt, const void* ikey,
   RTB_ARG(nrows >= 0 && unique_rows >= 0 && out, "GroupByAll32: bad sizes or null output");
   RTB_ARG(nrows == 0 || (values && ikey), "GroupByAll32: null input");
   int vsz = dtype_size(vdt), ksz = dtype_size(kdt);
-  RTB_ARG(((uintptr_t)values % (4 * vsz)) == 0 && ((uintptr_t)ikey % (4 * ksz)) == 0,
+  RTB_ARG(((uintptr_t)values % vec4_align(vsz)) == 0 && ((uintptr_t)ikey % vec4_align(ksz)) == 0,
           "GroupByAll32: inputs must be aligned to 4 rows");
   const int64_t nb = unique_rows + 1;
   RTB_ARG(nb < (1ll << 31), "GroupByAll32: too many bins");
@@ -343,7 +355,7 @@ extern "C" int rtb_bincount(const void* ikey, int kdt, int64_t nrows, int64_t nb
   RTB_ARG(nrows >= 0 && nbins >= 0 && nbins < (1ll << 31), "BinCount: bad sizes");
   if (nbins == 0) return RTB_OK;
   RTB_ARG(out, "BinCount: null output");
-  RTB_ARG(nrows == 0 || ((uintptr_t)ikey % (4 * dtype_size(kdt))) == 0, "BinCount: ikey must be aligned to 4 rows");
+  RTB_ARG(nrows == 0 || ((uintptr_t)ikey % vec4_align(dtype_size(kdt))) == 0, "BinCount: ikey must be aligned to 4 rows");
   RTB_CUDA(cudaMemsetAsync(out, 0, sizeof(int32_t) * (size_t)nbins, stream));
   AccumArgs a;
   memset(&a, 0, sizeof(a));

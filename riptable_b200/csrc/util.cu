@@ -266,7 +266,7 @@ int rtb_combine_filter(const void* ikey, int kdtype, const uint8_t* filter, int6
   RTB_ARG(ikey && filter && out, "CombineFilter: null pointer");
   // vector path needs 4-row alignment of the base pointers
   int ksz = dtype_size(kdtype);
-  RTB_ARG(((uintptr_t)ikey % (4 * ksz)) == 0 && ((uintptr_t)filter % 4) == 0, "CombineFilter: unaligned input");
+  RTB_ARG(((uintptr_t)ikey % vec4_align(ksz)) == 0 && ((uintptr_t)filter % 4) == 0, "CombineFilter: unaligned input");
   combine_filter_kernel<<<grid_for(nrows, 256, 4), 256, 0, (cudaStream_t)stream>>>(ikey, kdtype, filter, nrows, out);
   RTB_LAUNCH_CHECK();
   return RTB_OK;

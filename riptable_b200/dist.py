@@ -35,6 +35,7 @@ from .enums import GB_FUNCTIONS as GB
 ALLTOALL_MIN_BINS = 8_000_000  # above this many bins the partials are merged by bin-partitioned all-to-all
 SEEDED = os.environ.get("RTB_DIST_SEEDED", "1") == "1"
 SEED_ROWS = 1 << 25  # rows of the first shard that are grouped before the other shards start
+SEEDED_MIN_UNIQUE = 1 << 20  # the seeded path provisions max(this, largest shard / 16) bins; beyond that it falls back
 
 
 # ====================================================================================================
@@ -43,8 +44,10 @@ class CudaOps:
 
     def __init__(self, device=None):
         from . import rc
+        from ._lib import RtbWorkspaceError
 
         self.rc = rc
+        self.workspace_error = (RtbWorkspaceError,)  # what a grouping that ran out of provisioned bins raises
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self._side = None
 
@@ -241,7 +244,10 @@ def sharded_groupby(ops, key_cols, filter=None, group=None) -> ShardedGrouping:
     cols = [ops.as_col(c) for c in key_cols]
     n = ops.nrows(cols[0])
     if len(cols) == 1 and SEEDED and hasattr(ops, "stream") and ops.can_stream(cols[0]):
-        return _sharded_groupby_seeded(ops, cols[0], filter, group)
+        g = _sharded_groupby_seeded(ops, cols[0], filter, group)
+        if g is not None:
+            return g
+        # a shard holds more unique keys than the seeded table was provisioned for: every rank takes the generic path
     tick = _Tick()
     ik, ifk, u = ops.groupby(cols, filter)
     ik, ifk = ops.to_torch(ik), ops.to_torch(ifk)
@@ -315,19 +321,27 @@ def _sharded_groupby_seeded(ops, col, filter, group) -> ShardedGrouping:
     for r in range(1, G):
         row_off[r] = row_off[r - 1] + ns[r - 1]
     nmax = max(ns) if ns else 0
-    max_unique = max(1 << 20, nmax // 16, 1)
+    max_unique = max(SEEDED_MIN_UNIQUE, nmax // 16, 1)
     S = min(ns[0], SEED_ROWS) & ~127 if ns[0] > SEED_ROWS else ns[0]
     st = ops.stream(max_unique, max(nmax, 1))
     ikey = ops.empty_ikey(n)
 
+    # A push that runs out of table room fails on that rank alone; the failure is carried by the next collective
+    # every rank takes part in (u0 = -1 / late = -1), so that all ranks leave the seeded path together.
+    overflow = getattr(ops, "workspace_error", ())
+
     # 1. shard 0 groups its prefix and publishes the seed
+    failed = False
     if rank == 0:
-        st.push(ops.slice_rows(col, 0, S), ops.slice_filter(filter, 0, S), 0, ikey[:S] if S else None)
-    u0_t = ops.tensor([st.unique_count if rank == 0 else 0], dtype=torch.int64)
+        try:
+            st.push(ops.slice_rows(col, 0, S), ops.slice_filter(filter, 0, S), 0, ikey[:S] if S else None)
+        except overflow:
+            failed = True
+    u0_t = ops.tensor([-1 if failed else (st.unique_count if rank == 0 else 0)], dtype=torch.int64)
     tdist.broadcast(u0_t, src=tdist.get_global_rank(group, 0) if group is not None else 0, group=group)
     u0 = int(u0_t.item())
-    if u0 > max_unique:
-        raise RuntimeError("sharded_groupby: more unique keys than the provisioned table holds")
+    if u0 < 0:
+        return None
     if rank == 0:
         seed_first = ops.to_torch(st.ifirstkey).to(torch.int64).clone()
         seed_bytes = ops.col_bytes(ops.take_rows(col, ops.to_torch(st.ifirstkey))).clone()
@@ -341,22 +355,27 @@ def _sharded_groupby_seeded(ops, col, filter, group) -> ShardedGrouping:
     tick.mark("seed (shard 0 prefix + broadcast)")
 
     # 2. every other rank pre-loads the seed, then all ranks hash their (remaining) rows
-    if rank != 0 and u0:
-        st.push(ops.col_from_bytes(seed_bytes, dt, u0), None, 0, None)
-        if st.unique_count != u0:
-            raise RuntimeError("sharded_groupby: the broadcast seed holds duplicate keys")
-    lo = S if rank == 0 else 0
-    if n > lo:
-        st.push(ops.slice_rows(col, lo, n), ops.slice_filter(filter, lo, n), lo, ikey[lo:n])
+    try:
+        if rank != 0 and u0:
+            st.push(ops.col_from_bytes(seed_bytes, dt, u0), None, 0, None)
+            if st.unique_count != u0:
+                raise RuntimeError("sharded_groupby: the broadcast seed holds duplicate keys")
+        lo = S if rank == 0 else 0
+        if n > lo:
+            st.push(ops.slice_rows(col, lo, n), ops.slice_filter(filter, lo, n), lo, ikey[lo:n])
+    except overflow:
+        failed = True
     ikey = ikey[:n]
     U_r = st.unique_count
     tick.mark("hash shard")
 
     # 3. late keys (rare): merge them across ranks
-    late = ops.tensor([U_r - u0], dtype=torch.int64)
+    late = ops.tensor([-1 if failed else U_r - u0], dtype=torch.int64)
     lates = late.new_empty(G)
     tdist.all_gather_into_tensor(lates, late, group=group)
     lates = lates.cpu().tolist()
+    if min(lates) < 0:
+        return None
     total_late = sum(lates)
     if total_late == 0:
         tick.mark("late check")

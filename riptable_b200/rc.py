@@ -254,6 +254,16 @@ def _as_list(list_arrays):
     return list_arrays
 
 
+def _initial_max_unique(n: int, hint_size) -> int:
+    """Bins the first attempt provisions for.  `hint_size` (riptable's own estimate of the unique count,
+    riptable/rt_numpy.py:2066-2070) is taken as given; without one, room for n/8 uniques (at least 1 Mi).  The C side
+    reports RTB_ERR_WORKSPACE with an extrapolated requirement when a call needs more, and the shim retries with it, so
+    a 1 B-row call with 1 M keys no longer reserves a table region sized for 500 M."""
+    if hint_size and hint_size > 0:
+        return min(n, max(int(hint_size), 1024))
+    return min(n, max(1 << 20, n // 8))
+
+
 # ==================================================================================================
 # a1  rc.MultiKeyGroupBy32 (riptable/rt_numpy.py:2073-2075)
 def MultiKeyGroupBy32(list_arrays, hint_size=0, filter=None, hash_mode=2, cutoffs=None):
@@ -279,9 +289,7 @@ def MultiKeyGroupBy32(list_arrays, hint_size=0, filter=None, hash_mode=2, cutoff
         e = DevArray.empty(0, np.int32)
         return _from_dev(e, device_mode), _from_dev(e, device_mode), 0
 
-    # room for n/2 uniques up front: the workspace is only touched as far as the table really grows, and running
-    # out of room means starting over with a larger one
-    max_unique = min(n, max(int(hint_size), 1024)) if hint_size and hint_size > 0 else min(n, max(1 << 20, n // 2))
+    max_unique = _initial_max_unique(n, hint_size)
     carr = _cols(cols)
     ikey = DevArray.empty(n, np.int32, dev)
     ucount, needed = C.c_int64(0), C.c_int64(0)
@@ -312,6 +320,64 @@ def MultiKeyGroupBy32(list_arrays, hint_size=0, filter=None, hash_mode=2, cutoff
     if cut is not None:
         return ik, (ifk, ucut), u
     return ik, ifk, u
+
+
+# ==================================================================================================
+# a1 + a5 fused: what `ds.gb(key).sum()` / `Categorical(key).sum(v)` run back to back (riptable/rt_groupbyops.py:1161-1225)
+def MultiKeyGroupBySum32(list_arrays, values, hint_size=0, filter=None, hash_mode=2, func=GB_FUNCTIONS.GB_SUM, bin_low=1):
+    """MultiKeyGroupBy32(list_arrays, hint_size, filter) and GroupByAll32([values], iKey, U, [func], [bin_low], [U + 1])
+    in one pass over the rows.  func: GB_SUM or GB_NANSUM.
+    -> (iKey int32[N], iFirstKey int32[U], unique_count, sums[U + 1]) with exactly the values of the two calls."""
+    list_arrays = _as_list(list_arrays)
+    if not isinstance(list_arrays, list) or len(list_arrays) == 0:
+        raise ValueError("groupbyhash first argument is not a list of numpy arrays")
+    device_mode = any(_is_device(a) for a in list_arrays) or _is_device(values)
+    cols = [_to_dev(a) for a in list_arrays]
+    n = cols[0].n
+    if any(c.n != n for c in cols):
+        raise ValueError(f"groupbyhash all arrays must have same length not {set(c.n for c in cols)}")
+    v = _to_dev(values)
+    if v.n != n:
+        raise ValueError(f"GroupByAll32: value length {v.n} does not match ikey length {n}")
+    if v.dtype.kind not in "biuf" or v.dtype == np.float16:
+        raise TypeError(f"GroupByAll32: {v.dtype} cannot be summed")
+    vcode = dtype_code(v.dtype)
+    ocode = lib.rtb_reduce_out_dtype(int(func), vcode)
+    if ocode < 0 or int(func) not in (GB_FUNCTIONS.GB_SUM, GB_FUNCTIONS.GB_NANSUM):
+        raise TypeError("MultiKeyGroupBySum32: GB_SUM / GB_NANSUM of a numeric column")
+    odt = code_dtype(ocode)
+    fdev = _bool_dev(filter, n) if filter is not None else None
+    dev = _device()
+    if n == 0:
+        e = DevArray.empty(0, np.int32)
+        z = DevArray(torch.zeros(16, dtype=torch.uint8, device=dev), odt, 1)
+        return _from_dev(e, device_mode), _from_dev(e, device_mode), 0, _from_dev(z, device_mode)
+    max_unique = _initial_max_unique(n, hint_size)
+    carr = _cols(cols)
+    ikey = DevArray.empty(n, np.int32, dev)
+    single = len(cols) == 1 and cols[0].dtype.kind in "biuf"
+    row_bytes = 0 if single else sum(c.dtype.itemsize for c in cols)
+    ucount, needed = C.c_int64(0), C.c_int64(0)
+    while True:
+        ifirst = DevArray.empty(max_unique, np.int32, dev)
+        sums = DevArray.empty(max_unique + 1, odt, dev)
+        ws = _ws(lib.rtb_groupby_sum_workspace_bytes(n, max_unique, row_bytes))
+        rc_ = lib.rtb_multikey_groupby_sum32(
+            carr, len(cols), n, C.c_void_p(fdev.ptr) if fdev is not None else None, C.c_void_p(v.ptr), vcode, int(func),
+            int(bin_low), C.c_void_p(ikey.ptr), C.c_void_p(ifirst.ptr), max_unique, C.c_void_p(sums.ptr), C.byref(ucount),
+            C.byref(needed), C.c_void_p(ws.data_ptr()), ws.numel(), _stream())
+        if rc_ == _lib.RTB_ERR_WORKSPACE and max_unique < n:
+            max_unique = min(n, max(int(needed.value), 4 * max_unique))
+            continue
+        check(rc_, needed.value)
+        break
+    u = int(ucount.value)
+    ifirst = DevArray(ifirst.buf, np.int32, u)
+    sums = DevArray(sums.buf, odt, u + 1)
+    ik, ifk, sm = _from_dev(ikey, device_mode), _from_dev(ifirst, device_mode), _from_dev(sums, device_mode)
+    if device_mode and u < max_unique // 2:
+        ifk, sm = ifk.clone(), sm.clone()  # do not pin max_unique-sized buffers behind small results
+    return ik, ifk, u, sm
 
 
 # ==================================================================================================
@@ -807,7 +873,7 @@ def ReIndexGroups(ikey, uikey, u_cutoffs, i_cutoffs):
     return res if device_mode or kdt == np.dtype(np.int32) else res.astype(kdt)
 
 
-__all__ = ["GroupByStream", "ReIndexGroups", "LexPartition", "MultiKeyGroupBy32", "CombineFilter", "CombineAccum1Filter", "CombineAccum2Filter", "GroupByAll32", "BinCount",
+__all__ = ["MultiKeyGroupBySum32", "GroupByStream", "ReIndexGroups", "LexPartition", "MultiKeyGroupBy32", "CombineFilter", "CombineAccum1Filter", "CombineAccum2Filter", "GroupByAll32", "BinCount",
            "GroupFromBinCount", "GroupByPack32", "GroupByAllPack32", "EmaAll32", "MakeiFirst", "MakeiNext", "LexSort32",
            "LexSort64", "GroupFromLexSort", "ReverseShuffle", "IsMember32", "IsMemberCategorical", "MultiKeyIsMember32", "LedgerFunction"]
 

@@ -17,8 +17,14 @@ def _np(x):
     return x.numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
 
 
+class _StreamOverflow(RuntimeError):
+    """Stand-in for RtbWorkspaceError: the resumable grouping ran out of provisioned bins."""
+
+
 class OracleOps:
     """NumPy/oracle stand-in for CudaOps (same method set), CPU tensors for the collectives."""
+
+    workspace_error = (_StreamOverflow,)
 
     def as_col(self, x):
         return x.numpy() if isinstance(x, torch.Tensor) else np.ascontiguousarray(x)
@@ -122,7 +128,7 @@ class OracleOps:
 
     # --- resumable single-key grouping (stand-in for rc.GroupByStream) ---------------------------------------
     def stream(self, max_unique, max_chunk_rows):
-        return _OracleStream()
+        return _OracleStream(max_unique)
 
     def can_stream(self, col):
         return col.dtype.kind in "biuf" and col.dtype.itemsize in (1, 2, 4, 8)
@@ -143,8 +149,9 @@ class OracleOps:
 class _OracleStream:
     """Chunked first-appearance grouping restated with the oracle: group [uniques so far ; chunk] in one call."""
 
-    def __init__(self):
+    def __init__(self, max_unique=1 << 62):
         self.uniq = None
+        self.max_unique = max_unique
         self.first = np.zeros(0, np.int32)
 
     @property
@@ -164,6 +171,8 @@ class _OracleStream:
             f = np.concatenate([np.ones(u, bool), np.asarray(filter, dtype=bool)])
         ik, ifk, U = orc.MultiKeyGroupBy32([allk], 0, f, 2)
         assert np.array_equal(ik[:u], np.arange(1, u + 1))
+        if U > self.max_unique:
+            raise _StreamOverflow(f"more than {self.max_unique} unique keys")
         self.first = np.concatenate([self.first, (ifk[u:] - u + row_offset).astype(np.int32)])
         self.uniq = allk[ifk]
         res = torch.from_numpy(ik[u:].copy())
@@ -350,3 +359,51 @@ def test_sharded_groupby_and_reduce_world2(cuts, a2a):
         exp = orc.EmaAll32([np.nan_to_num(v).astype(np.float32)], eik, eu, 300, (0.0, None, f, None))[0]
         assert full("cumsum_f32").dtype == np.float32
         np.testing.assert_allclose(full("cumsum_f32"), exp, rtol=2e-5, atol=1e-2, equal_nan=True)
+
+
+def _overflow_worker(rank, world, port, cuts, where, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    tdist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from riptable_b200 import dist as rd
+
+        rd.SEED_ROWS = 1024
+        rd.SEEDED_MIN_UNIQUE = 64  # the seeded table holds 64 bins; one shard has far more keys than that
+        k = _overflow_keys(cuts[-1], where, cuts)
+        lo, hi = cuts[rank], cuts[rank + 1]
+        g = rd.sharded_groupby(OracleOps(), [k[lo:hi]], None)
+        q.put((rank, {"ikey": g.ikey.numpy().copy(), "ifk": g.ifirstkey.numpy().copy(), "u": g.unique_count}))
+    finally:
+        tdist.destroy_process_group()
+
+
+def _overflow_keys(n, where, cuts):
+    rng = np.random.default_rng(3)
+    k = rng.integers(0, 30, n).astype(np.int64)
+    lo, hi = cuts[where], cuts[where + 1]
+    k[lo:hi] = rng.integers(0, 900, hi - lo)  # only this shard overflows
+    return k
+
+
+@pytest.mark.parametrize("where", [0, 1])
+def test_seeded_overflow_on_one_rank_falls_back_on_all_ranks(where):
+    """a shard with more uniques than the seeded table holds fails on that rank alone; every rank must
+    leave the seeded path together (no rank may be left waiting in a collective) and the result stays exact."""
+    cuts = (0, 3000, 6500)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_overflow_worker, args=(r, 2, port, cuts, where, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    k = _overflow_keys(cuts[-1], where, cuts)
+    eik, eifk, eu = orc.MultiKeyGroupBy32([k], 0, None, 2)
+    assert eu > 64
+    np.testing.assert_array_equal(np.concatenate([got[0]["ikey"], got[1]["ikey"]]), eik)
+    for r in range(2):
+        assert got[r]["u"] == eu
+        np.testing.assert_array_equal(got[r]["ifk"], eifk)

@@ -469,3 +469,127 @@ def test_ismember_vs_oracle(rc):
     assert len(m) == 0 and len(idx) == 0
     m, idx = rc.IsMember32(np.arange(3, dtype=np.int32), np.zeros(0, np.int32))
     assert not m.any() and (idx == np.iinfo(np.int8).min).all()
+
+
+# ---- fused grouping + sum (rtb_multikey_groupby_sum32): must equal the two reference calls it stands for ----------
+def _check_fused(rc, keys, val, filter=None, func=0, bin_low=1, hint=0):
+    ik, ifk, u, s = rc.MultiKeyGroupBySum32(keys, val, hint, filter, 2, func, bin_low)
+    ok, ofk, ou = orc.MultiKeyGroupBy32(keys, hint, filter, 2)
+    assert u == ou and ik.dtype == np.int32 and ifk.dtype == np.int32
+    np.testing.assert_array_equal(ik, ok)
+    np.testing.assert_array_equal(ifk, ofk)
+    exp = orc.GroupByAll32([val], ok, ou, [func], [bin_low], [ou + 1], 0)[0]
+    assert s.dtype == exp.dtype and s.shape == exp.shape
+    if exp.dtype.kind == "f":
+        rtol = 1e-12 if exp.dtype == np.float64 else 1e-5
+        scale = max(1.0, float(np.nanmax(np.abs(val.astype(np.float64)))) if len(val) else 1.0)
+        cnt = np.bincount(ok, minlength=ou + 1)
+        np.testing.assert_allclose(s[bin_low:], exp[bin_low:], rtol=rtol, atol=rtol * scale * max(1.0, float(cnt.max()) ** 0.5))
+    else:
+        np.testing.assert_array_equal(s[bin_low:], exp[bin_low:])
+    return u
+
+
+@pytest.mark.parametrize("kdt", [np.int64, np.int32, np.uint16, np.int8, np.float64])
+@pytest.mark.parametrize("vdt", [np.float64, np.float32, np.int64, np.int32, np.int16, np.uint8, np.bool_])
+@pytest.mark.parametrize("n,u", [(1, 1), (130, 7), (100_003, 900), (3_000_017, 50_000)])
+def test_fused_groupby_sum(rc, kdt, vdt, n, u):
+    rng = np.random.default_rng(n + u)
+    info_hi = 100 if np.dtype(kdt).itemsize == 1 else u
+    uv = rng.permutation(np.arange(-(info_hi // 2), info_hi - info_hi // 2))[: min(u, info_hi)]
+    if np.dtype(kdt).kind == "u":
+        uv = np.abs(uv)
+    k = uv[rng.integers(0, len(uv), n)].astype(kdt)
+    if np.dtype(vdt).kind == "f":
+        v = (rng.random(n) * 2 - 1).astype(vdt)
+    elif vdt == np.bool_:
+        v = rng.random(n) < 0.5
+    else:
+        v = rng.integers(0, 100, n).astype(vdt)
+    _check_fused(rc, [k], v)
+    _check_fused(rc, [k], v, filter=rng.random(n) < 0.7)
+    _check_fused(rc, [k], v, filter=rng.random(n) < 0.7, bin_low=0)
+
+
+def test_fused_groupby_sum_late_keys_nan_and_multikey(rc):
+    rng = np.random.default_rng(5)
+    n = 6_000_000
+    # keys that only appear late: provisional rows inside fused steady-state rounds, summed by the fix-up pass
+    k = rng.integers(0, 2000, n).astype(np.int64) * 7919
+    late = rng.integers(4_500_000, n, 3000)
+    k[late] = 10**12 + rng.integers(0, 500, len(late))
+    v = rng.random(n) * 2 - 1
+    v[rng.integers(0, n, 1000)] = np.nan
+    _check_fused(rc, [k], v, func=50)             # GB_NANSUM skips the NaNs
+    u = _check_fused(rc, [k], np.nan_to_num(v))
+    assert u > 2000
+    # a burst of new keys large enough to overflow the settled table: the fused round aborts, is redone unfused, and
+    # the sums are rebuilt from the rows grouped so far
+    k2 = k.copy()
+    k2[5_000_000:] = 10**15 + np.arange(n - 5_000_000)
+    _check_fused(rc, [k2], np.nan_to_num(v))
+    # multi-key and string rows have no fused kernel: every round is grouped, then summed
+    a = rng.integers(0, 300, 400_000).astype(np.int64)
+    b = rng.integers(0, 50, 400_000).astype(np.int32)
+    s = np.array([b"k%03d" % i for i in range(200)], dtype="S10")[rng.integers(0, 200, 400_000)]
+    w = rng.integers(-1000, 1000, 400_000).astype(np.int32)
+    _check_fused(rc, [a, b], w)
+    _check_fused(rc, [a, s, b], w.astype(np.float32))
+    _check_fused(rc, [s], w.astype(np.float64), filter=rng.random(400_000) < 0.5)
+
+
+def test_fused_groupby_sum_device_mode_and_empty(rc):
+    import torch
+
+    rng = np.random.default_rng(9)
+    n = 2_500_000
+    k = rng.integers(-(2**62), 2**62, 20_000)[rng.integers(0, 20_000, n)]
+    v = rng.random(n)
+    ik, ifk, u, s = rc.MultiKeyGroupBySum32([torch.from_numpy(k).cuda()], torch.from_numpy(v).cuda())
+    assert ik.is_cuda and ifk.is_cuda and s.is_cuda
+    ok, ofk, ou = orc.MultiKeyGroupBy32([k])
+    np.testing.assert_array_equal(ik.cpu().numpy(), ok)
+    np.testing.assert_array_equal(ifk.cpu().numpy(), ofk)
+    exp = orc.GroupByAll32([v], ok, ou, [0], [1], [ou + 1], 0)[0]
+    np.testing.assert_allclose(s.cpu().numpy()[1:], exp[1:], rtol=1e-12, atol=1e-10)
+    ik, ifk, u, s = rc.MultiKeyGroupBySum32([np.zeros(0, np.int64)], np.zeros(0, np.float32))
+    assert u == 0 and len(ik) == 0 and s.dtype == np.float32 and s.tolist() == [0.0]
+    with pytest.raises(TypeError):
+        rc.MultiKeyGroupBySum32([k], np.array([b"a"] * n))
+    with pytest.raises(ValueError):
+        rc.MultiKeyGroupBySum32([k], v[:-1])
+
+
+def test_16_byte_aligned_slices_take_the_direct_path(rc):
+    """a 16- but not 32-byte aligned int64 / float64 slice (tensor[2:]) is all the 128-bit loads need; it
+    must neither change the slot format of a resumable grouping nor be refused by GroupByAll32 / BinCount."""
+    import torch
+
+    g = torch.Generator(device="cuda")
+    g.manual_seed(3)
+    n = 3_000_000
+    base = torch.randint(0, 5000, (n + 2,), dtype=torch.int64, device="cuda", generator=g) * 977 - 12345
+    vbase = torch.rand(n + 2, dtype=torch.float64, device="cuda", generator=g)
+    k, v = base[2:], vbase[2:]
+    assert k.data_ptr() % 32 == 16 and v.data_ptr() % 32 == 16
+    kh, vh = k.cpu().numpy(), v.cpu().numpy()
+    ok, ofk, ou = orc.MultiKeyGroupBy32([kh])
+    ik, ifk, u = rc.MultiKeyGroupBy32([k], 0, None, 2)
+    assert u == ou
+    np.testing.assert_array_equal(ik.cpu().numpy(), ok)
+    np.testing.assert_array_equal(ifk.cpu().numpy(), ofk)
+    half = 1_500_000
+    st = rc.GroupByStream(1 << 20, 2_000_000)
+    a = st.push(k[:half]).clone()
+    b = st.push(k[half:], row_offset=half).clone()  # this chunk starts 16 bytes off a 32-byte boundary
+    np.testing.assert_array_equal(torch.cat([a, b]).cpu().numpy(), ok)
+    np.testing.assert_array_equal(st.ifirstkey.cpu().numpy(), ofk)
+    ikl = torch.empty(n + 2, dtype=torch.int64, device="cuda")
+    ikl[2:] = ik
+    s = rc.GroupByAll32([v], ikl[2:], u, [0], [1], [u + 1], 0)[0]
+    exp = orc.GroupByAll32([vh], ok, ou, [0], [1], [ou + 1], 0)[0]
+    np.testing.assert_allclose(s.cpu().numpy()[1:], exp[1:], rtol=1e-12, atol=1e-9)
+    np.testing.assert_array_equal(rc.BinCount(ikl[2:], u + 1).cpu().numpy(), np.bincount(ok, minlength=ou + 1))
+    ik2, ifk2, u2, s2 = rc.MultiKeyGroupBySum32([k], v)
+    np.testing.assert_array_equal(ik2.cpu().numpy(), ok)
+    np.testing.assert_allclose(s2.cpu().numpy()[1:], exp[1:], rtol=1e-12, atol=1e-9)

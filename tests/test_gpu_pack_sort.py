@@ -295,6 +295,41 @@ def test_ema(rc, vdt, nb):
         rc.EmaAll32([v], ikey, nb, 301, (0.5, None, None, None))
 
 
+def test_ema_nonfinite_values_stay_inside_their_group(rc):
+    """a NaN / Inf value (or an overflowing decay weight on unsorted times) in one bin must not reach the
+    bins that follow it in packed order, and reset_filter restarts a group after a NaN."""
+    rng = np.random.default_rng(77)
+    n, nb = 20_000, 50
+    ikey = rng.integers(1, nb + 1, n).astype(np.int32)
+    t = np.cumsum(rng.integers(0, 4, n)).astype(np.float64)
+    for bad in (np.nan, np.inf, -np.inf):
+        v = rng.normal(0, 1, n)
+        rows1 = np.flatnonzero(ikey == 1)
+        v[rows1[3]] = bad  # early in bin 1, the first bin of the packed order
+        v[np.flatnonzero(ikey == 7)[0]] = bad  # and as the very first value of a group
+        reset = np.zeros(n, dtype=bool)
+        reset[rows1[10]] = True  # bin 1 restarts after its bad value
+        for fn, rate in ((301, 0.05), (304, 0.3), (305, 0.9)):
+            for fp in [(rate, t, None, None), (rate, t, None, reset)]:
+                exp = orc.EmaAll32([v], ikey, nb, fn, fp)[0]
+                got = rc.EmaAll32([v], ikey, nb, fn, fp)[0]
+                other = (ikey != 1) & (ikey != 7)
+                assert np.isfinite(exp[other]).all() and np.isfinite(got[other]).all(), f"func {fn}: leaked out of its bin"
+                np.testing.assert_allclose(got, exp, rtol=1e-11, atol=1e-9, equal_nan=True, err_msg=f"func {fn} bad {bad}")
+                if fp[3] is not None:
+                    assert np.isfinite(got[rows1[10:]]).all(), "reset_filter did not clear the group"
+    # unsorted times: exp(-rate * dt) overflows to Inf inside bin 2 only
+    v = rng.normal(0, 1, n)
+    t2 = t.copy()
+    rows2 = np.flatnonzero(ikey == 2)
+    t2[rows2[5]] = -1e6
+    for fn in (301, 304):
+        exp = orc.EmaAll32([v], ikey, nb, fn, (1.0, t2, None, None))[0]
+        got = rc.EmaAll32([v], ikey, nb, fn, (1.0, t2, None, None))[0]
+        assert np.isfinite(got[ikey != 2]).all()
+        np.testing.assert_allclose(got[ikey != 2], exp[ikey != 2], rtol=1e-11, atol=1e-9)
+
+
 def test_ema_docstring_kats(rc):
     test = np.arange(10)
     g = (np.arange(10) % 3 + 1).astype(np.int8)

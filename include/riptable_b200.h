@@ -128,6 +128,19 @@ int rtb_multikey_groupby_sum32(const rtb_column* keys, int nkeys, int64_t nrows,
                                int32_t* ifirstkey_out, int64_t max_unique, void* sum_out, int64_t* unique_count_host,
                                int64_t* needed_unique_host, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Resumable form of the fused call (one key column of 1, 2, 4 or 8 bytes), as rtb_multikey_groupby32_chunk is to
+ * rtb_multikey_groupby32: consecutive calls group-and-sum consecutive row chunks as if they were one array.  `acc` holds
+ * max_unique + 1 raw accumulators that persist between calls -- float64 for float columns, int64 (wrap-around) for
+ * integer columns, indexed by bin, slot 0 = filtered rows (summed only when bin_low == 0); the library zeroes an
+ * accumulator when its bin comes into existence.  `values` may be NULL: the chunk then only creates bins (this is how a
+ * row shard pre-loads the keys another shard found first, riptable_b200/dist.py).  The workspace
+ * (rtb_groupby_sum_chunk_workspace_bytes(largest chunk, max_unique)) must be the same buffer on every call. */
+size_t rtb_groupby_sum_chunk_workspace_bytes(int64_t max_chunk_rows, int64_t max_unique);
+int rtb_multikey_groupby_sum32_chunk(const rtb_column* key, int64_t nrows, const uint8_t* filter, const void* values,
+                                     int vdtype, int func, int64_t bin_low, int32_t* ikey_out, int32_t* ifirstkey_out,
+                                     int64_t max_unique, void* acc, int64_t row_offset, rtb_gb_state* state, int resume,
+                                     int64_t* needed_unique_host, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- 8f.1: rc.IsMember32(a, b, h, hint) / rc.IsMemberCategorical — riptable/rt_numpy.py:1388-1391, one numeric key
  * column of the same dtype on both sides.  found_out uint8[na]; index_out (index_dtype: an int rtb_dtype chosen by
  * len(b), riptable/rt_enum.py:666-679) = position of the first occurrence of a[i] in b, + base_index; absent rows get
@@ -277,6 +290,32 @@ size_t rtb_group_from_lexsort_workspace_bytes(int64_t nrows, int64_t nindex);
 int rtb_group_from_lexsort(const int32_t* igroup, int64_t nindex, const rtb_column* keys, int nkeys, int64_t nrows,
                            int base_index, int32_t* ikey_out, int32_t* ifirstkey_out, int32_t* ncountgroup_out,
                            int64_t* unique_count_host, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- `cutoffs=` of rc.LexSort32 / rc.GroupFromLexSort / rc.GroupByPack32 — riptable/rt_numpy.py:2199-2207, 1972.
+ * cutoffs (int64 cumulative row ends; a DEVICE array here) splits the rows into contiguous partitions that behave as
+ * arrays of their own (the meaning riptable/tests/test_pgroupby.py:7-86 pins for the hash case; the sort / pack cases
+ * are unpinned by the reference's tests and derived from it).  The shim runs ONE sort / pack over all rows with the
+ * partition id as an additional most significant key and uses these helpers to translate between global and
+ * partition-relative numbers:
+ *   rtb_partition_ids        pid_out[r] = partition of row r
+ *   rtb_partition_shift      values[i] -/+= first row of the partition POSITION i lies in (to_relative = 1 / 0)
+ *   rtb_partition_count_rows count_out[p] = number of entries of rows[] lying in partition p
+ *   rtb_partition_localize   iKey numbered over all partitions (partition-major, base 1) -> numbering that restarts in
+ *                            every partition, in base `base_index` (bin_base[p] = bins before partition p);
+ *                            ifirstkey (may be NULL) -> partition-relative rows
+ *   rtb_partition_max_ikey   umax_out[p] = largest iKey in partition p; *bad_out counts negative keys
+ *   rtb_partition_compose_ikey out[r] = bin_off[partition of r] + iKey[r] */
+int rtb_partition_ids(int64_t n, const int64_t* cutoffs, int64_t ncutoffs, int32_t* pid_out, void* stream);
+int rtb_partition_shift(int32_t* values, int64_t n, const int32_t* pid, const int64_t* cutoffs, int64_t ncutoffs,
+                        int to_relative, void* stream);
+int rtb_partition_count_rows(const int32_t* rows, int64_t m, const int32_t* pid, int64_t ncutoffs, int32_t* count_out,
+                             void* stream);
+int rtb_partition_localize(int32_t* ikey, int64_t n, int32_t* ifirstkey, int64_t nbins, const int32_t* pid,
+                           const int32_t* bin_base, const int64_t* cutoffs, int64_t ncutoffs, int base_index, void* stream);
+int rtb_partition_max_ikey(const void* ikey, int kdtype, int64_t n, const int32_t* pid, int64_t ncutoffs, int32_t* umax_out,
+                           uint32_t* bad_out, void* stream);
+int rtb_partition_compose_ikey(const void* ikey, int kdtype, int64_t n, const int32_t* pid, const int64_t* bin_off,
+                               int32_t* out, void* stream);
 
 /* ---- a13: rc.ReverseShuffle(perm) — riptable/rt_grouping.py:1659.  out[perm[i]] = i. */
 int rtb_reverse_shuffle(const int32_t* perm, int64_t n, int32_t* out, void* stream);

@@ -200,13 +200,35 @@ def GroupFromBinCount(ikey, ncountgroup):
     return igroup, ifirst.astype(idt)
 
 
+def _partitions(cutoffs, n):
+    """Row ranges [lo, hi) of the `cutoffs` partitions (int64 cumulative row ends, rt_numpy.py:1999-2000)."""
+    cut = np.asarray(cutoffs, dtype=np.int64)
+    if cut.ndim != 1 or len(cut) == 0 or cut[-1] != n or (np.diff(cut) < 0).any() or cut[0] < 0:
+        raise ValueError("cutoffs must be a non-decreasing 1-D int64 array whose last entry is the row count")
+    return list(zip(np.r_[0, cut[:-1]].tolist(), cut.tolist()))
+
+
 def GroupByPack32(ikey, _unused, n, cutoffs=None):
     """Old cutoffs-capable packer (rt_numpy.py:1972) -> (iGroup, iFirstGroup, nCountGroup).
-    cutoffs behaviour is UNPINNED; without cutoffs it equals BinCount(pack=True)."""
-    if cutoffs is not None:
-        raise NotImplementedError("GroupByPack32 with cutoffs is unpinned by the reference tests")
-    cnt, igroup, ifirstgroup = BinCount(ikey, n, pack=True)
-    return igroup, ifirstgroup, cnt
+    Without cutoffs it equals BinCount(pack=True).
+
+    cutoffs: UNPINNED by the reference's tests, DERIVED from the one cutoffs case they do pin
+    (tests/test_pgroupby.py:7-86: every partition behaves as an array of its own and the results are laid end to
+    end).  Partition p holds rows [c[p-1], c[p]) whose iKey is numbered per partition (what groupbyhash(cutoffs=)
+    produces); it is packed on its own with U_p + 1 bins, U_p = the largest iKey it holds:
+    iGroup[c[p-1]:c[p]] = that partition's packed rows (partition-relative), and iFirstGroup / nCountGroup are the
+    per-partition arrays (each with its own slot 0) laid end to end (length sum(U_p + 1))."""
+    if cutoffs is None:
+        cnt, igroup, ifirstgroup = BinCount(ikey, n, pack=True)
+        return igroup, ifirstgroup, cnt
+    ikey = np.asarray(ikey)
+    ig, ifg, cnt = [], [], []
+    for lo, hi in _partitions(cutoffs, len(ikey)):
+        part = ikey[lo:hi]
+        nb = int(part.max()) + 1 if hi > lo else 1
+        c, g, f = BinCount(part, nb, pack=True)
+        ig.append(g.astype(np.int32)); ifg.append(f.astype(np.int32)); cnt.append(c)
+    return np.concatenate(ig), np.concatenate(ifg), np.concatenate(cnt)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -754,7 +776,12 @@ def LexSort32(list_arrays, cutoffs=None, index=None, ascending=True):
         if len(asc) != len(list_arrays):
             raise ValueError("ascending must have one entry per key")
     if cutoffs is not None:
-        raise NotImplementedError("LexSort with cutoffs is unpinned by the reference tests")
+        # UNPINNED by the reference's tests, DERIVED from the pinned hash case (tests/test_pgroupby.py:7-86): every
+        # partition is sorted as an array of its own; out[c[p-1]:c[p]] holds partition-relative row numbers.
+        if index is not None:
+            raise ValueError("lexsort: cutoffs and index (a filter) cannot be combined")
+        parts = [LexSort32([k[lo:hi] for k in list_arrays], None, None, asc) for lo, hi in _partitions(cutoffs, n)]
+        return np.concatenate(parts).astype(np.int32) if parts else np.zeros(0, np.int32)
     keys = list_arrays
     if index is not None:
         index = np.asarray(index).astype(np.int64)
@@ -774,11 +801,24 @@ def GroupFromLexSort(iGroup, value_array, cutoffs=None, base_index=1):
     """Walk the sorted order; a new bin starts where the key row differs (bytewise) from the
     previous one.  -> (iKey int32[N] in base `base_index`, iFirstKey[U] = first (smallest) row of
     each bin, nCountGroup int32[U+1] with slot 0 = 0).  Rows absent from iGroup keep iKey 0."""
-    if cutoffs is not None:
-        raise NotImplementedError("GroupFromLexSort with cutoffs is unpinned by the reference tests")
     iGroup = np.asarray(iGroup)
     cols = value_array if isinstance(value_array, (list, tuple)) else [value_array]
     n = len(cols[0])
+    if cutoffs is not None:
+        # UNPINNED, DERIVED as for LexSort32: per-partition calls laid end to end.  iKey numbering restarts in every
+        # partition, iFirstKey holds partition-relative rows, nCountGroup = [0] + every partition's counts, and the
+        # fourth result is the cumulative unique count per partition (what groupbylex stores as nUniqueCutoffs,
+        # rt_numpy.py:2209-2212; the shape test_pgroupby.py pins for iFirstKey[1]).
+        if len(iGroup) != n:
+            raise ValueError("GroupFromLexSort: cutoffs need an iGroup that covers every row (no filter)")
+        ik, ifk, cnt, ucut = [], [], [np.zeros(1, np.int32)], []
+        total = 0
+        for lo, hi in _partitions(cutoffs, n):
+            a, b, c = GroupFromLexSort(iGroup[lo:hi], [np.asarray(x)[lo:hi] for x in cols], None, base_index)
+            ik.append(a.astype(np.int32)); ifk.append(b.astype(np.int32)); cnt.append(c[1:])
+            total += len(b)
+            ucut.append(total)
+        return (np.concatenate(ik), np.concatenate(ifk), np.concatenate(cnt), np.asarray(ucut, dtype=np.int64))
     codes = _row_codes([np.asarray(c) for c in cols])
     idt = _index_dtype(n)
     ikey = np.zeros(n, dtype=idt)
@@ -817,6 +857,9 @@ def groupbyhash(list_arrays, hint_size=0, filter=None, hash_mode=2, cutoffs=None
 
 def groupbypack(ikey, ncountgroup, unique_count=None, cutoffs=None):
     """rt_numpy.py:1901-1975."""
+    if cutoffs is not None:  # rt_numpy.py:1972
+        igroup, ifirstgroup, cnt = GroupByPack32(ikey, None, unique_count, cutoffs=cutoffs)
+        return {"iGroup": igroup, "iFirstGroup": ifirstgroup, "nCountGroup": cnt}
     if ncountgroup is None:
         cnt, igroup, ifirstgroup = BinCount(ikey, unique_count, pack=True)
     else:
@@ -838,7 +881,8 @@ def groupbylex(list_arrays, filter=None, cutoffs=None, base_index=1, rec=False):
         index = np.flatnonzero(filter).astype(np.int32)
         filterfalse = np.flatnonzero(~filter)
     iGroup = LexSort32(sort_keys, cutoffs=cutoffs, index=index)
-    iKey, iFirstKey, nCountGroup = GroupFromLexSort(iGroup, value_cols, cutoffs=cutoffs, base_index=base_index)
+    retval = GroupFromLexSort(iGroup, value_cols, cutoffs=cutoffs, base_index=base_index)
+    iKey, iFirstKey, nCountGroup = retval[:3]
     if base_index == 0:
         iKey = iKey + 1
     else:
@@ -849,7 +893,7 @@ def groupbylex(list_arrays, filter=None, cutoffs=None, base_index=1, rec=False):
         nCountGroup[0] = len(filterfalse)
         iKey[filterfalse] = 0
         iFirstGroup[0] = len(index)
-    return {
+    d = {
         "iKey": iKey,
         "iFirstKey": iFirstKey,
         "unique_count": len(iFirstKey),
@@ -857,6 +901,9 @@ def groupbylex(list_arrays, filter=None, cutoffs=None, base_index=1, rec=False):
         "iFirstGroup": iFirstGroup,
         "nCountGroup": nCountGroup,
     }
+    if len(retval) == 4:  # rt_numpy.py:2209-2212, 2249-2250
+        d["nUniqueCutoffs"] = retval[3]
+    return d
 
 
 # ----------------------------------------------------------------------------------------------

@@ -52,6 +52,11 @@ PROTOTYPES = {
         C.c_int,
         [C.POINTER(rtb_column), _i32, _i64, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _i64, _vp, _pi64, _pi64, _vp, _sz, _vp],
     ),
+    "rtb_groupby_sum_chunk_workspace_bytes": (_sz, [_i64, _i64]),
+    "rtb_multikey_groupby_sum32_chunk": (
+        C.c_int,
+        [C.POINTER(rtb_column), _i64, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _i32, _pi64, _vp, _sz, _vp],
+    ),
     "rtb_combine_filter": (C.c_int, [_vp, _i32, _vp, _i64, _vp, _vp]),
     "rtb_combine_accum2": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i64, _i64, _vp, _i32, _vp]),
     "rtb_reduce_out_dtype": (C.c_int, [_i32, _i32]),
@@ -90,6 +95,12 @@ PROTOTYPES = {
         C.c_int,
         [_vp, _i64, C.POINTER(rtb_column), _i32, _i64, _i32, _vp, _vp, _vp, _pi64, _vp, _sz, _vp],
     ),
+    "rtb_partition_ids": (C.c_int, [_i64, _vp, _i64, _vp, _vp]),
+    "rtb_partition_shift": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i32, _vp]),
+    "rtb_partition_count_rows": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
+    "rtb_partition_localize": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "rtb_partition_max_ikey": (C.c_int, [_vp, _i32, _i64, _vp, _i64, _vp, _vp, _vp]),
+    "rtb_partition_compose_ikey": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp, _vp]),
     "rtb_reverse_shuffle": (C.c_int, [_vp, _i64, _vp, _vp]),
     "rtb_remap_ikey": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
 }

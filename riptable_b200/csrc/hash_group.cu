@@ -223,6 +223,7 @@ __device__ __forceinline__ void load_tile_keys(const void* keys, int64_t tb, int
 struct GbFuse {
   const void* values;        // one value per row
   unsigned long long* acc;   // per-bin accumulators (f64 bits, or 64-bit wrap-around integers), zeroed as bins are created
+  unsigned long long* snap;  // as large as acc: the accumulators as they stood before the current fused round
   int vdt;                   // rtb_dtype of the values
   int vsz;                   // bytes per value
   int nanskip;               // GB_NANSUM: NaN / integer sentinels are skipped
@@ -1576,8 +1577,10 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
   memset(&fz_none, 0, sizeof(fz_none));
   // fused sum: accumulators are zeroed as bins come into existence (bin 0 now, new bins after every round), so the
   // cost follows the bins actually found, not max_unique
-  if (fuse) RTB_CUDA(cudaMemsetAsync(fuse->acc, 0, sizeof(unsigned long long), stream));
-  const bool fuse_kernel_ok = fuse && (fuse->vsz == 8 || fuse->vsz == 4) && ((uintptr_t)fuse->values % 16) == 0;
+  // (a resumed chunk keeps what earlier chunks accumulated; a chunk without values only creates -- and zeroes -- bins)
+  if (fuse && st->rounds == 0) RTB_CUDA(cudaMemsetAsync(fuse->acc, 0, sizeof(unsigned long long), stream));
+  const bool fuse_values = fuse && fuse->values != nullptr;
+  const bool fuse_kernel_ok = fuse_values && (fuse->vsz == 8 || fuse->vsz == 4) && ((uintptr_t)fuse->values % 16) == 0;
   uint32_t snap_cap = 0;   // inline-key snapshot (16-byte packed rows): entries in use, bins it holds
   int64_t snap_built = 0;
   uint32_t cap = st->cap;
@@ -1691,6 +1694,10 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
         } else {
         fused_round = fuse_kernel_ok;
         const GbFuse fz = fused_round ? *fuse : fz_none;
+        // a fused round that runs out of table room has already added some of its rows: keep a copy of the live
+        // accumulators (U + 1 of them; provisional rows are never added by the round kernel) to fall back on
+        if (fused_round)
+          RTB_CUDA(cudaMemcpyAsync(fuse->snap, fuse->acc, sizeof(unsigned long long) * (size_t)(U + 1), cudaMemcpyDeviceToDevice, stream));
         const int fk = !fused_round ? 0 : (fuse->vsz == 8 ? 1 : 2);
 #define RTB_ROUND(ISZ_, PF_, FK_)                                                                                          \
   do {                                                                                                                    \
@@ -1833,15 +1840,8 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
       want = g > capmax ? capmax : (uint32_t)g;
     }
 
-    if (fuse && redo_sums) {
-      // the aborted attempt of this round had already added some of its rows: start the sums over from the rows
-      // grouped so far (their iKey is final); the repeat of the round ran unfused and is added below
-      RTB_CUDA(cudaMemsetAsync(fuse->acc, 0, sizeof(unsigned long long) * (size_t)(U + 1), stream));
-      if (lo > 0) {
-        int rc = accum_sum_rows(fuse->values, fuse->vdt, ikey_out, RTB_I32, lo, U + 1, fuse->bin_low, fuse->nanskip, fuse->acc, stream);
-        if (rc != RTB_OK) return rc;
-      }
-    }
+    if (fuse_values && redo_sums)  // the aborted attempt's partial sums go; the repeat ran unfused and is added below
+      RTB_CUDA(cudaMemcpyAsync(fuse->acc, fuse->snap, sizeof(unsigned long long) * (size_t)(U + 1), cudaMemcpyDeviceToDevice, stream));
     if (fuse && prev_new > 0)
       RTB_CUDA(cudaMemsetAsync(fuse->acc + U + 1, 0, sizeof(unsigned long long) * (size_t)prev_new, stream));
     if (prev_new > 0) {
@@ -1858,7 +1858,7 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
       RTB_LAUNCH_CHECK();
       U += prev_new;
     }
-    if (fuse && !fused_round) {
+    if (fuse_values && !fused_round) {
       // rounds whose kernel has no fused form (discovery, shared-memory tables, multi-key rows): the round's rows are
       // summed from the iKey it just wrote, while that is still in L2 for all but the largest rounds
       const int vsz = fuse->vsz;
@@ -1974,7 +1974,8 @@ __global__ void __launch_bounds__(256) gb_cast_sums_f32(const unsigned long long
 
 extern "C" size_t rtb_groupby_sum_workspace_bytes(int64_t nrows, int64_t max_unique, int64_t row_bytes) {
   if (nrows < 0 || max_unique < 0 || row_bytes < 0) return 0;
-  return align_up(rtb_groupby_workspace_bytes_rows(nrows, max_unique, row_bytes, 0), 256) + sizeof(unsigned long long) * ((size_t)max_unique + 1) + 256;
+  return align_up(rtb_groupby_workspace_bytes_rows(nrows, max_unique, row_bytes, 0), 256) +
+         2 * align_up(sizeof(unsigned long long) * ((size_t)max_unique + 1), 256) + 256;
 }
 
 extern "C" int rtb_multikey_groupby_sum32(const rtb_column* keys, int nkeys, int64_t nrows, const uint8_t* filter,
@@ -2010,7 +2011,8 @@ extern "C" int rtb_multikey_groupby_sum32(const rtb_column* keys, int nkeys, int
   for (int c = 0; c < nkeys; c++) row_bytes += keys[c].itemsize;
   const bool single = nkeys == 1 && (keys[0].itemsize == 1 || keys[0].itemsize == 2 || keys[0].itemsize == 4 || keys[0].itemsize == 8);
   const size_t gb_bytes = align_up(rtb_groupby_workspace_bytes_rows(nrows, max_unique, single ? 0 : row_bytes, 0), 256);
-  RTB_ARG(workspace && ((uintptr_t)workspace % 256) == 0 && gb_bytes + sizeof(unsigned long long) * ((size_t)max_unique + 1) <= workspace_bytes,
+  const size_t acc_bytes = align_up(sizeof(unsigned long long) * ((size_t)max_unique + 1), 256);
+  RTB_ARG(workspace && ((uintptr_t)workspace % 256) == 0 && gb_bytes + 2 * acc_bytes <= workspace_bytes,
           "MultiKeyGroupBySum32: workspace too small or not 256-byte aligned");
   GbFuse fz;
   memset(&fz, 0, sizeof(fz));
@@ -2022,6 +2024,7 @@ extern "C" int rtb_multikey_groupby_sum32(const rtb_column* keys, int nkeys, int
   fz.bin_low = (int)bin_low;
   // 64-bit outputs accumulate in place; float32 sums accumulate in f64 and are rounded once at the end
   fz.acc = vdtype == RTB_F32 ? (unsigned long long*)((uint8_t*)workspace + gb_bytes) : (unsigned long long*)sum_out;
+  fz.snap = (unsigned long long*)((uint8_t*)workspace + gb_bytes + acc_bytes);
   rtb_gb_state st;
   memset(&st, 0, sizeof(st));
   int rc = gb_core(keys, nkeys, nrows, filter, nullptr, 0, ikey_out, ifirstkey_out, max_unique, unique_count_host, nullptr,
@@ -2033,6 +2036,59 @@ extern "C" int rtb_multikey_groupby_sum32(const rtb_column* keys, int nkeys, int
     RTB_LAUNCH_CHECK();
   }
   return RTB_OK;
+}
+
+extern "C" size_t rtb_groupby_sum_chunk_workspace_bytes(int64_t max_chunk_rows, int64_t max_unique) {
+  if (max_chunk_rows < 0 || max_unique < 0) return 0;
+  return align_up(rtb_groupby_workspace_bytes(max_chunk_rows, max_unique, 1, 0), 256) +
+         align_up(sizeof(unsigned long long) * ((size_t)max_unique + 1), 256) + 256;
+}
+
+extern "C" int rtb_multikey_groupby_sum32_chunk(const rtb_column* key, int64_t nrows, const uint8_t* filter,
+                                                const void* values, int vdtype, int func, int64_t bin_low,
+                                                int32_t* ikey_out, int32_t* ifirstkey_out, int64_t max_unique,
+                                                void* acc, int64_t row_offset, rtb_gb_state* state, int resume,
+                                                int64_t* needed_unique_host, void* workspace, size_t workspace_bytes,
+                                                void* stream_) {
+  RTB_ARG(key && state && acc, "groupby-sum chunk: null key, state or accumulators");
+  RTB_ARG(key->itemsize == 1 || key->itemsize == 2 || key->itemsize == 4 || key->itemsize == 8,
+          "groupby-sum chunk: one key column of 1, 2, 4 or 8 bytes");
+  RTB_ARG(nrows >= 0 && nrows <= 2147483646ll, "groupby-sum chunk: row count out of range");
+  RTB_ARG(max_unique >= 1 && ifirstkey_out, "groupby-sum chunk: bad max_unique or null iFirstKey");
+  RTB_ARG(row_offset >= 0 && row_offset + nrows <= 2147483646ll, "groupby-sum chunk: first rows must fit int32");
+  RTB_ARG(func == RTB_GB_SUM || func == RTB_GB_NANSUM, "groupby-sum chunk: GB_SUM or GB_NANSUM");
+  RTB_ARG(bin_low == 0 || bin_low == 1, "groupby-sum chunk: bin_low must be 0 or 1");
+  RTB_ARG(!values || rtb_reduce_out_dtype(func, vdtype) >= 0, "groupby-sum chunk: the value dtype cannot be summed");
+  if (!resume) memset(state, 0, sizeof(*state));
+  else RTB_ARG(state->max_unique == max_unique, "groupby-sum chunk: max_unique must not change between chunks");
+  state->max_unique = max_unique;
+  if (needed_unique_host) *needed_unique_host = 0;
+  if (nrows == 0) {
+    if (!resume) RTB_CUDA(cudaMemsetAsync(acc, 0, sizeof(unsigned long long), (cudaStream_t)stream_));
+    return RTB_OK;
+  }
+  RTB_ARG(key->data && ikey_out && ((uintptr_t)ikey_out % 16) == 0 && ((uintptr_t)key->data % 16) == 0 &&
+              (!filter || ((uintptr_t)filter % 4) == 0) && ((uintptr_t)values % 16) == 0 && ((uintptr_t)acc % 8) == 0,
+          "groupby-sum chunk: buffers must be 16-byte aligned");
+  const size_t gb_bytes = align_up(rtb_groupby_workspace_bytes(nrows, max_unique, 1, 0), 256);
+  const size_t acc_bytes = align_up(sizeof(unsigned long long) * ((size_t)max_unique + 1), 256);
+  RTB_ARG(workspace && ((uintptr_t)workspace % 256) == 0 && workspace_bytes >= acc_bytes + gb_bytes,
+          "groupby-sum chunk: workspace too small or not 256-byte aligned");
+  GbFuse fz;
+  memset(&fz, 0, sizeof(fz));
+  fz.values = values;
+  fz.vdt = vdtype;
+  fz.vsz = values ? dtype_size(vdtype) : 0;
+  fz.nanskip = func == RTB_GB_NANSUM;
+  fz.isfloat = vdtype == RTB_F32 || vdtype == RTB_F64;
+  fz.bin_low = (int)bin_low;
+  fz.acc = (unsigned long long*)acc;
+  // the hash table sits at the start of the workspace and must stay put between chunks; the snapshot goes behind the
+  // grouping scratch of the LARGEST chunk (the size the caller provisioned), i.e. at the very end
+  fz.snap = (unsigned long long*)((uint8_t*)workspace + ((workspace_bytes - acc_bytes) & ~(size_t)255));
+  int64_t u = 0;
+  return gb_core(key, 1, nrows, filter, nullptr, 0, ikey_out, ifirstkey_out, max_unique, &u, nullptr, needed_unique_host,
+                 workspace, (size_t)((uint8_t*)fz.snap - (uint8_t*)workspace), (cudaStream_t)stream_, state, row_offset, &fz);
 }
 
 struct IsMemberLayout {

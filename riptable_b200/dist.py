@@ -117,9 +117,10 @@ class CudaOps:
         if ev is not None:
             torch.cuda.current_stream().wait_event(ev)
 
-    def stream(self, max_unique, max_chunk_rows):
-        """Resumable single-key grouping (rc.GroupByStream): push(keys, filter, row_offset, out) -> iKey of the chunk."""
-        return self.rc.GroupByStream(max_unique, max_chunk_rows)
+    def stream(self, max_unique, max_chunk_rows, with_sums=False):
+        """Resumable single-key grouping (rc.GroupByStream): push(keys, filter, row_offset, out[, values]) -> iKey of
+        the chunk; with_sums: the pushes also add the chunk's values to per-bin accumulators (stream.sums())."""
+        return self.rc.GroupByStream(max_unique, max_chunk_rows, with_sums=with_sums)
 
     def can_stream(self, col):
         return col.dtype.kind in "biuf" and col.dtype.itemsize in (1, 2, 4, 8)
@@ -228,6 +229,7 @@ class ShardedGrouping:
         self.row_offset = row_offset        # first global row of this shard
         self.nrows_total = nrows_total
         self.shard_unique_counts = shard_unique_counts
+        self.partial_sums = None            # raw per-bin sums of this shard by GLOBAL bin, when the grouping pass made them
 
     @property
     def ikey(self):
@@ -238,13 +240,15 @@ class ShardedGrouping:
         return self._gikey
 
 
-def sharded_groupby(ops, key_cols, filter=None, group=None) -> ShardedGrouping:
-    """MultiKeyGroupBy32 over rows sharded contiguously across the ranks of `group` (module docstring, steps 1-4)."""
+def sharded_groupby(ops, key_cols, filter=None, group=None, sum_values=None) -> ShardedGrouping:
+    """MultiKeyGroupBy32 over rows sharded contiguously across the ranks of `group` (module docstring, steps 1-4).
+    `sum_values`: a value column to sum in the same pass where the path allows it (single-key seeded shards); the
+    grouping then carries `partial_sums` (this shard's raw per-bin sums by GLOBAL bin) for sharded_groupby_sum."""
     G, rank = _world(group)
     cols = [ops.as_col(c) for c in key_cols]
     n = ops.nrows(cols[0])
     if len(cols) == 1 and SEEDED and hasattr(ops, "stream") and ops.can_stream(cols[0]):
-        g = _sharded_groupby_seeded(ops, cols[0], filter, group)
+        g = _sharded_groupby_seeded(ops, cols[0], filter, group, sum_values)
         if g is not None:
             return g
         # a shard holds more unique keys than the seeded table was provisioned for: every rank takes the generic path
@@ -300,7 +304,7 @@ def sharded_groupby(ops, key_cols, filter=None, group=None) -> ShardedGrouping:
     return ShardedGrouping(ops, gikey, ready, ik, u, table, ifirst_global, int(U), row_off[rank], sum(ns), us)
 
 
-def _sharded_groupby_seeded(ops, col, filter, group) -> ShardedGrouping:
+def _sharded_groupby_seeded(ops, col, filter, group, sum_values=None) -> ShardedGrouping:
     """Single-key shards, seeded: global bin ids come out of the hash pass itself, no per-row re-index.
 
     Global first-appearance order lists every key of shard 0 first (in shard 0's own order).  Shard 0 therefore groups
@@ -323,8 +327,16 @@ def _sharded_groupby_seeded(ops, col, filter, group) -> ShardedGrouping:
     nmax = max(ns) if ns else 0
     max_unique = max(SEEDED_MIN_UNIQUE, nmax // 16, 1)
     S = min(ns[0], SEED_ROWS) & ~127 if ns[0] > SEED_ROWS else ns[0]
-    st = ops.stream(max_unique, max(nmax, 1))
+    fused = sum_values is not None
+    vcol = ops.as_col(sum_values) if fused else None
+    st = ops.stream(max_unique, max(nmax, 1), with_sums=True) if fused else ops.stream(max_unique, max(nmax, 1))
     ikey = ops.empty_ikey(n)
+
+    def push(lo_, hi_, out):
+        if fused:
+            st.push(ops.slice_rows(col, lo_, hi_), ops.slice_filter(filter, lo_, hi_), lo_, out, values=ops.slice_rows(vcol, lo_, hi_))
+        else:
+            st.push(ops.slice_rows(col, lo_, hi_), ops.slice_filter(filter, lo_, hi_), lo_, out)
 
     # A push that runs out of table room fails on that rank alone; the failure is carried by the next collective
     # every rank takes part in (u0 = -1 / late = -1), so that all ranks leave the seeded path together.
@@ -334,7 +346,7 @@ def _sharded_groupby_seeded(ops, col, filter, group) -> ShardedGrouping:
     failed = False
     if rank == 0:
         try:
-            st.push(ops.slice_rows(col, 0, S), ops.slice_filter(filter, 0, S), 0, ikey[:S] if S else None)
+            push(0, S, ikey[:S] if S else None)
         except overflow:
             failed = True
     u0_t = ops.tensor([-1 if failed else (st.unique_count if rank == 0 else 0)], dtype=torch.int64)
@@ -362,7 +374,7 @@ def _sharded_groupby_seeded(ops, col, filter, group) -> ShardedGrouping:
                 raise RuntimeError("sharded_groupby: the broadcast seed holds duplicate keys")
         lo = S if rank == 0 else 0
         if n > lo:
-            st.push(ops.slice_rows(col, lo, n), ops.slice_filter(filter, lo, n), lo, ikey[lo:n])
+            push(lo, n, ikey[lo:n])
     except overflow:
         failed = True
     ikey = ikey[:n]
@@ -380,7 +392,10 @@ def _sharded_groupby_seeded(ops, col, filter, group) -> ShardedGrouping:
     if total_late == 0:
         tick.mark("late check")
         tick.report()
-        return ShardedGrouping(ops, ikey, None, ikey, u0, None, seed_first, u0, row_off[rank], sum(ns), [u0] * G)
+        g = ShardedGrouping(ops, ikey, None, ikey, u0, None, seed_first, u0, row_off[rank], sum(ns), [u0] * G)
+        if fused:
+            g.partial_sums = ops.to_torch(st.sums())  # bins are global already: ready for the all-reduce
+        return g
     ifk = ops.to_torch(st.ifirstkey)
     late_rows = ifk[u0:U_r]
     late_keys = ops.take_rows(col, late_rows)
@@ -928,6 +943,13 @@ def sharded_group_from_lexsort(ops, key_cols, ascending=True, group=None, replic
 def sharded_groupby_sum(key_cols, values, group=None, ops=None):
     """bench.py's multi-GPU step: sharded hash grouping + GB_SUM.  -> (ikey, ifirstkey, U, sums[U+1])."""
     ops = ops or CudaOps()
-    g = sharded_groupby(ops, key_cols, None, group)
+    g = sharded_groupby(ops, key_cols, None, group, sum_values=values)
+    if g.partial_sums is not None:
+        # the grouping pass summed the shard as it went (fused kernel) and its bins are global: one all-reduce is left
+        s = _combine("sum", {"v": g.partial_sums}, g.unique_count + 1, False, group, ALLTOALL_MIN_BINS)["v"]
+        vcol = ops.as_col(values)
+        if ops.is_f32(vcol):
+            s = s.to(torch.float32)
+        return g.ikey, g.ifirstkey, g.unique_count, s
     s = sharded_reduce(ops, values, g, GB.GB_SUM, group)  # runs while the re-index pass is still on its side stream
     return g.ikey, g.ifirstkey, g.unique_count, s

@@ -246,6 +246,19 @@ def _ws(nbytes: int) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=_device())
 
 
+def _cutoffs_dev(cutoffs, n):
+    """cutoffs (int64 cumulative row ends) validated on the host and staged on the device, with the partition id of
+    every row.  -> (host int64 array, device int64 tensor, pid int32 tensor[n])"""
+    cut = np.ascontiguousarray(np.asarray(cutoffs.cpu() if isinstance(cutoffs, torch.Tensor) else cutoffs), dtype=np.int64)
+    if cut.ndim != 1 or len(cut) == 0 or cut[-1] != n or cut[0] < 0 or (np.diff(cut) < 0).any():
+        raise ValueError("cutoffs must be a non-decreasing 1-D int64 array whose last entry is the row count")
+    dev = _device()
+    cdev = torch.from_numpy(cut).to(dev)
+    pid = torch.empty(max(n, 4), dtype=torch.int32, device=dev)
+    check(lib.rtb_partition_ids(n, C.c_void_p(cdev.data_ptr()), len(cut), C.c_void_p(pid.data_ptr()), _stream()))
+    return cut, cdev, pid[:n]
+
+
 def _as_list(list_arrays):
     if isinstance(list_arrays, (np.ndarray, torch.Tensor, DevArray)):
         return [list_arrays]
@@ -412,15 +425,24 @@ class GroupByStream:
 
     `push(chunk)` returns the chunk's iKey; bins keep counting in first-appearance order across chunks, so the
     concatenation of the returned iKeys equals one MultiKeyGroupBy32 call on the concatenated keys.  Used by
-    riptable_b200.dist (seeded shards) and by the host-mode pipeline that overlaps PCIe copies with hashing."""
+    riptable_b200.dist (seeded shards) and by the host-mode pipeline that overlaps PCIe copies with hashing.
 
-    def __init__(self, max_unique: int, max_chunk_rows: int):
+    With `with_sums=True` the stream is the resumable form of MultiKeyGroupBySum32: `push(chunk, values=v)` also adds
+    every row's value to its bin (`sums()`), in the same pass; a push without values only creates bins."""
+
+    def __init__(self, max_unique: int, max_chunk_rows: int, with_sums: bool = False, func=GB_FUNCTIONS.GB_SUM, bin_low: int = 1):
         self.max_unique = int(max_unique)
         self.max_chunk_rows = int(max_chunk_rows)
         self.state = _lib.rtb_gb_state()
         self._started = False
         self.ifirst = DevArray.empty(self.max_unique, np.int32)
-        self._ws = _ws(lib.rtb_groupby_workspace_bytes(self.max_chunk_rows, self.max_unique, 1, 0))
+        self.with_sums, self.func, self.bin_low = bool(with_sums), int(func), int(bin_low)
+        self._vdtype = None
+        if self.with_sums:
+            self._acc = torch.empty(self.max_unique + 1, dtype=torch.int64, device=_device())
+            self._ws = _ws(lib.rtb_groupby_sum_chunk_workspace_bytes(self.max_chunk_rows, self.max_unique))
+        else:
+            self._ws = _ws(lib.rtb_groupby_workspace_bytes(self.max_chunk_rows, self.max_unique, 1, 0))
 
     @property
     def unique_count(self) -> int:
@@ -430,7 +452,12 @@ class GroupByStream:
     def ifirstkey(self) -> torch.Tensor:
         return self.ifirst.torch()[: self.unique_count]
 
-    def push(self, keys, filter=None, row_offset: int = 0, out=None):
+    def sums(self) -> torch.Tensor:
+        """Raw accumulators [unique_count + 1]: float64 for float value columns, int64 for integer ones."""
+        a = self._acc[: self.unique_count + 1]
+        return a.view(torch.float64) if self._vdtype is not None and self._vdtype.kind == "f" else a
+
+    def push(self, keys, filter=None, row_offset: int = 0, out=None, values=None):
         k = _to_dev(keys)
         if k.n > self.max_chunk_rows:
             raise ValueError(f"chunk of {k.n} rows exceeds max_chunk_rows={self.max_chunk_rows}")
@@ -438,10 +465,29 @@ class GroupByStream:
         ik = out if out is not None else torch.empty(max(k.n, 4), dtype=torch.int32, device=_device())
         needed = C.c_int64(0)
         col = _col(k)
-        rc_ = lib.rtb_multikey_groupby32_chunk(
-            C.byref(col), k.n, C.c_void_p(f.ptr) if f is not None else None, C.c_void_p(ik.data_ptr()),
-            C.c_void_p(self.ifirst.ptr), self.max_unique, int(row_offset), C.byref(self.state), int(self._started),
-            C.byref(needed), C.c_void_p(self._ws.data_ptr()), self._ws.numel(), _stream())
+        if self.with_sums:
+            v, vcode = None, dtype_code(self._vdtype) if self._vdtype is not None else RTB_I32
+            if values is not None:
+                v = _to_dev(values)
+                if v.n != k.n:
+                    raise ValueError("GroupByStream.push: values and keys differ in length")
+                if v.dtype.kind not in "biuf" or v.dtype == np.float16:
+                    raise TypeError(f"GroupByStream.push: {v.dtype} cannot be summed")
+                if self._vdtype is not None and (self._vdtype.kind == "f") != (v.dtype.kind == "f"):
+                    raise TypeError("GroupByStream.push: float and integer value chunks cannot share accumulators")
+                self._vdtype, vcode = v.dtype, dtype_code(v.dtype)
+            rc_ = lib.rtb_multikey_groupby_sum32_chunk(
+                C.byref(col), k.n, C.c_void_p(f.ptr) if f is not None else None, C.c_void_p(v.ptr) if v is not None else None,
+                vcode, self.func, self.bin_low, C.c_void_p(ik.data_ptr()), C.c_void_p(self.ifirst.ptr), self.max_unique,
+                C.c_void_p(self._acc.data_ptr()), int(row_offset), C.byref(self.state), int(self._started), C.byref(needed),
+                C.c_void_p(self._ws.data_ptr()), self._ws.numel(), _stream())
+        else:
+            if values is not None:
+                raise ValueError("GroupByStream.push: create the stream with with_sums=True to sum values")
+            rc_ = lib.rtb_multikey_groupby32_chunk(
+                C.byref(col), k.n, C.c_void_p(f.ptr) if f is not None else None, C.c_void_p(ik.data_ptr()),
+                C.c_void_p(self.ifirst.ptr), self.max_unique, int(row_offset), C.byref(self.state), int(self._started),
+                C.byref(needed), C.c_void_p(self._ws.data_ptr()), self._ws.numel(), _stream())
         check(rc_, needed.value)
         self._started = True
         return ik[: k.n]
@@ -544,10 +590,41 @@ def GroupFromBinCount(ikey, nCountGroup):
 
 def GroupByPack32(ikey, _unused, n, cutoffs=None):
     """-> (iGroup, iFirstGroup, nCountGroup) (riptable/rt_numpy.py:1972)."""
-    if cutoffs is not None:
-        raise NotImplementedError("GroupByPack32(cutoffs=) is unpinned by the reference tests and not provided")
     device_mode = _is_device(ikey)
-    ig, ifg, cnt = _pack(_ikey_dev(ikey), int(n))
+    if cutoffs is None:
+        ig, ifg, cnt = _pack(_ikey_dev(ikey), int(n))
+        return _from_dev(ig, device_mode), _from_dev(ifg, device_mode), _from_dev(cnt, device_mode)
+    # cutoffs: every partition is packed as an array of its own (iKey numbered per partition, as groupbyhash(cutoffs=)
+    # numbers it): U_p + 1 bins, U_p = its largest iKey.  iGroup holds partition-relative rows, partition after
+    # partition; iFirstGroup / nCountGroup are the per-partition arrays laid end to end.  Unpinned by the reference's
+    # tests, derived from the pinned hash case (oracle.GroupByPack32).  One pack over composite bins does it all.
+    k = _ikey_dev(ikey)
+    cut, cdev, pid = _cutoffs_dev(cutoffs, k.n)
+    P = len(cut)
+    dev = _device()
+    umax = torch.empty(P, dtype=torch.int32, device=dev)
+    bad = torch.empty(1, dtype=torch.int32, device=dev)
+    check(lib.rtb_partition_max_ikey(C.c_void_p(k.ptr), dtype_code(k.dtype), k.n, C.c_void_p(pid.data_ptr()), P,
+                                     C.c_void_p(umax.data_ptr()), C.c_void_p(bad.data_ptr()), _stream()))
+    if int(bad.item()):
+        raise ValueError("GroupByPack32: negative ikey values")
+    nb_p = umax.to(torch.int64) + 1                      # bins of each partition, its slot 0 included
+    off_incl = torch.cumsum(nb_p, 0)
+    bin_off = (off_incl - nb_p).contiguous()
+    nbins = int(off_incl[-1].item())
+    if nbins >= 2**31:
+        raise ValueError("GroupByPack32: too many bins")
+    comp = DevArray.empty(k.n, np.int32)
+    check(lib.rtb_partition_compose_ikey(C.c_void_p(k.ptr), dtype_code(k.dtype), k.n, C.c_void_p(pid.data_ptr()),
+                                         C.c_void_p(bin_off.data_ptr()), C.c_void_p(comp.ptr), _stream()))
+    ig, ifg, cnt = _pack(comp, nbins)
+    if k.n:
+        check(lib.rtb_partition_shift(C.c_void_p(ig.ptr), k.n, C.c_void_p(pid.data_ptr()), C.c_void_p(cdev.data_ptr()), P, 1, _stream()))
+    # positions -> partition-relative positions (a table of `nbins` entries)
+    starts = torch.cat([cdev.new_zeros(1), cdev[:-1]])
+    part_of_bin = torch.searchsorted(off_incl, torch.arange(nbins, device=dev, dtype=torch.int64), right=True)
+    ifg_t = ifg.torch()
+    ifg_t -= starts[part_of_bin].to(torch.int32)
     return _from_dev(ig, device_mode), _from_dev(ifg, device_mode), _from_dev(cnt, device_mode)
 
 
@@ -745,9 +822,9 @@ def MakeiNext(key, n, mode=0):
 # ==================================================================================================
 # a11  rc.LexSort32 / rc.LexSort64 (riptable/rt_numpy.py:2670-2671, 2200-2202)
 def LexSort32(list_arrays, cutoffs=None, index=None, ascending=True):
-    """Stable lexicographic argsort; the LAST array is the primary key (numpy.lexsort convention), NaN last."""
-    if cutoffs is not None:
-        raise NotImplementedError("LexSort32(cutoffs=) is unpinned by the reference tests and not provided")
+    """Stable lexicographic argsort; the LAST array is the primary key (numpy.lexsort convention), NaN last.
+    cutoffs: every partition is sorted as an array of its own, out[c[p-1]:c[p]] = its partition-relative order
+    (unpinned by the reference's tests; derived from the pinned hash case, see oracle.LexSort32)."""
     list_arrays = _as_list(list_arrays)
     if not isinstance(list_arrays, list) or len(list_arrays) == 0:
         raise ValueError("lexsort needs a list of arrays")
@@ -764,6 +841,16 @@ def LexSort32(list_arrays, cutoffs=None, index=None, ascending=True):
         asc = np.asarray([1 if a else 0 for a in ascending], dtype=np.int8)
         if len(asc) != len(cols):
             raise ValueError("ascending must have one entry per key")
+    cut = None
+    if cutoffs is not None:
+        if index is not None:
+            raise ValueError("lexsort: cutoffs and index (a filter) cannot be combined")
+        if n == 0:
+            return _from_dev(DevArray.empty(0, np.int32), device_mode)
+        # the partition id is one more key, more significant than all others: one sort, partitions end to end
+        cut, cdev, pid = _cutoffs_dev(cutoffs, n)
+        cols = cols + [_to_dev(pid)]
+        asc = np.concatenate([asc, np.ones(1, dtype=np.int8)])
     idx = None
     m = n
     if index is not None:
@@ -779,6 +866,8 @@ def LexSort32(list_arrays, cutoffs=None, index=None, ascending=True):
     check(lib.rtb_lexsort32(_cols(cols), len(cols), n, C.c_void_p(idx.ptr) if idx is not None else None, m,
                             asc.ctypes.data_as(C.POINTER(C.c_int8)), C.c_void_p(out.ptr), C.c_void_p(ws.data_ptr()),
                             ws.numel(), _stream()))
+    if cut is not None:  # global rows -> partition-relative rows (position i lies in partition pid[i])
+        check(lib.rtb_partition_shift(C.c_void_p(out.ptr), n, C.c_void_p(pid.data_ptr()), C.c_void_p(cdev.data_ptr()), len(cut), 1, _stream()))
     return _from_dev(out, device_mode)
 
 
@@ -809,9 +898,10 @@ def LexSort64(list_arrays, cutoffs=None, index=None, ascending=True):
 # ==================================================================================================
 # a12  rc.GroupFromLexSort (riptable/rt_numpy.py:2207)
 def GroupFromLexSort(iGroup, value_array, cutoffs=None, base_index=1):
-    """-> (iKey int32[N], iFirstKey int32[U], nCountGroup int32[U+1] with slot 0 = 0)."""
-    if cutoffs is not None:
-        raise NotImplementedError("GroupFromLexSort(cutoffs=) is unpinned by the reference tests and not provided")
+    """-> (iKey int32[N], iFirstKey int32[U], nCountGroup int32[U+1] with slot 0 = 0).
+    cutoffs: -> (iKey, iFirstKey, nCountGroup, nUniqueCutoffs): per-partition results laid end to end -- bin numbering
+    restarts in every partition, iFirstKey holds partition-relative rows, nUniqueCutoffs the cumulative unique counts
+    (unpinned by the reference's tests; derived from the pinned hash case, see oracle.GroupFromLexSort)."""
     if isinstance(value_array, np.ndarray) and value_array.dtype.names:
         value_array = [np.ascontiguousarray(value_array[nm]) for nm in value_array.dtype.names]
     vals = _as_list(value_array)
@@ -822,18 +912,42 @@ def GroupFromLexSort(iGroup, value_array, cutoffs=None, base_index=1):
     cols = [_to_dev(v) for v in vals]
     n = cols[0].n
     m = ig.n
+    cut = None
+    base = int(base_index)
+    if cutoffs is not None:
+        if m != n:
+            raise ValueError("GroupFromLexSort: cutoffs need an iGroup that covers every row (no filter)")
+        cut, cdev, pid = _cutoffs_dev(cutoffs, n)
+        if n:
+            # partition-relative sorted rows -> global rows; the partition id becomes one more key column, so bins never
+            # run across a partition boundary
+            g = ig.torch().clone()
+            check(lib.rtb_partition_shift(C.c_void_p(g.data_ptr()), n, C.c_void_p(pid.data_ptr()), C.c_void_p(cdev.data_ptr()), len(cut), 0, _stream()))
+            ig = _to_dev(g)
+            cols = cols + [_to_dev(pid)]
+        base = 1
     ikey = DevArray.empty(n, np.int32)
     ifk = DevArray.empty(max(m, 1), np.int32)
     cnt = DevArray.empty(m + 1, np.int32)
     u = C.c_int64(0)
     ws = _ws(lib.rtb_group_from_lexsort_workspace_bytes(n, m))
-    check(lib.rtb_group_from_lexsort(C.c_void_p(ig.ptr), m, _cols(cols), len(cols), n, int(base_index), C.c_void_p(ikey.ptr),
+    check(lib.rtb_group_from_lexsort(C.c_void_p(ig.ptr), m, _cols(cols), len(cols), n, base, C.c_void_p(ikey.ptr),
                                      C.c_void_p(ifk.ptr), C.c_void_p(cnt.ptr), C.byref(u), C.c_void_p(ws.data_ptr()),
                                      ws.numel(), _stream()))
     U = int(u.value)
     ifk = DevArray(ifk.buf, np.int32, U)
     cnt = DevArray(cnt.buf, np.int32, U + 1)
-    return _from_dev(ikey, device_mode), _from_dev(ifk, device_mode), _from_dev(cnt, device_mode)
+    if cut is None:
+        return _from_dev(ikey, device_mode), _from_dev(ifk, device_mode), _from_dev(cnt, device_mode)
+    P = len(cut)
+    ucount = torch.empty(P, dtype=torch.int32, device=_device())
+    check(lib.rtb_partition_count_rows(C.c_void_p(ifk.ptr), U, C.c_void_p(pid.data_ptr()), P, C.c_void_p(ucount.data_ptr()), _stream()))
+    ucut = torch.cumsum(ucount.to(torch.int64), 0)
+    bin_base = (ucut - ucount).to(torch.int32).contiguous()
+    check(lib.rtb_partition_localize(C.c_void_p(ikey.ptr), n, C.c_void_p(ifk.ptr), U, C.c_void_p(pid.data_ptr()),
+                                     C.c_void_p(bin_base.data_ptr()), C.c_void_p(cdev.data_ptr()), P, int(base_index), _stream()))
+    return (_from_dev(ikey, device_mode), _from_dev(ifk, device_mode), _from_dev(cnt, device_mode),
+            ucut if device_mode else ucut.cpu().numpy())
 
 
 # ==================================================================================================

@@ -63,7 +63,12 @@ def groupbylex(rc, list_arrays, filter=None, cutoffs=None, base_index=1, rec=Fal
         index = np.flatnonzero(filter).astype(np.int32)
         filterfalse = np.flatnonzero(~filter).astype(np.int32)
     iGroup = rc.LexSort32(list_arrays, cutoffs=cutoffs, index=index)
-    iKey, iFirstKey, nCountGroup = rc.GroupFromLexSort(iGroup, value_array, cutoffs=cutoffs, base_index=base_index)
+    retval = rc.GroupFromLexSort(iGroup, value_array, cutoffs=cutoffs, base_index=base_index)
+    nUniqueCutoffs = None
+    if len(retval) == 3:  # rt_numpy.py:2209-2212
+        iKey, iFirstKey, nCountGroup = retval
+    else:
+        iKey, iFirstKey, nCountGroup, nUniqueCutoffs = retval
     if base_index == 0:
         iKey = iKey + 1
     else:
@@ -74,8 +79,11 @@ def groupbylex(rc, list_arrays, filter=None, cutoffs=None, base_index=1, rec=Fal
         nCountGroup[0] = len(filterfalse)
         iKey[filterfalse] = 0
         iFirstGroup[0] = len(index)
-    return {"iKey": iKey, "iFirstKey": iFirstKey, "unique_count": len(iFirstKey), "iGroup": iGroup,
-            "iFirstGroup": iFirstGroup, "nCountGroup": nCountGroup}
+    d = {"iKey": iKey, "iFirstKey": iFirstKey, "unique_count": len(iFirstKey), "iGroup": iGroup,
+         "iFirstGroup": iFirstGroup, "nCountGroup": nCountGroup}
+    if nUniqueCutoffs is not None:
+        d["nUniqueCutoffs"] = nUniqueCutoffs
+    return d
 
 
 def hstack_reindex(mod_groupby, mod_reindex, keys, cuts):

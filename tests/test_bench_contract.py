@@ -28,6 +28,9 @@ def test_reference_arm_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+    # the CPU sample is fixed-size: asking for more steps must not shrink it
+    d5 = _run(["--impl", "reference", "--steps", "5", "--warmup", "1", "--cpu-rows", "1000000", "--uniques", "1000"], 300)
+    assert d["config"]["rows_per_step"] == d5["config"]["rows_per_step"] == 1_000_000 == d5["cpu_baseline"]["rows"]
 
 
 @pytest.mark.gpu
@@ -39,3 +42,5 @@ def test_gpu_arm_line():
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
     assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
+    assert d["cpu_baseline"]["parity"].startswith("ok"), d["cpu_baseline"]["parity"]
+    assert d["two_call"]["value"] > 0 and d["config"]["step"].startswith("one rc.MultiKeyGroupBySum32")

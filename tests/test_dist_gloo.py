@@ -127,8 +127,8 @@ class OracleOps:
         return torch.as_tensor(x, dtype=dtype)
 
     # --- resumable single-key grouping (stand-in for rc.GroupByStream) ---------------------------------------
-    def stream(self, max_unique, max_chunk_rows):
-        return _OracleStream(max_unique)
+    def stream(self, max_unique, max_chunk_rows, with_sums=False):
+        return _OracleStream(max_unique, with_sums)
 
     def can_stream(self, col):
         return col.dtype.kind in "biuf" and col.dtype.itemsize in (1, 2, 4, 8)
@@ -149,10 +149,15 @@ class OracleOps:
 class _OracleStream:
     """Chunked first-appearance grouping restated with the oracle: group [uniques so far ; chunk] in one call."""
 
-    def __init__(self, max_unique=1 << 62):
+    def __init__(self, max_unique=1 << 62, with_sums=False):
         self.uniq = None
         self.max_unique = max_unique
+        self.with_sums = with_sums
+        self.acc = np.zeros(1)
         self.first = np.zeros(0, np.int32)
+
+    def sums(self):
+        return torch.from_numpy(self.acc.copy())
 
     @property
     def unique_count(self):
@@ -162,7 +167,7 @@ class _OracleStream:
     def ifirstkey(self):
         return self.first
 
-    def push(self, keys, filter=None, row_offset=0, out=None):
+    def push(self, keys, filter=None, row_offset=0, out=None, values=None):
         keys = np.asarray(keys)
         u = self.unique_count
         allk = keys if self.uniq is None else np.concatenate([self.uniq, keys])
@@ -176,6 +181,13 @@ class _OracleStream:
         self.first = np.concatenate([self.first, (ifk[u:] - u + row_offset).astype(np.int32)])
         self.uniq = allk[ifk]
         res = torch.from_numpy(ik[u:].copy())
+        if self.with_sums:
+            acc = np.zeros(U + 1, dtype=self.acc.dtype if values is None else (np.float64 if np.asarray(values).dtype.kind == "f" else np.int64))
+            acc[: len(self.acc)] = self.acc
+            if values is not None:
+                part = orc.GroupByAll32([np.asarray(values)], ik[u:], U, [0], [1], [U + 1], 0)[0]
+                acc += part.astype(acc.dtype)
+            self.acc = acc
         if out is not None:
             out[: len(res)] = res
         return res
@@ -220,6 +232,11 @@ def _worker(rank, world, port, n, cuts, a2a, q):
             if name in ("one", "filt"):
                 pk = rd.sharded_pack(ops, g)
                 res["pack"] = {k2_: (_np(v2_).copy() if hasattr(v2_, "shape") else v2_) for k2_, v2_ in pk.items()}
+            if filt is None:
+                gi, gf, gu, gs = rd.sharded_groupby_sum([k[lo:hi] for k in keys], np.nan_to_num(v[lo:hi]), ops=ops)
+                res["gbsum"] = (_np(gi).copy(), _np(gf).copy(), gu, _np(gs).copy())
+                gi, gf, gu, gs = rd.sharded_groupby_sum([k[lo:hi] for k in keys], vi[lo:hi], ops=ops)
+                res["gbsum_i"] = (_np(gi).copy(), _np(gs).copy())
             res["cumsum_v"] = _np(rd.sharded_cumsum(ops, np.nan_to_num(v[lo:hi]), g)).copy()
             res["cumsum_vi"] = _np(rd.sharded_cumsum(ops, vi[lo:hi], g, f[lo:hi])).copy()
             res["cumsum_f32"] = _np(rd.sharded_cumsum(ops, np.nan_to_num(v[lo:hi]).astype(np.float32), g, f[lo:hi])).copy()
@@ -350,6 +367,16 @@ def test_sharded_groupby_and_reduce_world2(cuts, a2a):
                 hi_p = int(ifg[b1]) if b1 < len(ifg) else len(ig)
                 np.testing.assert_array_equal(pk["iGroup_owned"], ig[lo_p:hi_p], err_msg=f"{name} pack rank {r}")
             assert got[0][name]["pack"]["bin_hi"] == got[1][name]["pack"]["bin_lo"]
+        if filt is None:
+            np.testing.assert_array_equal(np.concatenate([got[r][name]["gbsum"][0] for r in range(2)]), eik)
+            np.testing.assert_array_equal(np.concatenate([got[r][name]["gbsum_i"][0] for r in range(2)]), eik)
+            for r in range(2):
+                np.testing.assert_array_equal(got[r][name]["gbsum"][1], eifk)
+                assert got[r][name]["gbsum"][2] == eu
+                exp = orc.GroupByAll32([np.nan_to_num(v)], eik, eu, [0], [1], [eu + 1], 0)[0]
+                np.testing.assert_allclose(got[r][name]["gbsum"][3][1:], exp[1:], rtol=1e-12, atol=1e-9)
+                exp = orc.GroupByAll32([vi], eik, eu, [0], [1], [eu + 1], 0)[0]
+                np.testing.assert_array_equal(got[r][name]["gbsum_i"][1][1:], exp[1:])
         lo_, hi_ = cuts[0], cuts[2]
         full = lambda key: np.concatenate([got[r][name][key] for r in range(2)])  # noqa: E731
         exp = orc.EmaAll32([np.nan_to_num(v)], eik, eu, 300, (0.0, None, None, None))[0]

@@ -593,3 +593,35 @@ def test_16_byte_aligned_slices_take_the_direct_path(rc):
     ik2, ifk2, u2, s2 = rc.MultiKeyGroupBySum32([k], v)
     np.testing.assert_array_equal(ik2.cpu().numpy(), ok)
     np.testing.assert_allclose(s2.cpu().numpy()[1:], exp[1:], rtol=1e-12, atol=1e-9)
+
+
+def test_groupby_stream_with_sums(rc):
+    """The resumable fused call: chunks pushed one after the other == one MultiKeyGroupBySum32 over all rows; a push
+    without values (a pre-loaded seed) creates bins whose sums start at zero."""
+    import torch
+
+    rng = np.random.default_rng(21)
+    n = 5_000_000
+    uv = rng.integers(-(2**62), 2**62, 30_000)
+    k = uv[rng.integers(0, 30_000, n)]
+    # a burst of all-distinct keys that overflows the settled table: the fused round of that chunk aborts, its partial
+    # sums are rolled back from the snapshot, and the round is redone unfused
+    k[4_000_000:] = 2**62 + 5 * np.arange(1_000_000)
+    for vdt in (np.float64, np.float32, np.int32):
+        v = (rng.random(n) * 2 - 1).astype(vdt) if np.dtype(vdt).kind == "f" else rng.integers(-50, 50, n).astype(vdt)
+        seed = uv[:1000].copy()
+        st = rc.GroupByStream(1 << 20, 2_000_000, with_sums=True)
+        st.push(torch.from_numpy(seed).cuda())
+        assert st.unique_count == 1000
+        parts, cuts = [], [0, 1_999_872, 3_999_744, n]
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            parts.append(st.push(torch.from_numpy(k[a:b]).cuda(), None, a, None, values=torch.from_numpy(v[a:b]).cuda()).clone())
+        ok, ofk, ou = orc.MultiKeyGroupBy32([np.concatenate([seed, k])])
+        np.testing.assert_array_equal(torch.cat(parts).cpu().numpy(), ok[1000:])
+        assert st.unique_count == ou
+        exp = orc.GroupByAll32([v], ok[1000:], ou, [0], [1], [ou + 1], 0)[0]
+        got = st.sums().cpu().numpy()
+        if np.dtype(vdt).kind == "f":
+            np.testing.assert_allclose(got[1:], exp[1:].astype(np.float64), rtol=1e-5 if vdt == np.float32 else 1e-12, atol=1e-9 if vdt == np.float64 else 1e-3)
+        else:
+            np.testing.assert_array_equal(got[1:], exp[1:])

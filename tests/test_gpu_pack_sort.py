@@ -605,3 +605,96 @@ def test_lex_partition_matches_sorted_rank(rc):
         got = rc.LexPartition([torch.from_numpy(c).cuda() if c.dtype.kind not in "SU" else rc._to_dev(c) for c in cols],
                               [c[srt] for c in cols], srt.astype(np.int64) + row_offset, row_offset, asc).cpu().numpy()
         np.testing.assert_array_equal(got, exp, err_msg=str(combo))
+
+
+# ---- cutoffs= on the sort / pack entry points (unpinned by the reference's tests; derived semantics in the oracle) ----
+def _cut_cases(n, rng):
+    yield np.array([n], dtype=np.int64)
+    if n >= 4:
+        yield np.array([n // 3, n // 3, (2 * n) // 3, n], dtype=np.int64)  # with an empty partition
+        yield np.sort(np.r_[rng.integers(0, n, 40), n]).astype(np.int64)
+    if n <= 5000:
+        yield np.arange(1, n + 1, dtype=np.int64)                           # one row per partition
+
+
+@pytest.mark.parametrize("n", [1, 37, 4099, 300_007])
+def test_lexsort_and_group_from_lexsort_with_cutoffs(rc, n):
+    rng = np.random.default_rng(n)
+    a = rng.integers(-3, 4, n).astype(np.int16)
+    f = np.round(rng.random(n) * 5)
+    f[rng.random(n) < 0.1] = np.nan
+    s = rng.choice(np.array([b"", b"x", b"xy", b"zzz"], dtype="S3"), n)
+    for cut in _cut_cases(n, rng):
+        for keys, asc in (([a], True), ([s, f, a], True), ([f, a], [False, True])):
+            got = rc.LexSort32(keys, cutoffs=cut, ascending=asc)
+            exp = orc.LexSort32(keys, cutoffs=cut, ascending=asc)
+            assert got.dtype == np.int32
+            np.testing.assert_array_equal(got, exp)
+        vals = [a, f, s]
+        ig = orc.LexSort32(vals[::-1], cutoffs=cut)
+        for base in (1, 0):
+            gik, gifk, gcnt, gucut = rc.GroupFromLexSort(ig, vals, cutoffs=cut, base_index=base)
+            eik, eifk, ecnt, eucut = orc.GroupFromLexSort(ig, vals, cutoffs=cut, base_index=base)
+            np.testing.assert_array_equal(gik, eik)
+            np.testing.assert_array_equal(gifk, eifk)
+            np.testing.assert_array_equal(gcnt, ecnt)
+            np.testing.assert_array_equal(gucut, eucut)
+        # the same partitions through the hash route find the same number of groups per partition
+        _, (_, hucut), hu = orc.MultiKeyGroupBy32(vals, cutoffs=cut)
+        np.testing.assert_array_equal(gucut, hucut)
+    with pytest.raises(ValueError):
+        rc.LexSort32([a], cutoffs=np.array([n + 1], dtype=np.int64))
+    if n > 1:
+        with pytest.raises(ValueError):
+            rc.LexSort32([a], cutoffs=np.array([n], dtype=np.int64), index=np.arange(n // 2, dtype=np.int32))
+
+
+@pytest.mark.parametrize("n", [1, 50, 5001, 400_003])
+@pytest.mark.parametrize("kdt", [np.int8, np.int32, np.int64])
+def test_groupby_pack32_with_cutoffs(rc, n, kdt):
+    rng = np.random.default_rng(n + 1)
+    key = rng.integers(0, 60, n)
+    for cut in _cut_cases(n, rng):
+        ik, _, u = orc.MultiKeyGroupBy32([key], 0, rng.random(n) < 0.9, 2, cutoffs=cut)  # per-partition numbering, some 0s
+        ik = ik.astype(kdt)
+        gig, gifg, gcnt = rc.GroupByPack32(ik, None, u + 1, cutoffs=cut)
+        eig, eifg, ecnt = orc.GroupByPack32(ik, None, u + 1, cutoffs=cut)
+        np.testing.assert_array_equal(gig, eig)
+        np.testing.assert_array_equal(gifg, eifg)
+        np.testing.assert_array_equal(gcnt, ecnt)
+    # without cutoffs it stays BinCount(pack=True)
+    ik, _, u = orc.MultiKeyGroupBy32([key])
+    gig, gifg, gcnt = rc.GroupByPack32(ik.astype(kdt), None, u + 1)
+    ecnt, eig, eifg = orc.BinCount(ik, u + 1, pack=True)
+    np.testing.assert_array_equal(gig, eig)
+    np.testing.assert_array_equal(gifg, eifg)
+    np.testing.assert_array_equal(gcnt, ecnt)
+
+
+def test_riptable_glue_with_cutoffs(rc):
+    """Grouping.pack_by_group's groupbypack(iKey, None, U + 1, cutoffs=pcutoffs) (riptable/rt_grouping.py:2407) and
+    groupbylex(cutoffs=) as riptable's Python glue drives them (riptable/rt_numpy.py:1945-1972, 2157-2251): the rc
+    module and the oracle must agree on every entry of the dicts."""
+    import rt_glue
+
+    rng = np.random.default_rng(8)
+    n = 50_000
+    a = rng.integers(0, 40, n).astype(np.int32)
+    b = rng.choice(np.array([b"u", b"vv", b"w"], dtype="S2"), n)
+    cut = np.array([10_000, 10_000, 32_123, n], dtype=np.int64)
+    hk, _, hu = orc.MultiKeyGroupBy32([a, b], cutoffs=cut)
+    got, exp = rt_glue.groupbypack(rc, hk, None, hu + 1, cutoffs=cut), rt_glue.groupbypack(orc, hk, None, hu + 1, cutoffs=cut)
+    for k in exp:
+        np.testing.assert_array_equal(got[k], exp[k], err_msg=f"groupbypack {k}")
+    for fn, kw in ((rt_glue.groupbyhash, {"cutoffs": cut}), (rt_glue.groupbylex, {"cutoffs": cut})):
+        got, exp = fn(rc, [a, b], **kw), fn(orc, [a, b], **kw)
+        assert set(got) == set(exp)
+        for k in exp:
+            if exp[k] is None:
+                assert got[k] is None
+            elif isinstance(exp[k], tuple):
+                for x, y in zip(got[k], exp[k]):
+                    np.testing.assert_array_equal(x, y, err_msg=f"{fn.__name__} {k}")
+            else:
+                np.testing.assert_array_equal(got[k], exp[k], err_msg=f"{fn.__name__} {k}")
+    assert "nUniqueCutoffs" in rt_glue.groupbylex(rc, [a, b], cutoffs=cut)

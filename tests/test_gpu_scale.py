@@ -68,11 +68,58 @@ def test_c2_groupby_sum_min_max_count_1e9_rows(rc):
     assert U2 == U and bool((ik2 == ik).all()) and bool((ifk2 == ifk).all())
 
 
+def _categorical_route(rcm, key, val, enums):
+    """`Categorical(key).sum(val) / .mean(val)` restated (riptable/rt_grouping.py:944-987, 1009-1043): hash grouping,
+    uniques sorted, iKey re-indexed through ismember to the sorted order, down-cast by unique count, then the
+    per-bin reductions against that iKey."""
+    ik, ifk, u = rcm.MultiKeyGroupBy32([key], 0, None, 2)
+    uniques = key[ifk]
+    sortidx = rcm.LexSort32([uniques])                                   # _make_isortrows (rt_grouping.py:2204-2210)
+    _, ik = rcm.IsMemberCategorical(ik, (sortidx + 1).astype(ik.dtype))  # rt_grouping.py:963
+    ik = ik.astype(enums.int_dtype_from_len(u))                          # possibly_recast (rt_enum.py:666-679)
+    s = rcm.GroupByAll32([val], ik, u, [0], [1], [u + 1], 0)[0]
+    m = rcm.GroupByAll32([val], ik, u, [1], [1], [u + 1], 0)[0]
+    return ik, uniques[sortidx], u, s, m
+
+
+def test_c1_categorical_sum_mean_10m_rows_against_the_oracle(rc):
+    """configs[0] at its stated size, row for row against the oracle: 10 M rows, int32 key with 1 K uniques, f64 value
+    (recipe of SURVEY 8d: seed 12345, value = random * 1e10 - 0.5e10), through the Categorical route: the stored iKey
+    is int16 and the reductions run on the shared-memory path."""
+    from oracle import riptide_oracle as orc
+    from riptable_b200 import enums
+
+    rng = np.random.default_rng(12345)
+    n, u = 10_000_000, 1000
+    key = np.arange(u, dtype=np.int32)[rng.integers(0, u, n)]
+    val = rng.random(n) * 1e10 - 0.5e10
+    gik, gcat, gu, gs, gm = _categorical_route(rc, key, val, enums)
+    oik, ocat, ou, os_, om = _categorical_route(orc, key, val, enums)
+    assert gu == ou == u and gik.dtype == np.int16 == oik.dtype
+    np.testing.assert_array_equal(gik, oik)                                   # every row's bin, bit-exact
+    np.testing.assert_array_equal(gcat, ocat)
+    np.testing.assert_array_equal(gik, (np.searchsorted(gcat, key) + 1))      # ordered Categorical: bin = rank of the key
+    assert gs.dtype == np.float64 and gm.dtype == np.float64 and gs.shape == (u + 1,)
+    # 1e-12 relative to the data magnitude (the values are ~1e10 and mostly cancel inside a bin)
+    scale = np.abs(val).max() * np.sqrt(n / u)
+    np.testing.assert_allclose(gs[1:], os_[1:], rtol=1e-12, atol=1e-12 * scale)
+    np.testing.assert_allclose(gm[1:], om[1:], rtol=1e-12, atol=1e-12 * scale / (n / u))
+    np.testing.assert_allclose(gs[1:], np.bincount(gik, weights=val, minlength=u + 1)[1:], rtol=1e-12, atol=1e-12 * scale)
+    # the fused entry on the same column gives the unordered (first-appearance) grouping and the same sums, re-ordered
+    fik, fifk, fu, fs = rc.MultiKeyGroupBySum32([key], val)
+    eik, eifk, eu = orc.MultiKeyGroupBy32([key])
+    np.testing.assert_array_equal(fik, eik)
+    np.testing.assert_array_equal(fifk, eifk)
+    order = np.searchsorted(gcat, key[fifk]) + 1                               # first-appearance bin -> sorted bin
+    np.testing.assert_allclose(fs[1:], os_[order], rtol=1e-12, atol=1e-12 * scale)
+
+
 def test_c3_multikey_with_strings_nanmean_nanstd(rc):
-    """configs[2] at 1/5 scale (100 M rows): keys (int64, S16, int32), value f64 with 1 % NaN."""
+    """configs[2] at its stated size: 500 M rows, keys (int64 of 1e4 values, S16 of 1e3 strings, int32 of 5 values)
+    -> about 5e7 distinct tuples, value f64 with 1 % NaN, nanmean / nanstd."""
     import torch
 
-    n = 100_000_000
+    n = 500_000_000
     g = torch.Generator(device="cuda")
     g.manual_seed(3)
     k1 = torch.randint(0, 10_000, (n,), device="cuda", generator=g, dtype=torch.int64) * 1_000_003
@@ -87,6 +134,9 @@ def test_c3_multikey_with_strings_nanmean_nanstd(rc):
     assert U == int(torch.unique(combo).numel())
     assert bool((ifk[1:] > ifk[:-1]).all())
     assert bool((combo == combo[ifk.long()[ik.long() - 1]]).all())
+    assert 45_000_000 <= U <= 50_000_000
+    del combo, k1, s16, k3, sidx
+    torch.cuda.empty_cache()
     val = torch.rand(n, device="cuda", generator=g, dtype=torch.float64)
     val[torch.rand(n, device="cuda", generator=g) < 0.01] = float("nan")
     mean = rc.GroupByAll32([val], ik, U, [51], [1], [U + 1], 0)[0]
@@ -103,10 +153,12 @@ def test_c3_multikey_with_strings_nanmean_nanstd(rc):
 
 
 def test_c4_lexsort_three_keys_and_group_from_lexsort(rc):
-    """configs[3] at 1/5 scale (200 M rows): sort keys (int64 1e3 values, f64 with NaN, int32 1e6 values)."""
+    """configs[3] at its stated size: 1 B rows, sort keys (int64 of 1e3 values, f64 with 0.1 % NaN, int32 of 1e6
+    values), int64 primary; then GroupFromLexSort.  Verified in 100 M-row slices of the sorted order (sortedness under
+    np.lexsort's rules incl. NaN last, stability, permutation, bin boundaries) to keep the checker's memory bounded."""
     import torch
 
-    n = 200_000_000
+    n = 1_000_000_000
     g = torch.Generator(device="cuda")
     g.manual_seed(4)
     a = torch.randint(0, 1000, (n,), device="cuda", generator=g, dtype=torch.int64) - 500
@@ -114,43 +166,55 @@ def test_c4_lexsort_three_keys_and_group_from_lexsort(rc):
     f[torch.rand(n, device="cuda", generator=g) < 0.001] = float("nan")
     c = torch.randint(0, 1_000_000, (n,), device="cuda", generator=g, dtype=torch.int32)
     perm = rc.LexSort32([c, f, a])  # last key (a) primary
-    p = perm.long()
-    assert int(torch.bincount(p[:: max(1, n // 50_000_000)].clamp(0, 0)).sum()) > 0  # touches the result
+    assert perm.dtype == torch.int32 and perm.numel() == n
     chk = torch.zeros(n, dtype=torch.bool, device="cuda")
-    chk[p] = True
+    chk[perm.long()] = True
     assert bool(chk.all())  # a permutation
     del chk
-    sa, sf, sc = a[p], f[p], c[p]
-    nan2 = torch.isnan(sf)
-    fkey = torch.where(nan2, torch.full_like(sf, float("inf")), sf)
-    a_ok = sa[1:] >= sa[:-1]
-    same_a = sa[1:] == sa[:-1]
-    f_le = (fkey[1:] >= fkey[:-1]) & ~(nan2[:-1] & ~nan2[1:])
-    same_f = (sf[1:] == sf[:-1]) | (nan2[1:] & nan2[:-1])
-    c_ok = sc[1:] >= sc[:-1]
-    same_c = sc[1:] == sc[:-1]
-    stable = p[1:] > p[:-1]
-    assert bool(a_ok.all())
-    assert bool((~same_a | f_le).all())
-    assert bool((~(same_a & same_f) | c_ok).all())
-    assert bool((~(same_a & same_f & same_c) | stable).all())  # ties keep row order
     ik, ifk, cnt = rc.GroupFromLexSort(perm, [a, f, c], base_index=1)
     U = int(ifk.numel())
     assert int(cnt.sum()) == n and int(cnt[0]) == 0 and cnt.numel() == U + 1
-    new_group = torch.ones(n, dtype=torch.bool, device="cuda")
-    new_group[1:] = ~(same_a & same_f & same_c)
-    assert U == int(new_group.sum())
-    assert bool((ik[p] == torch.cumsum(new_group.int(), 0)).all())
+    step = 100_000_000
+    nbins = 0
+    for lo in range(0, n, step):
+        hi = min(n, lo + step)
+        p = perm[max(lo - 1, 0):hi].long()  # one row of overlap so that every adjacent pair is checked
+        sa, sf, sc = a[p], f[p], c[p]
+        nan2 = torch.isnan(sf)
+        fkey = torch.where(nan2, torch.full_like(sf, float("inf")), sf)
+        same_a = sa[1:] == sa[:-1]
+        f_le = (fkey[1:] >= fkey[:-1]) & ~(nan2[:-1] & ~nan2[1:])
+        same_f = (sf[1:] == sf[:-1]) | (nan2[1:] & nan2[:-1])
+        same_c = sc[1:] == sc[:-1]
+        assert bool((sa[1:] >= sa[:-1]).all())
+        assert bool((~same_a | f_le).all())
+        assert bool((~(same_a & same_f) | (sc[1:] >= sc[:-1])).all())
+        assert bool((~(same_a & same_f & same_c) | (p[1:] > p[:-1])).all())  # ties keep row order
+        new_group = ~(same_a & same_f & same_c)
+        if lo == 0:
+            new_group = torch.cat([torch.ones(1, dtype=torch.bool, device="cuda"), new_group])
+        bins = nbins + torch.cumsum(new_group.int(), 0)
+        assert bool((ik[perm[lo:hi].long()] == bins.int()).all())  # bins numbered in sorted order, base 1
+        nbins = int(bins[-1])
+        del p, sa, sf, sc, nan2, fkey, same_a, f_le, same_f, same_c, new_group, bins
+    assert U == nbins
+    assert bool((ik[ifk.long()] == torch.arange(1, U + 1, device="cuda", dtype=torch.int32)).all())
 
 
 def test_c5_high_cardinality_pack_first_last_cumsum(rc):
-    """configs[4] at 1/5 scale (200 M rows, 20 M uniques): pack, first/last, cumsum."""
+    """configs[4] at its stated size: 1 B rows, 100 M uniques: hash grouping, pack, first / last, cumsum."""
     import torch
 
-    n, u = 200_000_000, 20_000_000
+    n, u = 1_000_000_000, 100_000_000
     key, uvals = _c2(torch, n, u, seed=5)
     ik, ifk, U = rc.MultiKeyGroupBy32([key], 0, None, 2)
-    del key
+    assert U == int(torch.unique(uvals).numel()) or U <= u  # (nearly) every one of the 1e8 values occurs in 1e9 draws
+    assert bool((ifk[1:] > ifk[:-1]).all())
+    assert bool((ik[ifk.long()] == torch.arange(1, U + 1, device="cuda", dtype=torch.int32)).all())
+    rows = torch.arange(0, n, 5, device="cuda")
+    assert bool((key[rows] == key[ifk.long()[ik[rows].long() - 1]]).all())  # same key <=> same bin
+    del key, rows, uvals
+    torch.cuda.empty_cache()
     cnt, ig, ifg = rc.BinCount(ik, U + 1, pack=True)
     assert int(cnt.sum()) == n
     assert bool((ifg[1:] == torch.cumsum(cnt.long(), 0)[:-1].int()).all())

@@ -709,3 +709,37 @@ def test_ismember_reference_kats():
     m, idx = orc.MultiKeyIsMember32(([np.array([1, 2, 1]), np.array([b"x", b"y", b"z"])],),
                                    ([np.array([1, 1]), np.array([b"z", b"x"])],))
     assert m.tolist() == [True, False, True] and idx[[0, 2]].tolist() == [1, 0]
+
+
+def test_cutoffs_on_lexsort_pack_are_per_partition_calls_laid_end_to_end():
+    """UNPINNED by the reference's tests; DERIVED from tests/test_pgroupby.py:7-41, which pins that a `cutoffs` call on
+    the stacked array equals the separate calls on each part (iKey per part, first rows relative to the part,
+    cumulative unique cutoffs).  The sort / pack entry points follow the same rule."""
+    rng = np.random.default_rng(4)
+    arr, arr2 = rng.integers(0, 5, 15), rng.integers(0, 5, 15)
+    f1, f2 = np.round(rng.random(15) * 3), np.round(rng.random(15) * 3)
+    arr3, f3 = np.hstack([arr, arr2]), np.hstack([f1, f2])
+    cut = np.array([15, 30], dtype=np.int64)
+    ig = orc.LexSort32([f3, arr3], cutoffs=cut)
+    np.testing.assert_array_equal(ig[:15], np.lexsort([f1, arr]))
+    np.testing.assert_array_equal(ig[15:], np.lexsort([f2, arr2]))
+    ik, ifk, cnt, ucut = orc.GroupFromLexSort(ig, [arr3, f3], cutoffs=cut)
+    ik1, ifk1, cnt1 = orc.GroupFromLexSort(ig[:15], [arr, f1])
+    ik2, ifk2, cnt2 = orc.GroupFromLexSort(ig[15:], [arr2, f2])
+    np.testing.assert_array_equal(ik, np.r_[ik1, ik2])
+    np.testing.assert_array_equal(ifk, np.r_[ifk1, ifk2])
+    np.testing.assert_array_equal(cnt, np.r_[0, cnt1[1:], cnt2[1:]])
+    assert ucut.tolist() == [len(ifk1), len(ifk1) + len(ifk2)]
+    # the partitions found by sorting are those the hash route finds (test_pgroupby's own cross-check, multikey form)
+    _, (_, hucut), hu = orc.MultiKeyGroupBy32([arr3, f3], cutoffs=cut)
+    assert ucut.tolist() == hucut.tolist() and hu == len(ifk)
+    # groupbylex carries the fourth result as nUniqueCutoffs and its Python glue still works on the stacked arrays
+    hk, _, hu = orc.MultiKeyGroupBy32([arr3], cutoffs=cut)
+    g, fg, c = orc.GroupByPack32(hk, None, hu + 1, cutoffs=cut)
+    c1, g1, fg1 = orc.BinCount(hk[:15], hk[:15].max() + 1, pack=True)
+    c2, g2, fg2 = orc.BinCount(hk[15:], hk[15:].max() + 1, pack=True)
+    np.testing.assert_array_equal(g, np.r_[g1, g2])
+    np.testing.assert_array_equal(fg, np.r_[fg1, fg2])
+    np.testing.assert_array_equal(c, np.r_[c1, c2])
+    with pytest.raises(ValueError):
+        orc.LexSort32([arr3], cutoffs=np.array([15, 31], dtype=np.int64))

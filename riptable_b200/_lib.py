@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libriptable_b200.so")
+# RTB_LIB: measurement aid (profiles/r02/ab: an older build of this library timed beside the current one)
+LIB_PATH = os.environ.get("RTB_LIB") or os.path.join(HERE, "libriptable_b200.so")
 
 RTB_OK, RTB_ERR_ARG, RTB_ERR_WORKSPACE, RTB_ERR_CUDA, RTB_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 

@@ -239,11 +239,12 @@ __device__ __forceinline__ void fuse_add(const GbFuse& f, int32_t bin, unsigned 
 // One round of the direct path over rows [lo, hi).  lo is a multiple of 128; the key / filter / ikey base
 // pointers are 16-byte aligned (checked on the host).
 // FUSE: 0 = grouping only; 1 / 2 = also sum an 8-byte / 4-byte value column into `fz.acc` (see GbFuse).
-#ifndef RTB_FUSE_MINB
-#define RTB_FUSE_MINB 1
-#endif
+// Occupancy is what this kernel lives on: the grouping-only form is compiled for 4 CTAs per SM (64 registers; the same
+// code left at 82 registers / 3 CTAs ran its rounds at 142 instead of 202 G rows/s).  The fused form carries four
+// 64-bit values more per thread: with the next tile's keys prefetched it needs 78 registers (3 CTAs per SM), without
+// the prefetch it fits 64 registers (4 CTAs per SM) -- both are built, the plan picks (GbPlan::fuse_prefetch).
 template <int ISZ, bool PREFETCH, int FUSE>
-__global__ void __launch_bounds__(256, FUSE ? RTB_FUSE_MINB : 1) gb_round_direct(const void* __restrict__ keys, const uint8_t* __restrict__ filter,
+__global__ void __launch_bounds__(256, (FUSE && PREFETCH) ? 3 : 4) gb_round_direct(const void* __restrict__ keys, const uint8_t* __restrict__ filter,
                                                        int32_t* __restrict__ ikey, Slot* table, uint32_t mask,
                                                        int64_t lo, int64_t hi, uint32_t* newlist, GbCounters* ctr,
                                                        uint32_t new_limit, GbFuse fz) {
@@ -1216,6 +1217,7 @@ struct GbPlan {
   int packed_rows = 1;                // packed-row kernels for multi-key / string rows (0: by-reference kernel)
   int smem_table = 1;                 // shared-memory tables for settled low-cardinality rounds
   int prefetch = 1;                   // gb_round_direct: next tile's keys in flight during the probes
+  int fuse_prefetch = 0;              // the same for the fused (group-and-sum) form: 1 = 3 CTAs per SM with, 0 = 4 without
   double discovery_frac = 0.002;      // a round whose predecessor found more new keys than this share of its rows is a discovery round
   int ctas_per_sm = 4;                // gb_round_direct grid = 148 x this
   int64_t round0 = 1 << 20;           // rows of the first round
@@ -1239,6 +1241,7 @@ static GbPlan get_plan() {
   if (const char* e = getenv("RTB_GB_PACKED")) p.packed_rows = atoi(e);
   if (const char* e = getenv("RTB_GB_SMEM")) p.smem_table = atoi(e);
   if (const char* e = getenv("RTB_GB_PREFETCH")) p.prefetch = atoi(e);
+  if (const char* e = getenv("RTB_GB_FUSEPF")) p.fuse_prefetch = atoi(e);
   if (const char* e = getenv("RTB_GB_CTAS")) p.ctas_per_sm = atoi(e);
   if (const char* e = getenv("RTB_GB_ROUND0")) p.round0 = atoll(e);
   if (const char* e = getenv("RTB_GB_LOAD")) p.load_target = atof(e);
@@ -1255,6 +1258,7 @@ struct GbLayout {
   Slot* table;
   Slot* staged;       // max_unique slots; aliased by newlist during rounds
   uint32_t* bitmap;   // words for the largest round
+  int64_t bitmap_words;
   uint32_t* prefix;
   uint32_t* scan_scratch;
   GbCounters* ctr;
@@ -1276,6 +1280,9 @@ static uint32_t snap_cap_for(int64_t max_unique) {
   return c;
 }
 
+// Rows of the largest round a call over n rows can run: the geometric schedule, or the one round that finishes a
+// settled table's remainder (up to finish_rows rows, from any round boundary on) -- the first-row bitmap and its
+// prefix counts are sized by this.
 static int64_t largest_round(int64_t n, const GbPlan& p) {
   int64_t lo = 0, hi = p.round0 < n ? p.round0 : n, best = hi;
   while (hi < n) {
@@ -1284,7 +1291,8 @@ static int64_t largest_round(int64_t n, const GbPlan& p) {
     hi = nh < n ? nh : n;
     if (hi - lo > best) best = hi - lo;
   }
-  return best;
+  const int64_t finish = n < p.finish_rows ? n : p.finish_rows;
+  return best > finish ? best : finish;
 }
 
 static GbLayout layout(void* ws, size_t wsbytes, int64_t nrows, int64_t max_unique, bool cutoffs, int64_t ncut,
@@ -1296,6 +1304,7 @@ static GbLayout layout(void* ws, size_t wsbytes, int64_t nrows, int64_t max_uniq
   L.table = a.take<Slot>((size_t)capmax + 1);
   L.staged = a.take<Slot>((size_t)max_unique + 1);
   int64_t words = (largest_round(nrows, p) + 31) / 32 + 1;
+  L.bitmap_words = words;
   L.bitmap = a.take<uint32_t>((size_t)words);
   L.prefix = a.take<uint32_t>((size_t)words);
   L.scan_scratch = a.take<uint32_t>(scan_u32_workspace_elems(words));
@@ -1717,8 +1726,8 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
     else RTB_ROUND(ISZ_, PF_, 0);                                                                                         \
   } while (0)
         switch (dkey.itemsize) {
-          case 8: if (plan.prefetch) RTB_ROUND_F(8, true); else RTB_ROUND_F(8, false); break;
-          case 4: if (plan.prefetch) RTB_ROUND_F(4, true); else RTB_ROUND_F(4, false); break;
+          case 8: if (fk ? plan.fuse_prefetch : plan.prefetch) RTB_ROUND_F(8, true); else RTB_ROUND_F(8, false); break;
+          case 4: if (fk ? plan.fuse_prefetch : plan.prefetch) RTB_ROUND_F(4, true); else RTB_ROUND_F(4, false); break;
           case 2: RTB_ROUND_F(2, false); break;
           default: RTB_ROUND_F(1, false);
         }
@@ -1846,6 +1855,7 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
       RTB_CUDA(cudaMemsetAsync(fuse->acc + U + 1, 0, sizeof(unsigned long long) * (size_t)prev_new, stream));
     if (prev_new > 0) {
       int64_t words = (rows + 31) / 32;
+      RTB_ARG(words <= L.bitmap_words, "MultiKeyGroupBy32: internal error, a round of %lld rows exceeds the first-row bitmap", (long long)rows);
       RTB_CUDA(cudaMemsetAsync(L.bitmap, 0, sizeof(uint32_t) * words, stream));
       gb_mark_firstrows<<<grid_for(prev_new, 256, 1), 256, 0, stream>>>(L.table, newlist, L.ctr, lo, L.bitmap);
       RTB_LAUNCH_CHECK();

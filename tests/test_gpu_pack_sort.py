@@ -315,7 +315,15 @@ def test_ema_nonfinite_values_stay_inside_their_group(rc):
                 got = rc.EmaAll32([v], ikey, nb, fn, fp)[0]
                 other = (ikey != 1) & (ikey != 7)
                 assert np.isfinite(exp[other]).all() and np.isfinite(got[other]).all(), f"func {fn}: leaked out of its bin"
-                np.testing.assert_allclose(got, exp, rtol=1e-11, atol=1e-9, equal_nan=True, err_msg=f"func {fn} bad {bad}")
+                # rows of the two affected groups that follow the bad value (up to a reset) are non-finite on both sides;
+                # WHICH non-finite value is not compared: the row-by-row recurrence keeps Inf * w = Inf for ever, while a
+                # scan composes the weights first and their product underflows to 0 over a long run (0 * Inf = NaN)
+                tainted = np.zeros(n, dtype=bool)
+                rows7 = np.flatnonzero(ikey == 7)
+                tainted[rows1[3:10] if fp[3] is not None else rows1[3:]] = True
+                tainted[rows7] = True
+                assert (~np.isfinite(exp[tainted])).all() and (~np.isfinite(got[tainted])).all()
+                np.testing.assert_allclose(got[~tainted], exp[~tainted], rtol=1e-11, atol=1e-9, err_msg=f"func {fn} bad {bad}")
                 if fp[3] is not None:
                     assert np.isfinite(got[rows1[10:]]).all(), "reset_filter did not clear the group"
     # unsorted times: exp(-rate * dt) overflows to Inf inside bin 2 only

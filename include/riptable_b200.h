@@ -150,6 +150,18 @@ size_t rtb_ismember_workspace_bytes(int64_t nb);
 int rtb_ismember32(const void* a, int64_t na, const void* b, int64_t nb, int dtype, int base_index, int index_dtype,
                    uint8_t* found_out, void* index_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- 8f.1: rc.IsMemberCategoricalFixup(a_codes, b_codes, on_unique, num_unique_b, a_base, b_base) —
+ * riptable/rt_numpy.py:1302-1305: membership of one Categorical's rows in another, from the match of their UNIQUES.
+ * on_unique int32[n_unique_a] = position of a's unique in b's uniques (negative = absent); b_first int32[num_unique_b +
+ * b_base] = first row of b holding each CODE of b (rtb_first_row_per_code; negative = that code never occurs).
+ * found_out uint8[na]; index_out int32[na] = first row of b with the same category, int32 invalid where there is none
+ * (filtered / invalid codes of a, categories missing from b).  Pinned by riptable/tests/test_ismember.py:162-195, 491-505. */
+int rtb_ismember_categorical_fixup(const void* a_codes, int adtype, int64_t na, const int32_t* on_unique, int64_t n_unique_a,
+                                   const int32_t* b_first, int64_t num_unique_b, int a_base, int b_base, uint8_t* found_out,
+                                   int32_t* index_out, void* stream);
+/* out[c] = first row whose code is c, for c in [0, nslots); -1 where a code never occurs (other codes are ignored). */
+int rtb_first_row_per_code(const void* codes, int dtype, int64_t n, int64_t nslots, int32_t* out, void* stream);
+
 /* ---- a4: rc.CombineFilter(key, filter) — riptable/rt_numpy.py:1508.  out = filter ? key : 0, key dtype kept. */
 int rtb_combine_filter(const void* ikey, int kdtype, const uint8_t* filter, int64_t nrows, void* out, void* stream);
 
@@ -275,6 +287,12 @@ size_t rtb_lexsort_workspace_bytes(int64_t nrows, int64_t nindex, int nkeys, con
 int rtb_lexsort32(const rtb_column* keys, int nkeys, int64_t nrows, const int32_t* index, int64_t nindex,
                   const int8_t* ascending_host, int32_t* perm_out, void* workspace, size_t workspace_bytes,
                   void* stream);
+
+/* rc.LexSort64 (riptable/rt_numpy.py:2199-2200, 2669-2670: the entry riptable calls above 2e9 rows): the same sort with
+ * an int64 result and an int64 `index`; up to 2^32 - 2 rows (row ids are uint32 inside the radix engine). */
+size_t rtb_lexsort64_workspace_bytes(int64_t nrows, int64_t nindex, int nkeys, const int32_t* itemsizes_host);
+int rtb_lexsort64(const rtb_column* keys, int nkeys, int64_t nrows, const int64_t* index, int64_t nindex,
+                  const int8_t* ascending_host, int64_t* perm_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- multi-GPU sample sort: dest_out[r] = number of the `nsplit` splitter rows that sort at or before
  * row r under LexSort32's order (last key primary, NaN last, per-key ascending flags) with the global row id

@@ -960,6 +960,33 @@ def IsMemberCategorical(a, b, h=2, hint_size=0):
     return found, out
 
 
+def IsMemberCategoricalFixup(a_codes, b_codes, on_unique, num_unique_b, a_base_index=1, b_base_index=1):
+    """rc.IsMemberCategoricalFixup (rt_numpy.py:1288-1305): ismember of two Categoricals computed from the match of
+    their uniques: code of a -> unique of a -> unique of b (`on_unique`, the index result of ismember(acats, bcats)) ->
+    code of b -> FIRST row of b holding that code.  Equals ismember(a.as_string_array, b.as_string_array)
+    (tests/test_ismember.py:162-195); filtered rows (code 0 in base 1) and sentinel codes match nothing
+    (tests/test_ismember.py:491-505).  The index dtype is int32 (the tests cast it before comparing)."""
+    a = np.asarray(a_codes).astype(np.int64)
+    b = np.asarray(b_codes).astype(np.int64)
+    on_unique = np.asarray(on_unique).astype(np.int64)
+    nslots = int(num_unique_b) + int(b_base_index)
+    first = np.full(nslots, -1, dtype=np.int64)
+    okb = (b >= 0) & (b < nslots)
+    rows = np.flatnonzero(okb)
+    first[b[rows][::-1]] = rows[::-1]
+    ua = a - int(a_base_index)
+    inv = invalid_for(np.int32)
+    found = np.zeros(len(a), dtype=bool)
+    idx = np.full(len(a), inv, dtype=np.int32)
+    ok = (ua >= 0) & (ua < len(on_unique))
+    ub = np.where(ok, on_unique[np.clip(ua, 0, max(len(on_unique) - 1, 0))] if len(on_unique) else -1, -1)
+    ok &= (ub >= 0) & (ub < int(num_unique_b))
+    pos = np.where(ok, first[np.clip(ub + int(b_base_index), 0, max(nslots - 1, 0))] if nslots else -1, -1)
+    found = pos >= 0
+    idx[found] = pos[found]
+    return found, idx
+
+
 def MultiKeyIsMember32(a_tuple, b_tuple, hint_size=0):
     """rt_numpy.py:1325: rc.MultiKeyIsMember32((a_cols,), (b_cols,), hint_size) -- tuple equality across the columns."""
     return _ismember_cols(list(a_tuple[0]), list(b_tuple[0]))

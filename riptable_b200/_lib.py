@@ -58,6 +58,8 @@ PROTOTYPES = {
         C.c_int,
         [C.POINTER(rtb_column), _i64, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _i32, _pi64, _vp, _sz, _vp],
     ),
+    "rtb_ismember_categorical_fixup": (C.c_int, [_vp, _i32, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
+    "rtb_first_row_per_code": (C.c_int, [_vp, _i32, _i64, _i64, _vp, _vp]),
     "rtb_combine_filter": (C.c_int, [_vp, _i32, _vp, _i64, _vp, _vp]),
     "rtb_combine_accum2": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i64, _i64, _vp, _i32, _vp]),
     "rtb_reduce_out_dtype": (C.c_int, [_i32, _i32]),
@@ -89,6 +91,8 @@ PROTOTYPES = {
     "rtb_make_inext": (C.c_int, [_vp, _i32, _i64, _i64, _i32, _vp, _vp, _sz, _vp]),
     "rtb_lexsort_workspace_bytes": (_sz, [_i64, _i64, _i32, C.POINTER(C.c_int32)]),
     "rtb_lexsort32": (C.c_int, [C.POINTER(rtb_column), _i32, _i64, _vp, _i64, C.POINTER(C.c_int8), _vp, _vp, _sz, _vp]),
+    "rtb_lexsort64_workspace_bytes": (_sz, [_i64, _i64, _i32, C.POINTER(C.c_int32)]),
+    "rtb_lexsort64": (C.c_int, [C.POINTER(rtb_column), _i32, _i64, _vp, _i64, C.POINTER(C.c_int8), _vp, _vp, _sz, _vp]),
     "rtb_lex_partition": (C.c_int, [C.POINTER(rtb_column), _i32, _i64, C.POINTER(C.c_int8), C.POINTER(rtb_column), _i32, _vp,
                                     _i64, _vp, _vp]),
     "rtb_group_from_lexsort_workspace_bytes": (_sz, [_i64, _i64]),

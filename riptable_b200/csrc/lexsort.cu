@@ -205,30 +205,22 @@ extern "C" size_t rtb_lexsort_workspace_bytes(int64_t nrows, int64_t nindex, int
   return lex_layout(nullptr, 0, nindex).bytes + 256;
 }
 
-extern "C" int rtb_lexsort32(const rtb_column* keys, int nkeys, int64_t nrows, const int32_t* index, int64_t nindex,
-                             const int8_t* ascending_host, int32_t* perm_out, void* workspace, size_t workspace_bytes,
-                             void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  RTB_ARG(keys && nkeys >= 1, "LexSort32: first argument is not a list of arrays");
-  RTB_ARG(nrows >= 0 && nrows <= 2147483646ll, "LexSort32: row count out of range for an int32 result");
-  const int64_t m = index ? nindex : nrows;
-  RTB_ARG(m >= 0 && m <= 2147483646ll, "LexSort32: bad index length");
-  if (m == 0) return RTB_OK;
-  RTB_ARG(perm_out, "LexSort32: null output");
+// The sort itself, shared by the 32- and 64-bit entry points: row ids travel as uint32 through the radix engine, so any
+// row count below 2^32 - 1 sorts the same way; only the result's dtype differs.  `perm` (m uint32) receives the result
+// and doubles as a working buffer; `index_u32` (or nullptr) lists the rows to sort.
+static int lexsort_core(const rtb_column* keys, int nkeys, int64_t m, const uint32_t* index_u32, const int8_t* ascending_host,
+                        uint32_t* perm, const LexLayout& L, cudaStream_t stream, const char* who) {
   for (int c = 0; c < nkeys; c++) {
-    RTB_ARG(keys[c].data && keys[c].itemsize >= 1, "LexSort32: bad key column %d", c);
-    RTB_ARG(keys[c].dtype >= RTB_BOOL && keys[c].dtype <= RTB_UCS4, "LexSort32: bad dtype for key column %d", c);
-    RTB_ARG(keys[c].dtype > RTB_F64 || keys[c].itemsize == dtype_size(keys[c].dtype), "LexSort32: itemsize/dtype mismatch");
-    RTB_ARG(keys[c].dtype != RTB_UCS4 || keys[c].itemsize % 4 == 0, "LexSort32: UCS4 itemsize must be a multiple of 4");
+    RTB_ARG(keys[c].data && keys[c].itemsize >= 1, "%s: bad key column %d", who, c);
+    RTB_ARG(keys[c].dtype >= RTB_BOOL && keys[c].dtype <= RTB_UCS4, "%s: bad dtype for key column %d", who, c);
+    RTB_ARG(keys[c].dtype > RTB_F64 || keys[c].itemsize == dtype_size(keys[c].dtype), "%s: itemsize/dtype mismatch", who);
+    RTB_ARG(keys[c].dtype != RTB_UCS4 || keys[c].itemsize % 4 == 0, "%s: UCS4 itemsize must be a multiple of 4", who);
   }
-  LexLayout L = lex_layout(workspace, workspace_bytes, m);
-  RTB_ARG(workspace && L.bytes <= workspace_bytes, "LexSort32: workspace too small");
-
-  uint32_t* cur = (uint32_t*)perm_out;  // current permutation (valid once `started`)
+  uint32_t* cur = perm;  // current permutation (valid once `started`)
   uint32_t* other = L.vals_b;
   bool started = false;
-  if (index) {
-    RTB_CUDA(cudaMemcpyAsync(cur, index, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToDevice, stream));
+  if (index_u32) {
+    if (index_u32 != cur) RTB_CUDA(cudaMemcpyAsync(cur, index_u32, sizeof(uint32_t) * (size_t)m, cudaMemcpyDeviceToDevice, stream));
     started = true;
   }
   for (int c = 0; c < nkeys; c++) {
@@ -265,8 +257,63 @@ extern "C" int rtb_lexsort32(const rtb_column* keys, int nkeys, int64_t nrows, c
       if (in_b) { uint32_t* t = cur; cur = other; other = t; }
     }
   }
-  if (cur != (uint32_t*)perm_out)
-    RTB_CUDA(cudaMemcpyAsync(perm_out, cur, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToDevice, stream));
+  if (cur != perm) RTB_CUDA(cudaMemcpyAsync(perm, cur, sizeof(uint32_t) * (size_t)m, cudaMemcpyDeviceToDevice, stream));
+  return RTB_OK;
+}
+
+extern "C" int rtb_lexsort32(const rtb_column* keys, int nkeys, int64_t nrows, const int32_t* index, int64_t nindex,
+                             const int8_t* ascending_host, int32_t* perm_out, void* workspace, size_t workspace_bytes,
+                             void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RTB_ARG(keys && nkeys >= 1, "LexSort32: first argument is not a list of arrays");
+  RTB_ARG(nrows >= 0 && nrows <= 2147483646ll, "LexSort32: row count out of range for an int32 result");
+  const int64_t m = index ? nindex : nrows;
+  RTB_ARG(m >= 0 && m <= 2147483646ll, "LexSort32: bad index length");
+  if (m == 0) return RTB_OK;
+  RTB_ARG(perm_out, "LexSort32: null output");
+  LexLayout L = lex_layout(workspace, workspace_bytes, m);
+  RTB_ARG(workspace && L.bytes <= workspace_bytes, "LexSort32: workspace too small");
+  return lexsort_core(keys, nkeys, m, (const uint32_t*)index, ascending_host, (uint32_t*)perm_out, L, stream, "LexSort32");
+}
+
+// ---- rc.LexSort64 (riptable/rt_numpy.py:2199-2200, 2669-2670: what riptable calls above 2e9 rows): int64 result, int64
+// `index`.  Row ids still travel as uint32 inside the radix engine, so this entry sorts up to 2^32 - 2 rows.
+__global__ void __launch_bounds__(256) widen_u32_to_i64_kernel(const uint32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (int64_t)in[i];
+}
+__global__ void __launch_bounds__(256) narrow_i64_to_u32_kernel(const int64_t* __restrict__ in, int64_t n, uint32_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (uint32_t)in[i];
+}
+
+extern "C" size_t rtb_lexsort64_workspace_bytes(int64_t nrows, int64_t nindex, int nkeys, const int32_t* itemsizes_host) {
+  (void)nrows; (void)nkeys; (void)itemsizes_host;
+  if (nindex < 0) return 0;
+  return align_up(lex_layout(nullptr, 0, nindex).bytes, 256) + sizeof(uint32_t) * (size_t)(nindex > 0 ? nindex : 1) + 512;
+}
+
+extern "C" int rtb_lexsort64(const rtb_column* keys, int nkeys, int64_t nrows, const int64_t* index, int64_t nindex,
+                             const int8_t* ascending_host, int64_t* perm_out, void* workspace, size_t workspace_bytes,
+                             void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RTB_ARG(keys && nkeys >= 1, "LexSort64: first argument is not a list of arrays");
+  RTB_ARG(nrows >= 0 && nrows <= 4294967294ll, "LexSort64: at most 2^32 - 2 rows");
+  const int64_t m = index ? nindex : nrows;
+  RTB_ARG(m >= 0 && m <= 4294967294ll, "LexSort64: bad index length");
+  if (m == 0) return RTB_OK;
+  RTB_ARG(perm_out, "LexSort64: null output");
+  const size_t lex_bytes = align_up(lex_layout(nullptr, 0, m).bytes, 256);
+  RTB_ARG(workspace && ((uintptr_t)workspace % 256) == 0 && lex_bytes + sizeof(uint32_t) * (size_t)m <= workspace_bytes,
+          "LexSort64: workspace too small or not 256-byte aligned");
+  LexLayout L = lex_layout(workspace, lex_bytes, m);
+  uint32_t* perm = (uint32_t*)((uint8_t*)workspace + lex_bytes);
+  if (index) {
+    narrow_i64_to_u32_kernel<<<grid_for(m, 256, 4), 256, 0, stream>>>(index, m, perm);
+    RTB_LAUNCH_CHECK();
+  }
+  int rc = lexsort_core(keys, nkeys, m, index ? perm : nullptr, ascending_host, perm, L, stream, "LexSort64");
+  if (rc != RTB_OK) return rc;
+  widen_u32_to_i64_kernel<<<grid_for(m, 256, 4), 256, 0, stream>>>(perm, m, perm_out);
+  RTB_LAUNCH_CHECK();
   return RTB_OK;
 }
 

@@ -235,11 +235,68 @@ __global__ void __launch_bounds__(256) reindex_kernel(const int32_t* __restrict_
   }
 }
 
+// first row holding each code in [0, nslots) (0xFFFFFFFF = -1 where a code never occurs; other codes are ignored)
+__global__ void __launch_bounds__(256) first_row_per_code_kernel(const void* __restrict__ codes, int dt, int64_t n, int64_t nslots,
+                                                                  uint32_t* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+    const int64_t c = load_ikey(codes, dt, r);
+    if (c >= 0 && c < nslots && (uint32_t)r < __ldg(out + c)) atomicMin(&out[c], (uint32_t)r);
+  }
+}
+
+// rc.IsMemberCategoricalFixup (riptable/rt_numpy.py:1302-1305): code of a's Categorical -> a's unique -> b's unique
+// (on_unique) -> b's code -> first row of b holding that code.  Two gathers from U-sized tables per row.
+__global__ void __launch_bounds__(256) ismember_cat_fixup_kernel(const void* __restrict__ a, int adt, int64_t na,
+                                                                  const int32_t* __restrict__ on_unique, int64_t nua,
+                                                                  const int32_t* __restrict__ b_first, int64_t num_unique_b,
+                                                                  int a_base, int b_base, uint8_t* __restrict__ found,
+                                                                  int32_t* __restrict__ index_out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < na; i += stride) {
+    const int64_t ua = load_ikey(a, adt, i) - a_base;  // filtered (0 in base 1) and sentinel codes fall out of range
+    int32_t pos = (int32_t)0x80000000;
+    if (ua >= 0 && ua < nua) {
+      const int32_t ub = __ldg(on_unique + ua);
+      if (ub >= 0 && ub < num_unique_b) pos = __ldg(b_first + ub + b_base);
+    }
+    found[i] = pos >= 0;
+    index_out[i] = pos >= 0 ? pos : (int32_t)0x80000000;
+  }
+}
+
 }  // namespace rtb
 
 using namespace rtb;
 
 extern "C" {
+
+int rtb_first_row_per_code(const void* codes, int dtype, int64_t n, int64_t nslots, int32_t* out, void* stream) {
+  RTB_ARG(is_ikey_dtype(dtype), "first row per code: the codes must be int8/16/32/64");
+  RTB_ARG(n >= 0 && n <= 2147483646ll && nslots >= 0 && (out || nslots == 0), "first row per code: bad arguments");
+  if (nslots == 0) return RTB_OK;
+  RTB_CUDA(cudaMemsetAsync(out, 0xFF, sizeof(int32_t) * (size_t)nslots, (cudaStream_t)stream));
+  if (n == 0) return RTB_OK;
+  RTB_ARG(codes, "first row per code: null pointer");
+  first_row_per_code_kernel<<<grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(codes, dtype, n, nslots, (uint32_t*)out);
+  RTB_LAUNCH_CHECK();
+  return RTB_OK;
+}
+
+int rtb_ismember_categorical_fixup(const void* a_codes, int adtype, int64_t na, const int32_t* on_unique, int64_t n_unique_a,
+                                   const int32_t* b_first, int64_t num_unique_b, int a_base, int b_base, uint8_t* found_out,
+                                   int32_t* index_out, void* stream) {
+  RTB_ARG(is_ikey_dtype(adtype), "IsMemberCategoricalFixup: the codes must be int8/16/32/64");
+  RTB_ARG(na >= 0 && n_unique_a >= 0 && num_unique_b >= 0, "IsMemberCategoricalFixup: bad sizes");
+  RTB_ARG((a_base == 0 || a_base == 1) && (b_base == 0 || b_base == 1), "IsMemberCategoricalFixup: base index must be 0 or 1");
+  if (na == 0) return RTB_OK;
+  RTB_ARG(a_codes && found_out && index_out && (on_unique || n_unique_a == 0) && (b_first || num_unique_b == 0),
+          "IsMemberCategoricalFixup: null pointer");
+  ismember_cat_fixup_kernel<<<grid_for(na, 256, 4), 256, 0, (cudaStream_t)stream>>>(a_codes, adtype, na, on_unique, n_unique_a, b_first,
+                                                                                   num_unique_b, a_base, b_base, found_out, index_out);
+  RTB_LAUNCH_CHECK();
+  return RTB_OK;
+}
 
 int rtb_version(void) { return 100; }
 const char* rtb_last_error(void) { return g_err; }

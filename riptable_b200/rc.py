@@ -891,8 +891,46 @@ def LexPartition(list_arrays, splitter_arrays, splitter_rows, row_offset=0, asce
 
 
 def LexSort64(list_arrays, cutoffs=None, index=None, ascending=True):
-    # riptable only routes here above 2e9 rows (rt_numpy.py:2669-2671); below that the 32-bit result is identical
-    return LexSort32(list_arrays, cutoffs=cutoffs, index=index, ascending=ascending)
+    """rc.LexSort64 (riptable/rt_numpy.py:2199-2200, 2669-2670: what riptable calls above 2e9 rows): the same stable
+    lexicographic argsort with an int64 result (and an int64 `index`), for up to 2^32 - 2 rows."""
+    list_arrays = _as_list(list_arrays)
+    if not isinstance(list_arrays, list) or len(list_arrays) == 0:
+        raise ValueError("lexsort needs a list of arrays")
+    n0 = len(list_arrays[0])
+    if n0 <= 2_000_000_000 and (index is None or len(index) <= 2_000_000_000) and cutoffs is not None:
+        # partitions: the 32-bit path does the partition bookkeeping; only the result's dtype differs
+        out = LexSort32(list_arrays, cutoffs=cutoffs, index=index, ascending=ascending)
+        return out.to(torch.int64) if isinstance(out, torch.Tensor) else out.astype(np.int64)
+    if cutoffs is not None:
+        raise ValueError("LexSort64: cutoffs are provided up to 2e9 rows")
+    device_mode = any(_is_device(a) for a in list_arrays) or _is_device(index)
+    cols = [_to_dev(a) for a in list_arrays]
+    n = cols[0].n
+    if any(c.n != n for c in cols):
+        raise ValueError("lexsort: all keys must have the same length")
+    if n > 4_294_967_294:
+        raise ValueError("LexSort64: at most 2^32 - 2 rows")
+    if isinstance(ascending, (bool, np.bool_)):
+        asc = np.full(len(cols), 1 if ascending else 0, dtype=np.int8)
+    else:
+        asc = np.asarray([1 if a else 0 for a in ascending], dtype=np.int8)
+        if len(asc) != len(cols):
+            raise ValueError("ascending must have one entry per key")
+    idx, m = None, n
+    if index is not None:
+        idx = _to_dev(index)
+        if idx.dtype != np.dtype(np.int64):
+            idx = _to_dev(idx.torch().to(torch.int64))
+        m = idx.n
+    out = DevArray.empty(m, np.int64)
+    if m == 0:
+        return _from_dev(out, device_mode)
+    isz = (C.c_int32 * len(cols))(*[c.dtype.itemsize for c in cols])
+    ws = _ws(lib.rtb_lexsort64_workspace_bytes(n, m, len(cols), isz))
+    check(lib.rtb_lexsort64(_cols(cols), len(cols), n, C.c_void_p(idx.ptr) if idx is not None else None, m,
+                            asc.ctypes.data_as(C.POINTER(C.c_int8)), C.c_void_p(out.ptr), C.c_void_p(ws.data_ptr()),
+                            ws.numel(), _stream()))
+    return _from_dev(out, device_mode)
 
 
 # ==================================================================================================
@@ -989,7 +1027,7 @@ def ReIndexGroups(ikey, uikey, u_cutoffs, i_cutoffs):
 
 __all__ = ["MultiKeyGroupBySum32", "GroupByStream", "ReIndexGroups", "LexPartition", "MultiKeyGroupBy32", "CombineFilter", "CombineAccum1Filter", "CombineAccum2Filter", "GroupByAll32", "BinCount",
            "GroupFromBinCount", "GroupByPack32", "GroupByAllPack32", "EmaAll32", "MakeiFirst", "MakeiNext", "LexSort32",
-           "LexSort64", "GroupFromLexSort", "ReverseShuffle", "IsMember32", "IsMemberCategorical", "MultiKeyIsMember32", "LedgerFunction"]
+           "LexSort64", "GroupFromLexSort", "ReverseShuffle", "IsMember32", "IsMemberCategorical", "IsMemberCategoricalFixup", "MultiKeyIsMember32", "LedgerFunction"]
 
 
 # ==================================================================================================
@@ -1069,6 +1107,34 @@ def IsMemberCategorical(a, b, h=2, hint_size=0):
     """rc.IsMemberCategorical (riptable/rt_numpy.py:1388-1389, `ismember(..., base_index=1)`): the position is 1-based
     and 0 where absent, ready to be used as a Categorical's codes (riptable/rt_grouping.py:959-963)."""
     return _ismember([a], [b], 1)
+
+
+def IsMemberCategoricalFixup(a_codes, b_codes, on_unique, num_unique_b, a_base_index=1, b_base_index=1):
+    """rc.IsMemberCategoricalFixup (riptable/rt_numpy.py:1302-1305): ismember of two Categoricals from the match of their
+    uniques.  a_codes / b_codes: the Categoricals' underlying integer arrays; on_unique: int32 position of each unique of
+    `a` in the uniques of `b` (invalid / negative where absent).  -> (bool[len(a)], int32 first row of b holding the same
+    category, the int32 invalid where there is none) == ismember(a.expand_array, b.expand_array)
+    (riptable/tests/test_ismember.py:162-195)."""
+    device_mode = _is_device(a_codes) or _is_device(b_codes)
+    a, b = _ikey_dev(a_codes), _ikey_dev(b_codes)
+    ou = _to_dev(on_unique)
+    if ou.dtype != np.dtype(np.int32):
+        ou = _to_dev((ou.torch() if ou.dtype in _TORCH_OF else torch.from_numpy(ou.numpy())).to(torch.int32))
+    nub = int(num_unique_b)
+    dev = _device()
+    # first row of b per CODE of b (codes 0 .. nub + b_base - 1); codes outside that range are ignored
+    nslots = nub + int(b_base_index)
+    b_first = DevArray.empty(nslots + 1, np.int32)
+    check(lib.rtb_first_row_per_code(C.c_void_p(b.ptr), dtype_code(b.dtype), b.n, nslots, C.c_void_p(b_first.ptr), _stream()))
+    found = torch.empty(max(a.n, 1), dtype=torch.uint8, device=dev)[: a.n]
+    idx = torch.empty(max(a.n, 1), dtype=torch.int32, device=dev)[: a.n]
+    check(lib.rtb_ismember_categorical_fixup(C.c_void_p(a.ptr), dtype_code(a.dtype), a.n, C.c_void_p(ou.ptr), ou.n,
+                                             C.c_void_p(b_first.ptr), nub, int(a_base_index), int(b_base_index),
+                                             C.c_void_p(found.data_ptr()), C.c_void_p(idx.data_ptr()), _stream()))
+    found = found.view(torch.bool)
+    if device_mode:
+        return found, idx
+    return found.cpu().numpy(), idx.cpu().numpy()
 
 
 def MultiKeyIsMember32(a_tuple, b_tuple, hint_size=0):

@@ -625,3 +625,28 @@ def test_groupby_stream_with_sums(rc):
             np.testing.assert_allclose(got[1:], exp[1:].astype(np.float64), rtol=1e-5 if vdt == np.float32 else 1e-12, atol=1e-9 if vdt == np.float64 else 1e-3)
         else:
             np.testing.assert_array_equal(got[1:], exp[1:])
+
+
+@pytest.mark.parametrize("n", [0, 1, 1000, 300_001])
+def test_ismember_categorical_fixup(rc, n):
+    rng = np.random.default_rng(n + 5)
+    for ba in (0, 1):
+        for bb in (0, 1):
+            nua, nub = 40, 25
+            for adt in (np.int8, np.int32, np.int64):
+                a = rng.integers(ba - (1 if ba else 0), nua + ba, n).astype(adt)   # base 1: includes the filtered code 0
+                b = rng.integers(0, nub + bb, max(n // 2, 3)).astype(np.int16)
+                b[b == 7 + bb] = 3 + bb                                            # one category of b never occurs
+                if n > 10:
+                    a[5] = np.iinfo(adt).min                                       # a sentinel code
+                on_unique = rng.integers(-1, nub, nua).astype(np.int32)
+                on_unique[on_unique < 0] = np.iinfo(np.int32).min
+                gf, gi = rc.IsMemberCategoricalFixup(a, b, on_unique, nub, ba, bb)
+                ef, ei = orc.IsMemberCategoricalFixup(a, b, on_unique, nub, ba, bb)
+                assert gf.dtype == np.bool_ and gi.dtype == np.int32
+                np.testing.assert_array_equal(gf, ef)
+                np.testing.assert_array_equal(gi, ei)
+    c1 = np.array([0, -128, 3], dtype=np.int8)
+    c2 = np.array([1, 2, -128, 0, 3], dtype=np.int8)
+    is_in, idx = rc.IsMemberCategoricalFixup(c1, c2, np.array([0, 1, 2], dtype=np.int32), 4, 1, 1)
+    assert is_in.tolist() == [False, False, True] and idx.tolist() == [np.iinfo(np.int32).min] * 2 + [4]

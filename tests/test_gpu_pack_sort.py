@@ -706,3 +706,52 @@ def test_riptable_glue_with_cutoffs(rc):
             else:
                 np.testing.assert_array_equal(got[k], exp[k], err_msg=f"{fn.__name__} {k}")
     assert "nUniqueCutoffs" in rt_glue.groupbylex(rc, [a, b], cutoffs=cut)
+
+
+def test_lexsort64_small_and_index(rc):
+    rng = np.random.default_rng(64)
+    n = 200_003
+    a = rng.integers(-100, 100, n).astype(np.int32)
+    f = np.round(rng.random(n) * 50)
+    f[rng.random(n) < 0.05] = np.nan
+    got = rc.LexSort64([f, a])
+    assert got.dtype == np.int64
+    np.testing.assert_array_equal(got, np.lexsort([f, a]))
+    idx = np.flatnonzero(rng.random(n) < 0.4).astype(np.int64)
+    np.testing.assert_array_equal(rc.LexSort64([f, a], index=idx, ascending=[True, False]),
+                                  orc.LexSort32([f, a], index=idx, ascending=[True, False]).astype(np.int64))
+    cut = np.array([1000, 150_000, n], dtype=np.int64)
+    np.testing.assert_array_equal(rc.LexSort64([f, a], cutoffs=cut), orc.LexSort32([f, a], cutoffs=cut).astype(np.int64))
+
+
+def test_lexsort64_above_two_billion_rows(rc):
+    """rc.LexSort64 where riptable calls it (rt_numpy.py:2669-2670): more rows than an int32 result can index.  2.2e9
+    int8 keys; the int64 permutation is checked in slices: a permutation, sorted, ties in row order."""
+    import torch
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 100 * 2**30:
+        pytest.skip("needs about 80 GB of device memory")
+    n = 2_200_000_000
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1)
+    key = torch.empty(n, dtype=torch.int8, device="cuda")
+    step = 1 << 28
+    for lo in range(0, n, step):
+        hi = min(n, lo + step)
+        key[lo:hi] = torch.randint(-100, 100, (hi - lo,), device="cuda", generator=g, dtype=torch.int8)
+    perm = rc.LexSort64([key])
+    assert perm.dtype == torch.int64 and perm.numel() == n
+    assert int(perm.max()) == n - 1 and int(perm.min()) == 0
+    seen = torch.zeros(n, dtype=torch.bool, device="cuda")
+    for lo in range(0, n, step):
+        seen[perm[lo:min(n, lo + step)]] = True
+    assert bool(seen.all())
+    del seen
+    for lo in range(0, n, step):
+        hi = min(n, lo + step)
+        p = perm[max(lo - 1, 0):hi]
+        k = key[p]
+        assert bool((k[1:] >= k[:-1]).all())
+        assert bool(((k[1:] != k[:-1]) | (p[1:] > p[:-1])).all())
+        del p, k

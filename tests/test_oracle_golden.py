@@ -743,3 +743,34 @@ def test_cutoffs_on_lexsort_pack_are_per_partition_calls_laid_end_to_end():
     np.testing.assert_array_equal(c, np.r_[c1, c2])
     with pytest.raises(ValueError):
         orc.LexSort32([arr3], cutoffs=np.array([15, 31], dtype=np.int64))
+
+
+def _cat(values, base_index, cats=None):
+    """(codes, sorted uniques) of an ordered Categorical in the given base index."""
+    values = np.asarray(values)
+    cats = np.unique(values) if cats is None else np.asarray(cats)
+    return (np.searchsorted(cats, values) + base_index).astype(np.int8), cats
+
+
+def test_ismember_categorical_fixup_kats():
+    """tests/test_ismember.py:162-195: ismember(c, d) on Categoricals == ismember on their expanded strings, for both
+    base indices on both sides; :491-505: filtered and sentinel codes match nothing."""
+    rng = np.random.default_rng(0)
+    for ba in (0, 1):
+        for bb in (0, 1):
+            cs = rng.choice(np.array(["a", "b", "c", "d", "e", "f"]), 15)
+            ds = rng.choice(np.array(["a", "b", "c"]), 10)
+            (c, ccats), (d, dcats) = _cat(cs, ba), _cat(ds, bb)
+            for (x, xc, xb, xs), (y, yc, yb, ys) in (((c, ccats, ba, cs), (d, dcats, bb, ds)), ((d, dcats, bb, ds), (c, ccats, ba, cs))):
+                _, on_unique = orc.IsMember32(xc, yc)
+                b, f = orc.IsMemberCategoricalFixup(x, y, on_unique.astype(np.int32), len(yc), xb, yb)
+                bs, fs = orc.IsMember32(xs, ys)
+                np.testing.assert_array_equal(b, bs)
+                np.testing.assert_array_equal(f[b].astype(np.int8), fs[bs])
+                assert (f[~b] == np.iinfo(np.int32).min).all()
+    # tests/test_ismember.py:491-505
+    c1 = np.array([0, -128, 3], dtype=np.int8)           # ["a", "b", "c"] with row 0 filtered and row 1 set to the sentinel
+    c2 = np.array([1, 2, -128, 0, 3], dtype=np.int8)     # ["a", "b", "c", "d", "c"] with row 3 filtered and row 2 the sentinel
+    is_in, idx = orc.IsMemberCategoricalFixup(c1, c2, np.array([0, 1, 2], dtype=np.int32), 4, 1, 1)
+    assert is_in.tolist() == [False, False, True]
+    assert idx.tolist() == [np.iinfo(np.int32).min, np.iinfo(np.int32).min, 4]

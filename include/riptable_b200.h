@@ -335,6 +335,31 @@ int rtb_partition_max_ikey(const void* ikey, int kdtype, int64_t n, const int32_
 int rtb_partition_compose_ikey(const void* ikey, int kdtype, int64_t n, const int32_t* pid, const int64_t* bin_off,
                                int32_t* out, void* stream);
 
+/* ---- 8f.4: join-index construction — riptable/rt_merge.py:734-1190 (`_build_left_fancyindex`,
+ * `_build_right_fancyindex`) and its numba loops :611-665, 668-731, 887-975; no rc entry exists for these (riptable
+ * runs them in Python / numba), so riptable_b200/merge.py mirrors `rt.merge_indices` and calls:
+ *   rtb_valid_mask        out[r] = key r is usable: not NaN / not the integer sentinel (`_create_column_valid_mask`,
+ *                         rt_merge.py:1848-1872); mode 0 sets, 1 ANDs into, 2 ORs into `out`
+ *   rtb_merge_row_counts  per left row: keyid_out = the 1-based right key id its key maps to through `keymap`
+ *                         (int32[nmap] indexed by left key id - 1; negative = no such key on the right) or the int32
+ *                         invalid; count_out = rows it contributes: that right group's size, or nonmatched_count
+ *   rtb_merge_scan_counts exclusive scan of the counts and their total (host)
+ *   rtb_merge_expand      left_out[off .. off + count) = the left row (left_rows[i], or i when NULL);
+ *                         right_out[...] = right_igroup[right_ifirstgroup[keyid] ...], or the int32 invalid for an
+ *                         unmatched row.  Either output may be NULL.
+ * rtb_merge_row_counts: a row whose key id is 0 (an invalid key) contributes invalid_row_count rows, a row whose key has no
+ * partner nonmatched_count rows (0 for an inner join, 1 for a left join). */
+int rtb_valid_mask(const void* col, int dtype, int64_t n, int mode, uint8_t* out, void* stream);
+int rtb_merge_row_counts(const int32_t* left_ikey, int64_t n, const int32_t* keymap, int64_t nmap,
+                         const int32_t* right_ncountgroup, int64_t ngroups, int64_t nonmatched_count,
+                         int64_t invalid_row_count, int32_t* keyid_out, uint32_t* count_out, void* stream);
+size_t rtb_merge_scan_workspace_bytes(int64_t n);
+int rtb_merge_scan_counts(const uint32_t* counts, int64_t n, uint32_t* offsets_out, int64_t* total_host, void* workspace,
+                          size_t workspace_bytes, void* stream);
+int rtb_merge_expand(const int32_t* keyid, const uint32_t* offsets, const uint32_t* counts, int64_t n,
+                     const int32_t* left_rows, const int32_t* right_ifirstgroup, const int32_t* right_igroup,
+                     int32_t* left_out, int32_t* right_out, void* stream);
+
 /* ---- a13: rc.ReverseShuffle(perm) — riptable/rt_grouping.py:1659.  out[perm[i]] = i. */
 int rtb_reverse_shuffle(const int32_t* perm, int64_t n, int32_t* out, void* stream);
 

@@ -106,6 +106,11 @@ PROTOTYPES = {
     "rtb_partition_localize": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _vp]),
     "rtb_partition_max_ikey": (C.c_int, [_vp, _i32, _i64, _vp, _i64, _vp, _vp, _vp]),
     "rtb_partition_compose_ikey": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp, _vp]),
+    "rtb_valid_mask": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _vp]),
+    "rtb_merge_row_counts": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "rtb_merge_scan_workspace_bytes": (_sz, [_i64]),
+    "rtb_merge_scan_counts": (C.c_int, [_vp, _i64, _vp, _pi64, _vp, _sz, _vp]),
+    "rtb_merge_expand": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rtb_reverse_shuffle": (C.c_int, [_vp, _i64, _vp, _vp]),
     "rtb_remap_ikey": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
 }

@@ -774,3 +774,101 @@ def test_ismember_categorical_fixup_kats():
     is_in, idx = orc.IsMemberCategoricalFixup(c1, c2, np.array([0, 1, 2], dtype=np.int32), 4, 1, 1)
     assert is_in.tolist() == [False, False, True]
     assert idx.tolist() == [np.iinfo(np.int32).min, np.iinfo(np.int32).min, 4]
+
+
+# ---- 8f.4: join-index construction (oracle/merge_oracle.py restates rt_merge.py; pinned to pandas.merge) --------------
+def _pandas_join(lk, rk, how, keep):
+    import pandas as pd
+
+    l = pd.DataFrame({f"k{i}": c for i, c in enumerate(lk)})
+    r = pd.DataFrame({f"k{i}": c for i, c in enumerate(rk)})
+    l["lid"], r["rid"] = np.arange(len(l)), np.arange(len(r))
+    on = [c for c in l.columns if c.startswith("k")]
+    if keep[0]:
+        l = l.drop_duplicates(on, keep=keep[0])
+    if keep[1]:
+        r = r.drop_duplicates(on, keep=keep[1])
+    m = pd.merge(l, r, on=on, how=how)
+    return m["lid"].to_numpy(dtype=np.float64), m["rid"].to_numpy(dtype=np.float64)
+
+
+def _as_float(idx, n):
+    from oracle import merge_oracle as mo
+
+    if idx is None:
+        return np.arange(n, dtype=np.float64)
+    out = np.asarray(idx).astype(np.float64)
+    out[np.asarray(idx) == mo.INV] = np.nan
+    return out
+
+
+@pytest.mark.parametrize("how", ["left", "inner", "right"])
+@pytest.mark.parametrize("keep", [(None, None), (None, "first"), ("last", None), ("first", "last")])
+def test_merge_indices_row_order_equals_pandas_merge(how, keep):
+    """rt_merge.py:2107-2113: left / right / inner joins preserve the key order of the left (right) side; matching rows of
+    the other side come in their own row order -- which is pandas.merge's contract too."""
+    from oracle import merge_oracle as mo
+
+    rng = np.random.default_rng(hash((how, keep)) % 2**32)
+    for nl, nr, span in ((0, 5, 3), (7, 0, 3), (50, 40, 12), (300, 500, 40), (200, 30, 500)):
+        for cols in (1, 2):
+            lk = [rng.integers(0, span, nl) for _ in range(cols)]
+            rk = [rng.integers(0, span, nr) for _ in range(cols)]
+            if cols == 2:
+                lk[1] = np.array(["x", "yy", "z"])[lk[1] % 3]
+                rk[1] = np.array(["x", "yy", "z"])[rk[1] % 3]
+            li, ri, _ = mo.merge_indices(lk, rk, how, keep)
+            pl, pr = _pandas_join(lk, rk, how, keep)
+            n_out = len(pl)
+            gl = _as_float(li, nl)
+            gr = _as_float(ri, nr)
+            assert len(gl) == len(gr) == n_out, (how, keep, nl, nr)
+            driving_keep = keep[1] if how == "right" else keep[0]
+            if driving_keep == "last":
+                # riptable walks the driving side's groups in first-appearance order and takes each group's LAST row
+                # (rt_merge.py:785-789: ikey[ilastkey]); pandas keeps the surviving rows in row order.  Same pairs.
+                key = lambda a, b: sorted(zip(np.nan_to_num(a, nan=-1).tolist(), np.nan_to_num(b, nan=-1).tolist()))  # noqa: E731
+                assert key(gl, gr) == key(pl, pr)
+                drv, dk = (gr, rk) if how == "right" else (gl, lk)
+                rows = drv[~np.isnan(drv)].astype(np.int64)
+                bins, _, _ = orc.MultiKeyGroupBy32([np.asarray(c) for c in dk]) if len(dk[0]) else (np.zeros(0, np.int32), None, 0)
+                order = bins[rows].tolist()  # first-appearance number of each surviving row's key
+                assert order == sorted(order)
+            else:
+                np.testing.assert_array_equal(gl, pl)
+                np.testing.assert_array_equal(gr, pr)
+
+
+def test_merge_indices_outer_and_null_keys():
+    """Outer join (rt_merge.py:1404-1588): the left-join rows first, then the rows of right whose key is not in left, in
+    right row order.  NaN keys never match (SQL JOIN semantics, rt_merge.py:1968-1981) but their rows are kept."""
+    from oracle import merge_oracle as mo
+
+    lk = [np.array([3.0, np.nan, 1.0, 3.0, 7.0])]
+    rk = [np.array([1.0, 1.0, np.nan, 9.0, 3.0, 8.0])]
+    li, ri, k = mo.merge_indices(lk, rk, "outer")
+    assert k == 3
+    assert _as_float(li, 5).tolist()[:6] == [0.0, 1.0, 2.0, 2.0, 3.0, 4.0] and np.isnan(_as_float(li, 5)[6:]).all()
+    r = _as_float(ri, 6)
+    assert r[[0, 2, 3, 4]].tolist() == [4.0, 0.0, 1.0, 4.0] and np.isnan(r[[1, 5]]).all() and r[6:].tolist() == [2.0, 3.0, 5.0]
+    # left join: the left NaN row stays (and matches nothing); inner: it goes
+    li, ri, _ = mo.merge_indices(lk, rk, "left")
+    assert _as_float(li, 5).tolist() == [0.0, 1.0, 2.0, 2.0, 3.0, 4.0]
+    li, ri, _ = mo.merge_indices(lk, rk, "inner")
+    assert li.tolist() == [0, 2, 2, 3] and ri.tolist() == [4, 0, 1, 4]
+    # unique right keys: the left columns are used as they are (rt_merge.py:1060-1095)
+    li, ri, _ = mo.merge_indices([np.array([5, 6, 5])], [np.array([6, 5, 9])], "left")
+    assert li is None and ri.tolist() == [1, 0, 1]
+    # outer with keep on the right: one row per right-only key, all pairs as a set equal pandas' outer join
+    rng = np.random.default_rng(1)
+    lk, rk = [rng.integers(0, 30, 80)], [rng.integers(10, 50, 90)]
+    for keep in ((None, None), (None, "first"), (None, "last")):
+        li, ri, k = mo.merge_indices(lk, rk, "outer", keep)
+        pl, pr = _pandas_join(lk, rk, "outer", keep)
+        got = sorted(zip(np.nan_to_num(_as_float(li, 80), nan=-1).tolist(), np.nan_to_num(_as_float(ri, 90), nan=-1).tolist()))
+        exp = sorted(zip(np.nan_to_num(pl, nan=-1).tolist(), np.nan_to_num(pr, nan=-1).tolist()))
+        assert got == exp
+        tail = _as_float(ri, 90)[len(ri) - k:]
+        assert (np.diff(tail) > 0).all() and np.isnan(_as_float(li, 80)[len(li) - k:]).all()
+    with pytest.raises(ValueError):
+        mo.merge_indices(lk, rk, "outer", ("first", None))

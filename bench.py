@@ -278,7 +278,7 @@ def main():
         v = val if v is None else v
         if dist is None:
             return rc.MultiKeyGroupBySum32([k], v, 0, None, 2, GB_FUNCTIONS.GB_SUM, 1)
-        return dist.sharded_groupby_sum([k], v)
+        return dist.sharded_groupby_sum([k], v, shard_sizes=[int(k.numel())] * world)  # equal shards: sizes known
 
     def step_two_call():
         ik, ifk, u = rc.MultiKeyGroupBy32([key], 0, None, 2)
@@ -364,7 +364,7 @@ def main():
         try:
             prow = min(rows, 1 << 22)
             pk, pv = key[:prow].contiguous(), val[:prow].contiguous()
-            gik, gifk, gu, gs = dist.sharded_groupby_sum([pk], pv)
+            gik, gifk, gu, gs = dist.sharded_groupby_sum([pk], pv)  # (this call also exercises the shard-size all-gather)
             allk = torch.empty(prow * world, dtype=pk.dtype, device=dev)
             allv = torch.empty(prow * world, dtype=pv.dtype, device=dev)
             alli = torch.empty(prow * world, dtype=torch.int32, device=dev)

@@ -129,6 +129,37 @@ class CudaOps:
         isz = col.dtype.itemsize
         return self.rc.DevArray(col.buf[lo * isz:], col.dtype, hi - lo) if hi > lo else self.rc.DevArray.empty(0, col.dtype)
 
+    # -- adopting a seed (dist._sharded_groupby_seeded): U-sized tables, plus one re-index of the prefix rows -----------
+    def bin_table(self, newbins):
+        """[0, new bin of old bin 1, new bin of old bin 2, ...] as int32."""
+        t = torch.empty(newbins.numel() + 1, dtype=torch.int32, device=newbins.device)
+        t[0] = 0
+        t[1:] = newbins
+        return t
+
+    def stream_fix_first(self, st, u0, u_mid, old_first):
+        """First rows of bins (u0, u_mid] were recorded as positions in the chunk of local unique keys: turn them into rows."""
+        f = st.ifirst.torch()
+        f[u0:u_mid] = old_first[f[u0:u_mid].to(torch.int64)].to(torch.int32)
+
+    def remap_prefix(self, ikey, S, table):
+        """ikey[:S] <- table[ikey[:S]] (rtb_remap_ikey); the rest of the buffer is still to be written."""
+        if S == 0:
+            return ikey
+        from ._lib import lib, check
+        import ctypes as C
+
+        # in place: every thread reads its four rows before it writes them
+        check(lib.rtb_remap_ikey(C.c_void_p(ikey.data_ptr()), int(S), C.c_void_p(table.data_ptr()), table.numel(),
+                                 C.c_void_p(ikey.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return ikey
+
+    def stream_move_sums(self, old, new, table, u_loc):
+        """Partial sums of the prefix, accumulated under the local bins, move to the adopted bins (a permutation)."""
+        src = old._acc[: u_loc + 1]
+        new._vdtype = old._vdtype
+        new._acc[table.to(torch.int64)] = src
+
     def slice_filter(self, f, lo, hi):
         return None if f is None else f[lo:hi]
 
@@ -240,15 +271,16 @@ class ShardedGrouping:
         return self._gikey
 
 
-def sharded_groupby(ops, key_cols, filter=None, group=None, sum_values=None) -> ShardedGrouping:
+def sharded_groupby(ops, key_cols, filter=None, group=None, sum_values=None, shard_sizes=None) -> ShardedGrouping:
     """MultiKeyGroupBy32 over rows sharded contiguously across the ranks of `group` (module docstring, steps 1-4).
     `sum_values`: a value column to sum in the same pass where the path allows it (single-key seeded shards); the
-    grouping then carries `partial_sums` (this shard's raw per-bin sums by GLOBAL bin) for sharded_groupby_sum."""
+    grouping then carries `partial_sums` (this shard's raw per-bin sums by GLOBAL bin) for sharded_groupby_sum.
+    `shard_sizes`: the row count of every rank's shard, when the caller knows them (saves a collective and a host sync)."""
     G, rank = _world(group)
     cols = [ops.as_col(c) for c in key_cols]
     n = ops.nrows(cols[0])
     if len(cols) == 1 and SEEDED and hasattr(ops, "stream") and ops.can_stream(cols[0]):
-        g = _sharded_groupby_seeded(ops, cols[0], filter, group, sum_values)
+        g = _sharded_groupby_seeded(ops, cols[0], filter, group, sum_values, shard_sizes)
         if g is not None:
             return g
         # a shard holds more unique keys than the seeded table was provisioned for: every rank takes the generic path
@@ -304,82 +336,112 @@ def sharded_groupby(ops, key_cols, filter=None, group=None, sum_values=None) -> 
     return ShardedGrouping(ops, gikey, ready, ik, u, table, ifirst_global, int(U), row_off[rank], sum(ns), us)
 
 
-def _sharded_groupby_seeded(ops, col, filter, group, sum_values=None) -> ShardedGrouping:
+def _sharded_groupby_seeded(ops, col, filter, group, sum_values=None, shard_sizes=None) -> ShardedGrouping:
     """Single-key shards, seeded: global bin ids come out of the hash pass itself, no per-row re-index.
 
     Global first-appearance order lists every key of shard 0 first (in shard 0's own order).  Shard 0 therefore groups
-    a prefix of its rows, broadcasts the keys it found (u0 of them, typically all) with their bins 1..u0, and every
-    other rank pre-loads its table with exactly those keys before hashing its own rows (the resumable grouping of
-    rc.GroupByStream).  Rows whose key is in the seed get their GLOBAL bin directly.  Keys outside the seed ("late"
-    keys: first seen after the prefix of shard 0, or absent from shard 0) get provisional bins above u0; only if any
-    rank reports such keys are they merged (all-gather of the late uniques in rank order, re-group, re-index)."""
+    a prefix of its rows and broadcasts the keys it found (u0 of them, typically all) with their bins 1..u0; every other
+    rank hashes its rows against a table that holds exactly those keys under exactly those bins (the resumable grouping
+    of rc.GroupByStream), so rows whose key is in the seed get their GLOBAL bin straight out of the hash pass.
+
+    The other ranks do not wait for the seed: while shard 0 groups its prefix they group a prefix of their own under
+    local bins, and when the seed arrives they ADOPT it -- a fresh table is loaded with the seed keys, the local unique
+    keys are pushed through it (one U-sized chunk: seeded keys come back with their global bin, the others get bins above
+    u0 in local first-appearance order), and the prefix's iKey and partial sums are re-indexed through that U-sized map.
+    Only the prefix is re-indexed; the rest of the shard is hashed against the adopted table.
+
+    Keys outside the seed ("late" keys: first seen after the prefix of shard 0, or absent from shard 0) end up with
+    provisional bins above u0; only if any rank reports such keys are they merged (all-gather of the late uniques in
+    rank order, re-group, re-index)."""
     G, rank = _world(group)
     n = ops.nrows(col)
     dt = ops.col_dtype(col)
     tick = _Tick()
-    meta = ops.tensor([n], dtype=torch.int64)
-    alln = meta.new_empty(G)
-    tdist.all_gather_into_tensor(alln, meta, group=group)
-    ns = alln.cpu().tolist()
+    if shard_sizes is not None:
+        ns = [int(x) for x in shard_sizes]  # the caller knows the shard sizes: no collective, no host sync
+    else:
+        meta = ops.tensor([n], dtype=torch.int64)
+        alln = meta.new_empty(G)
+        tdist.all_gather_into_tensor(alln, meta, group=group)
+        ns = alln.cpu().tolist()
     row_off = [0] * G
     for r in range(1, G):
         row_off[r] = row_off[r - 1] + ns[r - 1]
     nmax = max(ns) if ns else 0
     max_unique = max(SEEDED_MIN_UNIQUE, nmax // 16, 1)
-    S = min(ns[0], SEED_ROWS) & ~127 if ns[0] > SEED_ROWS else ns[0]
+    S = (min(n, SEED_ROWS) & ~127) if n > SEED_ROWS else n  # this rank's prefix
     fused = sum_values is not None
     vcol = ops.as_col(sum_values) if fused else None
-    st = ops.stream(max_unique, max(nmax, 1), with_sums=True) if fused else ops.stream(max_unique, max(nmax, 1))
+
+    def new_stream():
+        return ops.stream(max_unique, max(nmax, 1), with_sums=True) if fused else ops.stream(max_unique, max(nmax, 1))
+
+    st = new_stream()
     ikey = ops.empty_ikey(n)
 
-    def push(lo_, hi_, out):
+    def push(s_, lo_, hi_, out):
         if fused:
-            st.push(ops.slice_rows(col, lo_, hi_), ops.slice_filter(filter, lo_, hi_), lo_, out, values=ops.slice_rows(vcol, lo_, hi_))
+            s_.push(ops.slice_rows(col, lo_, hi_), ops.slice_filter(filter, lo_, hi_), lo_, out, values=ops.slice_rows(vcol, lo_, hi_))
         else:
-            st.push(ops.slice_rows(col, lo_, hi_), ops.slice_filter(filter, lo_, hi_), lo_, out)
+            s_.push(ops.slice_rows(col, lo_, hi_), ops.slice_filter(filter, lo_, hi_), lo_, out)
 
     # A push that runs out of table room fails on that rank alone; the failure is carried by the next collective
     # every rank takes part in (u0 = -1 / late = -1), so that all ranks leave the seeded path together.
     overflow = getattr(ops, "workspace_error", ())
 
-    # 1. shard 0 groups its prefix and publishes the seed
+    # 1. every rank groups its own prefix; shard 0's is the seed
     failed = False
-    if rank == 0:
-        try:
-            push(0, S, ikey[:S] if S else None)
-        except overflow:
-            failed = True
-    u0_t = ops.tensor([-1 if failed else (st.unique_count if rank == 0 else 0)], dtype=torch.int64)
-    tdist.broadcast(u0_t, src=tdist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    try:
+        if S:
+            push(st, 0, S, ikey[:S])
+    except overflow:
+        failed = True
+    src = tdist.get_global_rank(group, 0) if group is not None else 0
+    u0_t = ops.tensor([(-1 if failed else st.unique_count) if rank == 0 else 0], dtype=torch.int64)
+    tdist.broadcast(u0_t, src=src, group=group)
     u0 = int(u0_t.item())
     if u0 < 0:
         return None
-    if rank == 0:
-        seed_first = ops.to_torch(st.ifirstkey).to(torch.int64).clone()
-        seed_bytes = ops.col_bytes(ops.take_rows(col, ops.to_torch(st.ifirstkey))).clone()
-    else:
-        seed_first = ops.tensor([0], dtype=torch.int64).new_empty(u0)
-        seed_bytes = ops.tensor([0], dtype=torch.uint8).new_empty(u0 * dt.itemsize)
-    src = tdist.get_global_rank(group, 0) if group is not None else 0
+    # one payload: the seed's key bytes followed by its first rows
+    isz = dt.itemsize
+    payload = ops.tensor([0], dtype=torch.uint8).new_empty(u0 * (isz + 8))
+    if rank == 0 and u0:
+        first0 = ops.to_torch(st.ifirstkey).to(torch.int64)
+        payload[: u0 * isz] = ops.col_bytes(ops.take_rows(col, first0))
+        payload[u0 * isz:] = first0.contiguous().view(torch.uint8)
     if u0:
-        tdist.broadcast(seed_bytes, src=src, group=group)
-        tdist.broadcast(seed_first, src=src, group=group)
-    tick.mark("seed (shard 0 prefix + broadcast)")
+        tdist.broadcast(payload, src=src, group=group)
+    seed_bytes = payload[: u0 * isz]
+    seed_first = payload[u0 * isz:].clone().view(torch.int64) if u0 else ops.tensor([0], dtype=torch.int64).new_empty(0)
+    tick.mark("prefix + seed broadcast")
 
-    # 2. every other rank pre-loads the seed, then all ranks hash their (remaining) rows
+    # 2. the other ranks adopt the seed, then all ranks hash the rest of their rows
     try:
-        if rank != 0 and u0:
-            st.push(ops.col_from_bytes(seed_bytes, dt, u0), None, 0, None)
-            if st.unique_count != u0:
-                raise RuntimeError("sharded_groupby: the broadcast seed holds duplicate keys")
-        lo = S if rank == 0 else 0
-        if n > lo:
-            push(lo, n, ikey[lo:n])
+        if rank != 0 and not failed:
+            st2 = new_stream()
+            if u0:
+                st2.push(ops.col_from_bytes(seed_bytes, dt, u0), None, 0, None)
+                if st2.unique_count != u0:
+                    raise RuntimeError("sharded_groupby: the broadcast seed holds duplicate keys")
+            u_loc = st.unique_count
+            if u_loc:
+                old_first = ops.to_torch(st.ifirstkey).to(torch.int64).clone()
+                newbins = st2.push(ops.take_rows(col, old_first), None, 0, None)   # local unique keys, local order
+                table = ops.bin_table(newbins)                                     # [0, new bin of local bin 1, ...]
+                u_mid = st2.unique_count
+                if u_mid > u0:  # first rows of the local keys the seed does not hold: positions in the chunk -> rows
+                    ops.stream_fix_first(st2, u0, u_mid, old_first)
+                ikey = ops.remap_prefix(ikey, S, table)
+                if fused:
+                    ops.stream_move_sums(st, st2, table, u_loc)
+            st = st2
+        if n > S and not failed:
+            push(st, S, n, ikey[S:n])
     except overflow:
         failed = True
     ikey = ikey[:n]
     U_r = st.unique_count
-    tick.mark("hash shard")
+    tick.mark("adopt seed + hash shard")
 
     # 3. late keys (rare): merge them across ranks
     late = ops.tensor([-1 if failed else U_r - u0], dtype=torch.int64)
@@ -940,10 +1002,10 @@ def sharded_group_from_lexsort(ops, key_cols, ascending=True, group=None, replic
     return out
 
 
-def sharded_groupby_sum(key_cols, values, group=None, ops=None):
+def sharded_groupby_sum(key_cols, values, group=None, ops=None, shard_sizes=None):
     """bench.py's multi-GPU step: sharded hash grouping + GB_SUM.  -> (ikey, ifirstkey, U, sums[U+1])."""
     ops = ops or CudaOps()
-    g = sharded_groupby(ops, key_cols, None, group, sum_values=values)
+    g = sharded_groupby(ops, key_cols, None, group, sum_values=values, shard_sizes=shard_sizes)
     if g.partial_sums is not None:
         # the grouping pass summed the shard as it went (fused kernel) and its bins are global: one all-reduce is left
         s = _combine("sum", {"v": g.partial_sums}, g.unique_count + 1, False, group, ALLTOALL_MIN_BINS)["v"]

@@ -133,6 +133,23 @@ class OracleOps:
     def can_stream(self, col):
         return col.dtype.kind in "biuf" and col.dtype.itemsize in (1, 2, 4, 8)
 
+    def bin_table(self, newbins):
+        return torch.cat([torch.zeros(1, dtype=torch.int32), newbins.to(torch.int32)])
+
+    def stream_fix_first(self, st, u0, u_mid, old_first):
+        st.first[u0:u_mid] = _np(old_first)[st.first[u0:u_mid].astype(np.int64)].astype(np.int32)
+
+    def remap_prefix(self, ikey, S, table):
+        if S:
+            ikey[:S] = table[ikey[:S].to(torch.int64)]
+        return ikey
+
+    def stream_move_sums(self, old, new, table, u_loc):
+        acc = np.zeros(max(len(new.acc), int(table.max()) + 1), dtype=old.acc.dtype)
+        acc[: len(new.acc)] = new.acc.astype(old.acc.dtype)
+        acc[_np(table).astype(np.int64)] = old.acc[: u_loc + 1]
+        new.acc = acc
+
     def slice_rows(self, col, lo, hi):
         return col[lo:hi]
 

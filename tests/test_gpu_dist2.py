@@ -54,6 +54,14 @@ def _worker(rank, world, port, n, q):
         fs = [torch.from_numpy(f[lo:hi]).cuda(), s[lo:hi]]
         g = rd.sharded_group_from_lexsort(ops, fs)
         out["gfl"] = {k_: (v_.cpu().numpy() if isinstance(v_, torch.Tensor) else v_) for k_, v_ in g.items()}
+        # the fused group-and-sum step of bench.py: with late keys (falls back to the merge + separate reduction), and
+        # with every key inside shard 0's seed prefix (sums come out of the grouping pass, one all-reduce)
+        kt = torch.from_numpy(k[lo:hi]).cuda()
+        for name, keys, seed_rows in (("gs_late", kt, 4096), ("gs_seeded", kt % (7919 * 700), 1 << 25), ("gs_seeded_small_prefix", kt % (7919 * 700), 65_536)):
+            rd.SEED_ROWS = seed_rows
+            for vname, vals in (("f64", vt), ("f32", vt.float()), ("i32", (vt * 100).to(torch.int32))):
+                gi, gf, gu, gs = rd.sharded_groupby_sum([keys], vals, ops=ops, shard_sizes=[n // 3, n - n // 3])
+                out[f"{name}_{vname}"] = (gi.cpu().numpy(), gf.cpu().numpy(), gu, gs.cpu().numpy())
         q.put((rank, out))
     finally:
         tdist.destroy_process_group()
@@ -111,3 +119,17 @@ def test_two_rank_nccl_paths():
     np.testing.assert_array_equal(g1["iFirstKey"], eifk)
     np.testing.assert_array_equal(g0["nCountGroup"], ecnt)
     np.testing.assert_array_equal(np.concatenate([g0["nCountGroup_owned"], g1["nCountGroup_owned"]]), ecnt[1:])
+    for name, keys in (("gs_late", k), ("gs_seeded", k % (7919 * 700)), ("gs_seeded_small_prefix", k % (7919 * 700))):
+        eik, eifk, eu = orc.MultiKeyGroupBy32([keys], 0, None, 2)
+        for vname, vals in (("f64", v), ("f32", v.astype(np.float32)), ("i32", (v * 100).astype(np.int32))):
+            exp = orc.GroupByAll32([vals], eik, eu, [0], [1], [eu + 1], 0)[0]
+            np.testing.assert_array_equal(np.concatenate([got[0][f"{name}_{vname}"][0], got[1][f"{name}_{vname}"][0]]), eik, err_msg=name)
+            for r in range(2):
+                gi, gf, gu, gs = got[r][f"{name}_{vname}"]
+                assert gu == eu
+                np.testing.assert_array_equal(gf, eifk, err_msg=name)
+                assert gs.dtype == exp.dtype
+                if vname == "i32":
+                    np.testing.assert_array_equal(gs[1:], exp[1:], err_msg=name)
+                else:
+                    np.testing.assert_allclose(gs[1:], exp[1:], rtol=1e-5 if vname == "f32" else 1e-12, atol=1e-3 if vname == "f32" else 1e-9, err_msg=name)

@@ -1280,19 +1280,12 @@ static uint32_t snap_cap_for(int64_t max_unique) {
   return c;
 }
 
-// Rows of the largest round a call over n rows can run: the geometric schedule, or the one round that finishes a
-// settled table's remainder (up to finish_rows rows, from any round boundary on) -- the first-row bitmap and its
-// prefix counts are sized by this.
+// Rows of the largest round a call over n rows can run.  The schedule depends on what the rounds find (geometric
+// growth, one round that finishes a settled table's remainder, a resumed chunk that starts settled), so the first-row
+// bitmap and its prefix counts are simply sized for the whole call: n / 4 bytes, touched only as far as a round reaches.
 static int64_t largest_round(int64_t n, const GbPlan& p) {
-  int64_t lo = 0, hi = p.round0 < n ? p.round0 : n, best = hi;
-  while (hi < n) {
-    lo = hi;
-    int64_t nh = hi * p.ratio;
-    hi = nh < n ? nh : n;
-    if (hi - lo > best) best = hi - lo;
-  }
-  const int64_t finish = n < p.finish_rows ? n : p.finish_rows;
-  return best > finish ? best : finish;
+  (void)p;
+  return n;
 }
 
 static GbLayout layout(void* ws, size_t wsbytes, int64_t nrows, int64_t max_unique, bool cutoffs, int64_t ncut,
@@ -1599,7 +1592,10 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
   int round = st->rounds;  // rounds since the table was created (0 = nothing known yet)
   int cround = 0;          // rounds of this chunk: every chunk restarts the geometric schedule with a small probe round
   while (lo < nrows) {
-    int64_t hi = cround == 0 ? plan.round0 : lo * plan.ratio;
+    // a chunk that resumes a settled table (nothing new in the previous chunk's last round) does not probe with a small
+    // round again: it starts with the largest round a settled table may take
+    const bool resumed_settled = cround == 0 && round > 0 && (double)prev_new <= plan.discovery_frac * (double)prev_rows;
+    int64_t hi = cround == 0 ? (resumed_settled ? plan.finish_rows : plan.round0) : lo * plan.ratio;
     // a settled table and a short remainder: one round to the end saves the host round trips of the schedule (a burst of
     // late keys then costs at most one repeat of this short round)
     if (cround > 0 && nrows - lo <= plan.finish_rows && (double)prev_new <= plan.discovery_frac * (double)prev_rows) hi = nrows;

@@ -1008,7 +1008,7 @@ def sharded_groupby_sum(key_cols, values, group=None, ops=None, shard_sizes=None
     g = sharded_groupby(ops, key_cols, None, group, sum_values=values, shard_sizes=shard_sizes)
     if g.partial_sums is not None:
         # the grouping pass summed the shard as it went (fused kernel) and its bins are global: one all-reduce is left
-        s = _combine("sum", {"v": g.partial_sums}, g.unique_count + 1, False, group, ALLTOALL_MIN_BINS)["v"]
+        s = _combine("sum", {"v": g.partial_sums[: g.unique_count + 1]}, g.unique_count + 1, False, group, ALLTOALL_MIN_BINS)["v"]
         vcol = ops.as_col(values)
         if ops.is_f32(vcol):
             s = s.to(torch.float32)

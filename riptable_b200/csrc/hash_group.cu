@@ -1203,6 +1203,167 @@ __global__ void __launch_bounds__(256) gb_renumber_partitions(int32_t* ikey, int
   }
 }
 
+
+// ---- small inputs: the whole grouping in ONE cooperative launch -----------------------------------------------------
+// Below kSmallRows rows the round schedule's host round trips (a counter read-back and two stream synchronisations per
+// round, 140-170 us per call) cost more than the work.  One cooperative kernel does it all, phases separated by grid
+// barriers: clear the table and the first-row bitmap | insert every row (CAS claim, atomicMin of the row; the row keeps
+// -(slot + 1)) | mark every claimed slot's first row in the bitmap | popcount-scan the bitmap (per-CTA totals, then the
+// prefix of every word) | rank each slot by its first row = its bin, write iFirstKey | rewrite the rows.  The table it
+// leaves behind has the standard format, so rtb_ismember32 probes it like any other.
+constexpr int64_t kSmallRows = 1 << 20;
+constexpr int kSmallPartials = 4096;  // upper bound of the cooperative grid (148 SMs x at most 4 CTAs)
+
+struct GbSmallArgs {
+  const void* keys;
+  const uint8_t* filter;
+  int32_t* ikey;
+  int32_t* ifirstkey;
+  Slot* table;
+  uint32_t* bitmap;   // one bit per row
+  uint32_t* prefix;   // set bits before each bitmap word
+  uint32_t* partial;  // per-CTA popcounts
+  uint32_t* result;   // [0] unique count, [1] overflow flag
+  int64_t n, max_unique;
+  uint32_t mask;      // capacity - 1
+};
+
+__device__ __forceinline__ uint32_t block_sum_256(uint32_t v, uint32_t* sh /* 9 */) {
+#pragma unroll
+  for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int i = 0; i < 8; i++) t += sh[i];
+    sh[8] = t;
+  }
+  __syncthreads();
+  const uint32_t r = sh[8];
+  __syncthreads();
+  return r;
+}
+
+template <int ISZ>
+__global__ void __launch_bounds__(256) gb_small_kernel(GbSmallArgs a) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ uint32_t sh[16];
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (int64_t)gridDim.x * blockDim.x;
+  const uint32_t cap = a.mask + 1, bmask = a.mask >> 1;
+  const int64_t words = (a.n + 31) >> 5;
+  // 0. clear
+  for (int64_t i = tid; i <= cap; i += nthreads) {
+    Slot e;
+    e.key = kEmpty; e.minrow = 0xFFFFFFFFu; e.nbin = 0xFFFFFFFFu;
+    a.table[i] = e;
+  }
+  for (int64_t w = tid; w < words; w += nthreads) a.bitmap[w] = 0;
+  grid.sync();
+  // 1. insert
+  for (int64_t r = tid; r < a.n; r += nthreads) {
+    int32_t o = 0;
+    if (!a.filter || a.filter[r]) {
+      const unsigned long long k = load_key1<ISZ>(a.keys, r);
+      uint32_t idx;
+      if (k == kEmpty) {  // the key that equals the empty marker lives in the extra slot
+        idx = cap;
+        atomicCAS(&a.table[idx].key, kEmpty, 0ull);
+      } else {
+        idx = (hash_u64(k) & bmask) * 2;
+        for (;;) {
+          const unsigned long long cur = *(volatile unsigned long long*)&a.table[idx].key;
+          if (cur == k) break;
+          if (cur == kEmpty) {
+            const unsigned long long old = atomicCAS(&a.table[idx].key, kEmpty, k);
+            if (old == kEmpty || old == k) break;
+          }
+          idx = (idx + 1) & a.mask;
+        }
+      }
+      atomicMin(&a.table[idx].minrow, (uint32_t)r);
+      o = -(int32_t)(idx + 1);
+    }
+    a.ikey[r] = o;
+  }
+  grid.sync();
+  // 2. first rows -> bitmap
+  for (int64_t i = tid; i <= cap; i += nthreads) {
+    const Slot e = a.table[i];
+    if (e.key != kEmpty) atomicOr(&a.bitmap[e.minrow >> 5], 1u << (e.minrow & 31));
+  }
+  grid.sync();
+  // 3. popcount scan: every CTA owns a contiguous range of words
+  const int64_t per = (words + gridDim.x - 1) / gridDim.x;
+  const int64_t w0 = (int64_t)blockIdx.x * per, w1 = w0 + per < words ? w0 + per : words;
+  {
+    uint32_t c = 0;
+    for (int64_t w = w0 + threadIdx.x; w < w1; w += blockDim.x) c += __popc(a.bitmap[w]);
+    c = block_sum_256(c, sh);
+    if (threadIdx.x == 0) a.partial[blockIdx.x] = c;
+  }
+  grid.sync();
+  {
+    uint32_t before = 0, total = 0;
+    for (uint32_t j = threadIdx.x; j < gridDim.x; j += blockDim.x) {
+      const uint32_t p = a.partial[j];
+      total += p;
+      if (j < blockIdx.x) before += p;
+    }
+    before = block_sum_256(before, sh);
+    total = block_sum_256(total, sh);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      a.result[0] = total;
+      a.result[1] = total > (uint32_t)a.max_unique ? 1u : 0u;
+    }
+    uint32_t run = before;
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    for (int64_t b0 = w0; b0 < w1; b0 += blockDim.x) {
+      const int64_t w = b0 + threadIdx.x;
+      const uint32_t v = w < w1 ? (uint32_t)__popc(a.bitmap[w]) : 0u;
+      uint32_t inc = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+      }
+      if (lane == 31) sh[wp] = inc;
+      __syncthreads();
+      uint32_t base = 0, chunk = 0;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        if (i < wp) base += sh[i];
+        chunk += sh[i];
+      }
+      if (w < w1) a.prefix[w] = run + base + inc - v;
+      run += chunk;
+      __syncthreads();
+    }
+  }
+  grid.sync();
+  // 4. bins
+  const bool overflow = a.result[1] != 0;
+  if (!overflow) {
+    for (int64_t i = tid; i <= cap; i += nthreads) {
+      const Slot e = a.table[i];
+      if (e.key != kEmpty) {
+        const uint32_t m = e.minrow;
+        const uint32_t bin = a.prefix[m >> 5] + __popc(a.bitmap[m >> 5] & ((1u << (m & 31)) - 1u)) + 1u;
+        a.table[i].nbin = ~bin;
+        a.ifirstkey[bin - 1] = (int32_t)m;
+      }
+    }
+  }
+  grid.sync();
+  // 5. rows
+  if (!overflow) {
+    for (int64_t r = tid; r < a.n; r += nthreads) {
+      const int32_t v = a.ikey[r];
+      if (v < 0) a.ikey[r] = (int32_t)a.table[-(v + 1)].bin();
+    }
+  }
+}
+
 // ---- host side -------------------------------------------------------------------------------------
 static uint32_t next_pow2_u64(uint64_t v) {
   uint64_t p = 1;
@@ -1217,6 +1378,7 @@ struct GbPlan {
   int packed_rows = 1;                // packed-row kernels for multi-key / string rows (0: by-reference kernel)
   int smem_table = 1;                 // shared-memory tables for settled low-cardinality rounds
   int prefetch = 1;                   // gb_round_direct: next tile's keys in flight during the probes
+  int small_path = 1;                 // inputs up to kSmallRows rows: one cooperative launch instead of the round schedule
   int fuse_prefetch = 0;              // the same for the fused (group-and-sum) form: 1 = 3 CTAs per SM with, 0 = 4 without
   double discovery_frac = 0.002;      // a round whose predecessor found more new keys than this share of its rows is a discovery round
   int ctas_per_sm = 4;                // gb_round_direct grid = 148 x this
@@ -1242,6 +1404,7 @@ static GbPlan get_plan() {
   if (const char* e = getenv("RTB_GB_SMEM")) p.smem_table = atoi(e);
   if (const char* e = getenv("RTB_GB_PREFETCH")) p.prefetch = atoi(e);
   if (const char* e = getenv("RTB_GB_FUSEPF")) p.fuse_prefetch = atoi(e);
+  if (const char* e = getenv("RTB_GB_SMALL")) p.small_path = atoi(e);
   if (const char* e = getenv("RTB_GB_CTAS")) p.ctas_per_sm = atoi(e);
   if (const char* e = getenv("RTB_GB_ROUND0")) p.round0 = atoll(e);
   if (const char* e = getenv("RTB_GB_LOAD")) p.load_target = atof(e);
@@ -1262,6 +1425,7 @@ struct GbLayout {
   uint32_t* prefix;
   uint32_t* scan_scratch;
   GbCounters* ctr;
+  uint32_t* small_partial;  // per-CTA popcounts of the single-launch small path (kSmallPartials entries)
   int32_t* pid;       // partition ids (cutoffs only)
   int64_t* cutoffs_dev;
   uint32_t* ucount;   // per-partition unique counts, then exclusive bases
@@ -1302,6 +1466,7 @@ static GbLayout layout(void* ws, size_t wsbytes, int64_t nrows, int64_t max_uniq
   L.prefix = a.take<uint32_t>((size_t)words);
   L.scan_scratch = a.take<uint32_t>(scan_u32_workspace_elems(words));
   L.ctr = a.take<GbCounters>(1);
+  L.small_partial = a.take<uint32_t>(kSmallPartials);
   L.pid = cutoffs ? a.take<int32_t>((size_t)nrows) : nullptr;
   L.cutoffs_dev = cutoffs ? a.take<int64_t>((size_t)ncut) : nullptr;
   L.ucount = cutoffs ? a.take<uint32_t>((size_t)ncut) : nullptr;
@@ -1583,6 +1748,74 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
   if (fuse && st->rounds == 0) RTB_CUDA(cudaMemsetAsync(fuse->acc, 0, sizeof(unsigned long long), stream));
   const bool fuse_values = fuse && fuse->values != nullptr;
   const bool fuse_kernel_ok = fuse_values && (fuse->vsz == 8 || fuse->vsz == 4) && ((uintptr_t)fuse->values % 16) == 0;
+  // ---- small one-shot inputs: a single cooperative launch (see gb_small_kernel)
+  if (direct && plan.small_path && st->rounds == 0 && row_offset == 0 && nrows <= kSmallRows) {
+    const uint32_t want_cap = next_pow2_u64((uint64_t)(2 * nrows < 1024 ? 1024 : 2 * nrows));
+    static int coop = -1, occ8 = 0, occ4 = 0, occ2 = 0, occ1 = 0;
+    if (coop < 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ8, gb_small_kernel<8>, 256, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4, gb_small_kernel<4>, 256, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, gb_small_kernel<2>, 256, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, gb_small_kernel<1>, 256, 0);
+      cudaGetLastError();
+    }
+    const int occ = dkey.itemsize == 8 ? occ8 : dkey.itemsize == 4 ? occ4 : dkey.itemsize == 2 ? occ2 : occ1;
+    if (coop > 0 && occ > 0 && want_cap <= capmax && max_unique >= 1) {
+      // one row per thread while the machine has room (the insert and rewrite phases are chains of dependent L2 round trips:
+      // few threads with many rows each made a 10 K-row call take 87 us); never more CTAs than can be resident at once
+      int64_t ctas = (nrows + 255) / 256;
+      const int64_t resident = (int64_t)kSMs * (occ < 4 ? occ : 4);
+      if (ctas > resident) ctas = resident;
+      if (ctas < 1) ctas = 1;
+      GbSmallArgs sa;
+      sa.keys = dkey.data; sa.filter = filter; sa.ikey = ikey_out; sa.ifirstkey = ifirstkey_out; sa.table = L.table;
+      sa.bitmap = L.bitmap; sa.prefix = L.prefix; sa.partial = L.small_partial; sa.result = (uint32_t*)L.ctr;
+      sa.n = nrows; sa.max_unique = max_unique; sa.mask = want_cap - 1;
+      void* kargs[] = {&sa};
+      const void* fn = dkey.itemsize == 8 ? (const void*)gb_small_kernel<8> : dkey.itemsize == 4 ? (const void*)gb_small_kernel<4>
+                       : dkey.itemsize == 2 ? (const void*)gb_small_kernel<2> : (const void*)gb_small_kernel<1>;
+      prof_begin(PROF_GB_ROUND, stream);
+      RTB_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)ctas), dim3(256), kargs, 0, stream));
+      RTB_LAUNCH_CHECK();
+      prof_end(PROF_GB_ROUND, stream, (uint64_t)nrows);
+      // the two result words come back through a page-locked buffer (a pageable target costs the driver a staging copy)
+      static thread_local uint32_t* pinned = nullptr;
+      if (!pinned && cudaHostAlloc((void**)&pinned, 64, cudaHostAllocDefault) != cudaSuccess) {
+        pinned = nullptr;
+        cudaGetLastError();
+      }
+      uint32_t res_local[2] = {0, 0};
+      uint32_t* res = pinned ? pinned : res_local;
+      RTB_CUDA(cudaMemcpyAsync(res, L.ctr, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+      RTB_CUDA(cudaStreamSynchronize(stream));
+      if (res[1]) {
+        if (needed_unique_host) *needed_unique_host = (int64_t)res[0];
+        set_error("MultiKeyGroupBy32: more than %lld unique keys; retry with max_unique >= %u", (long long)max_unique, res[0]);
+        return RTB_ERR_WORKSPACE;
+      }
+      const int64_t Us = (int64_t)res[0];
+      if (fuse && fuse->values) {
+        RTB_CUDA(cudaMemsetAsync(fuse->acc, 0, sizeof(unsigned long long) * (size_t)(Us + 1), stream));
+        int rc = accum_sum_rows(fuse->values, fuse->vdt, ikey_out, RTB_I32, nrows, Us + 1, fuse->bin_low, fuse->nanskip, fuse->acc, stream);
+        if (rc != RTB_OK) return rc;
+        RTB_CUDA(cudaStreamSynchronize(stream));
+      } else if (fuse) {
+        RTB_CUDA(cudaMemsetAsync(fuse->acc, 0, sizeof(unsigned long long) * (size_t)(Us + 1), stream));
+      }
+      st->cap = want_cap;
+      st->unique = Us;
+      st->prev_new = Us;
+      st->prev_rows = nrows;
+      st->rounds = 1;
+      st->max_unique = max_unique;
+      *unique_count_host = Us;
+      return RTB_OK;
+    }
+  }
+
   uint32_t snap_cap = 0;   // inline-key snapshot (16-byte packed rows): entries in use, bins it holds
   int64_t snap_built = 0;
   uint32_t cap = st->cap;

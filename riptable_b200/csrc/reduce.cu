@@ -23,7 +23,8 @@ namespace rtb {
 #ifndef RTB_ACCUM_MIN_CTAS
 #define RTB_ACCUM_MIN_CTAS 1
 #endif
-constexpr int64_t kSmemBins = 3584;  // 13 B/bin keeps the CTA under the 48 KB default dynamic smem limit
+constexpr int64_t kSmemBins = 3584;      // 13 B/bin keeps the CTA under the 48 KB default dynamic smem limit
+constexpr int64_t kSmemBinsBig = 16384;  // with the opt-in limit (213 KB): one 1024-thread CTA per SM
 
 enum AccOp { OP_SUMF = 0, OP_SUMI = 1, OP_MEAN = 2, OP_MINMAX = 3, OP_M2 = 4, OP_COUNT = 5 };
 
@@ -76,8 +77,8 @@ __device__ __forceinline__ unsigned long long acc_identity(int ismax) {
   return OP == OP_MINMAX ? (ismax ? 0ull : ~0ull) : 0ull;
 }
 
-template <int OP, bool SMEM>
-__global__ void __launch_bounds__(256, RTB_ACCUM_MIN_CTAS) accum_kernel(AccumArgs a) {
+template <int OP, bool SMEM, int THREADS = 256>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? RTB_ACCUM_MIN_CTAS : 1) accum_kernel(AccumArgs a) {
   extern __shared__ unsigned long long smem_raw[];
   unsigned long long* acc = a.acc;
   uint32_t* cnt = a.cnt;
@@ -224,6 +225,17 @@ static int launch_accum(const AccumArgs& a, cudaStream_t stream) {
     // enough CTAs to fill the machine, few enough that the per-CTA flush stays negligible
     int grid = grid_for(a.n, 256, 4 * 8, 4);
     accum_kernel<OP, true><<<grid, 256, smem, stream>>>(a);
+  } else if (a.nb <= kSmemBinsBig && a.n >= (int64_t)kSMs * 1024 * 64) {
+    // up to 16 Ki bins still fit one SM's shared memory (opt-in limit): one 1024-thread CTA per SM keeps its own copy of
+    // the accumulators; worth it once every CTA has enough rows to amortise clearing and flushing them
+    static bool attr = false;
+    if (!attr) {
+      RTB_CUDA(cudaFuncSetAttribute(accum_kernel<OP, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(kSmemBinsBig * (8 + 4 + 1) + 16)));
+      attr = true;
+    }
+    size_t smem = (size_t)a.nb * (8 + 4 + 1) + 16;
+    accum_kernel<OP, true, 1024><<<kSMs, 1024, smem, stream>>>(a);
   } else {
     // one CTA per `tiles_per_cta` 128-row tiles (8192 rows by default)
     static const int tiles_per_cta = getenv("RTB_ACCUM_TILES") ? atoi(getenv("RTB_ACCUM_TILES")) : 64;

@@ -328,8 +328,8 @@ def MultiKeyGroupBy32(list_arrays, hint_size=0, filter=None, hash_mode=2, cutoff
     u = int(ucount.value)
     ifirst = DevArray(ifirst.buf, np.int32, u)
     ik, ifk = _from_dev(ikey, device_mode), _from_dev(ifirst, device_mode)
-    if device_mode and u < max_unique // 2:
-        ifk = ifk.clone()  # do not pin a max_unique-sized buffer behind a small result
+    if device_mode and u < max_unique // 2 and max_unique > (4 << 20):
+        ifk = ifk.clone()  # do not pin a large max_unique-sized buffer behind a small result
     if cut is not None:
         return ik, (ifk, ucut), u
     return ik, ifk, u
@@ -388,8 +388,8 @@ def MultiKeyGroupBySum32(list_arrays, values, hint_size=0, filter=None, hash_mod
     ifirst = DevArray(ifirst.buf, np.int32, u)
     sums = DevArray(sums.buf, odt, u + 1)
     ik, ifk, sm = _from_dev(ikey, device_mode), _from_dev(ifirst, device_mode), _from_dev(sums, device_mode)
-    if device_mode and u < max_unique // 2:
-        ifk, sm = ifk.clone(), sm.clone()  # do not pin max_unique-sized buffers behind small results
+    if device_mode and u < max_unique // 2 and max_unique > (4 << 20):
+        ifk, sm = ifk.clone(), sm.clone()  # do not pin large max_unique-sized buffers behind small results
     return ik, ifk, u, sm
 
 

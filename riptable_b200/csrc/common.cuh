@@ -92,25 +92,40 @@ inline int grid_for(int64_t work_items, int threads, int items_per_thread, int m
 }
 
 // ---- streaming loads / stores: keep the one-pass row streams out of the way of L2-resident tables
+// RTB_STREAM_CS=1 (measurement build): the `.cs` ("cache streaming, likely accessed once": evict-first in L1 and L2) forms
+// instead of `.nc.L1::no_allocate`, to see whether the key / value / iKey streams can be kept from evicting the hash table.
+#ifndef RTB_STREAM_CS
+#define RTB_STREAM_CS 0
+#endif
+#if RTB_STREAM_CS
+#define RTB_LD_STREAM "ld.global.cs"
+#define RTB_ST_STREAM "st.global.cs"
+#else
+#define RTB_LD_STREAM "ld.global.nc.L1::no_allocate"
+#define RTB_ST_STREAM "st.global.L1::no_allocate"
+#endif
 __device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
   uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+  asm volatile(RTB_LD_STREAM ".v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
 __device__ __forceinline__ uint2 ld_stream_u2(const void* p) {
   uint2 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  asm volatile(RTB_LD_STREAM ".v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
   return r;
 }
 __device__ __forceinline__ uint32_t ld_stream_u32(const void* p) {
   uint32_t r;
-  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  asm volatile(RTB_LD_STREAM ".u32 %0, [%1];" : "=r"(r) : "l"(p));
   return r;
 }
 __device__ __forceinline__ void st_stream_u4(void* p, uint4 v) {
-  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+  asm volatile(RTB_ST_STREAM ".v4.u32 [%0], {%1,%2,%3,%4};"
                :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_stream_u2(void* p, uint2 v) {
+  asm volatile(RTB_ST_STREAM ".v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
 
 // ---- iKey loads (int8/16/32/64 -> int64), 4 consecutive rows at r (r % 4 == 0, r+3 < n)

@@ -81,10 +81,21 @@ __device__ __forceinline__ Slot load_slot(const Slot* s) {
 struct Bucket {
   unsigned long long k0, w0, k1, w1;  // w = minrow | (nbin << 32)
 };
+// RTB_TABLE_EL=1 (measurement build): the bucket load carries an L2 evict-last policy.
+#ifndef RTB_TABLE_EL
+#define RTB_TABLE_EL 0
+#endif
 __device__ __forceinline__ Bucket load_bucket(const Slot* table, uint32_t b) {
   Bucket p;
+#if RTB_TABLE_EL
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("ld.global.L2::cache_hint.v4.b64 {%0,%1,%2,%3}, [%4], %5;"
+               : "=l"(p.k0), "=l"(p.w0), "=l"(p.k1), "=l"(p.w1) : "l"(table + 2 * (size_t)b), "l"(pol));
+#else
   asm volatile("ld.global.v4.b64 {%0,%1,%2,%3}, [%4];"
                : "=l"(p.k0), "=l"(p.w0), "=l"(p.k1), "=l"(p.w1) : "l"(table + 2 * (size_t)b));
+#endif
   return p;
 }
 
@@ -349,8 +360,13 @@ __global__ void __launch_bounds__(256, (FUSE && PREFETCH) ? 3 : 4) gb_round_dire
           o[i] = resolve_direct(table, mask, k[i], 2 * b[i], (uint32_t)(tb + tile_row<ISZ, PAIR>(lane, i)), newlist, ctr, new_limit);
     }
     if (PAIR) {
+#if RTB_STREAM_CS
+      st_stream_u2(ikey + tb + 2 * lane, make_uint2((uint32_t)o[0], (uint32_t)o[1]));
+      st_stream_u2(ikey + tb + 64 + 2 * lane, make_uint2((uint32_t)o[2], (uint32_t)o[3]));
+#else
       *(int2*)(ikey + tb + 2 * lane) = make_int2(o[0], o[1]);
       *(int2*)(ikey + tb + 64 + 2 * lane) = make_int2(o[2], o[3]);
+#endif
     } else {
       st_stream_u4(ikey + tb + 4 * lane, make_uint4((uint32_t)o[0], (uint32_t)o[1], (uint32_t)o[2], (uint32_t)o[3]));
     }

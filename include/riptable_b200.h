@@ -141,6 +141,18 @@ int rtb_multikey_groupby_sum32_chunk(const rtb_column* key, int64_t nrows, const
                                      int64_t max_unique, void* acc, int64_t row_offset, rtb_gb_state* state, int resume,
                                      int64_t* needed_unique_host, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Row shards (riptable_b200/dist.py): re-label a resumable grouping with a SEED, in place.  The grouping has so far numbered
+ * its keys locally (state->unique bins); `seed_keys` holds nseed distinct keys whose bins are 1..nseed in seed order (the bins
+ * the first shard gave them).  Afterwards seed keys have their seed bin (those the table lacked are inserted), the local keys
+ * the seed lacks are numbered nseed + 1 .. in their local first-appearance order (*nlate_host of them), iFirstKey and the
+ * accumulators `acc` (NULL, or the raw accumulators of rtb_multikey_groupby_sum32_chunk) are permuted accordingly (seed bins
+ * without a local row get iFirstKey -1), and map_out[old bin] = new bin (state->unique + 1 entries, map_out[0] = 0) lets the
+ * caller re-index the iKey it already holds (rtb_remap_ikey).  RTB_ERR_UNSUPPORTED: the table has no room for nseed more keys
+ * (the caller then builds a fresh table from the seed instead).  Same workspace as the chunk calls. */
+int rtb_multikey_groupby32_adopt_seed(const rtb_column* seed_keys, int64_t nseed, int32_t* ifirstkey, int64_t max_unique,
+                                      void* acc, rtb_gb_state* state, int32_t* map_out, int64_t* nlate_host, void* workspace,
+                                      size_t workspace_bytes, void* stream);
+
 /* ---- 8f.1: rc.IsMember32(a, b, h, hint) / rc.IsMemberCategorical — riptable/rt_numpy.py:1388-1391, one numeric key
  * column of the same dtype on both sides.  found_out uint8[na]; index_out (index_dtype: an int rtb_dtype chosen by
  * len(b), riptable/rt_enum.py:666-679) = position of the first occurrence of a[i] in b, + base_index; absent rows get

@@ -1380,6 +1380,72 @@ __global__ void __launch_bounds__(256) gb_small_kernel(GbSmallArgs a) {
   }
 }
 
+
+// ---- adopting a seed (row shards, riptable_b200/dist.py) --------------------------------------------------------------
+// A shard that has grouped a prefix of its rows under LOCAL bins receives the seed: u0 distinct keys whose bins are
+// 1..u0 in seed order (the bins shard 0 gave them = the global bins).  The table is re-labelled in place: seed keys found
+// in it take their seed bin, seed keys it lacks are inserted (first row unknown: 0xFFFFFFFF), local keys the seed lacks
+// ("late" keys) are numbered u0 + 1 .. in their local first-appearance order.  `map` (old bin -> new bin) lets the caller
+// re-index the prefix's iKey; iFirstKey and the accumulators are permuted here.
+template <int ISZ>
+__global__ void __launch_bounds__(256) gb_adopt_probe_kernel(const void* __restrict__ seed, int64_t u0, Slot* table, uint32_t mask,
+                                                             int32_t* __restrict__ map) {
+  const uint32_t bmask = mask >> 1;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < u0; j += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long k = load_key1<ISZ>(seed, j);
+    const uint32_t gbin = (uint32_t)(j + 1);
+    uint32_t idx;
+    if (k == kEmpty) {
+      idx = mask + 1;
+      const unsigned long long old = atomicCAS(&table[idx].key, kEmpty, 0ull);
+      if (old == kEmpty) {
+        table[idx].nbin = ~gbin;  // fresh: minrow stays 0xFFFFFFFF
+        continue;
+      }
+    } else {
+      idx = (hash_u64(k) & bmask) * 2;
+      bool fresh = false;
+      for (;;) {
+        const unsigned long long cur = *(volatile unsigned long long*)&table[idx].key;
+        if (cur == k) break;
+        if (cur == kEmpty) {
+          const unsigned long long old = atomicCAS(&table[idx].key, kEmpty, k);
+          if (old == kEmpty) { fresh = true; break; }
+          if (old == k) break;
+        }
+        idx = (idx + 1) & mask;
+      }
+      if (fresh) {
+        table[idx].nbin = ~gbin;
+        continue;
+      }
+    }
+    map[table[idx].bin()] = (int32_t)gbin;  // a local key: its slot is re-labelled by gb_adopt_relabel_kernel
+  }
+}
+__global__ void __launch_bounds__(256) gb_adopt_late_flags_kernel(const int32_t* __restrict__ map, int64_t u_loc, uint32_t* __restrict__ flags) {
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < u_loc; b += (int64_t)gridDim.x * blockDim.x)
+    flags[b] = map[b + 1] == 0 ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256) gb_adopt_late_bins_kernel(int32_t* __restrict__ map, int64_t u_loc, const uint32_t* __restrict__ flags,
+                                                                 const uint32_t* __restrict__ excl, uint32_t u0) {
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < u_loc; b += (int64_t)gridDim.x * blockDim.x)
+    if (flags[b]) map[b + 1] = (int32_t)(u0 + 1 + excl[b]);
+}
+__global__ void __launch_bounds__(256) gb_adopt_relabel_kernel(Slot* table, uint32_t nslots, const int32_t* __restrict__ map) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nslots; i += gridDim.x * blockDim.x) {
+    const Slot e = table[i];
+    if (e.key != kEmpty && e.minrow != 0xFFFFFFFFu) table[i].nbin = ~(uint32_t)map[e.bin()];
+  }
+}
+// out[map[b] - shift] = in[b] for b in [first, u_loc]; item = 4 or 8 bytes
+template <typename T>
+__global__ void __launch_bounds__(256) gb_adopt_permute_kernel(const T* __restrict__ in, T* __restrict__ out, const int32_t* __restrict__ map,
+                                                               int64_t first, int64_t u_loc, int shift) {
+  for (int64_t b = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b <= u_loc; b += (int64_t)gridDim.x * blockDim.x)
+    out[map[b] - shift] = in[b - shift];
+}
+
 // ---- host side -------------------------------------------------------------------------------------
 static uint32_t next_pow2_u64(uint64_t v) {
   uint64_t p = 1;
@@ -2344,6 +2410,86 @@ extern "C" int rtb_multikey_groupby_sum32_chunk(const rtb_column* key, int64_t n
   int64_t u = 0;
   return gb_core(key, 1, nrows, filter, nullptr, 0, ikey_out, ifirstkey_out, max_unique, &u, nullptr, needed_unique_host,
                  workspace, (size_t)((uint8_t*)fz.snap - (uint8_t*)workspace), (cudaStream_t)stream_, state, row_offset, &fz);
+}
+
+extern "C" int rtb_multikey_groupby32_adopt_seed(const rtb_column* seed_keys, int64_t nseed, int32_t* ifirstkey,
+                                                 int64_t max_unique, void* acc, rtb_gb_state* state, int32_t* map_out,
+                                                 int64_t* nlate_host, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RTB_ARG(seed_keys && state && map_out && nlate_host && ifirstkey, "adopt seed: null argument");
+  RTB_ARG(seed_keys->itemsize == 1 || seed_keys->itemsize == 2 || seed_keys->itemsize == 4 || seed_keys->itemsize == 8,
+          "adopt seed: one key column of 1, 2, 4 or 8 bytes");
+  RTB_ARG(nseed >= 0 && nseed <= 2147483646ll && state->max_unique == max_unique && state->cap != 0, "adopt seed: bad sizes or a fresh state");
+  RTB_ARG(nseed == 0 || seed_keys->data, "adopt seed: null seed");
+  *nlate_host = 0;
+  const int64_t u_loc = state->unique;
+  const uint32_t cap = state->cap;
+  GbPlan plan = get_plan();
+  // every seed key may be new to the table: it must have the room, and the bins must fit the provisioned arrays
+  if ((double)(u_loc + nseed) > (double)cap * plan.load_abort || u_loc + nseed > max_unique) {
+    set_error("adopt seed: the table has no room for %lld more keys", (long long)nseed);
+    return RTB_ERR_UNSUPPORTED;
+  }
+  GbLayout L = layout(workspace, workspace_bytes, 1, max_unique, false, 0);
+  RTB_ARG(workspace && L.bytes <= workspace_bytes, "adopt seed: workspace too small");
+  // scratch inside the staging area (16 bytes per provisioned bin): [flags | excl | scan scratch], later the permuted copies
+  uint8_t* scratch = (uint8_t*)L.staged;
+  const size_t scratch_bytes = sizeof(Slot) * ((size_t)max_unique + 1);
+  uint32_t* flags = (uint32_t*)scratch;
+  uint32_t* excl = flags + u_loc + 4;
+  uint32_t* scan_scratch = excl + u_loc + 4;
+  const size_t scan_elems = scan_u32_workspace_elems(u_loc > 0 ? u_loc : 1) + 8;
+  RTB_ARG((size_t)((uint8_t*)(scan_scratch + scan_elems) - scratch) <= scratch_bytes, "adopt seed: workspace too small for the scan");
+  RTB_CUDA(cudaMemsetAsync(map_out, 0, sizeof(int32_t) * (size_t)(u_loc + 1), stream));
+  if (nseed > 0) {
+    const int g = grid_for(nseed, 256, 1);
+    switch (seed_keys->itemsize) {
+      case 8: gb_adopt_probe_kernel<8><<<g, 256, 0, stream>>>(seed_keys->data, nseed, L.table, cap - 1, map_out); break;
+      case 4: gb_adopt_probe_kernel<4><<<g, 256, 0, stream>>>(seed_keys->data, nseed, L.table, cap - 1, map_out); break;
+      case 2: gb_adopt_probe_kernel<2><<<g, 256, 0, stream>>>(seed_keys->data, nseed, L.table, cap - 1, map_out); break;
+      default: gb_adopt_probe_kernel<1><<<g, 256, 0, stream>>>(seed_keys->data, nseed, L.table, cap - 1, map_out);
+    }
+    RTB_LAUNCH_CHECK();
+  }
+  uint32_t nlate = 0;
+  if (u_loc > 0) {
+    uint32_t* total_dev = scan_scratch + scan_elems - 4;
+    gb_adopt_late_flags_kernel<<<grid_for(u_loc, 256, 1), 256, 0, stream>>>(map_out, u_loc, flags);
+    RTB_LAUNCH_CHECK();
+    int rc = exclusive_scan_u32(flags, excl, u_loc, SCAN_IDENTITY, scan_scratch, total_dev, stream);
+    if (rc != RTB_OK) return rc;
+    gb_adopt_late_bins_kernel<<<grid_for(u_loc, 256, 1), 256, 0, stream>>>(map_out, u_loc, flags, excl, (uint32_t)nseed);
+    RTB_LAUNCH_CHECK();
+    gb_adopt_relabel_kernel<<<grid_for((int64_t)cap + 1, 256, 1), 256, 0, stream>>>(L.table, cap + 1, map_out);
+    RTB_LAUNCH_CHECK();
+    RTB_CUDA(cudaMemcpyAsync(&nlate, total_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    RTB_CUDA(cudaStreamSynchronize(stream));
+  }
+  const int64_t u_new = nseed + (int64_t)nlate;
+  // iFirstKey: seed bins this shard has not seen get -1, the others keep their local first rows under the new numbering
+  {
+    int32_t* tmp = (int32_t*)scratch;
+    RTB_CUDA(cudaMemsetAsync(tmp, 0xFF, sizeof(int32_t) * (size_t)(u_new > 0 ? u_new : 1), stream));
+    if (u_loc > 0) {
+      gb_adopt_permute_kernel<int32_t><<<grid_for(u_loc, 256, 1), 256, 0, stream>>>(ifirstkey, tmp, map_out, 1, u_loc, 1);
+      RTB_LAUNCH_CHECK();
+    }
+    RTB_CUDA(cudaMemcpyAsync(ifirstkey, tmp, sizeof(int32_t) * (size_t)u_new, cudaMemcpyDeviceToDevice, stream));
+  }
+  if (acc) {
+    unsigned long long* tmp = (unsigned long long*)scratch;  // stream order: the iFirstKey copy above is done by now
+    RTB_CUDA(cudaMemsetAsync(tmp, 0, sizeof(unsigned long long) * (size_t)(u_new + 1), stream));
+    gb_adopt_permute_kernel<unsigned long long><<<grid_for(u_loc + 1, 256, 1), 256, 0, stream>>>((const unsigned long long*)acc, tmp,
+                                                                                                   map_out, 0, u_loc, 0);
+    RTB_LAUNCH_CHECK();
+    RTB_CUDA(cudaMemcpyAsync(acc, tmp, sizeof(unsigned long long) * (size_t)(u_new + 1), cudaMemcpyDeviceToDevice, stream));
+  }
+  RTB_CUDA(cudaStreamSynchronize(stream));
+  state->unique = u_new;
+  state->prev_new = 0;  // the table is settled: the next chunk starts with a large round
+  state->prev_rows = u_new > 0 ? u_new : 1;
+  *nlate_host = (int64_t)nlate;
+  return RTB_OK;
 }
 
 struct IsMemberLayout {

@@ -418,23 +418,31 @@ def _sharded_groupby_seeded(ops, col, filter, group, sum_values=None, shard_size
     # 2. the other ranks adopt the seed, then all ranks hash the rest of their rows
     try:
         if rank != 0 and not failed:
-            st2 = new_stream()
-            if u0:
-                st2.push(ops.col_from_bytes(seed_bytes, dt, u0), None, 0, None)
-                if st2.unique_count != u0:
-                    raise RuntimeError("sharded_groupby: the broadcast seed holds duplicate keys")
-            u_loc = st.unique_count
-            if u_loc:
-                old_first = ops.to_torch(st.ifirstkey).to(torch.int64).clone()
-                newbins = st2.push(ops.take_rows(col, old_first), None, 0, None)   # local unique keys, local order
-                table = ops.bin_table(newbins)                                     # [0, new bin of local bin 1, ...]
-                u_mid = st2.unique_count
-                if u_mid > u0:  # first rows of the local keys the seed does not hold: positions in the chunk -> rows
-                    ops.stream_fix_first(st2, u0, u_mid, old_first)
-                ikey = ops.remap_prefix(ikey, S, table)
-                if fused:
-                    ops.stream_move_sums(st, st2, table, u_loc)
-            st = st2
+            seed_col = ops.col_from_bytes(seed_bytes, dt, u0)
+            table = st.adopt_seed(seed_col) if (u0 and hasattr(st, "adopt_seed")) else None
+            if table is not None:
+                # the table was re-labelled in place (first rows and partial sums with it): only the prefix's iKey is left
+                ikey = ops.remap_prefix(ikey, S, ops.to_torch(table))
+            else:
+                # no room in the local table (or no local prefix): a fresh table loaded with the seed, the local unique
+                # keys pushed through it as one chunk, and the prefix re-indexed through the resulting U-sized map
+                st2 = new_stream()
+                if u0:
+                    st2.push(seed_col, None, 0, None)
+                    if st2.unique_count != u0:
+                        raise RuntimeError("sharded_groupby: the broadcast seed holds duplicate keys")
+                u_loc = st.unique_count
+                if u_loc:
+                    old_first = ops.to_torch(st.ifirstkey).to(torch.int64).clone()
+                    newbins = st2.push(ops.take_rows(col, old_first), None, 0, None)   # local unique keys, local order
+                    table = ops.bin_table(newbins)                                     # [0, new bin of local bin 1, ...]
+                    u_mid = st2.unique_count
+                    if u_mid > u0:  # first rows of the local keys the seed does not hold: positions in the chunk -> rows
+                        ops.stream_fix_first(st2, u0, u_mid, old_first)
+                    ikey = ops.remap_prefix(ikey, S, table)
+                    if fused:
+                        ops.stream_move_sums(st, st2, table, u_loc)
+                st = st2
         if n > S and not failed:
             push(st, S, n, ikey[S:n])
     except overflow:

@@ -457,6 +457,27 @@ class GroupByStream:
         a = self._acc[: self.unique_count + 1]
         return a.view(torch.float64) if self._vdtype is not None and self._vdtype.kind == "f" else a
 
+    def adopt_seed(self, seed_keys):
+        """Re-label this grouping with a seed, in place (rtb_multikey_groupby32_adopt_seed): `seed_keys` are distinct keys
+        whose bins become 1..len(seed_keys); local keys the seed lacks follow in their first-appearance order.
+        -> int32 CUDA tensor map[old bin] = new bin (re-index already returned iKey with it), or None when the table has
+        no room for the seed (build a fresh stream from the seed instead)."""
+        if not self._started:
+            return None
+        sk = _to_dev(seed_keys)
+        u_loc = self.unique_count
+        mp = torch.empty(u_loc + 4, dtype=torch.int32, device=_device())
+        nlate = C.c_int64(0)
+        col = _col(sk)
+        rc_ = lib.rtb_multikey_groupby32_adopt_seed(
+            C.byref(col), sk.n, C.c_void_p(self.ifirst.ptr), self.max_unique,
+            C.c_void_p(self._acc.data_ptr()) if self.with_sums else None, C.byref(self.state), C.c_void_p(mp.data_ptr()),
+            C.byref(nlate), C.c_void_p(self._ws.data_ptr()), self._ws.numel(), _stream())
+        if rc_ == _lib.RTB_ERR_UNSUPPORTED:
+            return None
+        check(rc_)
+        return mp[: u_loc + 1]
+
     def push(self, keys, filter=None, row_offset: int = 0, out=None, values=None):
         k = _to_dev(keys)
         if k.n > self.max_chunk_rows:

@@ -692,3 +692,44 @@ def test_small_inputs_single_launch_path(rc, n):
     ef, ei = orc.IsMember32(rng.integers(0, 50, 0).astype(np.int64), k) if False else (None, None)
     v = rng.random(n)
     _check_fused(rc, [k], v)
+
+
+@pytest.mark.parametrize("kdt", [np.int64, np.int32, np.uint8])
+@pytest.mark.parametrize("with_sums", [False, True])
+def test_groupby_stream_adopt_seed(rc, kdt, with_sums):
+    """rtb_multikey_groupby32_adopt_seed: a stream that numbered a prefix locally is re-labelled with a seed in place.
+    Afterwards it must behave exactly like a stream that had been pre-loaded with the seed: the oracle groups
+    [seed ; prefix ; rest] as one array."""
+    import torch
+
+    rng = np.random.default_rng(12)
+    small = np.dtype(kdt).itemsize == 1
+    pool = (np.arange(200) if small else rng.integers(-(2**30), 2**30, 6000)).astype(kdt)
+    npre, nrest = 1_500_000, 2_000_000
+    prefix = pool[rng.integers(0, len(pool) * 2 // 3, npre)]
+    rest = pool[rng.integers(0, len(pool), nrest)]
+    # the seed: some keys the prefix has, some it lacks, in an order of its own; the key -1 (empty marker for int64) included
+    seed = rng.permutation(np.unique(np.r_[pool[len(pool) // 3:], np.array([-1 if not small else 255]).astype(kdt)]))
+    vpre, vrest = rng.random(npre), rng.random(nrest)
+    st = rc.GroupByStream(1 << 20, 2_000_000, with_sums=with_sums)
+    kw = {"values": torch.from_numpy(vpre).cuda()} if with_sums else {}
+    ik_pre = st.push(torch.from_numpy(prefix).cuda(), None, 0, None, **kw).clone()
+    u_loc = st.unique_count
+    mp = st.adopt_seed(torch.from_numpy(seed).cuda())
+    assert mp is not None and mp.numel() == u_loc + 1 and int(mp[0]) == 0
+    ik_pre = mp[ik_pre.long()]
+    kw = {"values": torch.from_numpy(vrest).cuda()} if with_sums else {}
+    ik_rest = st.push(torch.from_numpy(rest).cuda(), None, npre, None, **kw)
+    allk = np.concatenate([seed, prefix, rest])
+    ok, ofk, ou = orc.MultiKeyGroupBy32([allk])
+    u0 = len(seed)
+    np.testing.assert_array_equal(ok[:u0], np.arange(1, u0 + 1))
+    np.testing.assert_array_equal(ik_pre.cpu().numpy(), ok[u0:u0 + npre])
+    np.testing.assert_array_equal(ik_rest.cpu().numpy(), ok[u0 + npre:])
+    assert st.unique_count == ou
+    # first rows of the keys outside the seed are the shard's own rows
+    ifk = st.ifirstkey.cpu().numpy()
+    np.testing.assert_array_equal(ifk[u0:], ofk[u0:] - u0)
+    if with_sums:
+        exp = orc.GroupByAll32([np.concatenate([vpre, vrest])], ok[u0:], ou, [0], [1], [ou + 1], 0)[0]
+        np.testing.assert_allclose(st.sums().cpu().numpy()[1:], exp[1:], rtol=1e-12, atol=1e-9)

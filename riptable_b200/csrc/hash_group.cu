@@ -2128,9 +2128,18 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
       prof_end(PROF_GB_ROUND, stream, (uint64_t)rows);
       cudaEvent_t tev1 = nullptr;
       if (trace) { cudaEventCreate(&tev1); cudaEventRecord(tev1, stream); }
-      GbCounters h;
-      RTB_CUDA(cudaMemcpyAsync(&h, L.ctr, sizeof(h), cudaMemcpyDeviceToHost, stream));
+      // the round's counters come back through a page-locked buffer (a pageable target costs the driver a staging copy
+      // on every round)
+      static thread_local GbCounters* pinned_ctr = nullptr;
+      if (!pinned_ctr && cudaHostAlloc((void**)&pinned_ctr, sizeof(GbCounters), cudaHostAllocDefault) != cudaSuccess) {
+        pinned_ctr = nullptr;
+        cudaGetLastError();
+      }
+      GbCounters h_local;
+      GbCounters* hp = pinned_ctr ? pinned_ctr : &h_local;
+      RTB_CUDA(cudaMemcpyAsync(hp, L.ctr, sizeof(GbCounters), cudaMemcpyDeviceToHost, stream));
       RTB_CUDA(cudaStreamSynchronize(stream));
+      const GbCounters h = *hp;
       if (trace) {
         float tms = 0.f;
         cudaEventElapsedTime(&tms, tev0, tev1);

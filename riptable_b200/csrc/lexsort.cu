@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "keycols.cuh"
 #include "radix.cuh"
+#include "values.cuh"
 
 namespace rtb {
 
@@ -149,6 +150,37 @@ __global__ void __launch_bounds__(256) lexgroup_flags_kernel(KeyCols kc, const i
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride)
     flags[j] = (j == 0 || !rows_equal(kc, igroup[j], igroup[j - 1])) ? 1u : 0u;
+}
+
+// The same for up to four columns of 1 / 2 / 4 / 8-byte items (the numeric case).  The row fetches are random DRAM accesses
+// and the whole cost of this call, so as few as possible are made: columns are compared from the LAST one backwards (in
+// sorted order the least significant key is the one that tells neighbours apart), a lane stops at its first difference, a
+// column is fetched once per position -- the predecessor's value comes from the lane below (lane 0 fetches it) -- and only
+// while this position or the next still needs it, and the warp leaves the loop when every lane has its answer.
+template <int NC>
+__global__ void __launch_bounds__(256) lexgroup_flags_numeric_kernel(KeyCols kc, const int32_t* __restrict__ igroup, int64_t m,
+                                                                     uint32_t* __restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < m; base += stride) {
+    const int64_t j = base + lane;
+    const bool valid = j < m;
+    const int64_t row = valid ? igroup[j] : 0;
+    const int64_t prow = (lane == 0 && valid && j > 0) ? igroup[j - 1] : 0;
+    bool open = valid && j > 0;  // still comparing: no difference found so far
+#pragma unroll
+    for (int c = NC - 1; c >= 0; c--) {
+      bool next_open = __shfl_down_sync(0xffffffffu, open, 1);
+      if (lane == 31) next_open = false;  // the next warp's lane 0 fetches its predecessor itself
+      const unsigned long long v = (valid && (open || next_open)) ? load_raw1(kc.ptr[c], kc.itemsize[c], row) : 0ull;
+      unsigned long long pv = __shfl_up_sync(0xffffffffu, v, 1);
+      if (lane == 0 && open) pv = load_raw1(kc.ptr[c], kc.itemsize[c], prow);
+      if (open && v != pv) open = false;
+      if (!__any_sync(0xffffffffu, open)) break;
+    }
+    // `open` still set: every column equal -> same bin as the predecessor
+    if (valid) flags[j] = (j == 0 || !open) ? 1u : 0u;
+  }
 }
 
 // binid[j] (exclusive scan of flags, + flag = 1-based bin) -> iKey, iFirstKey, bin start positions
@@ -385,7 +417,21 @@ extern "C" int rtb_group_from_lexsort(const int32_t* igroup, int64_t nindex, con
   RTB_ARG(workspace && L.bytes <= workspace_bytes, "GroupFromLexSort: workspace too small");
   KeyCols kc;
   RTB_ARG(make_keycols(keys, nkeys, &kc), "GroupFromLexSort: too many key columns");
-  lexgroup_flags_kernel<<<grid_for(nindex, 256, 2), 256, 0, stream>>>(kc, igroup, nindex, L.flags);
+  bool numeric = kc.ncols <= 4;
+  for (int c = 0; c < kc.ncols && numeric; c++)
+    numeric = (kc.itemsize[c] == 1 || kc.itemsize[c] == 2 || kc.itemsize[c] == 4 || kc.itemsize[c] == 8) &&
+              ((uintptr_t)kc.ptr[c] % kc.itemsize[c]) == 0;
+  const int fg = grid_for(nindex, 256, 2);
+  if (numeric) {
+    switch (kc.ncols) {
+      case 1: lexgroup_flags_numeric_kernel<1><<<fg, 256, 0, stream>>>(kc, igroup, nindex, L.flags); break;
+      case 2: lexgroup_flags_numeric_kernel<2><<<fg, 256, 0, stream>>>(kc, igroup, nindex, L.flags); break;
+      case 3: lexgroup_flags_numeric_kernel<3><<<fg, 256, 0, stream>>>(kc, igroup, nindex, L.flags); break;
+      default: lexgroup_flags_numeric_kernel<4><<<fg, 256, 0, stream>>>(kc, igroup, nindex, L.flags);
+    }
+  } else {
+    lexgroup_flags_kernel<<<fg, 256, 0, stream>>>(kc, igroup, nindex, L.flags);
+  }
   RTB_LAUNCH_CHECK();
   int rc = exclusive_scan_u32(L.flags, L.excl, nindex, SCAN_IDENTITY, L.scan_scratch, L.total, stream);
   if (rc != RTB_OK) return rc;

@@ -174,6 +174,16 @@ int rtb_ismember_categorical_fixup(const void* a_codes, int adtype, int64_t na, 
 /* out[c] = first row whose code is c, for c in [0, nslots); -1 where a code never occurs (other codes are ignored). */
 int rtb_first_row_per_code(const void* codes, int dtype, int64_t n, int64_t nslots, int32_t* out, void* stream);
 
+/* Row-sized helpers of the shims that used to be eager tensor expressions:
+ *   rtb_positive_mask    out[r] = key[r] > 0 — rc.CombineAccum1Filter (riptable/rt_numpy.py:1512-1545) drops bin 0 before it
+ *                        renumbers the bins with rtb_multikey_groupby32
+ *   rtb_ismember_finish  multi-key / string rc.MultiKeyIsMember32 (riptable/rt_numpy.py:1325): after grouping [b ; a] as one
+ *                        array, a row of a is a member iff its bin's first row lies in b (< nb), and that row is the answer;
+ *                        absent rows get the index dtype's invalid (base_index 0) or 0 (base_index 1) */
+int rtb_positive_mask(const void* ikey, int kdtype, int64_t n, uint8_t* out, void* stream);
+int rtb_ismember_finish(const int32_t* ikey_a, int64_t na, const int32_t* ifirstkey, int64_t unique_count, int64_t nb,
+                        int base_index, int index_dtype, uint8_t* found_out, void* index_out, void* stream);
+
 /* ---- a4: rc.CombineFilter(key, filter) — riptable/rt_numpy.py:1508.  out = filter ? key : 0, key dtype kept. */
 int rtb_combine_filter(const void* ikey, int kdtype, const uint8_t* filter, int64_t nrows, void* out, void* stream);
 

@@ -61,6 +61,8 @@ PROTOTYPES = {
     "rtb_ismember_categorical_fixup": (C.c_int, [_vp, _i32, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "rtb_first_row_per_code": (C.c_int, [_vp, _i32, _i64, _i64, _vp, _vp]),
     "rtb_multikey_groupby32_adopt_seed": (C.c_int, [C.POINTER(rtb_column), _i64, _vp, _i64, _vp, _vp, _vp, _pi64, _vp, _sz, _vp]),
+    "rtb_positive_mask": (C.c_int, [_vp, _i32, _i64, _vp, _vp]),
+    "rtb_ismember_finish": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp]),
     "rtb_combine_filter": (C.c_int, [_vp, _i32, _vp, _i64, _vp, _vp]),
     "rtb_combine_accum2": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i64, _i64, _vp, _i32, _vp]),
     "rtb_reduce_out_dtype": (C.c_int, [_i32, _i32]),

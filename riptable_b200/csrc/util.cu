@@ -235,6 +235,37 @@ __global__ void __launch_bounds__(256) reindex_kernel(const int32_t* __restrict_
   }
 }
 
+// out[r] = key[r] > 0 (rc.CombineAccum1Filter: rows of bin 0 drop out of the renumbering)
+__global__ void __launch_bounds__(256) positive_mask_kernel(const void* __restrict__ key, int kdt, int64_t n, uint8_t* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) out[r] = load_ikey(key, kdt, r) > 0 ? 1 : 0;
+}
+
+// Multi-key / string ismember: the rows of `a` were grouped together with the rows of `b` ([b ; a], rows of b first).  A row
+// of a is a member iff its bin's first row lies in b, and that first row is the index of the key's first occurrence in b.
+__global__ void __launch_bounds__(256) ismember_finish_kernel(const int32_t* __restrict__ ikey_a, int64_t na,
+                                                               const int32_t* __restrict__ ifirstkey, int64_t nuniq, int64_t nb,
+                                                               int base_index, int idt, long long absent,
+                                                               uint8_t* __restrict__ found, void* __restrict__ index_out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < na; r += stride) {
+    const int32_t bin = ikey_a[r];
+    long long pos = -1;
+    if (bin > 0 && bin <= nuniq) {
+      const int32_t first = __ldg(ifirstkey + bin - 1);
+      if (first < nb) pos = first;
+    }
+    found[r] = pos >= 0;
+    const long long v = pos >= 0 ? pos + base_index : absent;
+    switch (idt) {
+      case RTB_I8: ((int8_t*)index_out)[r] = (int8_t)v; break;
+      case RTB_I16: ((int16_t*)index_out)[r] = (int16_t)v; break;
+      case RTB_I32: ((int32_t*)index_out)[r] = (int32_t)v; break;
+      default: ((long long*)index_out)[r] = v;
+    }
+  }
+}
+
 // first row holding each code in [0, nslots) (0xFFFFFFFF = -1 where a code never occurs; other codes are ignored)
 __global__ void __launch_bounds__(256) first_row_per_code_kernel(const void* __restrict__ codes, int dt, int64_t n, int64_t nslots,
                                                                   uint32_t* __restrict__ out) {
@@ -270,6 +301,29 @@ __global__ void __launch_bounds__(256) ismember_cat_fixup_kernel(const void* __r
 using namespace rtb;
 
 extern "C" {
+
+int rtb_positive_mask(const void* ikey, int kdtype, int64_t n, uint8_t* out, void* stream) {
+  RTB_ARG(is_ikey_dtype(kdtype) && n >= 0, "positive mask: bad arguments");
+  if (n == 0) return RTB_OK;
+  RTB_ARG(ikey && out, "positive mask: null pointer");
+  positive_mask_kernel<<<grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(ikey, kdtype, n, out);
+  RTB_LAUNCH_CHECK();
+  return RTB_OK;
+}
+
+int rtb_ismember_finish(const int32_t* ikey_a, int64_t na, const int32_t* ifirstkey, int64_t unique_count, int64_t nb, int base_index,
+                        int index_dtype, uint8_t* found_out, void* index_out, void* stream) {
+  RTB_ARG(index_dtype == RTB_I8 || index_dtype == RTB_I16 || index_dtype == RTB_I32 || index_dtype == RTB_I64, "ismember: bad index dtype");
+  RTB_ARG(na >= 0 && unique_count >= 0 && nb >= 0 && (base_index == 0 || base_index == 1), "ismember: bad arguments");
+  if (na == 0) return RTB_OK;
+  RTB_ARG(ikey_a && found_out && index_out && (ifirstkey || unique_count == 0), "ismember: null pointer");
+  long long absent = 0;
+  if (!base_index) absent = index_dtype == RTB_I8 ? -128ll : index_dtype == RTB_I16 ? -32768ll : index_dtype == RTB_I32 ? -2147483648ll : (long long)0x8000000000000000ull;
+  ismember_finish_kernel<<<grid_for(na, 256, 4), 256, 0, (cudaStream_t)stream>>>(ikey_a, na, ifirstkey, unique_count, nb, base_index, index_dtype,
+                                                                                absent, found_out, index_out);
+  RTB_LAUNCH_CHECK();
+  return RTB_OK;
+}
 
 int rtb_first_row_per_code(const void* codes, int dtype, int64_t n, int64_t nslots, int32_t* out, void* stream) {
   RTB_ARG(is_ikey_dtype(dtype), "first row per code: the codes must be int8/16/32/64");

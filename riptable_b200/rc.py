@@ -412,8 +412,9 @@ def CombineAccum1Filter(key1, unique_count1, filter=None):
     k = _ikey_dev(key1)
     if filter is not None:
         k = _combine_filter_dev(k, _bool_dev(filter, k.n))
-    keep = (k.torch() > 0) if k.n else torch.zeros(0, dtype=torch.bool, device=_device())
-    ik, ifk, u = MultiKeyGroupBy32([k], 0, keep, 2)
+    keep = torch.empty(max(k.n, 4), dtype=torch.uint8, device=_device())[: k.n]
+    check(lib.rtb_positive_mask(C.c_void_p(k.ptr), dtype_code(k.dtype), k.n, C.c_void_p(keep.data_ptr()), _stream()))
+    ik, ifk, u = MultiKeyGroupBy32([k], 0, keep.view(torch.bool), 2)
     ik = ik.to(_TORCH_OF[k.dtype]) if isinstance(ik, torch.Tensor) else ik
     if device_mode:
         return ik, ifk, u
@@ -1106,14 +1107,23 @@ def _ismember(a_cols, b_cols, base_index=0):
         cat = [_concat_dev(bc, ac) for ac, bc in zip(acs, bcs)]
         valid = None
         for c in cat:
-            if c.dtype.kind == "f":
-                ok = ~torch.isnan(c.torch())
-                valid = ok if valid is None else valid & ok
-        ik, ifk, u = MultiKeyGroupBy32(cat, 0, valid, 2)
-        ika = ik[nb:].to(torch.int64)
-        first = ifk.to(torch.int64)[(ika - 1).clamp(min=0)] if u else torch.zeros(na, dtype=torch.int64, device=dev)
-        found = (ika > 0) & (first < nb)
-        idx = torch.where(found, first + base_index, torch.full_like(first, inv)).to(tdt)
+            if c.dtype.kind == "f" and c.dtype != np.float16:  # NaN never matches: those rows stay out of the grouping
+                if valid is None:
+                    valid = torch.empty(max(c.n, 4), dtype=torch.uint8, device=dev)[: c.n]
+                    mode = 0
+                else:
+                    mode = 1
+                check(lib.rtb_valid_mask(C.c_void_p(c.ptr), dtype_code(c.dtype), c.n, mode, C.c_void_p(valid.data_ptr()), _stream()))
+        ik, ifk, u = MultiKeyGroupBy32(cat, 0, None if valid is None else valid.view(torch.bool), 2)
+        found_u8 = torch.empty(max(na, 1), dtype=torch.uint8, device=dev)[:na]
+        idx = torch.empty(max(na, 1), dtype=tdt, device=dev)[:na]
+        ika = ik[nb:].contiguous()
+        if ika.data_ptr() % 4:
+            ika = ika.clone()
+        check(lib.rtb_ismember_finish(C.c_void_p(ika.data_ptr()), na, C.c_void_p(ifk.data_ptr()) if u else None, int(u), nb,
+                                      int(base_index), dtype_code(idt), C.c_void_p(found_u8.data_ptr()), C.c_void_p(idx.data_ptr()),
+                                      _stream()))
+        found = found_u8.view(torch.bool)
     if device_mode:
         return found, idx
     return found.cpu().numpy(), idx.cpu().numpy()

@@ -733,3 +733,35 @@ def test_groupby_stream_adopt_seed(rc, kdt, with_sums):
     if with_sums:
         exp = orc.GroupByAll32([np.concatenate([vpre, vrest])], ok[u0:], ou, [0], [1], [ou + 1], 0)[0]
         np.testing.assert_allclose(st.sums().cpu().numpy()[1:], exp[1:], rtol=1e-12, atol=1e-9)
+
+
+def test_host_mode_chunk_pipeline(rc, monkeypatch):
+    """Large host-mode calls are cut into chunks so that the upload of the next rows, the grouping of the current ones and
+    the read-back of the previous iKey overlap (PCIe both ways).  With the thresholds lowered the pipeline runs on a few
+    million rows: same results as the oracle, for MultiKeyGroupBy32 and the fused call, with filters and late keys."""
+    monkeypatch.setattr(rc, "_PIPE_MIN_ROWS", 100_000)
+    monkeypatch.setattr(rc, "_PIPE_CHUNK_ROWS", 256 * 1024)
+    rng = np.random.default_rng(44)
+    n = 3_300_001
+    for kdt, vdt in ((np.int64, np.float64), (np.int32, np.float32), (np.uint16, np.int32), (np.float64, np.int64)):
+        k = rng.integers(0, 40_000, n).astype(kdt)
+        k[n - 400_000:] = (rng.integers(0, 60_000, 400_000)).astype(kdt)  # keys that first appear in the last chunks
+        v = (rng.random(n) * 2 - 1).astype(vdt) if np.dtype(vdt).kind == "f" else rng.integers(-100, 100, n).astype(vdt)
+        f = rng.random(n) < 0.8
+        for filt in (None, f):
+            ok, ofk, ou = orc.MultiKeyGroupBy32([k], 0, filt, 2)
+            ik, ifk, u = rc.MultiKeyGroupBy32([k], 0, filt, 2)
+            assert u == ou and ik.dtype == np.int32 and ifk.dtype == np.int32
+            np.testing.assert_array_equal(ik, ok)
+            np.testing.assert_array_equal(ifk, ofk)
+            _check_fused(rc, [k], v, filter=filt)
+    # a unique-count hint that is too small: the pipeline gives up and the one-shot path retries with more room
+    k = rng.permutation(n).astype(np.int64)
+    ik, ifk, u = rc.MultiKeyGroupBy32([k], 1000, None, 2)
+    assert u == n and np.array_equal(ifk, np.arange(n))
+    # pinned inputs take the direct copies
+    import torch
+
+    kp = torch.from_numpy(rng.integers(0, 5000, n)).pin_memory()
+    vp = torch.rand(n, dtype=torch.float64).pin_memory()
+    _check_fused(rc, [kp.numpy()], vp.numpy())

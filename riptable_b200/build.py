@@ -55,5 +55,25 @@ def build(force=False, verbose=False):
     return LIB
 
 
+NCCL_SRC = os.path.join(HERE, "csrc_nccl", "sharded_nccl.cu")
+NCCL_LIB = os.path.join(HERE, "libriptable_b200_nccl.so")
+
+
+def build_nccl(force=False):
+    """libriptable_b200_nccl.so: the multi-GPU C ABI (include/riptable_b200_nccl.h).  A library of its own, linked against
+    libriptable_b200.so and libnccl.so.2, so that the single-GPU library carries no NCCL dependency."""
+    build(force=force)
+    hdr = os.path.join(HERE, "..", "include", "riptable_b200_nccl.h")
+    if not force and os.path.exists(NCCL_LIB) and all(os.path.getmtime(NCCL_LIB) >= os.path.getmtime(d) for d in (NCCL_SRC, hdr, LIB)):
+        return NCCL_LIB
+    cmd = [NVCC, *FLAGS, "-shared", NCCL_SRC, "-o", NCCL_LIB, "-L" + HERE, "-lriptable_b200", "-lnccl", "-lcudart",
+           "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"]
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("riptable_b200: building the NCCL library failed:\n" + out.stdout)
+    return NCCL_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_nccl(force="--force" in sys.argv))

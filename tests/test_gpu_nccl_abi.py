@@ -58,7 +58,7 @@ def _worker(rank, world, uid, n, late, vdt, q):
         col = rtb_column(C.c_void_p(kd.data_ptr()), dtype_code(np.dtype(np.int64)), 8)
         res = nccl_abi.rtb_sharded_result()
         rc = nccl_abi.lib.rtb_sharded_groupby_sum32_nccl(
-            comm, rank, world, C.byref(col), C.c_void_p(vd.data_ptr()), dtype_code(np.dtype(vdt)), 0, m, 16_384,
+            comm, rank, world, C.byref(col), C.c_void_p(vd.data_ptr()), dtype_code(np.dtype(vdt)), 0, m, 131_072,
             C.c_void_p(ikey.data_ptr()), C.c_void_p(ifk.data_ptr()), C.c_void_p(sums.data_ptr()), mu, C.byref(res),
             C.c_void_p(ws.data_ptr()), ws.numel(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
         u = int(res.unique_count)

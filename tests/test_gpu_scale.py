@@ -238,3 +238,45 @@ def test_c5_high_cardinality_pack_first_last_cumsum(rc):
     r = torch.arange(n, device="cuda")[has]
     assert bool((ik[nxt[has].long()] == ik[r]).all()) and bool((nxt[has].long() > r).all())
     assert bool((cs[nxt[has].long()] == cs[r] + val[nxt[has].long()]).all())
+
+
+def test_c2_recipe_1e8_rows_row_for_row_against_the_c_oracle(rc):
+    """configs[1]'s recipe at the largest size the CPU restatement finishes in seconds (1e8 rows, 1 M uniques from the full
+    int64 range): iKey / iFirstKey bit for bit, sums / min / max / count against the oracle at the 1e-12 relative bar of
+    north_star — through the two reference calls and through the fused call (host mode: the chunk pipeline)."""
+    from oracle import c_oracle
+    from oracle import riptide_oracle as orc
+
+    rng = np.random.default_rng(12345)
+    n, u = 100_000_000, 1_000_000
+    uvals = rng.integers(-(2**63), 2**63 - 1, u, dtype=np.int64)
+    key = uvals[rng.integers(0, u, n)]
+    val = rng.random(n) * 2.0 - 1.0
+    threads = max(1, len(__import__("os").sched_getaffinity(0)))
+    oik, oifk, ou = c_oracle.groupby_u64(key, threads=threads)
+    osum = c_oracle.sum_f64(val, oik, ou, threads=threads)
+    ik, ifk, U = rc.MultiKeyGroupBy32([key], 0, None, 2)
+    assert U == ou
+    np.testing.assert_array_equal(ik, oik)
+    np.testing.assert_array_equal(ifk, oifk)
+    s = rc.GroupByAll32([val], ik, U, [0], [1], [U + 1], 0)[0]
+    rel = np.abs(s[1:] - osum[1:]) / np.maximum(1.0, np.abs(osum[1:]))
+    assert rel.max() <= 1e-12, rel.max()
+    fik, fifk, fu, fs = rc.MultiKeyGroupBySum32([key], val)
+    assert fu == ou
+    np.testing.assert_array_equal(fik, oik)
+    np.testing.assert_array_equal(fifk, oifk)
+    rel = np.abs(fs[1:] - osum[1:]) / np.maximum(1.0, np.abs(osum[1:]))
+    assert rel.max() <= 1e-12, rel.max()
+    # min / max are exact, count is exact; float32 sums at 1e-5
+    cnt = rc.BinCount(ik, U + 1)
+    np.testing.assert_array_equal(cnt, np.bincount(oik, minlength=ou + 1))
+    sub = slice(0, 20_000_000)  # the NumPy oracle's min / max on a 2e7-row prefix of the same grouping
+    for fn in (2, 3):
+        np.testing.assert_array_equal(rc.GroupByAll32([val[sub]], ik[sub], U, [fn], [1], [U + 1], 0)[0][1:],
+                                      orc.GroupByAll32([val[sub]], oik[sub], ou, [fn], [1], [ou + 1], 0)[0][1:])
+    v32 = val.astype(np.float32)
+    s32 = rc.GroupByAll32([v32], ik, U, [0], [1], [U + 1], 0)[0]
+    assert s32.dtype == np.float32
+    ref32 = np.bincount(oik, weights=v32.astype(np.float64), minlength=ou + 1)
+    assert (np.abs(s32[1:] - ref32[1:]) / np.maximum(1.0, np.abs(ref32[1:]))).max() <= 1e-5

@@ -365,7 +365,8 @@ int rtb_partition_compose_ikey(const void* ikey, int kdtype, int64_t n, const in
  *   rtb_merge_row_counts  per left row: keyid_out = the 1-based right key id its key maps to through `keymap`
  *                         (int32[nmap] indexed by left key id - 1; negative = no such key on the right) or the int32
  *                         invalid; count_out = rows it contributes: that right group's size, or nonmatched_count
- *   rtb_merge_scan_counts exclusive scan of the counts and their total (host)
+ *   rtb_merge_scan_counts exclusive scan of the counts and their total (host); RTB_ERR_ARG when the total does not fit an
+ *                         int32 row index (the total is still reported)
  *   rtb_merge_expand      left_out[off .. off + count) = the left row (left_rows[i], or i when NULL);
  *                         right_out[...] = right_igroup[right_ifirstgroup[keyid] ...], or the int32 invalid for an
  *                         unmatched row.  Either output may be NULL.

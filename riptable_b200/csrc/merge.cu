@@ -45,6 +45,17 @@ __global__ void __launch_bounds__(256) merge_row_counts_kernel(const int32_t* __
   }
 }
 
+// 64-bit total of the counts: the scan below runs in 32 bits, and a join whose result does not fit an int32 row index has
+// to be refused rather than wrapped.
+__global__ void __launch_bounds__(256) count_total_kernel(const uint32_t* __restrict__ counts, int64_t n,
+                                                          unsigned long long* __restrict__ total) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  unsigned long long t = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) t += counts[i];
+  for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if ((threadIdx.x & 31) == 0 && t) atomicAdd(total, t);
+}
+
 // One warp per 32 left rows.  Short runs are written by their own lane; a long run is taken over by the whole warp,
 // one after the other, so a key with a million matches is copied with coalesced loads and stores.
 __global__ void __launch_bounds__(256) merge_expand_kernel(const int32_t* __restrict__ keyid, const uint32_t* __restrict__ offset,
@@ -120,7 +131,7 @@ extern "C" int rtb_merge_row_counts(const int32_t* left_ikey, int64_t n, const i
 
 extern "C" size_t rtb_merge_scan_workspace_bytes(int64_t n) {
   if (n < 0) return 0;
-  return sizeof(uint32_t) * (scan_u32_workspace_elems(n) + 4) + 256;
+  return sizeof(uint32_t) * (scan_u32_workspace_elems(n) + 8) + 256;
 }
 
 // offsets_out[i] = sum of counts[j], j < i; *total_host = sum of all (the number of output rows).  Synchronises.
@@ -134,13 +145,18 @@ extern "C" int rtb_merge_scan_counts(const uint32_t* counts, int64_t n, uint32_t
               ((uintptr_t)workspace % 16) == 0,
           "merge scan: workspace too small");
   uint32_t* total_dev = (uint32_t*)workspace;
-  uint32_t* scratch = total_dev + 4;
+  unsigned long long* wide_dev = (unsigned long long*)(total_dev + 4);
+  uint32_t* scratch = total_dev + 8;
+  RTB_CUDA(cudaMemsetAsync(wide_dev, 0, sizeof(*wide_dev), stream));
+  count_total_kernel<<<grid_for(n, 256, 8, 4), 256, 0, stream>>>(counts, n, wide_dev);
+  RTB_LAUNCH_CHECK();
   int rc = exclusive_scan_u32(counts, offsets_out, n, SCAN_IDENTITY, scratch, total_dev, stream);
   if (rc != RTB_OK) return rc;
-  uint32_t h = 0;
-  RTB_CUDA(cudaMemcpyAsync(&h, total_dev, sizeof(h), cudaMemcpyDeviceToHost, stream));
+  unsigned long long h = 0;
+  RTB_CUDA(cudaMemcpyAsync(&h, wide_dev, sizeof(h), cudaMemcpyDeviceToHost, stream));
   RTB_CUDA(cudaStreamSynchronize(stream));
   *total_host = (int64_t)h;
+  RTB_ARG(h <= 2147483646ull, "merge scan: the join has %llu rows, more than an int32 row index can address", h);
   return RTB_OK;
 }
 

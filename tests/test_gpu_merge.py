@@ -107,3 +107,13 @@ def test_merge_indices_heavy_keys_and_device_mode():
         merge.merge_indices([lk], [rk.astype(np.float64)], "left")
     with pytest.raises(ValueError):
         merge.merge_indices([lk], [rk], "cross")
+
+
+def test_merge_result_too_large_is_refused():
+    """70 000 x 70 000 rows of one key = 4.9e9 result rows: past 2^32, so a 32-bit total would wrap to a small number."""
+    from riptable_b200 import merge
+
+    left = np.zeros(70_000, np.int32)
+    right = np.zeros(70_000, np.int32)
+    with pytest.raises(ValueError):
+        merge.merge_indices([left], [right], how="inner")

@@ -124,6 +124,37 @@ __device__ __forceinline__ bool claim_new(GbCounters* ctr, uint32_t* newlist, ui
   return true;
 }
 
+constexpr uint32_t kNoClaim = 0xFFFFFFFFu;
+
+// Hands the slots its caller's threads claimed (kNoClaim = none) to the round's new-key list: one bump of the shared
+// counter for all the threads that arrive together and all N of their rows.  (The counter is a single address; bumped once per coalesced
+// group *per row* it serialised a 1 Mi-row first round with 650 K new keys to 138 us.)
+template <int N>
+__device__ __forceinline__ void claim_new_n(GbCounters* ctr, uint32_t* newlist, const uint32_t (&claimed)[N], uint32_t new_limit) {
+  cooperative_groups::coalesced_group g = cooperative_groups::coalesced_threads();
+  uint32_t b[N];
+  uint32_t total = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    b[i] = g.ballot(claimed[i] != kNoClaim);
+    total += __popc(b[i]);
+  }
+  if (total == 0) return;
+  uint32_t base = 0;
+  if (g.thread_rank() == 0) base = atomicAdd(&ctr->newcount, total);
+  base = g.shfl(base, 0);
+  const uint32_t below = (1u << g.thread_rank()) - 1u;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    if (claimed[i] != kNoClaim) {
+      const uint32_t pos = base + __popc(b[i] & below);
+      if (pos < new_limit) newlist[pos] = claimed[i];
+      else ctr->abort = 1;  // out of room: the round is redone with a larger table, this entry is dropped by the re-stage
+    }
+    base += __popc(b[i]);
+  }
+}
+
 // ---- direct path -----------------------------------------------------------------------------
 // General resolution of one key, slot by slot from slot `idx` (even): handles matches, provisional slots,
 // insertion of new keys and the key that equals the empty marker.  `mask` = capacity - 1 (capacity in slots).
@@ -484,33 +515,6 @@ __global__ void __launch_bounds__(1024, 1) gb_round_smem(const void* __restrict_
 // ---- direct path, discovery rounds ------------------------------------------------------------------
 // Used while many keys are still new: 16-byte probes, everything inline (38 registers, full occupancy),
 // the four first probes of a thread in flight together.
-constexpr uint32_t kNoClaim = 0xFFFFFFFFu;
-
-// Hands the slots its caller's threads claimed to the round's new-key list: one bump of the shared counter for all the
-// threads that arrive together and all four of their rows.  (The counter is a single address; bumped once per coalesced
-// group *per row* it serialised a 1 Mi-row first round with 650 K new keys to 138 us.)
-__device__ __forceinline__ void claim_new4(GbCounters* ctr, uint32_t* newlist, const uint32_t claimed[4], uint32_t new_limit) {
-  cooperative_groups::coalesced_group g = cooperative_groups::coalesced_threads();
-  uint32_t b[4];
-#pragma unroll
-  for (int i = 0; i < 4; i++) b[i] = g.ballot(claimed[i] != kNoClaim);
-  const uint32_t total = __popc(b[0]) + __popc(b[1]) + __popc(b[2]) + __popc(b[3]);
-  if (total == 0) return;
-  uint32_t base = 0;
-  if (g.thread_rank() == 0) base = atomicAdd(&ctr->newcount, total);
-  base = g.shfl(base, 0);
-  const uint32_t below = (1u << g.thread_rank()) - 1u;
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    if (claimed[i] != kNoClaim) {
-      const uint32_t pos = base + __popc(b[i] & below);
-      if (pos < new_limit) newlist[pos] = claimed[i];
-      else ctr->abort = 1;  // out of room: the round is redone with a larger table, this entry is dropped by the re-stage
-    }
-    base += __popc(b[i]);
-  }
-}
-
 // Resolve one key.  `s` is the slot already fetched for idx (memory-level parallelism: the caller issues all its
 // first probes before resolving any).  A slot this call claims for a new key is reported in `claimed` (kNoClaim
 // otherwise); the caller hands it to the new-key list.
@@ -593,7 +597,7 @@ __global__ void __launch_bounds__(256) gb_round_insert(const void* __restrict__ 
         claimed[i] = kNoClaim;
         o[i] = ((f >> (8 * i)) & 0xff) ? resolve_insert(table, mask, k[i], idx[i], s[i], (uint32_t)(r + i), ctr, claimed[i]) : 0;
       }
-      claim_new4(ctr, newlist, claimed, new_limit);
+      claim_new_n<4>(ctr, newlist, claimed, new_limit);
       st_stream_u4(ikey + r, make_uint4((uint32_t)o[0], (uint32_t)o[1], (uint32_t)o[2], (uint32_t)o[3]));
     } else {
       for (int64_t q = r; q < hi; q++) {
@@ -857,7 +861,8 @@ __device__ __forceinline__ PackedRow<W16> load_row_cols(const KeyCols& kc, int64
 
 template <int W16>
 __device__ __noinline__ int32_t resolve_packed(const uint8_t* packed, Slot* table, uint32_t mask, int64_t r, uint32_t tag,
-                                               uint32_t idx, uint32_t* newlist, GbCounters* ctr, uint32_t new_limit, int rowsz) {
+                                               uint32_t idx, uint32_t* newlist, GbCounters* ctr, uint32_t new_limit, int rowsz,
+                                               uint32_t* deferred_claim = nullptr) {
   const unsigned long long mine = ((unsigned long long)tag << 32) | (uint32_t)r;
   const PackedRow<W16> me = load_packed<W16>(packed, r, rowsz);
   for (uint32_t probes = 0; probes <= mask; probes++) {
@@ -865,7 +870,13 @@ __device__ __noinline__ int32_t resolve_packed(const uint8_t* packed, Slot* tabl
     if (s.key == kEmpty) {
       if (*(volatile uint32_t*)&ctr->abort) return 0;
       unsigned long long old = atomicCAS(&table[idx].key, kEmpty, mine);
-      if (old == kEmpty) return claim_new(ctr, newlist, idx, new_limit) ? provisional(table, idx, (uint32_t)r, 0xFFFFFFFFu) : 0;
+      if (old == kEmpty) {
+        if (deferred_claim) {  // the caller lists the slot together with its other rows' (claim_new_n)
+          *deferred_claim = idx;
+          return provisional(table, idx, (uint32_t)r, 0xFFFFFFFFu);
+        }
+        return claim_new(ctr, newlist, idx, new_limit) ? provisional(table, idx, (uint32_t)r, 0xFFFFFFFFu) : 0;
+      }
       s.key = old;
       s.minrow = 0xFFFFFFFFu;
       s.nbin = 0xFFFFFFFFu;
@@ -913,16 +924,20 @@ __global__ void __launch_bounds__(256) gb_round_packed(const uint8_t* __restrict
       cand[i] = live[i] && s[i].key != kEmpty && (uint32_t)(s[i].key >> 32) == (uint32_t)(h[i] >> 32) && s[i].bin() != 0;
       if (cand[i]) rep[i] = load_packed<W16>(packed, (int64_t)(uint32_t)s[i].key, rowsz);
     }
+    uint32_t claimed[R];
 #pragma unroll
     for (int i = 0; i < R; i++) {
+      claimed[i] = kNoClaim;
       if (r[i] >= hi) continue;
       int32_t o = 0;
       if (live[i]) {
         if (cand[i] && packed_equal<W16>(me[i], rep[i])) o = (int32_t)s[i].bin();
-        else o = resolve_packed<W16>(packed, table, mask, r[i], (uint32_t)(h[i] >> 32), ((uint32_t)h[i] & bmask) * 2, newlist, ctr, new_limit, rowsz);
+        else o = resolve_packed<W16>(packed, table, mask, r[i], (uint32_t)(h[i] >> 32), ((uint32_t)h[i] & bmask) * 2, newlist, ctr, new_limit, rowsz,
+                                     &claimed[i]);
       }
       ikey[r[i]] = o;
     }
+    claim_new_n<R>(ctr, newlist, claimed, new_limit);
   }
 }
 

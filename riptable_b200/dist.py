@@ -35,6 +35,7 @@ from .enums import GB_FUNCTIONS as GB
 ALLTOALL_MIN_BINS = 8_000_000  # above this many bins the partials are merged by bin-partitioned all-to-all
 SEEDED = os.environ.get("RTB_DIST_SEEDED", "1") == "1"
 SEED_ROWS = 1 << 25  # rows of the first shard that are grouped before the other shards start
+HOST_CHUNK_ROWS = 1 << 25  # HostFeed: rows per host <-> device chunk
 SEEDED_MIN_UNIQUE = 1 << 20  # the seeded path provisions max(this, largest shard / 16) bins; beyond that it falls back
 
 
@@ -261,6 +262,7 @@ class ShardedGrouping:
         self.nrows_total = nrows_total
         self.shard_unique_counts = shard_unique_counts
         self.partial_sums = None            # raw per-bin sums of this shard by GLOBAL bin, when the grouping pass made them
+        self.host_ikey_streamed = False     # a HostFeed already holds the final iKey of every chunk
 
     @property
     def ikey(self):
@@ -271,7 +273,7 @@ class ShardedGrouping:
         return self._gikey
 
 
-def sharded_groupby(ops, key_cols, filter=None, group=None, sum_values=None, shard_sizes=None) -> ShardedGrouping:
+def sharded_groupby(ops, key_cols, filter=None, group=None, sum_values=None, shard_sizes=None, feed=None) -> ShardedGrouping:
     """MultiKeyGroupBy32 over rows sharded contiguously across the ranks of `group` (module docstring, steps 1-4).
     `sum_values`: a value column to sum in the same pass where the path allows it (single-key seeded shards); the
     grouping then carries `partial_sums` (this shard's raw per-bin sums by GLOBAL bin) for sharded_groupby_sum.
@@ -280,10 +282,12 @@ def sharded_groupby(ops, key_cols, filter=None, group=None, sum_values=None, sha
     cols = [ops.as_col(c) for c in key_cols]
     n = ops.nrows(cols[0])
     if len(cols) == 1 and SEEDED and hasattr(ops, "stream") and ops.can_stream(cols[0]):
-        g = _sharded_groupby_seeded(ops, cols[0], filter, group, sum_values, shard_sizes)
+        g = _sharded_groupby_seeded(ops, cols[0], filter, group, sum_values, shard_sizes, feed)
         if g is not None:
             return g
         # a shard holds more unique keys than the seeded table was provisioned for: every rank takes the generic path
+    if feed is not None:
+        feed.wait_rows(n)  # the generic path reads the whole shard
     tick = _Tick()
     ik, ifk, u = ops.groupby(cols, filter)
     ik, ifk = ops.to_torch(ik), ops.to_torch(ifk)
@@ -336,7 +340,7 @@ def sharded_groupby(ops, key_cols, filter=None, group=None, sum_values=None, sha
     return ShardedGrouping(ops, gikey, ready, ik, u, table, ifirst_global, int(U), row_off[rank], sum(ns), us)
 
 
-def _sharded_groupby_seeded(ops, col, filter, group, sum_values=None, shard_sizes=None) -> ShardedGrouping:
+def _sharded_groupby_seeded(ops, col, filter, group, sum_values=None, shard_sizes=None, feed=None) -> ShardedGrouping:
     """Single-key shards, seeded: global bin ids come out of the hash pass itself, no per-row re-index.
 
     Global first-appearance order lists every key of shard 0 first (in shard 0's own order).  Shard 0 therefore groups
@@ -349,6 +353,9 @@ def _sharded_groupby_seeded(ops, col, filter, group, sum_values=None, shard_size
     keys are pushed through it (one U-sized chunk: seeded keys come back with their global bin, the others get bins above
     u0 in local first-appearance order), and the prefix's iKey and partial sums are re-indexed through that U-sized map.
     Only the prefix is re-indexed; the rest of the shard is hashed against the adopted table.
+
+    `feed` (HostFeed): the shard is still arriving from host memory.  Rows are pushed chunk by chunk as they land, and
+    every chunk's iKey is handed back as soon as it is final (the prefix after the adoption, the rest after its push).
 
     Keys outside the seed ("late" keys: first seen after the prefix of shard 0, or absent from shard 0) end up with
     provisional bins above u0; only if any rank reports such keys are they merged (all-gather of the late uniques in
@@ -393,6 +400,8 @@ def _sharded_groupby_seeded(ops, col, filter, group, sum_values=None, shard_size
     failed = False
     try:
         if S:
+            if feed is not None:
+                feed.wait_rows(S)
             push(st, 0, S, ikey[:S])
     except overflow:
         failed = True
@@ -443,8 +452,16 @@ def _sharded_groupby_seeded(ops, col, filter, group, sum_values=None, shard_size
                     if fused:
                         ops.stream_move_sums(st, st2, table, u_loc)
                 st = st2
+        if feed is not None and S and not failed:
+            feed.ikey_final(0, S, ikey)
         if n > S and not failed:
-            push(st, S, n, ikey[S:n])
+            if feed is None:
+                push(st, S, n, ikey[S:n])
+            else:
+                for lo_, hi_ in feed.chunks(S, n):
+                    feed.wait_rows(hi_)
+                    push(st, lo_, hi_, ikey[lo_:hi_])
+                    feed.ikey_final(lo_, hi_, ikey)
     except overflow:
         failed = True
     ikey = ikey[:n]
@@ -465,6 +482,7 @@ def _sharded_groupby_seeded(ops, col, filter, group, sum_values=None, shard_size
         g = ShardedGrouping(ops, ikey, None, ikey, u0, None, seed_first, u0, row_off[rank], sum(ns), [u0] * G)
         if fused:
             g.partial_sums = ops.to_torch(st.sums())  # bins are global already: ready for the all-reduce
+        g.host_ikey_streamed = feed is not None  # every chunk's iKey went to the host as it became final
         return g
     ifk = ops.to_torch(st.ifirstkey)
     late_rows = ifk[u0:U_r]
@@ -1008,6 +1026,89 @@ def sharded_group_from_lexsort(ops, key_cols, ascending=True, group=None, replic
         out["nCountGroup"] = torch.cat([allc.new_zeros(1), allc])
         out["iFirstKey"] = allf
     return out
+
+
+class HostFeed:
+    """A shard that lives in (pinned) host memory, on its way to the device while it is being grouped.
+
+    All host -> device copies are enqueued up front on their own stream, chunk by chunk, key and value of a chunk
+    together; the grouping waits for a chunk's event right before it pushes the chunk, and every chunk's iKey goes back
+    to the host on a third stream as soon as it is final -- PCIe runs in both directions under the hash passes.
+    The first chunk is the seeded path's prefix (SEED_ROWS)."""
+
+    def __init__(self, key_host: np.ndarray, val_host: np.ndarray, device=None, chunk_rows=None):
+        n = len(key_host)
+        if len(val_host) != n:
+            raise ValueError("key and value columns differ in length")
+        self.n = n
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.chunk_rows = int(chunk_rows or HOST_CHUNK_ROWS)
+        first = (min(n, SEED_ROWS) & ~127) if n > SEED_ROWS else n
+        self.bounds = [0]
+        if first:
+            self.bounds.append(first)
+        self.bounds += [hi for _, hi in self.chunks(first, n)]
+        kt, vt = torch.from_numpy(key_host), torch.from_numpy(val_host)
+        self.key = torch.empty(n, dtype=kt.dtype, device=self.device)
+        self.val = torch.empty(n, dtype=vt.dtype, device=self.device)
+        self.host_ikey = torch.empty(n, dtype=torch.int32, pin_memory=True)
+        cur = torch.cuda.current_stream(self.device)
+        self.up, self.down = torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device)
+        self.up.wait_stream(cur)
+        self.events = []
+        with torch.cuda.stream(self.up):
+            for lo, hi in zip(self.bounds[:-1], self.bounds[1:]):
+                self.key[lo:hi].copy_(kt[lo:hi], non_blocking=True)
+                self.val[lo:hi].copy_(vt[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.up)
+                self.events.append((hi, ev))
+        self.h2d_bytes = n * (kt.element_size() + vt.element_size())
+
+    def chunks(self, lo, hi):
+        c = self.chunk_rows
+        return [(a, min(hi, a + c)) for a in range(lo, hi, c)]
+
+    def wait_rows(self, hi):
+        """The current stream waits until rows [0, hi) are on the device."""
+        cur = torch.cuda.current_stream(self.device)
+        for end, ev in self.events:
+            cur.wait_event(ev)
+            if end >= hi:
+                break
+
+    def ikey_final(self, lo, hi, ikey):
+        """iKey[lo:hi] holds its final values on the current stream: start its copy to the host."""
+        self.down.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.down):
+            self.host_ikey[lo:hi].copy_(ikey[lo:hi], non_blocking=True)
+
+    def finish(self, ikey=None):
+        """-> the host iKey (NumPy).  `ikey`: re-read everything from this device tensor (the streamed copies are stale)."""
+        if ikey is not None:
+            self.down.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self.down):
+                self.host_ikey.copy_(ikey, non_blocking=True)
+        self.down.synchronize()
+        torch.cuda.current_stream(self.device).wait_stream(self.up)
+        return self.host_ikey.numpy()
+
+
+def sharded_groupby_sum_host(key_host, values_host, group=None, ops=None, shard_sizes=None, chunk_rows=None):
+    """sharded_groupby_sum for shards held in host memory (NumPy in, NumPy out): every rank streams its shard to its GPU
+    while the shard is being grouped and streams iKey back (HostFeed).  Pinned inputs make the copies asynchronous.
+    -> (iKey int32[n] of this shard, iFirstKey int64[U] global rows, U, sums[U + 1])."""
+    ops = ops or CudaOps()
+    feed = HostFeed(np.ascontiguousarray(key_host), np.ascontiguousarray(values_host), ops.device, chunk_rows)
+    g = sharded_groupby(ops, [feed.key], None, group, sum_values=feed.val, shard_sizes=shard_sizes, feed=feed)
+    if g.partial_sums is not None:
+        s = _combine("sum", {"v": g.partial_sums[: g.unique_count + 1]}, g.unique_count + 1, False, group, ALLTOALL_MIN_BINS)["v"]
+        if feed.val.dtype == torch.float32:
+            s = s.to(torch.float32)
+    else:
+        s = sharded_reduce(ops, feed.val, g, GB.GB_SUM, group)
+    ik = feed.finish(None if g.host_ikey_streamed else g.ikey[: feed.n])
+    return ik, g.ifirstkey.cpu().numpy(), g.unique_count, s.cpu().numpy()
 
 
 def sharded_groupby_sum(key_cols, values, group=None, ops=None, shard_sizes=None):

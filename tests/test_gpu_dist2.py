@@ -62,6 +62,12 @@ def _worker(rank, world, port, n, q):
             for vname, vals in (("f64", vt), ("f32", vt.float()), ("i32", (vt * 100).to(torch.int32))):
                 gi, gf, gu, gs = rd.sharded_groupby_sum([keys], vals, ops=ops, shard_sizes=[n // 3, n - n // 3])
                 out[f"{name}_{vname}"] = (gi.cpu().numpy(), gf.cpu().numpy(), gu, gs.cpu().numpy())
+        # the same step for shards held in host memory (HostFeed: chunked copies under the grouping), with and without
+        # late keys, in chunks small enough that a shard is several of them
+        for name, keys, seed_rows in (("host_late", k[lo:hi], 4096), ("host_seeded", k[lo:hi] % (7919 * 700), 65_536)):
+            rd.SEED_ROWS = seed_rows
+            hi_, hf, hu, hs = rd.sharded_groupby_sum_host(keys, v[lo:hi], ops=ops, shard_sizes=[n // 3, n - n // 3], chunk_rows=50_000)
+            out[name] = (hi_.copy(), hf, hu, hs)
         q.put((rank, out))
     finally:
         tdist.destroy_process_group()
@@ -119,6 +125,15 @@ def test_two_rank_nccl_paths():
     np.testing.assert_array_equal(g1["iFirstKey"], eifk)
     np.testing.assert_array_equal(g0["nCountGroup"], ecnt)
     np.testing.assert_array_equal(np.concatenate([g0["nCountGroup_owned"], g1["nCountGroup_owned"]]), ecnt[1:])
+    for name, keys in (("host_late", k), ("host_seeded", k % (7919 * 700))):
+        eik, eifk, eu = orc.MultiKeyGroupBy32([keys], 0, None, 2)
+        exp = orc.GroupByAll32([v], eik, eu, [0], [1], [eu + 1], 0)[0]
+        np.testing.assert_array_equal(np.concatenate([got[0][name][0], got[1][name][0]]), eik, err_msg=name)
+        for r in range(2):
+            gi, gf, gu, gs = got[r][name]
+            assert gu == eu and gi.dtype == np.int32
+            np.testing.assert_array_equal(gf, eifk, err_msg=name)
+            np.testing.assert_allclose(gs[1:], exp[1:], rtol=1e-12, atol=1e-9, err_msg=name)
     for name, keys in (("gs_late", k), ("gs_seeded", k % (7919 * 700)), ("gs_seeded_small_prefix", k % (7919 * 700))):
         eik, eifk, eu = orc.MultiKeyGroupBy32([keys], 0, None, 2)
         for vname, vals in (("f64", v), ("f32", v.astype(np.float32)), ("i32", (v * 100).astype(np.int32))):

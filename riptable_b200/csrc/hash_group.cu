@@ -1981,6 +1981,9 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
     bool packed_this_round = false;
     bool fused_round = false;   // this round's kernel summed the rows whose bin was final at probe time
     bool redo_sums = false;     // a fused round aborted half-way: its partial sums are discarded below
+    cudaEvent_t tev_pre = nullptr, tev_post0 = nullptr;
+    if (trace) { cudaEventCreate(&tev_pre); cudaEventRecord(tev_pre, stream); }
+    float trace_resize_ms = 0.f;
     for (int attempt = 0;; attempt++) {  // attempt loop: (re)size, run the round, grow on abort
       fused_round = false;
       if (want != cap) {
@@ -2189,8 +2192,9 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
       if (trace) {
         float tms = 0.f;
         cudaEventElapsedTime(&tms, tev0, tev1);
-        fprintf(stderr, "[rtb gb] round %d rows %lld cap %u U %lld new %u abort %u kernel %.3f ms (%.1f G rows/s)\n", round,
-                (long long)rows, cap, (long long)U, h.newcount, h.abort, tms, rows / (tms * 1e6));
+        cudaEventElapsedTime(&trace_resize_ms, tev_pre, tev0);
+        fprintf(stderr, "[rtb gb] round %d rows %lld cap %u U %lld new %u abort %u resize %.3f ms kernel %.3f ms (%.1f G rows/s)\n", round,
+                (long long)rows, cap, (long long)U, h.newcount, h.abort, trace_resize_ms, tms, rows / (tms * 1e6));
         cudaEventDestroy(tev0);
         cudaEventDestroy(tev1);
       }
@@ -2215,6 +2219,7 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
       want = g > capmax ? capmax : (uint32_t)g;
     }
 
+    if (trace) { cudaEventCreate(&tev_post0); cudaEventRecord(tev_post0, stream); }
     if (fuse_values && redo_sums)  // the aborted attempt's partial sums go; the repeat ran unfused and is added below
       RTB_CUDA(cudaMemcpyAsync(fuse->acc, fuse->snap, sizeof(unsigned long long) * (size_t)(U + 1), cudaMemcpyDeviceToDevice, stream));
     if (fuse && prev_new > 0)
@@ -2241,6 +2246,18 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
       int rc = accum_sum_rows((const uint8_t*)fuse->values + lo * vsz, fuse->vdt, ikey_out + lo, RTB_I32, rows, U + 1,
                               fuse->bin_low, fuse->nanskip, fuse->acc, stream);
       if (rc != RTB_OK) return rc;
+    }
+    if (trace) {
+      cudaEvent_t tev_post1;
+      cudaEventCreate(&tev_post1);
+      cudaEventRecord(tev_post1, stream);
+      cudaEventSynchronize(tev_post1);
+      float pms = 0.f;
+      cudaEventElapsedTime(&pms, tev_post0, tev_post1);
+      fprintf(stderr, "[rtb gb]   first rows / bins / fix-up%s: %.3f ms\n", (fuse_values && !fused_round) ? " / sums" : "", pms);
+      cudaEventDestroy(tev_pre);
+      cudaEventDestroy(tev_post0);
+      cudaEventDestroy(tev_post1);
     }
     prev_rows = rows;
     lo = hi;

@@ -284,7 +284,7 @@ def _initial_max_unique(n: int, hint_size) -> int:
 # their way up and the iKey of chunk i - 1 is on its way down.  Results are those of the one-shot call (the resumable
 # grouping numbers bins as if the chunks were one array).
 _PIPE_MIN_ROWS = 48 << 20
-_PIPE_CHUNK_ROWS = 32 << 20
+_PIPE_CHUNK_ROWS = int(os.environ.get("RTB_PIPE_CHUNK_ROWS", 32 << 20)) & ~1023  # measurement override
 _PIPE_DEPTH = 3
 
 

@@ -223,6 +223,26 @@ def cpu_arm(rows, uniques, steps, warmup, sample_rows=CPU_SAMPLE_ROWS, check_gpu
     return out
 
 
+def pin_to_gpu_cpus(local):
+    """One rank per GPU on one host: run this rank (and first-touch its pinned host buffers) on the CPUs next to its GPU,
+    what `numactl --cpunodebind` does for a multi-process launch.  Best effort: None when NVML cannot say."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # ---------------------------------------------------------------------------------------------------
 def main():
     a = parse()
@@ -252,6 +272,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device (this framework has no CPU product path)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = pin_to_gpu_cpus(local) if world > 1 else None
     import riptable_b200.rc as rc
     from riptable_b200 import _lib
     from riptable_b200.enums import GB_FUNCTIONS
@@ -431,7 +452,7 @@ def main():
                 dt = float(t.item())
             d2h = erows * 4 + u * (4 if dist is None else 8) + (u + 1) * 8
             e2e = {"value": erows * world * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                   "steps": e2e_steps, "rows_per_gpu": erows,
+                   "steps": e2e_steps, "rows_per_gpu": erows, "cpus_bound_per_rank": numa,
                    "note": ("rc.MultiKeyGroupBySum32 in host mode: pinned NumPy inputs in, NumPy iKey/iFirstKey/sums out; PCIe-bound" if dist is None else
                             "per rank: dist.sharded_groupby_sum_host -- the pinned host shard streams to the device in 32 Mi-row "
                             "chunks under the sharded groupby-sum, iKey chunks stream back, iFirstKey/sums at the end; "
@@ -463,7 +484,7 @@ def main():
     roofline = None
     if dom:
         k = kern[dom]
-        roofline = {"bound": "hbm", "kernel": "gb_round_direct<8,1,1> (fused probe + sum; + gb_round_insert<8> in the discovery rounds)" if dom == "gb_round" else "accum_kernel<OP_SUMF,false>",
+        roofline = {"bound": "hbm", "kernel": "gb_round_direct<8,0,1> (fused probe + sum; + gb_round_insert<8> in the discovery rounds)" if dom == "gb_round" else "accum_kernel<OP_SUMF,false>",
                     "achieved": k["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": k["achieved_gbs"] / peak,
                     "traffic": None, "peak_source": peak_src,
                     "alg_bytes_per_launch": k["rows"] * k["alg_bytes_per_row"] / k["launches"],

@@ -221,10 +221,16 @@ int rtb_groupby_pick(const void* values, int vdtype, int32_t itemsize, const int
                      int64_t nth, int64_t bin_low, int64_t bin_high, void* out, void* stream);
 
 /* ---- a9: rc.EmaAll32(values, ikey, unique_rows, GB_CUMSUM, (decay, time, filter, reset_filter))
- *          — riptable/rt_grouping.py:3430.  Per-group running sum in row order through the packed layout.
+ *          — riptable/rt_grouping.py:3430.  Per-group running sum in row order.
+ * Two forms: without a reset filter, up to 4 Mi bins and from 4 Mi rows, a blocked scan over the rows in their own order
+ * (per-chunk bin totals, a scan over the chunks, then every chunk's rows in order against a shared-memory table of
+ * running values; workspace = chunks x bins x 8 bytes, <= 8 GB); otherwise through the packed layout (sort by bin, gather,
+ * segmented scan, scatter).  rtb_cumop_workspace_bytes says what one call needs, rtb_cumsum_workspace_bytes is enough
+ * for either form.
  * out: nrows items of rtb_cumsum_out_dtype(vdtype); bin-0 rows get the invalid of that dtype. */
 int rtb_cumsum_out_dtype(int vdtype);
 size_t rtb_cumsum_workspace_bytes(int64_t nrows, int64_t unique_rows);
+size_t rtb_cumop_workspace_bytes(int func, int64_t nrows, int64_t unique_rows, int has_reset_filter);
 int rtb_groupby_cumsum(const void* values, int vdtype, const void* ikey, int kdtype, int64_t nrows,
                        int64_t unique_rows, const uint8_t* filter, const uint8_t* reset_filter, void* out,
                        void* workspace, size_t workspace_bytes, void* stream);

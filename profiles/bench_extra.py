@@ -52,6 +52,8 @@ def main():
     line("C1 sum f64 by int16 iKey (smem-privatised)", n, ms, 10)
     ms, _ = timed(lambda: rc.GroupByAll32([val], ik16, u, [1], [1], [u + 1], 0))
     line("C1 mean f64 by int16 iKey", n, ms, 10)
+    ms, _ = timed(lambda: rc.EmaAll32([val], ik16, u, 300, (0.0, None, None, None)), reps=2)
+    line("C1 cumsum f64 by int16 iKey (blocked form, no sort)", n, ms, 18)
     del k32, ik16
 
     # C2: int64 key with 1M uniques; the other reductions the config names (sum f64 is the headline bench)

@@ -88,6 +88,7 @@ PROTOTYPES = {
     "rtb_cumop_out_dtype": (C.c_int, [_i32, _i32]),
     "rtb_groupby_cumop": (C.c_int, [_i32, _vp, _i32, _vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rtb_cumsum_workspace_bytes": (_sz, [_i64, _i64]),
+    "rtb_cumop_workspace_bytes": (_sz, [_i32, _i64, _i64, _i32]),
     "rtb_groupby_cumsum": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rtb_make_ifirst": (C.c_int, [_vp, _i32, _i64, _i64, _vp, _i32, _vp, _vp]),
     "rtb_make_inext_workspace_bytes": (_sz, [_i64, _i64]),

@@ -7,6 +7,7 @@
 //       segmented inclusive scan over the packed order, scattered back to row order
 //   rc.MakeiFirst / rc.MakeiNext                                      (riptable/rt_numpy.py:1791-1854)
 #include "common.cuh"
+#include "cumsum_blocked.cuh"
 #include "radix.cuh"
 #include "values.cuh"
 
@@ -856,8 +857,18 @@ extern "C" int rtb_cumop_out_dtype(int func, int vdt) {
 extern "C" int rtb_cumsum_out_dtype(int vdt) { return rtb_cumop_out_dtype(RTB_GB_CUMSUM, vdt); }
 
 extern "C" size_t rtb_cumsum_workspace_bytes(int64_t nrows, int64_t unique_rows) {
-  (void)unique_rows;
   if (nrows < 0) return 0;
+  const size_t sorted = cum_layout(nullptr, 0, nrows).bytes + 256;
+  const CbPlan bp = cumsum_blocked_plan(RTB_GB_CUMSUM, nrows, unique_rows, false);
+  return bp.ok && bp.bytes + 256 > sorted ? bp.bytes + 256 : sorted;  // enough for either form
+}
+
+// What one call needs: the blocked form's chunk matrix when it applies (GB_CUMSUM, no reset filter, up to 4 Mi bins),
+// the packed layout otherwise.
+extern "C" size_t rtb_cumop_workspace_bytes(int func, int64_t nrows, int64_t unique_rows, int has_reset_filter) {
+  if (nrows < 0) return 0;
+  const CbPlan bp = cumsum_blocked_plan(func, nrows, unique_rows, has_reset_filter != 0);
+  if (bp.ok) return bp.bytes + 256;
   return cum_layout(nullptr, 0, nrows).bytes + 256;
 }
 
@@ -875,6 +886,14 @@ extern "C" int rtb_groupby_cumop(int func, const void* values, int vdt, const vo
   if (nrows == 0) return RTB_OK;
   RTB_ARG(values && ikey && out, "EmaAll32: null pointer");
   RTB_ARG(((uintptr_t)ikey % vec4_align(dtype_size(kdt))) == 0, "EmaAll32: ikey must be aligned to 4 rows");
+  const CbPlan bp = cumsum_blocked_plan(func, nrows, unique_rows, reset_filter != nullptr);
+  if (bp.ok && workspace && bp.bytes <= workspace_bytes && ((uintptr_t)workspace % 16) == 0) {
+    prof_begin(PROF_SEGSCAN, stream);
+    int brc = cumsum_blocked_run(bp, values, vdt, odt, ikey, kdt, nrows, unique_rows, filter, out, workspace, stream);
+    if (brc != RTB_OK) return brc;
+    prof_end(PROF_SEGSCAN, stream, (uint64_t)nrows);
+    return RTB_OK;
+  }
   CumLayout L = cum_layout(workspace, workspace_bytes, nrows);
   RTB_ARG(workspace && L.bytes <= workspace_bytes, "EmaAll32: workspace too small");
   uint32_t *skeys, *ig;

@@ -942,7 +942,7 @@ def EmaAll32(values, ikey, unique_rows, funcNum, func_param):
                                       dtype_code(tdev.dtype) if tdev is not None else 0, float(rate), fptr, rptr,
                                       C.c_void_p(res.ptr), C.c_void_p(ws.data_ptr()), ws.numel(), _stream()))
         else:
-            ws = _ws(lib.rtb_cumsum_workspace_bytes(k.n, int(unique_rows)))
+            ws = _ws(lib.rtb_cumop_workspace_bytes(func, k.n, int(unique_rows), int(rdev is not None)))
             check(lib.rtb_groupby_cumop(func, C.c_void_p(d.ptr), vcode, C.c_void_p(k.ptr), dtype_code(k.dtype), k.n,
                                         int(unique_rows), fptr, rptr,
                                         C.c_void_p(res.ptr), C.c_void_p(ws.data_ptr()), ws.numel(), _stream()))

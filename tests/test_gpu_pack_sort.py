@@ -134,6 +134,79 @@ def test_cumsum(rc, vdt, nb):
         _cmp_cumsum(got, exp, v)
 
 
+@pytest.fixture
+def blocked_cumsum(monkeypatch):
+    """RTB_CUMSUM_BLOCKED=2: the sort-free (blocked) form of GB_CUMSUM runs whenever it can, however small the call."""
+    monkeypatch.setenv("RTB_CUMSUM_BLOCKED", "2")
+
+
+@pytest.mark.parametrize("vdt", [np.bool_, np.int8, np.uint16, np.int32, np.int64, np.uint64, np.float32, np.float64])
+@pytest.mark.parametrize("nb,kdt", [(1, np.int8), (7, np.int16), (40, np.int32), (3000, np.int64), (3500, np.int32), (16_000, np.int32)])
+def test_cumsum_blocked(rc, blocked_cumsum, vdt, nb, kdt):
+    """The blocked form (csrc/cumsum_blocked.cu) against the oracle: few bins (a chunk per warp, whole warps of one bin),
+    more bins (a chunk per CTA, a table slot per bin of the tile), every iKey width, the op filter, bin 0, ragged last
+    tile / chunk."""
+    rng = np.random.default_rng(nb + 17)
+    n = 300_017
+    ikey = rng.integers(0, nb + 1, n).astype(kdt)
+    if np.dtype(vdt).kind == "f":
+        v = (rng.random(n) * 2 - 1).astype(vdt)
+    elif np.dtype(vdt).kind == "b":
+        v = rng.integers(0, 2, n).astype(vdt)
+    else:
+        v = rng.integers(0, 100, n).astype(vdt)
+    filt = rng.random(n) < 0.7
+    for fp in [(0.0, None, None, None), (0.0, None, filt, None)]:
+        got = rc.EmaAll32([v], ikey, nb, 300, fp)[0]
+        exp = orc.EmaAll32([v], ikey, nb, 300, fp)[0]
+        _cmp_cumsum(got, exp, v)
+
+
+def test_cumsum_blocked_special_values(rc, blocked_cumsum):
+    """NaN / Inf poison the rest of their group exactly as a sequential sum does, across tile and chunk boundaries;
+    negative integers and the int64 sentinel are ordinary values (tests/test_merge.py:6425-6426)."""
+    rng = np.random.default_rng(3)
+    n = 150_000
+    ikey = rng.integers(0, 51, n).astype(np.int32)
+    v = rng.normal(0, 1, n)
+    v[rng.integers(0, n, 6)] = np.nan
+    v[rng.integers(0, n, 4)] = np.inf
+    v[rng.integers(0, n, 4)] = -np.inf
+    got = rc.EmaAll32([v], ikey, 50, 300, (0.0, None, None, None))[0]
+    exp = orc.EmaAll32([v], ikey, 50, 300, (0.0, None, None, None))[0]
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(exp))
+    np.testing.assert_array_equal(np.isposinf(got), np.isposinf(exp))
+    np.testing.assert_array_equal(np.isneginf(got), np.isneginf(exp))
+    fin = np.isfinite(exp)
+    np.testing.assert_allclose(got[fin], exp[fin], rtol=1e-12, atol=1e-9)
+    vi = rng.integers(-10**15, 10**15, n).astype(np.int64)
+    vi[::5000] = np.iinfo(np.int64).min
+    got = rc.EmaAll32([vi], ikey, 50, 300, (0.0, None, None, None))[0]
+    exp = orc.EmaAll32([vi], ikey, 50, 300, (0.0, None, None, None))[0]
+    np.testing.assert_array_equal(got, exp)
+
+
+@pytest.mark.parametrize("nb", [500, 12_000])
+def test_cumsum_blocked_matches_sorted_form_at_size(rc, monkeypatch, nb):
+    """8 Mi rows, 500 bins (a chunk per warp) / 12 000 bins (a chunk per CTA): the call takes the blocked form on its own
+    (no override); integers must equal the sort-based form and the oracle bit for bit, floats within the summation
+    tolerance."""
+    rng = np.random.default_rng(8)
+    n = 8 << 20
+    ikey = rng.integers(0, nb + 1, n).astype(np.int32)
+    vi = rng.integers(-1000, 1000, n).astype(np.int32)
+    vf = rng.random(n)
+    monkeypatch.setenv("RTB_CUMSUM_BLOCKED", "0")
+    si = rc.EmaAll32([vi], ikey, nb, 300, (0.0, None, None, None))[0]
+    sf = rc.EmaAll32([vf], ikey, nb, 300, (0.0, None, None, None))[0]
+    monkeypatch.delenv("RTB_CUMSUM_BLOCKED")
+    bi = rc.EmaAll32([vi], ikey, nb, 300, (0.0, None, None, None))[0]
+    bf = rc.EmaAll32([vf], ikey, nb, 300, (0.0, None, None, None))[0]
+    np.testing.assert_array_equal(bi, si)
+    np.testing.assert_allclose(bf, sf, rtol=1e-12, atol=1e-7, equal_nan=True)
+    np.testing.assert_array_equal(bi, orc.EmaAll32([vi], ikey, nb, 300, (0.0, None, None, None))[0])
+
+
 def test_cumsum_kat(rc):
     # tests/test_groupby.py:555-602: op-filter False -> carry the running value; bin 0 -> invalid
     ikey = np.array([1, 2, 1, 0, 2, 1], dtype=np.int8)

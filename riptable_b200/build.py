@@ -51,7 +51,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("riptable_b200: CUDA build failed")
-    subprocess.check_call([NVCC, "-shared", "-o", LIB, *objs, "-lcudart"])
+    subprocess.check_call([NVCC, "-Wno-deprecated-gpu-targets", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-lcudart"])
     return LIB
 
 
@@ -66,7 +66,7 @@ def build_nccl(force=False):
     hdr = os.path.join(HERE, "..", "include", "riptable_b200_nccl.h")
     if not force and os.path.exists(NCCL_LIB) and all(os.path.getmtime(NCCL_LIB) >= os.path.getmtime(d) for d in (NCCL_SRC, hdr, LIB)):
         return NCCL_LIB
-    cmd = [NVCC, *FLAGS, "-shared", NCCL_SRC, "-o", NCCL_LIB, "-L" + HERE, "-lriptable_b200", "-lnccl", "-lcudart",
+    cmd = [NVCC, "-Wno-deprecated-gpu-targets", *FLAGS, "-shared", NCCL_SRC, "-o", NCCL_LIB, "-L" + HERE, "-lriptable_b200", "-lnccl", "-lcudart",
            "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"]
     out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if out.returncode != 0:

@@ -723,7 +723,7 @@ def BinCount(ikey, n, pack=False):
 
 def _pack(k: DevArray, nbins: int):
     if k.n > 2_000_000_000:
-        raise ValueError("pack: more than 2e9 rows needs the 64-bit variant, which this build does not provide")
+        raise ValueError("pack: more than 2e9 rows needs int64 iGroup, which this build does not provide (iKey itself is int32-indexed)")
     ig = DevArray.empty(k.n, np.int32)
     ifg = DevArray.empty(nbins, np.int32)
     cnt = DevArray.empty(nbins, np.int32)
@@ -987,7 +987,7 @@ def LexSort32(list_arrays, cutoffs=None, index=None, ascending=True):
     if any(c.n != n for c in cols):
         raise ValueError("lexsort: all keys must have the same length")
     if n > 2_000_000_000:
-        raise ValueError("LexSort32: more than 2e9 rows; LexSort64 is not provided by this build")
+        raise ValueError("LexSort32: more than 2e9 rows; call LexSort64 (int64 row numbers)")
     if isinstance(ascending, (bool, np.bool_)):
         asc = np.full(len(cols), 1 if ascending else 0, dtype=np.int8)
     else:

@@ -405,10 +405,12 @@ def _sharded_groupby_seeded(ops, col, filter, group, sum_values=None, shard_size
             push(st, 0, S, ikey[:S])
     except overflow:
         failed = True
+    tick.mark("own prefix")
     src = tdist.get_global_rank(group, 0) if group is not None else 0
     u0_t = ops.tensor([(-1 if failed else st.unique_count) if rank == 0 else 0], dtype=torch.int64)
     tdist.broadcast(u0_t, src=src, group=group)
     u0 = int(u0_t.item())
+    tick.mark("u0 broadcast")
     if u0 < 0:
         return None
     # one payload: the seed's key bytes followed by its first rows
@@ -422,7 +424,7 @@ def _sharded_groupby_seeded(ops, col, filter, group, sum_values=None, shard_size
         tdist.broadcast(payload, src=src, group=group)
     seed_bytes = payload[: u0 * isz]
     seed_first = payload[u0 * isz:].clone().view(torch.int64) if u0 else ops.tensor([0], dtype=torch.int64).new_empty(0)
-    tick.mark("prefix + seed broadcast")
+    tick.mark("seed broadcast")
 
     # 2. the other ranks adopt the seed, then all ranks hash the rest of their rows
     try:
@@ -452,6 +454,7 @@ def _sharded_groupby_seeded(ops, col, filter, group, sum_values=None, shard_size
                     if fused:
                         ops.stream_move_sums(st, st2, table, u_loc)
                 st = st2
+        tick.mark("adopt seed")
         if feed is not None and S and not failed:
             feed.ikey_final(0, S, ikey)
         if n > S and not failed:
@@ -466,7 +469,7 @@ def _sharded_groupby_seeded(ops, col, filter, group, sum_values=None, shard_size
         failed = True
     ikey = ikey[:n]
     U_r = st.unique_count
-    tick.mark("adopt seed + hash shard")
+    tick.mark("hash shard")
 
     # 3. late keys (rare): merge them across ranks
     late = ops.tensor([-1 if failed else U_r - u0], dtype=torch.int64)

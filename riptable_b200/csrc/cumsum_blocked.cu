@@ -62,7 +62,7 @@ CbPlan cumsum_blocked_plan(int func, int64_t nrows, int64_t unique_rows, bool ha
       p.chunk_rows = (rows + 255) & ~255ll;
       p.chunks = (int)((nrows + p.chunk_rows - 1) / p.chunk_rows);
       p.warp_chunks = true;
-      p.bytes = (size_t)p.chunks * (size_t)p.stride * 8;
+      p.bytes = (size_t)p.chunks * (size_t)p.stride * 8 + 16;
       p.ok = true;
       return p;
     }
@@ -75,7 +75,7 @@ CbPlan cumsum_blocked_plan(int func, int64_t nrows, int64_t unique_rows, bool ha
   int64_t tpc = (tiles + c - 1) / c;
   p.chunk_rows = tpc * kCbTile;
   p.chunks = (int)((nrows + p.chunk_rows - 1) / p.chunk_rows);
-  p.bytes = (size_t)p.chunks * (size_t)p.stride * 8;
+  p.bytes = (size_t)p.chunks * (size_t)p.stride * 8 + 16;
   p.ok = true;
   return p;
 }
@@ -95,9 +95,11 @@ __device__ __forceinline__ unsigned long long cb_add(unsigned long long a, unsig
 template <bool FLOAT>
 __global__ void __launch_bounds__(256) cb_totals_kernel(const void* __restrict__ values, int vdt, const void* __restrict__ ikey, int kdt,
                                                         int64_t n, int64_t unique_rows, const uint8_t* __restrict__ filter,
-                                                        int64_t chunk_rows, int64_t stride, unsigned long long* __restrict__ M) {
+                                                        int64_t chunk_rows, int64_t stride, unsigned long long* __restrict__ M,
+                                                        uint32_t* bad) {
   const int vsz = dsize(vdt);
   const int64_t ntiles = (n + kCbTile - 1) / kCbTile;
+  uint32_t nbad = 0;
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int64_t lo = t * kCbTile;
     unsigned long long* row = M + (lo / chunk_rows) * stride;
@@ -106,12 +108,14 @@ __global__ void __launch_bounds__(256) cb_totals_kernel(const void* __restrict__
       const int64_t i = lo + k * kCbThreads + threadIdx.x;
       if (i >= n) break;
       const int64_t b = load_ikey(ikey, kdt, i);
+      if (b < 0 || b > unique_rows) nbad++;
       if (b <= 0 || b > unique_rows || (filter && !filter[i])) continue;
       const unsigned long long v = cb_value<FLOAT>(load_raw1(values, vsz, i), vdt);
       if (FLOAT) atomicAdd((double*)&row[b], __longlong_as_double((long long)v));
       else atomicAdd(&row[b], v);
     }
   }
+  if (nbad) atomicAdd(bad, nbad);  // rows outside [0, unique_rows]: the caller rejects the input, as the packed form does
 }
 
 // Few bins: one RED per row would queue on a handful of L2 addresses.  A CTA sums a contiguous part of one chunk in shared
@@ -121,8 +125,10 @@ constexpr int kCbParts = 8;  // CTAs per chunk
 template <bool FLOAT>
 __global__ void __launch_bounds__(256) cb_totals_smem_kernel(const void* __restrict__ values, int vdt, const void* __restrict__ ikey, int kdt,
                                                              int64_t n, int64_t unique_rows, const uint8_t* __restrict__ filter,
-                                                             int64_t chunk_rows, int64_t stride, unsigned long long* __restrict__ M) {
+                                                             int64_t chunk_rows, int64_t stride, unsigned long long* __restrict__ M,
+                                                             uint32_t* bad) {
   __shared__ unsigned long long acc[kCbSmemBins];
+  uint32_t nbad = 0;
   const int nb = (int)unique_rows + 1;
   const unsigned long long zero = FLOAT ? (unsigned long long)__double_as_longlong(0.0) : 0ull;
   for (int b = threadIdx.x; b < nb; b += blockDim.x) acc[b] = zero;
@@ -140,6 +146,7 @@ __global__ void __launch_bounds__(256) cb_totals_smem_kernel(const void* __restr
     unsigned long long v = zero;
     if (i < hi) {
       const int64_t bb = load_ikey(ikey, kdt, i);
+      if (bb < 0 || bb > unique_rows) nbad++;
       if (bb > 0 && bb <= unique_rows && (!filter || filter[i])) {
         b = (int)bb;
         v = cb_value<FLOAT>(load_raw1(values, vsz, i), vdt);
@@ -161,6 +168,7 @@ __global__ void __launch_bounds__(256) cb_totals_smem_kernel(const void* __restr
       else atomicAdd(&acc[b], sum);
     }
   }
+  if (nbad) atomicAdd(bad, nbad);
   __syncthreads();
   unsigned long long* row = M + (int64_t)blockIdx.y * stride;
   for (int b = threadIdx.x; b < nb; b += blockDim.x) {
@@ -369,6 +377,7 @@ __global__ void __launch_bounds__(256) cb_rows_warp_kernel(const void* __restric
 int cumsum_blocked_run(const CbPlan& p, const void* values, int vdt, int odt, const void* ikey, int kdt, int64_t nrows,
                        int64_t unique_rows, const uint8_t* filter, void* out, void* workspace, cudaStream_t stream) {
   unsigned long long* M = (unsigned long long*)workspace;
+  uint32_t* bad = (uint32_t*)((unsigned char*)workspace + p.bytes - 16);  // the plan's bytes end with a 16-byte counter slot
   const bool fl = vdt == RTB_F32 || vdt == RTB_F64;
   RTB_CUDA(cudaMemsetAsync(M, 0, p.bytes, stream));
   const int64_t ntiles = (nrows + kCbTile - 1) / kCbTile;
@@ -381,8 +390,8 @@ int cumsum_blocked_run(const CbPlan& p, const void* values, int vdt, int odt, co
   const int gw = (p.chunks + 7) / 8;
 #define RTB_CB_RUN(FL_)                                                                                                              \
   do {                                                                                                                               \
-    if (few) cb_totals_smem_kernel<FL_><<<gs, 256, 0, stream>>>(values, vdt, ikey, kdt, nrows, unique_rows, filter, p.chunk_rows, p.stride, M); \
-    else cb_totals_kernel<FL_><<<g1, 256, 0, stream>>>(values, vdt, ikey, kdt, nrows, unique_rows, filter, p.chunk_rows, p.stride, M); \
+    if (few) cb_totals_smem_kernel<FL_><<<gs, 256, 0, stream>>>(values, vdt, ikey, kdt, nrows, unique_rows, filter, p.chunk_rows, p.stride, M, bad); \
+    else cb_totals_kernel<FL_><<<g1, 256, 0, stream>>>(values, vdt, ikey, kdt, nrows, unique_rows, filter, p.chunk_rows, p.stride, M, bad); \
     RTB_LAUNCH_CHECK();                                                                                                              \
     cb_scan_chunks_kernel<FL_><<<g2, 256, 0, stream>>>(M, p.chunks, p.stride, unique_rows + 1);                                       \
     RTB_LAUNCH_CHECK();                                                                                                              \
@@ -396,6 +405,11 @@ int cumsum_blocked_run(const CbPlan& p, const void* values, int vdt, int odt, co
   if (fl) RTB_CB_RUN(true);
   else RTB_CB_RUN(false);
 #undef RTB_CB_RUN
+  RTB_LAUNCH_CHECK();
+  uint32_t hbad = 0;
+  RTB_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+  RTB_CUDA(cudaStreamSynchronize(stream));
+  RTB_ARG(hbad == 0, "EmaAll32: %u ikey values lie outside [0, %lld]", hbad, (long long)unique_rows);
   RTB_LAUNCH_CHECK();
   return RTB_OK;
 }

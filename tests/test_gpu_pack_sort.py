@@ -162,6 +162,14 @@ def test_cumsum_blocked(rc, blocked_cumsum, vdt, nb, kdt):
         _cmp_cumsum(got, exp, v)
 
 
+def test_cumsum_blocked_bad_ikey(rc, blocked_cumsum):
+    """An iKey outside [0, unique_rows] is an error on the blocked form as on the packed one."""
+    for nb, bad in ((2, 9), (5000, 5001), (2, -1)):
+        ikey = np.array([1, 2, bad, 1], dtype=np.int32)
+        with pytest.raises(ValueError):
+            rc.EmaAll32([np.arange(4.0)], ikey, nb, 300, (0.0, None, None, None))
+
+
 def test_cumsum_blocked_special_values(rc, blocked_cumsum):
     """NaN / Inf poison the rest of their group exactly as a sequential sum does, across tile and chunk boundaries;
     negative integers and the int64 sentinel are ordinary values (tests/test_merge.py:6425-6426)."""

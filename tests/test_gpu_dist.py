@@ -79,3 +79,36 @@ def test_sharded_groupby_reduce_single_rank(group, a2a):
     np.testing.assert_array_equal(gl["nCountGroup"].cpu().numpy(), ecnt)
     ik, ifk, u, s = rd.sharded_groupby_sum([torch.from_numpy(k1).cuda()], torch.from_numpy(v).cuda(), group, ops)
     assert u == len(np.unique(k1)) and s.shape[0] == u + 1
+
+
+@pytest.mark.parametrize("seed_rows,chunk_rows", [(4096, 50_000), (1 << 25, 100_000), (70_000, 1 << 25)])
+def test_sharded_groupby_sum_host_single_rank(group, seed_rows, chunk_rows):
+    """The host-shard form (HostFeed: the shard streams to the device chunk by chunk under the grouping, iKey chunks
+    stream back) on one rank: late keys after a short seed prefix, a prefix that covers the shard, one chunk / many."""
+    import torch
+    from riptable_b200 import dist as rd
+
+    rng = np.random.default_rng(12)
+    n = 400_003
+    k = rng.integers(0, 3000, n).astype(np.int64) * 7919
+    k[: n // 2] %= 7919 * 1500  # half of the keys first appear in the second half
+    v = rng.random(n) * 10 - 5
+    old = rd.SEED_ROWS
+    rd.SEED_ROWS = seed_rows
+    try:
+        for vals in (v, v.astype(np.float32), (v * 100).astype(np.int32)):
+            hk = torch.from_numpy(k).pin_memory().numpy()
+            hv = torch.from_numpy(vals).pin_memory().numpy()
+            ik, ifk, u, s = rd.sharded_groupby_sum_host(hk, hv, group, chunk_rows=chunk_rows)
+            eik, eifk, eu = orc.MultiKeyGroupBy32([k], 0, None, 2)
+            exp = orc.GroupByAll32([vals], eik, eu, [0], [1], [eu + 1], 0)[0]
+            assert u == eu and isinstance(ik, np.ndarray) and ik.dtype == np.int32
+            np.testing.assert_array_equal(ik, eik)
+            np.testing.assert_array_equal(ifk, eifk)
+            assert s.dtype == exp.dtype
+            if exp.dtype.kind == "f":
+                np.testing.assert_allclose(s[1:], exp[1:], rtol=1e-5 if exp.dtype == np.float32 else 1e-12, atol=1e-3 if exp.dtype == np.float32 else 1e-9)
+            else:
+                np.testing.assert_array_equal(s[1:], exp[1:])
+    finally:
+        rd.SEED_ROWS = old

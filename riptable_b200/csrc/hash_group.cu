@@ -859,6 +859,20 @@ __device__ __forceinline__ PackedRow<W16> load_row_cols(const KeyCols& kc, int64
   return x;
 }
 
+// The packing pass in one launch: a thread assembles its row from the columns and stores it whole (the per-column launches
+// of gb_pack_column each touch every 32-byte sector of the packed rows with a partial store, after a memset for the padding).
+template <int W16>
+__global__ void __launch_bounds__(256) gb_pack_rows_kernel(KeyCols kc, WordMap wm, int whole_words, int64_t a, int64_t b,
+                                                           uint8_t* __restrict__ packed) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = a + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < b; r += stride) {
+    const PackedRow<W16> x = load_row_cols<W16>(kc, r, whole_words != 0, wm);
+    uint4* dst = (uint4*)(packed + r * (int64_t)(16 * W16));
+#pragma unroll
+    for (int j = 0; j < W16; j++) dst[j] = x.w[j];
+  }
+}
+
 template <int W16>
 __device__ __noinline__ int32_t resolve_packed(const uint8_t* packed, Slot* table, uint32_t mask, int64_t r, uint32_t tag,
                                                uint32_t idx, uint32_t* newlist, GbCounters* ctr, uint32_t new_limit, int rowsz,
@@ -938,6 +952,107 @@ __global__ void __launch_bounds__(256) gb_round_packed(const uint8_t* __restrict
       ikey[r[i]] = o;
     }
     claim_new_n<R>(ctr, newlist, claimed, new_limit);
+  }
+}
+
+// ---- packed rows, table in DRAM: the fast path and the general path in separate launches ---------------------
+// gb_round_packed resolves a row that misses its home slot (a fifth of them at the usual load), lands on a provisional
+// slot or is new inside the row loop: two or three more dependent DRAM-class accesses during which the other lanes of the
+// warp wait -- a settled 231 M-row round of C3 ran at 6 G rows/s.  Here the first launch only takes the fast path -- both
+// slots of the home bucket (one 32-byte load), the representative row of the slot whose tag matches, compare -- and marks
+// every other row with kDeferred; the second launch compacts the marked rows of a tile and resolves them with all lanes busy.
+constexpr int32_t kDeferred = INT32_MIN;  // never a provisional value while the table has at most 2^30 slots
+
+template <int W16>
+__global__ void __launch_bounds__(256) gb_round_packed_fast(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ filter,
+                                                            int32_t* __restrict__ ikey, const Slot* __restrict__ table, uint32_t mask,
+                                                            int64_t lo, int64_t hi, int rowsz) {
+  constexpr int R = 2;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const uint32_t bmask = mask >> 1;
+  for (int64_t tb = lo + gw * (32 * R); tb < hi; tb += nwarps * (32 * R)) {
+    int64_t r[R];
+    bool live[R];
+    PackedRow<W16> me[R];
+    unsigned long long h[R];
+    Bucket b[R];
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+      r[i] = tb + i * 32 + lane;
+      live[i] = r[i] < hi && (!filter || filter[r[i]]);
+      if (live[i]) me[i] = load_packed<W16>(packed, r[i], rowsz);
+    }
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+      h[i] = live[i] ? hash_packed<W16>(me[i]) : 0ull;
+      if (live[i]) b[i] = load_bucket(table, (uint32_t)h[i] & bmask);
+    }
+    PackedRow<W16> rep[R];
+    uint32_t bin[R];
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+      bin[i] = 0;
+      if (live[i]) {
+        const uint32_t tag = (uint32_t)(h[i] >> 32);
+        const uint32_t bin0 = ~(uint32_t)(b[i].w0 >> 32), bin1 = ~(uint32_t)(b[i].w1 >> 32);
+        unsigned long long k = kEmpty;
+        if (b[i].k0 != kEmpty && (uint32_t)(b[i].k0 >> 32) == tag && bin0) { k = b[i].k0; bin[i] = bin0; }
+        else if (b[i].k1 != kEmpty && (uint32_t)(b[i].k1 >> 32) == tag && bin1) { k = b[i].k1; bin[i] = bin1; }
+        if (bin[i]) rep[i] = load_packed<W16>(packed, (int64_t)(uint32_t)k, rowsz);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+      if (r[i] >= hi) continue;
+      int32_t o = 0;
+      if (live[i]) o = (bin[i] && packed_equal<W16>(me[i], rep[i])) ? (int32_t)bin[i] : kDeferred;
+      ikey[r[i]] = o;
+    }
+  }
+}
+
+template <int W16>
+__global__ void __launch_bounds__(256) gb_round_packed_deferred(const uint8_t* __restrict__ packed, int32_t* __restrict__ ikey, Slot* table,
+                                                                uint32_t mask, int64_t lo, int64_t hi, uint32_t* newlist,
+                                                                GbCounters* ctr, uint32_t new_limit, int rowsz) {
+  constexpr int T = 2048;  // rows per tile
+  __shared__ uint32_t list[T];
+  __shared__ uint32_t cnt, stop;
+  const int lane = threadIdx.x & 31;
+  for (int64_t tile = lo + (int64_t)blockIdx.x * T; tile < hi; tile += (int64_t)gridDim.x * T) {
+    if (threadIdx.x == 0) {
+      cnt = 0;
+      stop = *(volatile uint32_t*)&ctr->abort;  // the round is out of room and will be redone
+    }
+    __syncthreads();
+    if (stop) break;
+#pragma unroll
+    for (int k = 0; k < T / 256; k++) {
+      const int64_t r = tile + k * 256 + threadIdx.x;
+      const bool f = r < hi && ikey[r] == kDeferred;
+      const uint32_t m = __ballot_sync(0xffffffffu, f);
+      uint32_t base = 0;
+      if (lane == 0 && m) base = atomicAdd(&cnt, (uint32_t)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (f) list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)(r - tile);
+    }
+    __syncthreads();
+    const uint32_t n = cnt;
+    for (uint32_t j0 = 0; j0 < n; j0 += 256) {  // whole warps enter, so that the new-slot list is bumped once per warp
+      const uint32_t j = j0 + threadIdx.x;
+      uint32_t claimed[1] = {kNoClaim};
+      if (j < n) {
+        const int64_t r = tile + list[j];
+        const unsigned long long h = hash_packed<W16>(load_packed<W16>(packed, r, rowsz));
+        ikey[r] = resolve_packed<W16>(packed, table, mask, r, (uint32_t)(h >> 32), ((uint32_t)h & (mask >> 1)) * 2, newlist, ctr,
+                                      new_limit, rowsz, &claimed[0]);
+      }
+      __syncwarp();
+      claim_new_n<1>(ctr, newlist, claimed, new_limit);
+    }
+    __syncthreads();
   }
 }
 
@@ -1517,6 +1632,8 @@ struct GbPlan {
   double big_table_bytes = 8.0 * 1024 * 1024 * 1024;  // above this table size every round uses the slot-wise kernel
   int64_t finish_rows = 256ll << 20;  // a settled table finishes a remainder of at most this many rows in one round
   int snapshot = 1;                   // 16- / 32-byte packed rows: inline-key snapshot table for the settled rounds
+  int defer_packed = 1;               // packed rows over a table beyond defer_table_bytes: fast path and general path in separate launches
+  double defer_table_bytes = 128.0 * 1024 * 1024;
   double snap_fill = 2.0;             // snapshot entries per key (power of two above it)
 };
 
@@ -1524,6 +1641,8 @@ static GbPlan get_plan() {
   GbPlan p;
   if (const char* e = getenv("RTB_GB_SNAPSHOT")) p.snapshot = atoi(e);
   if (const char* e = getenv("RTB_GB_SNAPFILL")) p.snap_fill = atof(e);
+  if (const char* e = getenv("RTB_GB_DEFER")) p.defer_packed = atoi(e);
+  if (const char* e = getenv("RTB_GB_DEFER_BYTES")) p.defer_table_bytes = atof(e);
   if (const char* e = getenv("RTB_GB_FINISH")) p.finish_rows = atoll(e);
   if (const char* e = getenv("RTB_GB_BIGTABLE")) p.big_table_bytes = atof(e);
   if (const char* e = getenv("RTB_GB_L2WIN")) p.l2_window = atoi(e);
@@ -1846,6 +1965,13 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
   }
   auto pack_range = [&](int64_t a, int64_t b) -> int {
     if (b <= a) return RTB_OK;
+    if (W <= 32 && cols_aligned) {  // rows of up to 32 bytes from 4-byte aligned columns: one launch, whole rows
+      const int grid = grid_for(b - a, 256, 2, 16);
+      if (W == 16) gb_pack_rows_kernel<1><<<grid, 256, 0, stream>>>(kc, wm, whole_words_all ? 1 : 0, a, b, L.packed);
+      else gb_pack_rows_kernel<2><<<grid, 256, 0, stream>>>(kc, wm, whole_words_all ? 1 : 0, a, b, L.packed);
+      RTB_LAUNCH_CHECK();
+      return RTB_OK;
+    }
     uint8_t* dst = L.packed + a * (int64_t)W;
     if (row_bytes < W) RTB_CUDA(cudaMemsetAsync(dst, 0, (size_t)(b - a) * W, stream));  // zero the padding
     int off = 0;
@@ -2164,6 +2290,26 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
           if (prc != RTB_OK) return prc;
           packed_this_round = true;
         }
+        // a table far beyond L2 and a round that mostly looks keys up: fast path first, everything else in a second launch
+        const bool defer = plan.defer_packed && (W == 16 || W == 32 || W == 48 || W == 64) && round > 0 && attempt == 0 && cap <= (1u << 30) &&
+                           (double)cap * sizeof(Slot) > plan.defer_table_bytes && (double)prev_new <= 0.5 * (double)prev_rows;
+        if (defer) {
+          const int gf = grid_for(rows, 256, 2, 8), gd = grid_for(rows, 256, 8, 8);
+#define RTB_DEFER_ROUND(W16_)                                                                                               \
+  do {                                                                                                                    \
+    gb_round_packed_fast<W16_><<<gf, 256, 0, stream>>>(L.packed, filter, ikey_out, L.table, mask, lo, hi, rowsz);          \
+    RTB_LAUNCH_CHECK();                                                                                                   \
+    gb_round_packed_deferred<W16_><<<gd, 256, 0, stream>>>(L.packed, ikey_out, L.table, mask, lo, hi, newlist, L.ctr,      \
+                                                           new_limit, rowsz);                                             \
+  } while (0)
+          switch (W) {
+            case 16: RTB_DEFER_ROUND(1); break;
+            case 32: RTB_DEFER_ROUND(2); break;
+            case 48: RTB_DEFER_ROUND(3); break;
+            default: RTB_DEFER_ROUND(4);
+          }
+#undef RTB_DEFER_ROUND
+        } else
         switch (W) {
           case 16: gb_round_packed<1><<<grid_for(rows, 256, 2, 8), 256, 0, stream>>>(L.packed, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit, rowsz); break;
           case 32: gb_round_packed<2><<<grid_for(rows, 256, 2, 8), 256, 0, stream>>>(L.packed, filter, ikey_out, L.table, mask, lo, hi, newlist, L.ctr, new_limit, rowsz); break;

@@ -765,3 +765,33 @@ def test_host_mode_chunk_pipeline(rc, monkeypatch):
     kp = torch.from_numpy(rng.integers(0, 5000, n)).pin_memory()
     vp = torch.rand(n, dtype=torch.float64).pin_memory()
     _check_fused(rc, [kp.numpy()], vp.numpy())
+
+
+@pytest.mark.parametrize("cols", ["i64_s16_i32", "s12", "i64_i64", "s40_i32"])
+def test_packed_rows_deferred_general_path(rc, monkeypatch, cols):
+    """RTB_GB_DEFER_BYTES=0: packed-row rounds after the first run as two launches whatever the table size -- the fast path
+    (home bucket, representative row, compare) and a second launch over the rows it marked (collisions, provisional slots,
+    new keys).  Many uniques, a filter, rows that differ only in the last column."""
+    monkeypatch.setenv("RTB_GB_DEFER_BYTES", "0")
+    rng = np.random.default_rng(41)
+    n = 2_500_003
+    a = rng.integers(0, 3000, n).astype(np.int64) * 1_000_003
+    b = rng.integers(0, 50, n).astype(np.int32)
+    pool = np.array([("%c%c" % (65 + i % 26, 65 + i // 26)).encode() * 6 for i in range(300)], dtype="S12")
+    s12 = pool[rng.integers(0, 300, n)]
+    if cols == "i64_s16_i32":
+        keys = [a, s12.astype("S16"), b]
+    elif cols == "s12":
+        keys = [pool[rng.integers(0, 300, n)].astype("S12")]
+        keys = [np.char.add(keys[0], rng.integers(0, 2000, n).astype("S4")).astype("S12")]
+    elif cols == "i64_i64":
+        keys = [a, rng.integers(0, 40, n).astype(np.int64)]
+    else:
+        keys = [np.char.add(s12, rng.integers(0, 500, n).astype("S6")).astype("S40"), b]
+    filt = rng.random(n) < 0.9
+    for f in (None, filt):
+        ik, ifk, u = rc.MultiKeyGroupBy32(keys, 0, f, 2)
+        eik, eifk, eu = orc.MultiKeyGroupBy32(keys, 0, f, 2)
+        assert u == eu
+        np.testing.assert_array_equal(ik, eik)
+        np.testing.assert_array_equal(ifk, eifk)

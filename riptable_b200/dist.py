@@ -1059,13 +1059,14 @@ class HostFeed:
         self.up, self.down = torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device)
         self.up.wait_stream(cur)
         self.events = []
-        with torch.cuda.stream(self.up):
-            for lo, hi in zip(self.bounds[:-1], self.bounds[1:]):
-                self.key[lo:hi].copy_(kt[lo:hi], non_blocking=True)
-                self.val[lo:hi].copy_(vt[lo:hi], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(self.up)
-                self.events.append((hi, ev))
+        from . import rc as _rc  # pinned arrays are copied asynchronously, pageable ones through the shim's staging ring
+
+        for lo, hi in zip(self.bounds[:-1], self.bounds[1:]):
+            _rc._h2d_chunk(self.key[lo:hi].view(torch.uint8), key_host[lo:hi], self.up)
+            _rc._h2d_chunk(self.val[lo:hi].view(torch.uint8), val_host[lo:hi], self.up)
+            ev = torch.cuda.Event()
+            ev.record(self.up)
+            self.events.append((hi, ev))
         self.h2d_bytes = n * (kt.element_size() + vt.element_size())
 
     def chunks(self, lo, hi):

@@ -96,9 +96,9 @@ def test_sharded_groupby_sum_host_single_rank(group, seed_rows, chunk_rows):
     old = rd.SEED_ROWS
     rd.SEED_ROWS = seed_rows
     try:
-        for vals in (v, v.astype(np.float32), (v * 100).astype(np.int32)):
-            hk = torch.from_numpy(k).pin_memory().numpy()
-            hv = torch.from_numpy(vals).pin_memory().numpy()
+        for pinned, vals in ((True, v), (False, v.astype(np.float32)), (True, (v * 100).astype(np.int32))):
+            hk = torch.from_numpy(k).pin_memory().numpy() if pinned else k  # pageable inputs go through the staging ring
+            hv = torch.from_numpy(vals).pin_memory().numpy() if pinned else vals
             ik, ifk, u, s = rd.sharded_groupby_sum_host(hk, hv, group, chunk_rows=chunk_rows)
             eik, eifk, eu = orc.MultiKeyGroupBy32([k], 0, None, 2)
             exp = orc.GroupByAll32([vals], eik, eu, [0], [1], [eu + 1], 0)[0]

@@ -240,7 +240,8 @@ int rtb_groupby_cumsum(const void* values, int vdtype, const void* ikey, int kdt
  * func = RTB_GB_CUM*.  cumprod: out dtype as cumsum.  cummin / cummax: out dtype = vdtype
  * (riptable/tests/test_groupbyops.py:524-525); the NAN variants skip NaN / integer sentinels (np.fmin.accumulate),
  * the plain ones turn the rest of the group invalid after the first one (np.minimum.accumulate); a row before the
- * group's first valid value gets the invalid.  Workspace: rtb_cumsum_workspace_bytes. */
+ * group's first valid value gets the invalid.  Workspace: rtb_cumsum_workspace_bytes (or rtb_cumop_workspace_bytes for
+ * exactly one call).  cummin / cummax take the sort-free blocked form under the same conditions as cumsum. */
 int rtb_cumop_out_dtype(int func, int vdtype);
 int rtb_groupby_cumop(int func, const void* values, int vdtype, const void* ikey, int kdtype, int64_t nrows,
                       int64_t unique_rows, const uint8_t* filter, const uint8_t* reset_filter, void* out,

@@ -49,7 +49,8 @@ CbPlan cumsum_blocked_plan(int func, int64_t nrows, int64_t unique_rows, bool ha
   const char* e = getenv("RTB_CUMSUM_BLOCKED");
   const int mode = e ? atoi(e) : 1;
   const bool force = mode == 2;
-  if (mode == 0 || func != RTB_GB_CUMSUM || has_reset || nrows < (force ? 1 : kCbMinRows) || unique_rows + 1 > kCbMaxBins) return p;
+  const bool served = func == RTB_GB_CUMSUM || func == RTB_GB_CUMMIN || func == RTB_GB_CUMMAX || func == RTB_GB_CUMNANMIN || func == RTB_GB_CUMNANMAX;
+  if (mode == 0 || !served || has_reset || nrows < (force ? 1 : kCbMinRows) || unique_rows + 1 > kCbMaxBins) return p;
   p.stride = (unique_rows + 1 + 15) & ~15ll;
   const int64_t tiles = (nrows + kCbTile - 1) / kCbTile;
   if (unique_rows + 1 <= kCbWarpMaxBins) {
@@ -80,20 +81,51 @@ CbPlan cumsum_blocked_plan(int func, int64_t nrows, int64_t unique_rows, bool ha
   return p;
 }
 
-template <bool FLOAT>
-__device__ __forceinline__ unsigned long long cb_value(unsigned long long raw, int vdt) {
-  if (FLOAT) return (unsigned long long)__double_as_longlong(raw_to_f64(raw, vdt));
-  return (unsigned long long)raw_to_i64(raw, vdt);
+// OP: what a bin accumulates.  Sums run on int64 / float64 bit patterns; running minima / maxima run on the order-preserving
+// codes of values.cuh, whose two extreme codes are free: one is the identity ("nothing seen yet"), the other absorbs
+// (skipna = 0: a NaN / sentinel poisons the rest of the group), and both come out as the invalid value.
+enum { CB_SUM_I = 0, CB_SUM_F = 1, CB_MIN = 2, CB_MAX = 3 };
+
+template <int OP>
+__device__ __forceinline__ unsigned long long cb_identity() {
+  return OP == CB_SUM_F ? (unsigned long long)__double_as_longlong(0.0) : OP == CB_MIN ? ~0ull : 0ull;
 }
-template <bool FLOAT>
+template <int OP>
+__device__ __forceinline__ unsigned long long cb_poison() {
+  return OP == CB_MIN ? 0ull : ~0ull;
+}
+template <int OP>
+__device__ __forceinline__ unsigned long long cb_value(unsigned long long raw, int vdt, int skipna) {
+  if (OP == CB_SUM_F) return (unsigned long long)__double_as_longlong(raw_to_f64(raw, vdt));
+  if (OP == CB_SUM_I) return (unsigned long long)raw_to_i64(raw, vdt);
+  if (raw_invalid(raw, vdt)) return skipna ? cb_identity<OP>() : cb_poison<OP>();
+  return raw_to_code(raw, vdt, OP == CB_MAX);
+}
+template <int OP>
 __device__ __forceinline__ unsigned long long cb_add(unsigned long long a, unsigned long long b) {
-  if (FLOAT) return (unsigned long long)__double_as_longlong(__longlong_as_double((long long)a) + __longlong_as_double((long long)b));
+  if (OP == CB_SUM_F) return (unsigned long long)__double_as_longlong(__longlong_as_double((long long)a) + __longlong_as_double((long long)b));
+  if (OP == CB_MIN) return a < b ? a : b;
+  if (OP == CB_MAX) return a > b ? a : b;
   return a + b;
+}
+template <int OP>
+__device__ __forceinline__ void cb_atomic(unsigned long long* p, unsigned long long v) {
+  if (OP == CB_SUM_F) atomicAdd((double*)p, __longlong_as_double((long long)v));
+  else if (OP == CB_MIN) atomicMin(p, v);
+  else if (OP == CB_MAX) atomicMax(p, v);
+  else atomicAdd(p, v);
+}
+// the stored form of a running value (bins > 0 only)
+template <int OP>
+__device__ __forceinline__ unsigned long long cb_out(unsigned long long acc, int vdt, int odt) {
+  if (OP == CB_MIN || OP == CB_MAX) return (acc == cb_identity<OP>() || acc == cb_poison<OP>()) ? invalid_raw(odt) : code_to_raw(acc, vdt, OP == CB_MAX);
+  if (odt == RTB_F32) return (unsigned long long)__float_as_uint((float)__longlong_as_double((long long)acc));
+  return acc;
 }
 
 // ---- 1. per-chunk totals ----------------------------------------------------------------------------------------
-template <bool FLOAT>
-__global__ void __launch_bounds__(256) cb_totals_kernel(const void* __restrict__ values, int vdt, const void* __restrict__ ikey, int kdt,
+template <int OP>
+__global__ void __launch_bounds__(256) cb_totals_kernel(const void* __restrict__ values, int vdt, int skipna, const void* __restrict__ ikey, int kdt,
                                                         int64_t n, int64_t unique_rows, const uint8_t* __restrict__ filter,
                                                         int64_t chunk_rows, int64_t stride, unsigned long long* __restrict__ M,
                                                         uint32_t* bad) {
@@ -110,9 +142,8 @@ __global__ void __launch_bounds__(256) cb_totals_kernel(const void* __restrict__
       const int64_t b = load_ikey(ikey, kdt, i);
       if (b < 0 || b > unique_rows) nbad++;
       if (b <= 0 || b > unique_rows || (filter && !filter[i])) continue;
-      const unsigned long long v = cb_value<FLOAT>(load_raw1(values, vsz, i), vdt);
-      if (FLOAT) atomicAdd((double*)&row[b], __longlong_as_double((long long)v));
-      else atomicAdd(&row[b], v);
+      const unsigned long long v = cb_value<OP>(load_raw1(values, vsz, i), vdt, skipna);
+      cb_atomic<OP>(&row[b], v);
     }
   }
   if (nbad) atomicAdd(bad, nbad);  // rows outside [0, unique_rows]: the caller rejects the input, as the packed form does
@@ -122,15 +153,15 @@ __global__ void __launch_bounds__(256) cb_totals_kernel(const void* __restrict__
 // memory instead (rows of the same bin inside a warp are combined first) and adds its part to the chunk's slice once.
 constexpr int kCbSmemBins = 4096;
 constexpr int kCbParts = 8;  // CTAs per chunk
-template <bool FLOAT>
-__global__ void __launch_bounds__(256) cb_totals_smem_kernel(const void* __restrict__ values, int vdt, const void* __restrict__ ikey, int kdt,
+template <int OP>
+__global__ void __launch_bounds__(256) cb_totals_smem_kernel(const void* __restrict__ values, int vdt, int skipna, const void* __restrict__ ikey, int kdt,
                                                              int64_t n, int64_t unique_rows, const uint8_t* __restrict__ filter,
                                                              int64_t chunk_rows, int64_t stride, unsigned long long* __restrict__ M,
                                                              uint32_t* bad) {
   __shared__ unsigned long long acc[kCbSmemBins];
   uint32_t nbad = 0;
   const int nb = (int)unique_rows + 1;
-  const unsigned long long zero = FLOAT ? (unsigned long long)__double_as_longlong(0.0) : 0ull;
+  const unsigned long long zero = cb_identity<OP>();
   for (int b = threadIdx.x; b < nb; b += blockDim.x) acc[b] = zero;
   __syncthreads();
   const int vsz = dsize(vdt);
@@ -149,7 +180,7 @@ __global__ void __launch_bounds__(256) cb_totals_smem_kernel(const void* __restr
       if (bb < 0 || bb > unique_rows) nbad++;
       if (bb > 0 && bb <= unique_rows && (!filter || filter[i])) {
         b = (int)bb;
-        v = cb_value<FLOAT>(load_raw1(values, vsz, i), vdt);
+        v = cb_value<OP>(load_raw1(values, vsz, i), vdt, skipna);
       }
     }
     const uint32_t m = __match_any_sync(0xffffffffu, b);
@@ -159,13 +190,12 @@ __global__ void __launch_bounds__(256) cb_totals_smem_kernel(const void* __restr
       const int src = lower ? (__ffs(lower) - 1) : lane;
       const unsigned long long t = __shfl_sync(0xffffffffu, v, src);
       if (lower) {
-        sum = cb_add<FLOAT>(sum, t);
+        sum = cb_add<OP>(sum, t);
         lower &= lower - 1;
       }
     }
     if (b >= 0 && (m >> lane) == 1u) {  // the last lane of a bin holds the sum of the bin's rows in this warp
-      if (FLOAT) atomicAdd((double*)&acc[b], __longlong_as_double((long long)sum));
-      else atomicAdd(&acc[b], sum);
+      cb_atomic<OP>(&acc[b], sum);
     }
   }
   if (nbad) atomicAdd(bad, nbad);
@@ -174,18 +204,17 @@ __global__ void __launch_bounds__(256) cb_totals_smem_kernel(const void* __restr
   for (int b = threadIdx.x; b < nb; b += blockDim.x) {
     const unsigned long long a = acc[b];
     if (a != zero) {
-      if (FLOAT) atomicAdd((double*)&row[b], __longlong_as_double((long long)a));
-      else atomicAdd(&row[b], a);
+      cb_atomic<OP>(&row[b], a);
     }
   }
 }
 
 // ---- 2. exclusive scan over the chunks, one thread per bin ---------------------------------------------------------
-template <bool FLOAT>
+template <int OP>
 __global__ void __launch_bounds__(256) cb_scan_chunks_kernel(unsigned long long* __restrict__ M, int chunks, int64_t stride, int64_t nbins) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nbins) return;
-  unsigned long long run = FLOAT ? (unsigned long long)__double_as_longlong(0.0) : 0ull;
+  unsigned long long run = cb_identity<OP>();
   unsigned long long* p = M + b;
   int c = 0;
   for (; c + 8 <= chunks; c += 8) {  // the loads of a batch are independent of the running sum
@@ -195,13 +224,13 @@ __global__ void __launch_bounds__(256) cb_scan_chunks_kernel(unsigned long long*
 #pragma unroll
     for (int j = 0; j < 8; j++) {
       p[(int64_t)(c + j) * stride] = run;
-      run = cb_add<FLOAT>(run, t[j]);
+      run = cb_add<OP>(run, t[j]);
     }
   }
   for (; c < chunks; c++) {
     const unsigned long long t = p[(int64_t)c * stride];
     p[(int64_t)c * stride] = run;
-    run = cb_add<FLOAT>(run, t);
+    run = cb_add<OP>(run, t);
   }
 }
 
@@ -220,8 +249,8 @@ __device__ __forceinline__ void cb_st_cg(unsigned long long* p, unsigned long lo
 // 128 at 4 K bins, 32 at 16 K) are compacted in row order into a short list, which one warp walks 32 at a time, ordering
 // rows of the same bin with match.any.  (Taking the whole tile through that ordered walk -- the first version -- cost 32
 // serial steps per tile, 17 us; with few bins, where most rows repeat, the warp-owned form is used instead.)
-template <bool FLOAT>
-__global__ void __launch_bounds__(kCbThreads, 4) cb_rows_kernel(const void* __restrict__ values, int vdt, int odt,
+template <int OP>
+__global__ void __launch_bounds__(kCbThreads, 4) cb_rows_kernel(const void* __restrict__ values, int vdt, int skipna, int odt,
                                                               const void* __restrict__ ikey, int kdt, int64_t n, int64_t unique_rows,
                                                               const uint8_t* __restrict__ filter, int64_t chunk_rows, int64_t stride,
                                                               unsigned long long* __restrict__ M, void* __restrict__ out) {
@@ -238,7 +267,7 @@ __global__ void __launch_bounds__(kCbThreads, 4) cb_rows_kernel(const void* __re
   const int64_t hi = lo + chunk_rows < n ? lo + chunk_rows : n;
   unsigned long long* row = M + (int64_t)blockIdx.x * stride;
   const unsigned long long inv = invalid_raw(odt);
-  const unsigned long long zero = FLOAT ? (unsigned long long)__double_as_longlong(0.0) : 0ull;
+  const unsigned long long zero = cb_identity<OP>();
 
   // the next tile's keys / values / filter bytes are in flight while this tile is resolved
   int64_t nbin[R];
@@ -268,7 +297,7 @@ __global__ void __launch_bounds__(kCbThreads, 4) cb_rows_kernel(const void* __re
     for (int k = 0; k < R; k++) {
       const bool live = nbin[k] > 0 && nbin[k] <= unique_rows;
       bin[k] = live ? (int32_t)nbin[k] : 0;
-      val[k] = (live && nflt[k]) ? cb_value<FLOAT>(nraw[k], vdt) : zero;
+      val[k] = (live && nflt[k]) ? cb_value<OP>(nraw[k], vdt, skipna) : zero;
     }
     if (tlo + kCbTile < hi) fetch(tlo + kCbTile);
 #pragma unroll
@@ -326,7 +355,7 @@ __global__ void __launch_bounds__(kCbThreads, 4) cb_rows_kernel(const void* __re
         lslot[base + before[k]] = slot[k];
         lval[base + before[k]] = val[k];
       } else if (slot[k] >= 0) {  // the bin's only row in this tile
-        res[k] = cb_add<FLOAT>(sval[slot[k]], val[k]);
+        res[k] = cb_add<OP>(sval[slot[k]], val[k]);
         sval[slot[k]] = res[k];
       }
     }
@@ -343,11 +372,11 @@ __global__ void __launch_bounds__(kCbThreads, 4) cb_rows_kernel(const void* __re
           const int src = lower ? (__ffs(lower) - 1) : lane;
           const unsigned long long t = __shfl_sync(0xffffffffu, v, src);
           if (lower) {
-            acc = cb_add<FLOAT>(acc, t);
+            acc = cb_add<OP>(acc, t);
             lower &= lower - 1;
           }
         }
-        acc = cb_add<FLOAT>(acc, v);
+        acc = cb_add<OP>(acc, v);
         if (s_ >= 0) {
           lval[j] = acc;
           if ((m >> lane) == 1u) sval[s_] = acc;  // the last row of the bin in this step
@@ -362,10 +391,7 @@ __global__ void __launch_bounds__(kCbThreads, 4) cb_rows_kernel(const void* __re
       if (rep[k]) res[k] = lval[base + before[k]];
       if (i < hi) {
         unsigned long long o = inv;
-        if (bin[k]) {
-          if (odt == RTB_F32) o = (unsigned long long)__float_as_uint((float)__longlong_as_double((long long)res[k]));
-          else o = res[k];
-        }
+        if (bin[k]) o = cb_out<OP>(res[k], vdt, odt);
         store_raw(out, odt, i, o);
       }
       if (owner[k]) cb_st_cg(&row[bin[k]], sval[slot[k]]);
@@ -376,8 +402,8 @@ __global__ void __launch_bounds__(kCbThreads, 4) cb_rows_kernel(const void* __re
 
 // Few bins: one warp per chunk, 32 rows per step.  Rows of the same bin inside the step are ordered with match.any; the
 // bin's running value lives in M[c][b] (L2), read by every row of the bin and written back by the last one.
-template <bool FLOAT>
-__global__ void __launch_bounds__(256) cb_rows_warp_kernel(const void* __restrict__ values, int vdt, int odt,
+template <int OP>
+__global__ void __launch_bounds__(256) cb_rows_warp_kernel(const void* __restrict__ values, int vdt, int skipna, int odt,
                                                            const void* __restrict__ ikey, int kdt, int64_t n, int64_t unique_rows,
                                                            const uint8_t* __restrict__ filter, int64_t chunk_rows, int64_t stride,
                                                            int chunks, unsigned long long* __restrict__ M, void* __restrict__ out) {
@@ -389,7 +415,7 @@ __global__ void __launch_bounds__(256) cb_rows_warp_kernel(const void* __restric
   const int64_t hi = lo + chunk_rows < n ? lo + chunk_rows : n;
   unsigned long long* row = M + c * stride;
   const unsigned long long inv = invalid_raw(odt);
-  const unsigned long long zero = FLOAT ? (unsigned long long)__double_as_longlong(0.0) : 0ull;
+  const unsigned long long zero = cb_identity<OP>();
   // the next step's key / value / filter are in flight while this step is resolved
   int64_t nb = 0;
   unsigned long long nraw = 0;
@@ -412,7 +438,7 @@ __global__ void __launch_bounds__(256) cb_rows_warp_kernel(const void* __restric
     }
     const bool live = i < hi && b > 0 && b <= unique_rows;
     const int key = live ? (int)b : -1;
-    const unsigned long long v = (live && f) ? cb_value<FLOAT>(raw, vdt) : zero;
+    const unsigned long long v = (live && f) ? cb_value<OP>(raw, vdt, skipna) : zero;
     const uint32_t m = __match_any_sync(0xffffffffu, key);
     unsigned long long acc = live ? cb_ld_cg(&row[b]) : zero;
     uint32_t lower = live ? (m & ((1u << lane) - 1u)) : 0u;
@@ -420,27 +446,31 @@ __global__ void __launch_bounds__(256) cb_rows_warp_kernel(const void* __restric
       const int src = lower ? (__ffs(lower) - 1) : lane;
       const unsigned long long t = __shfl_sync(0xffffffffu, v, src);
       if (lower) {
-        acc = cb_add<FLOAT>(acc, t);
+        acc = cb_add<OP>(acc, t);
         lower &= lower - 1;
       }
     }
-    acc = cb_add<FLOAT>(acc, v);
+    acc = cb_add<OP>(acc, v);
     if (live && (m >> lane) == 1u) cb_st_cg(&row[b], acc);
     if (i < hi) {
       unsigned long long o = inv;
-      if (live) o = odt == RTB_F32 ? (unsigned long long)__float_as_uint((float)__longlong_as_double((long long)acc)) : acc;
+      if (live) o = cb_out<OP>(acc, vdt, odt);
       store_raw(out, odt, i, o);
     }
     __syncwarp();  // the stored running values are ordered before the next step's loads
   }
 }
 
-int cumsum_blocked_run(const CbPlan& p, const void* values, int vdt, int odt, const void* ikey, int kdt, int64_t nrows,
+int cumsum_blocked_run(const CbPlan& p, int func, const void* values, int vdt, int odt, const void* ikey, int kdt, int64_t nrows,
                        int64_t unique_rows, const uint8_t* filter, void* out, void* workspace, cudaStream_t stream) {
   unsigned long long* M = (unsigned long long*)workspace;
   uint32_t* bad = (uint32_t*)((unsigned char*)workspace + p.bytes - 16);  // the plan's bytes end with a 16-byte counter slot
   const bool fl = vdt == RTB_F32 || vdt == RTB_F64;
-  RTB_CUDA(cudaMemsetAsync(M, 0, p.bytes, stream));
+  const bool ismin = func == RTB_GB_CUMMIN || func == RTB_GB_CUMNANMIN, ismax = func == RTB_GB_CUMMAX || func == RTB_GB_CUMNANMAX;
+  const int skipna = func == RTB_GB_CUMNANMIN || func == RTB_GB_CUMNANMAX;
+  // the accumulators start at the operation's identity: all-ones bytes for a running minimum, zero bytes otherwise
+  RTB_CUDA(cudaMemsetAsync(M, ismin ? 0xFF : 0, p.bytes - 16, stream));
+  RTB_CUDA(cudaMemsetAsync(bad, 0, 16, stream));
   const int64_t ntiles = (nrows + kCbTile - 1) / kCbTile;
   const int g1 = (int)(ntiles < (int64_t)kSMs * 8 ? ntiles : (int64_t)kSMs * 8);
   const int g2 = (int)((unique_rows + 1 + 255) / 256);
@@ -451,20 +481,22 @@ int cumsum_blocked_run(const CbPlan& p, const void* values, int vdt, int odt, co
   const int gw = (p.chunks + 7) / 8;
 #define RTB_CB_RUN(FL_)                                                                                                              \
   do {                                                                                                                               \
-    if (few) cb_totals_smem_kernel<FL_><<<gs, 256, 0, stream>>>(values, vdt, ikey, kdt, nrows, unique_rows, filter, p.chunk_rows, p.stride, M, bad); \
-    else cb_totals_kernel<FL_><<<g1, 256, 0, stream>>>(values, vdt, ikey, kdt, nrows, unique_rows, filter, p.chunk_rows, p.stride, M, bad); \
+    if (few) cb_totals_smem_kernel<FL_><<<gs, 256, 0, stream>>>(values, vdt, skipna, ikey, kdt, nrows, unique_rows, filter, p.chunk_rows, p.stride, M, bad); \
+    else cb_totals_kernel<FL_><<<g1, 256, 0, stream>>>(values, vdt, skipna, ikey, kdt, nrows, unique_rows, filter, p.chunk_rows, p.stride, M, bad); \
     RTB_LAUNCH_CHECK();                                                                                                              \
     cb_scan_chunks_kernel<FL_><<<g2, 256, 0, stream>>>(M, p.chunks, p.stride, unique_rows + 1);                                       \
     RTB_LAUNCH_CHECK();                                                                                                              \
     if (p.warp_chunks)                                                                                                               \
-      cb_rows_warp_kernel<FL_><<<gw, 256, 0, stream>>>(values, vdt, odt, ikey, kdt, nrows, unique_rows, filter, p.chunk_rows, p.stride, \
+      cb_rows_warp_kernel<FL_><<<gw, 256, 0, stream>>>(values, vdt, skipna, odt, ikey, kdt, nrows, unique_rows, filter, p.chunk_rows, p.stride, \
                                                       p.chunks, M, out);                                                             \
     else                                                                                                                             \
-      cb_rows_kernel<FL_><<<p.chunks, kCbThreads, 0, stream>>>(values, vdt, odt, ikey, kdt, nrows, unique_rows, filter, p.chunk_rows, \
+      cb_rows_kernel<FL_><<<p.chunks, kCbThreads, 0, stream>>>(values, vdt, skipna, odt, ikey, kdt, nrows, unique_rows, filter, p.chunk_rows, \
                                                               p.stride, M, out);                                                     \
   } while (0)
-  if (fl) RTB_CB_RUN(true);
-  else RTB_CB_RUN(false);
+  if (ismin) RTB_CB_RUN(CB_MIN);
+  else if (ismax) RTB_CB_RUN(CB_MAX);
+  else if (fl) RTB_CB_RUN(CB_SUM_F);
+  else RTB_CB_RUN(CB_SUM_I);
 #undef RTB_CB_RUN
   RTB_LAUNCH_CHECK();
   uint32_t hbad = 0;

@@ -1,4 +1,4 @@
-// Sort-free GB_CUMSUM for groupings of up to a few million bins (cumsum_blocked.cu).
+// Sort-free GB_CUMSUM / GB_CUM[NAN]MIN / GB_CUM[NAN]MAX for groupings of up to 16 Ki bins (cumsum_blocked.cu).
 #pragma once
 #include "common.cuh"
 
@@ -16,7 +16,7 @@ struct CbPlan {
 // Whether rtb_groupby_cumop(func, ...) over nrows rows and unique_rows bins takes the blocked form, and its geometry.
 CbPlan cumsum_blocked_plan(int func, int64_t nrows, int64_t unique_rows, bool has_reset);
 
-int cumsum_blocked_run(const CbPlan& p, const void* values, int vdt, int odt, const void* ikey, int kdt, int64_t nrows,
+int cumsum_blocked_run(const CbPlan& p, int func, const void* values, int vdt, int odt, const void* ikey, int kdt, int64_t nrows,
                        int64_t unique_rows, const uint8_t* filter, void* out, void* workspace, cudaStream_t stream);
 
 }  // namespace rtb

@@ -889,7 +889,7 @@ extern "C" int rtb_groupby_cumop(int func, const void* values, int vdt, const vo
   const CbPlan bp = cumsum_blocked_plan(func, nrows, unique_rows, reset_filter != nullptr);
   if (bp.ok && workspace && bp.bytes <= workspace_bytes && ((uintptr_t)workspace % 16) == 0) {
     prof_begin(PROF_SEGSCAN, stream);
-    int brc = cumsum_blocked_run(bp, values, vdt, odt, ikey, kdt, nrows, unique_rows, filter, out, workspace, stream);
+    int brc = cumsum_blocked_run(bp, func, values, vdt, odt, ikey, kdt, nrows, unique_rows, filter, out, workspace, stream);
     if (brc != RTB_OK) return brc;
     prof_end(PROF_SEGSCAN, stream, (uint64_t)nrows);
     return RTB_OK;

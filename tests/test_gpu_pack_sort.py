@@ -261,6 +261,36 @@ def test_cum_min_max(rc, vdt, nb, bad_frac):
             np.testing.assert_array_equal(got, exp)
 
 
+@pytest.mark.parametrize("vdt", _ALL_NUM)
+@pytest.mark.parametrize("nb,bad_frac", [(1, 0.0), (40, 0.02), (3500, 0.3), (16_000, 0.05), (40, 1.0)])
+def test_cum_min_max_blocked(rc, blocked_cumsum, vdt, nb, bad_frac):
+    """Running minima / maxima on the sort-free blocked form (csrc/cumsum_blocked.cu): the order-preserving codes with
+    "nothing yet" as the identity and "poisoned" as the absorbing extreme; skipna and plain variants, every dtype,
+    chunk-per-warp and chunk-per-CTA bin counts, a group that is invalid throughout."""
+    rng = np.random.default_rng(nb * 7 + int(bad_frac * 100) + 1)
+    n = 200_003
+    ikey = rng.integers(0, nb + 1, n).astype(np.int32)
+    dt = np.dtype(vdt)
+    if dt.kind == "f":
+        v = rng.normal(0, 1e4, n).astype(vdt)
+        v[rng.random(n) < bad_frac / 2] = np.inf
+        v[rng.random(n) < bad_frac / 2] = -np.inf
+    elif dt.kind == "b":
+        v = rng.integers(0, 2, n).astype(vdt)
+    else:
+        info = np.iinfo(dt)
+        v = rng.integers(info.min, info.max, n, dtype=dt, endpoint=True)
+    if dt.kind != "b":
+        v[rng.random(n) < bad_frac] = orc.invalid_for(dt)
+    filt = rng.random(n) < 0.7
+    for func in (306, 307, 308, 309):
+        for fp in [(0.0, None, None, None), (0.0, None, filt, None)]:
+            got = rc.EmaAll32([v], ikey, nb, func, fp)[0]
+            exp = orc.EmaAll32([v], ikey, nb, func, fp)[0]
+            assert got.dtype == exp.dtype == dt
+            np.testing.assert_array_equal(got, exp)
+
+
 @pytest.mark.parametrize("vdt", [np.bool_, np.int8, np.int32, np.int64, np.uint64, np.float32, np.float64])
 @pytest.mark.parametrize("nb", [1, 40, 25_000])
 def test_cumprod(rc, vdt, nb):

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 import torch
 import riptable_b200.rc as rc
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 125_000_000
-u = 1_000_000
+u = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
 g = torch.Generator(device="cuda"); g.manual_seed(7)
 pool = torch.randint(-2**62, 2**62, (u,), device="cuda", generator=g, dtype=torch.int64)
 key = pool[torch.randint(0, u, (n,), device="cuda", generator=g)]

@@ -1632,6 +1632,9 @@ struct GbPlan {
   double big_table_bytes = 8.0 * 1024 * 1024 * 1024;  // above this table size every round uses the slot-wise kernel
   int64_t finish_rows = 256ll << 20;  // a settled table finishes a remainder of at most this many rows in one round
   int snapshot = 1;                   // 16- / 32-byte packed rows: inline-key snapshot table for the settled rounds
+  uint32_t window_slots = 1u << 22;   // the 64 MB table window (see the resize rule)
+  double window_load = 0.55;          // ... which a table keeps up to this load
+  double dense_load = 0.5;            // target load of a single-key table that has to leave the window
   int defer_packed = 1;               // packed rows over a table beyond defer_table_bytes: fast path and general path in separate launches
   double defer_table_bytes = 128.0 * 1024 * 1024;
   double snap_fill = 2.0;             // snapshot entries per key (power of two above it)
@@ -1641,6 +1644,8 @@ static GbPlan get_plan() {
   GbPlan p;
   if (const char* e = getenv("RTB_GB_SNAPSHOT")) p.snapshot = atoi(e);
   if (const char* e = getenv("RTB_GB_SNAPFILL")) p.snap_fill = atof(e);
+  if (const char* e = getenv("RTB_GB_WINDOW_LOAD")) p.window_load = atof(e);
+  if (const char* e = getenv("RTB_GB_DENSE_LOAD")) p.dense_load = atof(e);
   if (const char* e = getenv("RTB_GB_DEFER")) p.defer_packed = atoi(e);
   if (const char* e = getenv("RTB_GB_DEFER_BYTES")) p.defer_table_bytes = atof(e);
   if (const char* e = getenv("RTB_GB_FINISH")) p.finish_rows = atoll(e);
@@ -2093,6 +2098,18 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
     if (proj > (double)rows) proj = (double)rows;
     if (proj > (double)(max_unique - U)) proj = (double)(max_unique - U);
     uint32_t ideal = next_pow2_u64((uint64_t)ceil(((double)U + proj) / plan.load_target));
+    // 4 Mi slots (64 MB) is the largest table whose random probes still run at the L2 rate (beyond it every probe also
+    // misses the translation caches: 2 M keys probe at 65 G rows/s in 128 MB and at 87 G rows/s in 64 MB at twice the
+    // load), so a single-key table stays there while its load allows
+    // ... and beyond it the smaller of two tables wins again (3 M keys: 48 G rows/s in 256 MB at 19 % load), so a table
+    // outside the window is sized for twice the usual load
+    if (direct && ideal > plan.window_slots) {
+      if ((double)U + proj <= (double)plan.window_slots * plan.window_load) ideal = plan.window_slots;
+      else if (ideal <= (1u << 25)) {  // (no gain measured above 512 MB: 10 M keys probe at 22 G rows/s either way)
+        const uint32_t dense = next_pow2_u64((uint64_t)ceil(((double)U + proj) / plan.dense_load));
+        if (dense >= plan.window_slots && dense < ideal) ideal = dense;
+      }
+    }
     if (ideal < 1024) ideal = 1024;
     if (ideal > capmax) ideal = capmax;
     // Resizing re-stages every entry, so keep the table while it still fits: grow only when the projection would

@@ -795,3 +795,17 @@ def test_packed_rows_deferred_general_path(rc, monkeypatch, cols):
         assert u == eu
         np.testing.assert_array_equal(ik, eik)
         np.testing.assert_array_equal(ifk, eifk)
+
+
+@pytest.mark.parametrize("uniques", [2_200_000, 3_500_000])
+def test_table_window_sizing(rc, uniques):
+    """Unique counts whose 25 %-load table would leave the 64 MB window: the table stays at 4 Mi slots (2.2 M keys, 52 % load)
+    or is sized for 50 % load beyond it (3.5 M keys, 8 Mi slots) -- same bins, first rows and count as the oracle."""
+    rng = np.random.default_rng(uniques)
+    n = 14_000_000
+    key = rng.integers(0, uniques, n).astype(np.int64) * 104_729
+    ik, ifk, u = rc.MultiKeyGroupBy32([key], 0, None, 2)
+    eik, eifk, eu = orc.MultiKeyGroupBy32([key], 0, None, 2)
+    assert u == eu
+    np.testing.assert_array_equal(ik, eik)
+    np.testing.assert_array_equal(ifk, eifk)

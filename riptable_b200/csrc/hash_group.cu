@@ -1248,27 +1248,44 @@ __global__ void __launch_bounds__(256) gb_reinsert_packed(const uint8_t* __restr
 }
 
 // ---- per-round finalisation --------------------------------------------------------------------
+// First rows of the round's new keys -> bitmap.  The row (relative to the round) is also kept next to the key's list entry,
+// so that gb_assign_bins does not fetch the slot a second time (with a table in DRAM every such fetch is a DRAM-class access).
 __global__ void __launch_bounds__(256) gb_mark_firstrows(const Slot* table, const uint32_t* newlist,
-                                                         const GbCounters* ctr, int64_t lo, uint32_t* bitmap) {
+                                                         const GbCounters* ctr, int64_t lo, uint32_t* bitmap, uint32_t* minrows) {
   uint32_t n = ctr->newcount;
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     uint32_t m = table[newlist[j]].minrow - (uint32_t)lo;
+    minrows[j] = m;
     atomicOr(&bitmap[m >> 5], 1u << (m & 31));
   }
 }
 
 __global__ void __launch_bounds__(256) gb_assign_bins(Slot* table, const uint32_t* newlist, const GbCounters* ctr,
-                                                      int64_t lo, const uint32_t* bitmap, const uint32_t* prefix,
-                                                      uint32_t ubase, int32_t* ifirstkey, int64_t ifirst_sub) {
+                                                      const uint32_t* bitmap, const uint32_t* prefix, uint32_t ubase,
+                                                      const uint32_t* minrows) {
   uint32_t n = ctr->newcount;
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-    uint32_t sidx = newlist[j];
-    uint32_t row = table[sidx].minrow;
-    uint32_t m = row - (uint32_t)lo;
+    uint32_t m = minrows[j];
     uint32_t rank = prefix[m >> 5] + __popc(bitmap[m >> 5] & ((1u << (m & 31)) - 1u));
-    uint32_t bin = ubase + rank + 1;
-    table[sidx].nbin = ~bin;
-    ifirstkey[bin - 1] = (int32_t)((int64_t)row - ifirst_sub);
+    table[newlist[j]].nbin = ~(ubase + rank + 1);
+  }
+}
+
+// iFirstKey of the round's new bins, read off the bitmap in row order: the k-th set bit is bin ubase + k + 1.  Streaming
+// (a thread per bitmap word writes its word's run of entries), where gb_assign_bins used to scatter one entry per new key.
+__global__ void __launch_bounds__(256) gb_firstkeys_from_bitmap(const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix,
+                                                                int64_t words, int64_t lo, uint32_t ubase, int32_t* __restrict__ ifirstkey,
+                                                                int64_t ifirst_sub) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += stride) {
+    uint32_t bits = bitmap[w];
+    if (!bits) continue;
+    uint32_t at = ubase + prefix[w];
+    const int64_t row0 = lo + (w << 5) - ifirst_sub;
+    while (bits) {
+      ifirstkey[at++] = (int32_t)(row0 + (__ffs(bits) - 1));
+      bits &= bits - 1;
+    }
   }
 }
 
@@ -2391,12 +2408,15 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
       int64_t words = (rows + 31) / 32;
       RTB_ARG(words <= L.bitmap_words, "MultiKeyGroupBy32: internal error, a round of %lld rows exceeds the first-row bitmap", (long long)rows);
       RTB_CUDA(cudaMemsetAsync(L.bitmap, 0, sizeof(uint32_t) * words, stream));
-      gb_mark_firstrows<<<grid_for(prev_new, 256, 1), 256, 0, stream>>>(L.table, newlist, L.ctr, lo, L.bitmap);
+      uint32_t* minrows = newlist + ((size_t)max_unique + 1);  // the list uses at most max_unique of the staging area's 4 (max_unique + 1) words
+      gb_mark_firstrows<<<grid_for(prev_new, 256, 1), 256, 0, stream>>>(L.table, newlist, L.ctr, lo, L.bitmap, minrows);
       RTB_LAUNCH_CHECK();
       int rc = exclusive_scan_u32(L.bitmap, L.prefix, words, SCAN_POPC, L.scan_scratch, nullptr, stream);
       if (rc != RTB_OK) return rc;
-      gb_assign_bins<<<grid_for(prev_new, 256, 1), 256, 0, stream>>>(L.table, newlist, L.ctr, lo, L.bitmap, L.prefix,
-                                                                    (uint32_t)U, ifirstkey_out, -row_offset);
+      gb_assign_bins<<<grid_for(prev_new, 256, 1), 256, 0, stream>>>(L.table, newlist, L.ctr, L.bitmap, L.prefix, (uint32_t)U, minrows);
+      RTB_LAUNCH_CHECK();
+      gb_firstkeys_from_bitmap<<<grid_for(words, 256, 1), 256, 0, stream>>>(L.bitmap, L.prefix, words, lo, (uint32_t)U, ifirstkey_out,
+                                                                           -row_offset);
       RTB_LAUNCH_CHECK();
       gb_fixup<<<grid_for(rows, 256, 4), 256, 0, stream>>>(ikey_out, L.table, lo, hi, 0, fused_round ? *fuse : fz_none);
       RTB_LAUNCH_CHECK();

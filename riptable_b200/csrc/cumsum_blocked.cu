@@ -234,6 +234,31 @@ __global__ void __launch_bounds__(256) cb_scan_chunks_kernel(unsigned long long*
   }
 }
 
+// Few bins, thousands of chunks (the warp-owned form): a warp per bin, 32 chunks per step, instead of one thread walking
+// 9 472 chunks.
+template <int OP>
+__global__ void __launch_bounds__(256) cb_scan_chunks_warp_kernel(unsigned long long* __restrict__ M, int chunks, int64_t stride, int64_t nbins) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= nbins) return;
+  unsigned long long run = cb_identity<OP>();
+  unsigned long long* p = M + b;
+  for (int c0 = 0; c0 < chunks; c0 += 32) {
+    const int c = c0 + lane;
+    const unsigned long long t = c < chunks ? p[(int64_t)c * stride] : cb_identity<OP>();
+    unsigned long long inc = t;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long u = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc = cb_add<OP>(u, inc);
+    }
+    unsigned long long ex = __shfl_up_sync(0xffffffffu, inc, 1);
+    ex = lane ? cb_add<OP>(run, ex) : run;
+    if (c < chunks) p[(int64_t)c * stride] = ex;
+    run = cb_add<OP>(run, __shfl_sync(0xffffffffu, inc, 31));
+  }
+}
+
 // ---- 3. the rows of a chunk, in order --------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long cb_ld_cg(const unsigned long long* p) {
   unsigned long long v;
@@ -484,7 +509,10 @@ int cumsum_blocked_run(const CbPlan& p, int func, const void* values, int vdt, i
     if (few) cb_totals_smem_kernel<FL_><<<gs, 256, 0, stream>>>(values, vdt, skipna, ikey, kdt, nrows, unique_rows, filter, p.chunk_rows, p.stride, M, bad); \
     else cb_totals_kernel<FL_><<<g1, 256, 0, stream>>>(values, vdt, skipna, ikey, kdt, nrows, unique_rows, filter, p.chunk_rows, p.stride, M, bad); \
     RTB_LAUNCH_CHECK();                                                                                                              \
-    cb_scan_chunks_kernel<FL_><<<g2, 256, 0, stream>>>(M, p.chunks, p.stride, unique_rows + 1);                                       \
+    if (p.warp_chunks && unique_rows + 1 <= 4096)                                                                                    \
+      cb_scan_chunks_warp_kernel<FL_><<<(int)((unique_rows + 1 + 7) / 8), 256, 0, stream>>>(M, p.chunks, p.stride, unique_rows + 1); \
+    else                                                                                                                             \
+      cb_scan_chunks_kernel<FL_><<<g2, 256, 0, stream>>>(M, p.chunks, p.stride, unique_rows + 1);                                     \
     RTB_LAUNCH_CHECK();                                                                                                              \
     if (p.warp_chunks)                                                                                                               \
       cb_rows_warp_kernel<FL_><<<gw, 256, 0, stream>>>(values, vdt, skipna, odt, ikey, kdt, nrows, unique_rows, filter, p.chunk_rows, p.stride, \

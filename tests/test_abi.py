@@ -37,3 +37,16 @@ def test_out_dtype_table_matches_contract():
     assert f(1, RTB_I8) == RTB_F64 and f(55, RTB_F32) == RTB_F64
     assert f(2, RTB_I8) == RTB_I8 and f(53, RTB_F32) == RTB_F32
     assert f(0, RTB_BYTES) < 0 and f(100, RTB_I8) < 0
+
+
+def test_every_exported_entry_point_is_declared():
+    """The reverse direction: nothing is exported under the rtb_ prefix that include/riptable_b200.h does not declare
+    (one debugging aid excepted), so the header is the whole boundary."""
+    import subprocess
+    import riptable_b200.build as b
+
+    b.build()
+    out = subprocess.run(["nm", "-D", "--defined-only", b.LIB], capture_output=True, text=True, check=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if line.split() and line.split()[-1].startswith("rtb_")}
+    undeclared = exported - set(_declared()) - {"rtb_debug_sort_codes"}
+    assert not undeclared, sorted(undeclared)

@@ -1652,6 +1652,7 @@ struct GbPlan {
   uint32_t window_slots = 1u << 22;   // the 64 MB table window (see the resize rule)
   double window_load = 0.55;          // ... which a table keeps up to this load
   double dense_load = 0.5;            // target load of a single-key table that has to leave the window
+  int window_packed = 0;              // the same two rules for packed-row (multi-key) tables
   int defer_packed = 1;               // packed rows over a table beyond defer_table_bytes: fast path and general path in separate launches
   double defer_table_bytes = 128.0 * 1024 * 1024;
   double snap_fill = 2.0;             // snapshot entries per key (power of two above it)
@@ -1663,6 +1664,7 @@ static GbPlan get_plan() {
   if (const char* e = getenv("RTB_GB_SNAPFILL")) p.snap_fill = atof(e);
   if (const char* e = getenv("RTB_GB_WINDOW_LOAD")) p.window_load = atof(e);
   if (const char* e = getenv("RTB_GB_DENSE_LOAD")) p.dense_load = atof(e);
+  if (const char* e = getenv("RTB_GB_WINDOW_PACKED")) p.window_packed = atoi(e);
   if (const char* e = getenv("RTB_GB_DEFER")) p.defer_packed = atoi(e);
   if (const char* e = getenv("RTB_GB_DEFER_BYTES")) p.defer_table_bytes = atof(e);
   if (const char* e = getenv("RTB_GB_FINISH")) p.finish_rows = atoll(e);
@@ -2120,7 +2122,7 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
     // load), so a single-key table stays there while its load allows
     // ... and beyond it the smaller of two tables wins again (3 M keys: 48 G rows/s in 256 MB at 19 % load), so a table
     // outside the window is sized for twice the usual load
-    if (direct && ideal > plan.window_slots) {
+    if ((direct || plan.window_packed) && ideal > plan.window_slots) {
       if ((double)U + proj <= (double)plan.window_slots * plan.window_load) ideal = plan.window_slots;
       else if (ideal <= (1u << 25)) {  // (no gain measured above 512 MB: 10 M keys probe at 22 G rows/s either way)
         const uint32_t dense = next_pow2_u64((uint64_t)ceil(((double)U + proj) / plan.dense_load));

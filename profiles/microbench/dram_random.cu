@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33; return x;
@@ -105,7 +106,18 @@ static void launch_bits(void* c_) {
   bits<<<148 * 8, 256>>>((uint32_t*)c->table, c->mask, c->n);
 }
 
-int main() {
+int main(int argc, char** argv) {
+  // optional argument: the L2 fetch granularity hint in bytes (cudaLimitMaxL2FetchGranularity: 32, 64 or 128)
+  if (argc > 1) {
+    cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(argv[1]));
+    size_t got = 0;
+    cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+    printf("cudaLimitMaxL2FetchGranularity: asked %s, set -> %s, now %zu\n", argv[1], cudaGetErrorString(e), got);
+  } else {
+    size_t got = 0;
+    cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+    printf("cudaLimitMaxL2FetchGranularity (default): %zu\n", got);
+  }
   const int64_t n = 1ll << 29;
   void* table; cudaMalloc(&table, (size_t)16 << 30); cudaMemset(table, 0, (size_t)16 << 30);
   unsigned long long* in; cudaMalloc(&in, (size_t)8 * n); cudaMemset(in, 1, (size_t)8 * n);

@@ -2117,9 +2117,9 @@ static int gb_core(const rtb_column* keys, int nkeys, int64_t nrows, const uint8
     if (proj > (double)rows) proj = (double)rows;
     if (proj > (double)(max_unique - U)) proj = (double)(max_unique - U);
     uint32_t ideal = next_pow2_u64((uint64_t)ceil(((double)U + proj) / plan.load_target));
-    // 4 Mi slots (64 MB) is the largest table whose random probes still run at the L2 rate (beyond it every probe also
-    // misses the translation caches: 2 M keys probe at 65 G rows/s in 128 MB and at 87 G rows/s in 64 MB at twice the
-    // load), so a single-key table stays there while its load allows
+    // 4 Mi slots (64 MB) is the largest table whose random probes still run at the L2 rate (a table probed from both dies
+    // can count on about half of the nominal L2: 2 M keys probe at 65 G rows/s in 128 MB and at 87 G rows/s in 64 MB at
+    // twice the load), so a single-key table stays there while its load allows
     // ... and beyond it the smaller of two tables wins again (3 M keys: 48 G rows/s in 256 MB at 19 % load), so a table
     // outside the window is sized for twice the usual load
     if ((direct || plan.window_packed) && ideal > plan.window_slots) {

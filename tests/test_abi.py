@@ -50,3 +50,23 @@ def test_every_exported_entry_point_is_declared():
     exported = {line.split()[-1] for line in out.splitlines() if line.split() and line.split()[-1].startswith("rtb_")}
     undeclared = exported - set(_declared()) - {"rtb_debug_sort_codes"}
     assert not undeclared, sorted(undeclared)
+
+
+def test_cumop_workspace_query_follows_the_form_a_call_takes():
+    """Host arithmetic only (no device): GB_CUMSUM / GB_CUM[NAN]MIN / MAX without a reset filter, from 4 Mi rows and up to
+    16 Ki bins, take the sort-free blocked form, whose workspace is the chunk matrix; everything else the packed layout,
+    which grows with the row count.  rtb_cumsum_workspace_bytes covers either."""
+    from riptable_b200 import _lib
+
+    q = _lib.lib.rtb_cumop_workspace_bytes
+    n = 64 << 20
+    packed = q(302, n, 1000, 0)  # cumprod: always the packed layout
+    assert packed > 20 * n
+    for func in (300, 306, 307, 308, 309):
+        blocked = q(func, n, 1000, 0)
+        assert blocked < packed // 8, func
+        assert q(func, n, 1000, 1) == packed          # a reset filter
+        assert q(func, n, 1_000_000, 0) == packed     # too many bins
+        assert q(func, 1 << 20, 1000, 0) == q(302, 1 << 20, 1000, 0)  # too few rows
+    assert q(300, n, 16_383, 0) < packed and q(300, n, 16_384, 0) == packed
+    assert _lib.lib.rtb_cumsum_workspace_bytes(n, 1000) >= packed
